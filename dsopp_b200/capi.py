@@ -1,0 +1,322 @@
+"""ctypes binding of the C ABI in include/dsopp_cuda_pba.h (test / bench plumbing).
+
+The product path is the CUDA library: if it is missing or no GPU is present this module raises --
+there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB_PATH = os.path.join(HERE, "lib", "libdsopp_pba_cuda.so")
+HOST_LIB_PATH = os.path.join(HERE, "lib", "libdsopp_pba_host.so")
+
+MAX_FRAMES = 16
+BLOCK = 8
+
+
+class DpbaError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("max_frames", C.c_int32),
+        ("max_points_per_frame", C.c_int32),
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("device", C.c_int32),
+        ("rank", C.c_int32),
+        ("world_size", C.c_int32),
+    ]
+
+
+class ResidualView(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("residuals", C.c_void_p),
+        ("d_reference_state_eps", C.c_void_p),
+        ("d_target_state_eps", C.c_void_p),
+        ("d_idepth", C.c_void_p),
+        ("huber_weight", C.c_void_p),
+        ("energy", C.c_void_p),
+        ("connection_status", C.c_void_p),
+        ("connection_status_candidate", C.c_void_p),
+    ]
+
+
+_P = C.c_void_p
+_I = C.c_int32
+_D = C.c_double
+
+# name -> (restype, argtypes); exactly the symbols declared in include/dsopp_cuda_pba.h
+SIGNATURES = {
+    "dpba_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    "dpba_destroy": (C.c_int, [_P]),
+    "dpba_last_error": (C.c_char_p, [_P]),
+    "dpba_version": (C.c_char_p, []),
+    "dpba_stream": (_P, [_P]),
+    "dpba_push_frame": (C.c_int, [_P, _I, _P, _P, _P, _D, _P, _P, _I]),
+    "dpba_push_frame_intensity": (C.c_int, [_P, _I, _P, _P, _P, _D, _P, _P, _I]),
+    "dpba_remove_frame": (C.c_int, [_P, _I]),
+    "dpba_num_frames": (C.c_int, [_P]),
+    "dpba_set_frame_linearization": (C.c_int, [_P, _I, _P, _P]),
+    "dpba_set_frame_flags": (C.c_int, [_P, _I, _I, _I]),
+    "dpba_set_landmarks": (C.c_int, [_P, _I, _I, _P, _P, _P, _P]),
+    "dpba_append_landmarks": (C.c_int, [_P, _I, _I, _P, _P, _P, _P]),
+    "dpba_set_landmark_flags": (C.c_int, [_P, _I, _I, _P]),
+    "dpba_num_landmarks": (C.c_int, [_P, _I]),
+    "dpba_get_landmarks": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "dpba_get_pose_idepth_blocks": (C.c_int, [_P, _I, _I, _P]),
+    "dpba_set_statuses": (C.c_int, [_P, _I, _I, _I, _P]),
+    "dpba_get_statuses": (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    "dpba_set_state": (C.c_int, [_P, _P, _P]),
+    "dpba_get_state": (C.c_int, [_P, _P, _P]),
+    "dpba_first_estimate": (C.c_int, [_P]),
+    "dpba_evaluate": (C.c_int, [_P, _D, _I, _I, C.POINTER(_D), C.POINTER(_I)]),
+    "dpba_evaluate_jacobians": (C.c_int, [_P, _D, _I, _I]),
+    "dpba_download_residual_block": (C.c_int, [_P, _I, _I, C.POINTER(ResidualView)]),
+    "dpba_linearize": (C.c_int, [_P, _D, _I, _I, _I, _P, _P, _P, _P]),
+    "dpba_linearize_materialized": (C.c_int, [_P, _D, _I, _I, _I, _P, _P, _P, _P]),
+    "dpba_back_substitute": (C.c_int, [_P, _P, _D]),
+    "dpba_accept": (C.c_int, [_P, C.POINTER(_D), C.POINTER(_D)]),
+    "dpba_reject": (C.c_int, [_P]),
+    "dpba_change_residual_statuses": (C.c_int, [_P, _I]),
+    "dpba_landmarks_energy": (C.c_int, [_P, _I, C.POINTER(_D), C.POINTER(_I)]),
+    "dpba_update_point_statuses": (C.c_int, [_P, _I, _D, C.POINTER(_D)]),
+    "dpba_comm_unique_id": (C.c_int, [_P]),
+    "dpba_comm_init": (C.c_int, [_P, _P, _I, _I]),
+}
+
+_lib = None
+
+
+def load_library(path: str = CUDA_LIB_PATH):
+    """dlopen the CUDA library and bind every declared entry point; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise DpbaError(f"{path} is not built: run `python -m dsopp_b200.build` (no CPU fallback exists)")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _u8(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def pose34(T):
+    """4x4 (or 3x4) pose -> 12 doubles, 3x4 row-major."""
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float64)[:3, :4]).reshape(12)
+
+
+class Handle:
+    """Thin RAII wrapper: one dpba_handle.  Method names follow the C entry points."""
+
+    def __init__(self, max_frames, max_points_per_frame, width, height, device=0, rank=0, world_size=1):
+        self.lib = load_library()
+        self.cfg = Config(max_frames, max_points_per_frame, width, height, device, rank, world_size)
+        self.h = C.c_void_p()
+        rc = self.lib.dpba_create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            raise DpbaError(f"dpba_create failed with {rc} (is a CUDA device visible? there is no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.dpba_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise DpbaError(f"dpba error {rc}: {self.lib.dpba_last_error(self.h).decode()}")
+        return rc
+
+    @property
+    def n_frames(self):
+        return self.lib.dpba_num_frames(self.h)
+
+    @property
+    def stream(self):
+        return self.lib.dpba_stream(self.h)
+
+    def push_frame(self, frame_id, image, mask, T_w_lin, exposure, ab0, intr, fixed):
+        image = _f32(image)
+        mask = _u8(mask)
+        T, ab, it = pose34(T_w_lin), _f64(ab0), _f64(intr)
+        if image.ndim == 3:
+            return self._ck(self.lib.dpba_push_frame(self.h, frame_id, _ptr(image), _ptr(mask), _ptr(T), exposure,
+                                                     _ptr(ab), _ptr(it), int(fixed)))
+        return self._ck(self.lib.dpba_push_frame_intensity(self.h, frame_id, _ptr(image), _ptr(mask), _ptr(T),
+                                                           exposure, _ptr(ab), _ptr(it), int(fixed)))
+
+    def remove_frame(self, slot):
+        self._ck(self.lib.dpba_remove_frame(self.h, slot))
+
+    def set_frame_linearization(self, slot, T_w_lin, ab0):
+        T, ab = pose34(T_w_lin), _f64(ab0)
+        self._ck(self.lib.dpba_set_frame_linearization(self.h, slot, _ptr(T), _ptr(ab)))
+
+    def set_frame_flags(self, slot, fixed, to_marginalize):
+        self._ck(self.lib.dpba_set_frame_flags(self.h, slot, int(fixed), int(to_marginalize)))
+
+    def set_landmarks(self, slot, uv, idepth, patch, flags=None, append=False):
+        uv, idepth, patch, flags = _f32(uv), _f32(idepth), _f32(patch), _u8(flags)
+        fn = self.lib.dpba_append_landmarks if append else self.lib.dpba_set_landmarks
+        self._ck(fn(self.h, slot, len(idepth), _ptr(uv), _ptr(idepth), _ptr(patch), _ptr(flags)))
+
+    def set_landmark_flags(self, slot, flags):
+        flags = _u8(flags)
+        self._ck(self.lib.dpba_set_landmark_flags(self.h, slot, len(flags), _ptr(flags)))
+
+    def num_landmarks(self, slot):
+        return self._ck(self.lib.dpba_num_landmarks(self.h, slot))
+
+    def get_landmarks(self, slot):
+        n = self.num_landmarks(slot)
+        out = dict(
+            idepth=np.zeros(n, np.float32), idepth_step=np.zeros(n, np.float32), inv_hdd=np.zeros(n, np.float32),
+            b_d=np.zeros(n, np.float32), flags=np.zeros(n, np.uint8), n_inliers=np.zeros(n, np.uint32),
+            rel_baseline=np.zeros(n, np.float32))
+        self._ck(self.lib.dpba_get_landmarks(self.h, slot, n, _ptr(out["idepth"]), _ptr(out["idepth_step"]),
+                                             _ptr(out["inv_hdd"]), _ptr(out["b_d"]), _ptr(out["flags"]),
+                                             _ptr(out["n_inliers"]), _ptr(out["rel_baseline"])))
+        return out
+
+    def get_pose_idepth_blocks(self, slot):
+        n = self.num_landmarks(slot)
+        out = np.zeros((n, BLOCK * self.n_frames), np.float32)
+        self._ck(self.lib.dpba_get_pose_idepth_blocks(self.h, slot, n, _ptr(out)))
+        return out
+
+    def set_statuses(self, r, t, statuses):
+        st = _u8(statuses)
+        self._ck(self.lib.dpba_set_statuses(self.h, r, t, len(st), _ptr(st)))
+
+    def get_statuses(self, r, t):
+        n = self.num_landmarks(r)
+        st, cand = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        self._ck(self.lib.dpba_get_statuses(self.h, r, t, n, _ptr(st), _ptr(cand)))
+        return st, cand
+
+    def set_state(self, eps=None, step=None):
+        eps, step = _f64(eps), _f64(step)
+        self._ck(self.lib.dpba_set_state(self.h, _ptr(eps), _ptr(step)))
+
+    def get_state(self):
+        n = BLOCK * self.n_frames
+        eps, step = np.zeros(n), np.zeros(n)
+        self._ck(self.lib.dpba_get_state(self.h, _ptr(eps), _ptr(step)))
+        return eps, step
+
+    def first_estimate(self):
+        self._ck(self.lib.dpba_first_estimate(self.h))
+
+    def evaluate(self, sigma, huber=True, fej=True):
+        e, n = _D(), _I()
+        self._ck(self.lib.dpba_evaluate(self.h, sigma, int(huber), int(fej), C.byref(e), C.byref(n)))
+        return e.value, n.value
+
+    def evaluate_jacobians(self, sigma, huber=True, fej=True):
+        self._ck(self.lib.dpba_evaluate_jacobians(self.h, sigma, int(huber), int(fej)))
+
+    def download_residual_block(self, r, t):
+        n = self.num_landmarks(r)
+        out = dict(
+            r=np.zeros((n, 8), np.float32), J_ref=np.zeros((n, 8, 8), np.float32),
+            J_tgt=np.zeros((n, 8, 8), np.float32), d_idepth=np.zeros((n, 8), np.float32),
+            w=np.zeros(n, np.float32), e=np.zeros(n, np.float32), status=np.zeros(n, np.uint8),
+            cand=np.zeros(n, np.uint8))
+        v = ResidualView(n, _ptr(out["r"]), _ptr(out["J_ref"]), _ptr(out["J_tgt"]), _ptr(out["d_idepth"]),
+                         _ptr(out["w"]), _ptr(out["e"]), _ptr(out["status"]), _ptr(out["cand"]))
+        self._ck(self.lib.dpba_download_residual_block(self.h, r, t, C.byref(v)))
+        return out
+
+    def linearize(self, sigma, huber=True, fej=True, for_marginalized=False, materialized=False):
+        d = BLOCK * self.n_frames
+        Hp, bp, Hs, bs = np.zeros((d, d)), np.zeros(d), np.zeros((d, d)), np.zeros(d)
+        fn = self.lib.dpba_linearize_materialized if materialized else self.lib.dpba_linearize
+        self._ck(fn(self.h, sigma, int(huber), int(fej), int(for_marginalized), _ptr(Hp), _ptr(bp), _ptr(Hs),
+                    _ptr(bs)))
+        return Hp, bp, Hs, bs
+
+    def back_substitute(self, step_pose, lam):
+        s = _f64(step_pose)
+        self._ck(self.lib.dpba_back_substitute(self.h, _ptr(s), lam))
+
+    def accept(self):
+        a, b = _D(), _D()
+        self._ck(self.lib.dpba_accept(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def reject(self):
+        self._ck(self.lib.dpba_reject(self.h))
+
+    def change_residual_statuses(self, accept=True):
+        self._ck(self.lib.dpba_change_residual_statuses(self.h, int(accept)))
+
+    def landmarks_energy(self, for_marginalized=False):
+        e, n = _D(), _I()
+        self._ck(self.lib.dpba_landmarks_energy(self.h, int(for_marginalized), C.byref(e), C.byref(n)))
+        return e.value, n.value
+
+    def update_point_statuses(self, min_valid, sigma):
+        t = _D()
+        self._ck(self.lib.dpba_update_point_statuses(self.h, min_valid, sigma, C.byref(t)))
+        return t.value
+
+    def comm_init(self, uid: bytes, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self.lib.dpba_comm_init(self.h, C.cast(buf, C.c_void_p), rank, world))
+
+
+def comm_unique_id() -> bytes:
+    lib = load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.dpba_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise DpbaError(f"dpba_comm_unique_id failed with {rc}")
+    return bytes(buf)
+
+
+def upload_window(win, max_frames=None, max_points=None, device=0, rank=0, world_size=1) -> Handle:
+    """Create a handle and load a dsopp_b200.synth.SynthWindow into it (landmark shard `rank` of `world_size`)."""
+    n = win.n_frames
+    shard = [np.arange(rank, len(f.idepth), world_size) for f in win.frames]
+    mp = max_points or max(1, max(len(s) for s in shard))
+    h = Handle(max_frames or max(2, n), mp, win.width, win.height, device, rank, world_size)
+    for f in win.frames:
+        h.push_frame(f.frame_id, f.image, f.mask, f.T_w_lin, f.exposure, f.ab0, f.intr, f.fixed)
+    for i, f in enumerate(win.frames):
+        s = shard[i]
+        h.set_landmarks(i, f.uv[s], f.idepth[s], f.patch[s], f.flags[s])
+    for (r, t), st in win.statuses.items():
+        h.set_statuses(r, t, st[shard[r]])
+    h.set_state(np.concatenate([f.state_eps for f in win.frames]), np.zeros(BLOCK * n))
+    return h

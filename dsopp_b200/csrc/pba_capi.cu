@@ -1,0 +1,864 @@
+// C ABI of the B200 photometric bundle-adjustment path (include/dsopp_cuda_pba.h).
+// Host side of the handle: owns device memory, the stream and the frame state; no compute happens on the CPU
+// here except O(N) frame-state bookkeeping and the nth_element of updatePointStatuses.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>  // types only: the library is resolved at run time (see nccl_api below)
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/dsopp_cuda_pba.h"
+#include "pba_internal.h"
+
+namespace {
+
+// NCCL is bound lazily with dlopen so that (a) single-GPU users never load it and (b) under torchrun the
+// process-wide libnccl.so.2 that torch already loaded (2.28.x here) is the one we call, instead of pulling a
+// second, older copy in through DT_NEEDED.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(lib, "ncclAllReduce");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+  return api;
+}
+
+struct FrameHost {
+  int id = 0;
+  int phys = -1;
+  double T_lin[12];
+  double exposure = 1;
+  double ab0[2] = {0, 0};
+  double intr[4];
+  int fixed = 0;
+  int to_marg = 0;
+  int is_marg = 0;
+  int n_lm = 0;
+  double eps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double step[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+}  // namespace
+
+struct dpba_handle {
+  dpba_config cfg;
+  cudaStream_t stream = nullptr;
+  std::string err = "";
+  int n_frames = 0;
+  FrameHost fr[PBA_MAXF];
+  bool phys_used[PBA_MAXF] = {};
+  float4* img[PBA_MAXF] = {};
+  uint8_t* mask[PBA_MAXF] = {};
+  // landmark SoA
+  float2* uv = nullptr;
+  float *idepth = nullptr, *idepth_step = nullptr, *idepth_fej = nullptr, *patch = nullptr;
+  uint8_t* flags = nullptr;
+  float *inv_hdd = nullptr, *b_d = nullptr, *hpd = nullptr, *rel_baseline = nullptr;
+  uint32_t* n_inliers = nullptr;
+  uint8_t *status = nullptr, *cand = nullptr;
+  float* energy = nullptr;
+  PairConst* pairs = nullptr;
+  PairAssemble* pasm = nullptr;
+  FrameParams* fparams = nullptr;    // device
+  FrameParams* fparams_h = nullptr;  // pinned
+  double* red = nullptr;             // device reduction buffer
+  double* red_h = nullptr;           // pinned mirror
+  size_t red_n = 0;
+  double* step_dev = nullptr;
+  float* pair_dist = nullptr;
+  float* stage = nullptr;  // image upload staging (device)
+  float* stage_h = nullptr;  // pinned staging for images
+  float *m_r = nullptr, *m_jref = nullptr, *m_jtgt = nullptr, *m_did = nullptr, *m_w = nullptr;
+  bool linearized = false;
+  int lin_frames = 0;
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
+};
+
+namespace {
+
+constexpr size_t OFF_CORE = 0;
+constexpr size_t N_CORE = (size_t)PBA_MAXF * PBA_MAXF * PBA_CORE;
+constexpr size_t MAXD = PBA_MAXF * 8;
+constexpr size_t OFF_HS = OFF_CORE + N_CORE;
+constexpr size_t OFF_BS = OFF_HS + MAXD * MAXD;
+constexpr size_t OFF_SCAL = OFF_BS + MAXD;
+constexpr size_t N_EXCHANGE = OFF_SCAL + 8;  // [core | Hs | bs | scal] is what crosses NVLink
+constexpr size_t OFF_HP = N_EXCHANGE;
+constexpr size_t OFF_BP = OFF_HP + MAXD * MAXD;
+constexpr size_t N_RED = OFF_BP + MAXD;
+
+int fail(dpba_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CK(expr)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (expr);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(h, DPBA_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));               \
+  } while (0)
+
+#define REQUIRE(cond, msg)                                  \
+  do {                                                      \
+    if (!(cond)) return fail(h, DPBA_E_INVALID, (msg));     \
+  } while (0)
+
+ReduceBuf redbuf(dpba_handle* h) {
+  ReduceBuf rb;
+  rb.core = h->red + OFF_CORE;
+  rb.Hs = h->red + OFF_HS;
+  rb.bs = h->red + OFF_BS;
+  rb.scal = h->red + OFF_SCAL;
+  rb.Hp = h->red + OFF_HP;
+  rb.bp = h->red + OFF_BP;
+  return rb;
+}
+
+WindowDev make_window(dpba_handle* h) {
+  WindowDev w;
+  memset(&w, 0, sizeof(w));
+  w.n_frames = h->n_frames;
+  w.W = h->cfg.width;
+  w.H = h->cfg.height;
+  w.max_pts = h->cfg.max_points_per_frame;
+  w.hpd_stride = 8 * (h->linearized ? h->lin_frames : h->n_frames);
+  for (int f = 0; f < h->n_frames; ++f) {
+    const FrameHost& F = h->fr[f];
+    w.n_lm[f] = F.n_lm;
+    w.fixed[f] = F.fixed;
+    w.frame_marg[f] = F.is_marg;
+    w.phys[f] = F.phys;
+    w.img[f] = h->img[F.phys];
+    w.mask[f] = h->mask[F.phys];
+  }
+  w.uv = h->uv;
+  w.idepth = h->idepth;
+  w.idepth_step = h->idepth_step;
+  w.idepth_fej = h->idepth_fej;
+  w.patch = h->patch;
+  w.flags = h->flags;
+  w.inv_hdd = h->inv_hdd;
+  w.b_d = h->b_d;
+  w.hpd = h->hpd;
+  w.rel_baseline = h->rel_baseline;
+  w.n_inliers = h->n_inliers;
+  w.status = h->status;
+  w.cand = h->cand;
+  w.energy = h->energy;
+  w.pairs = h->pairs;
+  w.pairs_asm = h->pasm;
+  w.m_r = h->m_r;
+  w.m_jref = h->m_jref;
+  w.m_jtgt = h->m_jtgt;
+  w.m_did = h->m_did;
+  w.m_w = h->m_w;
+  return w;
+}
+
+// upload the frame state and recompute the per-pair constants on the device
+int sync_pairs(dpba_handle* h) {
+  for (int f = 0; f < h->n_frames; ++f) {
+    FrameParams& p = h->fparams_h[f];
+    const FrameHost& F = h->fr[f];
+    memcpy(p.T_lin, F.T_lin, sizeof(p.T_lin));
+    memcpy(p.eps, F.eps, sizeof(p.eps));
+    memcpy(p.step, F.step, sizeof(p.step));
+    p.exposure = F.exposure;
+    p.ab0[0] = F.ab0[0];
+    p.ab0[1] = F.ab0[1];
+    memcpy(p.intr, F.intr, sizeof(p.intr));
+  }
+  CK(cudaMemcpyAsync(h->fparams, h->fparams_h, sizeof(FrameParams) * h->n_frames, cudaMemcpyHostToDevice, h->stream));
+  pba::launch_pair_setup(h->fparams, h->n_frames, h->pairs, h->pasm, h->stream);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int ensure_materialized(dpba_handle* h) {
+  if (h->m_r) return 0;
+  const size_t nres = (size_t)PBA_MAXF * PBA_MAXF * h->cfg.max_points_per_frame;
+  // only max_frames^2 blocks are ever addressed, but the index uses the PBA_MAXF stride
+  CK(cudaMalloc(&h->m_r, nres * 8 * sizeof(float)));
+  CK(cudaMalloc(&h->m_did, nres * 8 * sizeof(float)));
+  CK(cudaMalloc(&h->m_w, nres * sizeof(float)));
+  CK(cudaMalloc(&h->m_jref, nres * 64 * sizeof(float)));
+  CK(cudaMalloc(&h->m_jtgt, nres * 64 * sizeof(float)));
+  CK(cudaMemsetAsync(h->m_r, 0, nres * 8 * sizeof(float), h->stream));
+  CK(cudaMemsetAsync(h->m_did, 0, nres * 8 * sizeof(float), h->stream));
+  CK(cudaMemsetAsync(h->m_jref, 0, nres * 64 * sizeof(float), h->stream));
+  CK(cudaMemsetAsync(h->m_jtgt, 0, nres * 64 * sizeof(float), h->stream));
+  // huber_weight = 1 in the ResidualPoint ctor (local_frame.hpp:218)
+  std::vector<float> ones(nres, 1.f);
+  CK(cudaMemcpyAsync(h->m_w, ones.data(), nres * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// sum the [core | Hs | bs | scal] block over ranks (one fused in-place NCCL allreduce on the compute stream)
+int exchange(dpba_handle* h, size_t off, size_t n) {
+  if (h->world <= 1 || !h->comm) return 0;
+  NcclApi& nc = nccl_api();
+  ncclResult_t r = nc.AllReduce(h->red + off, h->red + off, n, ncclDouble, ncclSum, h->comm, h->stream);
+  if (r != ncclSuccess) return fail(h, DPBA_E_COMM, std::string("ncclAllReduce: ") + nc.GetErrorString(r));
+  return 0;
+}
+
+void host_se3_exp_translation(const double* T_lin, const double* eps, double* t_out) {
+  // translation of T_lin * exp(eps[0:6])  (LocalFrame::tWorldAgent, local_frame.hpp:525-527)
+  const double* v = eps;
+  const double* w = eps + 3;
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th = sqrt(th2);
+  double b, c;
+  if (th < 1e-10) {
+    b = 0.5;
+    c = 1.0 / 6.0;
+  } else {
+    b = (1.0 - cos(th)) / th2;
+    c = (th - sin(th)) / (th2 * th);
+  }
+  const double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double W2[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += W[i * 3 + k] * W[k * 3 + j];
+      W2[i * 3 + j] = s;
+    }
+  double tv[3];
+  for (int i = 0; i < 3; ++i) {
+    tv[i] = 0;
+    for (int j = 0; j < 3; ++j) tv[i] += ((i == j ? 1.0 : 0.0) + b * W[i * 3 + j] + c * W2[i * 3 + j]) * v[j];
+  }
+  for (int i = 0; i < 3; ++i)
+    t_out[i] = T_lin[i * 4 + 3] + T_lin[i * 4 + 0] * tv[0] + T_lin[i * 4 + 1] * tv[1] + T_lin[i * 4 + 2] * tv[2];
+}
+
+int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int channels, const uint8_t* mask,
+                      const double* T, double exposure, const double* ab0, const double* intr, int32_t fixed) {
+  REQUIRE(h, "null handle");
+  REQUIRE(image && T && ab0 && intr, "null argument");
+  if (h->n_frames >= h->cfg.max_frames) return fail(h, DPBA_E_CAPACITY, "window is full");
+  REQUIRE(!fixed || h->n_frames == 0, "only the first frame can be fixed (hessian_block_evaluation.hpp:143)");
+  REQUIRE(exposure > 0, "exposure_time must be positive");
+  int phys = -1;
+  for (int p = 0; p < h->cfg.max_frames; ++p)
+    if (!h->phys_used[p]) {
+      phys = p;
+      break;
+    }
+  if (phys < 0) return fail(h, DPBA_E_CAPACITY, "no free frame slot");
+  const int W = h->cfg.width, H = h->cfg.height;
+  const size_t npx = (size_t)W * H;
+  memcpy(h->stage_h, image, npx * channels * sizeof(float));
+  CK(cudaMemcpyAsync(h->stage, h->stage_h, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (channels == 3) pba::launch_pack_image(h->stage, h->img[phys], (int)npx, h->stream);
+  else pba::launch_pixelinfo(h->stage, h->img[phys], W, H, h->stream);
+  CK(cudaGetLastError());
+  if (mask) CK(cudaMemcpyAsync(h->mask[phys], mask, npx, cudaMemcpyHostToDevice, h->stream));
+  else CK(cudaMemsetAsync(h->mask[phys], 255, npx, h->stream));
+  // new residual vectors of this frame start as kOk until dpba_set_statuses says otherwise
+  const size_t mp = h->cfg.max_points_per_frame;
+  for (int p = 0; p < h->cfg.max_frames; ++p) {
+    const size_t a = ((size_t)(phys * PBA_MAXF + p)) * mp, b = ((size_t)(p * PBA_MAXF + phys)) * mp;
+    CK(cudaMemsetAsync(h->status + a, 0, mp, h->stream));
+    CK(cudaMemsetAsync(h->cand + a, 0, mp, h->stream));
+    CK(cudaMemsetAsync(h->energy + a, 0, mp * sizeof(float), h->stream));
+    CK(cudaMemsetAsync(h->status + b, 0, mp, h->stream));
+    CK(cudaMemsetAsync(h->cand + b, 0, mp, h->stream));
+    CK(cudaMemsetAsync(h->energy + b, 0, mp * sizeof(float), h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));  // stage_h is reused by the next push
+  FrameHost& F = h->fr[h->n_frames];
+  F = FrameHost();
+  F.id = frame_id;
+  F.phys = phys;
+  memcpy(F.T_lin, T, sizeof(F.T_lin));
+  F.exposure = exposure;
+  F.ab0[0] = ab0[0];
+  F.ab0[1] = ab0[1];
+  memcpy(F.intr, intr, sizeof(F.intr));
+  F.fixed = fixed ? 1 : 0;
+  h->phys_used[phys] = true;
+  h->linearized = false;
+  return h->n_frames++;
+}
+
+int upload_landmarks(dpba_handle* h, int slot, int first, int n, const float* uv, const float* idepth,
+                     const float* patch, const uint8_t* flags) {
+  const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame + first;
+  if (n == 0) return 0;
+  CK(cudaMemcpyAsync(h->uv + base, uv, sizeof(float2) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->idepth + base, idepth, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->idepth_fej + base, idepth, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->patch + base * 8, patch, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, h->stream));
+  if (flags) CK(cudaMemcpyAsync(h->flags + base, flags, n, cudaMemcpyHostToDevice, h->stream));
+  else CK(cudaMemsetAsync(h->flags + base, 0, n, h->stream));
+  CK(cudaMemsetAsync(h->idepth_step + base, 0, sizeof(float) * n, h->stream));
+  CK(cudaMemsetAsync(h->inv_hdd + base, 0, sizeof(float) * n, h->stream));
+  CK(cudaMemsetAsync(h->b_d + base, 0, sizeof(float) * n, h->stream));
+  CK(cudaMemsetAsync(h->rel_baseline + base, 0, sizeof(float) * n, h->stream));
+  CK(cudaMemsetAsync(h->n_inliers + base, 0, sizeof(uint32_t) * n, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // the caller keeps ownership of its (possibly pageable) buffers
+  return 0;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* dpba_version(void) { return "dsopp_b200 0.1 (sm_100a)"; }
+
+const char* dpba_last_error(const dpba_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+void* dpba_stream(dpba_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int dpba_create(const dpba_config* cfg, dpba_handle** out) {
+  if (!cfg || !out) return DPBA_E_INVALID;
+  *out = nullptr;
+  if (cfg->max_frames < 2 || cfg->max_frames > DPBA_MAX_FRAMES || cfg->max_points_per_frame < 1 || cfg->width < 16 ||
+      cfg->height < 16)
+    return DPBA_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+    // no CPU fallback: the product path needs the GPU
+    fprintf(stderr, "dpba_create: CUDA device %d not available (%d devices)\n", cfg->device, ndev);
+    return DPBA_E_CUDA;
+  }
+  dpba_handle* h = new dpba_handle();
+  h->cfg = *cfg;
+  h->rank = cfg->rank;
+  h->world = cfg->world_size > 0 ? cfg->world_size : 1;
+#define CKC(expr)                                                                    \
+  do {                                                                               \
+    cudaError_t e_ = (expr);                                                         \
+    if (e_ != cudaSuccess) {                                                         \
+      fprintf(stderr, "dpba_create: %s: %s\n", #expr, cudaGetErrorString(e_));       \
+      dpba_destroy(h);                                                               \
+      return DPBA_E_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const size_t npx = (size_t)cfg->width * cfg->height;
+  const size_t mp = cfg->max_points_per_frame;
+  const size_t nlm = (size_t)cfg->max_frames * mp;
+  const size_t nres = (size_t)PBA_MAXF * PBA_MAXF * mp;
+  for (int p = 0; p < cfg->max_frames; ++p) {
+    CKC(cudaMalloc(&h->img[p], npx * sizeof(float4)));
+    CKC(cudaMalloc(&h->mask[p], npx));
+  }
+  CKC(cudaMalloc(&h->uv, nlm * sizeof(float2)));
+  CKC(cudaMalloc(&h->idepth, nlm * sizeof(float)));
+  CKC(cudaMalloc(&h->idepth_step, nlm * sizeof(float)));
+  CKC(cudaMalloc(&h->idepth_fej, nlm * sizeof(float)));
+  CKC(cudaMalloc(&h->patch, nlm * 8 * sizeof(float)));
+  CKC(cudaMalloc(&h->flags, nlm));
+  CKC(cudaMalloc(&h->inv_hdd, nlm * sizeof(float)));
+  CKC(cudaMalloc(&h->b_d, nlm * sizeof(float)));
+  CKC(cudaMalloc(&h->hpd, nlm * MAXD * sizeof(float)));
+  CKC(cudaMalloc(&h->rel_baseline, nlm * sizeof(float)));
+  CKC(cudaMalloc(&h->n_inliers, nlm * sizeof(uint32_t)));
+  CKC(cudaMalloc(&h->status, nres));
+  CKC(cudaMalloc(&h->cand, nres));
+  CKC(cudaMalloc(&h->energy, nres * sizeof(float)));
+  CKC(cudaMemset(h->status, 0, nres));
+  CKC(cudaMemset(h->cand, 0, nres));
+  CKC(cudaMemset(h->energy, 0, nres * sizeof(float)));
+  CKC(cudaMemset(h->flags, 0, nlm));
+  CKC(cudaMemset(h->hpd, 0, nlm * MAXD * sizeof(float)));
+  CKC(cudaMalloc(&h->pairs, sizeof(PairConst) * PBA_MAXF * PBA_MAXF));
+  CKC(cudaMalloc(&h->pasm, sizeof(PairAssemble) * PBA_MAXF * PBA_MAXF));
+  CKC(cudaMalloc(&h->fparams, sizeof(FrameParams) * PBA_MAXF));
+  CKC(cudaMallocHost(&h->fparams_h, sizeof(FrameParams) * PBA_MAXF));
+  h->red_n = N_RED;
+  CKC(cudaMalloc(&h->red, N_RED * sizeof(double)));
+  CKC(cudaMallocHost(&h->red_h, N_RED * sizeof(double)));
+  CKC(cudaMalloc(&h->step_dev, MAXD * sizeof(double)));
+  CKC(cudaMalloc(&h->pair_dist, PBA_MAXF * PBA_MAXF * sizeof(float)));
+  CKC(cudaMalloc(&h->stage, npx * 3 * sizeof(float)));
+  CKC(cudaMallocHost(&h->stage_h, npx * 3 * sizeof(float)));
+#undef CKC
+  *out = h;
+  return DPBA_SUCCESS;
+}
+
+int dpba_destroy(dpba_handle* h) {
+  if (!h) return DPBA_E_INVALID;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) nccl_api().CommDestroy(h->comm);
+  for (int p = 0; p < PBA_MAXF; ++p) {
+    cudaFree(h->img[p]);
+    cudaFree(h->mask[p]);
+  }
+  void* dev[] = {h->uv,      h->idepth, h->idepth_step,  h->idepth_fej, h->patch,  h->flags,   h->inv_hdd,
+                 h->b_d,     h->hpd,    h->rel_baseline, h->n_inliers,  h->status, h->cand,    h->energy,
+                 h->pairs,   h->pasm,   h->fparams,      h->red,        h->step_dev, h->pair_dist, h->stage,
+                 h->m_r,     h->m_jref, h->m_jtgt,       h->m_did,      h->m_w};
+  for (void* p : dev) cudaFree(p);
+  cudaFreeHost(h->fparams_h);
+  cudaFreeHost(h->red_h);
+  cudaFreeHost(h->stage_h);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DPBA_SUCCESS;
+}
+
+int dpba_push_frame(dpba_handle* h, int32_t frame_id, const float* image_I_dx_dy, const uint8_t* mask,
+                    const double T[12], double exposure, const double ab0[2], const double intr[4], int32_t fixed) {
+  return push_frame_common(h, frame_id, image_I_dx_dy, 3, mask, T, exposure, ab0, intr, fixed);
+}
+
+int dpba_push_frame_intensity(dpba_handle* h, int32_t frame_id, const float* image_I, const uint8_t* mask,
+                              const double T[12], double exposure, const double ab0[2], const double intr[4],
+                              int32_t fixed) {
+  return push_frame_common(h, frame_id, image_I, 1, mask, T, exposure, ab0, intr, fixed);
+}
+
+int dpba_remove_frame(dpba_handle* h, int32_t slot) {
+  REQUIRE(h, "null handle");
+  REQUIRE(slot >= 0 && slot < h->n_frames, "slot out of range");
+  h->phys_used[h->fr[slot].phys] = false;
+  for (int f = slot; f + 1 < h->n_frames; ++f) h->fr[f] = h->fr[f + 1];
+  --h->n_frames;
+  h->linearized = false;
+  return DPBA_SUCCESS;
+}
+
+int dpba_num_frames(const dpba_handle* h) { return h ? h->n_frames : DPBA_E_INVALID; }
+
+int dpba_set_frame_linearization(dpba_handle* h, int32_t slot, const double T[12], const double ab0[2]) {
+  REQUIRE(h, "null handle");
+  REQUIRE(slot >= 0 && slot < h->n_frames && T && ab0, "bad argument");
+  FrameHost& F = h->fr[slot];
+  memcpy(F.T_lin, T, sizeof(F.T_lin));
+  F.ab0[0] = ab0[0];
+  F.ab0[1] = ab0[1];
+  for (int k = 0; k < 8; ++k) F.eps[k] = 0;
+  return DPBA_SUCCESS;
+}
+
+int dpba_set_frame_flags(dpba_handle* h, int32_t slot, int32_t fixed, int32_t to_marginalize) {
+  REQUIRE(h, "null handle");
+  REQUIRE(slot >= 0 && slot < h->n_frames, "slot out of range");
+  REQUIRE(!fixed || slot == 0, "only the first frame can be fixed");
+  h->fr[slot].fixed = fixed ? 1 : 0;
+  h->fr[slot].to_marg = to_marginalize ? 1 : 0;
+  return DPBA_SUCCESS;
+}
+
+int dpba_set_landmarks(dpba_handle* h, int32_t slot, int32_t n, const float* uv, const float* idepth,
+                       const float* patch, const uint8_t* flags) {
+  REQUIRE(h, "null handle");
+  REQUIRE(slot >= 0 && slot < h->n_frames, "slot out of range");
+  REQUIRE(n >= 0 && (n == 0 || (uv && idepth && patch)), "null landmark arrays");
+  if (n > h->cfg.max_points_per_frame) return fail(h, DPBA_E_CAPACITY, "too many landmarks for this handle");
+  int rc = upload_landmarks(h, slot, 0, n, uv, idepth, patch, flags);
+  if (rc) return rc;
+  h->fr[slot].n_lm = n;
+  return DPBA_SUCCESS;
+}
+
+int dpba_append_landmarks(dpba_handle* h, int32_t slot, int32_t n, const float* uv, const float* idepth,
+                          const float* patch, const uint8_t* flags) {
+  REQUIRE(h, "null handle");
+  REQUIRE(slot >= 0 && slot < h->n_frames, "slot out of range");
+  REQUIRE(n >= 0 && (n == 0 || (uv && idepth && patch)), "null landmark arrays");
+  const int first = h->fr[slot].n_lm;
+  if (first + n > h->cfg.max_points_per_frame) return fail(h, DPBA_E_CAPACITY, "too many landmarks for this handle");
+  int rc = upload_landmarks(h, slot, first, n, uv, idepth, patch, flags);
+  if (rc) return rc;
+  h->fr[slot].n_lm = first + n;
+  return DPBA_SUCCESS;
+}
+
+int dpba_set_landmark_flags(dpba_handle* h, int32_t slot, int32_t n, const uint8_t* flags) {
+  REQUIRE(h, "null handle");
+  REQUIRE(slot >= 0 && slot < h->n_frames && flags, "bad argument");
+  REQUIRE(n == h->fr[slot].n_lm, "flag count must equal the landmark count");
+  const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame;
+  if (n) CK(cudaMemcpyAsync(h->flags + base, flags, n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
+int dpba_num_landmarks(const dpba_handle* h, int32_t slot) {
+  if (!h || slot < 0 || slot >= h->n_frames) return DPBA_E_INVALID;
+  return h->fr[slot].n_lm;
+}
+
+int dpba_get_landmarks(dpba_handle* h, int32_t slot, int32_t n, float* idepth, float* idepth_step, float* inv_hdd,
+                       float* b_d, uint8_t* flags, uint32_t* n_inl, float* rel_baseline) {
+  REQUIRE(h, "null handle");
+  REQUIRE(slot >= 0 && slot < h->n_frames, "slot out of range");
+  REQUIRE(n >= 0 && n <= h->fr[slot].n_lm, "n exceeds the landmark count");
+  const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame;
+  if (n == 0) return DPBA_SUCCESS;
+  if (idepth) CK(cudaMemcpyAsync(idepth, h->idepth + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (idepth_step)
+    CK(cudaMemcpyAsync(idepth_step, h->idepth_step + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (inv_hdd) CK(cudaMemcpyAsync(inv_hdd, h->inv_hdd + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (b_d) CK(cudaMemcpyAsync(b_d, h->b_d + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (flags) CK(cudaMemcpyAsync(flags, h->flags + base, n, cudaMemcpyDeviceToHost, h->stream));
+  if (n_inl) CK(cudaMemcpyAsync(n_inl, h->n_inliers + base, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (rel_baseline)
+    CK(cudaMemcpyAsync(rel_baseline, h->rel_baseline + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
+int dpba_get_pose_idepth_blocks(dpba_handle* h, int32_t slot, int32_t n, float* out) {
+  REQUIRE(h, "null handle");
+  REQUIRE(slot >= 0 && slot < h->n_frames && out, "bad argument");
+  REQUIRE(n >= 0 && n <= h->fr[slot].n_lm, "n exceeds the landmark count");
+  if (!h->linearized) return fail(h, DPBA_E_STATE, "linearize first");
+  const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame;
+  const size_t stride = 8 * (size_t)h->lin_frames;
+  if (n) CK(cudaMemcpyAsync(out, h->hpd + base * stride, sizeof(float) * stride * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
+int dpba_set_statuses(dpba_handle* h, int32_t r, int32_t t, int32_t n, const uint8_t* st) {
+  REQUIRE(h, "null handle");
+  REQUIRE(r >= 0 && r < h->n_frames && t >= 0 && t < h->n_frames && r != t && st, "bad pair");
+  REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
+  const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
+  if (n) {
+    CK(cudaMemcpyAsync(h->status + base, st, n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cand + base, st, n, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
+int dpba_get_statuses(dpba_handle* h, int32_t r, int32_t t, int32_t n, uint8_t* st, uint8_t* cand) {
+  REQUIRE(h, "null handle");
+  REQUIRE(r >= 0 && r < h->n_frames && t >= 0 && t < h->n_frames && r != t, "bad pair");
+  REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
+  const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
+  if (n && st) CK(cudaMemcpyAsync(st, h->status + base, n, cudaMemcpyDeviceToHost, h->stream));
+  if (n && cand) CK(cudaMemcpyAsync(cand, h->cand + base, n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
+int dpba_set_state(dpba_handle* h, const double* eps, const double* step) {
+  REQUIRE(h, "null handle");
+  for (int f = 0; f < h->n_frames; ++f)
+    for (int k = 0; k < 8; ++k) {
+      if (eps) h->fr[f].eps[k] = eps[8 * f + k];
+      if (step) h->fr[f].step[k] = step[8 * f + k];
+    }
+  return DPBA_SUCCESS;
+}
+
+int dpba_get_state(dpba_handle* h, double* eps, double* step) {
+  REQUIRE(h, "null handle");
+  for (int f = 0; f < h->n_frames; ++f)
+    for (int k = 0; k < 8; ++k) {
+      if (eps) eps[8 * f + k] = h->fr[f].eps[k];
+      if (step) step[8 * f + k] = h->fr[f].step[k];
+    }
+  return DPBA_SUCCESS;
+}
+
+int dpba_first_estimate(dpba_handle* h) {
+  REQUIRE(h, "null handle");
+  WindowDev w = make_window(h);
+  pba::launch_snapshot_fej(w, h->stream);
+  CK(cudaGetLastError());
+  return DPBA_SUCCESS;
+}
+
+int dpba_evaluate(dpba_handle* h, double sigma, int32_t huber, int32_t fej, double* energy, int32_t* n_valid) {
+  REQUIRE(h, "null handle");
+  REQUIRE(h->n_frames >= 2, "need at least two frames");
+  REQUIRE(huber || sigma == 0, "sigma_huber must be 0 without huber (evaluate_jacobians.hpp:25)");
+  int rc = sync_pairs(h);
+  if (rc) return rc;
+  ReduceBuf rb = redbuf(h);
+  CK(cudaMemsetAsync(rb.scal, 0, 8 * sizeof(double), h->stream));
+  WindowDev w = make_window(h);
+  pba::launch_residual_sweep(w, (float)sigma, huber, fej, rb.scal, h->stream);
+  CK(cudaGetLastError());
+  rc = exchange(h, OFF_SCAL, 8);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->red_h + OFF_SCAL, rb.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (energy) *energy = h->red_h[OFF_SCAL + 0];
+  if (n_valid) *n_valid = (int32_t)llround(h->red_h[OFF_SCAL + 1]);
+  return DPBA_SUCCESS;
+}
+
+int dpba_evaluate_jacobians(dpba_handle* h, double sigma, int32_t huber, int32_t fej) {
+  REQUIRE(h, "null handle");
+  REQUIRE(h->n_frames >= 2, "need at least two frames");
+  REQUIRE(huber || sigma == 0, "sigma_huber must be 0 without huber");
+  int rc = ensure_materialized(h);
+  if (rc) return rc;
+  rc = sync_pairs(h);
+  if (rc) return rc;
+  WindowDev w = make_window(h);
+  pba::launch_materialise_sweep(w, (float)sigma, huber, fej, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
+int dpba_download_residual_block(dpba_handle* h, int32_t r, int32_t t, dpba_residual_view* v) {
+  REQUIRE(h, "null handle");
+  REQUIRE(v, "null view");
+  REQUIRE(r >= 0 && r < h->n_frames && t >= 0 && t < h->n_frames && r != t, "bad pair");
+  if (!h->m_r) return fail(h, DPBA_E_STATE, "dpba_evaluate_jacobians has not run");
+  const int n = std::min<int>(v->n, h->fr[r].n_lm);
+  const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
+  auto dl = [&](void* dst, const void* src, size_t bytes) {
+    return dst && bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream) : cudaSuccess;
+  };
+  CK(dl(v->residuals, h->m_r + base * 8, sizeof(float) * 8 * n));
+  CK(dl(v->d_reference_state_eps, h->m_jref + base * 64, sizeof(float) * 64 * n));
+  CK(dl(v->d_target_state_eps, h->m_jtgt + base * 64, sizeof(float) * 64 * n));
+  CK(dl(v->d_idepth, h->m_did + base * 8, sizeof(float) * 8 * n));
+  CK(dl(v->huber_weight, h->m_w + base, sizeof(float) * n));
+  CK(dl(v->energy, h->energy + base, sizeof(float) * n));
+  CK(dl(v->connection_status, h->status + base, n));
+  CK(dl(v->connection_status_candidate, h->cand + base, n));
+  CK(cudaStreamSynchronize(h->stream));
+  v->n = n;
+  return DPBA_SUCCESS;
+}
+
+static int linearize_impl(dpba_handle* h, double sigma, int32_t huber, int32_t fej, int32_t for_marg, bool fused,
+                          double* H_pose, double* b_pose, double* H_schur, double* b_schur) {
+  REQUIRE(h, "null handle");
+  REQUIRE(h->n_frames >= 2, "need at least two frames");
+  REQUIRE(huber || sigma == 0, "sigma_huber must be 0 without huber");
+  int rc;
+  if (!fused && (rc = ensure_materialized(h))) return rc;
+  if ((rc = sync_pairs(h))) return rc;
+  const int N = h->n_frames, D = 8 * N;
+  h->linearized = true;
+  h->lin_frames = N;
+  ReduceBuf rb = redbuf(h);
+  CK(cudaMemsetAsync(h->red, 0, N_RED * sizeof(double), h->stream));
+  WindowDev w = make_window(h);
+  if (fused) {
+    pba::launch_linearize_fused(w, (float)sigma, huber, fej, for_marg, rb, h->stream);
+    CK(cudaGetLastError());
+    pba::launch_schur(w, for_marg, rb, h->stream);
+    CK(cudaGetLastError());
+    if ((rc = exchange(h, OFF_CORE, N_EXCHANGE))) return rc;
+    pba::launch_assemble(w, fej, rb, h->stream);
+  } else {
+    pba::launch_materialise_sweep(w, (float)sigma, huber, fej, h->stream);
+    CK(cudaGetLastError());
+    pba::launch_linearize_from_materialized(w, for_marg, rb, h->stream);
+    CK(cudaGetLastError());
+    pba::launch_schur(w, for_marg, rb, h->stream);
+    CK(cudaGetLastError());
+    if (h->world > 1 && h->comm) {
+      if ((rc = exchange(h, OFF_HS, N_EXCHANGE - OFF_HS))) return rc;
+      if ((rc = exchange(h, OFF_HP, N_RED - OFF_HP))) return rc;
+    }
+    pba::launch_symmetrise_only(D, rb.Hp, h->stream);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->red_h + OFF_HS, rb.Hs, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->red_h + OFF_BS, rb.bs, D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->red_h + OFF_HP, rb.Hp, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->red_h + OFF_BP, rb.bp, D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (H_pose) memcpy(H_pose, h->red_h + OFF_HP, (size_t)D * D * sizeof(double));
+  if (b_pose) memcpy(b_pose, h->red_h + OFF_BP, D * sizeof(double));
+  if (H_schur) memcpy(H_schur, h->red_h + OFF_HS, (size_t)D * D * sizeof(double));
+  if (b_schur) memcpy(b_schur, h->red_h + OFF_BS, D * sizeof(double));
+  return DPBA_SUCCESS;
+}
+
+int dpba_linearize(dpba_handle* h, double sigma, int32_t huber, int32_t fej, int32_t for_marg, double* H_pose,
+                   double* b_pose, double* H_schur, double* b_schur) {
+  return linearize_impl(h, sigma, huber, fej, for_marg, true, H_pose, b_pose, H_schur, b_schur);
+}
+
+int dpba_linearize_materialized(dpba_handle* h, double sigma, int32_t huber, int32_t fej, int32_t for_marg,
+                                double* H_pose, double* b_pose, double* H_schur, double* b_schur) {
+  return linearize_impl(h, sigma, huber, fej, for_marg, false, H_pose, b_pose, H_schur, b_schur);
+}
+
+int dpba_back_substitute(dpba_handle* h, const double* step_pose, double lambda) {
+  REQUIRE(h, "null handle");
+  REQUIRE(step_pose, "null step");
+  if (!h->linearized || h->lin_frames != h->n_frames) return fail(h, DPBA_E_STATE, "linearize first");
+  const int D = 8 * h->n_frames;
+  memcpy(h->red_h, step_pose, D * sizeof(double));  // pinned staging
+  CK(cudaMemcpyAsync(h->step_dev, h->red_h, D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  WindowDev w = make_window(h);
+  pba::launch_back_substitute(w, h->step_dev, lambda, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
+int dpba_accept(dpba_handle* h, double* state_sq, double* step_sq) {
+  REQUIRE(h, "null handle");
+  ReduceBuf rb = redbuf(h);
+  CK(cudaMemsetAsync(rb.scal, 0, 8 * sizeof(double), h->stream));
+  WindowDev w = make_window(h);
+  pba::launch_accept(w, 1, rb.scal, h->stream);
+  pba::launch_change_statuses(w, 1, h->stream);
+  CK(cudaGetLastError());
+  int rc = exchange(h, OFF_SCAL, 8);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->red_h + OFF_SCAL, rb.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double st = h->red_h[OFF_SCAL + 2], sp = h->red_h[OFF_SCAL + 3];
+  for (int f = 0; f < h->n_frames; ++f) {  // problem.hpp:369-376
+    FrameHost& F = h->fr[f];
+    for (int k = 0; k < 8; ++k) st += F.eps[k] * F.eps[k];
+    st += F.ab0[0] * F.ab0[0] + F.ab0[1] * F.ab0[1];
+    for (int k = 0; k < 8; ++k) {
+      F.eps[k] += F.step[k];
+      sp += F.step[k] * F.step[k];
+      F.step[k] = 0;
+    }
+  }
+  if (state_sq) *state_sq = st;
+  if (step_sq) *step_sq = sp;
+  return DPBA_SUCCESS;
+}
+
+int dpba_reject(dpba_handle* h) {
+  REQUIRE(h, "null handle");
+  WindowDev w = make_window(h);
+  pba::launch_accept(w, 0, nullptr, h->stream);
+  pba::launch_change_statuses(w, 0, h->stream);
+  CK(cudaGetLastError());
+  for (int f = 0; f < h->n_frames; ++f)
+    for (int k = 0; k < 8; ++k) h->fr[f].step[k] = 0;
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
+int dpba_change_residual_statuses(dpba_handle* h, int32_t accept) {
+  REQUIRE(h, "null handle");
+  WindowDev w = make_window(h);
+  pba::launch_change_statuses(w, accept ? 1 : 0, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
+int dpba_landmarks_energy(dpba_handle* h, int32_t for_marg, double* energy, int32_t* n_valid) {
+  REQUIRE(h, "null handle");
+  ReduceBuf rb = redbuf(h);
+  CK(cudaMemsetAsync(rb.scal, 0, 8 * sizeof(double), h->stream));
+  WindowDev w = make_window(h);
+  pba::launch_landmarks_energy(w, for_marg, rb.scal, h->stream);
+  CK(cudaGetLastError());
+  int rc = exchange(h, OFF_SCAL, 8);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->red_h + OFF_SCAL, rb.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (energy) *energy = h->red_h[OFF_SCAL];
+  if (n_valid) *n_valid = (int32_t)llround(h->red_h[OFF_SCAL + 1]);
+  return DPBA_SUCCESS;
+}
+
+int dpba_update_point_statuses(dpba_handle* h, int32_t min_valid, double sigma, double* thr_out) {
+  REQUIRE(h, "null handle");
+  const int N = h->n_frames;
+  const size_t mp = h->cfg.max_points_per_frame;
+  // first half (photometric_bundle_adjustment.cpp:325-361): energies of kOk residuals of active landmarks
+  std::vector<float> energies;
+  std::vector<float> e(mp);
+  std::vector<uint8_t> st(mp), fl(mp);
+  for (int r = 0; r < N; ++r) {
+    const int n = h->fr[r].n_lm;
+    if (!n) continue;
+    CK(cudaMemcpyAsync(fl.data(), h->flags + (size_t)h->fr[r].phys * mp, n, cudaMemcpyDeviceToHost, h->stream));
+    for (int t = 0; t < N; ++t) {
+      if (t == r || h->fr[t].is_marg) continue;
+      const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * mp;
+      CK(cudaMemcpyAsync(e.data(), h->energy + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(st.data(), h->status + base, n, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      for (int l = 0; l < n; ++l)
+        if (!(fl[l] & DPBA_LM_MARGINALIZED) && st[l] == DPBA_OK_STATUS) energies.push_back(e[l]);
+    }
+  }
+  if (h->world > 1) return fail(h, DPBA_E_STATE, "update_point_statuses: gather the energies on the caller for world_size > 1");
+  float thr = 0.f;
+  if (!energies.empty()) {
+    const size_t k = (size_t)((double)energies.size() * 0.75);
+    std::nth_element(energies.begin(), energies.begin() + (long)k, energies.end());
+    thr = energies[k] + (float)(sigma * sigma / 2);
+  }
+  float dist[PBA_MAXF * PBA_MAXF] = {};
+  double tw[PBA_MAXF][3];
+  for (int f = 0; f < N; ++f) host_se3_exp_translation(h->fr[f].T_lin, h->fr[f].eps, tw[f]);
+  for (int r = 0; r < N; ++r)
+    for (int t = 0; t < N; ++t) {
+      const double dx = tw[r][0] - tw[t][0], dy = tw[r][1] - tw[t][1], dz = tw[r][2] - tw[t][2];
+      dist[r * PBA_MAXF + t] = (float)sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  CK(cudaMemcpyAsync(h->pair_dist, dist, sizeof(dist), cudaMemcpyHostToDevice, h->stream));
+  WindowDev w = make_window(h);
+  pba::launch_apply_point_statuses(w, thr, min_valid, h->pair_dist, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  if (thr_out) *thr_out = thr;
+  return DPBA_SUCCESS;
+}
+
+int dpba_comm_unique_id(uint8_t id[128]) {
+  if (!id) return DPBA_E_INVALID;
+  ncclUniqueId uid;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  if (!nccl_api().ok || nccl_api().GetUniqueId(&uid) != ncclSuccess) return DPBA_E_COMM;
+  memcpy(id, &uid, 128);
+  return DPBA_SUCCESS;
+}
+
+int dpba_comm_init(dpba_handle* h, const uint8_t id[128], int32_t rank, int32_t world) {
+  REQUIRE(h, "null handle");
+  REQUIRE(id && world >= 1 && rank >= 0 && rank < world, "bad communicator arguments");
+  CK(cudaSetDevice(h->cfg.device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  NcclApi& nc = nccl_api();
+  if (!nc.ok) return fail(h, DPBA_E_COMM, "libnccl.so.2 could not be loaded");
+  ncclResult_t r = nc.CommInitRank(&h->comm, world, uid, rank);
+  if (r != ncclSuccess) return fail(h, DPBA_E_COMM, std::string("ncclCommInitRank: ") + nc.GetErrorString(r));
+  h->world = world;
+  h->rank = rank;
+  return DPBA_SUCCESS;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,118 @@
+// Internal device-side data model and kernel launchers of the photometric BA path (sm_100a).
+// Reference data model being replaced: LocalFrame / Landmark / ResidualPoint,
+// src/energy/problems/internal/energy/problems/photometric_bundle_adjustment/local_frame.hpp:173-584.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PBA_MAXF 16
+#define PBA_P 8
+#define PBA_B 8
+#define PBA_CORE 48  // 36 (upper triangle of the 8x8 core) + 8 (core^T r) padded to 48 doubles per ordered pair
+
+// Per ordered pair (reference r, target t) constants, computed in double on the device from the frame
+// state (k_pair_setup) and rounded to fp32.  Replaces the ArrayReprojector members
+// (src/energy/projector/include/energy/projector/camera_reproject.hpp:235-260,369-377) and the per-pair
+// prologue of evaluateJacobians (evaluate_jacobians.hpp:36-66).
+struct PairConst {
+  float A[12];     // reproject_            = K_t [R|t] Kr^-1  at the CURRENT state (eps + step)
+  float M[12];     // transform_unproject_  = [R|t] Kr^-1      at the current state
+  float tr[3];     // translation_ at the current state
+  float M0[12];    // transform_unproject_ at the linearisation point (first_estimate_jacobians.hpp:28-32)
+  float t0[3];     // translation_ at the linearisation point
+  float adj[36];   // Adj(T_t_r)   row-major (rightLogTransformer, se3_motion.hpp:245)
+  float adj0[36];  // Adj(T_t_r0)
+  float s;         // brightness_change_scale at the current state (evaluate_jacobians.hpp:56-57)
+  float s0;        // ... at the linearisation point (first_estimate_jacobians.hpp:36-37)
+  float s0_last;   // s0 towards the LAST target of this reference frame (quirk Q1: corrected_intensities)
+  float b_t;       // target affine shift, current
+  float b_r;       // reference affine shift, current
+  float b_r0;      // reference affine shift at the linearisation point
+  float fx_t, fy_t, cx_t, cy_t;
+  float pad[2];
+};
+
+// blockdiag(Adj^T, 1, s') per pair in double for the final assembly (J_ref = U B^T, J_tgt = -U)
+struct PairAssemble {
+  double adj_fej[36];
+  double adj_cur[36];
+  double s0, s;
+};
+
+struct FrameParams {   // double-precision frame state on the device
+  double T_lin[12];    // world<-agent 3x4 row-major
+  double eps[8];
+  double step[8];
+  double exposure;
+  double ab0[2];
+  double intr[4];
+};
+
+struct WindowDev {
+  int n_frames, W, H, max_pts, hpd_stride;
+  int n_lm[PBA_MAXF];
+  int fixed[PBA_MAXF];
+  int frame_marg[PBA_MAXF];  // LocalFrame::is_marginalized
+  int phys[PBA_MAXF];        // logical slot -> physical storage slot
+  const float4* img[PBA_MAXF];     // {I, dx, dy, 0} per pixel
+  const uint8_t* mask[PBA_MAXF];
+  // landmark SoA, frame f at [phys[f] * max_pts, phys[f] * max_pts + n_lm[f])
+  const float2* uv;
+  float* idepth;
+  float* idepth_step;
+  float* idepth_fej;
+  const float* patch;      // [lm][8]
+  uint8_t* flags;
+  float* inv_hdd;
+  float* b_d;
+  float* hpd;              // [lm][hpd_stride], hpd_stride = 8 * n_frames
+  float* rel_baseline;
+  uint32_t* n_inliers;
+  // per residual (r, t, l) -> ((phys[r] * PBA_MAXF + phys[t]) * max_pts + l)
+  uint8_t* status;
+  uint8_t* cand;
+  float* energy;
+  const PairConst* pairs;          // [PBA_MAXF * PBA_MAXF]
+  const PairAssemble* pairs_asm;
+  // materialised ResidualPoint arrays (reference-surface mode), may be null
+  float* m_r;      // [res][8]
+  float* m_jref;   // [res][8][8]
+  float* m_jtgt;   // [res][8][8]
+  float* m_did;    // [res][8]
+  float* m_w;      // [res]
+};
+
+// reduction buffer layout (doubles), also the multi-GPU exchange buffer:
+//   core  [PBA_MAXF*PBA_MAXF][PBA_CORE]   per ordered pair
+//   Hs    [D*D], bs [D]                   Schur complement (D = 8 n_frames)
+//   scal  [8]: 0 energy, 1 n_valid, 2 state_sq, 3 step_sq
+struct ReduceBuf {
+  double* core;
+  double* Hs;
+  double* bs;
+  double* scal;
+  double* Hp;   // assembled pose-pose H [D*D] (not exchanged)
+  double* bp;   // [D]
+};
+
+namespace pba {
+void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
+void launch_pack_image(const float* src3, float4* dst, int n_px, cudaStream_t s);
+void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s);
+void launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* scal, cudaStream_t s);
+void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s);
+void launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
+                            cudaStream_t s);
+void launch_linearize_from_materialized(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
+void launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
+void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, cudaStream_t s);
+void launch_symmetrise_only(int D, double* Hp, cudaStream_t s);
+void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, double lambda, cudaStream_t s);
+void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s);
+void launch_change_statuses(const WindowDev& w, int accept, cudaStream_t s);
+void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cudaStream_t s);
+void launch_snapshot_fej(const WindowDev& w, cudaStream_t s);
+void launch_apply_point_statuses(const WindowDev& w, float threshold, int min_valid, const float* pair_dist,
+                                 cudaStream_t s);
+int sm_count();
+}  // namespace pba

@@ -1,0 +1,203 @@
+/*
+ * dsopp_cuda_pba.h -- C ABI of the B200-native photometric bundle-adjustment hot path.
+ *
+ * Drop-in boundary for RoadlyInc/DSOPP @ a4af2aa (paths relative to the reference's src/):
+ * the device owns the LocalFrame-equivalent data and runs the data-parallel loops of
+ *   energy/problems/internal/energy/problems/photometric_bundle_adjustment/  ("PBA/" below)
+ * while the host keeps levenberg_marquardt_algorithm::solve, the priors and the 8Nx8N solve.
+ * Every entry point replaces one reference interface, cited beside it.  The C++ adapter that
+ * satisfies the reference's LevenbergMarquardtProblem concept on top of this header is
+ * dsopp_b200/csrc/host/cuda_pba_problem.hpp; INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative DPBA_E_* code; dpba_last_error() gives text.
+ *     Nothing throws, aborts or logs (reference: LOG(ERROR)+return / CHECK abort,
+ *     energy/problems/src/photometric_bundle_adjustment.cpp:66-69,101).
+ *   - the library COPIES everything it is given (LocalFrame copies landmarks/statuses,
+ *     PBA/local_frame.hpp:309-335); host buffers stay owned by the caller.
+ *   - frames live in dense slots 0..N-1 in ascending timestamp order
+ *     (photometric_bundle_adjustment.cpp:101); only slot 0 may be fixed
+ *     (PBA/hessian_block_evaluation.hpp:143); single sensor, C = 1, pinhole + SE3
+ *     (energy/problems/src/eigen_photometric_bundle_adjustment.cpp:64,155).
+ *   - per-frame state block = [tx ty tz rx ry rz a b] (Sophus tangent order + affine brightness),
+ *     matrices are row-major, poses are 3x4 row-major [R|t] world<-agent, doubles.
+ *   - a handle is NOT thread-safe (the tracker is single-threaded around the solver).
+ *   - landmark index == residual index == host landmark order (PBA/evaluate_jacobians.hpp:77).
+ */
+#ifndef DSOPP_CUDA_PBA_H_
+#define DSOPP_CUDA_PBA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPBA_MAX_FRAMES 16 /* steady state is maximum_size+1 = 9 (standart.yaml), 16 with dense.yaml */
+#define DPBA_PATTERN 8     /* common/pattern/include/common/pattern/pattern.hpp:17 */
+#define DPBA_BLOCK 8       /* Motion::DoF + 2, PBA/eigen_photometric_bundle_adjustment_problem.hpp:259 */
+
+/* track/connections/include/track/connections/frame_connection.hpp:19-25 */
+enum { DPBA_OK_STATUS = 0, DPBA_OUTLIER = 1, DPBA_OCCLUDED = 2, DPBA_OOB = 3, DPBA_UNKNOWN = 4 };
+
+/* LocalFrame::Landmark flags, PBA/local_frame.hpp:276-293 */
+enum {
+  DPBA_LM_MARGINALIZED = 1,
+  DPBA_LM_TO_MARGINALIZE = 2,
+  DPBA_LM_OUTLIER = 4,
+  DPBA_LM_ILL_CONDITIONED = 8
+};
+
+enum {
+  DPBA_SUCCESS = 0,
+  DPBA_E_INVALID = -1, /* bad argument / precondition of the reference violated */
+  DPBA_E_CUDA = -2,    /* CUDA runtime error, no CPU fallback exists */
+  DPBA_E_CAPACITY = -3,
+  DPBA_E_STATE = -4, /* call order (e.g. back_substitute before linearize) */
+  DPBA_E_COMM = -5   /* multi-GPU exchange failed */
+};
+
+typedef struct dpba_handle dpba_handle;
+
+typedef struct dpba_config {
+  int32_t max_frames;           /* <= DPBA_MAX_FRAMES */
+  int32_t max_points_per_frame; /* landmarks hosted by one frame ON THIS HANDLE (shard) */
+  int32_t width, height;        /* level-0 image size */
+  int32_t device;               /* CUDA ordinal */
+  int32_t rank, world_size;     /* landmark shard: this handle holds landmarks l with l % world_size == rank */
+} dpba_config;
+
+/* ResidualPoint-shaped view of one (reference, target) pair, the four arrays that
+ * BundleAdjustmentPhotometricCostFunctorAnalytic::Evaluate memcpy's
+ * (energy/problems/internal/energy/problems/cost_functors/bundle_adjustment_photometric_cost_functor_analytic.hpp:46-68)
+ * plus huber_weight / energy / statuses (PBA/local_frame.hpp:173-220).  Any pointer may be NULL. */
+typedef struct dpba_residual_view {
+  int32_t n;                     /* in: capacity (landmarks); out: landmarks written */
+  float* residuals;              /* [n][8] */
+  float* d_reference_state_eps;  /* [n][8][8] row-major, as ResidualPoint stores it */
+  float* d_target_state_eps;     /* [n][8][8] row-major */
+  float* d_idepth;               /* [n][8] */
+  float* huber_weight;           /* [n] */
+  float* energy;                 /* [n] */
+  uint8_t* connection_status;            /* [n] */
+  uint8_t* connection_status_candidate;  /* [n] */
+} dpba_residual_view;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int dpba_create(const dpba_config* cfg, dpba_handle** out);
+int dpba_destroy(dpba_handle* h);
+const char* dpba_last_error(const dpba_handle* h); /* never NULL */
+const char* dpba_version(void);
+/* cudaStream_t all kernels of this handle are launched on (for CUDA-event timing by the caller) */
+void* dpba_stream(dpba_handle* h);
+
+/* ---- window: PhotometricBundleAdjustment::pushFrame / LocalFrame ctor ------------------- */
+/* Appends a frame at slot N (photometric_bundle_adjustment.cpp:98-106, PBA/local_frame.hpp:309-335).
+ * image_I_dx_dy: HxWx3 float, the PixelMap<1> storage {I,dx,dy} interleaved
+ * (features/include/features/camera/pixel_map.hpp:126-131); mask: HxW uchar or NULL (= all valid),
+ * sensors/camera_calibration/include/sensors/camera_calibration/mask/camera_mask.hpp:48-89.
+ * intr = fx, fy, cx, cy of the level-0 pinhole model.  Returns the slot (>= 0) or an error. */
+int dpba_push_frame(dpba_handle* h, int32_t frame_id, const float* image_I_dx_dy, const uint8_t* mask,
+                    const double T_w_agent_lin[12], double exposure_time, const double affine_brightness0[2],
+                    const double intr[4], int32_t fixed);
+/* As dpba_push_frame but from the raw intensity plane (HxW float): {I,dx,dy} is built on the device
+ * with the reference's gradient definition (features/src/calculate_pixelinfo.cpp:340-374). */
+int dpba_push_frame_intensity(dpba_handle* h, int32_t frame_id, const float* image_I, const uint8_t* mask,
+                              const double T_w_agent_lin[12], double exposure_time,
+                              const double affine_brightness0[2], const double intr[4], int32_t fixed);
+/* frames.erase(...) of a marginalised frame (PBA/eigen_photometric_bundle_adjustment_problem.hpp:201-202);
+ * later slots shift down by one. */
+int dpba_remove_frame(dpba_handle* h, int32_t slot);
+int dpba_num_frames(const dpba_handle* h);
+/* relinearizeSystem (photometric_bundle_adjustment.cpp:311-316): new linearisation point / affine0, eps := 0 */
+int dpba_set_frame_linearization(dpba_handle* h, int32_t slot, const double T_w_agent_lin[12],
+                                 const double affine_brightness0[2]);
+int dpba_set_frame_flags(dpba_handle* h, int32_t slot, int32_t fixed, int32_t to_marginalize);
+
+/* Landmarks hosted by `slot` (LocalFrame::active_landmarks, PBA/local_frame.hpp:327-333): replaces all n
+ * landmarks.  proj_xy [n][2], idepth [n], patch [n][8], flags [n] (DPBA_LM_*).  idepth_step := 0. */
+int dpba_set_landmarks(dpba_handle* h, int32_t slot, int32_t n, const float* proj_xy, const float* idepth,
+                       const float* patch, const uint8_t* flags);
+/* LocalFrame::update appends freshly matured landmarks (PBA/local_frame.hpp:498-505) */
+int dpba_append_landmarks(dpba_handle* h, int32_t slot, int32_t n, const float* proj_xy, const float* idepth,
+                          const float* patch, const uint8_t* flags);
+int dpba_set_landmark_flags(dpba_handle* h, int32_t slot, int32_t n, const uint8_t* flags);
+int dpba_num_landmarks(const dpba_handle* h, int32_t slot);
+/* Read back what updateFrame needs (photometric_bundle_adjustment.cpp:223-262).  Any pointer may be NULL. */
+int dpba_get_landmarks(dpba_handle* h, int32_t slot, int32_t n, float* idepth, float* idepth_step,
+                       float* inv_hessian_idepth_idepth, float* b_idepth, uint8_t* flags,
+                       uint32_t* number_of_inlier_residuals, float* relative_baseline);
+/* hessian_poses_idepth_block of the landmarks of `slot`: [n][8N] (PBA/local_frame.hpp:297) */
+int dpba_get_pose_idepth_blocks(dpba_handle* h, int32_t slot, int32_t n, float* out);
+
+/* connection statuses of the residual vector (ref_slot -> tgt_slot), one per host landmark
+ * (ResidualPoint ctor, PBA/local_frame.hpp:212-213: status and candidate both := given) */
+int dpba_set_statuses(dpba_handle* h, int32_t ref_slot, int32_t tgt_slot, int32_t n, const uint8_t* statuses);
+int dpba_get_statuses(dpba_handle* h, int32_t ref_slot, int32_t tgt_slot, int32_t n, uint8_t* statuses,
+                      uint8_t* candidates);
+
+/* state_eps / state_eps_step of all frames, [8N] each (PBA/local_frame.hpp:561-563) */
+int dpba_set_state(dpba_handle* h, const double* state_eps, const double* state_eps_step);
+int dpba_get_state(dpba_handle* h, double* state_eps, double* state_eps_step);
+
+/* ---- the sweeps ------------------------------------------------------------------------ */
+/* firstEstimateJacobians_ (PBA/first_estimate_jacobians.hpp:14-71): freezes the linearisation point used by
+ * the FEJ reprojection Jacobians (idepth snapshot, T_t_r0, brightness scale, corrected intensities). */
+int dpba_first_estimate(dpba_handle* h);
+
+/* evaluateJacobians<..., EVALUATE_JACOBIANS=false, NEW_EVALUATION_POINT=true, APPLY_HUBER_LOSS=huber>
+ * followed by calculateLandmarksEnergy (PBA/evaluate_jacobians.hpp:20-202;
+ * PBA/eigen_photometric_bundle_adjustment_problem.hpp:93-144): residual-only sweep at state_eps+step,
+ * idepth+idepth_step.  energy = sum over non-marginalised landmarks, n_valid = #(energy > 0). */
+int dpba_evaluate(dpba_handle* h, double sigma_huber, int32_t huber, int32_t fej, double* energy,
+                  int32_t* n_valid);
+
+/* evaluateJacobians<..., true, true, huber> materialising every ResidualPoint (reference-surface mode):
+ * residuals, d_reference_state_eps, d_target_state_eps, d_idepth, huber_weight, energy, candidates. */
+int dpba_evaluate_jacobians(dpba_handle* h, double sigma_huber, int32_t huber, int32_t fej);
+int dpba_download_residual_block(dpba_handle* h, int32_t ref_slot, int32_t tgt_slot, dpba_residual_view* view);
+
+/* linearize(): evaluateJacobians<true,true,huber> + evaluateLinearSystemPosePose<for_marginalized> +
+ * evaluateLinearSystemPoseDepthSchurComplement<for_marginalized>
+ * (PBA/eigen_photometric_bundle_adjustment_problem.hpp:322-336; PBA/hessian_block_evaluation.hpp:96-236),
+ * fused: no Jacobian is written to memory.  Outputs are [8N][8N] row-major / [8N] doubles, WITHOUT the priors
+ * (evaluateLinearSystemPrior stays on the host).  With world_size > 1 the outputs are already summed over
+ * ranks.  Also stores per landmark hessian_poses_idepth_block, b_idepth_block, inv_hessian_idepth_idepth,
+ * ill_conditioned. */
+int dpba_linearize(dpba_handle* h, double sigma_huber, int32_t huber, int32_t fej, int32_t for_marginalized,
+                   double* H_pose, double* b_pose, double* H_schur, double* b_schur);
+/* Same result through the reference's three-pass dataflow on the device: K1 materialise, then PosePose and
+ * Schur passes that re-read it.  Exists to cross-check the fused path and to measure the materialising sweep. */
+int dpba_linearize_materialized(dpba_handle* h, double sigma_huber, int32_t huber, int32_t fej,
+                                int32_t for_marginalized, double* H_pose, double* b_pose, double* H_schur,
+                                double* b_schur);
+
+/* calculateIdepths (PBA/hessian_block_evaluation.hpp:238-263): step_pose is the solution of the reduced
+ * system (the caller sets state_eps_step = -step_pose itself, as calculateStep does). */
+int dpba_back_substitute(dpba_handle* h, const double* step_pose, double levenberg_marquardt_lambda);
+
+/* acceptStep / rejectStep (PBA/eigen_photometric_bundle_adjustment_problem.hpp:366-402) for landmarks and
+ * statuses AND the frame state held by the handle.  Norms include frames and landmarks; with
+ * world_size > 1 the landmark part is summed over ranks. */
+int dpba_accept(dpba_handle* h, double* state_squared_norm, double* step_squared_norm);
+int dpba_reject(dpba_handle* h);
+/* changeResidualStatuses(frames, accept) alone (PBA/eigen_photometric_bundle_adjustment_problem.hpp:20-35) */
+int dpba_change_residual_statuses(dpba_handle* h, int32_t accept);
+/* calculateLandmarksEnergy<for_marginalized> over the stored per-residual energies */
+int dpba_landmarks_energy(dpba_handle* h, int32_t for_marginalized, double* energy, int32_t* n_valid);
+
+/* updatePointStatuses (photometric_bundle_adjustment.cpp:322-406): 75-percentile energy + sigma^2/2
+ * threshold, outlier reset, inlier counts, relative baseline, is_outlier. */
+int dpba_update_point_statuses(dpba_handle* h, int32_t minimum_valid_reprojections, double sigma_huber,
+                               double* energy_threshold);
+
+/* ---- multi-GPU (one process per GPU; landmarks sharded, frames replicated) -------------- */
+/* 128-byte NCCL unique id created on rank 0, broadcast by the caller (torch.distributed / MPI / files). */
+int dpba_comm_unique_id(uint8_t id[128]);
+int dpba_comm_init(dpba_handle* h, const uint8_t id[128], int32_t rank, int32_t world_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSOPP_CUDA_PBA_H_ */

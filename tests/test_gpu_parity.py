@@ -1,0 +1,297 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the float64 NumPy oracle on the same inputs.
+
+Tolerances (fp32 device arithmetic vs the float64 oracle; intensities 0..255, f = 400 px):
+  * per-residual r, J, d_idepth, energy : |d| <= RTOL_RES * |x| + ATOL_RES * max|array|
+  * H / b blocks                        : |d| <= RTOL_SYS * max|H|   (fp64 accumulation on the device)
+  * GN step (after the float64 solve)   : rel 1e-4 of the step norm
+  * statuses / candidates / flags       : exact, except residuals whose float64 reprojection lies within
+                                          BORDER_EPS px of the ROI border (counted and reported)
+"""
+import numpy as np
+import pytest
+
+from dsopp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL_RES, ATOL_RES = 2e-4, 2e-5
+RTOL_SYS = 2e-5
+BORDER_EPS = 2e-3
+SIGMA = 20.0
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from dsopp_b200 import capi as c
+    c.load_library()
+    return c
+
+
+def oracle():
+    from oracle import pba_oracle as O
+    return O
+
+
+def close(got, ref, rtol=RTOL_RES, atol_frac=ATOL_RES):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    scale = max(np.abs(ref).max(), 1e-30)
+    bad = np.abs(got - ref) > rtol * np.abs(ref) + atol_frac * scale
+    return not bad.any(), float(np.abs(got - ref).max() / scale)
+
+
+def near_border_mask(O, frames, r, t, eps_px=BORDER_EPS):
+    """Residuals whose float64 reprojection (current or FEJ) has a pattern point within eps of the ROI border."""
+    ref, tgt = frames[r], frames[t]
+    T0, T = O.relative_pose(ref, tgt)
+    out = np.zeros(len(ref.idepth), dtype=bool)
+    for TT, rho in ((T, ref.idepth + ref.idepth_step), (T0, ref.idepth)):
+        tp, _ = O.Reprojector(ref, tgt, TT).values(ref.ref_pattern, rho)
+        with np.errstate(invalid="ignore"):
+            for lim in (4.0, tgt.W - 5.0):
+                out |= (np.abs(tp[..., 0] - lim) < eps_px).any(axis=1)
+            for lim in (4.0, tgt.H - 5.0):
+                out |= (np.abs(tp[..., 1] - lim) < eps_px).any(axis=1)
+            frac = np.abs(tp - np.round(tp))  # mask rounding boundary at .5
+            out |= (np.abs(frac - 0.5) < eps_px).any(axis=(1, 2)) & (tgt.mask.min() == 0)
+    return out
+
+
+def make(win_kw, capi_mod, fej=True, sigma=SIGMA, mutate=None):
+    O = oracle()
+    win = synth.make_window(**win_kw)
+    if mutate:
+        mutate(win)
+    frames = O.frames_from_window(win)
+    h = capi_mod.upload_window(win)
+    if fej:
+        O.first_estimate_jacobians(frames)
+        h.first_estimate()
+    return O, win, frames, h
+
+
+WINDOWS = {
+    "anchor3x200": dict(n_frames=3, points_per_frame=200, seed=0),
+    "w5x300": dict(n_frames=5, points_per_frame=300, seed=1),
+    "ragged": dict(n_frames=4, points_per_frame=257, seed=2),
+}
+
+
+def ragged(win):
+    # ragged landmark counts, one empty frame, non-kOk statuses, flagged landmarks, a mask with holes
+    rng = np.random.default_rng(7)
+    keep = [257, 0, 33, 130]
+    for f, k in zip(win.frames, keep):
+        f.uv, f.idepth, f.idepth_true, f.patch, f.flags = f.uv[:k], f.idepth[:k], f.idepth_true[:k], f.patch[:k], f.flags[:k]
+    for (r, t) in list(win.statuses):
+        st = np.zeros(keep[r], dtype=np.uint8)
+        if keep[r]:
+            st[rng.random(keep[r]) < 0.15] = rng.integers(1, 5)
+        win.statuses[(r, t)] = st
+    win.frames[0].flags[::7] = synth.FLAG_MARGINALIZED
+    win.frames[0].flags[::21] = synth.FLAG_MARGINALIZED | synth.FLAG_TO_MARGINALIZE
+    win.frames[3].idepth[:5] = -1.0  # invalid idepth
+    win.frames[3].idepth[5:8] = 2000.0
+    m = win.frames[2].mask
+    m[100:200, 150:400] = 0
+
+
+@pytest.mark.parametrize("name", list(WINDOWS))
+@pytest.mark.parametrize("fej", [True, False])
+def test_materialised_sweep_matches_oracle(capi, name, fej):
+    O, win, frames, h = make(WINDOWS[name], capi, fej, mutate=ragged if name == "ragged" else None)
+    O.evaluate_jacobians(frames, SIGMA, fej=fej, evaluate_jacobians=True, new_point=True, huber=True)
+    h.evaluate_jacobians(SIGMA, True, fej)
+    n = len(frames)
+    flips, total, worst = 0, 0, {}
+    for r in range(n):
+        for t in range(n):
+            if r == t:
+                continue
+            res = frames[r].residuals[frames[t].id]
+            got = h.download_residual_block(r, t)
+            swept = ~(frames[r].lm_marginalized & ~frames[r].lm_to_marginalize)
+            same = got["cand"] == res.cand
+            nb = near_border_mask(O, frames, r, t)
+            assert (same | nb | ~swept).all(), f"candidate status mismatch away from the border, pair {r}->{t}"
+            flips += int((~same & swept).sum())
+            total += int(swept.sum())
+            ok = same & swept
+            for key, ref in (("r", res.r), ("J_ref", res.J_ref), ("J_tgt", res.J_tgt), ("d_idepth", res.d_idepth),
+                             ("e", res.e)):
+                if ok.any():
+                    good, err = close(got[key][ok], ref[ok])
+                    worst[key] = max(worst.get(key, 0.0), err)
+                    assert good, f"{key} mismatch on pair {r}->{t}: rel-to-max err {err:.3e}"
+            ev = ok & (res.cand == O.K_OK) & (res.status == O.K_OK)
+            if ev.any():
+                assert close(got["w"][ev], res.w[ev])[0]
+    print(f"[{name} fej={fej}] residuals={total} near-border flips={flips} worst rel-to-max errors={worst}")
+    assert flips <= max(2, total // 2000)
+    h.close()
+
+
+@pytest.mark.parametrize("name", list(WINDOWS))
+def test_residual_sweep_energy(capi, name):
+    O, win, frames, h = make(WINDOWS[name], capi, True, mutate=ragged if name == "ragged" else None)
+    O.evaluate_jacobians(frames, SIGMA, fej=True, evaluate_jacobians=False, new_point=True, huber=True)
+    e_ref, n_ref = O.landmarks_energy(frames)
+    e, nv = h.evaluate(SIGMA, True, True)
+    assert abs(nv - n_ref) <= max(2, n_ref // 2000)
+    assert abs(e - e_ref) <= 1e-4 * e_ref + 1e-3 + SIGMA * 30 * abs(nv - n_ref)
+    e2, n2 = h.landmarks_energy(False)
+    assert n2 == nv and abs(e2 - e) <= 1e-6 * abs(e) + 1e-6
+    h.close()
+
+
+@pytest.mark.parametrize("name", list(WINDOWS))
+@pytest.mark.parametrize("fej", [True, False])
+@pytest.mark.parametrize("for_marg", [False, True])
+def test_fused_linearize_matches_oracle(capi, name, fej, for_marg):
+    def mut(win):
+        if name == "ragged":
+            ragged(win)
+        elif for_marg:
+            win.frames[0].flags[:] = synth.FLAG_MARGINALIZED | synth.FLAG_TO_MARGINALIZE
+            win.frames[1].flags[::3] = synth.FLAG_MARGINALIZED | synth.FLAG_TO_MARGINALIZE
+    O, win, frames, h = make(WINDOWS[name], capi, fej, mutate=mut)
+    O.evaluate_jacobians(frames, SIGMA, fej=fej, evaluate_jacobians=True, new_point=True, huber=True)
+    Hp_ref, bp_ref = O.pose_pose(frames, for_marg)
+    Hs_ref, bs_ref = O.schur_complement(frames, for_marg)
+    Hp, bp, Hs, bs = h.linearize(SIGMA, True, fej, for_marg)
+    for got, ref, nm in ((Hp, Hp_ref, "H_pose"), (bp, bp_ref, "b_pose"), (Hs, Hs_ref, "H_schur"), (bs, bs_ref, "b_schur")):
+        scale = max(np.abs(ref).max(), 1e-30)
+        err = np.abs(got - ref).max() / scale
+        print(f"[{name} fej={fej} marg={for_marg}] {nm}: max|d|/max|ref| = {err:.3e}")
+        assert err < RTOL_SYS * (50 if name == "ragged" else 1), nm  # ragged: near-border flips may move whole residuals
+    assert np.allclose(Hp, Hp.T, rtol=0, atol=1e-9 * np.abs(Hp).max())
+    # per-landmark Schur ingredients
+    for i, f in enumerate(frames):
+        if len(f.idepth) == 0:
+            continue
+        lm = h.get_landmarks(i)
+        sel = f.lm_to_marginalize if for_marg else ~f.lm_marginalized
+        ill_ref = f.ill[sel]
+        ill = (lm["flags"][sel] & synth.FLAG_ILL_CONDITIONED) != 0
+        assert (ill == ill_ref).mean() > 0.995
+        good = sel & ~f.ill & ((lm["flags"] & synth.FLAG_ILL_CONDITIONED) == 0)
+        if good.any():
+            hpd = h.get_pose_idepth_blocks(i)
+            assert close(hpd[good], f.Hpd[good], 1e-3, 1e-4)[0]
+            assert close(lm["b_d"][good], f.b_d[good], 1e-3, 1e-4)[0]
+            assert close(lm["inv_hdd"][good], f.inv_hdd[good], 1e-3, 1e-4)[0]
+    h.close()
+
+
+@pytest.mark.parametrize("fej", [True, False])
+def test_fused_equals_three_pass_on_device(capi, fej):
+    O, win, frames, h = make(WINDOWS["w5x300"], capi, fej)
+    a = h.linearize(SIGMA, True, fej, False, materialized=False)
+    b = h.linearize(SIGMA, True, fej, False, materialized=True)
+    for x, y in zip(a, b):
+        assert np.abs(x - y).max() <= 2e-6 * np.abs(y).max()
+    h.close()
+
+
+def run_lm(O, problem, max_it=7):
+    opt = O.LMOptions(max_it, 1e-5, 1e-8, 1e-8, True, 3, 1.0, 1.0)
+    trace = []
+    res = O.lm_solve(problem, opt, trace)
+    return res, trace
+
+
+@pytest.mark.parametrize("name,ab_scale,ab_reg", [("anchor3x200", 0.0, (1e12, 1e8)), ("w5x300", 1.0, (10.0, 1e-2))])
+def test_lm_solve_through_the_c_abi_tracks_the_oracle(capi, name, ab_scale, ab_reg):
+    from dsopp_b200.problem import CudaProblem
+    kw = dict(WINDOWS[name], ab_scale=ab_scale)
+    O, win, frames, h = make(kw, capi, True)
+    meta = [dict(ab0=f.ab0, fixed=f.fixed) for f in win.frames]
+    (e_ref, n_ref, _), tr_ref = run_lm(O, O.Problem(frames, SIGMA, ab_reg=ab_reg))
+    (e, n, _), tr = run_lm(O, CudaProblem(h, meta, SIGMA, ab_reg=ab_reg))
+    assert len(tr) == len(tr_ref)
+    for a, b in zip(tr, tr_ref):
+        assert a["accepted"] == b["accepted"]
+        assert abs(a["n"] - b["n"]) <= 2
+        assert abs(a["energy"] - b["energy"]) <= 2e-4 * abs(b["energy"])
+        sn = np.linalg.norm(b["step"])
+        assert np.linalg.norm(a["step"] - b["step"]) <= 1e-4 * sn + 1e-7, (a["it"], np.linalg.norm(a["step"] - b["step"]), sn)
+    assert abs(e - e_ref) <= 2e-4 * abs(e_ref)
+    eps, _ = h.get_state()
+    eps_ref = O.state_eps_stacked(frames)
+    assert np.abs(eps - eps_ref).max() <= 1e-5 * max(1.0, np.abs(eps_ref).max()) + 2e-6
+    for i, f in enumerate(frames):
+        lm = h.get_landmarks(i)
+        assert np.abs(lm["idepth"] - f.idepth).max() <= 2e-5
+        for j, g in enumerate(frames):
+            if i != j:
+                st, _ = h.get_statuses(i, j)
+                assert (st != f.residuals[g.id].status).sum() <= 1
+    h.close()
+
+
+def test_update_point_statuses(capi):
+    O, win, frames, h = make(WINDOWS["w5x300"], capi, True)
+    O.evaluate_jacobians(frames, SIGMA, fej=True, evaluate_jacobians=False, new_point=True, huber=True)
+    O.change_residual_statuses(frames)
+    h.evaluate(SIGMA, True, True)
+    h.change_residual_statuses(True)
+    thr_ref = O.update_point_statuses(frames, 1, SIGMA)
+    thr = h.update_point_statuses(1, SIGMA)
+    assert abs(thr - thr_ref) <= 1e-4 * thr_ref
+    for i, f in enumerate(frames):
+        lm = h.get_landmarks(i)
+        assert (lm["n_inliers"] != f.n_inliers).sum() <= 2
+        assert (((lm["flags"] & synth.FLAG_OUTLIER) != 0) != f.lm_outlier).sum() <= 1
+        ok = lm["n_inliers"] == f.n_inliers
+        assert np.allclose(lm["rel_baseline"][ok], f.rel_baseline[ok], rtol=1e-4, atol=1e-6)
+    h.close()
+
+
+def test_intensity_upload_builds_the_same_pixel_map(capi):
+    win = synth.make_window(**WINDOWS["anchor3x200"])
+    h1 = capi.upload_window(win)
+    for f in win.frames:
+        f.image = np.ascontiguousarray(f.image[..., 0])
+    h2 = capi.upload_window(win)
+    h1.first_estimate(), h2.first_estimate()
+    a = h1.linearize(SIGMA, True, True, False)
+    b = h2.linearize(SIGMA, True, True, False)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y) or np.abs(x - y).max() <= 1e-12 * np.abs(x).max()
+    h1.close(), h2.close()
+
+
+def test_remove_frame_and_slot_reuse(capi):
+    O = oracle()
+    win = synth.make_window(n_frames=4, points_per_frame=150, seed=4)
+    h = capi.upload_window(win, max_frames=4)
+    h.remove_frame(0)
+    assert h.n_frames == 3
+    win3 = synth.make_window(n_frames=4, points_per_frame=150, seed=4)
+    win3.frames = win3.frames[1:]
+    win3.statuses = {(r - 1, t - 1): v for (r, t), v in win3.statuses.items() if r > 0 and t > 0}
+    h3 = capi.upload_window(win3)
+    for hh in (h, h3):
+        hh.first_estimate()
+    a = h.linearize(SIGMA, True, True, False)
+    b = h3.linearize(SIGMA, True, True, False)
+    for x, y in zip(a, b):
+        assert np.abs(x - y).max() <= 1e-9 * max(np.abs(y).max(), 1e-30)
+    # the freed physical slot is reused by the next push
+    f = win.frames[0]
+    assert h.push_frame(99, f.image, f.mask, f.T_w_lin, f.exposure, f.ab0, f.intr, False) == 3
+    h.close(), h3.close()
+
+
+def test_error_codes(capi):
+    win = synth.make_window(n_frames=2, points_per_frame=10, seed=0)
+    h = capi.upload_window(win, max_frames=2)
+    f = win.frames[0]
+    with pytest.raises(capi.DpbaError):
+        h.push_frame(5, f.image, f.mask, f.T_w_lin, f.exposure, f.ab0, f.intr, False)  # window full
+    with pytest.raises(capi.DpbaError):
+        h.back_substitute(np.zeros(16), 0.0)  # before linearize
+    with pytest.raises(capi.DpbaError):
+        h.set_landmarks(0, np.zeros((11, 2)), np.zeros(11), np.zeros((11, 8)))  # capacity
+    with pytest.raises(capi.DpbaError):
+        h.set_statuses(0, 0, np.zeros(10, np.uint8))  # r == t
+    h.close()
