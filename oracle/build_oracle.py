@@ -1,0 +1,42 @@
+"""Builds oracle/cpu_ref (the C++ restatement used as checker and as the timed CPU baseline).
+
+  oracle/_build/libpba_cpu_ref.so         -O3 -march=x86-64-v3 -ffp-contract=off  (portable, bit-stable predicates)
+  oracle/_build/libpba_cpu_ref_native.so  -O3 -march=native                       (timing; the reference's own flags,
+                                          CMakeLists.txt:28) -- built on the machine that runs the benchmark
+
+The reference itself (oracle/_ref) cannot be built: its path needs Eigen, Sophus, TBB and glog, none of which
+is installed, so there is no recipe for it.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "cpu_ref", "pba_cpu_ref.cpp")
+OUT = os.path.join(HERE, "_build")
+PORTABLE = os.path.join(OUT, "libpba_cpu_ref.so")
+NATIVE = os.path.join(OUT, "libpba_cpu_ref_native.so")
+
+
+def _build(target, flags):
+    os.makedirs(OUT, exist_ok=True)
+    if os.path.exists(target) and os.path.getmtime(target) >= os.path.getmtime(SRC):
+        return target
+    cmd = ["g++", "-std=c++17", "-O3", "-fopenmp", "-fPIC", "-shared", "-Wall"] + flags + ["-o", target, SRC]
+    print("+", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return target
+
+
+def build_portable():
+    return _build(PORTABLE, ["-march=x86-64-v3", "-ffp-contract=off"])
+
+
+def build_native():
+    return _build(NATIVE, ["-march=native"])
+
+
+if __name__ == "__main__":
+    build_portable()
+    if "--native" in sys.argv:
+        build_native()

