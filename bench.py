@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the photometric bundle-adjustment hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one Levenberg-Marquardt solve of the sliding window = GN_ITERS Gauss-Newton iterations, each =
+linearize (residual+Jacobian sweep, H_pp, per-point Schur) + reduced solve + back-substitution + residual-only
+energy sweep + accept (the loop body of levenberg_marquardt_algorithm.hpp:85-114), driven by the C++ host LM
+through the C ABI.  metric = patch-residuals per second per GN iteration = units * GN_ITERS * steps / time.
+
+  value : window resident in HBM when the timed region starts.
+  e2e   : every step additionally re-uploads the whole window (images, masks, landmarks, statuses, state) from
+          pinned host memory through dpba_push_frame / dpba_set_* and reads the result (state, idepths, statuses)
+          back -- conservative: the tracker uploads ONE new keyframe per solve.
+
+Multi-GPU (weak scaling): every rank holds PTS_PER_GPU landmarks per keyframe of a window with
+PTS_PER_GPU * N landmarks per keyframe; frames are replicated; one NCCL allreduce of the packed reduced system
+per linearisation and one of (energy, n) per energy evaluation.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FRAMES = 8
+PTS_PER_GPU = 2000
+GN_ITERS = 7
+SIGMA = 20.0
+AB_REG = (1e12, 1e8)
+FIXED_REG = 1e16
+METRIC = "patch-residuals/sec per GN iter"
+UNIT = "patch-residuals/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_window(world):
+    from dsopp_b200 import synth
+    return synth.make_window(n_frames=N_FRAMES, points_per_frame=PTS_PER_GPU * world, seed=0, ab_scale=0.0)
+
+
+def config_dict(world, extra=None):
+    c = {
+        "workload": f"configs[1]: {N_FRAMES}-keyframe sliding window, {PTS_PER_GPU} active points/KF per GPU, 8-px patch, "
+                    f"640x480 level 0, Huber sigma=20, FEJ, affine a/b per frame, frame 0 fixed",
+        "units_per_gn_iter": N_FRAMES * (N_FRAMES - 1) * PTS_PER_GPU * world,
+        "gn_iters_per_step": GN_ITERS,
+        "lm": "levenberg_marquardt_algorithm::solve, force_accept, min_it=max_it=7, tolerances 0 (fixed work per step)",
+        "parallelism": f"landmarks sharded over {world} GPU(s), frames replicated",
+        "l2": "256 MiB buffer written between timed steps (L2 flush); within a step the 39 MB image set is L2-resident",
+    }
+    if extra:
+        c.update(extra)
+    return c
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the reference's algorithm and dataflow (oracle/cpu_ref: the reference binary cannot be built here --
+    Eigen/Sophus/TBB absent) on this box's host cores, same window, same 7-iteration step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_ref
+    win = build_window(1)
+    cores = os.cpu_count() or 1
+    threads = cores
+    cw = cpu_ref.CpuWindow(win, use_float=False, threads=threads, native=True)
+    cw.first_estimate()
+    units = win.units
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for _ in range(GN_ITERS):
+            cw.gn_iteration(SIGMA, True, 1e-5, AB_REG, FIXED_REG)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = units * GN_ITERS * len(times) / total
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(1, {"parallelism": f"{threads} OpenMP threads on the host"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{len(times)} full steps of {GN_ITERS} GN iterations on the whole window "
+                                   f"({units} patch-residuals), double precision, reference three-pass dataflow"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def pin(a):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t.numpy(), t
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dsopp_b200 import capi, host
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    win = build_window(world)
+    n = win.n_frames
+    shard = [np.arange(rank, len(f.idepth), world) for f in win.frames]
+    units_local = sum(len(s) for s in shard) * (n - 1)
+    units_global = win.units
+    h = capi.upload_window(win, device=local, rank=rank, world_size=world)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    ab0 = np.stack([f.ab0 for f in win.frames])
+    fixed = [int(f.fixed) for f in win.frames]
+    eps0 = np.concatenate([f.state_eps for f in win.frames])
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def solve():
+        return host.lm_solve(h, ab0, fixed, SIGMA, AB_REG, FIXED_REG, max_it=GN_ITERS, min_it=GN_ITERS, ftol=0.0,
+                             ptol=0.0, force_accept=True, lambda0=1e-5)
+
+    def reset_resident():
+        # same starting point for every step (untimed): landmarks + state back to the initial estimate
+        for i, f in enumerate(win.frames):
+            h.set_landmarks(i, f.uv[shard[i]], f.idepth[shard[i]], f.patch[shard[i]], f.flags[shard[i]])
+        for (r, t), st in win.statuses.items():
+            h.set_statuses(r, t, st[shard[r]])
+        h.set_state(eps0, np.zeros_like(eps0))
+
+    def timed(fn, count_launches=False):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = capi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), capi.launch_count() - l0
+
+    # ---- value: resident window ---------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    step_ms, launches, iters_seen = [], 0, []
+    for i in range(args.warmup + args.steps):
+        reset_resident()
+        if i == args.warmup:
+            h.profile_enable(True)
+            sampler.start()
+        ms, nl = timed(lambda: iters_seen.append(solve()[1]))
+        if i >= args.warmup:
+            step_ms.append(ms)
+            launches += nl
+    clocks = sampler.stop()
+    prof = h.profile_read()
+    h.profile_enable(False)
+    assert all(it == GN_ITERS for it in iters_seen), iters_seen
+    t_local = sum(step_ms)
+    t = torch.tensor([t_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = units_global * GN_ITERS * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers in, results out, every step ------------------------------------------------
+    keep = []
+    host_frames = []
+    for i, f in enumerate(win.frames):
+        img, t1 = pin(f.image.astype(np.float32))
+        msk, t2 = pin(f.mask)
+        s = shard[i]
+        uv, t3 = pin(f.uv[s].astype(np.float32))
+        idp, t4 = pin(f.idepth[s].astype(np.float32))
+        pat, t5 = pin(f.patch[s].astype(np.float32))
+        flg, t6 = pin(f.flags[s])
+        keep += [t1, t2, t3, t4, t5, t6]
+        host_frames.append((f, img, msk, uv, idp, pat, flg))
+    host_status = {k: pin(v[shard[k[0]]])[0] for k, v in win.statuses.items()}
+    h2d = sum(x[1].nbytes + x[2].nbytes + x[3].nbytes + x[4].nbytes + x[5].nbytes + x[6].nbytes for x in host_frames)
+    h2d += sum(v.nbytes for v in host_status.values()) + eps0.nbytes * 2
+    d2h_box = [0]
+
+    def e2e_step():
+        for _ in range(h.n_frames):
+            h.remove_frame(0)
+        for (f, img, msk, uv, idp, pat, flg) in host_frames:
+            h.push_frame(f.frame_id, img, msk, f.T_w_lin, f.exposure, f.ab0, f.intr, f.fixed)
+        for i, (f, img, msk, uv, idp, pat, flg) in enumerate(host_frames):
+            h.set_landmarks(i, uv, idp, pat, flg)
+        for (r, tt), st in host_status.items():
+            h.set_statuses(r, tt, st)
+        h.set_state(eps0, np.zeros_like(eps0))
+        solve()
+        nbytes = 0
+        eps, step = h.get_state()
+        nbytes += eps.nbytes + step.nbytes
+        for i in range(n):
+            lm = h.get_landmarks(i)
+            nbytes += sum(v.nbytes for v in lm.values())
+        for (r, tt) in host_status:
+            st, cd = h.get_statuses(r, tt)
+            nbytes += st.nbytes + cd.nbytes
+        d2h_box[0] = nbytes
+
+    e2e_ms = []
+    for i in range(args.warmup + args.steps):
+        ms, _ = timed(e2e_step)
+        if i >= args.warmup:
+            e2e_ms.append(ms)
+    t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = units_global * GN_ITERS * args.steps / (float(t.item()) * 1e-3)
+
+    # ---- materialising sweep (K1, reference-surface mode) timed alone with an L2 flush before each launch
+    sweep = None
+    if rank == 0:
+        reset_resident()
+        h.first_estimate()
+        h.profile_enable(True)
+        for i in range(3 + 10):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            if i == 3:
+                h.profile_enable(True)
+            h.evaluate_jacobians(SIGMA, True, True)
+        ms, cnt = h.profile_read()["materialise_sweep"]
+        h.profile_enable(False)
+        sweep = ms / max(cnt, 1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    W, H = win.width, win.height
+    D = 8 * n
+    img_bytes = 12 * n * W * H
+    fused_ms, fused_n = prof["linearize_fused"]
+    fused_avg = fused_ms / max(fused_n, 1)
+    fused_bytes = 51 * units_local + img_bytes + 2 * (D * D + D) * 8
+    achieved = fused_bytes / (fused_avg * 1e-3) / 1e9 if fused_avg > 0 else 0.0
+    roofline = {"kernel": "k_linearize_fused (K1+K3+K4a, nothing materialised)", "bound": "hbm",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": None, "peak_source": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+                "algorithmic_bytes_per_launch": fused_bytes, "avg_launch_ms": fused_avg, "launches_timed": fused_n,
+                "note": "fused linearise is bound by fp32 issue + L2 gathers, not HBM (SURVEY 8d: ~90 FLOP/B); "
+                        "see roofline_sweep for the HBM-bound materialising sweep the 60% target is stated on"}
+    sweep_bytes = 595 * units_local + img_bytes
+    sweep_ach = sweep_bytes / (sweep * 1e-3) / 1e9 if sweep else 0.0
+    roofline_sweep = {"kernel": "k_materialise_sweep (K1, reference-surface mode, 595 B/unit)", "bound": "hbm",
+                      "achieved": sweep_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                      "frac": sweep_ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": sweep_bytes,
+                      "avg_launch_ms": sweep, "timing": "alone, L2 flushed before each launch, 10 launches"}
+    kernel_ms = {k: {"ms_total": v[0], "launches": v[1]} for k, v in prof.items() if v[1]}
+
+    # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            from oracle import cpu_ref
+            from dsopp_b200 import synth
+            cwin = synth.make_window(n_frames=N_FRAMES, points_per_frame=PTS_PER_GPU, seed=0, ab_scale=0.0)
+            threads = max(1, min(os.cpu_count() or 1, 8) - 1)  # TBB cap of the reference, dsopp_main.cpp:114-117
+            cw = cpu_ref.CpuWindow(cwin, use_float=False, threads=threads, native=True)
+            cw.first_estimate()
+            ts, t_begin = [], time.perf_counter()
+            for i in range(2 + 40):
+                e, tm, _ = cw.gn_iteration(SIGMA, True, 1e-5, AB_REG, FIXED_REG)
+                if i >= 2:
+                    ts.append(tm.copy())
+                if time.perf_counter() - t_begin > 20 and len(ts) >= 5:
+                    break
+            ts = np.array(ts)
+            med = np.median(ts, axis=0)
+            cpu = {"value": cwin.units / med[5], "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{len(ts)} GN iterations of the same {cwin.units}-unit window, double precision, "
+                             f"reference three-pass dataflow (oracle/cpu_ref, -O3 -march=native), median",
+                   "phase_ms": {"sweep_K1": 1e3 * med[0], "posepose_K3": 1e3 * med[1], "schur_K4": 1e3 * med[2],
+                                "solve_K5": 1e3 * med[3], "energy_K2": 1e3 * med[4], "iteration": 1e3 * med[5]},
+                   "host_cores_total": os.cpu_count()}
+        except Exception as ex:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_box[0]),
+                "ms_per_step": sum(e2e_ms) / len(e2e_ms),
+                "path": "dpba_remove_frame/push_frame/set_landmarks/set_statuses/set_state from pinned host buffers, "
+                        "C++ levenberg_marquardt_algorithm::solve over the C ABI, dpba_get_* readback"},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_sweep": roofline_sweep, "kernel_ms": kernel_ms,
+        "cpu_baseline": cpu,
+        "us_per_gn_iter": 1e3 * total_ms / args.steps / GN_ITERS,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

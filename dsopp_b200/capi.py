@@ -87,6 +87,9 @@ SIGNATURES = {
     "dpba_change_residual_statuses": (C.c_int, [_P, _I]),
     "dpba_landmarks_energy": (C.c_int, [_P, _I, C.POINTER(_D), C.POINTER(_I)]),
     "dpba_update_point_statuses": (C.c_int, [_P, _I, _D, C.POINTER(_D)]),
+    "dpba_launch_count": (C.c_int64, []),
+    "dpba_profile_enable": (C.c_int, [_P, _I]),
+    "dpba_profile_read": (C.c_int, [_P, _P, _P]),
     "dpba_comm_unique_id": (C.c_int, [_P]),
     "dpba_comm_init": (C.c_int, [_P, _P, _I, _I]),
 }
@@ -291,9 +294,23 @@ class Handle:
         self._ck(self.lib.dpba_update_point_statuses(self.h, min_valid, sigma, C.byref(t)))
         return t.value
 
+    PROFILE_KINDS = ("linearize_fused", "schur", "residual_sweep", "materialise_sweep", "assemble", "back_substitute")
+
+    def profile_enable(self, on=True):
+        self._ck(self.lib.dpba_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        ms, n = np.zeros(6), np.zeros(6, np.int32)
+        self._ck(self.lib.dpba_profile_read(self.h, _ptr(ms), _ptr(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.PROFILE_KINDS)}
+
     def comm_init(self, uid: bytes, rank, world):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._ck(self.lib.dpba_comm_init(self.h, C.cast(buf, C.c_void_p), rank, world))
+
+
+def launch_count() -> int:
+    return int(load_library().dpba_launch_count())
 
 
 def comm_unique_id() -> bytes:

@@ -1,0 +1,235 @@
+// Flat C shim over the C++ host side (CudaPhotometricBundleAdjustment, the LM driver and NormalLinearSystem) so
+// that pytest / bench.py can drive exactly the code a C++ caller would link.  Not part of the drop-in boundary:
+// that is include/dsopp_cuda_pba.h.
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "cuda_photometric_bundle_adjustment.hpp"
+
+using namespace dsopp_b200;
+
+namespace {
+thread_local std::string g_err;
+struct Solver {
+  std::unique_ptr<CudaPhotometricBundleAdjustment> pba;
+};
+
+KeyframeView make_view(int id, long long ts, const double* T, double exposure, const double* ab, const double* intr,
+                       const float* image, const uint8_t* mask, int is_marg, int n, const float* proj,
+                       const float* idepth, const float* patch, const uint8_t* flags, int n_other,
+                       const int* other_ids, const uint8_t* ref_statuses, const uint8_t* tgt_statuses,
+                       const int* tgt_counts) {
+  KeyframeView v;
+  v.keyframe_id = id;
+  v.timestamp = ts;
+  std::memcpy(v.t_world_agent, T, sizeof(v.t_world_agent));
+  v.exposure_time = exposure;
+  v.affine_brightness[0] = ab[0];
+  v.affine_brightness[1] = ab[1];
+  std::memcpy(v.intrinsics, intr, sizeof(v.intrinsics));
+  v.image_I_dx_dy = image;
+  v.mask = mask;
+  v.is_marginalized = is_marg != 0;
+  v.n_landmarks = n;
+  v.projections = proj;
+  v.idepths = idepth;
+  v.patches = patch;
+  v.landmark_flags = flags;
+  size_t off = 0;
+  for (int i = 0; i < n_other; ++i) {
+    if (ref_statuses) v.statuses_as_reference[other_ids[i]].assign(ref_statuses + (size_t)i * n, ref_statuses + (size_t)(i + 1) * n);
+    if (tgt_statuses && tgt_counts) {
+      v.statuses_as_target[other_ids[i]].assign(tgt_statuses + off, tgt_statuses + off + tgt_counts[i]);
+      off += tgt_counts[i];
+    }
+  }
+  return v;
+}
+}  // namespace
+
+#define GUARD(...)                  \
+  try {                             \
+    __VA_ARGS__;                    \
+  } catch (const DpbaFailure& e) {  \
+    g_err = e.what();               \
+    return e.code;                  \
+  } catch (const std::exception& e) { \
+    g_err = e.what();               \
+    return -100;                    \
+  }
+
+extern "C" {
+
+__attribute__((visibility("default"))) const char* dpbah_last_error() { return g_err.c_str(); }
+
+__attribute__((visibility("default"))) void* dpbah_create(int width, int height, int max_frames, int max_points,
+                                                         int device, int estimate_uncertainty, int force_accept,
+                                                         int max_iterations, int min_iterations, double radius,
+                                                         double ftol, double ptol, double ab_reg0, double ab_reg1,
+                                                         double fixed_reg, double sigma) {
+  try {
+    TrustRegionPhotometricBundleAdjustmentOptions o;
+    o.max_iterations = (size_t)max_iterations;
+    o.min_iterations = (size_t)min_iterations;
+    o.initial_trust_region_radius = radius;
+    o.function_tolerance = ftol;
+    o.parameter_tolerance = ptol;
+    o.affine_brightness_regularizer[0] = ab_reg0;
+    o.affine_brightness_regularizer[1] = ab_reg1;
+    o.fixed_state_regularizer = fixed_reg;
+    o.sigma_huber_loss = sigma;
+    auto* s = new Solver();
+    s->pba = std::make_unique<CudaPhotometricBundleAdjustment>(o, estimate_uncertainty != 0, force_accept != 0, width,
+                                                               height, max_frames, max_points, device);
+    return s;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+__attribute__((visibility("default"))) void dpbah_destroy(void* s) { delete (Solver*)s; }
+
+__attribute__((visibility("default"))) void* dpbah_handle(void* s) { return ((Solver*)s)->pba->handle(); }
+
+__attribute__((visibility("default"))) int dpbah_push_frame(
+    void* s, int id, long long ts, const double* T, double exposure, const double* ab, const double* intr,
+    const float* image, const uint8_t* mask, int is_marg, int n, const float* proj, const float* idepth,
+    const float* patch, const uint8_t* flags, int fixed, int n_other, const int* other_ids,
+    const uint8_t* ref_statuses, const uint8_t* tgt_statuses, const int* tgt_counts) {
+  GUARD(((Solver*)s)->pba->pushFrame(
+      make_view(id, ts, T, exposure, ab, intr, image, mask, is_marg, n, proj, idepth, patch, flags, n_other, other_ids,
+                ref_statuses, tgt_statuses, tgt_counts),
+      0, fixed ? FrameParameterization::kFixed : FrameParameterization::kFree));
+  return 0;
+}
+
+__attribute__((visibility("default"))) int dpbah_update_local_frame(
+    void* s, int id, long long ts, const double* T, double exposure, const double* ab, const double* intr,
+    int is_marg, int n, const float* proj, const float* idepth, const float* patch, const uint8_t* flags, int n_other,
+    const int* other_ids, const uint8_t* ref_statuses, const uint8_t* tgt_statuses, const int* tgt_counts) {
+  GUARD(((Solver*)s)->pba->updateLocalFrame(make_view(id, ts, T, exposure, ab, intr, nullptr, nullptr, is_marg, n, proj,
+                                                      idepth, patch, flags, n_other, other_ids, ref_statuses,
+                                                      tgt_statuses, tgt_counts)));
+  return 0;
+}
+
+__attribute__((visibility("default"))) int dpbah_solve(void* s, double* energy, int* iterations) {
+  GUARD({
+    auto& p = *((Solver*)s)->pba;
+    const double e = p.solve(1);
+    if (energy) *energy = e;
+    if (iterations) *iterations = (int)p.lastIterations();
+  });
+  return 0;
+}
+
+__attribute__((visibility("default"))) int dpbah_num_frames(void* s) { return (int)((Solver*)s)->pba->frames().size(); }
+
+__attribute__((visibility("default"))) int dpbah_frame_ids(void* s, int* ids) {
+  const auto& f = ((Solver*)s)->pba->frames();
+  for (size_t i = 0; i < f.size(); ++i) ids[i] = f[i].id;
+  return (int)f.size();
+}
+
+__attribute__((visibility("default"))) int dpbah_update_frame(void* s, long long ts, double* T, double* ab, int n,
+                                                             float* idepth, float* variance, float* baseline,
+                                                             uint8_t* outlier, uint32_t* inliers) {
+  GUARD({
+    LandmarkResult r;
+    std::map<int, std::vector<uint8_t>> st;
+    ((Solver*)s)->pba->updateFrame(ts, T, ab, r, st);
+    const int m = std::min<int>(n, (int)r.idepth.size());
+    for (int l = 0; l < m; ++l) {
+      if (idepth) idepth[l] = r.idepth[l];
+      if (variance) variance[l] = r.idepth_variance[l];
+      if (baseline) baseline[l] = r.relative_baseline[l];
+      if (outlier) outlier[l] = r.is_outlier[l];
+      if (inliers) inliers[l] = r.number_of_inlier_residuals[l];
+    }
+  });
+  return 0;
+}
+
+__attribute__((visibility("default"))) int dpbah_marginalized_system(void* s, double* H, double* b, double* energy) {
+  const auto& p = *((Solver*)s)->pba;
+  const auto& m = p.systemMarginalized();
+  if (H) std::memcpy(H, m.H.a.data(), m.H.a.size() * sizeof(double));
+  if (b) std::memcpy(b, m.b.data(), m.b.size() * sizeof(double));
+  if (energy) *energy = p.energyMarginalized();
+  return m.size();
+}
+
+__attribute__((visibility("default"))) int dpbah_covariance(void* s, int ref_id, int tgt_id, double* out36) {
+  const auto& c = ((Solver*)s)->pba->covariances();
+  auto it = c.find({ref_id, tgt_id});
+  if (it == c.end()) return -1;
+  std::memcpy(out36, it->second.data(), 36 * sizeof(double));
+  return 0;
+}
+
+// levenberg_marquardt_algorithm::solve over a window that was uploaded through the C ABI directly.
+// trace (optional): per loop body [accepted, energy, n_valid, step(8N)...], row stride 3 + 8N.
+__attribute__((visibility("default"))) int dpbah_lm_solve(dpba_handle* h, int n_frames, const double* ab0,
+                                                         const int* fixed, double sigma, double ab_reg0,
+                                                         double ab_reg1, double fixed_reg, int max_it, int min_it,
+                                                         double ftol, double ptol, int force_accept, double lambda0,
+                                                         double decrease, double increase, double* energy,
+                                                         int* iterations) {
+  GUARD({
+    namespace lm = levenberg_marquardt_algorithm;
+    std::vector<FrameMeta> frames(n_frames);
+    for (int i = 0; i < n_frames; ++i) {
+      frames[i].id = i;
+      frames[i].fixed = fixed[i] != 0;
+      frames[i].affine_brightness0[0] = ab0[2 * i];
+      frames[i].affine_brightness0[1] = ab0[2 * i + 1];
+    }
+    const double reg[2] = {ab_reg0, ab_reg1};
+    NormalLinearSystem marg(kBlockSize * n_frames);
+    CudaPhotometricBundleAdjustmentProblem problem(h, frames, sigma, marg, 0.0, reg, fixed_reg, true);
+    lm::Options o;
+    o.max_num_iterations = (size_t)max_it;
+    o.min_num_iterations = (size_t)min_it;
+    o.function_tolerance = ftol;
+    o.parameter_tolerance = ptol;
+    o.force_accept = force_accept != 0;
+    o.initial_levenberg_marquardt_regularizer = lambda0;
+    o.levenberg_marquardt_regularizer_decrease_on_accept = decrease;
+    o.levenberg_marquardt_regularizer_increase_on_reject = increase;
+    dpba_check(h, dpba_first_estimate(h));
+    const lm::Result r = lm::solve(problem, o);
+    if (energy) *energy = r.energy;
+    if (iterations) *iterations = (int)r.iterations;
+  });
+  return 0;
+}
+
+__attribute__((visibility("default"))) void dpbah_normal_solve(int n, const double* H, const double* b, double* x) {
+  NormalLinearSystem s(n);
+  std::memcpy(s.H.a.data(), H, (size_t)n * n * sizeof(double));
+  std::memcpy(s.b.data(), b, n * sizeof(double));
+  const dense::Vec r = s.solve();
+  std::memcpy(x, r.data(), n * sizeof(double));
+}
+
+__attribute__((visibility("default"))) int dpbah_reduce_system(int n, double* H, double* b, int n_elim, const int* elim) {
+  NormalLinearSystem s(n);
+  std::memcpy(s.H.a.data(), H, (size_t)n * n * sizeof(double));
+  std::memcpy(s.b.data(), b, n * sizeof(double));
+  s.reduce_system(std::vector<int>(elim, elim + n_elim));
+  std::memcpy(H, s.H.a.data(), s.H.a.size() * sizeof(double));
+  std::memcpy(b, s.b.data(), s.b.size() * sizeof(double));
+  return s.size();
+}
+
+__attribute__((visibility("default"))) void dpbah_sym_pinv(int n, const double* A, int n_null, double* out) {
+  dense::Mat M(n, n);
+  std::memcpy(M.a.data(), A, (size_t)n * n * sizeof(double));
+  const dense::Mat P = dense::sym_pinv(M, n_null);
+  std::memcpy(out, P.a.data(), (size_t)n * n * sizeof(double));
+}
+
+}  // extern "C"

@@ -94,6 +94,13 @@ struct dpba_handle {
   int lin_frames = 0;
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
+  // per-kernel CUDA-event profiling (dpba_profile_*)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;           // pairs: [2i] start, [2i+1] stop
+  std::vector<int> ev_kind;                   // kind of pair i
+  size_t ev_used = 0;
+  double prof_ms[DPBA_PROFILE_KINDS] = {};
+  int prof_n[DPBA_PROFILE_KINDS] = {};
 };
 
 namespace {
@@ -125,6 +132,41 @@ int fail(dpba_handle* h, int code, const std::string& msg) {
   do {                                                      \
     if (!(cond)) return fail(h, DPBA_E_INVALID, (msg));     \
   } while (0)
+
+// RAII scope that brackets one kernel launch with events on the handle's stream when profiling is on
+struct ProfScope {
+  dpba_handle* h;
+  size_t idx = (size_t)-1;
+  ProfScope(dpba_handle* h_, int kind) : h(h_) {
+    if (!h->profiling) return;
+    if (h->ev_used * 2 + 2 > h->ev_pool.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      h->ev_pool.push_back(a);
+      h->ev_pool.push_back(b);
+      h->ev_kind.push_back(kind);
+    }
+    idx = h->ev_used++;
+    h->ev_kind[idx] = kind;
+    cudaEventRecord(h->ev_pool[2 * idx], h->stream);
+  }
+  ~ProfScope() {
+    if (idx != (size_t)-1) cudaEventRecord(h->ev_pool[2 * idx + 1], h->stream);
+  }
+};
+
+void profile_collect(dpba_handle* h) {
+  if (!h->ev_used) return;
+  cudaStreamSynchronize(h->stream);
+  for (size_t i = 0; i < h->ev_used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]) == cudaSuccess) {
+      h->prof_ms[h->ev_kind[i]] += ms;
+      h->prof_n[h->ev_kind[i]] += 1;
+    }
+  }
+  h->ev_used = 0;
+}
 
 ReduceBuf redbuf(dpba_handle* h) {
   ReduceBuf rb;
@@ -273,8 +315,16 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
   if (phys < 0) return fail(h, DPBA_E_CAPACITY, "no free frame slot");
   const int W = h->cfg.width, H = h->cfg.height;
   const size_t npx = (size_t)W * H;
-  memcpy(h->stage_h, image, npx * channels * sizeof(float));
-  CK(cudaMemcpyAsync(h->stage, h->stage_h, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  // page-locked caller buffers are DMA'd directly; pageable ones go through the handle's pinned staging buffer
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const float* src = image;
+  if (!pinned) {
+    memcpy(h->stage_h, image, npx * channels * sizeof(float));
+    src = h->stage_h;
+  }
+  CK(cudaMemcpyAsync(h->stage, src, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   if (channels == 3) pba::launch_pack_image(h->stage, h->img[phys], (int)npx, h->stream);
   else pba::launch_pixelinfo(h->stage, h->img[phys], W, H, h->stream);
   CK(cudaGetLastError());
@@ -412,6 +462,7 @@ int dpba_destroy(dpba_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) nccl_api().CommDestroy(h->comm);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (int p = 0; p < PBA_MAXF; ++p) {
     cudaFree(h->img[p]);
     cudaFree(h->mask[p]);
@@ -605,7 +656,10 @@ int dpba_evaluate(dpba_handle* h, double sigma, int32_t huber, int32_t fej, doub
   ReduceBuf rb = redbuf(h);
   CK(cudaMemsetAsync(rb.scal, 0, 8 * sizeof(double), h->stream));
   WindowDev w = make_window(h);
-  pba::launch_residual_sweep(w, (float)sigma, huber, fej, rb.scal, h->stream);
+  {
+    ProfScope ps(h, 2);
+    pba::launch_residual_sweep(w, (float)sigma, huber, fej, rb.scal, h->stream);
+  }
   CK(cudaGetLastError());
   rc = exchange(h, OFF_SCAL, 8);
   if (rc) return rc;
@@ -625,7 +679,10 @@ int dpba_evaluate_jacobians(dpba_handle* h, double sigma, int32_t huber, int32_t
   rc = sync_pairs(h);
   if (rc) return rc;
   WindowDev w = make_window(h);
-  pba::launch_materialise_sweep(w, (float)sigma, huber, fej, h->stream);
+  {
+    ProfScope ps(h, 3);
+    pba::launch_materialise_sweep(w, (float)sigma, huber, fej, h->stream);
+  }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return DPBA_SUCCESS;
@@ -669,14 +726,26 @@ static int linearize_impl(dpba_handle* h, double sigma, int32_t huber, int32_t f
   CK(cudaMemsetAsync(h->red, 0, N_RED * sizeof(double), h->stream));
   WindowDev w = make_window(h);
   if (fused) {
-    pba::launch_linearize_fused(w, (float)sigma, huber, fej, for_marg, rb, h->stream);
+    {
+      ProfScope ps(h, 0);
+      pba::launch_linearize_fused(w, (float)sigma, huber, fej, for_marg, rb, h->stream);
+    }
     CK(cudaGetLastError());
-    pba::launch_schur(w, for_marg, rb, h->stream);
+    {
+      ProfScope ps(h, 1);
+      pba::launch_schur(w, for_marg, rb, h->stream);
+    }
     CK(cudaGetLastError());
     if ((rc = exchange(h, OFF_CORE, N_EXCHANGE))) return rc;
-    pba::launch_assemble(w, fej, rb, h->stream);
+    {
+      ProfScope ps(h, 4);
+      pba::launch_assemble(w, fej, rb, h->stream);
+    }
   } else {
-    pba::launch_materialise_sweep(w, (float)sigma, huber, fej, h->stream);
+    {
+      ProfScope ps(h, 3);
+      pba::launch_materialise_sweep(w, (float)sigma, huber, fej, h->stream);
+    }
     CK(cudaGetLastError());
     pba::launch_linearize_from_materialized(w, for_marg, rb, h->stream);
     CK(cudaGetLastError());
@@ -719,7 +788,10 @@ int dpba_back_substitute(dpba_handle* h, const double* step_pose, double lambda)
   memcpy(h->red_h, step_pose, D * sizeof(double));  // pinned staging
   CK(cudaMemcpyAsync(h->step_dev, h->red_h, D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   WindowDev w = make_window(h);
-  pba::launch_back_substitute(w, h->step_dev, lambda, h->stream);
+  {
+    ProfScope ps(h, 5);
+    pba::launch_back_substitute(w, h->step_dev, lambda, h->stream);
+  }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return DPBA_SUCCESS;
@@ -833,6 +905,29 @@ int dpba_update_point_statuses(dpba_handle* h, int32_t min_valid, double sigma, 
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   if (thr_out) *thr_out = thr;
+  return DPBA_SUCCESS;
+}
+
+int64_t dpba_launch_count(void) { return (int64_t)pba::launch_count(); }
+
+int dpba_profile_enable(dpba_handle* h, int32_t on) {
+  REQUIRE(h, "null handle");
+  profile_collect(h);
+  h->profiling = on != 0;
+  for (int k = 0; k < DPBA_PROFILE_KINDS; ++k) {
+    h->prof_ms[k] = 0;
+    h->prof_n[k] = 0;
+  }
+  return DPBA_SUCCESS;
+}
+
+int dpba_profile_read(dpba_handle* h, double ms[DPBA_PROFILE_KINDS], int32_t launches[DPBA_PROFILE_KINDS]) {
+  REQUIRE(h, "null handle");
+  profile_collect(h);
+  for (int k = 0; k < DPBA_PROFILE_KINDS; ++k) {
+    if (ms) ms[k] = h->prof_ms[k];
+    if (launches) launches[k] = h->prof_n[k];
+  }
   return DPBA_SUCCESS;
 }
 

@@ -115,4 +115,5 @@ void launch_snapshot_fej(const WindowDev& w, cudaStream_t s);
 void launch_apply_point_statuses(const WindowDev& w, float threshold, int min_valid, const float* pair_dist,
                                  cudaStream_t s);
 int sm_count();
+long long launch_count();
 }  // namespace pba

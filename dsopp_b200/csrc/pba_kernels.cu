@@ -18,6 +18,8 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "pba_internal.h"
 
 namespace {
@@ -1121,6 +1123,9 @@ int max_landmarks(const WindowDev& w) {
 
 namespace pba {
 
+std::atomic<long long> g_launches{0};
+long long launch_count() { return g_launches.load(); }
+
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -1133,15 +1138,18 @@ int sm_count() {
 }
 
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s) {
+  ++g_launches;
   k_pair_setup<<<(n_frames * n_frames + 63) / 64, 64, 0, s>>>(frames, n_frames, pairs, pasm);
 }
 
 void launch_pack_image(const float* src3, float4* dst, int n_px, cudaStream_t s) {
+  ++g_launches;
   k_pack_image<<<(n_px + 255) / 256, 256, 0, s>>>(src3, dst, n_px);
 }
 
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s) {
   dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+  ++g_launches;
   k_pixelinfo<<<g, b, 0, s>>>(I, dst, W, H);
 }
 
@@ -1149,6 +1157,7 @@ void launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, 
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return;
   dim3 g((m + 31) / 32, w.n_frames * (w.n_frames - 1));
+  ++g_launches;
   if (fej) k_residual_sweep<true><<<g, 256, 0, s>>>(w, sigma, huber, scal);
   else k_residual_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber, scal);
 }
@@ -1157,6 +1166,7 @@ void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fe
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return;
   dim3 g((m + 31) / 32, w.n_frames * (w.n_frames - 1));
+  ++g_launches;
   if (fej) k_materialise_sweep<true><<<g, 256, 0, s>>>(w, sigma, huber);
   else k_materialise_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber);
 }
@@ -1174,9 +1184,11 @@ void launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej,
   const int threads = 32 * (N - 1);
   if (fej) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_linearize_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ++g_launches;
     k_linearize_fused<true><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, rb.core);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_linearize_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ++g_launches;
     k_linearize_fused<false><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, rb.core);
   }
 }
@@ -1187,8 +1199,10 @@ void launch_linearize_from_materialized(const WindowDev& w, int for_marg, Reduce
   const int N = w.n_frames;
   const int chunk = 64;
   dim3 g((m + chunk - 1) / chunk, N * (N - 1));
+  ++g_launches;
   k_posepose_from_materialized<<<g, 224, 0, s>>>(w, for_marg, chunk, rb.Hp, rb.bp);
   dim3 g2(m, N);
+  ++g_launches;
   k_schur_prep_from_materialized<<<g2, 128, 0, s>>>(w, for_marg);
 }
 
@@ -1203,17 +1217,21 @@ void launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s
   const size_t smem = (size_t)(2 * SCHUR_TL * D + SCHUR_TL) * sizeof(float);
   const int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ++g_launches;
   k_schur<<<grid, threads, smem, s>>>(w, for_marg, rb.Hs, rb.bs);
 }
 
 void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, cudaStream_t s) {
   const int N = w.n_frames, D = 8 * N;
   if (N < 2) return;
+  ++g_launches;
   k_assemble<<<N * (N - 1), 64, 0, s>>>(w, fej, rb.core, rb.Hp, rb.bp);
+  ++g_launches;
   k_symmetrise<<<(D * D + 255) / 256, 256, 0, s>>>(D, rb.Hp);
 }
 
 void launch_symmetrise_only(int D, double* Hp, cudaStream_t s) {
+  ++g_launches;
   k_symmetrise<<<(D * D + 255) / 256, 256, 0, s>>>(D, Hp);
 }
 
@@ -1221,6 +1239,7 @@ void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, dou
   const int m = max_landmarks(w);
   if (m == 0) return;
   dim3 g((m + 31) / 32, w.n_frames);
+  ++g_launches;
   k_back_substitute<<<g, 256, 0, s>>>(w, step_pose_dev, (float)(1.0 / (1.0 + lambda)));
 }
 
@@ -1228,6 +1247,7 @@ void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s)
   const int m = max_landmarks(w);
   if (m == 0) return;
   dim3 g((m + 255) / 256, w.n_frames);
+  ++g_launches;
   k_accept_landmarks<<<g, 256, 0, s>>>(w, accept, scal);
 }
 
@@ -1235,6 +1255,7 @@ void launch_change_statuses(const WindowDev& w, int accept, cudaStream_t s) {
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return;
   dim3 g((m + 255) / 256, w.n_frames * (w.n_frames - 1));
+  ++g_launches;
   k_change_statuses<<<g, 256, 0, s>>>(w, accept);
 }
 
@@ -1242,6 +1263,7 @@ void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cud
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return;
   dim3 g((m + 255) / 256, w.n_frames * (w.n_frames - 1));
+  ++g_launches;
   k_landmarks_energy<<<g, 256, 0, s>>>(w, for_marg, scal);
 }
 
@@ -1249,6 +1271,7 @@ void launch_snapshot_fej(const WindowDev& w, cudaStream_t s) {
   const int m = max_landmarks(w);
   if (m == 0) return;
   dim3 g((m + 255) / 256, w.n_frames);
+  ++g_launches;
   k_snapshot_fej<<<g, 256, 0, s>>>(w);
 }
 
@@ -1257,6 +1280,7 @@ void launch_apply_point_statuses(const WindowDev& w, float threshold, int min_va
   const int m = max_landmarks(w);
   if (m == 0) return;
   dim3 g((m + 255) / 256, w.n_frames);
+  ++g_launches;
   k_apply_point_statuses<<<g, 256, 0, s>>>(w, threshold, min_valid, pair_dist);
 }
 

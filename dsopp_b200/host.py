@@ -1,0 +1,180 @@
+"""ctypes binding of the C++ host side (libdsopp_pba_host.so): CudaPhotometricBundleAdjustment, the LM driver and
+NormalLinearSystem.  Test / bench plumbing -- a C++ caller links the headers in dsopp_b200/csrc/host/ directly."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import BLOCK, DpbaError, _f32, _f64, _ptr, _u8, pose34
+
+_P, _I, _D, _LL = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    capi.load_library()  # RTLD_GLOBAL: the host library resolves dpba_* from it
+    import os
+    if not os.path.exists(capi.HOST_LIB_PATH):
+        raise DpbaError(f"{capi.HOST_LIB_PATH} is not built: run `python -m dsopp_b200.build`")
+    lib = C.CDLL(capi.HOST_LIB_PATH)
+    lib.dpbah_last_error.restype = C.c_char_p
+    lib.dpbah_create.restype = _P
+    lib.dpbah_create.argtypes = [_I] * 9 + [_D] * 7
+    lib.dpbah_destroy.argtypes = [_P]
+    lib.dpbah_handle.restype = _P
+    lib.dpbah_handle.argtypes = [_P]
+    lib.dpbah_push_frame.argtypes = [_P, _I, _LL, _P, _D, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]
+    lib.dpbah_update_local_frame.argtypes = [_P, _I, _LL, _P, _D, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P]
+    lib.dpbah_solve.argtypes = [_P, C.POINTER(_D), C.POINTER(_I)]
+    lib.dpbah_num_frames.argtypes = [_P]
+    lib.dpbah_frame_ids.argtypes = [_P, _P]
+    lib.dpbah_update_frame.argtypes = [_P, _LL, _P, _P, _I, _P, _P, _P, _P, _P]
+    lib.dpbah_marginalized_system.argtypes = [_P, _P, _P, C.POINTER(_D)]
+    lib.dpbah_covariance.argtypes = [_P, _I, _I, _P]
+    lib.dpbah_lm_solve.argtypes = [_P, _I, _P, _P, _D, _D, _D, _D, _I, _I, _D, _D, _I, _D, _D, _D, C.POINTER(_D),
+                                   C.POINTER(_I)]
+    lib.dpbah_normal_solve.argtypes = [_I, _P, _P, _P]
+    lib.dpbah_reduce_system.argtypes = [_I, _P, _P, _I, _P]
+    lib.dpbah_sym_pinv.argtypes = [_I, _P, _I, _P]
+    _lib = lib
+    return lib
+
+
+def _ck(rc):
+    if rc < 0:
+        raise DpbaError(f"host error {rc}: {load_library().dpbah_last_error().decode()}")
+    return rc
+
+
+def normal_solve(H, b):
+    lib = load_library()
+    H, b = _f64(H), _f64(b)
+    x = np.zeros_like(b)
+    lib.dpbah_normal_solve(len(b), _ptr(H), _ptr(b), _ptr(x))
+    return x
+
+
+def reduce_system(H, b, elim):
+    lib = load_library()
+    H, b = _f64(H).copy(), _f64(b).copy()
+    e = np.ascontiguousarray(elim, dtype=np.int32)
+    n = lib.dpbah_reduce_system(len(b), _ptr(H), _ptr(b), len(e), _ptr(e))
+    return H.reshape(-1)[: n * n].reshape(n, n).copy(), b[:n].copy()
+
+
+def sym_pinv(A, n_null):
+    lib = load_library()
+    A = _f64(A)
+    out = np.zeros_like(A)
+    lib.dpbah_sym_pinv(A.shape[0], _ptr(A), n_null, _ptr(out))
+    return out
+
+
+def lm_solve(handle: capi.Handle, ab0, fixed, sigma=20.0, ab_reg=(1e12, 1e8), fixed_reg=1e16, max_it=7, min_it=3,
+             ftol=1e-8, ptol=1e-8, force_accept=True, lambda0=1e-5, decrease=1.0, increase=1.0):
+    """levenberg_marquardt_algorithm::solve (C++) over a window already uploaded through the C ABI."""
+    lib = load_library()
+    ab0 = _f64(np.asarray(ab0).reshape(-1))
+    fx = np.ascontiguousarray(fixed, dtype=np.int32)
+    e, it = _D(), _I()
+    _ck(lib.dpbah_lm_solve(handle.h, len(fx), _ptr(ab0), _ptr(fx), sigma, ab_reg[0], ab_reg[1], fixed_reg, max_it,
+                           min_it, ftol, ptol, int(force_accept), lambda0, decrease, increase, C.byref(e), C.byref(it)))
+    return e.value, it.value
+
+
+class CudaPhotometricBundleAdjustment:
+    """Python proxy of the C++ class of the same name (csrc/host/cuda_photometric_bundle_adjustment.hpp)."""
+
+    def __init__(self, width, height, max_frames=9, max_points=4096, device=0, estimate_uncertainty=True,
+                 force_accept=True, max_iterations=7, min_iterations=3, radius=1e5, ftol=1e-8, ptol=1e-8,
+                 ab_reg=(1e12, 1e8), fixed_reg=1e16, sigma=20.0):
+        self.lib = load_library()
+        self.s = self.lib.dpbah_create(width, height, max_frames, max_points, device, int(estimate_uncertainty),
+                                       int(force_accept), max_iterations, min_iterations, radius, ftol, ptol,
+                                       ab_reg[0], ab_reg[1], fixed_reg, sigma)
+        if not self.s:
+            raise DpbaError("dpbah_create: " + self.lib.dpbah_last_error().decode())
+        self.s = C.c_void_p(self.s)
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "s", None):
+            self.lib.dpbah_destroy(self.s)
+            self.s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _statuses(n, other_ids, ref_statuses, tgt_statuses):
+        ids = np.ascontiguousarray(other_ids, dtype=np.int32)
+        ref = None
+        if ref_statuses is not None:
+            ref = np.ascontiguousarray(np.stack([_u8(ref_statuses[i]) for i in other_ids]) if len(ids) else
+                                       np.zeros((0, n), np.uint8))
+        tgt, cnt = None, None
+        if tgt_statuses is not None:
+            parts = [_u8(tgt_statuses[i]) for i in other_ids]
+            cnt = np.ascontiguousarray([len(p) for p in parts], dtype=np.int32)
+            tgt = np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(0, np.uint8))
+        return ids, ref, tgt, cnt
+
+    def push_frame(self, frame_id, timestamp, T_w_agent, exposure, ab, intr, image, mask, uv, idepth, patch, flags=None,
+                   fixed=False, is_marginalized=False, other_ids=(), ref_statuses=None, tgt_statuses=None):
+        T, ab, intr = pose34(T_w_agent), _f64(ab), _f64(intr)
+        image, mask = _f32(image), _u8(mask)
+        uv, idepth, patch, flags = _f32(uv), _f32(idepth), _f32(patch), _u8(flags)
+        ids, ref, tgt, cnt = self._statuses(len(idepth), list(other_ids), ref_statuses, tgt_statuses)
+        _ck(self.lib.dpbah_push_frame(self.s, frame_id, timestamp, _ptr(T), exposure, _ptr(ab), _ptr(intr), _ptr(image),
+                                      _ptr(mask), int(is_marginalized), len(idepth), _ptr(uv), _ptr(idepth), _ptr(patch),
+                                      _ptr(flags), int(fixed), len(ids), _ptr(ids), _ptr(ref), _ptr(tgt), _ptr(cnt)))
+
+    def update_local_frame(self, frame_id, timestamp, T_w_agent, exposure, ab, intr, uv, idepth, patch, flags=None,
+                           is_marginalized=False, other_ids=(), ref_statuses=None, tgt_statuses=None):
+        T, ab, intr = pose34(T_w_agent), _f64(ab), _f64(intr)
+        uv, idepth, patch, flags = _f32(uv), _f32(idepth), _f32(patch), _u8(flags)
+        ids, ref, tgt, cnt = self._statuses(len(idepth), list(other_ids), ref_statuses, tgt_statuses)
+        _ck(self.lib.dpbah_update_local_frame(self.s, frame_id, timestamp, _ptr(T), exposure, _ptr(ab), _ptr(intr),
+                                              int(is_marginalized), len(idepth), _ptr(uv), _ptr(idepth), _ptr(patch),
+                                              _ptr(flags), len(ids), _ptr(ids), _ptr(ref), _ptr(tgt), _ptr(cnt)))
+
+    def solve(self):
+        e, it = _D(), _I()
+        _ck(self.lib.dpbah_solve(self.s, C.byref(e), C.byref(it)))
+        return e.value, it.value
+
+    @property
+    def frame_ids(self):
+        ids = np.zeros(capi.MAX_FRAMES, np.int32)
+        n = self.lib.dpbah_frame_ids(self.s, _ptr(ids))
+        return ids[:n].tolist()
+
+    def update_frame(self, timestamp, n):
+        T, ab = np.zeros(12), np.zeros(2)
+        out = dict(idepth=np.zeros(n, np.float32), variance=np.zeros(n, np.float32), baseline=np.zeros(n, np.float32),
+                   outlier=np.zeros(n, np.uint8), inliers=np.zeros(n, np.uint32))
+        _ck(self.lib.dpbah_update_frame(self.s, timestamp, _ptr(T), _ptr(ab), n, _ptr(out["idepth"]),
+                                        _ptr(out["variance"]), _ptr(out["baseline"]), _ptr(out["outlier"]),
+                                        _ptr(out["inliers"])))
+        out["T_w_agent"], out["ab"] = T.reshape(3, 4), ab
+        return out
+
+    def marginalized_system(self):
+        n = BLOCK * self.lib.dpbah_num_frames(self.s)
+        H, b, e = np.zeros((n, n)), np.zeros(n), _D()
+        self.lib.dpbah_marginalized_system(self.s, _ptr(H), _ptr(b), C.byref(e))
+        return H, b, e.value
+
+    def covariance(self, ref_id, tgt_id):
+        out = np.zeros(36)
+        if self.lib.dpbah_covariance(self.s, ref_id, tgt_id, _ptr(out)) != 0:
+            return None
+        return out.reshape(6, 6)

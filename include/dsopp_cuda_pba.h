@@ -192,6 +192,17 @@ int dpba_landmarks_energy(dpba_handle* h, int32_t for_marginalized, double* ener
 int dpba_update_point_statuses(dpba_handle* h, int32_t minimum_valid_reprojections, double sigma_huber,
                                double* energy_threshold);
 
+/* ---- measurement hooks (no reference counterpart) --------------------------------------- */
+/* kernels launched by this process so far (every launch wrapper counts itself) */
+int64_t dpba_launch_count(void);
+/* Per-kernel device timing with CUDA events recorded on the handle's stream around each launch.
+ * kinds: 0 fused linearise sweep, 1 Schur SYRK, 2 residual-only sweep, 3 materialising sweep,
+ *        4 assemble+symmetrise, 5 back-substitution.  dpba_profile_read synchronises, returns per kind the
+ *        summed milliseconds and launch counts since the last dpba_profile_enable(h, 1), and keeps profiling on. */
+#define DPBA_PROFILE_KINDS 6
+int dpba_profile_enable(dpba_handle* h, int32_t on);
+int dpba_profile_read(dpba_handle* h, double ms[DPBA_PROFILE_KINDS], int32_t launches[DPBA_PROFILE_KINDS]);
+
 /* ---- multi-GPU (one process per GPU; landmarks sharded, frames replicated) -------------- */
 /* 128-byte NCCL unique id created on rank 0, broadcast by the caller (torch.distributed / MPI / files). */
 int dpba_comm_unique_id(uint8_t id[128]);

@@ -1,0 +1,116 @@
+"""GPU tests of the C++ host side (LM driver + CudaPhotometricBundleAdjustment) against the NumPy oracle's
+EigenPBA restatement (eigen_photometric_bundle_adjustment.cpp:59-141): solve, relinearise, uncertainty,
+point statuses, and a push / marginalise / solve sliding-window sequence."""
+import numpy as np
+import pytest
+
+from dsopp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+SIGMA = 20.0
+
+
+def test_cpp_lm_solve_matches_oracle_lm():
+    from dsopp_b200 import capi, host
+    from oracle import pba_oracle as O
+    win = synth.make_window(n_frames=4, points_per_frame=300, seed=21, ab_scale=0.0)
+    frames = O.frames_from_window(win)
+    O.first_estimate_jacobians(frames)
+    trace = []
+    e_ref, n_ref, _ = O.lm_solve(O.Problem(frames, SIGMA), O.LMOptions(7, 1e-5, 1e-8, 1e-8, True, 3, 1.0, 1.0), trace)
+    h = capi.upload_window(win)
+    e, it = host.lm_solve(h, np.stack([f.ab0 for f in win.frames]), [int(f.fixed) for f in win.frames])
+    assert it == len(trace)
+    assert abs(e - e_ref) <= 2e-4 * abs(e_ref)
+    eps, _ = h.get_state()
+    assert np.abs(eps - O.state_eps_stacked(frames)).max() <= 2e-5
+    h.close()
+
+
+def push_all(pba, win, upto):
+    ids = []
+    for i, f in enumerate(win.frames[:upto]):
+        pba.push_frame(f.frame_id, f.timestamp, f.T_w_lin, f.exposure, f.ab0, f.intr, f.image, f.mask, f.uv, f.idepth,
+                       f.patch, f.flags, fixed=f.fixed, other_ids=ids)
+        ids.append(f.frame_id)
+
+
+def test_solver_class_solve_and_update_frame():
+    from dsopp_b200 import host
+    from oracle import pba_oracle as O
+    win = synth.make_window(n_frames=4, points_per_frame=250, seed=22, ab_scale=0.0, eps_scale=0.0)
+    frames = O.frames_from_window(win)
+    ref = O.EigenPBA(estimate_uncertainty=True)
+    ref.set_frames(frames)
+    e_ref = ref.solve()
+    pba = host.CudaPhotometricBundleAdjustment(win.width, win.height, max_frames=5, max_points=256)
+    push_all(pba, win, 4)
+    e, it = pba.solve()
+    assert abs(e - e_ref) <= 2e-4 * abs(e_ref)
+    for i, f in enumerate(frames):
+        out = pba.update_frame(win.frames[i].timestamp, len(f.idepth))
+        assert np.abs(out["T_w_agent"] - f.t_world_agent()[:3, :4]).max() <= 2e-5
+        assert np.abs(out["ab"] - f.affine_brightness()).max() <= 2e-5
+        act = ~f.lm_marginalized
+        assert np.abs(out["idepth"][act] - f.idepth[act]).max() <= 3e-5
+        assert (out["outlier"].astype(bool) != f.lm_outlier).sum() <= 1
+        assert (out["inliers"] != f.n_inliers).sum() <= 2
+        good = ~f.ill & (f.inv_hdd > 0)
+        assert np.allclose(out["variance"][good], f.inv_hdd[good], rtol=2e-3, atol=1e-12)
+        for j, g in enumerate(frames):
+            if i != j:
+                c, c_ref = pba.covariance(f.id, g.id), f.cov[g.id]
+                assert np.abs(c - c_ref).max() <= 2e-2 * np.abs(c_ref).max()  # reference bar: 1e-2 (test_pba.cpp:159-243)
+    pba.close()
+
+
+def test_sliding_window_marginalisation_sequence():
+    """push 4, solve, marginalise frame 0 (all its landmarks), push a 5th, solve -- against the oracle's
+    updateMarginalizedLinearSystem + reduce_system path."""
+    from dsopp_b200 import host
+    from oracle import pba_oracle as O
+    win = synth.make_window(n_frames=5, points_per_frame=200, seed=23, ab_scale=0.0, eps_scale=0.0)
+    # --- oracle
+    frames_all = O.frames_from_window(win)
+    first4 = frames_all[:4]
+    for f in first4:
+        f.residuals = {k: v for k, v in f.residuals.items() if k != frames_all[4].id}
+    ref = O.EigenPBA(estimate_uncertainty=False)
+    ref.set_frames(first4)
+    ref.solve()
+    f0 = first4[0]
+    f0.lm_to_marginalize[:] = ~f0.lm_marginalized & ~f0.lm_outlier
+    f0.lm_marginalized[:] = True
+    f0.to_marginalize, f0.is_marginalized = True, True
+    ref.marginalize()
+    assert len(ref.frames) == 3
+    new = frames_all[4]
+    new.residuals = {k: v for k, v in new.residuals.items() if k != f0.id}
+    for f in ref.frames:
+        f.residuals.pop(f0.id, None)
+        f.residuals[new.id] = O.Residuals(np.zeros(len(f.idepth), dtype=np.uint8))
+    ref.set_frames(ref.frames + [new])
+    e_ref = ref.solve()
+    # --- C++ solver on the GPU
+    pba = host.CudaPhotometricBundleAdjustment(win.width, win.height, max_frames=5, max_points=256,
+                                               estimate_uncertainty=False)
+    push_all(pba, win, 4)
+    pba.solve()
+    f = win.frames[0]
+    out0 = pba.update_frame(f.timestamp, len(f.idepth))
+    flags = np.where(out0["outlier"] != 0, synth.FLAG_MARGINALIZED | synth.FLAG_OUTLIER, synth.FLAG_MARGINALIZED).astype(np.uint8)
+    pba.update_local_frame(f.frame_id, f.timestamp, f.T_w_lin, f.exposure, f.ab0, f.intr, f.uv, f.idepth, f.patch,
+                           flags, is_marginalized=True)
+    g = win.frames[4]
+    pba.push_frame(g.frame_id, g.timestamp, g.T_w_lin, g.exposure, g.ab0, g.intr, g.image, g.mask, g.uv, g.idepth,
+                   g.patch, g.flags, fixed=False, other_ids=pba.frame_ids)
+    assert pba.frame_ids == [1, 2, 3, 4]
+    Hm, bm, em = pba.marginalized_system()
+    assert np.abs(Hm[:24, :24] - ref.H_marg[:24, :24]).max() <= 2e-3 * np.abs(ref.H_marg).max()
+    assert np.abs(bm[:24] - ref.b_marg[:24]).max() <= 2e-3 * np.abs(ref.b_marg).max() + 1e-6 * np.abs(ref.H_marg).max()
+    e, it = pba.solve()
+    assert abs(e - e_ref) <= 2e-3 * abs(e_ref)
+    for i, fr in enumerate(ref.frames):
+        out = pba.update_frame(win.frames[i + 1].timestamp, len(fr.idepth))
+        assert np.abs(out["T_w_agent"] - fr.t_world_agent()[:3, :4]).max() <= 1e-4
+    pba.close()
