@@ -6,8 +6,9 @@
 
 A "step" is one Levenberg-Marquardt solve of the sliding window = GN_ITERS Gauss-Newton iterations, each =
 linearize (residual+Jacobian sweep, H_pp, per-point Schur) + reduced solve + back-substitution + residual-only
-energy sweep + accept (the loop body of levenberg_marquardt_algorithm.hpp:85-114), driven by the C++ host LM
-through the C ABI.  metric = patch-residuals per second per GN iteration = units * GN_ITERS * steps / time.
+energy sweep + accept (the loop body of levenberg_marquardt_algorithm.hpp:85-114), executed by dpba_solve_lm
+(the whole loop on the device, one host synchronisation per solve; --host-lm drives the same kernels from the C++
+LevenbergMarquardtProblem adapter instead).  metric = patch-residuals per second per GN iteration = units * GN_ITERS * steps / time.
 
   value : window resident in HBM when the timed region starts.
   e2e   : every step additionally re-uploads the whole window (images, masks, landmarks, statuses, state) from
@@ -207,8 +208,14 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def solve():
-        return host.lm_solve(h, ab0, fixed, SIGMA, AB_REG, FIXED_REG, max_it=GN_ITERS, min_it=GN_ITERS, ftol=0.0,
-                             ptol=0.0, force_accept=True, lambda0=1e-5)
+        # device-resident LM (dpba_solve_lm): same loop / problem methods as the C++ host LM, one host sync per solve
+        if args.host_lm:
+            return host.lm_solve(h, ab0, fixed, SIGMA, AB_REG, FIXED_REG, max_it=GN_ITERS, min_it=GN_ITERS, ftol=0.0,
+                                 ptol=0.0, force_accept=True, lambda0=1e-5)
+        h.first_estimate()
+        r = h.solve_lm(SIGMA, AB_REG, FIXED_REG, max_it=GN_ITERS, min_it=GN_ITERS, ftol=0.0, ptol=0.0,
+                       force_accept=True, lambda0=1e-5)
+        return r[0], r[1]
 
     def reset_resident():
         # same starting point for every step (untimed): landmarks + state back to the initial estimate
@@ -384,7 +391,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_box[0]),
                 "ms_per_step": sum(e2e_ms) / len(e2e_ms),
                 "path": "dpba_remove_frame/push_frame/set_landmarks/set_statuses/set_state from pinned host buffers, "
-                        "C++ levenberg_marquardt_algorithm::solve over the C ABI, dpba_get_* readback"},
+                        "dpba_first_estimate + dpba_solve_lm, dpba_get_* readback"},
         "gpu_launches": int(launches),
         "roofline": roofline, "roofline_sweep": roofline_sweep, "kernel_ms": kernel_ms,
         "cpu_baseline": cpu,
@@ -402,6 +409,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--host-lm", action="store_true", help="drive the LM loop from the C++ host adapter instead of dpba_solve_lm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

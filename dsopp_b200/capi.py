@@ -52,6 +52,28 @@ _P = C.c_void_p
 _I = C.c_int32
 _D = C.c_double
 
+
+class LmOptions(C.Structure):
+    _fields_ = [
+        ("max_num_iterations", C.c_int32),
+        ("min_num_iterations", C.c_int32),
+        ("force_accept", C.c_int32),
+        ("first_estimate_jacobians", C.c_int32),
+        ("initial_levenberg_marquardt_regularizer", C.c_double),
+        ("function_tolerance", C.c_double),
+        ("parameter_tolerance", C.c_double),
+        ("levenberg_marquardt_regularizer_decrease_on_accept", C.c_double),
+        ("levenberg_marquardt_regularizer_increase_on_reject", C.c_double),
+        ("sigma_huber_loss", C.c_double),
+        ("affine_brightness_regularizer", C.c_double * 2),
+        ("fixed_state_regularizer", C.c_double),
+    ]
+
+
+class LmResult(C.Structure):
+    _fields_ = [("energy", C.c_double), ("number_of_valid_residuals", C.c_int32), ("converged", C.c_int32),
+                ("iterations", C.c_int32)]
+
 # name -> (restype, argtypes); exactly the symbols declared in include/dsopp_cuda_pba.h
 SIGNATURES = {
     "dpba_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
@@ -87,6 +109,8 @@ SIGNATURES = {
     "dpba_change_residual_statuses": (C.c_int, [_P, _I]),
     "dpba_landmarks_energy": (C.c_int, [_P, _I, C.POINTER(_D), C.POINTER(_I)]),
     "dpba_update_point_statuses": (C.c_int, [_P, _I, _D, C.POINTER(_D)]),
+    "dpba_solve_lm": (C.c_int, [_P, C.POINTER(LmOptions), _P, _P, _D, C.POINTER(LmResult)]),
+    "dpba_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "dpba_launch_count": (C.c_int64, []),
     "dpba_profile_enable": (C.c_int, [_P, _I]),
     "dpba_profile_read": (C.c_int, [_P, _P, _P]),
@@ -294,13 +318,28 @@ class Handle:
         self._ck(self.lib.dpba_update_point_statuses(self.h, min_valid, sigma, C.byref(t)))
         return t.value
 
-    PROFILE_KINDS = ("linearize_fused", "schur", "residual_sweep", "materialise_sweep", "assemble", "back_substitute")
+    def solve_lm(self, sigma=20.0, ab_reg=(1e12, 1e8), fixed_reg=1e16, max_it=7, min_it=3, ftol=1e-8, ptol=1e-8,
+                 force_accept=True, lambda0=1e-5, decrease=1.0, increase=1.0, fej=True, H_marg=None, b_marg=None,
+                 energy_marg=0.0):
+        """levenberg_marquardt_algorithm::solve entirely on the device (dpba_solve_lm)."""
+        o = LmOptions(max_it, min_it, int(force_accept), int(fej), lambda0, ftol, ptol, decrease, increase, sigma,
+                      (C.c_double * 2)(*ab_reg), fixed_reg)
+        r = LmResult()
+        Hm, bm = _f64(H_marg), _f64(b_marg)
+        self._ck(self.lib.dpba_solve_lm(self.h, C.byref(o), _ptr(Hm), _ptr(bm), energy_marg, C.byref(r)))
+        return r.energy, r.iterations, bool(r.converged), r.number_of_valid_residuals
+
+    PROFILE_KINDS = ("linearize_fused", "schur", "residual_sweep", "materialise_sweep", "assemble", "back_substitute",
+                     "pair_setup", "lm_step")
+
+    def set_option(self, name, value):
+        self._ck(self.lib.dpba_set_option(self.h, name.encode(), int(value)))
 
     def profile_enable(self, on=True):
         self._ck(self.lib.dpba_profile_enable(self.h, int(on)))
 
     def profile_read(self):
-        ms, n = np.zeros(6), np.zeros(6, np.int32)
+        ms, n = np.zeros(8), np.zeros(8, np.int32)
         self._ck(self.lib.dpba_profile_read(self.h, _ptr(ms), _ptr(n)))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 

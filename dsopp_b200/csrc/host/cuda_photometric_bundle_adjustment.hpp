@@ -65,8 +65,12 @@ class CudaPhotometricBundleAdjustment {
  public:
   CudaPhotometricBundleAdjustment(const TrustRegionPhotometricBundleAdjustmentOptions& trust_region_options,
                                   bool estimate_uncertainty, bool force_accept, int width, int height,
-                                  int max_frames = 9, int max_points_per_frame = 4096, int device = 0)
-      : options_(trust_region_options), estimate_uncertainty_(estimate_uncertainty), force_accept_(force_accept) {
+                                  int max_frames = 9, int max_points_per_frame = 4096, int device = 0,
+                                  bool device_resident_lm = true)
+      : options_(trust_region_options),
+        estimate_uncertainty_(estimate_uncertainty),
+        force_accept_(force_accept),
+        device_resident_lm_(device_resident_lm) {
     dpba_config cfg{max_frames, max_points_per_frame, width, height, device, 0, 1};
     const int rc = dpba_create(&cfg, &h_);
     if (rc != 0) throw DpbaFailure(rc, "dpba_create failed (no CUDA device? there is no CPU fallback)");
@@ -155,11 +159,39 @@ class CudaPhotometricBundleAdjustment {
     o.force_accept = force_accept_;
     o.levenberg_marquardt_regularizer_decrease_on_accept = 1.;
     o.levenberg_marquardt_regularizer_increase_on_reject = 1.;
-    CudaPhotometricBundleAdjustmentProblem problem(h_, frames_, options_.sigma_huber_loss, system_marginalized_,
-                                                   energy_marginalized_, options_.affine_brightness_regularizer,
-                                                   options_.fixed_state_regularizer, true);
     dpba_check(h_, dpba_first_estimate(h_));
-    const lm::Result result = lm::solve(problem, o);
+    lm::Result result;
+    if (device_resident_lm_) {
+      // the same loop and problem methods, executed on the device with one host synchronisation (dpba_solve_lm)
+      dpba_lm_options d;
+      d.max_num_iterations = (int32_t)o.max_num_iterations;
+      d.min_num_iterations = (int32_t)o.min_num_iterations;
+      d.force_accept = o.force_accept;
+      d.first_estimate_jacobians = 1;
+      d.initial_levenberg_marquardt_regularizer = o.initial_levenberg_marquardt_regularizer;
+      d.function_tolerance = o.function_tolerance;
+      d.parameter_tolerance = o.parameter_tolerance;
+      d.levenberg_marquardt_regularizer_decrease_on_accept = o.levenberg_marquardt_regularizer_decrease_on_accept;
+      d.levenberg_marquardt_regularizer_increase_on_reject = o.levenberg_marquardt_regularizer_increase_on_reject;
+      d.sigma_huber_loss = options_.sigma_huber_loss;
+      d.affine_brightness_regularizer[0] = options_.affine_brightness_regularizer[0];
+      d.affine_brightness_regularizer[1] = options_.affine_brightness_regularizer[1];
+      d.fixed_state_regularizer = options_.fixed_state_regularizer;
+      if (system_marginalized_.size() != kBlockSize * (int)frames_.size())
+        system_marginalized_.resize(kBlockSize * (int)frames_.size());
+      dpba_lm_result r;
+      dpba_check(h_, dpba_solve_lm(h_, &d, system_marginalized_.H.a.data(), system_marginalized_.b.data(),
+                                   energy_marginalized_, &r));
+      result.energy = r.energy;
+      result.number_of_valid_residuals = r.number_of_valid_residuals;
+      result.converged = r.converged != 0;
+      result.iterations = (size_t)r.iterations;
+    } else {
+      CudaPhotometricBundleAdjustmentProblem problem(h_, frames_, options_.sigma_huber_loss, system_marginalized_,
+                                                     energy_marginalized_, options_.affine_brightness_regularizer,
+                                                     options_.fixed_state_regularizer, true);
+      result = lm::solve(problem, o);
+    }
     last_iterations_ = result.iterations;
     relinearizeSystem();
     if (estimate_uncertainty_) {
@@ -404,6 +436,7 @@ class CudaPhotometricBundleAdjustment {
   TrustRegionPhotometricBundleAdjustmentOptions options_;
   bool estimate_uncertainty_;
   bool force_accept_;
+  bool device_resident_lm_;
   std::vector<FrameMeta> frames_;
   NormalLinearSystem system_marginalized_{0};
   Precision energy_marginalized_ = 0;

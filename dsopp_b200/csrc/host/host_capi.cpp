@@ -68,7 +68,7 @@ __attribute__((visibility("default"))) void* dpbah_create(int width, int height,
                                                          int device, int estimate_uncertainty, int force_accept,
                                                          int max_iterations, int min_iterations, double radius,
                                                          double ftol, double ptol, double ab_reg0, double ab_reg1,
-                                                         double fixed_reg, double sigma) {
+                                                         double fixed_reg, double sigma, int device_lm) {
   try {
     TrustRegionPhotometricBundleAdjustmentOptions o;
     o.max_iterations = (size_t)max_iterations;
@@ -82,7 +82,7 @@ __attribute__((visibility("default"))) void* dpbah_create(int width, int height,
     o.sigma_huber_loss = sigma;
     auto* s = new Solver();
     s->pba = std::make_unique<CudaPhotometricBundleAdjustment>(o, estimate_uncertainty != 0, force_accept != 0, width,
-                                                               height, max_frames, max_points, device);
+                                                               height, max_frames, max_points, device, device_lm != 0);
     return s;
   } catch (const std::exception& e) {
     g_err = e.what();

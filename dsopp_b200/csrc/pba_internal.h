@@ -95,25 +95,50 @@ struct ReduceBuf {
   double* bp;   // [D]
 };
 
+// ---- device-resident Levenberg-Marquardt (levenberg_marquardt_algorithm.hpp:77-128 on the device) --------------
+struct LmOptionsDev {
+  int max_it, min_it, force_accept, fej, huber;
+  double lambda0, ftol, ptol, dec, inc, sigma;
+  double ab_reg[2], fixed_reg, energy_marg;
+};
+struct LmCtl {
+  double lambda, energy, next_energy;
+  double state_sq, step_sq;
+  int n_valid, next_n;
+  int converged, done, system_valid, accept, iteration, iterations_executed;
+};
+
 namespace pba {
+// kinds for launch_lm_energy
+enum { LM_ENERGY_INITIAL = 0, LM_ENERGY_TRIAL = 1, LM_ENERGY_FINAL = 2 };
+void launch_lm_init(LmCtl* ctl, const LmOptionsDev* opt, cudaStream_t s);
+void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s);
+void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr, int N, const double* scal,
+                      const double* Hmarg, const double* bmarg, int kind, cudaStream_t s);
+void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
+                    const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s);
+void launch_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, cudaStream_t s);
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
 void launch_pack_image(const float* src3, float4* dst, int n_px, cudaStream_t s);
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s);
-void launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* scal, cudaStream_t s);
+void launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* scal, cudaStream_t s,
+                           const LmCtl* ctl = nullptr, int ctl_mode = 0);
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s);
 void launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
-                            cudaStream_t s);
+                            cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_linearize_from_materialized(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
-void launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
-void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, cudaStream_t s);
+void launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
+void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_symmetrise_only(int D, double* Hp, cudaStream_t s);
-void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, double lambda, cudaStream_t s);
-void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s);
-void launch_change_statuses(const WindowDev& w, int accept, cudaStream_t s);
+void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, double lambda, cudaStream_t s,
+                            const LmCtl* ctl = nullptr, double* norms = nullptr);
+void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s, const LmCtl* ctl = nullptr);
+void launch_change_statuses(const WindowDev& w, int accept, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cudaStream_t s);
 void launch_snapshot_fej(const WindowDev& w, cudaStream_t s);
 void launch_apply_point_statuses(const WindowDev& w, float threshold, int min_valid, const float* pair_dist,
                                  cudaStream_t s);
 int sm_count();
 long long launch_count();
+void add_launches(long long n);
 }  // namespace pba

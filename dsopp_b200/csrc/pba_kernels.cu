@@ -101,6 +101,14 @@ __device__ __forceinline__ size_t res_index(const WindowDev& w, int r, int t, in
   return ((size_t)(w.phys[r] * PBA_MAXF + w.phys[t])) * w.max_pts + l;
 }
 
+// device-resident LM: kernels of a loop body return immediately once the loop has terminated (mode 1), and the
+// linearisation kernels also when the previous linear system is still valid (mode 2)
+__device__ __forceinline__ bool lm_skip(const LmCtl* ctl, int mode) {
+  if (!ctl || mode == 0) return false;
+  if (ctl->done) return true;
+  return mode == 2 && ctl->system_valid;
+}
+
 struct LandmarkIn {
   float u, v, rho, rho0, patch;
   int flags;
@@ -248,7 +256,9 @@ __device__ __forceinline__ LandmarkIn load_landmark(const WindowDev& w, int gl, 
 // ------------------------------------------------------------------------------------------------
 template <bool FEJ>
 __global__ void __launch_bounds__(256) k_residual_sweep(const __grid_constant__ WindowDev w, float sigma, int huber,
-                                                        double* __restrict__ scal) {
+                                                        double* __restrict__ scal, const LmCtl* __restrict__ ctl,
+                                                        int ctl_mode) {
+  if (lm_skip(ctl, ctl_mode)) return;
   __shared__ PairConst pcs;
   __shared__ float s_e[8];
   __shared__ int s_n[8];
@@ -384,7 +394,8 @@ __global__ void __launch_bounds__(256) k_materialise_sweep(const __grid_constant
 template <bool FEJ>
 __global__ void __launch_bounds__(32 * (PBA_MAXF - 1))
     k_linearize_fused(const __grid_constant__ WindowDev w, float sigma, int huber, int for_marg, int lpb,
-                      double* __restrict__ core) {
+                      double* __restrict__ core, const LmCtl* __restrict__ ctl) {
+  if (lm_skip(ctl, 2)) return;
   extern __shared__ float smem[];
   const int N = w.n_frames;
   const int D = 8 * N;
@@ -635,7 +646,9 @@ __global__ void __launch_bounds__(128) k_schur_prep_from_materialized(const __gr
 // ------------------------------------------------------------------------------------------------
 constexpr int SCHUR_TL = 32;
 __global__ void __launch_bounds__(1024) k_schur(const __grid_constant__ WindowDev w, int for_marg,
-                                                double* __restrict__ Hs, double* __restrict__ bs) {
+                                                double* __restrict__ Hs, double* __restrict__ bs,
+                                                const LmCtl* __restrict__ ctl) {
+  if (lm_skip(ctl, 2)) return;
   extern __shared__ float sm[];
   const int N = w.n_frames, D = 8 * N;
   const int T4 = D / 4;  // tiles per side
@@ -729,7 +742,8 @@ __global__ void __launch_bounds__(1024) k_schur(const __grid_constant__ WindowDe
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_assemble(const __grid_constant__ WindowDev w, int fej,
                                                  const double* __restrict__ core, double* __restrict__ Hp,
-                                                 double* __restrict__ bp) {
+                                                 double* __restrict__ bp, const LmCtl* __restrict__ ctl) {
+  if (lm_skip(ctl, 2)) return;
   const int N = w.n_frames, D = 8 * N;
   const int r = blockIdx.x / (N - 1);
   int t = blockIdx.x % (N - 1);
@@ -767,7 +781,8 @@ __global__ void __launch_bounds__(64) k_assemble(const __grid_constant__ WindowD
   }
 }
 
-__global__ void k_symmetrise(int D, double* __restrict__ Hp) {
+__global__ void k_symmetrise(int D, double* __restrict__ Hp, const LmCtl* __restrict__ ctl) {
+  if (lm_skip(ctl, 2)) return;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= D * D) return;
   const int i = a / D, j = a % D;
@@ -785,7 +800,10 @@ __global__ void k_symmetrise(int D, double* __restrict__ Hp) {
 // K5: calculateIdepths.  8 lanes per landmark, each lane 1/8 of the 8N-long dot product.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_back_substitute(const __grid_constant__ WindowDev w,
-                                                         const double* __restrict__ step_pose, float inv_lambda) {
+                                                         const double* __restrict__ step_pose, float inv_lambda,
+                                                         const LmCtl* __restrict__ ctl, double* __restrict__ norms) {
+  if (lm_skip(ctl, 1)) return;
+  if (ctl) inv_lambda = (float)(1.0 / (1.0 + ctl->lambda));
   __shared__ float sp[PBA_MAXF * 8];
   const int N = w.n_frames, D = 8 * N;
   for (int i = threadIdx.x; i < D; i += blockDim.x) sp[i] = (float)step_pose[i];
@@ -802,18 +820,51 @@ __global__ void __launch_bounds__(256) k_back_substitute(const __grid_constant__
     for (int c = px; c < D; c += 8) dot += h[c] * sp[c];
   }
   dot = group_sum(dot);
+  double n_state = 0, n_step = 0;
   if (inb && px == 0) {
     const int fl = w.flags[gl];
+    float stp = w.idepth_step[gl];
     if (!(fl & LM_MARG) && !(fl & LM_ILL)) {
-      const float step = (w.b_d[gl] - dot) * inv_lambda * w.inv_hdd[gl];
-      w.idepth_step[gl] = -step;
+      stp = -((w.b_d[gl] - dot) * inv_lambda * w.inv_hdd[gl]);
+      w.idepth_step[gl] = stp;
+    }
+    if (norms) {  // landmark part of acceptStep's norms (problem.hpp:377-382), used by the device LM
+      const float id = w.idepth[gl];
+      n_state = (double)id * id;
+      n_step = (double)stp * stp;
+    }
+  }
+  if (norms) {
+    __shared__ double sa[8], sb[8];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      n_state += __shfl_xor_sync(FULL, n_state, s);
+      n_step += __shfl_xor_sync(FULL, n_step, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      sa[threadIdx.x >> 5] = n_state;
+      sb[threadIdx.x >> 5] = n_step;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, b = 0;
+      for (int i = 0; i < 8; ++i) {
+        a += sa[i];
+        b += sb[i];
+      }
+      if (a != 0 || b != 0) {
+        atomicAdd(&norms[2], a);
+        atomicAdd(&norms[3], b);
+      }
     }
   }
 }
 
 // acceptStep / rejectStep over landmarks (problem.hpp:377-384,395-399); norms in fp64
 __global__ void __launch_bounds__(256) k_accept_landmarks(const __grid_constant__ WindowDev w, int accept,
-                                                          double* __restrict__ scal) {
+                                                          double* __restrict__ scal, const LmCtl* __restrict__ ctl) {
+  if (lm_skip(ctl, 1)) return;
+  if (ctl) accept = ctl->accept;
   const int f = blockIdx.y;
   const int M = w.n_lm[f];
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -821,7 +872,7 @@ __global__ void __launch_bounds__(256) k_accept_landmarks(const __grid_constant_
   if (l < M) {
     const int gl = lm_index(w, f, l);
     const float s = w.idepth_step[gl];
-    if (accept) {
+    if (accept > 0) {
       const float id = w.idepth[gl];
       st = (double)id * id;
       sp = (double)s * s;
@@ -829,7 +880,7 @@ __global__ void __launch_bounds__(256) k_accept_landmarks(const __grid_constant_
     }
     w.idepth_step[gl] = 0.f;
   }
-  if (!accept) return;
+  if (accept <= 0 || !scal) return;
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     st += __shfl_xor_sync(FULL, st, s);
@@ -853,7 +904,10 @@ __global__ void __launch_bounds__(256) k_accept_landmarks(const __grid_constant_
 }
 
 // changeResidualStatuses (problem.hpp:20-35)
-__global__ void __launch_bounds__(256) k_change_statuses(const __grid_constant__ WindowDev w, int accept) {
+__global__ void __launch_bounds__(256) k_change_statuses(const __grid_constant__ WindowDev w, int accept,
+                                                         const LmCtl* __restrict__ ctl) {
+  if (lm_skip(ctl, 1)) return;
+  if (ctl) accept = ctl->accept;
   const int N = w.n_frames;
   const int r = blockIdx.y / (N - 1);
   int t = blockIdx.y % (N - 1);
@@ -861,7 +915,7 @@ __global__ void __launch_bounds__(256) k_change_statuses(const __grid_constant__
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= w.n_lm[r]) return;
   const size_t res = res_index(w, r, t, l);
-  if (accept) w.status[res] = w.cand[res];
+  if (accept > 0) w.status[res] = w.cand[res];
   else w.cand[res] = w.status[res];
 }
 
@@ -976,9 +1030,11 @@ __device__ void se3_exp(const double* xi, double sign, SE3d& o) {
     b = 0.5;
     c = 1.0 / 6.0;
   } else {
-    a = sin(th) / th;
-    b = (1.0 - cos(th)) / th2;
-    c = (th - sin(th)) / (th2 * th);
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    a = sn / th;
+    b = (1.0 - cs) / th2;
+    c = (th - sn) / (th2 * th);
   }
   const double W[9] = {0, -wv[2], wv[1], wv[2], 0, -wv[0], -wv[1], wv[0], 0};
   double W2[9];
@@ -1028,34 +1084,39 @@ __device__ void make_proj(const SE3d& T, const double* ir, const double* it, flo
   }
 }
 
-__global__ void k_pair_setup(const FrameParams* __restrict__ fr, int N, PairConst* __restrict__ pairs,
-                             PairAssemble* __restrict__ pasm) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * N) return;
-  const int r = idx / N, t = idx % N;
+__global__ void __launch_bounds__(256) k_pair_setup(const FrameParams* __restrict__ fr, int N,
+                                                     PairConst* __restrict__ pairs, PairAssemble* __restrict__ pasm) {
+  // phase 1 (one thread per frame): exp(+eps), exp(-eps) and the inverse linearisation pose
+  __shared__ SE3d s_er[PBA_MAXF], s_et[PBA_MAXF], s_tl[PBA_MAXF], s_ti[PBA_MAXF];
+  __shared__ double s_a[PBA_MAXF], s_b[PBA_MAXF];
+  const int tid = threadIdx.x;
+  if (tid < N) {
+    const FrameParams& F = fr[tid];
+    double e[6];
+    for (int k = 0; k < 6; ++k) e[k] = F.eps[k] + F.step[k];
+    se3_exp(e, 1.0, s_er[tid]);
+    se3_exp(e, -1.0, s_et[tid]);
+    SE3d T;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) T.R[i * 3 + j] = F.T_lin[i * 4 + j];
+      T.t[i] = F.T_lin[i * 4 + 3];
+    }
+    s_tl[tid] = T;
+    se3_inv(T, s_ti[tid]);
+    s_a[tid] = F.ab0[0] + F.eps[6] + F.step[6];
+    s_b[tid] = F.ab0[1] + F.eps[7] + F.step[7];
+  }
+  __syncthreads();
+  // phase 2 (one thread per ordered pair)
+  if (tid >= N * N) return;
+  const int r = tid / N, t = tid % N;
   if (r == t) return;
   const FrameParams& R = fr[r];
   const FrameParams& T = fr[t];
-  SE3d Tr, Tt, Tti, T0, er, et, tmp, Tc;
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) {
-      Tr.R[i * 3 + j] = R.T_lin[i * 4 + j];
-      Tt.R[i * 3 + j] = T.T_lin[i * 4 + j];
-    }
-    Tr.t[i] = R.T_lin[i * 4 + 3];
-    Tt.t[i] = T.T_lin[i * 4 + 3];
-  }
-  se3_inv(Tt, Tti);
-  se3_mul(Tti, Tr, T0);  // t_t_r0 (evaluate_jacobians.hpp:47-48)
-  double epr[6], ept[6];
-  for (int k = 0; k < 6; ++k) {
-    epr[k] = R.eps[k] + R.step[k];
-    ept[k] = T.eps[k] + T.step[k];
-  }
-  se3_exp(epr, 1.0, er);
-  se3_exp(ept, -1.0, et);
-  se3_mul(T0, er, tmp);
-  se3_mul(et, tmp, Tc);  // t_t_r = exp(-eps_t) T0 exp(eps_r)  (:49)
+  SE3d T0, tmp, Tc;
+  se3_mul(s_ti[t], s_tl[r], T0);  // t_t_r0 (evaluate_jacobians.hpp:47-48)
+  se3_mul(T0, s_er[r], tmp);
+  se3_mul(s_et[t], tmp, Tc);      // t_t_r = exp(-eps_t) T0 exp(eps_r)  (:49)
 
   PairConst pc;
   make_proj(Tc, R.intr, T.intr, pc.M, pc.A);
@@ -1071,17 +1132,16 @@ __global__ void k_pair_setup(const FrameParams* __restrict__ fr, int N, PairCons
     pc.adj[i] = (float)pa.adj_cur[i];
     pc.adj0[i] = (float)pa.adj_fej[i];
   }
-  const double a_r = R.ab0[0] + R.eps[6] + R.step[6], b_r = R.ab0[1] + R.eps[7] + R.step[7];
-  const double a_t = T.ab0[0] + T.eps[6] + T.step[6], b_t = T.ab0[1] + T.eps[7] + T.step[7];
-  pa.s = (T.exposure / R.exposure) * exp(a_t - a_r);
-  pa.s0 = (T.exposure / R.exposure) * exp(T.ab0[0] - R.ab0[0]);
+  const double ratio = T.exposure / R.exposure;
+  pa.s = ratio * exp(s_a[t] - s_a[r]);
+  pa.s0 = ratio * exp(T.ab0[0] - R.ab0[0]);
   const int last = (r == N - 1) ? N - 2 : N - 1;  // last target in deque order (quirk Q1)
   const double s0_last = (fr[last].exposure / R.exposure) * exp(fr[last].ab0[0] - R.ab0[0]);
   pc.s = (float)pa.s;
   pc.s0 = (float)pa.s0;
   pc.s0_last = (float)s0_last;
-  pc.b_t = (float)b_t;
-  pc.b_r = (float)b_r;
+  pc.b_t = (float)s_b[t];
+  pc.b_r = (float)s_b[r];
   pc.b_r0 = (float)R.ab0[1];
   pc.fx_t = (float)T.intr[0];
   pc.fy_t = (float)T.intr[1];
@@ -1113,6 +1173,201 @@ __global__ void k_pixelinfo(const float* __restrict__ I, float4* __restrict__ ds
   dst[y * W + x] = make_float4(c, dx, dy, 0.f);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident Levenberg-Marquardt: the control flow of levenberg_marquardt_algorithm::solve
+// (levenberg_marquardt_algorithm.hpp:77-128) and the host half of PhotometricBundleAdjustmentProblem
+// (problem.hpp:290-402) as single-CTA fp64 kernels, so that a whole solve is one stream of launches with no
+// host round trip.  Decisions live in LmCtl; loop-body kernels early-out on ctl->done.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_lm_init(LmCtl* ctl, const LmOptionsDev* opt) {
+  if (threadIdx.x) return;
+  ctl->lambda = opt->lambda0;
+  ctl->energy = 0;
+  ctl->next_energy = 0;
+  ctl->state_sq = ctl->step_sq = 0;
+  ctl->n_valid = ctl->next_n = 0;
+  ctl->converged = 0;
+  ctl->done = 0;
+  ctl->system_valid = 0;
+  ctl->accept = 0;
+  ctl->iteration = 0;
+  ctl->iterations_executed = 0;
+}
+
+__global__ void k_lm_zero(const LmCtl* ctl, double* p, int n, int mode) {
+  if (lm_skip(ctl, mode)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+
+// calculateEnergy() tail (problem.hpp:293-316) + the accept decision (levenberg_marquardt_algorithm.hpp:95-104)
+__global__ void __launch_bounds__(128) k_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr,
+                                                   int N, const double* scal, const double* Hmarg,
+                                                   const double* bmarg, int kind) {
+  if (kind == pba::LM_ENERGY_TRIAL && ctl->done) return;
+  __shared__ double s[PBA_MAXF * 8];
+  __shared__ double red[128];
+  const int D = 8 * N, i = threadIdx.x;
+  if (i < D) s[i] = fr[i / 8].eps[i % 8] + fr[i / 8].step[i % 8];
+  __syncthreads();
+  double acc = 0;
+  if (i < D) {
+    if (Hmarg) {
+      double t = 0;
+      for (int j = 0; j < D; ++j) t += Hmarg[(size_t)i * D + j] * s[j];
+      acc += bmarg[i] * s[i] + 0.5 * s[i] * t;  // DSO eq 8.19
+    }
+    const int k = i % 8;
+    if (k >= 6) {  // AffineBrightnessPrior::energyTerm for every frame, fixed included (quirk Q8)
+      const double ab = fr[i / 8].ab0[k - 6] + s[i];
+      acc += 0.5 * ab * opt->ab_reg[k - 6] * ab;
+    }
+  }
+  red[i] = acc;
+  __syncthreads();
+  for (int st = 64; st > 0; st >>= 1) {
+    if (i < st) red[i] += red[i + st];
+    __syncthreads();
+  }
+  if (i) return;
+  const double E = opt->energy_marg + red[0] + scal[0];
+  const int n = (int)llrint(scal[1]);
+  if (kind == pba::LM_ENERGY_INITIAL) {
+    ctl->energy = E;
+    ctl->n_valid = n;
+    if (n <= 0 || opt->max_it <= 0) ctl->done = 1;
+  } else if (kind == pba::LM_ENERGY_TRIAL) {
+    ctl->next_energy = E;
+    ctl->next_n = n;
+    ctl->iterations_executed += 1;
+    // landmark parts of the norms, accumulated by k_back_substitute (problem.hpp:377-382)
+    ctl->state_sq = scal[2];
+    ctl->step_sq = scal[3];
+    if (n == 0) {
+      ctl->accept = -1;  // rejectStep(); break
+    } else {
+      if (fabs(ctl->energy - E) / ctl->energy < opt->ftol) ctl->converged = 1;  // before the accept test (Q7)
+      ctl->accept = (E < ctl->energy || (opt->force_accept && ctl->iteration < opt->min_it)) ? 1 : 0;
+    }
+  }
+}
+
+// acceptStep / rejectStep for the frame state + the loop bookkeeping (problem.hpp:366-402, lm.hpp:104-122)
+__global__ void k_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N) {
+  if (threadIdx.x || ctl->done) return;
+  if (ctl->accept > 0) {
+    double st = ctl->state_sq, sp = ctl->step_sq;
+    for (int f = 0; f < N; ++f) {
+      for (int k = 0; k < 8; ++k) st += fr[f].eps[k] * fr[f].eps[k];
+      st += fr[f].ab0[0] * fr[f].ab0[0] + fr[f].ab0[1] * fr[f].ab0[1];
+      for (int k = 0; k < 8; ++k) {
+        fr[f].eps[k] += fr[f].step[k];
+        sp += fr[f].step[k] * fr[f].step[k];
+        fr[f].step[k] = 0;
+      }
+    }
+    ctl->state_sq = st;
+    ctl->step_sq = sp;
+    if (sp < opt->ptol * (st + opt->ptol)) ctl->converged = 1;
+    ctl->energy = ctl->next_energy;
+    ctl->n_valid = ctl->next_n;
+    ctl->lambda /= opt->dec;
+    ctl->system_valid = 0;
+  } else {
+    for (int f = 0; f < N; ++f)
+      for (int k = 0; k < 8; ++k) fr[f].step[k] = 0;
+    if (ctl->accept < 0 || opt->force_accept) {
+      ctl->done = 1;
+      return;
+    }
+    ctl->lambda *= opt->inc;
+    ctl->system_valid = 1;
+  }
+  ctl->iteration += 1;
+  if (ctl->iteration >= opt->max_it || ctl->converged || ctl->n_valid <= 0) ctl->done = 1;
+}
+
+// calculateStep (problem.hpp:342-357): priors (problem.hpp:37-77), full system, Jacobi preconditioner + LDL^T
+// (normal_linear_system.cpp:10-59), all fp64 in one CTA; A lives in dynamic shared memory [D][D+1].
+__global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
+                                                 const int* fixed, int N, const double* __restrict__ Hp,
+                                                 const double* __restrict__ bp, const double* __restrict__ Hs,
+                                                 const double* __restrict__ bs, const double* __restrict__ Hmarg,
+                                                 const double* __restrict__ bmarg, double* __restrict__ step_dev) {
+  if (ctl->done) return;
+  extern __shared__ double sh[];
+  const int D = 8 * N, LD = D + 1, tid = threadIdx.x, nt = blockDim.x;
+  double* A = sh;              // [D][LD]
+  double* b = A + D * LD;      // [D]
+  double* pre = b + D;         // [D]
+  double* st = pre + D;        // [D] state eps
+  const double lambda = ctl->lambda, ks = -1.0 / (1.0 + lambda);
+  for (int i = tid; i < D; i += nt) st[i] = fr[i / 8].eps[i % 8];
+  __syncthreads();
+  for (int idx = tid; idx < D * D; idx += nt) {
+    const int i = idx / D, j = idx - i * D;
+    double hp = Hp[idx];
+    if (i == j) {
+      const int f = i / 8, k = i % 8;
+      if (fixed[f]) hp += opt->fixed_reg;
+      else if (k >= 6) hp += opt->ab_reg[k - 6];
+      hp += hp * lambda;
+    }
+    A[i * LD + j] = hp + (Hmarg ? Hmarg[idx] : 0.0) + ks * Hs[idx];
+  }
+  for (int i = tid; i < D; i += nt) {
+    const int f = i / 8, k = i % 8;
+    double v = bp[i] + ks * bs[i];
+    if (fixed[f]) v += opt->fixed_reg * st[i];
+    else if (k >= 6) v += opt->ab_reg[k - 6] * (fr[f].ab0[k - 6] + st[i]);
+    if (Hmarg) {
+      double t = 0;
+      for (int j = 0; j < D; ++j) t += Hmarg[(size_t)i * D + j] * st[j];
+      v += bmarg[i] + t;
+    }
+    b[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < D; i += nt) pre[i] = 1.0 / sqrt(A[i * LD + i] + 10.0);
+  __syncthreads();
+  for (int idx = tid; idx < D * D; idx += nt) {
+    const int i = idx / D, j = idx - i * D;
+    A[i * LD + j] *= pre[i] * pre[j];
+  }
+  for (int i = tid; i < D; i += nt) b[i] *= pre[i];
+  __syncthreads();
+  // LDL^T, right-looking, forward substitution folded in; row k keeps d * L^T so the update is A_ij -= L_ik A_kj
+  for (int k = 0; k < D; ++k) {
+    const double d = A[k * LD + k];
+    const double inv = d != 0.0 ? 1.0 / d : 0.0;
+    for (int i = k + 1 + tid; i < D; i += nt) A[i * LD + k] *= inv;
+    __syncthreads();
+    const int m = D - k - 1;
+    for (int idx = tid; idx < m * m; idx += nt) {
+      const int i = k + 1 + idx / m, j = k + 1 + idx % m;
+      A[i * LD + j] -= A[i * LD + k] * A[k * LD + j];
+    }
+    for (int i = k + 1 + tid; i < D; i += nt) b[i] -= A[i * LD + k] * b[k];
+    __syncthreads();
+  }
+  for (int i = tid; i < D; i += nt) {
+    const double d = A[i * LD + i];
+    b[i] = d != 0.0 ? b[i] / d : 0.0;
+  }
+  __syncthreads();
+  for (int k = D - 1; k > 0; --k) {
+    const double xk = b[k];
+    for (int i = tid; i < k; i += nt) b[i] -= A[k * LD + i] * xk;
+    __syncthreads();
+  }
+  for (int i = tid; i < D; i += nt) {
+    const double x = b[i] * pre[i];
+    step_dev[i] = x;
+    fr[i / 8].step[i % 8] = -x;  // frame.state_eps_step = -frame_step (problem.hpp:353-357)
+  }
+}
+
 int max_landmarks(const WindowDev& w) {
   int m = 0;
   for (int f = 0; f < w.n_frames; ++f) m = w.n_lm[f] > m ? w.n_lm[f] : m;
@@ -1125,6 +1380,7 @@ namespace pba {
 
 std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
+void add_launches(long long n) { g_launches += n; }
 
 int sm_count() {
   static int n = 0;
@@ -1137,9 +1393,44 @@ int sm_count() {
   return n;
 }
 
+
+void launch_lm_init(LmCtl* ctl, const LmOptionsDev* opt, cudaStream_t s) {
+  ++g_launches;
+  k_lm_init<<<1, 32, 0, s>>>(ctl, opt);
+}
+
+void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s) {
+  ++g_launches;
+  k_lm_zero<<<(n + 255) / 256, 256, 0, s>>>(ctl, p, n, mode);
+}
+
+void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr, int N, const double* scal,
+                      const double* Hmarg, const double* bmarg, int kind, cudaStream_t s) {
+  ++g_launches;
+  k_lm_energy<<<1, 128, 0, s>>>(ctl, opt, fr, N, scal, Hmarg, bmarg, kind);
+}
+
+void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
+                    const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s) {
+  const int D = 8 * N;
+  const size_t smem = (size_t)(D * (D + 1) + 3 * D) * sizeof(double);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaFuncSetAttribute(k_lm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(128 * 129 + 3 * 128) * 8));
+    attr_set = true;
+  }
+  ++g_launches;
+  k_lm_step<<<1, 256, smem, s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
+}
+
+void launch_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, cudaStream_t s) {
+  ++g_launches;
+  k_lm_finish<<<1, 32, 0, s>>>(ctl, opt, fr, N);
+}
+
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s) {
   ++g_launches;
-  k_pair_setup<<<(n_frames * n_frames + 63) / 64, 64, 0, s>>>(frames, n_frames, pairs, pasm);
+  k_pair_setup<<<1, 256, 0, s>>>(frames, n_frames, pairs, pasm);
 }
 
 void launch_pack_image(const float* src3, float4* dst, int n_px, cudaStream_t s) {
@@ -1153,13 +1444,14 @@ void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s)
   k_pixelinfo<<<g, b, 0, s>>>(I, dst, W, H);
 }
 
-void launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* scal, cudaStream_t s) {
+void launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* scal, cudaStream_t s,
+                           const LmCtl* ctl, int ctl_mode) {
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return;
   dim3 g((m + 31) / 32, w.n_frames * (w.n_frames - 1));
   ++g_launches;
-  if (fej) k_residual_sweep<true><<<g, 256, 0, s>>>(w, sigma, huber, scal);
-  else k_residual_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber, scal);
+  if (fej) k_residual_sweep<true><<<g, 256, 0, s>>>(w, sigma, huber, scal, ctl, ctl_mode);
+  else k_residual_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber, scal, ctl, ctl_mode);
 }
 
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s) {
@@ -1172,7 +1464,7 @@ void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fe
 }
 
 void launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
-                            cudaStream_t s) {
+                            cudaStream_t s, const LmCtl* ctl) {
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return;
   const int N = w.n_frames, D = 8 * N;
@@ -1185,11 +1477,11 @@ void launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej,
   if (fej) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_linearize_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ++g_launches;
-    k_linearize_fused<true><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, rb.core);
+    k_linearize_fused<true><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, rb.core, ctl);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_linearize_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ++g_launches;
-    k_linearize_fused<false><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, rb.core);
+    k_linearize_fused<false><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, rb.core, ctl);
   }
 }
 
@@ -1206,7 +1498,7 @@ void launch_linearize_from_materialized(const WindowDev& w, int for_marg, Reduce
   k_schur_prep_from_materialized<<<g2, 128, 0, s>>>(w, for_marg);
 }
 
-void launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s) {
+void launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl) {
   const int N = w.n_frames, D = 8 * N;
   int tiles = 0;
   for (int f = 0; f < N; ++f) tiles += (w.n_lm[f] + SCHUR_TL - 1) / SCHUR_TL;
@@ -1218,45 +1510,46 @@ void launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s
   const int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ++g_launches;
-  k_schur<<<grid, threads, smem, s>>>(w, for_marg, rb.Hs, rb.bs);
+  k_schur<<<grid, threads, smem, s>>>(w, for_marg, rb.Hs, rb.bs, ctl);
 }
 
-void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, cudaStream_t s) {
+void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl) {
   const int N = w.n_frames, D = 8 * N;
   if (N < 2) return;
   ++g_launches;
-  k_assemble<<<N * (N - 1), 64, 0, s>>>(w, fej, rb.core, rb.Hp, rb.bp);
+  k_assemble<<<N * (N - 1), 64, 0, s>>>(w, fej, rb.core, rb.Hp, rb.bp, ctl);
   ++g_launches;
-  k_symmetrise<<<(D * D + 255) / 256, 256, 0, s>>>(D, rb.Hp);
+  k_symmetrise<<<(D * D + 255) / 256, 256, 0, s>>>(D, rb.Hp, ctl);
 }
 
 void launch_symmetrise_only(int D, double* Hp, cudaStream_t s) {
   ++g_launches;
-  k_symmetrise<<<(D * D + 255) / 256, 256, 0, s>>>(D, Hp);
+  k_symmetrise<<<(D * D + 255) / 256, 256, 0, s>>>(D, Hp, nullptr);
 }
 
-void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, double lambda, cudaStream_t s) {
+void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, double lambda, cudaStream_t s,
+                            const LmCtl* ctl, double* norms) {
   const int m = max_landmarks(w);
   if (m == 0) return;
   dim3 g((m + 31) / 32, w.n_frames);
   ++g_launches;
-  k_back_substitute<<<g, 256, 0, s>>>(w, step_pose_dev, (float)(1.0 / (1.0 + lambda)));
+  k_back_substitute<<<g, 256, 0, s>>>(w, step_pose_dev, (float)(1.0 / (1.0 + lambda)), ctl, norms);
 }
 
-void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s) {
+void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s, const LmCtl* ctl) {
   const int m = max_landmarks(w);
   if (m == 0) return;
   dim3 g((m + 255) / 256, w.n_frames);
   ++g_launches;
-  k_accept_landmarks<<<g, 256, 0, s>>>(w, accept, scal);
+  k_accept_landmarks<<<g, 256, 0, s>>>(w, accept, scal, ctl);
 }
 
-void launch_change_statuses(const WindowDev& w, int accept, cudaStream_t s) {
+void launch_change_statuses(const WindowDev& w, int accept, cudaStream_t s, const LmCtl* ctl) {
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return;
   dim3 g((m + 255) / 256, w.n_frames * (w.n_frames - 1));
   ++g_launches;
-  k_change_statuses<<<g, 256, 0, s>>>(w, accept);
+  k_change_statuses<<<g, 256, 0, s>>>(w, accept, ctl);
 }
 
 void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cudaStream_t s) {

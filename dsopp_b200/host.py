@@ -24,7 +24,7 @@ def load_library():
     lib = C.CDLL(capi.HOST_LIB_PATH)
     lib.dpbah_last_error.restype = C.c_char_p
     lib.dpbah_create.restype = _P
-    lib.dpbah_create.argtypes = [_I] * 9 + [_D] * 7
+    lib.dpbah_create.argtypes = [_I] * 9 + [_D] * 7 + [_I]
     lib.dpbah_destroy.argtypes = [_P]
     lib.dpbah_handle.restype = _P
     lib.dpbah_handle.argtypes = [_P]
@@ -92,11 +92,11 @@ class CudaPhotometricBundleAdjustment:
 
     def __init__(self, width, height, max_frames=9, max_points=4096, device=0, estimate_uncertainty=True,
                  force_accept=True, max_iterations=7, min_iterations=3, radius=1e5, ftol=1e-8, ptol=1e-8,
-                 ab_reg=(1e12, 1e8), fixed_reg=1e16, sigma=20.0):
+                 ab_reg=(1e12, 1e8), fixed_reg=1e16, sigma=20.0, device_lm=True):
         self.lib = load_library()
         self.s = self.lib.dpbah_create(width, height, max_frames, max_points, device, int(estimate_uncertainty),
                                        int(force_accept), max_iterations, min_iterations, radius, ftol, ptol,
-                                       ab_reg[0], ab_reg[1], fixed_reg, sigma)
+                                       ab_reg[0], ab_reg[1], fixed_reg, sigma, int(device_lm))
         if not self.s:
             raise DpbaError("dpbah_create: " + self.lib.dpbah_last_error().decode())
         self.s = C.c_void_p(self.s)

@@ -192,14 +192,56 @@ int dpba_landmarks_energy(dpba_handle* h, int32_t for_marginalized, double* ener
 int dpba_update_point_statuses(dpba_handle* h, int32_t minimum_valid_reprojections, double sigma_huber,
                                double* energy_threshold);
 
+/* ---- device-resident solve --------------------------------------------------------------- */
+/* energy::levenberg_marquardt_algorithm::Options
+ * (energy/problems/include/energy/levenberg_marquardt_algorithm/levenberg_marquardt_algorithm.hpp:38-57) plus the
+ * problem constants of PhotometricBundleAdjustmentProblem (PBA/eigen_photometric_bundle_adjustment_problem.hpp:271-284) */
+typedef struct dpba_lm_options {
+  int32_t max_num_iterations;
+  int32_t min_num_iterations;
+  int32_t force_accept;
+  int32_t first_estimate_jacobians;
+  double initial_levenberg_marquardt_regularizer;
+  double function_tolerance;
+  double parameter_tolerance;
+  double levenberg_marquardt_regularizer_decrease_on_accept;
+  double levenberg_marquardt_regularizer_increase_on_reject;
+  double sigma_huber_loss;
+  double affine_brightness_regularizer[2];
+  double fixed_state_regularizer;
+} dpba_lm_options;
+
+/* levenberg_marquardt_algorithm::Result (:62-69) + the number of loop bodies executed */
+typedef struct dpba_lm_result {
+  double energy;
+  int32_t number_of_valid_residuals;
+  int32_t converged;
+  int32_t iterations;
+} dpba_lm_result;
+
+/* levenberg_marquardt_algorithm::solve(problem, options) (:77-128) with PhotometricBundleAdjustmentProblem's
+ * calculateEnergy / linearize / calculateStep / acceptStep / rejectStep (problem.hpp:290-402) executed ENTIRELY on
+ * the device: sweeps, priors, marginalised-prior terms, the Jacobi-preconditioned LDL^T of the 8N x 8N system and
+ * the accept/reject decisions, as one stream of kernel launches with a single host synchronisation at the end.
+ * H_marg [8N][8N] / b_marg [8N] may be NULL (no marginalised prior).  The caller runs dpba_first_estimate first,
+ * as EigenPhotometricBundleAdjustment::solve does.  On return the handle's frame state (dpba_get_state) is the
+ * accepted state with zero step. */
+int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* options, const double* H_marg, const double* b_marg,
+                  double energy_marg, dpba_lm_result* result);
+
+/* Tuning knobs without a reference counterpart.  "cuda_graph" (default 1): dpba_solve_lm replays its launch
+ * sequence as one CUDA graph. */
+int dpba_set_option(dpba_handle* h, const char* name, int64_t value);
+
 /* ---- measurement hooks (no reference counterpart) --------------------------------------- */
 /* kernels launched by this process so far (every launch wrapper counts itself) */
 int64_t dpba_launch_count(void);
 /* Per-kernel device timing with CUDA events recorded on the handle's stream around each launch.
  * kinds: 0 fused linearise sweep, 1 Schur SYRK, 2 residual-only sweep, 3 materialising sweep,
- *        4 assemble+symmetrise, 5 back-substitution.  dpba_profile_read synchronises, returns per kind the
+ *        4 assemble+symmetrise, 5 back-substitution, 6 per-pair constants, 7 device LM step (priors + LDL^T).
+ *        dpba_profile_read synchronises, returns per kind the
  *        summed milliseconds and launch counts since the last dpba_profile_enable(h, 1), and keeps profiling on. */
-#define DPBA_PROFILE_KINDS 6
+#define DPBA_PROFILE_KINDS 8
 int dpba_profile_enable(dpba_handle* h, int32_t on);
 int dpba_profile_read(dpba_handle* h, double ms[DPBA_PROFILE_KINDS], int32_t launches[DPBA_PROFILE_KINDS]);
 

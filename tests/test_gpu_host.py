@@ -114,3 +114,65 @@ def test_sliding_window_marginalisation_sequence():
         out = pba.update_frame(win.frames[i + 1].timestamp, len(fr.idepth))
         assert np.abs(out["T_w_agent"] - fr.t_world_agent()[:3, :4]).max() <= 1e-4
     pba.close()
+
+
+@pytest.mark.parametrize("ab_scale,ab_reg,force_accept,min_it", [(0.0, (1e12, 1e8), True, 3), (1.0, (10.0, 1e-2), True, 3),
+                                                               (0.0, (1e12, 1e8), False, 0)])
+def test_device_resident_lm_matches_host_lm_and_oracle(ab_scale, ab_reg, force_accept, min_it):
+    """dpba_solve_lm (whole LM loop on the device) vs the C++ host LM over the C ABI vs the NumPy oracle."""
+    from dsopp_b200 import capi, host
+    from oracle import pba_oracle as O
+    win = synth.make_window(n_frames=5, points_per_frame=300, seed=31, ab_scale=ab_scale)
+    ab0 = np.stack([f.ab0 for f in win.frames])
+    fixed = [int(f.fixed) for f in win.frames]
+    dec, inc = (1.0, 1.0) if force_accept else (2.0, 10.0)
+    frames = O.frames_from_window(win)
+    O.first_estimate_jacobians(frames)
+    trace = []
+    e_ref, n_ref, _ = O.lm_solve(O.Problem(frames, SIGMA, ab_reg=ab_reg),
+                                 O.LMOptions(7, 1e-5, 1e-8, 1e-8, force_accept, min_it, dec, inc), trace)
+    h1 = capi.upload_window(win)
+    e1, it1 = host.lm_solve(h1, ab0, fixed, SIGMA, ab_reg, 1e16, 7, min_it, 1e-8, 1e-8, force_accept, 1e-5, dec, inc)
+    h2 = capi.upload_window(win)
+    h2.first_estimate()
+    e2, it2, conv2, n2 = h2.solve_lm(SIGMA, ab_reg, 1e16, 7, min_it, 1e-8, 1e-8, force_accept, 1e-5, dec, inc)
+    print(f"oracle E={e_ref:.6f} it={len(trace)}  hostLM E={e1:.6f} it={it1}  deviceLM E={e2:.6f} it={it2}")
+    assert it2 == it1 == len(trace)
+    # same kernels; fp atomics order and the unpivoted device LDL^T differ from the host path at rounding level
+    assert abs(e2 - e1) <= 5e-5 * abs(e1)
+    assert abs(e2 - e_ref) <= 2e-4 * abs(e_ref)
+    assert abs(n2 - n_ref) <= 2
+    s1, _ = h1.get_state()
+    s2, st2 = h2.get_state()
+    assert np.abs(st2).max() == 0
+    assert np.abs(s2 - s1).max() <= 2e-5 * max(1.0, np.abs(ab0).max())
+    assert np.abs(s2 - O.state_eps_stacked(frames)).max() <= 2e-5 * max(1.0, np.abs(ab0).max())
+    for i, f in enumerate(frames):
+        a, b = h1.get_landmarks(i), h2.get_landmarks(i)
+        assert np.abs(a["idepth"] - b["idepth"]).max() <= 5e-5  # weakly observed idepths amplify rounding
+        assert np.abs(b["idepth_step"]).max() == 0
+        assert np.abs(b["idepth"] - f.idepth).max() <= 5e-5
+        for j in range(len(frames)):
+            if i != j:
+                assert (h1.get_statuses(i, j)[0] != h2.get_statuses(i, j)[0]).sum() <= 1
+    h1.close(), h2.close()
+
+
+def test_device_lm_with_marginalised_prior():
+    from dsopp_b200 import capi
+    from oracle import pba_oracle as O
+    win = synth.make_window(n_frames=4, points_per_frame=200, seed=32, ab_scale=0.0)
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(64, 32))
+    Hm = A.T @ A * 50.0
+    bm = rng.normal(size=32) * 5.0
+    frames = O.frames_from_window(win)
+    O.first_estimate_jacobians(frames)
+    e_ref, _, _ = O.lm_solve(O.Problem(frames, SIGMA, Hm, bm, 12.5), O.LMOptions(7, 1e-5, 1e-8, 1e-8, True, 3, 1.0, 1.0))
+    h = capi.upload_window(win)
+    h.first_estimate()
+    e, it, _, _ = h.solve_lm(SIGMA, H_marg=Hm, b_marg=bm, energy_marg=12.5)
+    assert abs(e - e_ref) <= 2e-4 * abs(e_ref)
+    s, _ = h.get_state()
+    assert np.abs(s - O.state_eps_stacked(frames)).max() <= 2e-5
+    h.close()
