@@ -55,6 +55,7 @@ struct FrameHost {
   int to_marg = 0;
   int is_marg = 0;
   int n_lm = 0;
+  int mask_all = 1;
   double eps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double step[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -70,13 +71,14 @@ struct dpba_handle {
   bool phys_used[PBA_MAXF] = {};
   float4* img[PBA_MAXF] = {};
   uint8_t* mask[PBA_MAXF] = {};
-  // landmark SoA
-  float2* uv = nullptr;
-  float *idepth = nullptr, *idepth_step = nullptr, *idepth_fej = nullptr, *patch = nullptr;
+  // landmark arrays
+  float4* lmk = nullptr;  // {u, v, idepth, idepth at the FEJ linearisation point}
+  float *idepth_step = nullptr, *patch = nullptr;
+  std::vector<float4> lmk_stage;
   uint8_t* flags = nullptr;
   float *inv_hdd = nullptr, *b_d = nullptr, *hpd = nullptr, *rel_baseline = nullptr;
   uint32_t* n_inliers = nullptr;
-  uint8_t *status = nullptr, *cand = nullptr;
+  uint8_t *status = nullptr, *cand = nullptr, *jac_valid = nullptr;
   float* energy = nullptr;
   PairConst* pairs = nullptr;
   PairAssemble* pasm = nullptr;
@@ -84,6 +86,11 @@ struct dpba_handle {
   FrameParams* fparams_h = nullptr;  // pinned
   double* red = nullptr;             // device reduction buffer (what the kernels accumulate into)
   double* red2 = nullptr;            // world_size > 1: out-of-place allreduce result of the exchanged block
+  float* core_part = nullptr;        // first-stage partials (see ReduceBuf)
+  float* fschur_part = nullptr;
+  double* core = nullptr;
+  double *schur_part = nullptr, *bs_part = nullptr, *e_part = nullptr, *n_part = nullptr;
+  int sm_count = 148;
   double* red_h = nullptr;           // pinned mirror
   // device-resident LM
   LmCtl* ctl = nullptr;
@@ -121,16 +128,25 @@ struct dpba_handle {
 
 namespace {
 
-constexpr size_t OFF_CORE = 0;
-constexpr size_t N_CORE = (size_t)PBA_MAXF * PBA_MAXF * PBA_CORE;
 constexpr size_t MAXD = PBA_MAXF * 8;
-constexpr size_t OFF_HS = OFF_CORE + N_CORE;
-constexpr size_t OFF_BS = OFF_HS + MAXD * MAXD;
-constexpr size_t OFF_SCAL = OFF_BS + MAXD;
-constexpr size_t N_EXCHANGE = OFF_SCAL + 8;  // [core | Hs | bs | scal] is what crosses NVLink
-constexpr size_t OFF_HP = N_EXCHANGE;
-constexpr size_t OFF_BP = OFF_HP + MAXD * MAXD;
-constexpr size_t N_RED = OFF_BP + MAXD;
+// exchange block [Hp | bp | Hs | bs | scal], packed for the CURRENT window (D = 8 n_frames): this is what crosses
+// NVLink, 2 (D^2 + D) + 8 doubles = 66.6 KB at 8 keyframes
+struct RedLayout {
+  size_t hp, bp, hs, bs, scal, n;
+};
+inline RedLayout red_layout(int n_frames) {
+  const size_t D = 8 * (size_t)n_frames;
+  RedLayout L;
+  L.hp = 0;
+  L.bp = D * D;
+  L.hs = L.bp + D;
+  L.bs = L.hs + D * D;
+  L.scal = L.bs + D;
+  L.n = L.scal + 8;
+  return L;
+}
+constexpr size_t N_RED = 2 * (MAXD * MAXD + MAXD) + 8;
+constexpr size_t N_EXCHANGE = N_RED;
 
 int fail(dpba_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -193,26 +209,35 @@ void profile_collect(dpba_handle* h) {
   cudaGetLastError();  // a failed elapsed-time query must not poison later cudaGetLastError() checks
 }
 
-// producers (sweeps, Schur, norms) accumulate into `red`
+// producers write `red` (and the first-stage partial buffers)
 ReduceBuf redbuf(dpba_handle* h) {
   ReduceBuf rb;
-  rb.core = h->red + OFF_CORE;
-  rb.Hs = h->red + OFF_HS;
-  rb.bs = h->red + OFF_BS;
-  rb.scal = h->red + OFF_SCAL;
-  rb.Hp = h->red + OFF_HP;
-  rb.bp = h->red + OFF_BP;
+  const RedLayout L = red_layout(h->n_frames);
+  rb.Hp = h->red + L.hp;
+  rb.bp = h->red + L.bp;
+  rb.Hs = h->red + L.hs;
+  rb.bs = h->red + L.bs;
+  rb.scal = h->red + L.scal;
+  rb.core_part = h->core_part;
+  rb.fschur_part = h->fschur_part;
+  rb.core = h->core;
+  rb.schur_part = h->schur_part;
+  rb.bs_part = h->bs_part;
+  rb.e_part = h->e_part;
+  rb.n_part = h->n_part;
   return rb;
 }
-// consumers (assembly, device solve, readback) read the cross-rank sums: `red2` when world_size > 1 (out-of-place
-// allreduce, so a skipped linearisation re-reduces the same partials instead of summing sums), else `red` itself
+// consumers (device solve, energy decision, readback) read the cross-rank sums: `red2` when world_size > 1
+// (out-of-place allreduce, so a skipped linearisation re-reduces the same partials instead of summing sums)
 ReduceBuf redbuf_out(dpba_handle* h) {
   ReduceBuf rb = redbuf(h);
   if (h->world > 1 && h->comm) {
-    rb.core = h->red2 + OFF_CORE;
-    rb.Hs = h->red2 + OFF_HS;
-    rb.bs = h->red2 + OFF_BS;
-    rb.scal = h->red2 + OFF_SCAL;
+    const RedLayout L = red_layout(h->n_frames);
+    rb.Hp = h->red2 + L.hp;
+    rb.bp = h->red2 + L.bp;
+    rb.Hs = h->red2 + L.hs;
+    rb.bs = h->red2 + L.bs;
+    rb.scal = h->red2 + L.scal;
   }
   return rb;
 }
@@ -231,13 +256,12 @@ WindowDev make_window(dpba_handle* h) {
     w.fixed[f] = F.fixed;
     w.frame_marg[f] = F.is_marg;
     w.phys[f] = F.phys;
+    w.mask_all[f] = F.mask_all;
     w.img[f] = h->img[F.phys];
     w.mask[f] = h->mask[F.phys];
   }
-  w.uv = h->uv;
-  w.idepth = h->idepth;
+  w.lmk = h->lmk;
   w.idepth_step = h->idepth_step;
-  w.idepth_fej = h->idepth_fej;
   w.patch = h->patch;
   w.flags = h->flags;
   w.inv_hdd = h->inv_hdd;
@@ -247,6 +271,7 @@ WindowDev make_window(dpba_handle* h) {
   w.n_inliers = h->n_inliers;
   w.status = h->status;
   w.cand = h->cand;
+  w.jac_valid = h->jac_valid;
   w.energy = h->energy;
   w.pairs = h->pairs;
   w.pairs_asm = h->pasm;
@@ -305,12 +330,19 @@ int ensure_materialized(dpba_handle* h) {
 }
 
 // sum the [core | Hs | bs | scal] block over ranks (one fused in-place NCCL allreduce on the compute stream)
-int exchange(dpba_handle* h, size_t off, size_t n) {
+enum { EX_SYSTEM = 0, EX_SCAL = 1 };
+int exchange_raw(dpba_handle* h, size_t off, size_t n) {
   if (h->world <= 1 || !h->comm) return 0;
   NcclApi& nc = nccl_api();
   ncclResult_t r = nc.AllReduce(h->red + off, h->red2 + off, n, ncclDouble, ncclSum, h->comm, h->stream);
   if (r != ncclSuccess) return fail(h, DPBA_E_COMM, std::string("ncclAllReduce: ") + nc.GetErrorString(r));
   return 0;
+}
+
+// one fused in-place-shaped allreduce of either the linear system [Hp | bp | Hs | bs] or the 8 scalars
+int exchange(dpba_handle* h, int what) {
+  const RedLayout L = red_layout(h->n_frames);
+  return what == EX_SYSTEM ? exchange_raw(h, L.hp, L.scal - L.hp) : exchange_raw(h, L.scal, 8);
 }
 
 void host_se3_exp_translation(const double* T_lin, const double* eps, double* t_out) {
@@ -381,6 +413,8 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
     const size_t a = ((size_t)(phys * PBA_MAXF + p)) * mp, b = ((size_t)(p * PBA_MAXF + phys)) * mp;
     CK(cudaMemsetAsync(h->status + a, 0, mp, h->stream));
     CK(cudaMemsetAsync(h->cand + a, 0, mp, h->stream));
+    CK(cudaMemsetAsync(h->jac_valid + a, 0, mp, h->stream));
+    CK(cudaMemsetAsync(h->jac_valid + b, 0, mp, h->stream));
     CK(cudaMemsetAsync(h->energy + a, 0, mp * sizeof(float), h->stream));
     CK(cudaMemsetAsync(h->status + b, 0, mp, h->stream));
     CK(cudaMemsetAsync(h->cand + b, 0, mp, h->stream));
@@ -397,6 +431,8 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
   F.ab0[1] = ab0[1];
   memcpy(F.intr, intr, sizeof(F.intr));
   F.fixed = fixed ? 1 : 0;
+  F.mask_all = 1;
+  if (mask) F.mask_all = memchr(mask, 0, npx) == nullptr;
   h->phys_used[phys] = true;
   h->linearized = false;
   return h->n_frames++;
@@ -406,9 +442,9 @@ int upload_landmarks(dpba_handle* h, int slot, int first, int n, const float* uv
                      const float* patch, const uint8_t* flags) {
   const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame + first;
   if (n == 0) return 0;
-  CK(cudaMemcpyAsync(h->uv + base, uv, sizeof(float2) * n, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->idepth + base, idepth, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->idepth_fej + base, idepth, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  h->lmk_stage.resize(n);
+  for (int l = 0; l < n; ++l) h->lmk_stage[l] = make_float4(uv[2 * l], uv[2 * l + 1], idepth[l], idepth[l]);
+  CK(cudaMemcpyAsync(h->lmk + base, h->lmk_stage.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->patch + base * 8, patch, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, h->stream));
   if (flags) CK(cudaMemcpyAsync(h->flags + base, flags, n, cudaMemcpyHostToDevice, h->stream));
   else CK(cudaMemsetAsync(h->flags + base, 0, n, h->stream));
@@ -467,10 +503,10 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
     CKC(cudaMalloc(&h->img[p], npx * sizeof(float4)));
     CKC(cudaMalloc(&h->mask[p], npx));
   }
-  CKC(cudaMalloc(&h->uv, nlm * sizeof(float2)));
-  CKC(cudaMalloc(&h->idepth, nlm * sizeof(float)));
+  CKC(cudaMalloc(&h->lmk, nlm * sizeof(float4)));
+  CKC(cudaMemset(h->lmk, 0, nlm * sizeof(float4)));
   CKC(cudaMalloc(&h->idepth_step, nlm * sizeof(float)));
-  CKC(cudaMalloc(&h->idepth_fej, nlm * sizeof(float)));
+  CKC(cudaMemset(h->idepth_step, 0, nlm * sizeof(float)));
   CKC(cudaMalloc(&h->patch, nlm * 8 * sizeof(float)));
   CKC(cudaMalloc(&h->flags, nlm));
   CKC(cudaMalloc(&h->inv_hdd, nlm * sizeof(float)));
@@ -480,6 +516,8 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   CKC(cudaMalloc(&h->n_inliers, nlm * sizeof(uint32_t)));
   CKC(cudaMalloc(&h->status, nres));
   CKC(cudaMalloc(&h->cand, nres));
+  CKC(cudaMalloc(&h->jac_valid, nres));
+  CKC(cudaMemset(h->jac_valid, 0, nres));  // ResidualPoint::reprojection_jacobians_valid = false (local_frame.hpp:191)
   CKC(cudaMalloc(&h->energy, nres * sizeof(float)));
   CKC(cudaMemset(h->status, 0, nres));
   CKC(cudaMemset(h->cand, 0, nres));
@@ -493,6 +531,21 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   h->red_n = N_RED;
   CKC(cudaMalloc(&h->red, N_RED * sizeof(double)));
   CKC(cudaMallocHost(&h->red_h, N_RED * sizeof(double)));
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  if (h->sm_count <= 0) h->sm_count = 148;
+  {
+    const size_t maxd = (size_t)8 * cfg->max_frames;
+    const size_t chunks = (mp + 7) / 8;  // k_linearize_fused never uses fewer than 8 landmarks per CTA
+    CKC(cudaMalloc(&h->core_part, (size_t)cfg->max_frames * chunks * (cfg->max_frames - 1) * PBA_CORE * sizeof(float)));
+    const size_t t4 = maxd / 4, nout = t4 * (t4 + 1) / 2 * 16 + maxd;
+    CKC(cudaMalloc(&h->fschur_part, (size_t)cfg->max_frames * chunks * nout * sizeof(float)));
+    CKC(cudaMalloc(&h->schur_part, (size_t)h->sm_count * maxd * maxd * sizeof(double)));
+    CKC(cudaMalloc(&h->core, (size_t)PBA_MAXF * PBA_MAXF * PBA_CORE * sizeof(double)));
+    CKC(cudaMalloc(&h->bs_part, (size_t)h->sm_count * maxd * sizeof(double)));
+    const size_t sweep_ctas = ((mp + 31) / 32) * (size_t)cfg->max_frames * (cfg->max_frames - 1);
+    CKC(cudaMalloc(&h->e_part, sweep_ctas * 2 * sizeof(double)));
+    CKC(cudaMalloc(&h->n_part, ((mp + 31) / 32) * (size_t)cfg->max_frames * 2 * sizeof(double)));
+  }
   CKC(cudaMalloc(&h->red2, N_EXCHANGE * sizeof(double)));
   CKC(cudaMemset(h->red2, 0, N_EXCHANGE * sizeof(double)));
   CKC(cudaMalloc(&h->ctl, sizeof(LmCtl)));
@@ -522,11 +575,12 @@ int dpba_destroy(dpba_handle* h) {
     cudaFree(h->img[p]);
     cudaFree(h->mask[p]);
   }
-  void* dev[] = {h->uv,      h->idepth, h->idepth_step,  h->idepth_fej, h->patch,  h->flags,   h->inv_hdd,
+  void* dev[] = {h->lmk,     h->jac_valid, h->idepth_step,              h->patch,  h->flags,   h->inv_hdd,
                  h->b_d,     h->hpd,    h->rel_baseline, h->n_inliers,  h->status, h->cand,    h->energy,
                  h->pairs,   h->pasm,   h->fparams,      h->red,        h->step_dev, h->pair_dist, h->stage,
                  h->m_r,     h->m_jref, h->m_jtgt,       h->m_did,      h->m_w,    h->red2,    h->ctl,
-                 h->lmopt,   h->fixed_dev, h->marg_dev};
+                 h->lmopt,   h->fixed_dev, h->marg_dev, h->core_part, h->fschur_part, h->core, h->schur_part, h->bs_part, h->e_part,
+                 h->n_part};
   for (void* p : dev) cudaFree(p);
   cudaFreeHost(h->fparams_h);
   cudaFreeHost(h->red_h);
@@ -631,7 +685,9 @@ int dpba_get_landmarks(dpba_handle* h, int32_t slot, int32_t n, float* idepth, f
   REQUIRE(n >= 0 && n <= h->fr[slot].n_lm, "n exceeds the landmark count");
   const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame;
   if (n == 0) return DPBA_SUCCESS;
-  if (idepth) CK(cudaMemcpyAsync(idepth, h->idepth + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (idepth)
+    CK(cudaMemcpy2DAsync(idepth, sizeof(float), reinterpret_cast<const float*>(h->lmk + base) + 2, sizeof(float4),
+                         sizeof(float), n, cudaMemcpyDeviceToHost, h->stream));
   if (idepth_step)
     CK(cudaMemcpyAsync(idepth_step, h->idepth_step + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
   if (inv_hdd) CK(cudaMemcpyAsync(inv_hdd, h->inv_hdd + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -702,8 +758,11 @@ int dpba_get_state(dpba_handle* h, double* eps, double* step) {
 
 int dpba_first_estimate(dpba_handle* h) {
   REQUIRE(h, "null handle");
+  REQUIRE(h->n_frames >= 2, "need at least two frames");
+  int rc = sync_pairs(h);  // the linearisation-point constants (M0, t0) of every pair
+  if (rc) return rc;
   WindowDev w = make_window(h);
-  pba::launch_snapshot_fej(w, h->stream);
+  pba::launch_first_estimate(w, h->stream);
   CK(cudaGetLastError());
   return DPBA_SUCCESS;
 }
@@ -717,17 +776,19 @@ int dpba_evaluate(dpba_handle* h, double sigma, int32_t huber, int32_t fej, doub
   ReduceBuf rb = redbuf(h);
   CK(cudaMemsetAsync(rb.scal, 0, 8 * sizeof(double), h->stream));
   WindowDev w = make_window(h);
+  int n_e;
   {
     ProfScope ps(h, 2);
-    pba::launch_residual_sweep(w, (float)sigma, huber, fej, rb.scal, h->stream);
+    n_e = pba::launch_residual_sweep(w, (float)sigma, huber, fej, rb.e_part, h->stream);
   }
+  pba::launch_reduce_scal(nullptr, 0, rb.e_part, n_e, nullptr, 0, rb.scal, h->stream);
   CK(cudaGetLastError());
-  rc = exchange(h, OFF_SCAL, 8);
+  rc = exchange(h, EX_SCAL);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h->red_h + OFF_SCAL, redbuf_out(h).scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->red_h, redbuf_out(h).scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (energy) *energy = h->red_h[OFF_SCAL + 0];
-  if (n_valid) *n_valid = (int32_t)llround(h->red_h[OFF_SCAL + 1]);
+  if (energy) *energy = h->red_h[0];
+  if (n_valid) *n_valid = (int32_t)llround(h->red_h[1]);
   return DPBA_SUCCESS;
 }
 
@@ -787,23 +848,19 @@ static int linearize_impl(dpba_handle* h, double sigma, int32_t huber, int32_t f
   CK(cudaMemsetAsync(h->red, 0, N_RED * sizeof(double), h->stream));
   WindowDev w = make_window(h);
   if (fused) {
+    FusedShape shape;
     {
       ProfScope ps(h, 0);
-      pba::launch_linearize_fused(w, (float)sigma, huber, fej, for_marg, rb, h->stream);
+      shape = pba::launch_linearize_fused(w, (float)sigma, huber, fej, for_marg, rb, h->stream);
     }
     CK(cudaGetLastError());
-    {
-      ProfScope ps(h, 1);
-      pba::launch_schur(w, for_marg, rb, h->stream);
-    }
-    CK(cudaGetLastError());
-    if ((rc = exchange(h, OFF_CORE, N_EXCHANGE))) return rc;
     {
       ProfScope ps(h, 4);
-      ReduceBuf ro = redbuf_out(h);
-      pba::launch_assemble(w, fej, ro, h->stream);
+      pba::launch_assemble(w, fej, rb, shape, h->stream);
+      pba::launch_finish_fused(w, rb, shape, h->stream);
     }
   } else {
+    if (h->world > 1 && h->comm) return fail(h, DPBA_E_STATE, "dpba_linearize_materialized is single-GPU only");
     {
       ProfScope ps(h, 3);
       pba::launch_materialise_sweep(w, (float)sigma, huber, fej, h->stream);
@@ -811,21 +868,21 @@ static int linearize_impl(dpba_handle* h, double sigma, int32_t huber, int32_t f
     CK(cudaGetLastError());
     pba::launch_linearize_from_materialized(w, for_marg, rb, h->stream);
     CK(cudaGetLastError());
-    pba::launch_schur(w, for_marg, rb, h->stream);
+    const int nsb = pba::launch_schur(w, for_marg, rb, h->stream);
     CK(cudaGetLastError());
-    if (h->world > 1 && h->comm) return fail(h, DPBA_E_STATE, "dpba_linearize_materialized is single-GPU only");
-    pba::launch_symmetrise_only(D, rb.Hp, h->stream);
+    pba::launch_finish_system(D, rb, nsb, h->stream);
   }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(h->red_h + OFF_HS, redbuf_out(h).Hs, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(h->red_h + OFF_BS, redbuf_out(h).bs, D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(h->red_h + OFF_HP, rb.Hp, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(h->red_h + OFF_BP, rb.bp, D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = exchange(h, EX_SYSTEM))) return rc;
+  CK(cudaGetLastError());
+  const RedLayout L = red_layout(N);
+  // [Hp | bp | Hs | bs] is contiguous: one device-to-host copy
+  CK(cudaMemcpyAsync(h->red_h, redbuf_out(h).Hp, (L.scal - L.hp) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (H_pose) memcpy(H_pose, h->red_h + OFF_HP, (size_t)D * D * sizeof(double));
-  if (b_pose) memcpy(b_pose, h->red_h + OFF_BP, D * sizeof(double));
-  if (H_schur) memcpy(H_schur, h->red_h + OFF_HS, (size_t)D * D * sizeof(double));
-  if (b_schur) memcpy(b_schur, h->red_h + OFF_BS, D * sizeof(double));
+  if (H_pose) memcpy(H_pose, h->red_h + L.hp, (size_t)D * D * sizeof(double));
+  if (b_pose) memcpy(b_pose, h->red_h + L.bp, D * sizeof(double));
+  if (H_schur) memcpy(H_schur, h->red_h + L.hs, (size_t)D * D * sizeof(double));
+  if (b_schur) memcpy(b_schur, h->red_h + L.bs, D * sizeof(double));
   return DPBA_SUCCESS;
 }
 
@@ -864,11 +921,11 @@ int dpba_accept(dpba_handle* h, double* state_sq, double* step_sq) {
   pba::launch_accept(w, 1, rb.scal, h->stream);
   pba::launch_change_statuses(w, 1, h->stream);
   CK(cudaGetLastError());
-  int rc = exchange(h, OFF_SCAL, 8);
+  int rc = exchange(h, EX_SCAL);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h->red_h + OFF_SCAL, redbuf_out(h).scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->red_h, redbuf_out(h).scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  double st = h->red_h[OFF_SCAL + 2], sp = h->red_h[OFF_SCAL + 3];
+  double st = h->red_h[2], sp = h->red_h[3];
   for (int f = 0; f < h->n_frames; ++f) {  // problem.hpp:369-376
     FrameHost& F = h->fr[f];
     for (int k = 0; k < 8; ++k) st += F.eps[k] * F.eps[k];
@@ -912,12 +969,12 @@ int dpba_landmarks_energy(dpba_handle* h, int32_t for_marg, double* energy, int3
   WindowDev w = make_window(h);
   pba::launch_landmarks_energy(w, for_marg, rb.scal, h->stream);
   CK(cudaGetLastError());
-  int rc = exchange(h, OFF_SCAL, 8);
+  int rc = exchange(h, EX_SCAL);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h->red_h + OFF_SCAL, redbuf_out(h).scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->red_h, redbuf_out(h).scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (energy) *energy = h->red_h[OFF_SCAL];
-  if (n_valid) *n_valid = (int32_t)llround(h->red_h[OFF_SCAL + 1]);
+  if (energy) *energy = h->red_h[0];
+  if (n_valid) *n_valid = (int32_t)llround(h->red_h[1]);
   return DPBA_SUCCESS;
 }
 
@@ -995,64 +1052,69 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
 
   pba::launch_lm_init(h->ctl, h->lmopt, s);
   pairs();
+  // residual-only sweep + calculateEnergy tail.  Single GPU: k_lm_energy sums the per-CTA partials itself; with
+  // several ranks the partials are summed first so that the 8 scalars can cross NVLink before the decision.
+  const bool multi = h->world > 1 && h->comm;
+  auto energy_eval = [&](int ctl_mode, int n_norm_parts, int kind) -> int {
+    int n_e;
+    {
+      ProfScope ps(h, 2);
+      n_e = pba::launch_residual_sweep(w, sigma, 1, fej, rb.e_part, s, h->ctl, ctl_mode);
+    }
+    if (multi) {
+      pba::launch_reduce_scal(h->ctl, ctl_mode, rb.e_part, n_e, n_norm_parts ? rb.n_part : nullptr, n_norm_parts, rb.scal, s);
+      const int rc2 = exchange(h, EX_SCAL);
+      if (rc2) return rc2;
+      if (kind != pba::LM_ENERGY_FINAL)
+        pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, ro.scal, Hm, bm, kind, s);
+    } else if (kind != pba::LM_ENERGY_FINAL) {
+      pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, rb.scal, Hm, bm, kind, s, rb.e_part, n_e,
+                            n_norm_parts ? rb.n_part : nullptr, n_norm_parts);
+    }
+    return 0;
+  };
+  const int m_max = [&]() {
+    int m = 0;
+    for (int f = 0; f < N; ++f) m = std::max(m, h->fr[f].n_lm);
+    return m;
+  }();
+  const int n_norm_parts = ((m_max + 31) / 32) * N;  // CTAs of k_back_substitute
   // result.energy = problem.calculateEnergy()
-  pba::launch_lm_zero(h->ctl, rb.scal, 8, 0, s);
-  {
-    ProfScope ps(h, 2);
-    pba::launch_residual_sweep(w, sigma, 1, fej, rb.scal, s, h->ctl, 0);
-  }
-  if ((rc = exchange(h, OFF_SCAL, 8))) return rc;
-  pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, ro.scal, Hm, bm, pba::LM_ENERGY_INITIAL, s);
+  if ((rc = energy_eval(0, 0, pba::LM_ENERGY_INITIAL))) return rc;
   for (int it = 0; it < od.max_it; ++it) {
-    // linearize()
-    pba::launch_lm_zero(h->ctl, h->red, (int)N_RED, 2, s);
-    if (it > 0) pairs();
+    // linearize().  The per-pair constants are already those of the current state: an accepted trial state IS the
+    // new state (eps + step, bit for bit), and after a rejection the loop either ends (force_accept) or keeps the
+    // previous linear system and skips the sweep.
+    FusedShape shape;
     {
       ProfScope ps(h, 0);
-      pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl);
+      shape = pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl);
     }
-    {
-      ProfScope ps(h, 1);
-      pba::launch_schur(w, 0, rb, s, h->ctl);
-    }
-    if ((rc = exchange(h, OFF_CORE, OFF_SCAL - OFF_CORE))) return rc;
     {
       ProfScope ps(h, 4);
-      ReduceBuf ra = ro;
-      ra.Hp = rb.Hp;
-      ra.bp = rb.bp;
-      pba::launch_assemble(w, fej, ra, s, h->ctl);
+      pba::launch_assemble(w, fej, rb, shape, s, h->ctl);
+      pba::launch_finish_fused(w, rb, shape, s, h->ctl);
     }
+    if ((rc = exchange(h, EX_SYSTEM))) return rc;
     // calculateStep(lambda)
     {
       ProfScope ps(h, 7);
       pba::launch_lm_step(h->ctl, h->lmopt, h->fparams, h->fixed_dev, N, ro, Hm, bm, h->step_dev, s);
     }
-    pba::launch_lm_zero(h->ctl, rb.scal, 8, 1, s);
     {
       ProfScope ps(h, 5);
-      pba::launch_back_substitute(w, h->step_dev, 0.0, s, h->ctl, rb.scal);
+      pba::launch_back_substitute(w, h->step_dev, 0.0, s, h->ctl, rb.n_part);
     }
     // calculateEnergy() at state + step
     pairs();
-    {
-      ProfScope ps(h, 2);
-      pba::launch_residual_sweep(w, sigma, 1, fej, rb.scal, s, h->ctl, 1);
-    }
-    if ((rc = exchange(h, OFF_SCAL, 8))) return rc;
-    pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, ro.scal, Hm, bm, pba::LM_ENERGY_TRIAL, s);
-    // acceptStep() / rejectStep()
-    pba::launch_accept(w, 0, nullptr, s, h->ctl);
-    pba::launch_change_statuses(w, 0, s, h->ctl);
+    if ((rc = energy_eval(1, n_norm_parts, pba::LM_ENERGY_TRIAL))) return rc;
+    // acceptStep() / rejectStep() incl. changeResidualStatuses
+    pba::launch_accept(w, 0, nullptr, s, h->ctl, 1);
     pba::launch_lm_finish(h->ctl, h->lmopt, h->fparams, N, s);
   }
   // the trailing problem.calculateEnergy() of both exits (lm.hpp:119,126)
   pairs();
-  pba::launch_lm_zero(h->ctl, rb.scal, 8, 0, s);
-  {
-    ProfScope ps(h, 2);
-    pba::launch_residual_sweep(w, sigma, 1, fej, rb.scal, s, h->ctl, 0);
-  }
+  if ((rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
@@ -1164,6 +1226,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
   REQUIRE(h && name, "null argument");
   if (!strcmp(name, "cuda_graph")) {
     h->use_graph = value != 0;
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "schur_tensor_cores")) {  // process-wide
+    pba::set_schur_mma(value != 0);
+    h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
   return fail(h, DPBA_E_INVALID, std::string("unknown option ") + name);

@@ -14,12 +14,12 @@
 // state (k_pair_setup) and rounded to fp32.  Replaces the ArrayReprojector members
 // (src/energy/projector/include/energy/projector/camera_reproject.hpp:235-260,369-377) and the per-pair
 // prologue of evaluateJacobians (evaluate_jacobians.hpp:36-66).
-struct PairConst {
+struct __align__(16) PairConst {   // 512 bytes, every member 16-byte aligned for LDS.128 / LDG.128
   float A[12];     // reproject_            = K_t [R|t] Kr^-1  at the CURRENT state (eps + step)
   float M[12];     // transform_unproject_  = [R|t] Kr^-1      at the current state
-  float tr[3];     // translation_ at the current state
   float M0[12];    // transform_unproject_ at the linearisation point (first_estimate_jacobians.hpp:28-32)
-  float t0[3];     // translation_ at the linearisation point
+  float tr[4];     // translation_ at the current state (+ pad)
+  float t0[4];     // translation_ at the linearisation point (+ pad)
   float adj[36];   // Adj(T_t_r)   row-major (rightLogTransformer, se3_motion.hpp:245)
   float adj0[36];  // Adj(T_t_r0)
   float s;         // brightness_change_scale at the current state (evaluate_jacobians.hpp:56-57)
@@ -28,9 +28,10 @@ struct PairConst {
   float b_t;       // target affine shift, current
   float b_r;       // reference affine shift, current
   float b_r0;      // reference affine shift at the linearisation point
-  float fx_t, fy_t, cx_t, cy_t;
-  float pad[2];
+  float fx_t, fy_t;
+  float cx_t, cy_t, pad0, pad1;
 };
+static_assert(sizeof(PairConst) == 512, "PairConst layout");
 
 // blockdiag(Adj^T, 1, s') per pair in double for the final assembly (J_ref = U B^T, J_tgt = -U)
 struct PairAssemble {
@@ -54,13 +55,12 @@ struct WindowDev {
   int fixed[PBA_MAXF];
   int frame_marg[PBA_MAXF];  // LocalFrame::is_marginalized
   int phys[PBA_MAXF];        // logical slot -> physical storage slot
+  int mask_all[PBA_MAXF];    // 1: the frame's mask has no zero, the lookup can be skipped
   const float4* img[PBA_MAXF];     // {I, dx, dy, 0} per pixel
   const uint8_t* mask[PBA_MAXF];
-  // landmark SoA, frame f at [phys[f] * max_pts, phys[f] * max_pts + n_lm[f])
-  const float2* uv;
-  float* idepth;
+  // landmark arrays, frame f at [phys[f] * max_pts, phys[f] * max_pts + n_lm[f])
+  float4* lmk;             // {u, v, idepth, idepth at the FEJ linearisation point}: one LDG.128 per landmark
   float* idepth_step;
-  float* idepth_fej;
   const float* patch;      // [lm][8]
   uint8_t* flags;
   float* inv_hdd;
@@ -71,6 +71,7 @@ struct WindowDev {
   // per residual (r, t, l) -> ((phys[r] * PBA_MAXF + phys[t]) * max_pts + l)
   uint8_t* status;
   uint8_t* cand;
+  uint8_t* jac_valid;      // ResidualPoint::reprojection_jacobians_valid of the FEJ pass (K6)
   float* energy;
   const PairConst* pairs;          // [PBA_MAXF * PBA_MAXF]
   const PairAssemble* pairs_asm;
@@ -82,17 +83,25 @@ struct WindowDev {
   float* m_w;      // [res]
 };
 
-// reduction buffer layout (doubles), also the multi-GPU exchange buffer:
-//   core  [PBA_MAXF*PBA_MAXF][PBA_CORE]   per ordered pair
-//   Hs    [D*D], bs [D]                   Schur complement (D = 8 n_frames)
-//   scal  [8]: 0 energy, 1 n_valid, 2 state_sq, 3 step_sq
+// reduction buffer (doubles), also the multi-GPU exchange buffer: [Hp | bp | Hs | bs | scal], D = 8 n_frames
 struct ReduceBuf {
-  double* core;
-  double* Hs;
-  double* bs;
-  double* scal;
-  double* Hp;   // assembled pose-pose H [D*D] (not exchanged)
+  double* Hp;   // assembled pose-pose H [D*D]
   double* bp;   // [D]
+  double* Hs;   // Schur complement [D*D]
+  double* bs;   // [D]
+  double* scal; // [8]: 0 energy, 1 n_valid, 2 state_sq, 3 step_sq
+  // first-stage partials (one slot per CTA / warp, never exchanged): hot-spot atomics are avoided on purpose --
+  // 10^5 fp64 atomics into a few KB serialise in a handful of L2 slices and cost more than the sweep itself
+  float* core_part;    // [host frame][chunk][target warp][PBA_CORE]
+  double* core;        // [PBA_MAXF * PBA_MAXF][PBA_CORE] per ordered pair, summed over the chunks
+  float* fschur_part;  // fused path: [host frame][chunk][ntri*16 + D] per-chunk Schur partial
+  double* schur_part;  // stand-alone SYRK kernel: [CTA][D*D] upper triangle
+  double* bs_part;     // [SYRK CTA][D]
+  double* e_part;      // [residual-sweep CTA] (energy, n_valid)
+  double* n_part;      // [back-substitution CTA] (state_sq, step_sq)
+};
+struct FusedShape {
+  int lpb, chunks;  // landmarks per CTA and CTAs per host frame of the last k_linearize_fused launch
 };
 
 // ---- device-resident Levenberg-Marquardt (levenberg_marquardt_algorithm.hpp:77-128 on the device) --------------
@@ -113,32 +122,39 @@ namespace pba {
 enum { LM_ENERGY_INITIAL = 0, LM_ENERGY_TRIAL = 1, LM_ENERGY_FINAL = 2 };
 void launch_lm_init(LmCtl* ctl, const LmOptionsDev* opt, cudaStream_t s);
 void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s);
-void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr, int N, const double* scal,
-                      const double* Hmarg, const double* bmarg, int kind, cudaStream_t s);
+void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr, int N, double* scal,
+                      const double* Hmarg, const double* bmarg, int kind, cudaStream_t s, const double* e_part = nullptr,
+                      int n_e = 0, const double* n_part = nullptr, int n_n = 0);
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
                     const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s);
 void launch_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, cudaStream_t s);
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
 void launch_pack_image(const float* src3, float4* dst, int n_px, cudaStream_t s);
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s);
-void launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* scal, cudaStream_t s,
-                           const LmCtl* ctl = nullptr, int ctl_mode = 0);
+int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* e_part, cudaStream_t s,
+                          const LmCtl* ctl = nullptr, int ctl_mode = 0);
+void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, int n_e, const double* n_part, int n_n,
+                        double* scal, cudaStream_t s);
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s);
-void launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
-                            cudaStream_t s, const LmCtl* ctl = nullptr);
+FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
+                                  cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_linearize_from_materialized(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
-void launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
-void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
-void launch_symmetrise_only(int D, double* Hp, cudaStream_t s);
+int launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
+void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,
+                     const LmCtl* ctl = nullptr);
+void launch_finish_system(int D, ReduceBuf rb, int nsb, cudaStream_t s, const LmCtl* ctl = nullptr);
+void launch_finish_fused(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, double lambda, cudaStream_t s,
                             const LmCtl* ctl = nullptr, double* norms = nullptr);
-void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s, const LmCtl* ctl = nullptr);
+void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s, const LmCtl* ctl = nullptr,
+                   int with_statuses = 0);
 void launch_change_statuses(const WindowDev& w, int accept, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cudaStream_t s);
-void launch_snapshot_fej(const WindowDev& w, cudaStream_t s);
+void launch_first_estimate(const WindowDev& w, cudaStream_t s);  // K6: idepth snapshot + reprojection_jacobians_valid
 void launch_apply_point_statuses(const WindowDev& w, float threshold, int min_valid, const float* pair_dist,
                                  cudaStream_t s);
 int sm_count();
 long long launch_count();
 void add_launches(long long n);
+void set_schur_mma(bool on);
 }  // namespace pba

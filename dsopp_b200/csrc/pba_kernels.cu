@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "pba_internal.h"
@@ -38,12 +39,6 @@ __device__ __forceinline__ bool in_roi(float x, float y, float xmax, float ymax)
 }
 // camera_model_base.hpp:68-74
 __device__ __forceinline__ bool valid_idepth(float r) { return r > -1e-4f && r < 1010.f; }
-
-// rows of a 3x4 matrix applied to [u, v, 1, rho] with the reference's association
-// (A[:, :2] uv) + (A[:,2] + A[:,3] rho)   (camera_reproject.hpp:283-284,323-325), no FMA contraction
-__device__ __forceinline__ float row_apply(const float* a, float u, float v, float rho) {
-  return __fadd_rn(__fadd_rn(__fmul_rn(a[0], u), __fmul_rn(a[1], v)), __fadd_rn(a[2], __fmul_rn(a[3], rho)));
-}
 
 __device__ __forceinline__ bool group_all(bool p, int lane) {
   unsigned b = __ballot_sync(FULL, p);
@@ -125,130 +120,175 @@ struct PixelOut {
   bool ev;     // ok && committed status == kOk  -> residual was evaluated
 };
 
+__device__ __forceinline__ float4 ldf4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// row of a 3x4 matrix applied to [u, v, 1, rho] with the reference's association
+// (A[:, :2] uv) + (A[:,2] + A[:,3] rho)   (camera_reproject.hpp:283-284,323-325), no FMA contraction
+__device__ __forceinline__ float row_apply4(const float4 a, float u, float v, float rho) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a.x, u), __fmul_rn(a.y, v)), __fadd_rn(a.z, __fmul_rn(a.w, rho)));
+}
+
 // Evaluates one pattern pixel of one patch-residual.  All 8 lanes of a group must call it together.
 //   FEJ : first-estimate Jacobians (production)   JAC : evaluate Jacobians
+//   jv  : reprojection_jacobians_valid of the FEJ pass (ignored unless FEJ)
+// The body is branch-free: when the residual is not evaluated every load goes to a safe texel and every
+// output is selected to zero, so the warp never diverges around the shuffles.
 template <bool FEJ, bool JAC>
-__device__ __forceinline__ void eval_pixel(const PairConst& pc, const LandmarkIn& lm, const float4* __restrict__ img,
-                                           const uint8_t* __restrict__ mask, int W, int H, int status, float sigma,
-                                           int huber, int lane, PixelOut& o) {
-  const int px = lane & 7;
+__device__ __forceinline__ void eval_pixel(const PairConst& pc, const LandmarkIn& lm, bool jv,
+                                           const float4* __restrict__ img, const uint8_t* __restrict__ mask, int W,
+                                           int H, int status, float sigma, int huber, int lane, float pox, float poy,
+                                           PixelOut& o) {
   const float xmax = (float)(W - 5), ymax = (float)(H - 5);
-  const float ur = lm.u + pat_x(px), vr = lm.v + pat_y(px);
+  const float ur = lm.u + pox, vr = lm.v + poy;  // pattern offsets of this lane's pixel, hoisted by the caller
 
   bool ok = valid_idepth(lm.rho) && in_roi(ur, vr, xmax, ymax);
   float tu, tv;
   float qx = 0.f, qy = 0.f, qz = 1.f, rho_j = 0.f;  // point used for the reprojection Jacobians
   if (FEJ || !JAC) {
-    // values-only reprojection at the current state (camera_reproject.hpp:270-293)
-    const float X = row_apply(pc.A + 0, ur, vr, lm.rho);
-    const float Y = row_apply(pc.A + 4, ur, vr, lm.rho);
-    const float Z = row_apply(pc.A + 8, ur, vr, lm.rho);
+    // values-only reprojection at the current state (camera_reproject.hpp:270-293); hnormalized() as one
+    // correctly rounded reciprocal and two products (the fp32 oracle does the same)
+    const float X = row_apply4(ldf4(pc.A + 0), ur, vr, lm.rho);
+    const float Y = row_apply4(ldf4(pc.A + 4), ur, vr, lm.rho);
+    const float Z = row_apply4(ldf4(pc.A + 8), ur, vr, lm.rho);
     ok = ok && (Z > 0.f);
-    tu = __fdiv_rn(X, Z);
-    tv = __fdiv_rn(Y, Z);
+    const float rz = __frcp_rn(Z);
+    tu = __fmul_rn(X, rz);
+    tv = __fmul_rn(Y, rz);
     ok = ok && in_roi(tu, tv, xmax, ymax);
-    if (FEJ) {
-      // reprojection_jacobians_valid of firstEstimateJacobians_ (first_estimate_jacobians.hpp:52-54):
-      // the Jacobian variant of reproject() at the linearisation point and the snapshot idepth
-      qx = row_apply(pc.M0 + 0, ur, vr, lm.rho0);
-      qy = row_apply(pc.M0 + 4, ur, vr, lm.rho0);
-      qz = row_apply(pc.M0 + 8, ur, vr, lm.rho0);
+    if (FEJ) ok = ok && jv;  // evaluate_jacobians.hpp:94
+    if (FEJ && JAC) {
+      // FEJ: the reprojection Jacobians are those of firstEstimateJacobians_, i.e. taken at the linearisation
+      // pose and the snapshot idepth; they are recomputed here instead of being stored (112 scalars per residual)
+      qx = row_apply4(ldf4(pc.M0 + 0), ur, vr, lm.rho0);
+      qy = row_apply4(ldf4(pc.M0 + 4), ur, vr, lm.rho0);
+      qz = row_apply4(ldf4(pc.M0 + 8), ur, vr, lm.rho0);
       rho_j = lm.rho0;
-      bool okj = valid_idepth(lm.rho0) && (qz > 0.f);
-      const float u0 = __fdiv_rn(__fadd_rn(__fmul_rn(pc.fx_t, qx), __fmul_rn(pc.cx_t, qz)), qz);
-      const float v0 = __fdiv_rn(__fadd_rn(__fmul_rn(pc.fy_t, qy), __fmul_rn(pc.cy_t, qz)), qz);
-      okj = okj && in_roi(u0, v0, xmax, ymax);
-      ok = ok && okj;
     }
   } else {
     // Jacobian variant at the current state (camera_reproject.hpp:305-367)
-    qx = row_apply(pc.M + 0, ur, vr, lm.rho);
-    qy = row_apply(pc.M + 4, ur, vr, lm.rho);
-    qz = row_apply(pc.M + 8, ur, vr, lm.rho);
+    qx = row_apply4(ldf4(pc.M + 0), ur, vr, lm.rho);
+    qy = row_apply4(ldf4(pc.M + 4), ur, vr, lm.rho);
+    qz = row_apply4(ldf4(pc.M + 8), ur, vr, lm.rho);
     rho_j = lm.rho;
     ok = ok && (qz > 0.f);
-    tu = __fdiv_rn(__fadd_rn(__fmul_rn(pc.fx_t, qx), __fmul_rn(pc.cx_t, qz)), qz);
-    tv = __fdiv_rn(__fadd_rn(__fmul_rn(pc.fy_t, qy), __fmul_rn(pc.cy_t, qz)), qz);
+    const float rz = __frcp_rn(qz);
+    tu = __fmul_rn(__fadd_rn(__fmul_rn(pc.fx_t, qx), __fmul_rn(pc.cx_t, qz)), rz);
+    tv = __fmul_rn(__fadd_rn(__fmul_rn(pc.fy_t, qy), __fmul_rn(pc.cy_t, qz)), rz);
     ok = ok && in_roi(tu, tv, xmax, ymax);
   }
-  ok = group_all(ok, lane);
-  // CameraMask::valid<false>: round() + lookup, only meaningful after the ROI test (quirk Q5)
-  bool mok = false;
-  if (ok) mok = mask[(int)roundf(tv) * W + (int)roundf(tu)] != 0;
-  ok = group_all(ok && mok, lane);
-
-  o.ok = ok;
-  o.ev = ok && (status == K_OK);
-  o.r = 0.f;
-  o.d = 0.f;
-  o.c = 0.f;
-  o.e = 0.f;
-  o.w = 1.f;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) o.g[k] = 0.f;
-
-  float r = 0.f, dIu = 0.f, dIv = 0.f;
-  if (o.ev) {
-    // interpolateLinear, features/include/features/camera/pixel_map.hpp:20-40
-    const int ix = (int)tu, iy = (int)tv;
-    const float dx = tu - (float)ix, dy = tv - (float)iy;
-    const float dxdy = dx * dy;
-    const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1.f - dx - dy + dxdy;
-    const float4* p = img + (size_t)iy * W + ix;
-    const float4 t00 = __ldg(p), t01 = __ldg(p + 1), t10 = __ldg(p + W), t11 = __ldg(p + W + 1);
-    const float I = w11 * t11.x + w10 * t10.x + w01 * t01.x + w00 * t00.x;
-    if (JAC) {
-      dIu = w11 * t11.y + w10 * t10.y + w01 * t01.y + w00 * t00.y;
-      dIv = w11 * t11.z + w10 * t10.z + w01 * t01.z + w00 * t00.z;
-    }
-    // r = (I_t - b_t) - s (patch - b_r), evaluate_jacobians.hpp:124-135
-    r = (I - pc.b_t) - pc.s * (lm.patch - pc.b_r);
+  // CameraMask::valid<false>: round() + lookup, only meaningful after the ROI test (quirk Q5).  mask == nullptr
+  // means the frame's mask has no zero (checked once at upload): the lookup and its dependent load are skipped.
+  if (mask) {
+    ok = group_all(ok, lane);
+    const int midx = ok ? (int)roundf(tv) * W + (int)roundf(tu) : 0;
+    ok = ok && (mask[midx] != 0);
   }
+  ok = group_all(ok, lane);
+  const bool ev = ok && (status == K_OK);
+  o.ok = ok;
+  o.ev = ev;
+
+  // interpolateLinear, features/include/features/camera/pixel_map.hpp:20-40 (texel (8,8) when not evaluated)
+  const float su = ev ? tu : 8.f, sv = ev ? tv : 8.f;
+  const int ix = (int)su, iy = (int)sv;
+  const float dx = su - (float)ix, dy = sv - (float)iy;
+  const float dxdy = dx * dy;
+  const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1.f - dx - dy + dxdy;
+  const float4* p = img + (size_t)iy * W + ix;
+  const float4 t00 = __ldg(p), t01 = __ldg(p + 1), t10 = __ldg(p + W), t11 = __ldg(p + W + 1);
+  const float I = w11 * t11.x + w10 * t10.x + w01 * t01.x + w00 * t00.x;
+  // r = (I_t - b_t) - s (patch - b_r), evaluate_jacobians.hpp:124-135
+  const float r = ev ? (I - pc.b_t) - pc.s * (lm.patch - pc.b_r) : 0.f;
   const float n2 = group_sum(r * r);
-  if (o.ev) {
-    o.r = r;
-    o.e = 0.5f * n2;
-    if (huber && n2 > sigma * sigma) {  // evaluate_jacobians.hpp:139-146
-      const float nrm = sqrtf(n2);
-      o.w = sigma / nrm;
-      o.e = sigma * nrm - sigma * sigma * 0.5f;
-    }
-    if (JAC) {
-      // camera_reproject.hpp:339-365
-      const float sI = 1.f / qz;
-      const float b0 = qx * sI, b1 = qy * sI;
-      const float nid = rho_j * sI;
-      const float* tt = FEJ ? pc.t0 : pc.tr;
-      const float fx = pc.fx_t, fy = pc.fy_t;
-      const float du_id = fx * (tt[0] * sI - tt[2] * sI * b0);
-      const float dv_id = fy * (tt[1] * sI - tt[2] * sI * b1);
-      const float b0b1 = b0 * b1;
-      const float gu = dIu * fx, gv = dIv * fy;
-      // Jg = dIv * dv/dxi + dIu * du/dxi   (evaluate_jacobians.hpp:149-157)
-      o.g[0] = gu * nid;
-      o.g[1] = gv * nid;
-      o.g[2] = -gu * (nid * b0) - gv * (nid * b1);
-      o.g[3] = -gu * b0b1 - gv * (b1 * b1 + 1.f);
-      o.g[4] = gu * (b0 * b0 + 1.f) + gv * b0b1;
-      o.g[5] = -gu * b1 + gv * b0;
-      o.d = dIu * du_id + dIv * dv_id;  // evaluate_jacobians.hpp:165-174
-      // corrected_reference_intensities: FEJ -> landmark.corrected_intensities (last target wins, Q1),
-      // else s (patch - b_r)   (evaluate_jacobians.hpp:96,103-106)
-      o.c = FEJ ? pc.s0_last * (lm.patch - pc.b_r0) : pc.s * (lm.patch - pc.b_r);
-    }
+  float e = 0.5f * n2, wgt = 1.f;
+  if (huber && n2 > sigma * sigma) {  // evaluate_jacobians.hpp:139-146
+    const float nrm = sqrtf(n2);
+    wgt = sigma / nrm;
+    e = sigma * nrm - sigma * sigma * 0.5f;
+  }
+  o.r = r;
+  o.e = ev ? e : 0.f;
+  o.w = wgt;
+  if (JAC) {
+    const float dIu = w11 * t11.y + w10 * t10.y + w01 * t01.y + w00 * t00.y;
+    const float dIv = w11 * t11.z + w10 * t10.z + w01 * t01.z + w00 * t00.z;
+    // camera_reproject.hpp:339-365
+    const float sI = __frcp_rn(ev ? qz : 1.f);
+    const float b0 = qx * sI, b1 = qy * sI;
+    const float nid = rho_j * sI;
+    const float* tt = FEJ ? pc.t0 : pc.tr;
+    const float evf = ev ? 1.f : 0.f;
+    const float gu = evf * dIu * pc.fx_t, gv = evf * dIv * pc.fy_t;
+    const float du_id = tt[0] * sI - tt[2] * sI * b0;
+    const float dv_id = tt[1] * sI - tt[2] * sI * b1;
+    const float b0b1 = b0 * b1;
+    // Jg = dIv * dv/dxi + dIu * du/dxi   (evaluate_jacobians.hpp:149-157)
+    o.g[0] = gu * nid;
+    o.g[1] = gv * nid;
+    o.g[2] = -gu * (nid * b0) - gv * (nid * b1);
+    o.g[3] = -gu * b0b1 - gv * (b1 * b1 + 1.f);
+    o.g[4] = gu * (b0 * b0 + 1.f) + gv * b0b1;
+    o.g[5] = -gu * b1 + gv * b0;
+    o.d = gu * du_id + gv * dv_id;  // evaluate_jacobians.hpp:165-174
+    // corrected_reference_intensities: FEJ -> landmark.corrected_intensities (last target wins, Q1),
+    // else s (patch - b_r)   (evaluate_jacobians.hpp:96,103-106)
+    o.c = evf * (FEJ ? pc.s0_last * (lm.patch - pc.b_r0) : pc.s * (lm.patch - pc.b_r));
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o.g[k] = 0.f;
+    o.d = 0.f;
+    o.c = 0.f;
   }
 }
 
 __device__ __forceinline__ LandmarkIn load_landmark(const WindowDev& w, int gl, int px) {
   LandmarkIn lm;
-  const float2 uv = w.uv[gl];
-  lm.u = uv.x;
-  lm.v = uv.y;
-  lm.rho = w.idepth[gl] + w.idepth_step[gl];
-  lm.rho0 = w.idepth_fej[gl];
+  const float4 k = w.lmk[gl];
+  lm.u = k.x;
+  lm.v = k.y;
+  lm.rho = k.z + w.idepth_step[gl];
+  lm.rho0 = k.w;
   lm.patch = w.patch[(size_t)gl * 8 + px];
   lm.flags = w.flags[gl];
   return lm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: firstEstimateJacobians_ (first_estimate_jacobians.hpp:14-71).  Freezes the idepth used by the FEJ
+// Jacobians (quirk Q9: the CURRENT idepth) and stores reprojection_jacobians_valid per residual; the Jacobians
+// themselves, corrected_intensities and brightness_change_scale are functions of the frozen point and are
+// recomputed by the sweeps.  grid = (chunks of 32 landmarks, ordered pairs)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_first_estimate(const __grid_constant__ WindowDev w) {
+  const int N = w.n_frames;
+  const int r = blockIdx.y / (N - 1);
+  int t = blockIdx.y % (N - 1);
+  t += (t >= r);
+  const int M = w.n_lm[r];
+  const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
+  if ((int)blockIdx.x * 32 >= M) return;
+  const int lane = threadIdx.x & 31, px = lane & 7;
+  const bool inb = l < M;
+  const int gl = lm_index(w, r, inb ? l : 0);
+  const float4 k = w.lmk[gl];
+  const int fl = w.flags[gl];
+  const bool skip = !inb || ((fl & LM_MARG) && !(fl & LM_TO_MARG));  // first_estimate_jacobians.hpp:49
+  const PairConst& pc = w.pairs[r * PBA_MAXF + t];
+  const float xmax = (float)(w.W - 5), ymax = (float)(w.H - 5);
+  const float ur = k.x + pat_x(px), vr = k.y + pat_y(px);
+  const float rho0 = k.z;  // the snapshot taken by this pass
+  const float qx = row_apply4(ldf4(pc.M0 + 0), ur, vr, rho0);
+  const float qy = row_apply4(ldf4(pc.M0 + 4), ur, vr, rho0);
+  const float qz = row_apply4(ldf4(pc.M0 + 8), ur, vr, rho0);
+  bool ok = valid_idepth(rho0) && in_roi(ur, vr, xmax, ymax) && (qz > 0.f);
+  const float rz = __frcp_rn(qz);
+  const float u0 = __fmul_rn(__fadd_rn(__fmul_rn(pc.fx_t, qx), __fmul_rn(pc.cx_t, qz)), rz);
+  const float v0 = __fmul_rn(__fadd_rn(__fmul_rn(pc.fy_t, qy), __fmul_rn(pc.cy_t, qz)), rz);
+  ok = group_all(ok && in_roi(u0, v0, xmax, ymax), lane);
+  if (!skip && px == 0) {
+    w.jac_valid[res_index(w, r, t, l)] = ok ? 1 : 0;
+    if (t == (r == 0 ? 1 : 0)) w.lmk[gl].w = rho0;  // one writer per landmark
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -256,9 +296,11 @@ __device__ __forceinline__ LandmarkIn load_landmark(const WindowDev& w, int gl, 
 // ------------------------------------------------------------------------------------------------
 template <bool FEJ>
 __global__ void __launch_bounds__(256) k_residual_sweep(const __grid_constant__ WindowDev w, float sigma, int huber,
-                                                        double* __restrict__ scal, const LmCtl* __restrict__ ctl,
+                                                        double2* __restrict__ part, const LmCtl* __restrict__ ctl,
                                                         int ctl_mode) {
   if (lm_skip(ctl, ctl_mode)) return;
+  // every CTA owns one slot of `part` (energy, n_valid): no same-address atomics, deterministic sum afterwards
+  double2* my_part = part + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
   __shared__ PairConst pcs;
   __shared__ float s_e[8];
   __shared__ int s_n[8];
@@ -267,9 +309,12 @@ __global__ void __launch_bounds__(256) k_residual_sweep(const __grid_constant__ 
   int t = blockIdx.y % (N - 1);
   t += (t >= r);
   const int M = w.n_lm[r];
-  if ((int)blockIdx.x * 32 >= M) return;
-  for (int i = threadIdx.x; i < (int)(sizeof(PairConst) / 4); i += blockDim.x)
-    ((float*)&pcs)[i] = ((const float*)&w.pairs[r * PBA_MAXF + t])[i];
+  if ((int)blockIdx.x * 32 >= M) {
+    if (threadIdx.x == 0) *my_part = make_double2(0.0, 0.0);
+    return;
+  }
+  if (threadIdx.x < 32)
+    reinterpret_cast<float4*>(&pcs)[threadIdx.x] = reinterpret_cast<const float4*>(&w.pairs[r * PBA_MAXF + t])[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
@@ -282,9 +327,11 @@ __global__ void __launch_bounds__(256) k_residual_sweep(const __grid_constant__ 
   const bool skip = !inb || ((lm.flags & LM_MARG) && !(lm.flags & LM_TO_MARG));  // evaluate_jacobians.hpp:83
   const size_t res = res_index(w, r, t, inb ? l : 0);
   const int status = skip ? K_OUTLIER : w.status[res];
-  if (skip) lm.rho = -1.f;  // forces !ok without touching memory
+  const bool jv = FEJ ? (w.jac_valid[res] != 0) : true;
+  if (skip) lm.rho = -1.f;  // forces !ok
   PixelOut o;
-  eval_pixel<FEJ, false>(pcs, lm, w.img[t], w.mask[t], w.W, w.H, status, sigma, huber, lane, o);
+  eval_pixel<FEJ, false>(pcs, lm, jv, w.img[t], w.mask_all[t] ? nullptr : w.mask[t], w.W, w.H, status, sigma, huber, lane,
+                         pat_x(px), pat_y(px), o);
   if (!skip && px == 0) {
     if (!o.ok) w.cand[res] = K_OOB;   // evaluate_jacobians.hpp:111-113
     else if (o.ev) w.cand[res] = K_OK;  // :115
@@ -312,9 +359,65 @@ __global__ void __launch_bounds__(256) k_residual_sweep(const __grid_constant__ 
       e += (double)s_e[i];
       n += s_n[i];
     }
-    if (n | (e != 0)) {
-      atomicAdd(&scal[0], e);
-      atomicAdd(&scal[1], (double)n);
+    *my_part = make_double2(e, (double)n);
+  }
+}
+
+// second stage of the (energy, n_valid) and landmark-norm reductions: one CTA sums the per-CTA partials
+__global__ void __launch_bounds__(1024) k_reduce_scal(const LmCtl* __restrict__ ctl, int ctl_mode,
+                                                      const double2* __restrict__ e_part, int n_e,
+                                                      const double2* __restrict__ n_part, int n_n,
+                                                      double* __restrict__ scal) {
+  if (lm_skip(ctl, ctl_mode)) return;
+  __shared__ double s[4][32];
+  double a = 0, b = 0, c = 0, d = 0;
+  for (int i = threadIdx.x; i < n_e; i += blockDim.x) {
+    const double2 v = e_part[i];
+    a += v.x;
+    b += v.y;
+  }
+  for (int i = threadIdx.x; i < n_n; i += blockDim.x) {
+    const double2 v = n_part[i];
+    c += v.x;
+    d += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(FULL, a, o);
+    b += __shfl_xor_sync(FULL, b, o);
+    c += __shfl_xor_sync(FULL, c, o);
+    d += __shfl_xor_sync(FULL, d, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s[0][warp] = a;
+    s[1][warp] = b;
+    s[2][warp] = c;
+    s[3][warp] = d;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    a = lane < nw ? s[0][lane] : 0;
+    b = lane < nw ? s[1][lane] : 0;
+    c = lane < nw ? s[2][lane] : 0;
+    d = lane < nw ? s[3][lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(FULL, a, o);
+      b += __shfl_xor_sync(FULL, b, o);
+      c += __shfl_xor_sync(FULL, c, o);
+      d += __shfl_xor_sync(FULL, d, o);
+    }
+    if (lane == 0) {
+      if (e_part) {
+        scal[0] = a;
+        scal[1] = b;
+      }
+      if (n_part) {
+        scal[2] = c;
+        scal[3] = d;
+      }
     }
   }
 }
@@ -332,8 +435,8 @@ __global__ void __launch_bounds__(256) k_materialise_sweep(const __grid_constant
   t += (t >= r);
   const int M = w.n_lm[r];
   if ((int)blockIdx.x * 32 >= M) return;
-  for (int i = threadIdx.x; i < (int)(sizeof(PairConst) / 4); i += blockDim.x)
-    ((float*)&pcs)[i] = ((const float*)&w.pairs[r * PBA_MAXF + t])[i];
+  if (threadIdx.x < 32)
+    reinterpret_cast<float4*>(&pcs)[threadIdx.x] = reinterpret_cast<const float4*>(&w.pairs[r * PBA_MAXF + t])[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
@@ -344,9 +447,11 @@ __global__ void __launch_bounds__(256) k_materialise_sweep(const __grid_constant
   const bool skip = !inb || ((lm.flags & LM_MARG) && !(lm.flags & LM_TO_MARG));
   const size_t res = res_index(w, r, t, inb ? l : 0);
   const int status = skip ? K_OUTLIER : w.status[res];
+  const bool jv = FEJ ? (w.jac_valid[res] != 0) : true;
   if (skip) lm.rho = -1.f;
   PixelOut o;
-  eval_pixel<FEJ, true>(pcs, lm, w.img[t], w.mask[t], w.W, w.H, status, sigma, huber, lane, o);
+  eval_pixel<FEJ, true>(pcs, lm, jv, w.img[t], w.mask_all[t] ? nullptr : w.mask[t], w.W, w.H, status, sigma, huber, lane,
+                        pat_x(px), pat_y(px), o);
   if (skip) return;
   if (px == 0) {
     if (!o.ok) w.cand[res] = K_OOB;
@@ -359,13 +464,21 @@ __global__ void __launch_bounds__(256) k_materialise_sweep(const __grid_constant
   const float* adj = FEJ ? pcs.adj0 : pcs.adj;
   float jr[8], jt[8];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    float a = 0.f;
+  for (int j = 0; j < 6; ++j) jr[j] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) a += o.g[k] * adj[k * 6 + j];  // J_ref[:,0:6] = Jg Adj  (:162-163)
-    jr[j] = a;
-    jt[j] = -o.g[j];  // J_tgt[:,0:6] = -Jg leftLog (= I)  (:159-160)
+  for (int k = 0; k < 6; ++k) {  // J_ref[:,0:6] = Jg Adj  (:162-163); rows of Adj as float2 pairs from shared memory
+    const float2 a0 = *reinterpret_cast<const float2*>(adj + k * 6);
+    const float2 a1 = *reinterpret_cast<const float2*>(adj + k * 6 + 2);
+    const float2 a2 = *reinterpret_cast<const float2*>(adj + k * 6 + 4);
+    jr[0] += o.g[k] * a0.x;
+    jr[1] += o.g[k] * a0.y;
+    jr[2] += o.g[k] * a1.x;
+    jr[3] += o.g[k] * a1.y;
+    jr[4] += o.g[k] * a2.x;
+    jr[5] += o.g[k] * a2.y;
   }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) jt[j] = -o.g[j];  // J_tgt[:,0:6] = -Jg leftLog (= I)  (:159-160)
   const float sp = FEJ ? pcs.s0 : pcs.s;  // d_reference_affineBrightnessShift (:95,107)
   jr[6] = o.c;
   jr[7] = o.ev ? sp : 0.f;
@@ -373,10 +486,10 @@ __global__ void __launch_bounds__(256) k_materialise_sweep(const __grid_constant
   jt[7] = o.ev ? -1.f : 0.f;
   float4* pr = reinterpret_cast<float4*>(w.m_jref + res * 64 + px * 8);
   float4* pt = reinterpret_cast<float4*>(w.m_jtgt + res * 64 + px * 8);
-  pr[0] = make_float4(jr[0], jr[1], jr[2], jr[3]);
-  pr[1] = make_float4(jr[4], jr[5], jr[6], jr[7]);
-  pt[0] = make_float4(jt[0], jt[1], jt[2], jt[3]);
-  pt[1] = make_float4(jt[4], jt[5], jt[6], jt[7]);
+  __stcs(pr, make_float4(jr[0], jr[1], jr[2], jr[3]));  // streaming stores: written once, never re-read here
+  __stcs(pr + 1, make_float4(jr[4], jr[5], jr[6], jr[7]));
+  __stcs(pt, make_float4(jt[0], jt[1], jt[2], jt[3]));
+  __stcs(pt + 1, make_float4(jt[4], jt[5], jt[6], jt[7]));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -385,41 +498,44 @@ __global__ void __launch_bounds__(256) k_materialise_sweep(const __grid_constant
 // With u_i = [g_i(6), c_i, 1] the two Jacobian rows of a pixel are  J_tgt_i = -u_i  and  J_ref_i = u_i B,
 // B = blockdiag(Adj, 1, s').  So per ordered pair only the 8x8 "core" C = sum w u^T u (36 unique) and
 // q = sum w u r (8) are accumulated (44 sums instead of 3*64+16 = 208); H_rr = B^T C B, H_rt = -B^T C,
-// H_tt = C, b_r = B^T q, b_t = -q are formed once per pair by k_assemble in fp64.
+// H_tt = C, b_r = B^T q, b_t = -q are formed once per pair by k_assemble in fp64.  Likewise the target block of a
+// landmark's H_pd is -p_t (p_t = sum w d u) and its reference block is sum_t B_t^T p_t, formed once per landmark
+// when the chunk is finalised.
 //
 // grid = (landmark chunks, host frames); one warp per target frame; each warp walks the chunk 4 landmarks at a
 // time keeping its pair's 44 running sums in registers, so the per-landmark quantities that couple the targets
 // (H_pd, H_dd, b_d) meet in shared memory.
 // ------------------------------------------------------------------------------------------------
-template <bool FEJ>
-__global__ void __launch_bounds__(32 * (PBA_MAXF - 1))
+template <bool FEJ, int NWMAX>
+__global__ void __launch_bounds__(32 * NWMAX, NWMAX <= 8 ? 4 : 2)
     k_linearize_fused(const __grid_constant__ WindowDev w, float sigma, int huber, int for_marg, int lpb,
-                      double* __restrict__ core, const LmCtl* __restrict__ ctl) {
+                      float* __restrict__ core_part, float* __restrict__ schur_part, const LmCtl* __restrict__ ctl) {
   if (lm_skip(ctl, 2)) return;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int N = w.n_frames;
   const int D = 8 * N;
   const int f = blockIdx.y;
   const int M = w.n_lm[f];
   const int l0 = blockIdx.x * lpb;
   if (l0 >= M) return;
-  float* hpd_s = smem;                 // [lpb][D]
-  float* hdd_s = hpd_s + lpb * D;      // [lpb]
-  float* bd_s = hdd_s + lpb;           // [lpb]
-  PairConst* pcs = reinterpret_cast<PairConst*>(bd_s + lpb);  // [nwarps]
+  const int nwarps = N - 1;
+  PairConst* pcs = reinterpret_cast<PairConst*>(smem);               // [nwarps]
+  float* hpd_s = smem + (size_t)nwarps * (sizeof(PairConst) / 4);    // [lpb][D]
+  float* hdd_s = hpd_s + lpb * D;                                    // [lpb]
+  float* bd_s = hdd_s + lpb;                                         // [lpb]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int px = lane & 7, grp = lane >> 3;
   const int t = warp + (warp >= f);
 
-  for (int i = threadIdx.x; i < lpb * (D + 2); i += blockDim.x) smem[i] = 0.f;
-  for (int i = lane; i < (int)(sizeof(PairConst) / 4); i += 32)
-    ((float*)&pcs[warp])[i] = ((const float*)&w.pairs[f * PBA_MAXF + t])[i];
+  for (int i = threadIdx.x; i < lpb * (D + 2); i += blockDim.x) hpd_s[i] = 0.f;
+  reinterpret_cast<float4*>(&pcs[warp])[lane] = reinterpret_cast<const float4*>(&w.pairs[f * PBA_MAXF + t])[lane];
   __syncthreads();
   const PairConst& pc = pcs[warp];
-  const float* adj = FEJ ? pc.adj0 : pc.adj;
-  const float sp = FEJ ? pc.s0 : pc.s;
   const float4* img = w.img[t];
-  const uint8_t* mask = w.mask[t];
+  const uint8_t* mask = w.mask_all[t] ? nullptr : w.mask[t];
+  const float pox = pat_x(px), poy = pat_y(px);
+  const int lm_base = lm_index(w, f, 0);
+  const size_t res_base = res_index(w, f, t, 0);
 
   float acc[PBA_CORE];
 #pragma unroll
@@ -429,14 +545,15 @@ __global__ void __launch_bounds__(32 * (PBA_MAXF - 1))
     const int ls = it + grp;  // slot in the chunk
     const int l = l0 + ls;
     const bool inb = l < M;
-    const int gl = lm_index(w, f, inb ? l : 0);
-    LandmarkIn lm = load_landmark(w, gl, px);
+    const int li = inb ? l : 0;
+    LandmarkIn lm = load_landmark(w, lm_base + li, px);
     const bool skip = !inb || ((lm.flags & LM_MARG) && !(lm.flags & LM_TO_MARG));
-    const size_t res = res_index(w, f, t, inb ? l : 0);
+    const size_t res = res_base + li;
     const int status = skip ? K_OUTLIER : w.status[res];
+    const bool jv = FEJ ? (w.jac_valid[res] != 0) : true;
     if (skip) lm.rho = -1.f;
     PixelOut o;
-    eval_pixel<FEJ, true>(pc, lm, img, mask, w.W, w.H, status, sigma, huber, lane, o);
+    eval_pixel<FEJ, true>(pc, lm, jv, img, mask, w.W, w.H, status, sigma, huber, lane, pox, poy, o);
     if (!skip && px == 0) {
       if (!o.ok) w.cand[res] = K_OOB;
       else if (o.ev) w.cand[res] = K_OK;
@@ -462,28 +579,16 @@ __global__ void __launch_bounds__(32 * (PBA_MAXF - 1))
 #pragma unroll
       for (int a = 0; a < 8; ++a) acc[36 + a] += wu[a] * o.r;
     }
-    // per landmark: H_pd blocks, H_dd, b_d  (hessian_block_evaluation.hpp:198-212)
+    // per landmark: target block of H_pd, H_dd, b_d  (hessian_block_evaluation.hpp:198-212)
     float pv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) pv[k] = wu[k] * o.d;
     const float P = group_transpose_reduce(pv, px);  // lane px holds sum_i w d_i u_i[px]
-    const float hdd = group_sum(wgt * o.d * o.d);
-    const float bd = group_sum(wgt * o.d * o.r);
-    // reference block: B^T-row px of P  ->  sum_k adj[k][px] P_k for px < 6
-    float Pk[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) Pk[k] = __shfl_sync(FULL, P, (lane & 24) + k);
-    float refv;
-    if (px < 6) {
-      refv = 0.f;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) refv += adj[k * 6 + px] * Pk[k];
-    } else {
-      refv = (px == 6) ? P : sp * P;
-    }
+    const float wd = wgt * o.d;
+    const float hdd = group_sum(wd * o.d);
+    const float bd = group_sum(wd * o.r);
     if (sel) {
-      hpd_s[ls * D + 8 * t + px] = -P;                 // target block: this warp is its only writer
-      atomicAdd(&hpd_s[ls * D + 8 * f + px], refv);    // reference block: summed over the target warps
+      hpd_s[ls * D + 8 * t + px] = -P;  // this warp is the only writer of target block t
       if (px == 0) {
         atomicAdd(&hdd_s[ls], hdd);
         atomicAdd(&bd_s[ls], bd);
@@ -491,7 +596,7 @@ __global__ void __launch_bounds__(32 * (PBA_MAXF - 1))
     }
   }
 
-  // warp-wide transpose-reduce of the 44(48) running sums: 24+12+6+3+2 = 47 shuffles, then <= 2 atomics per lane
+  // warp-wide transpose-reduce of the 44(48) running sums: 24+12+6+3+2 = 47 shuffles, then <= 2 stores per lane
   {
     float v24[24], v12[12], v6[6], v3[3], v2[2];
     tr_step<48, 16>(acc, v24, lane);
@@ -501,40 +606,116 @@ __global__ void __launch_bounds__(32 * (PBA_MAXF - 1))
     tr_step<3, 1>(v3, v2, lane);
     const int off = ((lane & 16) ? 24 : 0) + ((lane & 8) ? 12 : 0) + ((lane & 4) ? 6 : 0) + ((lane & 2) ? 3 : 0) +
                     ((lane & 1) ? 2 : 0);
-    double* dst = core + (size_t)(f * PBA_MAXF + t) * PBA_CORE;
-    if (off < 44 && v2[0] != 0.f) atomicAdd(dst + off, (double)v2[0]);
-    if (!(lane & 1) && off + 1 < 44 && v2[1] != 0.f) atomicAdd(dst + off + 1, (double)v2[1]);
+    // this warp's 48 partial sums go to its own slot [host frame][chunk][target warp][48]: plain coalesced stores,
+    // summed over the chunks in fp64 by k_assemble (no atomics, deterministic)
+    float* dst = core_part + (((size_t)f * gridDim.x + blockIdx.x) * nwarps + warp) * PBA_CORE;
+    dst[off] = v2[0];
+    if (!(lane & 1)) dst[off + 1] = v2[1];
   }
   __syncthreads();
 
-  // finalise the chunk's landmarks (hessian_block_evaluation.hpp:213-227)
+  // reference block of H_pd:  sum_t B_t^T p_t  with p_t = -(target block t)   (J_ref = U B)
+  for (int i = threadIdx.x; i < lpb * 8; i += blockDim.x) {
+    const int ls = i >> 3, j = i & 7;
+    float refv = 0.f;
+    for (int wi = 0; wi < nwarps; ++wi) {
+      const int tt = wi + (wi >= f);
+      const float* pt = hpd_s + ls * D + 8 * tt;
+      const PairConst& pw = pcs[wi];
+      if (j < 6) {
+        const float* adj = FEJ ? pw.adj0 : pw.adj;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) refv -= adj[k * 6 + j] * pt[k];
+      } else if (j == 6) {
+        refv -= pt[6];
+      } else {
+        refv -= (FEJ ? pw.s0 : pw.s) * pt[7];
+      }
+    }
+    hpd_s[ls * D + 8 * f + j] = refv;
+  }
+  __syncthreads();
+
+  // finalise the chunk's landmarks (hessian_block_evaluation.hpp:213-227); hdd_s / bd_s are overwritten with the
+  // Schur weights  s = 1/H_dd (0 when not selected or ill-conditioned)  and  s * b_d
   for (int ls = threadIdx.x; ls < lpb; ls += blockDim.x) {
     const int l = l0 + ls;
-    if (l >= M) continue;
-    const int gl = lm_index(w, f, l);
-    const int fl = w.flags[gl];
-    const bool skip = (fl & LM_MARG) && !(fl & LM_TO_MARG);
-    const bool sel = !skip && (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0);
-    if (!sel) continue;
-    float hdd = hdd_s[ls];
-    w.b_d[gl] = bd_s[ls];
-    if (hdd > 1e-15f) {
-      if (for_marg && w.fixed[f]) hdd += 1e8f;  // kScaleNullspaceRegularizer
-      w.inv_hdd[gl] = 1.f / hdd;
-      w.flags[gl] = (uint8_t)(fl & ~LM_ILL);
-    } else {
-      w.flags[gl] = (uint8_t)(fl | LM_ILL);
+    float sc = 0.f, sb = 0.f;
+    if (l < M) {
+      const int gl = lm_base + l;
+      const int fl = w.flags[gl];
+      const bool skip = (fl & LM_MARG) && !(fl & LM_TO_MARG);
+      const bool sel = !skip && (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0);
+      if (sel) {
+        float hdd = hdd_s[ls];
+        const float bd = bd_s[ls];
+        w.b_d[gl] = bd;
+        if (hdd > 1e-15f) {
+          if (for_marg && w.fixed[f]) hdd += 1e8f;  // kScaleNullspaceRegularizer
+          sc = 1.f / hdd;
+          sb = sc * bd;
+          w.inv_hdd[gl] = sc;
+          w.flags[gl] = (uint8_t)(fl & ~LM_ILL);
+        } else {
+          w.flags[gl] = (uint8_t)(fl | LM_ILL);
+        }
+      }
     }
+    hdd_s[ls] = sc;
+    bd_s[ls] = sb;
   }
-  for (int i = threadIdx.x; i < lpb * D; i += blockDim.x) {
-    const int ls = i / D;
+  __syncthreads();
+  const int D4 = D / 4;
+  for (int i = threadIdx.x; i < lpb * D4; i += blockDim.x) {
+    const int ls = i / D4;
     const int l = l0 + ls;
     if (l >= M) break;
-    const int gl = lm_index(w, f, l);
+    const int gl = lm_base + l;
     const int fl = w.flags[gl];
     const bool skip = (fl & LM_MARG) && !(fl & LM_TO_MARG);
     const bool sel = !skip && (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0);
-    if (sel) w.hpd[(size_t)gl * w.hpd_stride + (i - ls * D)] = hpd_s[i];
+    if (sel)
+      reinterpret_cast<float4*>(w.hpd + (size_t)gl * w.hpd_stride)[i - ls * D4] =
+          reinterpret_cast<const float4*>(hpd_s + ls * D)[i - ls * D4];
+  }
+  // K4 second half for this chunk while its H_pd rows are still in shared memory:
+  //   S = sum_l s_l H_pd_l H_pd_l^T (upper triangle as 4x4 tiles),  b = sum_l s_l b_d_l H_pd_l
+  // stored as this CTA's partial; k_finish_fused adds the CTAs up in fp64.
+  {
+    const int T4 = D / 4, ntri = T4 * (T4 + 1) / 2, nout = ntri * 16 + D;
+    float* part = schur_part + ((size_t)f * gridDim.x + blockIdx.x) * nout;
+    for (int tile = threadIdx.x; tile < ntri; tile += blockDim.x) {
+      int ty = 0, rem = tile;
+      while (rem >= T4 - ty) {
+        rem -= T4 - ty;
+        ++ty;
+      }
+      const int tx = ty + rem;
+      float a[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a[k] = 0.f;
+      for (int ls = 0; ls < lpb; ++ls) {
+        const float sc = hdd_s[ls];
+        const float4 qv = ldf4(hpd_s + ls * D + 4 * ty);
+        const float4 pv = ldf4(hpd_s + ls * D + 4 * tx);
+        const float qa[4] = {sc * qv.x, sc * qv.y, sc * qv.z, sc * qv.w};
+        const float pa[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[i * 4 + j] += qa[i] * pa[j];
+      }
+      float4* dst = reinterpret_cast<float4*>(part + tile * 16);
+      dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+      dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+      dst[2] = make_float4(a[8], a[9], a[10], a[11]);
+      dst[3] = make_float4(a[12], a[13], a[14], a[15]);
+    }
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float b = 0.f;
+      for (int ls = 0; ls < lpb; ++ls) b += bd_s[ls] * hpd_s[ls * D + c];
+      part[ntri * 16 + c] = b;
+    }
   }
 }
 
@@ -639,78 +820,112 @@ __global__ void __launch_bounds__(128) k_schur_prep_from_materialized(const __gr
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4 second half: H_s += inv H_pd H_pd^T, b_s += inv b_d H_pd over the selected, well-conditioned landmarks.
-// A (8N x L) x (L x 8N) SYRK.  Persistent grid; each block streams tiles of 32 landmarks through shared memory,
-// every thread owns a 4x4 output tile: fp32 products per tile, fp64 running sums, one fp64 atomic per output
-// element per block at the end.
+// K4 second half: H_s += inv H_pd H_pd^T, b_s += inv b_d H_pd over the selected, well-conditioned landmarks:
+// a (8N x L)(L x 8N) SYRK.  Persistent grid (<= one CTA per SM); every CTA streams tiles of 32 landmarks through a
+// cp.async double buffer, each thread owns one 4x4 tile of the UPPER triangle of H_s (fp32 products per tile, fp64
+// running sums) and stores its CTA's partial sums; k_finish_system adds the CTAs up and mirrors the lower triangle.
 // ------------------------------------------------------------------------------------------------
 constexpr int SCHUR_TL = 32;
-__global__ void __launch_bounds__(1024) k_schur(const __grid_constant__ WindowDev w, int for_marg,
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__global__ void __launch_bounds__(1024) k_schur(const __grid_constant__ WindowDev w, int for_marg, int G, int gthreads,
                                                 double* __restrict__ Hs, double* __restrict__ bs,
                                                 const LmCtl* __restrict__ ctl) {
   if (lm_skip(ctl, 2)) return;
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int N = w.n_frames, D = 8 * N;
-  const int T4 = D / 4;  // tiles per side
-  float* Ps = sm;                   // [TL][D]  H_pd
-  float* Qs = Ps + SCHUR_TL * D;    // [TL][D]  inv * H_pd
-  float* Bs = Qs + SCHUR_TL * D;    // [TL]     inv * b_d
-  const int tid = threadIdx.x;
-  const int ty = tid / T4, tx = tid % T4;
-  const bool active = tid < T4 * T4;
+  const int T4 = D / 4;               // 4x4 tiles per side
+  const int ntri = T4 * (T4 + 1) / 2; // tiles of the upper triangle
+  float* Ps[2] = {sm, sm + SCHUR_TL * D};           // [TL][D] H_pd, two stages
+  float* Sc = sm + 2 * SCHUR_TL * D;                // [2][TL] inv_hdd (0 when not selected)
+  float* Bs = Sc + 2 * SCHUR_TL;                    // [2][TL] inv_hdd * b_d
+  double* red = reinterpret_cast<double*>(Bs + 2 * SCHUR_TL);  // [ntri*16 + D] cross-group reduction
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // G groups of gthreads threads split the landmarks of a tile (K-split); inside a group thread t owns one 4x4
+  // tile (ty <= tx) of the upper triangle and, for t < D, entry t of b_s
+  const int g = tid / gthreads, t = tid - g * gthreads;
+  int ty = 0, tx = 0;
+  const bool active = t < ntri;
+  if (active) {
+    int rem = t;
+    while (rem >= T4 - ty) {
+      rem -= T4 - ty;
+      ++ty;
+    }
+    tx = ty + rem;
+  }
   double dacc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) dacc[k] = 0;
-  double bacc = 0;  // thread tid < D accumulates b_s[tid]
+  double bacc = 0;
 
-  // flattened tile list over all frames
   int tiles_of[PBA_MAXF + 1];
   tiles_of[0] = 0;
   for (int f = 0; f < N; ++f) tiles_of[f + 1] = tiles_of[f] + (w.n_lm[f] + SCHUR_TL - 1) / SCHUR_TL;
   const int total = tiles_of[N];
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  const int D4 = D / 4;
+
+  auto issue = [&](int tile, int stage) {
     int f = 0;
     while (tile >= tiles_of[f + 1]) ++f;
     const int l0 = (tile - tiles_of[f]) * SCHUR_TL;
     const int M = w.n_lm[f];
-    __syncthreads();
-    for (int i = tid; i < SCHUR_TL * D; i += blockDim.x) {
-      const int ls = i / D, c = i - ls * D;
-      const int l = l0 + ls;
-      float p = 0.f, q = 0.f;
+    const int base = lm_index(w, f, 0);
+    for (int i = tid; i < SCHUR_TL * D4; i += nt) {
+      const int ls = i / D4, c = i - ls * D4;
+      const int l = min(l0 + ls, M - 1);  // rows past the end re-read the last row, their scale is 0
+      cp_async16(Ps[stage] + ls * D + 4 * c, w.hpd + (size_t)(base + l) * w.hpd_stride + 4 * c);
+    }
+    if (tid < SCHUR_TL) {
+      const int l = l0 + tid;
+      float sc = 0.f, bv = 0.f;
       if (l < M) {
-        const int gl = lm_index(w, f, l);
+        const int gl = base + l;
         const int fl = w.flags[gl];
         const bool sel = (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0) && !(fl & LM_ILL);
         if (sel) {
-          p = w.hpd[(size_t)gl * w.hpd_stride + c];
-          q = p * w.inv_hdd[gl];
+          sc = w.inv_hdd[gl];
+          bv = sc * w.b_d[gl];
         }
       }
-      Ps[i] = p;
-      Qs[i] = q;
+      Sc[stage * SCHUR_TL + tid] = sc;
+      Bs[stage * SCHUR_TL + tid] = bv;
     }
-    for (int ls = tid; ls < SCHUR_TL; ls += blockDim.x) {
-      const int l = l0 + ls;
-      float v = 0.f;
-      if (l < M) {
-        const int gl = lm_index(w, f, l);
-        const int fl = w.flags[gl];
-        const bool sel = (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0) && !(fl & LM_ILL);
-        if (sel) v = w.inv_hdd[gl] * w.b_d[gl];
-      }
-      Bs[ls] = v;
+    cp_async_commit();
+  };
+
+  int stage = 0;
+  if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    if (next < total) {
+      issue(next, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const float* P = Ps[stage];
+    const float* S = Sc + stage * SCHUR_TL;
     if (active) {
       float a[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) a[k] = 0.f;
 #pragma unroll 4
-      for (int ls = 0; ls < SCHUR_TL; ++ls) {
-        const float4 qv = *reinterpret_cast<const float4*>(Qs + ls * D + 4 * ty);
-        const float4 pv = *reinterpret_cast<const float4*>(Ps + ls * D + 4 * tx);
-        const float qa[4] = {qv.x, qv.y, qv.z, qv.w};
+      for (int ls = g; ls < SCHUR_TL; ls += G) {
+        const float sc = S[ls];
+        const float4 qv = ldf4(P + ls * D + 4 * ty);
+        const float4 pv = ldf4(P + ls * D + 4 * tx);
+        const float qa[4] = {sc * qv.x, sc * qv.y, sc * qv.z, sc * qv.w};
         const float pa[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -720,72 +935,381 @@ __global__ void __launch_bounds__(1024) k_schur(const __grid_constant__ WindowDe
 #pragma unroll
       for (int k = 0; k < 16; ++k) dacc[k] += (double)a[k];
     }
-    if (tid < D) {
+    if (t < D) {
+      const float* B = Bs + stage * SCHUR_TL;
       float b = 0.f;
-      for (int ls = 0; ls < SCHUR_TL; ++ls) b += Bs[ls] * Ps[ls * D + tid];
+      for (int ls = g; ls < SCHUR_TL; ls += G) b += B[ls] * P[ls * D + t];
       bacc += (double)b;
     }
+    __syncthreads();
+    stage ^= 1;
   }
-  if (active) {
+  // cross-group reduction in shared memory, then one fp64 atomic per output element per CTA
+  for (int gg = 0; gg < G; ++gg) {
+    if (g == gg) {
+      if (active) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (dacc[i * 4 + j] != 0) atomicAdd(&Hs[(size_t)(4 * ty + i) * D + 4 * tx + j], dacc[i * 4 + j]);
+        for (int k = 0; k < 16; ++k) {
+          if (gg == 0) red[t * 16 + k] = dacc[k];
+          else red[t * 16 + k] += dacc[k];
+        }
+      }
+      if (t < D) {
+        if (gg == 0) red[ntri * 16 + t] = bacc;
+        else red[ntri * 16 + t] += bacc;
+      }
+    }
+    __syncthreads();
   }
-  if (tid < D && bacc != 0) atomicAdd(&bs[tid], bacc);
+  if (g == 0) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = 4 * ty + i, c = 4 * tx + j;
+          if (r <= c) Hs[(size_t)blockIdx.x * D * D + (size_t)r * D + c] = red[t * 16 + i * 4 + j];
+        }
+    }
+    if (t < D) bs[(size_t)blockIdx.x * D + t] = red[ntri * 16 + t];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// assembly of H_pp / b_p from the per-pair cores (fp64) with the reference's scatter + symmetrisation
-// (hessian_block_evaluation.hpp:118-163, quirk Q3).  grid = ordered pairs, 64 threads.
+// K4 second half on the tensor cores.  H_s = P^T diag(s) P with P = [H_pd rows] is a true dense contraction
+// (8N x L) x (L x 8N), L = landmarks, so it runs as warp-level mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (x = hi + lo, x y ~= hi hi' + hi lo' + lo hi': fp32-grade products, fp32 accumulators in the MMA, fp64 atomics
+// once per CTA).  The problem is far too small for a tcgen05/TMEM pipeline to pay (64x64 outputs, K = ~100 per
+// CTA); what matters is that the inner product leaves the FFMA/LDS-bound CUDA-core path.
+//   grid <= one CTA per SM, 8 warps; tiles of 32 landmarks stream through a cp.async double buffer [32][DP+8]
+//   (row padding of 8 floats makes every fragment load bank-conflict free); warp tile = 16 x 32 outputs.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int SCHUR_MAXWT = 4;  // warp tiles per warp (8N = 128 -> 32 warp tiles over 8 warps)
+
+__global__ void __launch_bounds__(256) k_schur_mma(const __grid_constant__ WindowDev w, int for_marg,
+                                                   double* __restrict__ Hs, double* __restrict__ bs,
+                                                   const LmCtl* __restrict__ ctl) {
+  if (lm_skip(ctl, 2)) return;
+  extern __shared__ __align__(16) float sm[];
+  const int N = w.n_frames, D = 8 * N;
+  const int DP = (D + 31) & ~31, LDP = DP + 8;
+  float* Ps[2] = {sm, sm + SCHUR_TL * LDP};
+  float* Sc = sm + 2 * SCHUR_TL * LDP;  // [2][TL] inv_hdd (0 when not selected)
+  float* Bs = Sc + 2 * SCHUR_TL;        // [2][TL] inv_hdd * b_d
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int nct = DP / 32, nwt = (DP / 16) * nct;
+  for (int i = tid; i < 2 * SCHUR_TL * LDP; i += nt) sm[i] = 0.f;  // pad columns stay zero
+
+  float acc[SCHUR_MAXWT][4][4];
+#pragma unroll
+  for (int a = 0; a < SCHUR_MAXWT; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  float bacc = 0.f;
+
+  int tiles_of[PBA_MAXF + 1];
+  tiles_of[0] = 0;
+  for (int f = 0; f < N; ++f) tiles_of[f + 1] = tiles_of[f] + (w.n_lm[f] + SCHUR_TL - 1) / SCHUR_TL;
+  const int total = tiles_of[N];
+  const int D4 = D / 4;
+  __syncthreads();
+
+  auto issue = [&](int tile, int stage) {
+    int f = 0;
+    while (tile >= tiles_of[f + 1]) ++f;
+    const int l0 = (tile - tiles_of[f]) * SCHUR_TL;
+    const int M = w.n_lm[f];
+    const int base = lm_index(w, f, 0);
+    for (int i = tid; i < SCHUR_TL * D4; i += nt) {
+      const int ls = i / D4, c = i - ls * D4;
+      const int l = min(l0 + ls, M - 1);  // rows past the end re-read the last row, their scale is 0
+      cp_async16(Ps[stage] + ls * LDP + 4 * c, w.hpd + (size_t)(base + l) * w.hpd_stride + 4 * c);
+    }
+    if (tid < SCHUR_TL) {
+      const int l = l0 + tid;
+      float sc = 0.f, bv = 0.f;
+      if (l < M) {
+        const int gl = base + l;
+        const int fl = w.flags[gl];
+        const bool sel = (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0) && !(fl & LM_ILL);
+        if (sel) {
+          sc = w.inv_hdd[gl];
+          bv = sc * w.b_d[gl];
+        }
+      }
+      Sc[stage * SCHUR_TL + tid] = sc;
+      Bs[stage * SCHUR_TL + tid] = bv;
+    }
+    cp_async_commit();
+  };
+
+  int stage = 0;
+  if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    if (next < total) {
+      issue(next, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* P = Ps[stage];
+    const float* S = Sc + stage * SCHUR_TL;
+#pragma unroll
+    for (int a = 0; a < SCHUR_MAXWT; ++a) {
+      const int wt = warp + 8 * a;
+      if (wt >= nwt) break;
+      const int row0 = 16 * (wt / nct), col0 = 32 * (wt % nct);
+      if (col0 + 31 < row0) continue;  // entirely below the diagonal
+#pragma unroll
+      for (int kk = 0; kk < SCHUR_TL; kk += 8) {
+        const float s0 = S[kk + tig], s1 = S[kk + tig + 4];
+        const float* p0 = P + (kk + tig) * LDP;
+        const float* p1 = P + (kk + tig + 4) * LDP;
+        float af[4] = {s0 * p0[row0 + gid], s0 * p0[row0 + gid + 8], s1 * p1[row0 + gid], s1 * p1[row0 + gid + 8]};
+        unsigned ah[4], al[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ah[q] = f2tf32(af[q]);
+          al[q] = f2tf32(af[q] - __uint_as_float(ah[q]));
+        }
+#pragma unroll
+        for (int nt8 = 0; nt8 < 4; ++nt8) {
+          const float bf[2] = {p0[col0 + 8 * nt8 + gid], p1[col0 + 8 * nt8 + gid]};
+          unsigned bh[2], bl[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            bh[q] = f2tf32(bf[q]);
+            bl[q] = f2tf32(bf[q] - __uint_as_float(bh[q]));
+          }
+          mma_tf32(acc[a][nt8], al, bh);
+          mma_tf32(acc[a][nt8], ah, bl);
+          mma_tf32(acc[a][nt8], ah, bh);
+        }
+      }
+    }
+    if (tid < D) {
+      const float* B = Bs + stage * SCHUR_TL;
+      float b = 0.f;
+#pragma unroll 8
+      for (int ls = 0; ls < SCHUR_TL; ++ls) b += B[ls] * P[ls * LDP + tid];
+      bacc += b;
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+#pragma unroll
+  for (int a = 0; a < SCHUR_MAXWT; ++a) {
+    const int wt = warp + 8 * a;
+    if (wt >= nwt) break;
+    const int row0 = 16 * (wt / nct), col0 = 32 * (wt % nct);
+    if (col0 + 31 < row0) continue;
+#pragma unroll
+    for (int nt8 = 0; nt8 < 4; ++nt8)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = row0 + gid + ((q & 2) ? 8 : 0);
+        const int c = col0 + 8 * nt8 + 2 * tig + (q & 1);
+        if (r <= c && c < D) Hs[(size_t)blockIdx.x * D * D + (size_t)r * D + c] = (double)acc[a][nt8][q];
+      }
+  }
+  if (tid < D) bs[(size_t)blockIdx.x * D + tid] = (double)bacc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// assembly of H_pp / b_p from the per-pair cores, in fp64 -- two kernels, no atomics, no zero-fill:
+//   k_core_reduce   : second stage of the per-pair core reduction (sum over the host frame's chunk CTAs)
+//   k_assemble      : GATHER form of the reference's scatter + symmetrisation
+//                     (hessian_block_evaluation.hpp:118-163, quirk Q3): one CTA per 8x8 block (bi, bj), bj >= bi
+//     H[r,r] = sum_t ( B_rt^T C_rt B_rt + C_tr ),  lower triangle mirrored (selfadjointView<Lower>)
+//     H[i,j] = -B_ij^T C_ij - (B_ji^T C_ji)^T  for i < j,  H[j,i] = H[i,j]^T
+//     b[r]   = sum_t ( B_rt^T q_rt - q_tr )
+//   with C_rt / q_rt the core of the ordered pair (reference r -> target t) and B = blockdiag(Adj, 1, s').
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_core_reduce(const __grid_constant__ WindowDev w,
+                                                     const float* __restrict__ core_part, int lpb, int chunk_stride,
+                                                     double* __restrict__ core, const LmCtl* __restrict__ ctl) {
+  if (lm_skip(ctl, 2)) return;
+  __shared__ double red[4][PBA_CORE];
+  const int N = w.n_frames;
+  const int r = blockIdx.x / (N - 1);
+  const int tw = blockIdx.x % (N - 1);  // the target's warp index in k_linearize_fused
+  const int t = tw + (tw >= r);
+  const int g = threadIdx.x >> 6, k = threadIdx.x & 63;
+  double acc = 0;
+  if (k < PBA_CORE) {
+    const int nchunk = (w.n_lm[r] + lpb - 1) / lpb;
+    const float* p = core_part + ((size_t)r * chunk_stride * (N - 1) + tw) * PBA_CORE + k;
+    for (int ch = g; ch < nchunk; ch += 4) acc += (double)p[(size_t)ch * (N - 1) * PBA_CORE];
+    red[g][k] = acc;
+  }
+  __syncthreads();
+  if (g == 0 && k < PBA_CORE) core[(size_t)(r * PBA_MAXF + t) * PBA_CORE + k] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+}
+
+__device__ __forceinline__ double core_at(const double* c, int i, int j) {  // symmetric 8x8 from its upper triangle
+  const int a = min(i, j), b = max(i, j);
+  return c[a * 8 - (a * (a - 1)) / 2 + (b - a)];
+}
+__device__ __forceinline__ double bm_at(const PairAssemble& pa, int fej, int i, int j) {  // B = blockdiag(Adj, 1, s')
+  if (i < 6 && j < 6) return (fej ? pa.adj_fej : pa.adj_cur)[i * 6 + j];
+  if (i == 6 && j == 6) return 1.0;
+  if (i == 7 && j == 7) return fej ? pa.s0 : pa.s;
+  return 0.0;
+}
+
 __global__ void __launch_bounds__(64) k_assemble(const __grid_constant__ WindowDev w, int fej,
                                                  const double* __restrict__ core, double* __restrict__ Hp,
                                                  double* __restrict__ bp, const LmCtl* __restrict__ ctl) {
   if (lm_skip(ctl, 2)) return;
   const int N = w.n_frames, D = 8 * N;
-  const int r = blockIdx.x / (N - 1);
-  int t = blockIdx.x % (N - 1);
-  t += (t >= r);
-  __shared__ double C[8][8], Bm[8][8], BC[8][8], q[8];
-  const int i = threadIdx.x / 8, j = threadIdx.x % 8;
-  const double* c = core + (size_t)(r * PBA_MAXF + t) * PBA_CORE;
-  const PairAssemble& pa = w.pairs_asm[r * PBA_MAXF + t];
-  {
-    const int a = min(i, j), b = max(i, j);
-    const int idx = a * 8 - (a * (a - 1)) / 2 + (b - a);  // upper-triangle row-major index
-    C[i][j] = c[idx];
-    double bm = 0;
-    if (i < 6 && j < 6) bm = (fej ? pa.adj_fej : pa.adj_cur)[i * 6 + j];
-    else if (i == 6 && j == 6) bm = 1.0;
-    else if (i == 7 && j == 7) bm = fej ? pa.s0 : pa.s;
-    Bm[i][j] = bm;
-    if (threadIdx.x < 8) q[threadIdx.x] = c[36 + threadIdx.x];
+  // blockIdx.x enumerates the upper-triangular block pairs (bi <= bj)
+  int bi = 0, rem = blockIdx.x;
+  while (rem >= N - bi) {
+    rem -= N - bi;
+    ++bi;
   }
+  const int bj = bi + rem;
+  const int i = threadIdx.x >> 3, j = threadIdx.x & 7;
+  __shared__ double C[8][8], Bm[8][8], T1[8][8], out[8][8];
+  if (bi != bj) {
+    double acc = 0;
+    for (int side = 0; side < 2; ++side) {
+      const int r = side ? bj : bi, t = side ? bi : bj;  // ordered pair r -> t contributes H_rt = -B^T C to block (r, t)
+      const double* c = core + (size_t)(r * PBA_MAXF + t) * PBA_CORE;
+      const PairAssemble& pa = w.pairs_asm[r * PBA_MAXF + t];
+      __syncthreads();
+      C[i][j] = core_at(c, i, j);
+      Bm[i][j] = bm_at(pa, fej, i, j);
+      __syncthreads();
+      double s = 0;
+      for (int k = 0; k < 8; ++k) s += Bm[k][i] * C[k][j];  // (B^T C)[i][j]
+      T1[i][j] = -s;
+      __syncthreads();
+      acc += side ? T1[j][i] : T1[i][j];  // block (bi,bj) += H_rt(bi->bj) + H_rt(bj->bi)^T
+    }
+    Hp[(size_t)(8 * bi + i) * D + 8 * bj + j] = acc;
+    Hp[(size_t)(8 * bj + j) * D + 8 * bi + i] = acc;
+    return;
+  }
+  // diagonal block r = bi, and b[r]
+  const int r = bi;
+  double acc = 0, bacc = 0;
+  for (int t = 0; t < N; ++t) {
+    if (t == r) continue;
+    const double* c_rt = core + (size_t)(r * PBA_MAXF + t) * PBA_CORE;
+    const double* c_tr = core + (size_t)(t * PBA_MAXF + r) * PBA_CORE;
+    const PairAssemble& pa = w.pairs_asm[r * PBA_MAXF + t];
+    __syncthreads();
+    C[i][j] = core_at(c_rt, i, j);
+    Bm[i][j] = bm_at(pa, fej, i, j);
+    __syncthreads();
+    double s = 0;
+    for (int k = 0; k < 8; ++k) s += Bm[k][i] * C[k][j];
+    T1[i][j] = s;  // B^T C
+    __syncthreads();
+    double hrr = 0;
+    for (int k = 0; k < 8; ++k) hrr += T1[i][k] * Bm[k][j];  // B^T C B
+    acc += hrr + core_at(c_tr, i, j);                          // + H_tt of the pair t -> r
+    if (j == 0) {
+      double br = 0;
+      for (int k = 0; k < 8; ++k) br += Bm[k][i] * c_rt[36 + k];  // B^T q_rt
+      bacc += br - c_tr[36 + i];                                    // b_t of the pair t -> r is -q_tr
+    }
+  }
+  out[i][j] = acc;
   __syncthreads();
-  double s = 0;
-  for (int k = 0; k < 8; ++k) s += Bm[k][i] * C[k][j];  // (B^T C)[i][j]
-  BC[i][j] = s;
+  Hp[(size_t)(8 * r + i) * D + 8 * r + j] = i >= j ? out[i][j] : out[j][i];  // selfadjointView<Lower>
+  if (j == 0) bp[8 * r + i] = bacc;
+}
+
+// second stage of the fused path's Schur reduction: out[o] = sum over the chunk CTAs of part[cta][o], o over the
+// 4x4 upper-triangle tiles and b.  16 groups of 64 outputs per CTA; each group strides over the chunk CTAs.
+__global__ void __launch_bounds__(1024) k_finish_fused(const __grid_constant__ WindowDev w, int lpb, int chunks,
+                                                       const float* __restrict__ part, double* __restrict__ Hs,
+                                                       double* __restrict__ bs, const LmCtl* __restrict__ ctl) {
+  if (lm_skip(ctl, 2)) return;
+  __shared__ double red[32][33];
+  const int N = w.n_frames, D = 8 * N;
+  const int T4 = D / 4, ntri = T4 * (T4 + 1) / 2, nout = ntri * 16 + D;
+  const int g = threadIdx.x >> 5, oo = threadIdx.x & 31;  // 32 groups stride over the chunk CTAs, 32 outputs per CTA
+  const int o = blockIdx.x * 32 + oo;
+  double acc = 0;
+  if (o < nout) {
+    for (int f = 0; f < N; ++f) {
+      const int nch = (w.n_lm[f] + lpb - 1) / lpb;  // CTAs past the last landmark never ran
+      const float* p = part + (size_t)f * chunks * nout + o;
+      float a0 = 0.f, a1 = 0.f;
+      int c = g;
+      for (; c + 32 < nch; c += 64) {
+        a0 += p[(size_t)c * nout];
+        a1 += p[(size_t)(c + 32) * nout];
+      }
+      if (c < nch) a0 += p[(size_t)c * nout];
+      acc += (double)a0 + (double)a1;
+    }
+  }
+  red[g][oo] = acc;
   __syncthreads();
-  double hrr = 0;
-  for (int k = 0; k < 8; ++k) hrr += BC[i][k] * Bm[k][j];
-  atomicAdd(&Hp[(size_t)(8 * r + i) * D + 8 * r + j], hrr);
-  Hp[(size_t)(8 * r + i) * D + 8 * t + j] = -BC[i][j];  // assignment (Q3); each (r,t) block has one writer
-  atomicAdd(&Hp[(size_t)(8 * t + i) * D + 8 * t + j], C[i][j]);
-  if (j == 0) {
-    double br = 0;
-    for (int k = 0; k < 8; ++k) br += Bm[k][i] * q[k];
-    atomicAdd(&bp[8 * r + i], br);
-    atomicAdd(&bp[8 * t + i], -q[i]);
+  if (g == 0 && o < nout) {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s += red[k][oo];
+    if (o >= ntri * 16) {
+      bs[o - ntri * 16] = s;
+    } else {
+      const int tile = o >> 4, e = o & 15;
+      int ty = 0, rem = tile;
+      while (rem >= T4 - ty) {
+        rem -= T4 - ty;
+        ++ty;
+      }
+      const int r = 4 * ty + (e >> 2), cc = 4 * (ty + rem) + (e & 3);
+      if (r <= cc) {  // diagonal tiles also carry r > cc: dropped, the mirror keeps H_s exactly symmetric
+        Hs[(size_t)r * D + cc] = s;
+        Hs[(size_t)cc * D + r] = s;
+      }
+    }
   }
 }
 
-__global__ void k_symmetrise(int D, double* __restrict__ Hp, const LmCtl* __restrict__ ctl) {
+// second stage of the Schur reduction + symmetrisation of both systems (hessian_block_evaluation.hpp:147-163):
+// H_s[i][j] = H_s[j][i] = sum over the SYRK CTAs of their upper-triangle partials; H_p mirrored as the reference does
+__global__ void k_finish_system(int D, double* __restrict__ Hp, double* __restrict__ Hs, double* __restrict__ bs,
+                                const double* __restrict__ schur_part, const double* __restrict__ bs_part, int nsb,
+                                const LmCtl* __restrict__ ctl) {
   if (lm_skip(ctl, 2)) return;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= D * D) return;
   const int i = a / D, j = a % D;
+  if (Hs && i <= j) {
+    double s = 0;
+    for (int b = 0; b < nsb; ++b) s += schur_part[(size_t)b * D * D + a];
+    Hs[(size_t)i * D + j] = s;
+    Hs[(size_t)j * D + i] = s;
+    if (i == 0) {
+      double t = 0;
+      for (int b = 0; b < nsb; ++b) t += bs_part[(size_t)b * D + j];
+      bs[j] = t;
+    }
+  }
+  if (!Hp) return;
   const int bi = i / 8, bj = j / 8;
   if (bi == bj) {
     if (i < j) Hp[(size_t)i * D + j] = Hp[(size_t)j * D + i];  // selfadjointView<Lower>
@@ -801,7 +1325,7 @@ __global__ void k_symmetrise(int D, double* __restrict__ Hp, const LmCtl* __rest
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_back_substitute(const __grid_constant__ WindowDev w,
                                                          const double* __restrict__ step_pose, float inv_lambda,
-                                                         const LmCtl* __restrict__ ctl, double* __restrict__ norms) {
+                                                         const LmCtl* __restrict__ ctl, double* __restrict__ norms /* per-CTA (state, step) partials or null */) {
   if (lm_skip(ctl, 1)) return;
   if (ctl) inv_lambda = (float)(1.0 / (1.0 + ctl->lambda));
   __shared__ float sp[PBA_MAXF * 8];
@@ -829,7 +1353,7 @@ __global__ void __launch_bounds__(256) k_back_substitute(const __grid_constant__
       w.idepth_step[gl] = stp;
     }
     if (norms) {  // landmark part of acceptStep's norms (problem.hpp:377-382), used by the device LM
-      const float id = w.idepth[gl];
+      const float id = w.lmk[gl].z;
       n_state = (double)id * id;
       n_step = (double)stp * stp;
     }
@@ -852,31 +1376,37 @@ __global__ void __launch_bounds__(256) k_back_substitute(const __grid_constant__
         a += sa[i];
         b += sb[i];
       }
-      if (a != 0 || b != 0) {
-        atomicAdd(&norms[2], a);
-        atomicAdd(&norms[3], b);
-      }
+      reinterpret_cast<double2*>(norms)[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = make_double2(a, b);
     }
   }
 }
 
 // acceptStep / rejectStep over landmarks (problem.hpp:377-384,395-399); norms in fp64
 __global__ void __launch_bounds__(256) k_accept_landmarks(const __grid_constant__ WindowDev w, int accept,
-                                                          double* __restrict__ scal, const LmCtl* __restrict__ ctl) {
+                                                          double* __restrict__ scal, const LmCtl* __restrict__ ctl,
+                                                          int with_statuses) {
   if (lm_skip(ctl, 1)) return;
   if (ctl) accept = ctl->accept;
   const int f = blockIdx.y;
   const int M = w.n_lm[f];
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   double st = 0, sp = 0;
+  if (l < M && with_statuses) {  // changeResidualStatuses folded in (problem.hpp:20-35)
+    for (int t = 0; t < w.n_frames; ++t) {
+      if (t == f) continue;
+      const size_t res = res_index(w, f, t, l);
+      if (accept > 0) w.status[res] = w.cand[res];
+      else w.cand[res] = w.status[res];
+    }
+  }
   if (l < M) {
     const int gl = lm_index(w, f, l);
     const float s = w.idepth_step[gl];
     if (accept > 0) {
-      const float id = w.idepth[gl];
+      const float id = w.lmk[gl].z;
       st = (double)id * id;
       sp = (double)s * s;
-      w.idepth[gl] = id + s;
+      w.lmk[gl].z = id + s;
     }
     w.idepth_step[gl] = 0.f;
   }
@@ -949,16 +1479,6 @@ __global__ void __launch_bounds__(256) k_landmarks_energy(const __grid_constant_
   }
 }
 
-__global__ void k_snapshot_fej(const __grid_constant__ WindowDev w) {
-  const int f = blockIdx.y;
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= w.n_lm[f]) return;
-  const int gl = lm_index(w, f, l);
-  const int fl = w.flags[gl];
-  if ((fl & LM_MARG) && !(fl & LM_TO_MARG)) return;  // first_estimate_jacobians.hpp:49
-  w.idepth_fej[gl] = w.idepth[gl];                   // quirk Q9: the CURRENT idepth, no step
-}
-
 // second half of updatePointStatuses (photometric_bundle_adjustment.cpp:363-405)
 __global__ void k_apply_point_statuses(const __grid_constant__ WindowDev w, float thr, int min_valid,
                                        const float* __restrict__ pair_dist) {
@@ -971,7 +1491,7 @@ __global__ void k_apply_point_statuses(const __grid_constant__ WindowDev w, floa
   if (fl & LM_MARG) return;
   unsigned valid = 0;
   float rb = w.rel_baseline[gl];
-  const float id = w.idepth[gl];
+  const float id = w.lmk[gl].z;
   for (int t = 0; t < N; ++t) {
     if (t == f || w.frame_marg[t]) continue;
     const size_t res = res_index(w, f, t, l);
@@ -1084,72 +1604,86 @@ __device__ void make_proj(const SE3d& T, const double* ir, const double* it, flo
   }
 }
 
-__global__ void __launch_bounds__(256) k_pair_setup(const FrameParams* __restrict__ fr, int N,
-                                                     PairConst* __restrict__ pairs, PairAssemble* __restrict__ pasm) {
-  // phase 1 (one thread per frame): exp(+eps), exp(-eps) and the inverse linearisation pose
-  __shared__ SE3d s_er[PBA_MAXF], s_et[PBA_MAXF], s_tl[PBA_MAXF], s_ti[PBA_MAXF];
+__global__ void __launch_bounds__(64) k_pair_setup(const FrameParams* __restrict__ fr, int N,
+                                                    PairConst* __restrict__ pairs, PairAssemble* __restrict__ pasm) {
+  // one CTA per reference frame r.  phase 1 (thread per frame): exp(+eps) of r, exp(-eps) and T_lin^-1 of every
+  // target; phase 2 (thread per target): the pair's constants, staged in shared memory; phase 3: coalesced write.
+  __shared__ SE3d s_et[PBA_MAXF], s_ti[PBA_MAXF];
+  __shared__ SE3d s_er, s_tl;
   __shared__ double s_a[PBA_MAXF], s_b[PBA_MAXF];
+  __shared__ PairConst s_pc[PBA_MAXF];
+  __shared__ PairAssemble s_pa[PBA_MAXF];
   const int tid = threadIdx.x;
+  const int r = blockIdx.x;
   if (tid < N) {
     const FrameParams& F = fr[tid];
     double e[6];
     for (int k = 0; k < 6; ++k) e[k] = F.eps[k] + F.step[k];
-    se3_exp(e, 1.0, s_er[tid]);
     se3_exp(e, -1.0, s_et[tid]);
     SE3d T;
     for (int i = 0; i < 3; ++i) {
       for (int j = 0; j < 3; ++j) T.R[i * 3 + j] = F.T_lin[i * 4 + j];
       T.t[i] = F.T_lin[i * 4 + 3];
     }
-    s_tl[tid] = T;
     se3_inv(T, s_ti[tid]);
     s_a[tid] = F.ab0[0] + F.eps[6] + F.step[6];
     s_b[tid] = F.ab0[1] + F.eps[7] + F.step[7];
+    if (tid == r) {
+      se3_exp(e, 1.0, s_er);
+      s_tl = T;
+    }
   }
   __syncthreads();
-  // phase 2 (one thread per ordered pair)
-  if (tid >= N * N) return;
-  const int r = tid / N, t = tid % N;
-  if (r == t) return;
-  const FrameParams& R = fr[r];
-  const FrameParams& T = fr[t];
-  SE3d T0, tmp, Tc;
-  se3_mul(s_ti[t], s_tl[r], T0);  // t_t_r0 (evaluate_jacobians.hpp:47-48)
-  se3_mul(T0, s_er[r], tmp);
-  se3_mul(s_et[t], tmp, Tc);      // t_t_r = exp(-eps_t) T0 exp(eps_r)  (:49)
-
-  PairConst pc;
-  make_proj(Tc, R.intr, T.intr, pc.M, pc.A);
-  make_proj(T0, R.intr, T.intr, pc.M0, nullptr);
-  for (int i = 0; i < 3; ++i) {
-    pc.tr[i] = (float)Tc.t[i];
-    pc.t0[i] = (float)T0.t[i];
+  const int t = tid;
+  if (t < N && t != r) {
+    const FrameParams& R = fr[r];
+    const FrameParams& T = fr[t];
+    SE3d T0, tmp, Tc;
+    se3_mul(s_ti[t], s_tl, T0);  // t_t_r0 (evaluate_jacobians.hpp:47-48)
+    se3_mul(T0, s_er, tmp);
+    se3_mul(s_et[t], tmp, Tc);   // t_t_r = exp(-eps_t) T0 exp(eps_r)  (:49)
+    PairConst& pc = s_pc[t];
+    PairAssemble& pa = s_pa[t];
+    make_proj(Tc, R.intr, T.intr, pc.M, pc.A);
+    make_proj(T0, R.intr, T.intr, pc.M0, nullptr);
+    for (int i = 0; i < 3; ++i) {
+      pc.tr[i] = (float)Tc.t[i];
+      pc.t0[i] = (float)T0.t[i];
+    }
+    pc.tr[3] = pc.t0[3] = 0.f;
+    se3_adj(Tc, pa.adj_cur);
+    se3_adj(T0, pa.adj_fej);
+    for (int i = 0; i < 36; ++i) {
+      pc.adj[i] = (float)pa.adj_cur[i];
+      pc.adj0[i] = (float)pa.adj_fej[i];
+    }
+    const double ratio = T.exposure / R.exposure;
+    pa.s = ratio * exp(s_a[t] - s_a[r]);
+    pa.s0 = ratio * exp(T.ab0[0] - R.ab0[0]);
+    const int last = (r == N - 1) ? N - 2 : N - 1;  // last target in deque order (quirk Q1)
+    const double s0_last = (fr[last].exposure / R.exposure) * exp(fr[last].ab0[0] - R.ab0[0]);
+    pc.s = (float)pa.s;
+    pc.s0 = (float)pa.s0;
+    pc.s0_last = (float)s0_last;
+    pc.b_t = (float)s_b[t];
+    pc.b_r = (float)s_b[r];
+    pc.b_r0 = (float)R.ab0[1];
+    pc.fx_t = (float)T.intr[0];
+    pc.fy_t = (float)T.intr[1];
+    pc.cx_t = (float)T.intr[2];
+    pc.cy_t = (float)T.intr[3];
+    pc.pad0 = pc.pad1 = 0.f;
   }
-  PairAssemble pa;
-  se3_adj(Tc, pa.adj_cur);
-  se3_adj(T0, pa.adj_fej);
-  for (int i = 0; i < 36; ++i) {
-    pc.adj[i] = (float)pa.adj_cur[i];
-    pc.adj0[i] = (float)pa.adj_fej[i];
+  __syncthreads();
+  for (int tt = 0; tt < N; ++tt) {
+    if (tt == r) continue;
+    const float4* src = reinterpret_cast<const float4*>(&s_pc[tt]);
+    float4* dst = reinterpret_cast<float4*>(&pairs[r * PBA_MAXF + tt]);
+    for (int i = tid; i < (int)(sizeof(PairConst) / 16); i += blockDim.x) dst[i] = src[i];
+    const double* ps = reinterpret_cast<const double*>(&s_pa[tt]);
+    double* pd = reinterpret_cast<double*>(&pasm[r * PBA_MAXF + tt]);
+    for (int i = tid; i < (int)(sizeof(PairAssemble) / 8); i += blockDim.x) pd[i] = ps[i];
   }
-  const double ratio = T.exposure / R.exposure;
-  pa.s = ratio * exp(s_a[t] - s_a[r]);
-  pa.s0 = ratio * exp(T.ab0[0] - R.ab0[0]);
-  const int last = (r == N - 1) ? N - 2 : N - 1;  // last target in deque order (quirk Q1)
-  const double s0_last = (fr[last].exposure / R.exposure) * exp(fr[last].ab0[0] - R.ab0[0]);
-  pc.s = (float)pa.s;
-  pc.s0 = (float)pa.s0;
-  pc.s0_last = (float)s0_last;
-  pc.b_t = (float)s_b[t];
-  pc.b_r = (float)s_b[r];
-  pc.b_r0 = (float)R.ab0[1];
-  pc.fx_t = (float)T.intr[0];
-  pc.fy_t = (float)T.intr[1];
-  pc.cx_t = (float)T.intr[2];
-  pc.cy_t = (float)T.intr[3];
-  pc.pad[0] = pc.pad[1] = 0.f;
-  pairs[r * PBA_MAXF + t] = pc;
-  pasm[r * PBA_MAXF + t] = pa;
 }
 
 // {I,dx,dy} float3 -> float4 texels
@@ -1203,12 +1737,46 @@ __global__ void k_lm_zero(const LmCtl* ctl, double* p, int n, int mode) {
 
 // calculateEnergy() tail (problem.hpp:293-316) + the accept decision (levenberg_marquardt_algorithm.hpp:95-104)
 __global__ void __launch_bounds__(128) k_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr,
-                                                   int N, const double* scal, const double* Hmarg,
-                                                   const double* bmarg, int kind) {
+                                                   int N, double* scal, const double* Hmarg,
+                                                   const double* bmarg, int kind, const double2* __restrict__ e_part,
+                                                   int n_e, const double2* __restrict__ n_part, int n_n) {
   if (kind == pba::LM_ENERGY_TRIAL && ctl->done) return;
   __shared__ double s[PBA_MAXF * 8];
   __shared__ double red[128];
+  __shared__ double r4[4][128];
   const int D = 8 * N, i = threadIdx.x;
+  if (e_part) {  // single-GPU: the second stage of the (energy, n) / norm reductions happens here, no extra launch
+    double a = 0, b = 0, c = 0, d = 0;
+    for (int k = i; k < n_e; k += 128) {
+      const double2 v = e_part[k];
+      a += v.x;
+      b += v.y;
+    }
+    for (int k = i; k < n_n; k += 128) {
+      const double2 v = n_part[k];
+      c += v.x;
+      d += v.y;
+    }
+    r4[0][i] = a;
+    r4[1][i] = b;
+    r4[2][i] = c;
+    r4[3][i] = d;
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+      if (i < st)
+        for (int q = 0; q < 4; ++q) r4[q][i] += r4[q][i + st];
+      __syncthreads();
+    }
+    if (i == 0) {
+      scal[0] = r4[0][0];
+      scal[1] = r4[1][0];
+      if (n_part) {
+        scal[2] = r4[2][0];
+        scal[3] = r4[3][0];
+      }
+    }
+    __syncthreads();
+  }
   if (i < D) s[i] = fr[i / 8].eps[i % 8] + fr[i / 8].step[i % 8];
   __syncthreads();
   double acc = 0;
@@ -1253,31 +1821,181 @@ __global__ void __launch_bounds__(128) k_lm_energy(LmCtl* ctl, const LmOptionsDe
   }
 }
 
-// acceptStep / rejectStep for the frame state + the loop bookkeeping (problem.hpp:366-402, lm.hpp:104-122)
-__global__ void k_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N) {
-  if (threadIdx.x || ctl->done) return;
-  if (ctl->accept > 0) {
-    double st = ctl->state_sq, sp = ctl->step_sq;
-    for (int f = 0; f < N; ++f) {
-      for (int k = 0; k < 8; ++k) st += fr[f].eps[k] * fr[f].eps[k];
-      st += fr[f].ab0[0] * fr[f].ab0[0] + fr[f].ab0[1] * fr[f].ab0[1];
-      for (int k = 0; k < 8; ++k) {
-        fr[f].eps[k] += fr[f].step[k];
-        sp += fr[f].step[k] * fr[f].step[k];
-        fr[f].step[k] = 0;
+// calculateStep (problem.hpp:342-357): priors (problem.hpp:37-77), full system, Jacobi preconditioner + LDL^T
+// (normal_linear_system.cpp:10-59), all fp64 in one CTA of 16x16 threads.  The (padded) matrix lives in REGISTERS:
+// thread (ty,tx) owns A[ty+16a][tx+16b], a,b < T (T = 4 for 8N <= 64, 8 for 8N <= 128).  Step k broadcasts column k
+// through a double-buffered shared vector, so the factorisation costs one barrier per column; L is collected in
+// shared memory for the warp-level back substitution.
+template <int T>
+__global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
+                                                 const int* fixed, int N, const double* __restrict__ Hp,
+                                                 const double* __restrict__ bp, const double* __restrict__ Hs,
+                                                 const double* __restrict__ bs, const double* __restrict__ Hmarg,
+                                                 const double* __restrict__ bmarg, double* __restrict__ step_dev) {
+  if (ctl->done) return;
+  constexpr int DP = 16 * T;
+  extern __shared__ double sh[];
+  const int D = 8 * N, tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  double* colk = sh;                 // [2][DP]
+  double* bk = colk + 2 * DP;        // [2]
+  double* dvec = bk + 2;             // [DP]
+  double* pre = dvec + DP;           // [DP]
+  double* st = pre + DP;             // [DP] state eps
+  double* hm = st + DP;              // [DP] H_marg * state
+  double* L = hm + DP;               // [DP][DP + 1]
+  const double lambda = ctl->lambda, ks = -1.0 / (1.0 + lambda);
+  if (tid < DP) st[tid] = tid < D ? fr[tid / 8].eps[tid % 8] : 0.0;
+  __syncthreads();
+  if (Hmarg) {  // warp per row, lanes along the row: coalesced
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < D; i += 8) {
+      double t = 0;
+      for (int j = lane; j < D; j += 32) t += Hmarg[(size_t)i * D + j] * st[j];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) t += __shfl_xor_sync(FULL, t, s);
+      if (lane == 0) hm[i] = t;
+    }
+  }
+  double a[T][T];
+#pragma unroll
+  for (int ai = 0; ai < T; ++ai)
+#pragma unroll
+    for (int aj = 0; aj < T; ++aj) {
+      const int i = ty + 16 * ai, j = tx + 16 * aj;
+      double v = (i == j) ? 1.0 : 0.0;  // identity padding
+      if (i < D && j < D) {
+        const size_t idx = (size_t)i * D + j;
+        double hp = Hp[idx];
+        if (i == j) {
+          const int f = i / 8, k = i % 8;
+          if (fixed[f]) hp += opt->fixed_reg;
+          else if (k >= 6) hp += opt->ab_reg[k - 6];
+          hp += hp * lambda;  // H.diagonal() += system_pose.H.diagonal() * lambda (prior included)
+        }
+        v = hp + (Hmarg ? Hmarg[idx] : 0.0) + ks * Hs[idx];
+      }
+      a[ai][aj] = v;
+      if (i == j) pre[i] = 1.0 / sqrt(v + 10.0);  // jacobiPreconditioner, +10 floor
+    }
+  __syncthreads();
+  double b = 0.0;
+  if (tid < D) {
+    const int f = tid / 8, k = tid % 8;
+    b = bp[tid] + ks * bs[tid];
+    if (fixed[f]) b += opt->fixed_reg * st[tid];
+    else if (k >= 6) b += opt->ab_reg[k - 6] * (fr[f].ab0[k - 6] + st[tid]);
+    if (Hmarg) b += bmarg[tid] + hm[tid];
+    b *= pre[tid];
+  }
+#pragma unroll
+  for (int ai = 0; ai < T; ++ai)
+#pragma unroll
+    for (int aj = 0; aj < T; ++aj) a[ai][aj] *= pre[ty + 16 * ai] * pre[tx + 16 * aj];
+
+  // Pivot loop.  fp64 arithmetic is the scarce resource here (one CTA, 8 warps, 8N strictly sequential pivots), so
+  // only the LOWER triangle is updated -- tiles with ai > aj entirely, diagonal tiles where tx <= ty -- and a
+  // column stops being updated once it is factored (k >= j).  Rows <= k are dead and may hold garbage.
+  const bool diag_lower = tx <= ty;
+  for (int k = 0; k < D; ++k) {
+    const int buf = k & 1;
+    double* ck = colk + buf * DP;
+    if (tx == (k & 15)) {  // owners of column k publish it (raw) and record it as column k of L * D
+      const int aj = k >> 4;
+#pragma unroll
+      for (int q = 0; q < T; ++q)
+        if (q == aj) {
+#pragma unroll
+          for (int ai = 0; ai < T; ++ai) {
+            const double v = a[ai][q];
+            ck[ty + 16 * ai] = v;
+            L[(ty + 16 * ai) * (DP + 1) + k] = v;
+          }
+        }
+    }
+    if (tid == k) bk[buf] = b;
+    __syncthreads();
+    const double d = ck[k];
+    // 1/d: fp32 reciprocal seed + one fp64 Newton step (relative error ~2^-46) instead of the ~15-deep IEEE
+    // division sequence; the preconditioned pivots are O(1), well inside the fp32 range
+    double inv = 0.0;
+    if (d != 0.0) {
+      inv = (double)__frcp_rn((float)d);
+      inv = inv * (2.0 - d * inv);
+    }
+    if (tid == 0) dvec[k] = inv;
+#pragma unroll
+    for (int aj = 0; aj < T; ++aj) {
+      if (k < tx + 16 * aj) {  // column still live
+        const double cj = ck[tx + 16 * aj] * inv;
+#pragma unroll
+        for (int ai = 0; ai < T; ++ai) {
+          if (ai > aj || (ai == aj && diag_lower)) a[ai][aj] -= ck[ty + 16 * ai] * cj;
+        }
       }
     }
-    ctl->state_sq = st;
-    ctl->step_sq = sp;
-    if (sp < opt->ptol * (st + opt->ptol)) ctl->converged = 1;
+    if (tid > k && tid < D) b -= ck[tid] * inv * bk[buf];
+  }
+  __syncthreads();
+  if (tid < D) st[tid] = b * dvec[tid];  // z = D^-1 L^-1 b  (reuse st; dvec holds 1/d)
+  __syncthreads();
+  // back substitution L^T x = z by one warp; L[k][i] = Lraw[k][i] / d_i
+  if (tid < 32) {
+    for (int k = D - 1; k > 0; --k) {
+      const double xk = st[k];
+      for (int i = tid; i < k; i += 32) st[i] -= L[k * (DP + 1) + i] * dvec[i] * xk;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (tid < D) {
+    const double x = st[tid] * pre[tid];
+    step_dev[tid] = x;
+    fr[tid / 8].step[tid % 8] = -x;  // frame.state_eps_step = -frame_step (problem.hpp:353-357)
+  }
+}
+
+// acceptStep / rejectStep for the frame state + the loop bookkeeping (problem.hpp:366-402, lm.hpp:104-122).
+// One thread per state entry, norms reduced in shared memory.
+__global__ void __launch_bounds__(128) k_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N) {
+  if (ctl->done) return;
+  __shared__ double r_st[128], r_sp[128];
+  const int i = threadIdx.x, D = 8 * N;
+  const int accept = ctl->accept;
+  double st = 0, sp = 0;
+  if (i < D) {
+    const int f = i / 8, k = i % 8;
+    const double e = fr[f].eps[k], s = fr[f].step[k];
+    if (accept > 0) {
+      st = e * e;
+      if (k >= 6) st += fr[f].ab0[k - 6] * fr[f].ab0[k - 6];
+      sp = s * s;
+      fr[f].eps[k] = e + s;
+    }
+    fr[f].step[k] = 0;
+  }
+  r_st[i] = st;
+  r_sp[i] = sp;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (i < s) {
+      r_st[i] += r_st[i + s];
+      r_sp[i] += r_sp[i + s];
+    }
+    __syncthreads();
+  }
+  if (i) return;
+  if (accept > 0) {
+    const double stt = ctl->state_sq + r_st[0], spp = ctl->step_sq + r_sp[0];
+    ctl->state_sq = stt;
+    ctl->step_sq = spp;
+    if (spp < opt->ptol * (stt + opt->ptol)) ctl->converged = 1;
     ctl->energy = ctl->next_energy;
     ctl->n_valid = ctl->next_n;
     ctl->lambda /= opt->dec;
     ctl->system_valid = 0;
   } else {
-    for (int f = 0; f < N; ++f)
-      for (int k = 0; k < 8; ++k) fr[f].step[k] = 0;
-    if (ctl->accept < 0 || opt->force_accept) {
+    if (accept < 0 || opt->force_accept) {
       ctl->done = 1;
       return;
     }
@@ -1288,85 +2006,6 @@ __global__ void k_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr
   if (ctl->iteration >= opt->max_it || ctl->converged || ctl->n_valid <= 0) ctl->done = 1;
 }
 
-// calculateStep (problem.hpp:342-357): priors (problem.hpp:37-77), full system, Jacobi preconditioner + LDL^T
-// (normal_linear_system.cpp:10-59), all fp64 in one CTA; A lives in dynamic shared memory [D][D+1].
-__global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
-                                                 const int* fixed, int N, const double* __restrict__ Hp,
-                                                 const double* __restrict__ bp, const double* __restrict__ Hs,
-                                                 const double* __restrict__ bs, const double* __restrict__ Hmarg,
-                                                 const double* __restrict__ bmarg, double* __restrict__ step_dev) {
-  if (ctl->done) return;
-  extern __shared__ double sh[];
-  const int D = 8 * N, LD = D + 1, tid = threadIdx.x, nt = blockDim.x;
-  double* A = sh;              // [D][LD]
-  double* b = A + D * LD;      // [D]
-  double* pre = b + D;         // [D]
-  double* st = pre + D;        // [D] state eps
-  const double lambda = ctl->lambda, ks = -1.0 / (1.0 + lambda);
-  for (int i = tid; i < D; i += nt) st[i] = fr[i / 8].eps[i % 8];
-  __syncthreads();
-  for (int idx = tid; idx < D * D; idx += nt) {
-    const int i = idx / D, j = idx - i * D;
-    double hp = Hp[idx];
-    if (i == j) {
-      const int f = i / 8, k = i % 8;
-      if (fixed[f]) hp += opt->fixed_reg;
-      else if (k >= 6) hp += opt->ab_reg[k - 6];
-      hp += hp * lambda;
-    }
-    A[i * LD + j] = hp + (Hmarg ? Hmarg[idx] : 0.0) + ks * Hs[idx];
-  }
-  for (int i = tid; i < D; i += nt) {
-    const int f = i / 8, k = i % 8;
-    double v = bp[i] + ks * bs[i];
-    if (fixed[f]) v += opt->fixed_reg * st[i];
-    else if (k >= 6) v += opt->ab_reg[k - 6] * (fr[f].ab0[k - 6] + st[i]);
-    if (Hmarg) {
-      double t = 0;
-      for (int j = 0; j < D; ++j) t += Hmarg[(size_t)i * D + j] * st[j];
-      v += bmarg[i] + t;
-    }
-    b[i] = v;
-  }
-  __syncthreads();
-  for (int i = tid; i < D; i += nt) pre[i] = 1.0 / sqrt(A[i * LD + i] + 10.0);
-  __syncthreads();
-  for (int idx = tid; idx < D * D; idx += nt) {
-    const int i = idx / D, j = idx - i * D;
-    A[i * LD + j] *= pre[i] * pre[j];
-  }
-  for (int i = tid; i < D; i += nt) b[i] *= pre[i];
-  __syncthreads();
-  // LDL^T, right-looking, forward substitution folded in; row k keeps d * L^T so the update is A_ij -= L_ik A_kj
-  for (int k = 0; k < D; ++k) {
-    const double d = A[k * LD + k];
-    const double inv = d != 0.0 ? 1.0 / d : 0.0;
-    for (int i = k + 1 + tid; i < D; i += nt) A[i * LD + k] *= inv;
-    __syncthreads();
-    const int m = D - k - 1;
-    for (int idx = tid; idx < m * m; idx += nt) {
-      const int i = k + 1 + idx / m, j = k + 1 + idx % m;
-      A[i * LD + j] -= A[i * LD + k] * A[k * LD + j];
-    }
-    for (int i = k + 1 + tid; i < D; i += nt) b[i] -= A[i * LD + k] * b[k];
-    __syncthreads();
-  }
-  for (int i = tid; i < D; i += nt) {
-    const double d = A[i * LD + i];
-    b[i] = d != 0.0 ? b[i] / d : 0.0;
-  }
-  __syncthreads();
-  for (int k = D - 1; k > 0; --k) {
-    const double xk = b[k];
-    for (int i = tid; i < k; i += nt) b[i] -= A[k * LD + i] * xk;
-    __syncthreads();
-  }
-  for (int i = tid; i < D; i += nt) {
-    const double x = b[i] * pre[i];
-    step_dev[i] = x;
-    fr[i / 8].step[i % 8] = -x;  // frame.state_eps_step = -frame_step (problem.hpp:353-357)
-  }
-}
 
 int max_landmarks(const WindowDev& w) {
   int m = 0;
@@ -1379,6 +2018,8 @@ int max_landmarks(const WindowDev& w) {
 namespace pba {
 
 std::atomic<long long> g_launches{0};
+bool g_schur_mma = false;  // true: Schur SYRK as 3xTF32 mma.sync (faster inner product, ~10x larger rounding error in the reduced system); default: fp32 FFMA kernel
+void set_schur_mma(bool on) { g_schur_mma = on; }
 long long launch_count() { return g_launches.load(); }
 void add_launches(long long n) { g_launches += n; }
 
@@ -1404,33 +2045,42 @@ void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s
   k_lm_zero<<<(n + 255) / 256, 256, 0, s>>>(ctl, p, n, mode);
 }
 
-void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr, int N, const double* scal,
-                      const double* Hmarg, const double* bmarg, int kind, cudaStream_t s) {
+void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr, int N, double* scal,
+                      const double* Hmarg, const double* bmarg, int kind, cudaStream_t s, const double* e_part, int n_e,
+                      const double* n_part, int n_n) {
   ++g_launches;
-  k_lm_energy<<<1, 128, 0, s>>>(ctl, opt, fr, N, scal, Hmarg, bmarg, kind);
+  k_lm_energy<<<1, 128, 0, s>>>(ctl, opt, fr, N, scal, Hmarg, bmarg, kind, reinterpret_cast<const double2*>(e_part), n_e,
+                                reinterpret_cast<const double2*>(n_part), n_n);
 }
 
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
                     const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s) {
   const int D = 8 * N;
-  const size_t smem = (size_t)(D * (D + 1) + 3 * D) * sizeof(double);
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    cudaFuncSetAttribute(k_lm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(128 * 129 + 3 * 128) * 8));
-    attr_set = true;
-  }
   ++g_launches;
-  k_lm_step<<<1, 256, smem, s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
+  if (D <= 64) {
+    constexpr int DP = 64;
+    const size_t smem = (size_t)(2 * DP + 2 + 4 * DP + DP * (DP + 1)) * sizeof(double);
+    k_lm_step<4><<<1, 256, smem, s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
+  } else {
+    constexpr int DP = 128;
+    const size_t smem = (size_t)(2 * DP + 2 + 4 * DP + DP * (DP + 1)) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_lm_step<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
+    k_lm_step<8><<<1, 256, smem, s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
+  }
 }
 
 void launch_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, cudaStream_t s) {
   ++g_launches;
-  k_lm_finish<<<1, 32, 0, s>>>(ctl, opt, fr, N);
+  k_lm_finish<<<1, 128, 0, s>>>(ctl, opt, fr, N);
 }
 
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s) {
   ++g_launches;
-  k_pair_setup<<<1, 256, 0, s>>>(frames, n_frames, pairs, pasm);
+  k_pair_setup<<<n_frames, 64, 0, s>>>(frames, n_frames, pairs, pasm);
 }
 
 void launch_pack_image(const float* src3, float4* dst, int n_px, cudaStream_t s) {
@@ -1444,14 +2094,22 @@ void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s)
   k_pixelinfo<<<g, b, 0, s>>>(I, dst, W, H);
 }
 
-void launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* scal, cudaStream_t s,
-                           const LmCtl* ctl, int ctl_mode) {
+int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* part, cudaStream_t s,
+                          const LmCtl* ctl, int ctl_mode) {
   const int m = max_landmarks(w);
-  if (m == 0 || w.n_frames < 2) return;
+  if (m == 0 || w.n_frames < 2) return 0;
   dim3 g((m + 31) / 32, w.n_frames * (w.n_frames - 1));
   ++g_launches;
-  if (fej) k_residual_sweep<true><<<g, 256, 0, s>>>(w, sigma, huber, scal, ctl, ctl_mode);
-  else k_residual_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber, scal, ctl, ctl_mode);
+  if (fej) k_residual_sweep<true><<<g, 256, 0, s>>>(w, sigma, huber, reinterpret_cast<double2*>(part), ctl, ctl_mode);
+  else k_residual_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber, reinterpret_cast<double2*>(part), ctl, ctl_mode);
+  return (int)(g.x * g.y);  // partial slots written
+}
+
+void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, int n_e, const double* n_part, int n_n,
+                        double* scal, cudaStream_t s) {
+  ++g_launches;
+  k_reduce_scal<<<1, 1024, 0, s>>>(ctl, ctl_mode, reinterpret_cast<const double2*>(e_part), n_e,
+                                   reinterpret_cast<const double2*>(n_part), n_n, scal);
 }
 
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s) {
@@ -1463,26 +2121,48 @@ void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fe
   else k_materialise_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber);
 }
 
-void launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
-                            cudaStream_t s, const LmCtl* ctl) {
+template <int NWMAX>
+static void launch_fused_t(const WindowDev& w, float sigma, int huber, int fej, int for_marg, int lpb, dim3 g,
+                           int threads, size_t smem, float* core, float* schur, cudaStream_t s, const LmCtl* ctl) {
+  static bool attr[2] = {false, false};
+  if (smem > 48 * 1024 && !attr[fej ? 1 : 0]) {
+    if (fej) cudaFuncSetAttribute(k_linearize_fused<true, NWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    else cudaFuncSetAttribute(k_linearize_fused<false, NWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr[fej ? 1 : 0] = true;
+  }
+  ++g_launches;
+  if (fej) k_linearize_fused<true, NWMAX><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl);
+  else k_linearize_fused<false, NWMAX><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl);
+}
+
+FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
+                                  cudaStream_t s, const LmCtl* ctl) {
+  FusedShape shape{0, 0};
   const int m = max_landmarks(w);
-  if (m == 0 || w.n_frames < 2) return;
+  if (m == 0 || w.n_frames < 2) return shape;
   const int N = w.n_frames, D = 8 * N;
-  // landmarks per block: small chunks while the window is small (fill the 148 SMs), larger once it is not
+  // landmarks per CTA: the candidate whose wave count times per-CTA work (lpb/4 loop trips + the fixed prologue /
+  // epilogue, worth ~1.5 trips) is smallest -- small windows want many small CTAs, large ones amortise the epilogue
+  const int resident = sm_count() * (N <= 9 ? 4 : 2);
   int lpb = 16;
-  while (lpb < 64 && (long)((m + lpb - 1) / lpb) * N > 8L * sm_count()) lpb *= 2;
-  const size_t smem = (size_t)lpb * (D + 2) * sizeof(float) + (size_t)(N - 1) * sizeof(PairConst);
+  double best = 1e30;
+  for (int cand = 8; cand <= 64; cand += 4) {
+    const long blocks = (long)((m + cand - 1) / cand) * N;
+    const double waves = (double)((blocks + resident - 1) / resident);
+    const double cost = waves * (cand / 4 + 1.5);
+    if (cost < best - 1e-9) {
+      best = cost;
+      lpb = cand;
+    }
+  }
+  const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + (size_t)lpb * (D + 2) * sizeof(float);
   dim3 g((m + lpb - 1) / lpb, N);
   const int threads = 32 * (N - 1);
-  if (fej) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_linearize_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ++g_launches;
-    k_linearize_fused<true><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, rb.core, ctl);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_linearize_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ++g_launches;
-    k_linearize_fused<false><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, rb.core, ctl);
-  }
+  if (N <= 9) launch_fused_t<8>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
+  else launch_fused_t<15>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
+  shape.lpb = lpb;
+  shape.chunks = (int)g.x;
+  return shape;
 }
 
 void launch_linearize_from_materialized(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s) {
@@ -1498,33 +2178,56 @@ void launch_linearize_from_materialized(const WindowDev& w, int for_marg, Reduce
   k_schur_prep_from_materialized<<<g2, 128, 0, s>>>(w, for_marg);
 }
 
-void launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl) {
+int launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl) {
   const int N = w.n_frames, D = 8 * N;
   int tiles = 0;
   for (int f = 0; f < N; ++f) tiles += (w.n_lm[f] + SCHUR_TL - 1) / SCHUR_TL;
-  if (tiles == 0) return;
+  if (tiles == 0) return 0;
   const int T4 = D / 4;
-  int threads = ((T4 * T4 + 31) / 32) * 32;
-  if (threads < D) threads = ((D + 31) / 32) * 32;
-  const size_t smem = (size_t)(2 * SCHUR_TL * D + SCHUR_TL) * sizeof(float);
-  const int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int ntri = T4 * (T4 + 1) / 2;
+  const int gthreads = ((std::max(ntri, D) + 31) / 32) * 32;
+  const int G = std::max(1, std::min(4, 1024 / gthreads));
+  const size_t smem = (size_t)(2 * SCHUR_TL * D + 4 * SCHUR_TL) * sizeof(float) + (size_t)(ntri * 16 + D) * sizeof(double);
+  const int grid = std::min(sm_count(), tiles);
+  static bool attr = false;
+  if (smem > 48 * 1024 && !attr) {
+    cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    attr = true;
+  }
   ++g_launches;
-  k_schur<<<grid, threads, smem, s>>>(w, for_marg, rb.Hs, rb.bs, ctl);
+  if (g_schur_mma) {
+    const int DP = (D + 31) & ~31;
+    const size_t smem2 = (size_t)(2 * SCHUR_TL * (DP + 8) + 4 * SCHUR_TL) * sizeof(float);
+    k_schur_mma<<<grid, 256, smem2, s>>>(w, for_marg, rb.schur_part, rb.bs_part, ctl);
+  } else {
+    k_schur<<<grid, G * gthreads, smem, s>>>(w, for_marg, G, gthreads, rb.schur_part, rb.bs_part, ctl);
+  }
+  return grid;  // CTAs that wrote a partial
 }
 
-void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl) {
+void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl) {
+  const int N = w.n_frames;
+  if (N < 2 || shape.lpb == 0) return;
+  ++g_launches;
+  k_core_reduce<<<N * (N - 1), 256, 0, s>>>(w, rb.core_part, shape.lpb, shape.chunks, rb.core, ctl);
+  ++g_launches;
+  k_assemble<<<N * (N + 1) / 2, 64, 0, s>>>(w, fej, rb.core, rb.Hp, rb.bp, ctl);
+}
+
+// fused path: sums the per-chunk Schur partials written by k_linearize_fused and mirrors H_s (k_assemble already
+// wrote a symmetric Hp)
+void launch_finish_fused(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl) {
   const int N = w.n_frames, D = 8 * N;
-  if (N < 2) return;
+  if (N < 2 || shape.lpb == 0) return;
+  const int T4 = D / 4, nout = T4 * (T4 + 1) / 2 * 16 + D;
   ++g_launches;
-  k_assemble<<<N * (N - 1), 64, 0, s>>>(w, fej, rb.core, rb.Hp, rb.bp, ctl);
-  ++g_launches;
-  k_symmetrise<<<(D * D + 255) / 256, 256, 0, s>>>(D, rb.Hp, ctl);
+  k_finish_fused<<<(nout + 31) / 32, 1024, 0, s>>>(w, shape.lpb, shape.chunks, rb.fschur_part, rb.Hs, rb.bs, ctl);
 }
 
-void launch_symmetrise_only(int D, double* Hp, cudaStream_t s) {
+// sums the Schur partials of `nsb` CTAs into Hs / bs (skipped when nsb == 0 and Hs == nullptr) and symmetrises Hp
+void launch_finish_system(int D, ReduceBuf rb, int nsb, cudaStream_t s, const LmCtl* ctl) {
   ++g_launches;
-  k_symmetrise<<<(D * D + 255) / 256, 256, 0, s>>>(D, Hp, nullptr);
+  k_finish_system<<<(D * D + 255) / 256, 256, 0, s>>>(D, rb.Hp, rb.Hs, rb.bs, rb.schur_part, rb.bs_part, nsb, ctl);
 }
 
 void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, double lambda, cudaStream_t s,
@@ -1536,12 +2239,12 @@ void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, dou
   k_back_substitute<<<g, 256, 0, s>>>(w, step_pose_dev, (float)(1.0 / (1.0 + lambda)), ctl, norms);
 }
 
-void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s, const LmCtl* ctl) {
+void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s, const LmCtl* ctl, int with_statuses) {
   const int m = max_landmarks(w);
   if (m == 0) return;
   dim3 g((m + 255) / 256, w.n_frames);
   ++g_launches;
-  k_accept_landmarks<<<g, 256, 0, s>>>(w, accept, scal, ctl);
+  k_accept_landmarks<<<g, 256, 0, s>>>(w, accept, scal, ctl, with_statuses);
 }
 
 void launch_change_statuses(const WindowDev& w, int accept, cudaStream_t s, const LmCtl* ctl) {
@@ -1560,12 +2263,12 @@ void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cud
   k_landmarks_energy<<<g, 256, 0, s>>>(w, for_marg, scal);
 }
 
-void launch_snapshot_fej(const WindowDev& w, cudaStream_t s) {
+void launch_first_estimate(const WindowDev& w, cudaStream_t s) {
   const int m = max_landmarks(w);
-  if (m == 0) return;
-  dim3 g((m + 255) / 256, w.n_frames);
+  if (m == 0 || w.n_frames < 2) return;
+  dim3 g((m + 31) / 32, w.n_frames * (w.n_frames - 1));
   ++g_launches;
-  k_snapshot_fej<<<g, 256, 0, s>>>(w);
+  k_first_estimate<<<g, 256, 0, s>>>(w);
 }
 
 void launch_apply_point_statuses(const WindowDev& w, float threshold, int min_valid, const float* pair_dist,

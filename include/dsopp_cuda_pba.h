@@ -230,7 +230,8 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* options, const double* 
                   double energy_marg, dpba_lm_result* result);
 
 /* Tuning knobs without a reference counterpart.  "cuda_graph" (default 1): dpba_solve_lm replays its launch
- * sequence as one CUDA graph. */
+ * sequence as one CUDA graph.  "schur_tensor_cores" (default 1, process-wide): the Schur-complement SYRK runs as
+ * 3xTF32 mma.sync; 0 selects the fp32 FFMA kernel. */
 int dpba_set_option(dpba_handle* h, const char* name, int64_t value);
 
 /* ---- measurement hooks (no reference counterpart) --------------------------------------- */

@@ -228,8 +228,9 @@ bool reproject_values(const Pair<S>& pc, const Landmark<S>& lm, S rho, int W, in
     const S u = lm.ref_pattern[i][0], v = lm.ref_pattern[i][1];
     const S X = row_apply(pc.A + 0, u, v, rho), Y = row_apply(pc.A + 4, u, v, rho), Z = row_apply(pc.A + 8, u, v, rho);
     zpos = zpos && (Z > S(0));
-    tp[i][0] = X / Z;
-    tp[i][1] = Y / Z;
+    const S rz = S(1) / Z;  // hnormalized() as reciprocal + products: the operation order of the CUDA kernels
+    tp[i][0] = X * rz;
+    tp[i][1] = Y * rz;
     roi = roi && in_roi(tp[i][0], tp[i][1], xmax, ymax);
   }
   return ok && zpos && roi;
@@ -247,8 +248,9 @@ bool reproject_jac(const S* M, const S* t, const Pair<S>& pc, const Landmark<S>&
     const S u = lm.ref_pattern[i][0], v = lm.ref_pattern[i][1];
     const S qx = row_apply(M + 0, u, v, rho), qy = row_apply(M + 4, u, v, rho), qz = row_apply(M + 8, u, v, rho);
     zpos = zpos && (qz > S(0));
-    tp[i][0] = (pc.fx * qx + pc.cx * qz) / qz;
-    tp[i][1] = (pc.fy * qy + pc.cy * qz) / qz;
+    const S rz = S(1) / qz;
+    tp[i][0] = (pc.fx * qx + pc.cx * qz) * rz;
+    tp[i][1] = (pc.fy * qy + pc.cy * qz) * rz;
     roi = roi && in_roi(tp[i][0], tp[i][1], xmax, ymax);
     const S sI = S(1) / qz, b0 = qx * sI, b1 = qy * sI, nid = rho * sI;
     r.d_u_idepth[i] = pc.fx * (t[0] * sI - t[2] * sI * b0);

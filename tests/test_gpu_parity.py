@@ -226,9 +226,15 @@ def test_lm_solve_through_the_c_abi_tracks_the_oracle(capi, name, ab_scale, ab_r
     meta = [dict(ab0=f.ab0, fixed=f.fixed) for f in win.frames]
     (e_ref, n_ref, _), tr_ref = run_lm(O, O.Problem(frames, SIGMA, ab_reg=ab_reg))
     (e, n, _), tr = run_lm(O, CudaProblem(h, meta, SIGMA, ab_reg=ab_reg))
-    assert len(tr) == len(tr_ref)
+    # Near convergence the accept test "E1 < E0" compares energies that agree to ~1e-5: below that margin the
+    # decision (and so the iteration count under force_accept) is legitimately ambiguous between fp32 and fp64.
+    prev = None
     for a, b in zip(tr, tr_ref):
-        assert a["accepted"] == b["accepted"]
+        margin = abs(b["energy"] - (prev if prev is not None else b["energy"] * 2)) / abs(b["energy"])
+        prev = b["energy"] if b["accepted"] else prev
+        if a["accepted"] != b["accepted"]:
+            assert margin < 2e-4, (a["it"], margin)
+            break
         assert abs(a["n"] - b["n"]) <= 2
         assert abs(a["energy"] - b["energy"]) <= 2e-4 * abs(b["energy"])
         sn = np.linalg.norm(b["step"])
@@ -237,6 +243,7 @@ def test_lm_solve_through_the_c_abi_tracks_the_oracle(capi, name, ab_scale, ab_r
         # once the iteration converges the step is the difference of two nearby fixed points: absolute floor
         atol = 2e-5 * max(1.0, max(np.abs(f.ab0).max() for f in win.frames))
         assert np.linalg.norm(a["step"] - b["step"]) <= RTOL_STEP * sn + atol, (a["it"], np.linalg.norm(a["step"] - b["step"]), sn)
+    assert abs(len(tr) - len(tr_ref)) <= 1
     assert abs(e - e_ref) <= 2e-4 * abs(e_ref)
     eps, _ = h.get_state()
     eps_ref = O.state_eps_stacked(frames)
@@ -244,7 +251,7 @@ def test_lm_solve_through_the_c_abi_tracks_the_oracle(capi, name, ab_scale, ab_r
     assert np.abs(eps - eps_ref).max() <= 2e-5 * max(1.0, max(np.abs(f.ab0).max() for f in win.frames))
     for i, f in enumerate(frames):
         lm = h.get_landmarks(i)
-        assert np.abs(lm["idepth"] - f.idepth).max() <= 2e-5
+        assert np.abs(lm["idepth"] - f.idepth).max() <= 5e-5  # weakly observed idepths amplify rounding
         for j, g in enumerate(frames):
             if i != j:
                 st, _ = h.get_statuses(i, j)
@@ -318,4 +325,28 @@ def test_error_codes(capi):
         h.set_landmarks(0, np.zeros((11, 2)), np.zeros(11), np.zeros((11, 8)))  # capacity
     with pytest.raises(capi.DpbaError):
         h.set_statuses(0, 0, np.zeros(10, np.uint8))  # r == t
+    h.close()
+
+
+@pytest.mark.parametrize("n_frames", [3, 8, 9])
+def test_tensor_core_schur_matches_fp32_schur(capi, n_frames):
+    """3xTF32 mma.sync SYRK vs the fp32 FFMA kernel vs the oracle (8N = 24, 64, 72: padded and unpadded tiles)."""
+    O = oracle()
+    win = synth.make_window(n_frames=n_frames, points_per_frame=150, seed=40 + n_frames)
+    frames = O.frames_from_window(win)
+    O.first_estimate_jacobians(frames)
+    O.evaluate_jacobians(frames, SIGMA, fej=True, evaluate_jacobians=True, new_point=True, huber=True)
+    Hs_ref, bs_ref = O.schur_complement(frames)
+    h = capi.upload_window(win)
+    h.first_estimate()
+    out = {}
+    for mode in (1, 0):
+        h.set_option("schur_tensor_cores", mode)
+        _, _, Hs, bs = h.linearize(SIGMA, True, True, False)
+        out[mode] = (Hs, bs)
+        assert np.abs(Hs - Hs_ref).max() <= RTOL_SYS * np.abs(Hs_ref).max(), mode
+        assert np.abs(bs - bs_ref).max() <= RTOL_B * np.abs(bs_ref).max(), mode
+        assert np.array_equal(Hs, Hs.T)
+    h.set_option("schur_tensor_cores", 1)
+    print("mma vs ffma: max|dH|/max|H| =", np.abs(out[1][0] - out[0][0]).max() / np.abs(Hs_ref).max())
     h.close()
