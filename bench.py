@@ -200,6 +200,8 @@ def run_ours(args):
             uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        h.first_estimate()
+        h.evaluate(SIGMA, True, True)  # first collective outside any graph capture: NCCL sets its channels up here
 
     ab0 = np.stack([f.ab0 for f in win.frames])
     fixed = [int(f.fixed) for f in win.frames]
@@ -328,9 +330,20 @@ def run_ours(args):
         h.profile_enable(False)
         sweep = ms / max(cnt, 1)
 
-    if rank != 0:
+    def teardown():
+        # the library's NCCL communicator is destroyed by every rank at the same point, while all are alive
+        sys.stdout.flush()
         if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            h.close()
+            dist.barrier()
             dist.destroy_process_group()
+        else:
+            h.close()
+
+    if rank != 0:
+        teardown()
         return
 
     peaks, peak_kind = measured_peaks()
@@ -398,8 +411,7 @@ def run_ours(args):
         "us_per_gn_iter": 1e3 * total_ms / args.steps / GN_ITERS,
     }
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 def main():
@@ -416,6 +428,9 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)  # skip interpreter finalisation (CUDA / NCCL destructors of other libraries may block at exit)
 
 
 if __name__ == "__main__":

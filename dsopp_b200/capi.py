@@ -363,8 +363,9 @@ def comm_unique_id() -> bytes:
 
 def upload_window(win, max_frames=None, max_points=None, device=0, rank=0, world_size=1) -> Handle:
     """Create a handle and load a dsopp_b200.synth.SynthWindow into it (landmark shard `rank` of `world_size`)."""
+    from .sharding import shard_indices
     n = win.n_frames
-    shard = [np.arange(rank, len(f.idepth), world_size) for f in win.frames]
+    shard = [shard_indices(len(f.idepth), rank, world_size) for f in win.frames]
     mp = max_points or max(1, max(len(s) for s in shard))
     h = Handle(max_frames or max(2, n), mp, win.width, win.height, device, rank, world_size)
     for f in win.frames:

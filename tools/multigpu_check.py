@@ -1,0 +1,78 @@
+"""Run under torchrun on N GPUs: the sharded solve (landmarks dealt over the ranks, NCCL exchange of the packed
+reduced system inside dpba_linearize / dpba_solve_lm) must reproduce the single-GPU solve of the same window.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multigpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dsopp_b200 import capi, sharding, synth  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    def say(*a):
+        print(f"[rank {rank}]", *a, flush=True)
+    dist.init_process_group("nccl", device_id=dev)
+    say("process group up")
+    win = synth.make_window(n_frames=5, points_per_frame=601, seed=9, ab_scale=0.0)
+    h = capi.upload_window(win, device=local, rank=rank, world_size=world)
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    say("unique id broadcast")
+    h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    say("dpba_comm_init done")
+    h.first_estimate()
+    Hp, bp, Hs, bs = h.linearize(20.0, True, True, False)
+    say("linearize done")
+    e, n = h.evaluate(20.0, True, True)
+    say("evaluate done")
+    h.first_estimate()
+    E, it, conv, nv = h.solve_lm(20.0)
+    say("solve_lm done")
+    eps, _ = h.get_state()
+    idepth = [h.get_landmarks(i)["idepth"] for i in range(win.n_frames)]
+    ok = True
+    if rank == 0:
+        ref = capi.upload_window(win, device=local)
+        ref.first_estimate()
+        Hp1, bp1, Hs1, bs1 = ref.linearize(20.0, True, True, False)
+        e1, n1 = ref.evaluate(20.0, True, True)
+        ref.first_estimate()
+        E1, it1, _, nv1 = ref.solve_lm(20.0)
+        eps1, _ = ref.get_state()
+        for a, b, nm in ((Hp, Hp1, "Hp"), (bp, bp1, "bp"), (Hs, Hs1, "Hs"), (bs, bs1, "bs")):
+            err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+            print(f"{nm}: max|d|/max|ref| = {err:.2e}")
+            ok &= err < 1e-6
+        print(f"energy {e} vs {e1}, n {n} vs {n1}; LM energy {E} vs {E1}, it {it} vs {it1}, max|d eps| {np.abs(eps - eps1).max():.2e}")
+        ok &= abs(e - e1) <= 1e-6 * abs(e1) and n == n1
+        ok &= abs(E - E1) <= 5e-5 * abs(E1) and abs(it - it1) <= 1 and np.abs(eps - eps1).max() < 2e-5
+        for i in range(win.n_frames):
+            full = ref.get_landmarks(i)["idepth"]
+            mine = full[sharding.shard_indices(len(full), 0, world)]
+            ok &= np.abs(mine - idepth[i]).max() < 5e-5
+        print("MULTIGPU_CHECK", "PASS" if ok else "FAIL", f"world={world}")
+        ref.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    h.close()  # ncclCommDestroy while every rank is still alive
+    say("closed")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
