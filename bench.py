@@ -241,21 +241,18 @@ def run_ours(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), capi.launch_count() - l0
 
-    # ---- value: resident window ---------------------------------------------------------------------
+    # ---- value: resident window (per-kernel event profiling OFF: the graph holds kernels only) ------------------
     sampler = ClockSampler(local)
     step_ms, launches, iters_seen = [], 0, []
     for i in range(args.warmup + args.steps):
         reset_resident()
         if i == args.warmup:
-            h.profile_enable(True)
             sampler.start()
         ms, nl = timed(lambda: iters_seen.append(solve()[1]))
         if i >= args.warmup:
             step_ms.append(ms)
             launches += nl
     clocks = sampler.stop()
-    prof = h.profile_read()
-    h.profile_enable(False)
     assert all(it == GN_ITERS for it in iters_seen), iters_seen
     t_local = sum(step_ms)
     t = torch.tensor([t_local], dtype=torch.float64, device=dev)
@@ -263,6 +260,16 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = units_global * GN_ITERS * args.steps / (total_ms * 1e-3)
+
+    # ---- the same steps again with CUDA events around every kernel inside the graph (roofline / kernel_ms) --------
+    h.profile_enable(True)
+    for i in range(2 + min(args.steps, 10)):
+        reset_resident()
+        if i == 2:
+            h.profile_enable(True)  # resets the sums after the re-capture + warm-up
+        timed(solve)
+    prof = h.profile_read()
+    h.profile_enable(False)
 
     # ---- e2e: host buffers in, results out, every step ------------------------------------------------
     keep = []
@@ -277,20 +284,28 @@ def run_ours(args):
         flg, t6 = pin(f.flags[s])
         keep += [t1, t2, t3, t4, t5, t6]
         host_frames.append((f, img, msk, uv, idp, pat, flg))
-    host_status = {k: pin(v[shard[k[0]]])[0] for k, v in win.statuses.items()}
+    host_status = []
+    for r in range(n):
+        rows = {}
+        for tt in range(n):
+            if tt != r:
+                a, tk = pin(win.statuses[(r, tt)][shard[r]])
+                keep.append(tk)
+                rows[tt] = a
+        host_status.append(rows)
     h2d = sum(x[1].nbytes + x[2].nbytes + x[3].nbytes + x[4].nbytes + x[5].nbytes + x[6].nbytes for x in host_frames)
-    h2d += sum(v.nbytes for v in host_status.values()) + eps0.nbytes * 2
+    h2d += sum(v.nbytes for rows in host_status for v in rows.values()) + eps0.nbytes * 2
     d2h_box = [0]
 
     def e2e_step():
+        # the whole window goes host -> device every step (the tracker uploads ONE new keyframe per solve)
         for _ in range(h.n_frames):
             h.remove_frame(0)
         for (f, img, msk, uv, idp, pat, flg) in host_frames:
             h.push_frame(f.frame_id, img, msk, f.T_w_lin, f.exposure, f.ab0, f.intr, f.fixed)
         for i, (f, img, msk, uv, idp, pat, flg) in enumerate(host_frames):
             h.set_landmarks(i, uv, idp, pat, flg)
-        for (r, tt), st in host_status.items():
-            h.set_statuses(r, tt, st)
+            h.set_frame_statuses(i, host_status[i])
         h.set_state(eps0, np.zeros_like(eps0))
         solve()
         nbytes = 0
@@ -299,9 +314,8 @@ def run_ours(args):
         for i in range(n):
             lm = h.get_landmarks(i)
             nbytes += sum(v.nbytes for v in lm.values())
-        for (r, tt) in host_status:
-            st, cd = h.get_statuses(r, tt)
-            nbytes += st.nbytes + cd.nbytes
+            st, cd = h.get_frame_statuses(i)
+            nbytes += (st.nbytes + cd.nbytes) * (n - 1) // n
         d2h_box[0] = nbytes
 
     e2e_ms = []
@@ -314,21 +328,35 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = units_global * GN_ITERS * args.steps / (float(t.item()) * 1e-3)
 
-    # ---- materialising sweep (K1, reference-surface mode) timed alone with an L2 flush before each launch
-    sweep = None
-    if rank == 0:
-        reset_resident()
-        h.first_estimate()
-        h.profile_enable(True)
+    # ---- materialising sweep (K1, reference-surface mode) timed alone with an L2 flush before each launch --------
+    def time_sweep(hh):
+        hh.first_estimate()
+        hh.profile_enable(True)
         for i in range(3 + 10):
             flush.fill_(1)
             torch.cuda.synchronize()
             if i == 3:
-                h.profile_enable(True)
-            h.evaluate_jacobians(SIGMA, True, True)
-        ms, cnt = h.profile_read()["materialise_sweep"]
-        h.profile_enable(False)
-        sweep = ms / max(cnt, 1)
+                hh.profile_enable(True)
+            hh.evaluate_jacobians(SIGMA, True, True)
+        ms, cnt = hh.profile_read()["materialise_sweep"]
+        hh.profile_enable(False)
+        return ms / max(cnt, 1)
+
+    sweep = sweep4 = None
+    units4 = 0
+    if rank == 0:
+        reset_resident()
+        sweep = time_sweep(h)
+        if world == 1 and not args.no_big_sweep:
+            # configs[3]'s per-GPU shape at G=1 (20000 points/KF, 1.12 M patch-residuals): the size at which the
+            # HBM roofline of the sweep is meaningful; same kernel, same code path
+            from dsopp_b200 import synth
+            win4 = synth.make_window(n_frames=N_FRAMES, points_per_frame=20000, seed=1, ab_scale=0.0)
+            h4 = capi.upload_window(win4, device=local)
+            units4 = win4.units
+            sweep4 = time_sweep(h4)
+            h4.close()
+            del win4
 
     def teardown():
         # the library's NCCL communicator is destroyed by every rank at the same point, while all are alive
@@ -365,7 +393,18 @@ def run_ours(args):
     roofline_sweep = {"kernel": "k_materialise_sweep (K1, reference-surface mode, 595 B/unit)", "bound": "hbm",
                       "achieved": sweep_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                       "frac": sweep_ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": sweep_bytes,
-                      "avg_launch_ms": sweep, "timing": "alone, L2 flushed before each launch, 10 launches"}
+                      "avg_launch_ms": sweep, "timing": "alone, L2 flushed before each launch, 10 launches",
+                      "workload": f"configs[1], {units_local} patch-residuals"}
+    roofline_sweep_big = None
+    if sweep4:
+        b4 = 595 * units4 + img_bytes
+        a4 = b4 / (sweep4 * 1e-3) / 1e9
+        roofline_sweep_big = {"kernel": "k_materialise_sweep (K1, reference-surface mode, 595 B/unit)", "bound": "hbm",
+                              "achieved": a4, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a4 / peaks["hbm_gbs"],
+                              "traffic": None, "algorithmic_bytes_per_launch": b4, "avg_launch_ms": sweep4,
+                              "timing": "alone, L2 flushed before each launch, 10 launches",
+                              "workload": f"configs[3] per-GPU shape at G=1: 8 KF x 20000 points, {units4} patch-residuals",
+                              "patch_residuals_per_s": units4 / (sweep4 * 1e-3)}
     kernel_ms = {k: {"ms_total": v[0], "launches": v[1]} for k, v in prof.items() if v[1]}
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------------------
@@ -403,10 +442,11 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_box[0]),
                 "ms_per_step": sum(e2e_ms) / len(e2e_ms),
-                "path": "dpba_remove_frame/push_frame/set_landmarks/set_statuses/set_state from pinned host buffers, "
+                "path": "dpba_remove_frame/push_frame/set_landmarks/set_frame_statuses/set_state from pinned host buffers, "
                         "dpba_first_estimate + dpba_solve_lm, dpba_get_* readback"},
         "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_sweep": roofline_sweep, "kernel_ms": kernel_ms,
+        "roofline": roofline, "roofline_sweep": roofline_sweep, "roofline_sweep_big": roofline_sweep_big,
+        "kernel_ms": kernel_ms,
         "cpu_baseline": cpu,
         "us_per_gn_iter": 1e3 * total_ms / args.steps / GN_ITERS,
     }
@@ -421,6 +461,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-big-sweep", action="store_true", help="skip the 20000-points/KF materialising-sweep roofline")
     ap.add_argument("--host-lm", action="store_true", help="drive the LM loop from the C++ host adapter instead of dpba_solve_lm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

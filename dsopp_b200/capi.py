@@ -95,6 +95,8 @@ SIGNATURES = {
     "dpba_get_pose_idepth_blocks": (C.c_int, [_P, _I, _I, _P]),
     "dpba_set_statuses": (C.c_int, [_P, _I, _I, _I, _P]),
     "dpba_get_statuses": (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    "dpba_set_frame_statuses": (C.c_int, [_P, _I, _I, _P]),
+    "dpba_get_frame_statuses": (C.c_int, [_P, _I, _I, _P, _P]),
     "dpba_set_state": (C.c_int, [_P, _P, _P]),
     "dpba_get_state": (C.c_int, [_P, _P, _P]),
     "dpba_first_estimate": (C.c_int, [_P]),
@@ -252,6 +254,24 @@ class Handle:
         self._ck(self.lib.dpba_get_statuses(self.h, r, t, n, _ptr(st), _ptr(cand)))
         return st, cand
 
+    def set_frame_statuses(self, r, per_target):
+        """per_target: dict {target slot: uint8[n]} or list indexed by slot (None entries skipped)."""
+        n_fr = self.n_frames
+        items = per_target.items() if isinstance(per_target, dict) else enumerate(per_target)
+        arrs = {t: _u8(a) for t, a in items if a is not None and t != r}
+        n = len(next(iter(arrs.values()))) if arrs else 0
+        ptrs = (C.c_void_p * n_fr)(*[arrs[t].ctypes.data if t in arrs else None for t in range(n_fr)])
+        self._ck(self.lib.dpba_set_frame_statuses(self.h, r, n, C.cast(ptrs, C.c_void_p)))
+
+    def get_frame_statuses(self, r):
+        """-> (statuses, candidates), each uint8 [n_frames][n]; row r is unused (zeros)."""
+        n_fr, n = self.n_frames, self.num_landmarks(r)
+        st, cd = np.zeros((n_fr, n), np.uint8), np.zeros((n_fr, n), np.uint8)
+        ps = (C.c_void_p * n_fr)(*[st[t].ctypes.data if t != r and n else None for t in range(n_fr)])
+        pc = (C.c_void_p * n_fr)(*[cd[t].ctypes.data if t != r and n else None for t in range(n_fr)])
+        self._ck(self.lib.dpba_get_frame_statuses(self.h, r, n, C.cast(ps, C.c_void_p), C.cast(pc, C.c_void_p)))
+        return st, cd
+
     def set_state(self, eps=None, step=None):
         eps, step = _f64(eps), _f64(step)
         self._ck(self.lib.dpba_set_state(self.h, _ptr(eps), _ptr(step)))
@@ -330,7 +350,7 @@ class Handle:
         return r.energy, r.iterations, bool(r.converged), r.number_of_valid_residuals
 
     PROFILE_KINDS = ("linearize_fused", "schur", "residual_sweep", "materialise_sweep", "assemble", "back_substitute",
-                     "pair_setup", "lm_step")
+                     "pair_setup", "lm_step", "core_reduce", "assemble_blocks", "schur_reduce", "lm_control")
 
     def set_option(self, name, value):
         self._ck(self.lib.dpba_set_option(self.h, name.encode(), int(value)))
@@ -339,7 +359,7 @@ class Handle:
         self._ck(self.lib.dpba_profile_enable(self.h, int(on)))
 
     def profile_read(self):
-        ms, n = np.zeros(8), np.zeros(8, np.int32)
+        ms, n = np.zeros(len(self.PROFILE_KINDS)), np.zeros(len(self.PROFILE_KINDS), np.int32)
         self._ck(self.lib.dpba_profile_read(self.h, _ptr(ms), _ptr(n)))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 

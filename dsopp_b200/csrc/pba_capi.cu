@@ -65,6 +65,9 @@ struct FrameHost {
 struct dpba_handle {
   dpba_config cfg;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // side branch of the LM launch sequence (fork/join inside the graph)
+  std::vector<cudaEvent_t> fork_ev;          // dependency-only events of the fork/join edges
+  size_t fork_used = 0;
   std::string err = "";
   int n_frames = 0;
   FrameHost fr[PBA_MAXF];
@@ -74,7 +77,10 @@ struct dpba_handle {
   // landmark arrays
   float4* lmk = nullptr;  // {u, v, idepth, idepth at the FEJ linearisation point}
   float *idepth_step = nullptr, *patch = nullptr;
-  std::vector<float4> lmk_stage;
+  // pinned staging arena for the small host arrays (landmarks, statuses): the caller's buffer is copied here and
+  // DMA'd asynchronously, so set_* calls return without a stream synchronisation and the caller may reuse its buffer
+  char* arena_h = nullptr;
+  size_t arena_cap = 0, arena_used = 0;
   uint8_t* flags = nullptr;
   float *inv_hdd = nullptr, *b_d = nullptr, *hpd = nullptr, *rel_baseline = nullptr;
   uint32_t* n_inliers = nullptr;
@@ -153,6 +159,20 @@ int fail(dpba_handle* h, int code, const std::string& msg) {
   return code;
 }
 
+// bump allocation out of the pinned arena; when it is full the stream is drained first (every DMA that reads the
+// arena has then completed) and allocation restarts at the bottom
+void* arena_alloc(dpba_handle* h, size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes > h->arena_cap) return nullptr;
+  if (h->arena_used + bytes > h->arena_cap) {
+    cudaStreamSynchronize(h->stream);
+    h->arena_used = 0;
+  }
+  void* p = h->arena_h + h->arena_used;
+  h->arena_used += bytes;
+  return p;
+}
+
 #define CK(expr)                                                                                     \
   do {                                                                                               \
     cudaError_t e_ = (expr);                                                                         \
@@ -168,8 +188,9 @@ int fail(dpba_handle* h, int code, const std::string& msg) {
 // RAII scope that brackets one kernel launch with events on the handle's stream when profiling is on
 struct ProfScope {
   dpba_handle* h;
+  cudaStream_t st;
   size_t idx = (size_t)-1;
-  ProfScope(dpba_handle* h_, int kind) : h(h_) {
+  ProfScope(dpba_handle* h_, int kind, cudaStream_t st_ = nullptr) : h(h_), st(st_ ? st_ : h_->stream) {
     if (!h->profiling) return;
     if (h->ev_used * 2 + 2 > h->ev_pool.size()) {
       cudaEvent_t a, b;
@@ -188,12 +209,25 @@ struct ProfScope {
   // inside stream capture a timing event must become an event-record NODE (cudaEventRecordExternal); a plain
   // cudaEventRecord would only express a dependency and never be stamped when the graph runs
   void record(cudaEvent_t e) {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(h->stream, &st);
-    if (st == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(e, h->stream, cudaEventRecordExternal);
-    else cudaEventRecord(e, h->stream);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(e, st, cudaEventRecordExternal);
+    else cudaEventRecord(e, st);
   }
 };
+
+// edge `from` -> `to` between the handle's two streams (a graph dependency under capture, a real wait otherwise)
+int stream_edge(dpba_handle* h, cudaStream_t from, cudaStream_t to) {
+  if (h->fork_used == h->fork_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(h, DPBA_E_CUDA, "cudaEventCreate");
+    h->fork_ev.push_back(e);
+  }
+  cudaEvent_t e = h->fork_ev[h->fork_used++];
+  if (cudaEventRecord(e, from) != cudaSuccess || cudaStreamWaitEvent(to, e, 0) != cudaSuccess)
+    return fail(h, DPBA_E_CUDA, "stream fork/join failed");
+  return 0;
+}
 
 void profile_collect(dpba_handle* h) {
   if (!h->ev_used) return;
@@ -407,20 +441,24 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
   CK(cudaGetLastError());
   if (mask) CK(cudaMemcpyAsync(h->mask[phys], mask, npx, cudaMemcpyHostToDevice, h->stream));
   else CK(cudaMemsetAsync(h->mask[phys], 255, npx, h->stream));
-  // new residual vectors of this frame start as kOk until dpba_set_statuses says otherwise
+  // new residual vectors of this frame start as kOk until dpba_set_statuses says otherwise: the rows (phys -> p) are
+  // contiguous, the rows (p -> phys) are one strided 2-D memset per array
   const size_t mp = h->cfg.max_points_per_frame;
-  for (int p = 0; p < h->cfg.max_frames; ++p) {
-    const size_t a = ((size_t)(phys * PBA_MAXF + p)) * mp, b = ((size_t)(p * PBA_MAXF + phys)) * mp;
-    CK(cudaMemsetAsync(h->status + a, 0, mp, h->stream));
-    CK(cudaMemsetAsync(h->cand + a, 0, mp, h->stream));
-    CK(cudaMemsetAsync(h->jac_valid + a, 0, mp, h->stream));
-    CK(cudaMemsetAsync(h->jac_valid + b, 0, mp, h->stream));
-    CK(cudaMemsetAsync(h->energy + a, 0, mp * sizeof(float), h->stream));
-    CK(cudaMemsetAsync(h->status + b, 0, mp, h->stream));
-    CK(cudaMemsetAsync(h->cand + b, 0, mp, h->stream));
-    CK(cudaMemsetAsync(h->energy + b, 0, mp * sizeof(float), h->stream));
+  const size_t nf = (size_t)h->cfg.max_frames;
+  {
+    const size_t a = (size_t)phys * PBA_MAXF * mp, b = (size_t)phys * mp, pitch = (size_t)PBA_MAXF * mp;
+    CK(cudaMemsetAsync(h->status + a, 0, nf * mp, h->stream));
+    CK(cudaMemsetAsync(h->cand + a, 0, nf * mp, h->stream));
+    CK(cudaMemsetAsync(h->jac_valid + a, 0, nf * mp, h->stream));
+    CK(cudaMemsetAsync(h->energy + a, 0, nf * mp * sizeof(float), h->stream));
+    CK(cudaMemset2DAsync(h->status + b, pitch, 0, mp, nf, h->stream));
+    CK(cudaMemset2DAsync(h->cand + b, pitch, 0, mp, nf, h->stream));
+    CK(cudaMemset2DAsync(h->jac_valid + b, pitch, 0, mp, nf, h->stream));
+    CK(cudaMemset2DAsync(h->energy + b, pitch * sizeof(float), 0, mp * sizeof(float), nf, h->stream));
   }
-  CK(cudaStreamSynchronize(h->stream));  // stage_h is reused by the next push
+  // pageable images went through stage_h, which the next push reuses; page-locked images are BORROWED until the next
+  // synchronising call (solve / get_*), exactly as LocalFrame borrows its PixelMap pointers (local_frame.hpp:44,325)
+  if (!pinned) CK(cudaStreamSynchronize(h->stream));
   FrameHost& F = h->fr[h->n_frames];
   F = FrameHost();
   F.id = frame_id;
@@ -442,18 +480,25 @@ int upload_landmarks(dpba_handle* h, int slot, int first, int n, const float* uv
                      const float* patch, const uint8_t* flags) {
   const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame + first;
   if (n == 0) return 0;
-  h->lmk_stage.resize(n);
-  for (int l = 0; l < n; ++l) h->lmk_stage[l] = make_float4(uv[2 * l], uv[2 * l + 1], idepth[l], idepth[l]);
-  CK(cudaMemcpyAsync(h->lmk + base, h->lmk_stage.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->patch + base * 8, patch, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, h->stream));
-  if (flags) CK(cudaMemcpyAsync(h->flags + base, flags, n, cudaMemcpyHostToDevice, h->stream));
-  else CK(cudaMemsetAsync(h->flags + base, 0, n, h->stream));
+  float4* lk = (float4*)arena_alloc(h, sizeof(float4) * n);
+  float* pt = (float*)arena_alloc(h, sizeof(float) * 8 * n);
+  uint8_t* fl = flags ? (uint8_t*)arena_alloc(h, n) : nullptr;
+  if (!lk || !pt || (flags && !fl)) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+  for (int l = 0; l < n; ++l) lk[l] = make_float4(uv[2 * l], uv[2 * l + 1], idepth[l], idepth[l]);
+  memcpy(pt, patch, sizeof(float) * 8 * n);
+  CK(cudaMemcpyAsync(h->lmk + base, lk, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->patch + base * 8, pt, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, h->stream));
+  if (flags) {
+    memcpy(fl, flags, n);
+    CK(cudaMemcpyAsync(h->flags + base, fl, n, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CK(cudaMemsetAsync(h->flags + base, 0, n, h->stream));
+  }
   CK(cudaMemsetAsync(h->idepth_step + base, 0, sizeof(float) * n, h->stream));
   CK(cudaMemsetAsync(h->inv_hdd + base, 0, sizeof(float) * n, h->stream));
   CK(cudaMemsetAsync(h->b_d + base, 0, sizeof(float) * n, h->stream));
   CK(cudaMemsetAsync(h->rel_baseline + base, 0, sizeof(float) * n, h->stream));
   CK(cudaMemsetAsync(h->n_inliers + base, 0, sizeof(uint32_t) * n, h->stream));
-  CK(cudaStreamSynchronize(h->stream));  // the caller keeps ownership of its (possibly pageable) buffers
   return 0;
 }
 
@@ -495,6 +540,7 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   } while (0)
   CKC(cudaSetDevice(cfg->device));
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   const size_t npx = (size_t)cfg->width * cfg->height;
   const size_t mp = cfg->max_points_per_frame;
   const size_t nlm = (size_t)cfg->max_frames * mp;
@@ -560,6 +606,9 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   CKC(cudaMalloc(&h->pair_dist, PBA_MAXF * PBA_MAXF * sizeof(float)));
   CKC(cudaMalloc(&h->stage, npx * 3 * sizeof(float)));
   CKC(cudaMallocHost(&h->stage_h, npx * 3 * sizeof(float)));
+  // one window's worth of landmark records (52 B each, 256 B aligned per array) and status rows, twice
+  h->arena_cap = 2 * ((size_t)cfg->max_frames * (mp * 64 + 1024) + (size_t)cfg->max_frames * cfg->max_frames * (mp + 256));
+  CKC(cudaMallocHost(&h->arena_h, h->arena_cap));
 #undef CKC
   *out = h;
   return DPBA_SUCCESS;
@@ -571,6 +620,8 @@ int dpba_destroy(dpba_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) nccl_api().CommDestroy(h->comm);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->fork_ev) cudaEventDestroy(e);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   for (int p = 0; p < PBA_MAXF; ++p) {
     cudaFree(h->img[p]);
     cudaFree(h->mask[p]);
@@ -585,6 +636,7 @@ int dpba_destroy(dpba_handle* h) {
   cudaFreeHost(h->fparams_h);
   cudaFreeHost(h->red_h);
   cudaFreeHost(h->stage_h);
+  cudaFreeHost(h->arena_h);
   cudaFreeHost(h->ctl_h);
   cudaFreeHost(h->lmopt_h);
   cudaFreeHost(h->marg_h);
@@ -668,8 +720,12 @@ int dpba_set_landmark_flags(dpba_handle* h, int32_t slot, int32_t n, const uint8
   REQUIRE(slot >= 0 && slot < h->n_frames && flags, "bad argument");
   REQUIRE(n == h->fr[slot].n_lm, "flag count must equal the landmark count");
   const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame;
-  if (n) CK(cudaMemcpyAsync(h->flags + base, flags, n, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  if (n) {
+    uint8_t* st = (uint8_t*)arena_alloc(h, n);
+    if (!st) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+    memcpy(st, flags, n);
+    CK(cudaMemcpyAsync(h->flags + base, st, n, cudaMemcpyHostToDevice, h->stream));
+  }
   return DPBA_SUCCESS;
 }
 
@@ -712,14 +768,45 @@ int dpba_get_pose_idepth_blocks(dpba_handle* h, int32_t slot, int32_t n, float* 
   return DPBA_SUCCESS;
 }
 
+static int set_statuses_row(dpba_handle* h, int r, int t, int n, const uint8_t* st) {
+  const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
+  if (!n) return 0;
+  uint8_t* stg = (uint8_t*)arena_alloc(h, n);
+  if (!stg) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+  memcpy(stg, st, n);
+  CK(cudaMemcpyAsync(h->status + base, stg, n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->cand + base, stg, n, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
 int dpba_set_statuses(dpba_handle* h, int32_t r, int32_t t, int32_t n, const uint8_t* st) {
   REQUIRE(h, "null handle");
   REQUIRE(r >= 0 && r < h->n_frames && t >= 0 && t < h->n_frames && r != t && st, "bad pair");
   REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
-  const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
-  if (n) {
-    CK(cudaMemcpyAsync(h->status + base, st, n, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->cand + base, st, n, cudaMemcpyHostToDevice, h->stream));
+  return set_statuses_row(h, r, t, n, st);
+}
+
+int dpba_set_frame_statuses(dpba_handle* h, int32_t r, int32_t n, const uint8_t* const* per_target) {
+  REQUIRE(h, "null handle");
+  REQUIRE(r >= 0 && r < h->n_frames && per_target, "bad argument");
+  REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
+  for (int t = 0; t < h->n_frames; ++t) {
+    if (t == r || !per_target[t]) continue;
+    const int rc = set_statuses_row(h, r, t, n, per_target[t]);
+    if (rc) return rc;
+  }
+  return DPBA_SUCCESS;
+}
+
+int dpba_get_frame_statuses(dpba_handle* h, int32_t r, int32_t n, uint8_t* const* statuses, uint8_t* const* candidates) {
+  REQUIRE(h, "null handle");
+  REQUIRE(r >= 0 && r < h->n_frames, "bad argument");
+  REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
+  for (int t = 0; t < h->n_frames && n; ++t) {
+    if (t == r) continue;
+    const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
+    if (statuses && statuses[t]) CK(cudaMemcpyAsync(statuses[t], h->status + base, n, cudaMemcpyDeviceToHost, h->stream));
+    if (candidates && candidates[t]) CK(cudaMemcpyAsync(candidates[t], h->cand + base, n, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
   return DPBA_SUCCESS;
@@ -1050,7 +1137,12 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
     pba::launch_pair_setup(h->fparams, N, h->pairs, h->pasm, s);
   };
 
-  pba::launch_lm_init(h->ctl, h->lmopt, s);
+  cudaStream_t s2 = h->stream2;
+  h->fork_used = 0;
+  {
+    ProfScope ps(h, 11);
+    pba::launch_lm_init(h->ctl, h->lmopt, s);
+  }
   pairs();
   // residual-only sweep + calculateEnergy tail.  Single GPU: k_lm_energy sums the per-CTA partials itself; with
   // several ranks the partials are summed first so that the 8 scalars can cross NVLink before the decision.
@@ -1065,9 +1157,12 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
       pba::launch_reduce_scal(h->ctl, ctl_mode, rb.e_part, n_e, n_norm_parts ? rb.n_part : nullptr, n_norm_parts, rb.scal, s);
       const int rc2 = exchange(h, EX_SCAL);
       if (rc2) return rc2;
-      if (kind != pba::LM_ENERGY_FINAL)
+      if (kind != pba::LM_ENERGY_FINAL) {
+        ProfScope ps(h, 11);
         pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, ro.scal, Hm, bm, kind, s);
+      }
     } else if (kind != pba::LM_ENERGY_FINAL) {
+      ProfScope ps(h, 11);
       pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, rb.scal, Hm, bm, kind, s, rb.e_part, n_e,
                             n_norm_parts ? rb.n_part : nullptr, n_norm_parts);
     }
@@ -1090,27 +1185,46 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
       ProfScope ps(h, 0);
       shape = pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl);
     }
+    // the two second-stage reductions are independent: H_pp / b_p (core reduce -> block assembly) on the main
+    // branch, the Schur partial sum on the side branch
+    if ((rc = stream_edge(h, s, s2))) return rc;
     {
-      ProfScope ps(h, 4);
-      pba::launch_assemble(w, fej, rb, shape, s, h->ctl);
-      pba::launch_finish_fused(w, rb, shape, s, h->ctl);
+      ProfScope ps(h, 10, s2);
+      pba::launch_finish_fused(w, rb, shape, s2, h->ctl);
     }
+    {
+      ProfScope ps(h, 8);
+      pba::launch_core_reduce(w, rb, shape, s, h->ctl);
+    }
+    {
+      ProfScope ps(h, 9);
+      pba::launch_assemble_blocks(w, fej, rb, shape, s, h->ctl);
+    }
+    if ((rc = stream_edge(h, s2, s))) return rc;
     if ((rc = exchange(h, EX_SYSTEM))) return rc;
     // calculateStep(lambda)
     {
       ProfScope ps(h, 7);
       pba::launch_lm_step(h->ctl, h->lmopt, h->fparams, h->fixed_dev, N, ro, Hm, bm, h->step_dev, s);
     }
+    // back-substitution (landmarks) and the per-pair constants of the trial state (frames) are independent
+    if ((rc = stream_edge(h, s, s2))) return rc;
+    {
+      ProfScope ps(h, 6, s2);
+      pba::launch_pair_setup(h->fparams, N, h->pairs, h->pasm, s2);
+    }
     {
       ProfScope ps(h, 5);
       pba::launch_back_substitute(w, h->step_dev, 0.0, s, h->ctl, rb.n_part);
     }
+    if ((rc = stream_edge(h, s2, s))) return rc;
     // calculateEnergy() at state + step
-    pairs();
     if ((rc = energy_eval(1, n_norm_parts, pba::LM_ENERGY_TRIAL))) return rc;
     // acceptStep() / rejectStep() incl. changeResidualStatuses
-    pba::launch_accept(w, 0, nullptr, s, h->ctl, 1);
-    pba::launch_lm_finish(h->ctl, h->lmopt, h->fparams, N, s);
+    {
+      ProfScope ps(h, 11);
+      pba::launch_accept(w, 0, nullptr, s, h->ctl, 1);
+    }
   }
   // the trailing problem.calculateEnergy() of both exits (lm.hpp:119,126)
   pairs();
@@ -1236,6 +1350,7 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
   return fail(h, DPBA_E_INVALID, std::string("unknown option ") + name);
 }
 
+void dpba_debug_lm_clocks(long long* out) { pba::read_lm_clocks(out); }
 int64_t dpba_launch_count(void) { return (int64_t)pba::launch_count(); }
 
 int dpba_profile_enable(dpba_handle* h, int32_t on) {

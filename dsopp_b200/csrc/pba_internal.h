@@ -115,6 +115,7 @@ struct LmCtl {
   double state_sq, step_sq;
   int n_valid, next_n;
   int converged, done, system_valid, accept, iteration, iterations_executed;
+  int apply;  // the last trial-energy kernel ran: k_accept_landmarks must apply ctl->accept
 };
 
 namespace pba {
@@ -122,12 +123,11 @@ namespace pba {
 enum { LM_ENERGY_INITIAL = 0, LM_ENERGY_TRIAL = 1, LM_ENERGY_FINAL = 2 };
 void launch_lm_init(LmCtl* ctl, const LmOptionsDev* opt, cudaStream_t s);
 void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s);
-void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr, int N, double* scal,
+void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, double* scal,
                       const double* Hmarg, const double* bmarg, int kind, cudaStream_t s, const double* e_part = nullptr,
                       int n_e = 0, const double* n_part = nullptr, int n_n = 0);
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
                     const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s);
-void launch_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, cudaStream_t s);
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
 void launch_pack_image(const float* src3, float4* dst, int n_px, cudaStream_t s);
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s);
@@ -142,6 +142,9 @@ void launch_linearize_from_materialized(const WindowDev& w, int for_marg, Reduce
 int launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,
                      const LmCtl* ctl = nullptr);
+void launch_core_reduce(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl = nullptr);
+void launch_assemble_blocks(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,
+                            const LmCtl* ctl = nullptr);
 void launch_finish_system(int D, ReduceBuf rb, int nsb, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_finish_fused(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, double lambda, cudaStream_t s,
@@ -153,6 +156,7 @@ void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cud
 void launch_first_estimate(const WindowDev& w, cudaStream_t s);  // K6: idepth snapshot + reprojection_jacobians_valid
 void launch_apply_point_statuses(const WindowDev& w, float threshold, int min_valid, const float* pair_dist,
                                  cudaStream_t s);
+void read_lm_clocks(long long* out);
 int sm_count();
 long long launch_count();
 void add_launches(long long n);

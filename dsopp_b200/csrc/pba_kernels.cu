@@ -1174,10 +1174,15 @@ __device__ __forceinline__ double bm_at(const PairAssemble& pa, int fej, int i, 
   return 0.0;
 }
 
-__global__ void __launch_bounds__(64) k_assemble(const __grid_constant__ WindowDev w, int fej,
-                                                 const double* __restrict__ core, double* __restrict__ Hp,
-                                                 double* __restrict__ bp, const LmCtl* __restrict__ ctl) {
+// One warp per contributing ordered pair: all its loads (core from L2, B from the pair table) are issued at once and
+// the two 8x8x8 fp64 products run warp-locally (lane = row i, two columns); the warps' terms meet in shared memory.
+// A serial loop over the targets costs one L2 round trip and four barriers per target instead.
+constexpr int ASM_W = 264;  // doubles of shared memory per warp: C, B, T1, out (64 each) + b (8)
+__global__ void __launch_bounds__(512) k_assemble(const __grid_constant__ WindowDev w, int fej,
+                                                  const double* __restrict__ core, double* __restrict__ Hp,
+                                                  double* __restrict__ bp, const LmCtl* __restrict__ ctl) {
   if (lm_skip(ctl, 2)) return;
+  extern __shared__ double asm_sm[];
   const int N = w.n_frames, D = 8 * N;
   // blockIdx.x enumerates the upper-triangular block pairs (bi <= bj)
   int bi = 0, rem = blockIdx.x;
@@ -1186,57 +1191,80 @@ __global__ void __launch_bounds__(64) k_assemble(const __grid_constant__ WindowD
     ++bi;
   }
   const int bj = bi + rem;
-  const int i = threadIdx.x >> 3, j = threadIdx.x & 7;
-  __shared__ double C[8][8], Bm[8][8], T1[8][8], out[8][8];
-  if (bi != bj) {
-    double acc = 0;
-    for (int side = 0; side < 2; ++side) {
-      const int r = side ? bj : bi, t = side ? bi : bj;  // ordered pair r -> t contributes H_rt = -B^T C to block (r, t)
-      const double* c = core + (size_t)(r * PBA_MAXF + t) * PBA_CORE;
-      const PairAssemble& pa = w.pairs_asm[r * PBA_MAXF + t];
-      __syncthreads();
-      C[i][j] = core_at(c, i, j);
-      Bm[i][j] = bm_at(pa, fej, i, j);
-      __syncthreads();
-      double s = 0;
-      for (int k = 0; k < 8; ++k) s += Bm[k][i] * C[k][j];  // (B^T C)[i][j]
-      T1[i][j] = -s;
-      __syncthreads();
-      acc += side ? T1[j][i] : T1[i][j];  // block (bi,bj) += H_rt(bi->bj) + H_rt(bj->bi)^T
-    }
-    Hp[(size_t)(8 * bi + i) * D + 8 * bj + j] = acc;
-    Hp[(size_t)(8 * bj + j) * D + 8 * bi + i] = acc;
-    return;
-  }
-  // diagonal block r = bi, and b[r]
-  const int r = bi;
-  double acc = 0, bacc = 0;
-  for (int t = 0; t < N; ++t) {
-    if (t == r) continue;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = lane >> 2, j0 = (lane & 3) * 2;
+  double* Cw = asm_sm + warp * ASM_W;
+  double* Bw = Cw + 64;
+  double* Tw = Bw + 64;
+  double* Ow = Tw + 64;
+  double* bw = Ow + 64;
+  const bool diag = bi == bj;
+  const int nterms = diag ? N - 1 : 2;
+  if (warp < nterms) {
+    // diagonal block r: term t gives B_rt^T C_rt B_rt + C_tr.  Off-diagonal block (bi, bj): the ordered pair r -> t
+    // contributes H_rt = -B^T C to block (r, t); side 1 is transposed when the terms are added.
+    const int r = diag ? bi : (warp ? bj : bi);
+    const int t = diag ? warp + (warp >= bi) : (warp ? bi : bj);
     const double* c_rt = core + (size_t)(r * PBA_MAXF + t) * PBA_CORE;
     const double* c_tr = core + (size_t)(t * PBA_MAXF + r) * PBA_CORE;
     const PairAssemble& pa = w.pairs_asm[r * PBA_MAXF + t];
-    __syncthreads();
-    C[i][j] = core_at(c_rt, i, j);
-    Bm[i][j] = bm_at(pa, fej, i, j);
-    __syncthreads();
-    double s = 0;
-    for (int k = 0; k < 8; ++k) s += Bm[k][i] * C[k][j];
-    T1[i][j] = s;  // B^T C
-    __syncthreads();
-    double hrr = 0;
-    for (int k = 0; k < 8; ++k) hrr += T1[i][k] * Bm[k][j];  // B^T C B
-    acc += hrr + core_at(c_tr, i, j);                          // + H_tt of the pair t -> r
-    if (j == 0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      Cw[i * 8 + j0 + q] = core_at(c_rt, i, j0 + q);
+      Bw[i * 8 + j0 + q] = bm_at(pa, fej, i, j0 + q);
+    }
+    const double ctr0 = diag ? core_at(c_tr, i, j0) : 0.0, ctr1 = diag ? core_at(c_tr, i, j0 + 1) : 0.0;
+    const double q_rt = (diag && lane < 8) ? c_rt[36 + lane] : 0.0, q_tr = (diag && lane < 8) ? c_tr[36 + lane] : 0.0;
+    if (diag && lane < 8) bw[lane] = q_rt;  // staged for the B^T q product below
+    __syncwarp();
+    double s0 = 0, s1 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {  // (B^T C)[i][j]
+      s0 += Bw[k * 8 + i] * Cw[k * 8 + j0];
+      s1 += Bw[k * 8 + i] * Cw[k * 8 + j0 + 1];
+    }
+    if (!diag) {
+      Ow[i * 8 + j0] = -s0;
+      Ow[i * 8 + j0 + 1] = -s1;
+    } else {
+      Tw[i * 8 + j0] = s0;
+      Tw[i * 8 + j0 + 1] = s1;
       double br = 0;
-      for (int k = 0; k < 8; ++k) br += Bm[k][i] * c_rt[36 + k];  // B^T q_rt
-      bacc += br - c_tr[36 + i];                                    // b_t of the pair t -> r is -q_tr
+      if (lane < 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) br += Bw[k * 8 + lane] * bw[k];  // B^T q_rt
+      }
+      __syncwarp();
+      double h0 = ctr0, h1 = ctr1;  // + H_tt of the pair t -> r
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {  // B^T C B
+        h0 += Tw[i * 8 + k] * Bw[k * 8 + j0];
+        h1 += Tw[i * 8 + k] * Bw[k * 8 + j0 + 1];
+      }
+      Ow[i * 8 + j0] = h0;
+      Ow[i * 8 + j0 + 1] = h1;
+      if (lane < 8) bw[lane] = br - q_tr;  // b_t of the pair t -> r is -q_tr
     }
   }
-  out[i][j] = acc;
   __syncthreads();
-  Hp[(size_t)(8 * r + i) * D + 8 * r + j] = i >= j ? out[i][j] : out[j][i];  // selfadjointView<Lower>
-  if (j == 0) bp[8 * r + i] = bacc;
+  for (int o = threadIdx.x; o < 64; o += blockDim.x) {
+    const int oi = o >> 3, oj = o & 7;
+    if (!diag) {
+      const double acc = asm_sm[oi * 8 + oj + 192] + asm_sm[ASM_W + oj * 8 + oi + 192];
+      Hp[(size_t)(8 * bi + oi) * D + 8 * bj + oj] = acc;
+      Hp[(size_t)(8 * bj + oj) * D + 8 * bi + oi] = acc;
+    } else {
+      const int ii = max(oi, oj), jj = min(oi, oj);  // selfadjointView<Lower>
+      double acc = 0;
+      for (int wi = 0; wi < nterms; ++wi) acc += asm_sm[wi * ASM_W + 192 + ii * 8 + jj];
+      Hp[(size_t)(8 * bi + oi) * D + 8 * bi + oj] = acc;
+      if (oj == 0) {
+        double bacc = 0;
+        for (int wi = 0; wi < nterms; ++wi) bacc += asm_sm[wi * ASM_W + 256 + oi];
+        bp[8 * bi + oi] = bacc;
+      }
+    }
+  }
 }
 
 // second stage of the fused path's Schur reduction: out[o] = sum over the chunk CTAs of part[cta][o], o over the
@@ -1250,20 +1278,33 @@ __global__ void __launch_bounds__(1024) k_finish_fused(const __grid_constant__ W
   const int T4 = D / 4, ntri = T4 * (T4 + 1) / 2, nout = ntri * 16 + D;
   const int g = threadIdx.x >> 5, oo = threadIdx.x & 31;  // 32 groups stride over the chunk CTAs, 32 outputs per CTA
   const int o = blockIdx.x * 32 + oo;
+  // rows of `part` = (host frame, chunk CTA) flattened: q = f * chunks + c; every thread keeps four independent loads
+  // in flight (CTAs past a frame's last landmark never ran: their rows are skipped)
+  __shared__ int s_nch[PBA_MAXF];
+  if (threadIdx.x < PBA_MAXF) s_nch[threadIdx.x] = threadIdx.x < N ? (w.n_lm[threadIdx.x] + lpb - 1) / lpb : 0;
+  __syncthreads();
   double acc = 0;
   if (o < nout) {
-    for (int f = 0; f < N; ++f) {
-      const int nch = (w.n_lm[f] + lpb - 1) / lpb;  // CTAs past the last landmark never ran
-      const float* p = part + (size_t)f * chunks * nout + o;
-      float a0 = 0.f, a1 = 0.f;
-      int c = g;
-      for (; c + 32 < nch; c += 64) {
-        a0 += p[(size_t)c * nout];
-        a1 += p[(size_t)(c + 32) * nout];
+    const int rows = N * chunks;
+    const float* p = part + o;
+    auto P = [&](int q) -> float {
+      const int f = q / chunks;
+      return (q - f * chunks) < s_nch[f] ? p[(size_t)q * nout] : 0.f;
+    };
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int q = g;
+    for (; q + 96 < rows; q += 128) {
+      a0 += P(q);
+      a1 += P(q + 32);
+      a2 += P(q + 64);
+      a3 += P(q + 96);
+      if (((q - g) & 511) == 384) {  // bound the fp32 partial sums: flush to fp64 every 16 rows
+        acc += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+        a0 = a1 = a2 = a3 = 0.f;
       }
-      if (c < nch) a0 += p[(size_t)c * nout];
-      acc += (double)a0 + (double)a1;
     }
+    for (; q < rows; q += 32) a0 += P(q);
+    acc += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
   }
   red[g][oo] = acc;
   __syncthreads();
@@ -1385,8 +1426,10 @@ __global__ void __launch_bounds__(256) k_back_substitute(const __grid_constant__
 __global__ void __launch_bounds__(256) k_accept_landmarks(const __grid_constant__ WindowDev w, int accept,
                                                           double* __restrict__ scal, const LmCtl* __restrict__ ctl,
                                                           int with_statuses) {
-  if (lm_skip(ctl, 1)) return;
-  if (ctl) accept = ctl->accept;
+  if (ctl) {  // device LM: k_lm_energy decided (and already closed the iteration's bookkeeping)
+    if (!ctl->apply) return;
+    accept = ctl->accept;
+  }
   const int f = blockIdx.y;
   const int M = w.n_lm[f];
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1725,6 +1768,7 @@ __global__ void k_lm_init(LmCtl* ctl, const LmOptionsDev* opt) {
   ctl->done = 0;
   ctl->system_valid = 0;
   ctl->accept = 0;
+  ctl->apply = 0;
   ctl->iteration = 0;
   ctl->iterations_executed = 0;
 }
@@ -1735,47 +1779,60 @@ __global__ void k_lm_zero(const LmCtl* ctl, double* p, int n, int mode) {
   if (i < n) p[i] = 0.0;
 }
 
-// calculateEnergy() tail (problem.hpp:293-316) + the accept decision (levenberg_marquardt_algorithm.hpp:95-104)
-__global__ void __launch_bounds__(128) k_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr,
+// calculateEnergy() tail (problem.hpp:293-316), the accept decision (levenberg_marquardt_algorithm.hpp:95-104) and,
+// for a trial energy, acceptStep / rejectStep of the frame state plus the loop bookkeeping (problem.hpp:366-402,
+// lm.hpp:104-122) -- one single-CTA kernel per energy evaluation.  k_accept_landmarks runs right after it and applies
+// the decision to the landmarks when ctl->apply is set.
+__device__ __forceinline__ double block_sum_256(double v, double* red /*[8]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  __syncthreads();  // red may still be read from the previous call
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += red[k];
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
                                                    int N, double* scal, const double* Hmarg,
                                                    const double* bmarg, int kind, const double2* __restrict__ e_part,
                                                    int n_e, const double2* __restrict__ n_part, int n_n) {
-  if (kind == pba::LM_ENERGY_TRIAL && ctl->done) return;
+  if (kind == pba::LM_ENERGY_TRIAL && ctl->done) {
+    if (threadIdx.x == 0) ctl->apply = 0;
+    return;
+  }
   __shared__ double s[PBA_MAXF * 8];
-  __shared__ double red[128];
-  __shared__ double r4[4][128];
+  __shared__ double red[8];
+  __shared__ int s_accept;
   const int D = 8 * N, i = threadIdx.x;
   if (e_part) {  // single-GPU: the second stage of the (energy, n) / norm reductions happens here, no extra launch
     double a = 0, b = 0, c = 0, d = 0;
-    for (int k = i; k < n_e; k += 128) {
+    for (int k = i; k < n_e; k += 256) {
       const double2 v = e_part[k];
       a += v.x;
       b += v.y;
     }
-    for (int k = i; k < n_n; k += 128) {
+    for (int k = i; k < n_n; k += 256) {
       const double2 v = n_part[k];
       c += v.x;
       d += v.y;
     }
-    r4[0][i] = a;
-    r4[1][i] = b;
-    r4[2][i] = c;
-    r4[3][i] = d;
-    __syncthreads();
-    for (int st = 64; st > 0; st >>= 1) {
-      if (i < st)
-        for (int q = 0; q < 4; ++q) r4[q][i] += r4[q][i + st];
-      __syncthreads();
+    a = block_sum_256(a, red);
+    b = block_sum_256(b, red);
+    if (n_part) {
+      c = block_sum_256(c, red);
+      d = block_sum_256(d, red);
     }
     if (i == 0) {
-      scal[0] = r4[0][0];
-      scal[1] = r4[1][0];
+      scal[0] = a;
+      scal[1] = b;
       if (n_part) {
-        scal[2] = r4[2][0];
-        scal[3] = r4[3][0];
+        scal[2] = c;
+        scal[3] = d;
       }
     }
-    __syncthreads();
   }
   if (i < D) s[i] = fr[i / 8].eps[i % 8] + fr[i / 8].step[i % 8];
   __syncthreads();
@@ -1792,201 +1849,52 @@ __global__ void __launch_bounds__(128) k_lm_energy(LmCtl* ctl, const LmOptionsDe
       acc += 0.5 * ab * opt->ab_reg[k - 6] * ab;
     }
   }
-  red[i] = acc;
-  __syncthreads();
-  for (int st = 64; st > 0; st >>= 1) {
-    if (i < st) red[i] += red[i + st];
-    __syncthreads();
-  }
-  if (i) return;
-  const double E = opt->energy_marg + red[0] + scal[0];
-  const int n = (int)llrint(scal[1]);
-  if (kind == pba::LM_ENERGY_INITIAL) {
-    ctl->energy = E;
-    ctl->n_valid = n;
-    if (n <= 0 || opt->max_it <= 0) ctl->done = 1;
-  } else if (kind == pba::LM_ENERGY_TRIAL) {
-    ctl->next_energy = E;
-    ctl->next_n = n;
-    ctl->iterations_executed += 1;
-    // landmark parts of the norms, accumulated by k_back_substitute (problem.hpp:377-382)
-    ctl->state_sq = scal[2];
-    ctl->step_sq = scal[3];
-    if (n == 0) {
-      ctl->accept = -1;  // rejectStep(); break
-    } else {
-      if (fabs(ctl->energy - E) / ctl->energy < opt->ftol) ctl->converged = 1;  // before the accept test (Q7)
-      ctl->accept = (E < ctl->energy || (opt->force_accept && ctl->iteration < opt->min_it)) ? 1 : 0;
-    }
-  }
-}
-
-// calculateStep (problem.hpp:342-357): priors (problem.hpp:37-77), full system, Jacobi preconditioner + LDL^T
-// (normal_linear_system.cpp:10-59), all fp64 in one CTA of 16x16 threads.  The (padded) matrix lives in REGISTERS:
-// thread (ty,tx) owns A[ty+16a][tx+16b], a,b < T (T = 4 for 8N <= 64, 8 for 8N <= 128).  Step k broadcasts column k
-// through a double-buffered shared vector, so the factorisation costs one barrier per column; L is collected in
-// shared memory for the warp-level back substitution.
-template <int T>
-__global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
-                                                 const int* fixed, int N, const double* __restrict__ Hp,
-                                                 const double* __restrict__ bp, const double* __restrict__ Hs,
-                                                 const double* __restrict__ bs, const double* __restrict__ Hmarg,
-                                                 const double* __restrict__ bmarg, double* __restrict__ step_dev) {
-  if (ctl->done) return;
-  constexpr int DP = 16 * T;
-  extern __shared__ double sh[];
-  const int D = 8 * N, tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
-  double* colk = sh;                 // [2][DP]
-  double* bk = colk + 2 * DP;        // [2]
-  double* dvec = bk + 2;             // [DP]
-  double* pre = dvec + DP;           // [DP]
-  double* st = pre + DP;             // [DP] state eps
-  double* hm = st + DP;              // [DP] H_marg * state
-  double* L = hm + DP;               // [DP][DP + 1]
-  const double lambda = ctl->lambda, ks = -1.0 / (1.0 + lambda);
-  if (tid < DP) st[tid] = tid < D ? fr[tid / 8].eps[tid % 8] : 0.0;
-  __syncthreads();
-  if (Hmarg) {  // warp per row, lanes along the row: coalesced
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int i = warp; i < D; i += 8) {
-      double t = 0;
-      for (int j = lane; j < D; j += 32) t += Hmarg[(size_t)i * D + j] * st[j];
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) t += __shfl_xor_sync(FULL, t, s);
-      if (lane == 0) hm[i] = t;
-    }
-  }
-  double a[T][T];
-#pragma unroll
-  for (int ai = 0; ai < T; ++ai)
-#pragma unroll
-    for (int aj = 0; aj < T; ++aj) {
-      const int i = ty + 16 * ai, j = tx + 16 * aj;
-      double v = (i == j) ? 1.0 : 0.0;  // identity padding
-      if (i < D && j < D) {
-        const size_t idx = (size_t)i * D + j;
-        double hp = Hp[idx];
-        if (i == j) {
-          const int f = i / 8, k = i % 8;
-          if (fixed[f]) hp += opt->fixed_reg;
-          else if (k >= 6) hp += opt->ab_reg[k - 6];
-          hp += hp * lambda;  // H.diagonal() += system_pose.H.diagonal() * lambda (prior included)
-        }
-        v = hp + (Hmarg ? Hmarg[idx] : 0.0) + ks * Hs[idx];
+  const double prior_e = block_sum_256(acc, red);
+  if (i == 0) {
+    const double E = opt->energy_marg + prior_e + scal[0];
+    const int n = (int)llrint(scal[1]);
+    if (kind == pba::LM_ENERGY_INITIAL) {
+      ctl->energy = E;
+      ctl->n_valid = n;
+      if (n <= 0 || opt->max_it <= 0) ctl->done = 1;
+    } else if (kind == pba::LM_ENERGY_TRIAL) {
+      ctl->next_energy = E;
+      ctl->next_n = n;
+      ctl->iterations_executed += 1;
+      // landmark parts of the norms, accumulated by k_back_substitute (problem.hpp:377-382)
+      ctl->state_sq = scal[2];
+      ctl->step_sq = scal[3];
+      if (n == 0) {
+        ctl->accept = -1;  // rejectStep(); break
+      } else {
+        if (fabs(ctl->energy - E) / ctl->energy < opt->ftol) ctl->converged = 1;  // before the accept test (Q7)
+        ctl->accept = (E < ctl->energy || (opt->force_accept && ctl->iteration < opt->min_it)) ? 1 : 0;
       }
-      a[ai][aj] = v;
-      if (i == j) pre[i] = 1.0 / sqrt(v + 10.0);  // jacobiPreconditioner, +10 floor
-    }
-  __syncthreads();
-  double b = 0.0;
-  if (tid < D) {
-    const int f = tid / 8, k = tid % 8;
-    b = bp[tid] + ks * bs[tid];
-    if (fixed[f]) b += opt->fixed_reg * st[tid];
-    else if (k >= 6) b += opt->ab_reg[k - 6] * (fr[f].ab0[k - 6] + st[tid]);
-    if (Hmarg) b += bmarg[tid] + hm[tid];
-    b *= pre[tid];
-  }
-#pragma unroll
-  for (int ai = 0; ai < T; ++ai)
-#pragma unroll
-    for (int aj = 0; aj < T; ++aj) a[ai][aj] *= pre[ty + 16 * ai] * pre[tx + 16 * aj];
-
-  // Pivot loop.  fp64 arithmetic is the scarce resource here (one CTA, 8 warps, 8N strictly sequential pivots), so
-  // only the LOWER triangle is updated -- tiles with ai > aj entirely, diagonal tiles where tx <= ty -- and a
-  // column stops being updated once it is factored (k >= j).  Rows <= k are dead and may hold garbage.
-  const bool diag_lower = tx <= ty;
-  for (int k = 0; k < D; ++k) {
-    const int buf = k & 1;
-    double* ck = colk + buf * DP;
-    if (tx == (k & 15)) {  // owners of column k publish it (raw) and record it as column k of L * D
-      const int aj = k >> 4;
-#pragma unroll
-      for (int q = 0; q < T; ++q)
-        if (q == aj) {
-#pragma unroll
-          for (int ai = 0; ai < T; ++ai) {
-            const double v = a[ai][q];
-            ck[ty + 16 * ai] = v;
-            L[(ty + 16 * ai) * (DP + 1) + k] = v;
-          }
-        }
-    }
-    if (tid == k) bk[buf] = b;
-    __syncthreads();
-    const double d = ck[k];
-    // 1/d: fp32 reciprocal seed + one fp64 Newton step (relative error ~2^-46) instead of the ~15-deep IEEE
-    // division sequence; the preconditioned pivots are O(1), well inside the fp32 range
-    double inv = 0.0;
-    if (d != 0.0) {
-      inv = (double)__frcp_rn((float)d);
-      inv = inv * (2.0 - d * inv);
-    }
-    if (tid == 0) dvec[k] = inv;
-#pragma unroll
-    for (int aj = 0; aj < T; ++aj) {
-      if (k < tx + 16 * aj) {  // column still live
-        const double cj = ck[tx + 16 * aj] * inv;
-#pragma unroll
-        for (int ai = 0; ai < T; ++ai) {
-          if (ai > aj || (ai == aj && diag_lower)) a[ai][aj] -= ck[ty + 16 * ai] * cj;
-        }
-      }
-    }
-    if (tid > k && tid < D) b -= ck[tid] * inv * bk[buf];
-  }
-  __syncthreads();
-  if (tid < D) st[tid] = b * dvec[tid];  // z = D^-1 L^-1 b  (reuse st; dvec holds 1/d)
-  __syncthreads();
-  // back substitution L^T x = z by one warp; L[k][i] = Lraw[k][i] / d_i
-  if (tid < 32) {
-    for (int k = D - 1; k > 0; --k) {
-      const double xk = st[k];
-      for (int i = tid; i < k; i += 32) st[i] -= L[k * (DP + 1) + i] * dvec[i] * xk;
-      __syncwarp();
+      ctl->apply = 1;
+      s_accept = ctl->accept;
     }
   }
+  if (kind != pba::LM_ENERGY_TRIAL) return;
   __syncthreads();
-  if (tid < D) {
-    const double x = st[tid] * pre[tid];
-    step_dev[tid] = x;
-    fr[tid / 8].step[tid % 8] = -x;  // frame.state_eps_step = -frame_step (problem.hpp:353-357)
-  }
-}
-
-// acceptStep / rejectStep for the frame state + the loop bookkeeping (problem.hpp:366-402, lm.hpp:104-122).
-// One thread per state entry, norms reduced in shared memory.
-__global__ void __launch_bounds__(128) k_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N) {
-  if (ctl->done) return;
-  __shared__ double r_st[128], r_sp[128];
-  const int i = threadIdx.x, D = 8 * N;
-  const int accept = ctl->accept;
+  // acceptStep / rejectStep for the frame state (problem.hpp:366-376,392-402); one thread per state entry
+  const int accept = s_accept;
   double st = 0, sp = 0;
   if (i < D) {
     const int f = i / 8, k = i % 8;
-    const double e = fr[f].eps[k], s = fr[f].step[k];
+    const double e = fr[f].eps[k], stp = fr[f].step[k];
     if (accept > 0) {
       st = e * e;
       if (k >= 6) st += fr[f].ab0[k - 6] * fr[f].ab0[k - 6];
-      sp = s * s;
-      fr[f].eps[k] = e + s;
+      sp = stp * stp;
+      fr[f].eps[k] = e + stp;
     }
     fr[f].step[k] = 0;
   }
-  r_st[i] = st;
-  r_sp[i] = sp;
-  __syncthreads();
-  for (int s = 64; s > 0; s >>= 1) {
-    if (i < s) {
-      r_st[i] += r_st[i + s];
-      r_sp[i] += r_sp[i + s];
-    }
-    __syncthreads();
-  }
+  st = block_sum_256(st, red);
+  sp = block_sum_256(sp, red);
   if (i) return;
   if (accept > 0) {
-    const double stt = ctl->state_sq + r_st[0], spp = ctl->step_sq + r_sp[0];
+    const double stt = ctl->state_sq + st, spp = ctl->step_sq + sp;
     ctl->state_sq = stt;
     ctl->step_sq = spp;
     if (spp < opt->ptol * (stt + opt->ptol)) ctl->converged = 1;
@@ -2004,6 +1912,199 @@ __global__ void __launch_bounds__(128) k_lm_finish(LmCtl* ctl, const LmOptionsDe
   }
   ctl->iteration += 1;
   if (ctl->iteration >= opt->max_it || ctl->converged || ctl->n_valid <= 0) ctl->done = 1;
+}
+
+// calculateStep (problem.hpp:342-357): priors (problem.hpp:37-77), full system, Jacobi preconditioner + LDL^T
+// (normal_linear_system.cpp:10-59), all fp64 in one CTA.
+//
+// Blocked right-looking LDL^T, block size 8, on the lower triangle held in shared memory.  The right-hand side rides
+// along as row D of the matrix, so z = L^-1 b falls out of the factorisation.  Per block step (3 barriers):
+//   panel : thread i owns row kb+i.  Every thread factors the 8x8 diagonal block redundantly in registers (no
+//           barrier, no broadcast) and runs the same recurrence on its own 8 panel entries
+//             a[c] -= a[j] * l_cj   (j < c),   l_cj = x_cj / d_j,   x = L D  ("raw" columns)
+//   update: A22 -= X L21^T over the trailing lower triangle, 16x16 thread tiling, K = 8.
+// A column-by-column factorisation needs 8N barrier-separated steps whose critical path (publish column, barrier,
+// reciprocal, update) measured ~1500 cycles each on B200 (profiles/r01d_k_lm_step.md); this form has N of them.
+__device__ __forceinline__ double rcp64(double d) {
+  // IEEE division: measured 67 cycles on B200 against 131 for an fp32 seed + two Newton steps (the f32<->f64
+  // conversions dominate), tools/fp64_probe.cu
+  return d == 0.0 ? 0.0 : 1.0 / d;
+}
+
+__device__ long long g_lmclk[16];
+#define LMCLK(i) do { if (threadIdx.x == 0) g_lmclk[i] = clock64(); } while (0)
+template <int DP>
+__global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
+                                                 const int* fixed, int N, const double* __restrict__ Hp,
+                                                 const double* __restrict__ bp, const double* __restrict__ Hs,
+                                                 const double* __restrict__ bs, const double* __restrict__ Hmarg,
+                                                 const double* __restrict__ bmarg, double* __restrict__ step_dev) {
+  LMCLK(0);
+  if (ctl->done) return;
+  LMCLK(1);
+  constexpr int LD = DP + 1;   // row stride of S (odd: conflict-free column walks)
+  constexpr int LPS = 9;       // row stride of Lp
+  extern __shared__ double sh[];
+  const int D = 8 * N, tid = threadIdx.x;
+  double* S = sh;                       // [DP + 1][LD] lower triangle of the preconditioned system, row D = rhs
+  double* Lp = S + (DP + 1) * LD;       // [DP + 1][LPS] l_cj of the current panel
+  double* dinv = Lp + (DP + 1) * LPS;   // [DP] 1 / d
+  double* pre = dinv + DP;              // [DP] Jacobi preconditioner
+  double* st = pre + DP;                // [DP] state eps, later the solution
+  double* hm = st + DP;                 // [DP] H_marg * state
+  const double lambda = ctl->lambda, ks = -1.0 / (1.0 + lambda);
+  if (tid < DP) st[tid] = tid < D ? fr[tid / 8].eps[tid % 8] : 0.0;
+  __syncthreads();
+  if (Hmarg) {  // warp per row, lanes along the row: coalesced
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < D; i += 8) {
+      double t = 0;
+      for (int j = lane; j < D; j += 32) t += Hmarg[(size_t)i * D + j] * st[j];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) t += __shfl_xor_sync(FULL, t, s);
+      if (lane == 0) hm[i] = t;
+    }
+  }
+  // unscaled system:  H_pose(+priors, +lambda on the diagonal) + H_marg - H_schur / (1 + lambda)
+  LMCLK(2);
+  if (tid < D) {
+    const size_t idx = (size_t)tid * D + tid;
+    const int f = tid / 8, k = tid % 8;
+    double hp = Hp[idx];
+    if (fixed[f]) hp += opt->fixed_reg;
+    else if (k >= 6) hp += opt->ab_reg[k - 6];
+    hp += hp * lambda;  // H.diagonal() += system_pose.H.diagonal() * lambda (prior included)
+    const double v = hp + (Hmarg ? Hmarg[idx] : 0.0) + ks * Hs[idx];
+    dinv[tid] = v;                        // parked here until the fill below
+    pre[tid] = 1.0 / sqrt(v + 10.0);      // jacobiPreconditioner, +10 floor
+  }
+  __syncthreads();
+  LMCLK(3);
+  // fill the lower triangle: 8 independent (Hp, Hs[, Hmarg]) loads in flight per thread per trip, so the fill costs
+  // a few L2 round trips instead of one per element
+  for (int base = 0; base < D * D; base += 256 * 8) {
+    double hp[8], hs[8], hg[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = base + q * 256 + tid;
+      const bool in = idx < D * D;
+      hp[q] = in ? Hp[idx] : 0.0;
+      hs[q] = in ? Hs[idx] : 0.0;
+      hg[q] = (in && Hmarg) ? Hmarg[idx] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = base + q * 256 + tid;
+      const int i = idx / D, j = idx - i * D;
+      if (idx < D * D && j <= i) S[i * LD + j] = (i == j ? dinv[i] : hp[q] + hg[q] + ks * hs[q]) * pre[i] * pre[j];
+    }
+  }
+  if (tid < D) {
+    const int f = tid / 8, k = tid % 8;
+    double b = bp[tid] + ks * bs[tid];
+    if (fixed[f]) b += opt->fixed_reg * st[tid];
+    else if (k >= 6) b += opt->ab_reg[k - 6] * (fr[f].ab0[k - 6] + st[tid]);
+    if (Hmarg) b += bmarg[tid] + hm[tid];
+    S[D * LD + tid] = b * pre[tid];
+  }
+
+  LMCLK(4);
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int kb = 0; kb < D; kb += 8) {
+    __syncthreads();
+    if (kb == 8) LMCLK(5);
+    const int i = kb + tid;  // this thread's row (row D is the right-hand side)
+    const bool act = i <= D;
+    // the 8x8 diagonal block, packed lower triangle g[r (r + 1) / 2 + c], factored redundantly by every thread
+    double g[36], inv[8], a[8];
+    if (act) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) g[r * (r + 1) / 2 + c] = S[(kb + r) * LD + kb + c];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = (i >= kb + c) ? S[i * LD + kb + c] : 0.0;
+    }
+    __syncthreads();  // rows kb..kb+7 are overwritten below by their owners
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        inv[j] = rcp64(g[j * (j + 1) / 2 + j]);
+#pragma unroll
+        for (int r = j + 1; r < 8; ++r) {
+          const double l = g[r * (r + 1) / 2 + j] * inv[j];
+#pragma unroll
+          for (int c = j + 1; c <= r; ++c) g[r * (r + 1) / 2 + c] -= l * g[c * (c + 1) / 2 + j];
+        }
+      }
+      // own row: same recurrence (for a row of the diagonal block the entries right of the diagonal are unused)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) a[c] -= a[j] * (g[c * (c + 1) / 2 + j] * inv[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (i >= kb + j) {
+          S[i * LD + kb + j] = a[j];        // raw column entry x_ij = l_ij d_j
+          Lp[i * LPS + j] = a[j] * inv[j];  // l_ij
+        }
+      }
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dinv[kb + j] = inv[j];
+      }
+    }
+    __syncthreads();
+    // trailing update of the lower triangle (and the rhs row): S[r][c] -= sum_j x_rj l_cj
+    const int m0 = kb + 8;
+    for (int r = m0 + ty; r <= D; r += 16) {
+      double x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = S[r * LD + kb + j];
+      const int cmax = min(r, D - 1);
+      for (int c = m0 + tx; c <= cmax; c += 16) {
+        double acc = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += x[j] * Lp[c * LPS + j];
+        S[r * LD + c] -= acc;
+      }
+    }
+  }
+  __syncthreads();
+  LMCLK(6);
+  if (tid < D) st[tid] = S[D * LD + tid] * dinv[tid];  // z = D^-1 L^-1 b
+  // blocked back substitution L^T x = z, l_ki = x_ki / d_i: every thread solves the 8x8 triangle of the block
+  // redundantly in registers, then row i < kb subtracts the block's contribution -- one barrier per 8 unknowns
+  for (int kb = D - 8; kb >= 0; kb -= 8) {
+    __syncthreads();
+    double x[8];
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      double v = st[kb + j];
+      const double dj = dinv[kb + j];
+#pragma unroll
+      for (int m = 7; m > j; --m) v -= S[(kb + m) * LD + kb + j] * dj * x[m];
+      x[j] = v;
+    }
+    if (tid == 0) {  // the solution is collected in hm (dead since the right-hand side was formed): no second barrier
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hm[kb + j] = x[j];
+    }
+    if (tid < kb) {
+      double acc = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += S[(kb + j) * LD + tid] * x[j];
+      st[tid] -= dinv[tid] * acc;
+    }
+  }
+  __syncthreads();
+  LMCLK(7);
+  if (tid < D) {
+    const double x = hm[tid] * pre[tid];
+    step_dev[tid] = x;
+    fr[tid / 8].step[tid % 8] = -x;  // frame.state_eps_step = -frame_step (problem.hpp:353-357)
+  }
 }
 
 
@@ -2045,37 +2146,30 @@ void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s
   k_lm_zero<<<(n + 255) / 256, 256, 0, s>>>(ctl, p, n, mode);
 }
 
-void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, const FrameParams* fr, int N, double* scal,
+void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, double* scal,
                       const double* Hmarg, const double* bmarg, int kind, cudaStream_t s, const double* e_part, int n_e,
                       const double* n_part, int n_n) {
   ++g_launches;
-  k_lm_energy<<<1, 128, 0, s>>>(ctl, opt, fr, N, scal, Hmarg, bmarg, kind, reinterpret_cast<const double2*>(e_part), n_e,
+  k_lm_energy<<<1, 256, 0, s>>>(ctl, opt, fr, N, scal, Hmarg, bmarg, kind, reinterpret_cast<const double2*>(e_part), n_e,
                                 reinterpret_cast<const double2*>(n_part), n_n);
 }
 
+void read_lm_clocks(long long* out) { cudaMemcpyFromSymbol(out, g_lmclk, sizeof(long long) * 16); }
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
                     const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s) {
   const int D = 8 * N;
   ++g_launches;
+  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP) * sizeof(double); };
   if (D <= 64) {
-    constexpr int DP = 64;
-    const size_t smem = (size_t)(2 * DP + 2 + 4 * DP + DP * (DP + 1)) * sizeof(double);
-    k_lm_step<4><<<1, 256, smem, s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
+    k_lm_step<64><<<1, 256, smem_of(64), s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
   } else {
-    constexpr int DP = 128;
-    const size_t smem = (size_t)(2 * DP + 2 + 4 * DP + DP * (DP + 1)) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(k_lm_step<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_lm_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128));
       attr_set = true;
     }
-    k_lm_step<8><<<1, 256, smem, s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
+    k_lm_step<128><<<1, 256, smem_of(128), s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
   }
-}
-
-void launch_lm_finish(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, cudaStream_t s) {
-  ++g_launches;
-  k_lm_finish<<<1, 128, 0, s>>>(ctl, opt, fr, N);
 }
 
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s) {
@@ -2205,13 +2299,25 @@ int launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s,
   return grid;  // CTAs that wrote a partial
 }
 
-void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl) {
+void launch_core_reduce(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl) {
   const int N = w.n_frames;
   if (N < 2 || shape.lpb == 0) return;
   ++g_launches;
   k_core_reduce<<<N * (N - 1), 256, 0, s>>>(w, rb.core_part, shape.lpb, shape.chunks, rb.core, ctl);
+}
+
+void launch_assemble_blocks(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,
+                            const LmCtl* ctl) {
+  const int N = w.n_frames;
+  if (N < 2 || shape.lpb == 0) return;
   ++g_launches;
-  k_assemble<<<N * (N + 1) / 2, 64, 0, s>>>(w, fej, rb.core, rb.Hp, rb.bp, ctl);
+  const int threads = 32 * std::max(2, N - 1);
+  k_assemble<<<N * (N + 1) / 2, threads, (size_t)(threads / 32) * ASM_W * sizeof(double), s>>>(w, fej, rb.core, rb.Hp, rb.bp, ctl);
+}
+
+void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl) {
+  launch_core_reduce(w, rb, shape, s, ctl);
+  launch_assemble_blocks(w, fej, rb, shape, s, ctl);
 }
 
 // fused path: sums the per-chunk Schur partials written by k_linearize_fused and mirrors H_s (k_assemble already

@@ -13,8 +13,12 @@
  *   - every call returns 0 on success or a negative DPBA_E_* code; dpba_last_error() gives text.
  *     Nothing throws, aborts or logs (reference: LOG(ERROR)+return / CHECK abort,
  *     energy/problems/src/photometric_bundle_adjustment.cpp:66-69,101).
- *   - the library COPIES everything it is given (LocalFrame copies landmarks/statuses,
- *     PBA/local_frame.hpp:309-335); host buffers stay owned by the caller.
+ *   - the library COPIES landmarks, statuses and state when it is given them (LocalFrame copies them,
+ *     PBA/local_frame.hpp:309-335): the caller may reuse those buffers as soon as the call returns (they are staged
+ *     in pinned memory and DMA'd asynchronously; no set_* call synchronises the stream).  Images and masks in
+ *     PAGE-LOCKED memory are BORROWED until the next synchronising call (dpba_solve_lm, dpba_linearize,
+ *     dpba_evaluate, any dpba_get_*), as LocalFrame borrows its PixelMap pointers (PBA/local_frame.hpp:44,325);
+ *     pageable images are copied before the call returns.
  *   - frames live in dense slots 0..N-1 in ascending timestamp order
  *     (photometric_bundle_adjustment.cpp:101); only slot 0 may be fixed
  *     (PBA/hessian_block_evaluation.hpp:143); single sensor, C = 1, pinhole + SE3
@@ -137,6 +141,14 @@ int dpba_set_statuses(dpba_handle* h, int32_t ref_slot, int32_t tgt_slot, int32_
 int dpba_get_statuses(dpba_handle* h, int32_t ref_slot, int32_t tgt_slot, int32_t n, uint8_t* statuses,
                       uint8_t* candidates);
 
+/* All residual vectors of one reference frame in one call -- what the LocalFrame ctor / LocalFrame::update do with
+ * frame.connections() (PBA/local_frame.hpp:336-347,506-520).  per_target[t] -> [n] statuses towards slot t;
+ * entry ref_slot is ignored and NULL entries are skipped.  The getter fills statuses[t] / candidates[t] (either
+ * array, or single entries, may be NULL) with ONE stream synchronisation for the whole frame. */
+int dpba_set_frame_statuses(dpba_handle* h, int32_t ref_slot, int32_t n, const uint8_t* const* per_target);
+int dpba_get_frame_statuses(dpba_handle* h, int32_t ref_slot, int32_t n, uint8_t* const* statuses,
+                            uint8_t* const* candidates);
+
 /* state_eps / state_eps_step of all frames, [8N] each (PBA/local_frame.hpp:561-563) */
 int dpba_set_state(dpba_handle* h, const double* state_eps, const double* state_eps_step);
 int dpba_get_state(dpba_handle* h, double* state_eps, double* state_eps_step);
@@ -238,11 +250,13 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value);
 /* kernels launched by this process so far (every launch wrapper counts itself) */
 int64_t dpba_launch_count(void);
 /* Per-kernel device timing with CUDA events recorded on the handle's stream around each launch.
- * kinds: 0 fused linearise sweep, 1 Schur SYRK, 2 residual-only sweep, 3 materialising sweep,
- *        4 assemble+symmetrise, 5 back-substitution, 6 per-pair constants, 7 device LM step (priors + LDL^T).
+ * kinds: 0 fused linearise sweep, 1 Schur SYRK (three-pass path), 2 residual-only sweep, 3 materialising sweep,
+ *        4 assemble+symmetrise (three-pass path), 5 back-substitution, 6 per-pair constants,
+ *        7 device LM step (priors + LDL^T), 8 per-pair core reduction, 9 H_pp block assembly,
+ *        10 Schur partial reduction, 11 LM control kernels (energy tail, accept, loop bookkeeping).
  *        dpba_profile_read synchronises, returns per kind the
  *        summed milliseconds and launch counts since the last dpba_profile_enable(h, 1), and keeps profiling on. */
-#define DPBA_PROFILE_KINDS 8
+#define DPBA_PROFILE_KINDS 12
 int dpba_profile_enable(dpba_handle* h, int32_t on);
 int dpba_profile_read(dpba_handle* h, double ms[DPBA_PROFILE_KINDS], int32_t launches[DPBA_PROFILE_KINDS]);
 

@@ -251,7 +251,11 @@ def test_lm_solve_through_the_c_abi_tracks_the_oracle(capi, name, ab_scale, ab_r
     assert np.abs(eps - eps_ref).max() <= 2e-5 * max(1.0, max(np.abs(f.ab0).max() for f in win.frames))
     for i, f in enumerate(frames):
         lm = h.get_landmarks(i)
-        assert np.abs(lm["idepth"] - f.idepth).max() <= 5e-5  # weakly observed idepths amplify rounding
+        # delta_rho = -(b_d - H_pd^T step) / ((1 + lambda) H_dd): the fp32 floor of b_d is amplified by 1/H_dd, so the
+        # bound scales with the landmark's own idepth standard deviation sqrt(inv_hdd) (weakly observed depths)
+        d_id = np.abs(lm["idepth"] - f.idepth)
+        assert (d_id <= 5e-5 + 2e-2 * np.sqrt(np.maximum(f.inv_hdd, 0.0))).all(), d_id.max()
+        assert np.mean(d_id <= 5e-5) >= 0.99
         for j, g in enumerate(frames):
             if i != j:
                 st, _ = h.get_statuses(i, j)
