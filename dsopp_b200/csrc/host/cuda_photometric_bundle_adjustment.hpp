@@ -233,12 +233,14 @@ class CudaPhotometricBundleAdjustment {
       }
     }
     statuses_as_reference.clear();
+    uint8_t* rows[DPBA_MAX_FRAMES] = {};
     for (size_t t = 0; t < frames_.size(); ++t) {
       if ((int)t == slot) continue;
-      std::vector<uint8_t> st(n);
-      if (n) dpba_check(h_, dpba_get_statuses(h_, slot, (int)t, n, st.data(), nullptr));
-      statuses_as_reference[frames_[t].id] = st;
+      auto& st = statuses_as_reference[frames_[t].id];
+      st.assign(n, 0);
+      rows[t] = st.data();
     }
+    if (n) dpba_check(h_, dpba_get_frame_statuses(h_, slot, n, rows, nullptr));  // one synchronisation per frame
   }
 
  private:

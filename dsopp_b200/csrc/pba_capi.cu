@@ -77,6 +77,7 @@ struct dpba_handle {
   // landmark arrays
   float4* lmk = nullptr;  // {u, v, idepth, idepth at the FEJ linearisation point}
   float *idepth_step = nullptr, *patch = nullptr;
+  float* lm_slab = nullptr;  // owns idepth_step, inv_hdd, b_d, rel_baseline, n_inliers ([5][max_frames * max_pts])
   // pinned staging arena for the small host arrays (landmarks, statuses): the caller's buffer is copied here and
   // DMA'd asynchronously, so set_* calls return without a stream synchronisation and the caller may reuse its buffer
   char* arena_h = nullptr;
@@ -436,7 +437,7 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
     src = h->stage_h;
   }
   CK(cudaMemcpyAsync(h->stage, src, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  if (channels == 3) pba::launch_pack_image(h->stage, h->img[phys], (int)npx, h->stream);
+  if (channels == 3) pba::launch_pack_image(h->stage, h->img[phys], (int)npx, W, h->stream);
   else pba::launch_pixelinfo(h->stage, h->img[phys], W, H, h->stream);
   CK(cudaGetLastError());
   if (mask) CK(cudaMemcpyAsync(h->mask[phys], mask, npx, cudaMemcpyHostToDevice, h->stream));
@@ -444,18 +445,8 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
   // new residual vectors of this frame start as kOk until dpba_set_statuses says otherwise: the rows (phys -> p) are
   // contiguous, the rows (p -> phys) are one strided 2-D memset per array
   const size_t mp = h->cfg.max_points_per_frame;
-  const size_t nf = (size_t)h->cfg.max_frames;
-  {
-    const size_t a = (size_t)phys * PBA_MAXF * mp, b = (size_t)phys * mp, pitch = (size_t)PBA_MAXF * mp;
-    CK(cudaMemsetAsync(h->status + a, 0, nf * mp, h->stream));
-    CK(cudaMemsetAsync(h->cand + a, 0, nf * mp, h->stream));
-    CK(cudaMemsetAsync(h->jac_valid + a, 0, nf * mp, h->stream));
-    CK(cudaMemsetAsync(h->energy + a, 0, nf * mp * sizeof(float), h->stream));
-    CK(cudaMemset2DAsync(h->status + b, pitch, 0, mp, nf, h->stream));
-    CK(cudaMemset2DAsync(h->cand + b, pitch, 0, mp, nf, h->stream));
-    CK(cudaMemset2DAsync(h->jac_valid + b, pitch, 0, mp, nf, h->stream));
-    CK(cudaMemset2DAsync(h->energy + b, pitch * sizeof(float), 0, mp * sizeof(float), nf, h->stream));
-  }
+  pba::launch_clear_frame_rows(h->status, h->cand, h->jac_valid, h->energy, phys, (int)mp, h->cfg.max_frames, h->stream);
+  CK(cudaGetLastError());
   // pageable images went through stage_h, which the next push reuses; page-locked images are BORROWED until the next
   // synchronising call (solve / get_*), exactly as LocalFrame borrows its PixelMap pointers (local_frame.hpp:44,325)
   if (!pinned) CK(cudaStreamSynchronize(h->stream));
@@ -494,11 +485,8 @@ int upload_landmarks(dpba_handle* h, int slot, int first, int n, const float* uv
   } else {
     CK(cudaMemsetAsync(h->flags + base, 0, n, h->stream));
   }
-  CK(cudaMemsetAsync(h->idepth_step + base, 0, sizeof(float) * n, h->stream));
-  CK(cudaMemsetAsync(h->inv_hdd + base, 0, sizeof(float) * n, h->stream));
-  CK(cudaMemsetAsync(h->b_d + base, 0, sizeof(float) * n, h->stream));
-  CK(cudaMemsetAsync(h->rel_baseline + base, 0, sizeof(float) * n, h->stream));
-  CK(cudaMemsetAsync(h->n_inliers + base, 0, sizeof(uint32_t) * n, h->stream));
+  const size_t nlm = (size_t)h->cfg.max_frames * h->cfg.max_points_per_frame;
+  CK(cudaMemset2DAsync(h->lm_slab + base, nlm * sizeof(float), 0, sizeof(float) * n, 5, h->stream));
   return 0;
 }
 
@@ -546,20 +534,23 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   const size_t nlm = (size_t)cfg->max_frames * mp;
   const size_t nres = (size_t)PBA_MAXF * PBA_MAXF * mp;
   for (int p = 0; p < cfg->max_frames; ++p) {
-    CKC(cudaMalloc(&h->img[p], npx * sizeof(float4)));
+    CKC(cudaMalloc(&h->img[p], npx * 2 * sizeof(float4)));  // {texel(x), texel(x+1)} records
     CKC(cudaMalloc(&h->mask[p], npx));
   }
   CKC(cudaMalloc(&h->lmk, nlm * sizeof(float4)));
   CKC(cudaMemset(h->lmk, 0, nlm * sizeof(float4)));
-  CKC(cudaMalloc(&h->idepth_step, nlm * sizeof(float)));
-  CKC(cudaMemset(h->idepth_step, 0, nlm * sizeof(float)));
+  // idepth_step | inv_hdd | b_d | rel_baseline | n_inliers carved out of ONE slab, so that a landmark upload clears
+  // them with one 2-D memset and a readback fetches them with one 2-D copy
+  CKC(cudaMalloc(&h->lm_slab, 5 * nlm * sizeof(float)));
+  CKC(cudaMemset(h->lm_slab, 0, 5 * nlm * sizeof(float)));
+  h->idepth_step = h->lm_slab;
+  h->inv_hdd = h->lm_slab + nlm;
+  h->b_d = h->lm_slab + 2 * nlm;
+  h->rel_baseline = h->lm_slab + 3 * nlm;
+  h->n_inliers = reinterpret_cast<uint32_t*>(h->lm_slab + 4 * nlm);
   CKC(cudaMalloc(&h->patch, nlm * 8 * sizeof(float)));
   CKC(cudaMalloc(&h->flags, nlm));
-  CKC(cudaMalloc(&h->inv_hdd, nlm * sizeof(float)));
-  CKC(cudaMalloc(&h->b_d, nlm * sizeof(float)));
   CKC(cudaMalloc(&h->hpd, nlm * MAXD * sizeof(float)));
-  CKC(cudaMalloc(&h->rel_baseline, nlm * sizeof(float)));
-  CKC(cudaMalloc(&h->n_inliers, nlm * sizeof(uint32_t)));
   CKC(cudaMalloc(&h->status, nres));
   CKC(cudaMalloc(&h->cand, nres));
   CKC(cudaMalloc(&h->jac_valid, nres));
@@ -588,7 +579,8 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
     CKC(cudaMalloc(&h->schur_part, (size_t)h->sm_count * maxd * maxd * sizeof(double)));
     CKC(cudaMalloc(&h->core, (size_t)PBA_MAXF * PBA_MAXF * PBA_CORE * sizeof(double)));
     CKC(cudaMalloc(&h->bs_part, (size_t)h->sm_count * maxd * sizeof(double)));
-    const size_t sweep_ctas = ((mp + 31) / 32) * (size_t)cfg->max_frames * (cfg->max_frames - 1);
+    // k_residual_sweep: one partial per (landmark chunk >= 8, host frame) CTA
+    const size_t sweep_ctas = ((mp + 7) / 8) * (size_t)cfg->max_frames;
     CKC(cudaMalloc(&h->e_part, sweep_ctas * 2 * sizeof(double)));
     CKC(cudaMalloc(&h->n_part, ((mp + 31) / 32) * (size_t)cfg->max_frames * 2 * sizeof(double)));
   }
@@ -626,8 +618,8 @@ int dpba_destroy(dpba_handle* h) {
     cudaFree(h->img[p]);
     cudaFree(h->mask[p]);
   }
-  void* dev[] = {h->lmk,     h->jac_valid, h->idepth_step,              h->patch,  h->flags,   h->inv_hdd,
-                 h->b_d,     h->hpd,    h->rel_baseline, h->n_inliers,  h->status, h->cand,    h->energy,
+  void* dev[] = {h->lmk,     h->jac_valid, h->lm_slab,                  h->patch,  h->flags,
+                 h->hpd,     h->status, h->cand,    h->energy,
                  h->pairs,   h->pasm,   h->fparams,      h->red,        h->step_dev, h->pair_dist, h->stage,
                  h->m_r,     h->m_jref, h->m_jtgt,       h->m_did,      h->m_w,    h->red2,    h->ctl,
                  h->lmopt,   h->fixed_dev, h->marg_dev, h->core_part, h->fschur_part, h->core, h->schur_part, h->bs_part, h->e_part,
@@ -741,18 +733,38 @@ int dpba_get_landmarks(dpba_handle* h, int32_t slot, int32_t n, float* idepth, f
   REQUIRE(n >= 0 && n <= h->fr[slot].n_lm, "n exceeds the landmark count");
   const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame;
   if (n == 0) return DPBA_SUCCESS;
-  if (idepth)
-    CK(cudaMemcpy2DAsync(idepth, sizeof(float), reinterpret_cast<const float*>(h->lmk + base) + 2, sizeof(float4),
-                         sizeof(float), n, cudaMemcpyDeviceToHost, h->stream));
-  if (idepth_step)
-    CK(cudaMemcpyAsync(idepth_step, h->idepth_step + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
-  if (inv_hdd) CK(cudaMemcpyAsync(inv_hdd, h->inv_hdd + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
-  if (b_d) CK(cudaMemcpyAsync(b_d, h->b_d + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
-  if (flags) CK(cudaMemcpyAsync(flags, h->flags + base, n, cudaMemcpyDeviceToHost, h->stream));
-  if (n_inl) CK(cudaMemcpyAsync(n_inl, h->n_inliers + base, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
-  if (rel_baseline)
-    CK(cudaMemcpyAsync(rel_baseline, h->rel_baseline + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  // device -> pinned arena (asynchronous, one synchronisation) -> caller; a direct copy into pageable memory would
+  // synchronise once per array.  The arena is emptied first so that it cannot wrap in the middle of this call.
   CK(cudaStreamSynchronize(h->stream));
+  h->arena_used = 0;
+  const size_t nlm = (size_t)h->cfg.max_frames * h->cfg.max_points_per_frame;
+  float* slab = nullptr;  // [5][n]: idepth_step, inv_hdd, b_d, rel_baseline, n_inliers
+  float* idp = nullptr;
+  uint8_t* flg = nullptr;
+  if (idepth_step || inv_hdd || b_d || n_inl || rel_baseline) {
+    if (!(slab = (float*)arena_alloc(h, 5 * sizeof(float) * n))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+    CK(cudaMemcpy2DAsync(slab, sizeof(float) * n, h->lm_slab + base, nlm * sizeof(float), sizeof(float) * n, 5,
+                         cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (idepth) {
+    if (!(idp = (float*)arena_alloc(h, sizeof(float) * n))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+    CK(cudaMemcpy2DAsync(idp, sizeof(float), reinterpret_cast<const float*>(h->lmk + base) + 2, sizeof(float4),
+                         sizeof(float), n, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (flags) {
+    if (!(flg = (uint8_t*)arena_alloc(h, n))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+    CK(cudaMemcpyAsync(flg, h->flags + base, n, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t nb = sizeof(float) * n;
+  if (idepth) memcpy(idepth, idp, nb);
+  if (idepth_step) memcpy(idepth_step, slab, nb);
+  if (inv_hdd) memcpy(inv_hdd, slab + n, nb);
+  if (b_d) memcpy(b_d, slab + 2 * (size_t)n, nb);
+  if (rel_baseline) memcpy(rel_baseline, slab + 3 * (size_t)n, nb);
+  if (n_inl) memcpy(n_inl, slab + 4 * (size_t)n, nb);
+  if (flags) memcpy(flags, flg, n);
+  h->arena_used = 0;  // the stream is idle: nothing references the arena any more
   return DPBA_SUCCESS;
 }
 
@@ -790,6 +802,36 @@ int dpba_set_frame_statuses(dpba_handle* h, int32_t r, int32_t n, const uint8_t*
   REQUIRE(h, "null handle");
   REQUIRE(r >= 0 && r < h->n_frames && per_target, "bad argument");
   REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
+  if (n == 0) return DPBA_SUCCESS;
+  // The residual vectors (r -> t) of one reference frame are rows [phys_t] of one contiguous [16][max_pts] block.
+  // When every other frame is given, the rows are packed in the arena in device layout and sent with ONE copy per
+  // array (the row of r itself is never read by any kernel); otherwise row by row.
+  bool all = true;
+  int lo = PBA_MAXF, hi = -1;
+  for (int t = 0; t < h->n_frames; ++t) {
+    if (t != r && !per_target[t]) all = false;
+    lo = std::min(lo, h->fr[t].phys);
+    hi = std::max(hi, h->fr[t].phys);
+  }
+  const size_t mp = h->cfg.max_points_per_frame;
+  if (all && h->n_frames >= 2) {
+    const size_t rows = (size_t)(hi - lo + 1);
+    uint8_t* stg = (uint8_t*)arena_alloc(h, rows * mp);
+    if (!stg) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+    bool covered[PBA_MAXF] = {};
+    for (int t = 0; t < h->n_frames; ++t) {
+      covered[h->fr[t].phys - lo] = true;
+      if (t != r) memcpy(stg + (size_t)(h->fr[t].phys - lo) * mp, per_target[t], n);
+    }
+    bool dense = true;  // a freed physical slot inside [lo, hi] may belong to nobody: leave its rows alone
+    for (size_t k = 0; k < rows; ++k) dense = dense && covered[k];
+    if (dense) {
+      const size_t base = ((size_t)h->fr[r].phys * PBA_MAXF + lo) * mp;
+      CK(cudaMemcpyAsync(h->status + base, stg, rows * mp, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->cand + base, stg, rows * mp, cudaMemcpyHostToDevice, h->stream));
+      return DPBA_SUCCESS;
+    }
+  }
   for (int t = 0; t < h->n_frames; ++t) {
     if (t == r || !per_target[t]) continue;
     const int rc = set_statuses_row(h, r, t, n, per_target[t]);
@@ -802,13 +844,34 @@ int dpba_get_frame_statuses(dpba_handle* h, int32_t r, int32_t n, uint8_t* const
   REQUIRE(h, "null handle");
   REQUIRE(r >= 0 && r < h->n_frames, "bad argument");
   REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
-  for (int t = 0; t < h->n_frames && n; ++t) {
-    if (t == r) continue;
-    const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
-    if (statuses && statuses[t]) CK(cudaMemcpyAsync(statuses[t], h->status + base, n, cudaMemcpyDeviceToHost, h->stream));
-    if (candidates && candidates[t]) CK(cudaMemcpyAsync(candidates[t], h->cand + base, n, cudaMemcpyDeviceToHost, h->stream));
+  if (n == 0) return DPBA_SUCCESS;
+  CK(cudaStreamSynchronize(h->stream));  // empty the arena first: it must not wrap in the middle of this call
+  h->arena_used = 0;
+  // one copy per array for the whole [phys lo .. phys hi] row range of reference r, then scattered on the host
+  int lo = PBA_MAXF, hi = -1;
+  for (int t = 0; t < h->n_frames; ++t) {
+    lo = std::min(lo, h->fr[t].phys);
+    hi = std::max(hi, h->fr[t].phys);
+  }
+  const size_t mp = h->cfg.max_points_per_frame, rows = (size_t)(hi - lo + 1);
+  const size_t base = ((size_t)h->fr[r].phys * PBA_MAXF + lo) * mp;
+  uint8_t *ss = nullptr, *sc = nullptr;
+  if (statuses) {
+    if (!(ss = (uint8_t*)arena_alloc(h, rows * mp))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+    CK(cudaMemcpyAsync(ss, h->status + base, rows * mp, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (candidates) {
+    if (!(sc = (uint8_t*)arena_alloc(h, rows * mp))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+    CK(cudaMemcpyAsync(sc, h->cand + base, rows * mp, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
+  for (int t = 0; t < h->n_frames; ++t) {
+    if (t == r) continue;
+    const size_t off = (size_t)(h->fr[t].phys - lo) * mp;
+    if (ss && statuses[t]) memcpy(statuses[t], ss + off, n);
+    if (sc && candidates[t]) memcpy(candidates[t], sc + off, n);
+  }
+  h->arena_used = 0;
   return DPBA_SUCCESS;
 }
 
@@ -1347,10 +1410,14 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "fused_min_blocks")) {  // process-wide: 4 (64 registers per thread) or 3 (96)
+    pba::set_fused_min_blocks((int)value);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
   return fail(h, DPBA_E_INVALID, std::string("unknown option ") + name);
 }
 
-void dpba_debug_lm_clocks(long long* out) { pba::read_lm_clocks(out); }
 int64_t dpba_launch_count(void) { return (int64_t)pba::launch_count(); }
 
 int dpba_profile_enable(dpba_handle* h, int32_t on) {

@@ -56,7 +56,7 @@ struct WindowDev {
   int frame_marg[PBA_MAXF];  // LocalFrame::is_marginalized
   int phys[PBA_MAXF];        // logical slot -> physical storage slot
   int mask_all[PBA_MAXF];    // 1: the frame's mask has no zero, the lookup can be skipped
-  const float4* img[PBA_MAXF];     // {I, dx, dy, 0} per pixel
+  const float4* img[PBA_MAXF];     // per pixel x a 32-byte record {texel(x), texel(x+1)}, texel = {I, dx, dy, 0}
   const uint8_t* mask[PBA_MAXF];
   // landmark arrays, frame f at [phys[f] * max_pts, phys[f] * max_pts + n_lm[f])
   float4* lmk;             // {u, v, idepth, idepth at the FEJ linearisation point}: one LDG.128 per landmark
@@ -129,7 +129,9 @@ void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int 
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
                     const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s);
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
-void launch_pack_image(const float* src3, float4* dst, int n_px, cudaStream_t s);
+void launch_clear_frame_rows(uint8_t* status, uint8_t* cand, uint8_t* jac_valid, float* energy, int phys, int mp,
+                             int max_frames, cudaStream_t s);
+void launch_pack_image(const float* src3, float4* dst, int n_px, int W, cudaStream_t s);
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s);
 int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* e_part, cudaStream_t s,
                           const LmCtl* ctl = nullptr, int ctl_mode = 0);
@@ -156,9 +158,9 @@ void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cud
 void launch_first_estimate(const WindowDev& w, cudaStream_t s);  // K6: idepth snapshot + reprojection_jacobians_valid
 void launch_apply_point_statuses(const WindowDev& w, float threshold, int min_valid, const float* pair_dist,
                                  cudaStream_t s);
-void read_lm_clocks(long long* out);
 int sm_count();
 long long launch_count();
 void add_launches(long long n);
 void set_schur_mma(bool on);
+void set_fused_min_blocks(int b);
 }  // namespace pba

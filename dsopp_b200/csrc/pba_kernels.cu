@@ -104,6 +104,19 @@ __device__ __forceinline__ bool lm_skip(const LmCtl* ctl, int mode) {
   return mode == 2 && ctl->system_valid;
 }
 
+// MUFU.RSQ / MUFU.RCP (<= 2 ulp) without the denormal fix-up code of rsqrtf() / 1.f / x; used only where no connection
+// status depends on the result (Huber weight, Jacobians)
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct LandmarkIn {
   float u, v, rho, rho0, patch;
   int flags;
@@ -121,6 +134,19 @@ struct PixelOut {
 };
 
 __device__ __forceinline__ float4 ldf4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// sm_100 256-bit global accesses (LDG.E.256 / STG.E.256): one instruction per 32-byte record.  The address must be
+// 32-byte aligned.
+__device__ __forceinline__ void ldg256_nc(const float4* p, float4& a, float4& b) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+}
+__device__ __forceinline__ void stg256_cs(float* p, const float (&v)[8]) {  // streaming (evict-first) store
+  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 
 // row of a 3x4 matrix applied to [u, v, 1, rho] with the reference's association
 // (A[:, :2] uv) + (A[:,2] + A[:,3] rho)   (camera_reproject.hpp:283-284,323-325), no FMA contraction
@@ -194,17 +220,21 @@ __device__ __forceinline__ void eval_pixel(const PairConst& pc, const LandmarkIn
   const float dx = su - (float)ix, dy = sv - (float)iy;
   const float dxdy = dx * dy;
   const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1.f - dx - dy + dxdy;
-  const float4* p = img + (size_t)iy * W + ix;
-  const float4 t00 = __ldg(p), t01 = __ldg(p + 1), t10 = __ldg(p + W), t11 = __ldg(p + W + 1);
+  // the image is stored as 32-byte records {texel(x), texel(x + 1)}: the two horizontal taps of a row are ONE
+  // 256-bit load (half the gather instructions and L1 wavefronts of four 128-bit loads)
+  const float4* p = img + ((size_t)iy * W + ix) * 2;
+  float4 t00, t01, t10, t11;
+  ldg256_nc(p, t00, t01);
+  ldg256_nc(p + 2 * (size_t)W, t10, t11);
   const float I = w11 * t11.x + w10 * t10.x + w01 * t01.x + w00 * t00.x;
   // r = (I_t - b_t) - s (patch - b_r), evaluate_jacobians.hpp:124-135
   const float r = ev ? (I - pc.b_t) - pc.s * (lm.patch - pc.b_r) : 0.f;
   const float n2 = group_sum(r * r);
   float e = 0.5f * n2, wgt = 1.f;
-  if (huber && n2 > sigma * sigma) {  // evaluate_jacobians.hpp:139-146
-    const float nrm = sqrtf(n2);
-    wgt = sigma / nrm;
-    e = sigma * nrm - sigma * sigma * 0.5f;
+  if (huber && n2 > sigma * sigma) {  // evaluate_jacobians.hpp:139-146; MUFU.RSQ (2 ulp) instead of IEEE sqrt + divide
+    const float rn = rsqrt_approx(n2);
+    wgt = sigma * rn;
+    e = sigma * (n2 * rn) - sigma * sigma * 0.5f;
   }
   o.r = r;
   o.e = ev ? e : 0.f;
@@ -213,7 +243,7 @@ __device__ __forceinline__ void eval_pixel(const PairConst& pc, const LandmarkIn
     const float dIu = w11 * t11.y + w10 * t10.y + w01 * t01.y + w00 * t00.y;
     const float dIv = w11 * t11.z + w10 * t10.z + w01 * t01.z + w00 * t00.z;
     // camera_reproject.hpp:339-365
-    const float sI = __frcp_rn(ev ? qz : 1.f);
+    const float sI = rcp_approx(ev ? qz : 1.f);  // Jacobians only (no status depends on it): MUFU.RCP
     const float b0 = qx * sI, b1 = qy * sI;
     const float nid = rho_j * sI;
     const float* tt = FEJ ? pc.t0 : pc.tr;
@@ -292,56 +322,95 @@ __global__ void __launch_bounds__(256) k_first_estimate(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: residual-only sweep + energy reduction.  grid = (chunks of 32 landmarks, ordered pairs)
+// K2: residual-only sweep + energy reduction.  grid = (landmark chunks, host frames), one warp per target frame (the
+// shape of the fused linearise): the chunk's landmark records are staged in shared memory once and shared by all
+// target warps, the pair constants once per warp, and every CTA leaves ONE (energy, n_valid) partial -- ~6x fewer
+// CTAs, prologues and partials than one CTA per (32 landmarks, ordered pair).
 // ------------------------------------------------------------------------------------------------
+struct __align__(16) LandmarkRec {  // 64 bytes
+  float4 k;        // u, v, idepth, idepth at the FEJ point
+  float patch[8];
+  float step;
+  int flags;
+  float pad0, pad1;
+};
+
 template <bool FEJ>
-__global__ void __launch_bounds__(256) k_residual_sweep(const __grid_constant__ WindowDev w, float sigma, int huber,
-                                                        double2* __restrict__ part, const LmCtl* __restrict__ ctl,
-                                                        int ctl_mode) {
+__global__ void __launch_bounds__(480) k_residual_sweep(const __grid_constant__ WindowDev w, float sigma, int huber,
+                                                        int lpb, double2* __restrict__ part,
+                                                        const LmCtl* __restrict__ ctl, int ctl_mode) {
   if (lm_skip(ctl, ctl_mode)) return;
+  extern __shared__ __align__(16) float smem[];
   // every CTA owns one slot of `part` (energy, n_valid): no same-address atomics, deterministic sum afterwards
   double2* my_part = part + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-  __shared__ PairConst pcs;
-  __shared__ float s_e[8];
-  __shared__ int s_n[8];
   const int N = w.n_frames;
-  const int r = blockIdx.y / (N - 1);
-  int t = blockIdx.y % (N - 1);
-  t += (t >= r);
-  const int M = w.n_lm[r];
-  if ((int)blockIdx.x * 32 >= M) {
+  const int f = blockIdx.y;
+  const int M = w.n_lm[f];
+  const int l0 = blockIdx.x * lpb;
+  if (l0 >= M) {
     if (threadIdx.x == 0) *my_part = make_double2(0.0, 0.0);
     return;
   }
-  if (threadIdx.x < 32)
-    reinterpret_cast<float4*>(&pcs)[threadIdx.x] = reinterpret_cast<const float4*>(&w.pairs[r * PBA_MAXF + t])[threadIdx.x];
+  const int nwarps = N - 1;
+  PairConst* pcs = reinterpret_cast<PairConst*>(smem);                                   // [nwarps]
+  LandmarkRec* recs = reinterpret_cast<LandmarkRec*>(smem + (size_t)nwarps * (sizeof(PairConst) / 4));  // [lpb]
+  float* s_e = reinterpret_cast<float*>(recs + lpb);                                     // [nwarps]
+  int* s_n = reinterpret_cast<int*>(s_e + nwarps);                                       // [nwarps]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int px = lane & 7, grp = lane >> 3;
+  const int t = warp + (warp >= f);
+  const int lm_base = lm_index(w, f, 0);
+  reinterpret_cast<float4*>(&pcs[warp])[lane] = reinterpret_cast<const float4*>(&w.pairs[f * PBA_MAXF + t])[lane];
+  for (int i = threadIdx.x; i < lpb; i += blockDim.x) {
+    const int l = min(l0 + i, M - 1);
+    const int gl = lm_base + l;
+    LandmarkRec r;
+    r.k = w.lmk[gl];
+    const float4 p0 = ldf4(w.patch + (size_t)gl * 8), p1 = ldf4(w.patch + (size_t)gl * 8 + 4);
+    r.patch[0] = p0.x, r.patch[1] = p0.y, r.patch[2] = p0.z, r.patch[3] = p0.w;
+    r.patch[4] = p1.x, r.patch[5] = p1.y, r.patch[6] = p1.z, r.patch[7] = p1.w;
+    r.step = w.idepth_step[gl];
+    r.flags = w.flags[gl];
+    r.pad0 = r.pad1 = 0.f;
+    recs[i] = r;
+  }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
-  const int px = lane & 7;
+  const PairConst& pc = pcs[warp];
+  const float4* img = w.img[t];
+  const uint8_t* mask = w.mask_all[t] ? nullptr : w.mask[t];
+  const float pox = pat_x(px), poy = pat_y(px);
+  const size_t res_base = res_index(w, f, t, 0);
   float e_acc = 0.f;
   int n_acc = 0;
-  const bool inb = l < M;
-  const int gl = lm_index(w, r, inb ? l : 0);
-  LandmarkIn lm = load_landmark(w, gl, px);
-  const bool skip = !inb || ((lm.flags & LM_MARG) && !(lm.flags & LM_TO_MARG));  // evaluate_jacobians.hpp:83
-  const size_t res = res_index(w, r, t, inb ? l : 0);
-  const int status = skip ? K_OUTLIER : w.status[res];
-  const bool jv = FEJ ? (w.jac_valid[res] != 0) : true;
-  if (skip) lm.rho = -1.f;  // forces !ok
-  PixelOut o;
-  eval_pixel<FEJ, false>(pcs, lm, jv, w.img[t], w.mask_all[t] ? nullptr : w.mask[t], w.W, w.H, status, sigma, huber, lane,
-                         pat_x(px), pat_y(px), o);
-  if (!skip && px == 0) {
-    if (!o.ok) w.cand[res] = K_OOB;   // evaluate_jacobians.hpp:111-113
-    else if (o.ev) w.cand[res] = K_OK;  // :115
-    w.energy[res] = o.e;
-    if (!(lm.flags & LM_MARG)) {  // calculateLandmarksEnergy, problem.hpp:124-133
-      e_acc = o.e;
-      n_acc = o.e > 0.f;
+  for (int it = 0; it < lpb; it += 4) {
+    const int ls = it + grp;
+    const int l = l0 + ls;
+    const bool inb = ls < lpb && l < M;
+    const LandmarkRec& rec = recs[inb ? ls : 0];
+    LandmarkIn lm;
+    lm.u = rec.k.x;
+    lm.v = rec.k.y;
+    lm.rho = rec.k.z + rec.step;
+    lm.rho0 = rec.k.w;
+    lm.patch = rec.patch[px];
+    lm.flags = rec.flags;
+    const bool skip = !inb || ((lm.flags & LM_MARG) && !(lm.flags & LM_TO_MARG));  // evaluate_jacobians.hpp:83
+    const size_t res = res_base + (inb ? l : 0);
+    const int status = skip ? K_OUTLIER : w.status[res];
+    const bool jv = FEJ ? (w.jac_valid[res] != 0) : true;
+    if (skip) lm.rho = -1.f;  // forces !ok
+    PixelOut o;
+    eval_pixel<FEJ, false>(pc, lm, jv, img, mask, w.W, w.H, status, sigma, huber, lane, pox, poy, o);
+    if (!skip && px == 0) {
+      if (!o.ok) w.cand[res] = K_OOB;   // evaluate_jacobians.hpp:111-113
+      else if (o.ev) w.cand[res] = K_OK;  // :115
+      w.energy[res] = o.e;
+      if (!(lm.flags & LM_MARG)) {  // calculateLandmarksEnergy, problem.hpp:124-133
+        e_acc += o.e;
+        n_acc += o.e > 0.f;
+      }
     }
   }
-  // block reduction -> one fp64 atomic per block
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     e_acc += __shfl_xor_sync(FULL, e_acc, s);
@@ -355,7 +424,7 @@ __global__ void __launch_bounds__(256) k_residual_sweep(const __grid_constant__ 
   if (threadIdx.x == 0) {
     double e = 0;
     int n = 0;
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < nwarps; ++i) {
       e += (double)s_e[i];
       n += s_n[i];
     }
@@ -427,69 +496,77 @@ __global__ void __launch_bounds__(1024) k_reduce_scal(const LmCtl* __restrict__ 
 // Per patch-residual: 146 floats written (r[8], J_ref[8x8], J_tgt[8x8], d_idepth[8], w, e) + statuses.
 // ------------------------------------------------------------------------------------------------
 template <bool FEJ>
-__global__ void __launch_bounds__(256) k_materialise_sweep(const __grid_constant__ WindowDev w, float sigma, int huber) {
+__global__ void __launch_bounds__(256) k_materialise_sweep(const __grid_constant__ WindowDev w, float sigma, int huber,
+                                                           int subs) {
   __shared__ PairConst pcs;
   const int N = w.n_frames;
   const int r = blockIdx.y / (N - 1);
   int t = blockIdx.y % (N - 1);
   t += (t >= r);
   const int M = w.n_lm[r];
-  if ((int)blockIdx.x * 32 >= M) return;
+  if ((int)blockIdx.x * 32 * subs >= M) return;
   if (threadIdx.x < 32)
     reinterpret_cast<float4*>(&pcs)[threadIdx.x] = reinterpret_cast<const float4*>(&w.pairs[r * PBA_MAXF + t])[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
   const int px = lane & 7;
-  const bool inb = l < M;
-  const int gl = lm_index(w, r, inb ? l : 0);
-  LandmarkIn lm = load_landmark(w, gl, px);
-  const bool skip = !inb || ((lm.flags & LM_MARG) && !(lm.flags & LM_TO_MARG));
-  const size_t res = res_index(w, r, t, inb ? l : 0);
-  const int status = skip ? K_OUTLIER : w.status[res];
-  const bool jv = FEJ ? (w.jac_valid[res] != 0) : true;
-  if (skip) lm.rho = -1.f;
-  PixelOut o;
-  eval_pixel<FEJ, true>(pcs, lm, jv, w.img[t], w.mask_all[t] ? nullptr : w.mask[t], w.W, w.H, status, sigma, huber, lane,
-                        pat_x(px), pat_y(px), o);
-  if (skip) return;
-  if (px == 0) {
-    if (!o.ok) w.cand[res] = K_OOB;
-    else if (o.ev) w.cand[res] = K_OK;
-    w.energy[res] = o.e;
-    if (o.ev) w.m_w[res] = o.w;  // huber_weight is left untouched when not evaluated (evaluate_jacobians.hpp:184-194)
-  }
-  w.m_r[res * 8 + px] = o.r;
-  w.m_did[res * 8 + px] = o.d;
+  const float pox = pat_x(px), poy = pat_y(px);
+  const float4* img = w.img[t];
+  const uint8_t* mask = w.mask_all[t] ? nullptr : w.mask[t];
   const float* adj = FEJ ? pcs.adj0 : pcs.adj;
-  float jr[8], jt[8];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) jr[j] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {  // J_ref[:,0:6] = Jg Adj  (:162-163); rows of Adj as float2 pairs from shared memory
-    const float2 a0 = *reinterpret_cast<const float2*>(adj + k * 6);
-    const float2 a1 = *reinterpret_cast<const float2*>(adj + k * 6 + 2);
-    const float2 a2 = *reinterpret_cast<const float2*>(adj + k * 6 + 4);
-    jr[0] += o.g[k] * a0.x;
-    jr[1] += o.g[k] * a0.y;
-    jr[2] += o.g[k] * a1.x;
-    jr[3] += o.g[k] * a1.y;
-    jr[4] += o.g[k] * a2.x;
-    jr[5] += o.g[k] * a2.y;
-  }
-#pragma unroll
-  for (int j = 0; j < 6; ++j) jt[j] = -o.g[j];  // J_tgt[:,0:6] = -Jg leftLog (= I)  (:159-160)
   const float sp = FEJ ? pcs.s0 : pcs.s;  // d_reference_affineBrightnessShift (:95,107)
-  jr[6] = o.c;
-  jr[7] = o.ev ? sp : 0.f;
-  jt[6] = -o.c;
-  jt[7] = o.ev ? -1.f : 0.f;
-  float4* pr = reinterpret_cast<float4*>(w.m_jref + res * 64 + px * 8);
-  float4* pt = reinterpret_cast<float4*>(w.m_jtgt + res * 64 + px * 8);
-  __stcs(pr, make_float4(jr[0], jr[1], jr[2], jr[3]));  // streaming stores: written once, never re-read here
-  __stcs(pr + 1, make_float4(jr[4], jr[5], jr[6], jr[7]));
-  __stcs(pt, make_float4(jt[0], jt[1], jt[2], jt[3]));
-  __stcs(pt + 1, make_float4(jt[4], jt[5], jt[6], jt[7]));
+  const int lm_base = lm_index(w, r, 0);
+  const size_t res_base = res_index(w, r, t, 0);
+  // a CTA walks `subs` consecutive groups of 32 landmarks of its pair: the pair constants are staged once
+  // (fetching group k+1 while group k is sampled was tried: the extra registers cost more occupancy than the
+  // saved round trip gains -- 0.51 -> 0.48 of the HBM roofline at 1.12 M units)
+  for (int sub = 0; sub < subs; ++sub) {
+    const int l = (blockIdx.x * subs + sub) * 32 + (threadIdx.x >> 3);
+    if ((l & ~31) >= M) break;  // uniform over the CTA
+    const bool inb = l < M;
+    const int li = inb ? l : 0;
+    LandmarkIn lm = load_landmark(w, lm_base + li, px);
+    const bool skip = !inb || ((lm.flags & LM_MARG) && !(lm.flags & LM_TO_MARG));
+    const size_t res = res_base + li;
+    const int status = skip ? K_OUTLIER : w.status[res];
+    const bool jv = FEJ ? (w.jac_valid[res] != 0) : true;
+    if (skip) lm.rho = -1.f;
+    PixelOut o;
+    eval_pixel<FEJ, true>(pcs, lm, jv, img, mask, w.W, w.H, status, sigma, huber, lane, pox, poy, o);
+    if (skip) continue;
+    if (px == 0) {
+      if (!o.ok) w.cand[res] = K_OOB;
+      else if (o.ev) w.cand[res] = K_OK;
+      w.energy[res] = o.e;
+      if (o.ev) w.m_w[res] = o.w;  // huber_weight is left untouched when not evaluated (evaluate_jacobians.hpp:184-194)
+    }
+    __stcs(w.m_r + res * 8 + px, o.r);
+    __stcs(w.m_did + res * 8 + px, o.d);
+    float jr[8], jt[8];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) jr[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {  // J_ref[:,0:6] = Jg Adj  (:162-163); rows of Adj as float2 pairs from shared memory
+      const float2 a0 = *reinterpret_cast<const float2*>(adj + k * 6);
+      const float2 a1 = *reinterpret_cast<const float2*>(adj + k * 6 + 2);
+      const float2 a2 = *reinterpret_cast<const float2*>(adj + k * 6 + 4);
+      jr[0] += o.g[k] * a0.x;
+      jr[1] += o.g[k] * a0.y;
+      jr[2] += o.g[k] * a1.x;
+      jr[3] += o.g[k] * a1.y;
+      jr[4] += o.g[k] * a2.x;
+      jr[5] += o.g[k] * a2.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) jt[j] = -o.g[j];  // J_tgt[:,0:6] = -Jg leftLog (= I)  (:159-160)
+    jr[6] = o.c;
+    jr[7] = o.ev ? sp : 0.f;
+    jt[6] = -o.c;
+    jt[7] = o.ev ? -1.f : 0.f;
+    // one 256-bit streaming store per Jacobian row: a warp writes 1 KB contiguous per instruction
+    stg256_cs(w.m_jref + res * 64 + px * 8, jr);
+    stg256_cs(w.m_jtgt + res * 64 + px * 8, jt);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -506,8 +583,8 @@ __global__ void __launch_bounds__(256) k_materialise_sweep(const __grid_constant
 // time keeping its pair's 44 running sums in registers, so the per-landmark quantities that couple the targets
 // (H_pd, H_dd, b_d) meet in shared memory.
 // ------------------------------------------------------------------------------------------------
-template <bool FEJ, int NWMAX>
-__global__ void __launch_bounds__(32 * NWMAX, NWMAX <= 8 ? 4 : 2)
+template <bool FEJ, int NWMAX, int MINB>
+__global__ void __launch_bounds__(32 * NWMAX, MINB)
     k_linearize_fused(const __grid_constant__ WindowDev w, float sigma, int huber, int for_marg, int lpb,
                       float* __restrict__ core_part, float* __restrict__ schur_part, const LmCtl* __restrict__ ctl) {
   if (lm_skip(ctl, 2)) return;
@@ -521,13 +598,15 @@ __global__ void __launch_bounds__(32 * NWMAX, NWMAX <= 8 ? 4 : 2)
   const int nwarps = N - 1;
   PairConst* pcs = reinterpret_cast<PairConst*>(smem);               // [nwarps]
   float* hpd_s = smem + (size_t)nwarps * (sizeof(PairConst) / 4);    // [lpb][D]
-  float* hdd_s = hpd_s + lpb * D;                                    // [lpb]
-  float* bd_s = hdd_s + lpb;                                         // [lpb]
+  float* hdd_s = hpd_s + lpb * D;                                    // [lpb] Schur weight 1/H_dd after the finalise
+  float* bd_s = hdd_s + lpb;                                         // [lpb] weight * b_d
+  float* hdd_w = bd_s + lpb;                                         // [lpb][nwarps] per-target H_dd terms
+  float* bd_w = hdd_w + lpb * nwarps;                                // [lpb][nwarps] per-target b_d terms
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int px = lane & 7, grp = lane >> 3;
   const int t = warp + (warp >= f);
 
-  for (int i = threadIdx.x; i < lpb * (D + 2); i += blockDim.x) hpd_s[i] = 0.f;
+  for (int i = threadIdx.x; i < lpb * (D + 2 + 2 * nwarps); i += blockDim.x) hpd_s[i] = 0.f;
   reinterpret_cast<float4*>(&pcs[warp])[lane] = reinterpret_cast<const float4*>(&w.pairs[f * PBA_MAXF + t])[lane];
   __syncthreads();
   const PairConst& pc = pcs[warp];
@@ -537,9 +616,9 @@ __global__ void __launch_bounds__(32 * NWMAX, NWMAX <= 8 ? 4 : 2)
   const int lm_base = lm_index(w, f, 0);
   const size_t res_base = res_index(w, f, t, 0);
 
-  float acc[PBA_CORE];
+  float acc[44];  // 36 (upper triangle of the core) + 8 (core^T r); padded to PBA_CORE only for the final reduction
 #pragma unroll
-  for (int k = 0; k < PBA_CORE; ++k) acc[k] = 0.f;
+  for (int k = 0; k < 44; ++k) acc[k] = 0.f;
 
   for (int it = 0; it < lpb; it += 4) {
     const int ls = it + grp;  // slot in the chunk
@@ -589,17 +668,19 @@ __global__ void __launch_bounds__(32 * NWMAX, NWMAX <= 8 ? 4 : 2)
     const float bd = group_sum(wd * o.r);
     if (sel) {
       hpd_s[ls * D + 8 * t + px] = -P;  // this warp is the only writer of target block t
-      if (px == 0) {
-        atomicAdd(&hdd_s[ls], hdd);
-        atomicAdd(&bd_s[ls], bd);
+      if (px == 0) {  // own slot per target warp, summed in a fixed order below: bit-reproducible runs
+        hdd_w[ls * nwarps + warp] = hdd;
+        bd_w[ls * nwarps + warp] = bd;
       }
     }
   }
 
   // warp-wide transpose-reduce of the 44(48) running sums: 24+12+6+3+2 = 47 shuffles, then <= 2 stores per lane
   {
-    float v24[24], v12[12], v6[6], v3[3], v2[2];
-    tr_step<48, 16>(acc, v24, lane);
+    float v48[PBA_CORE], v24[24], v12[12], v6[6], v3[3], v2[2];
+#pragma unroll
+    for (int k = 0; k < PBA_CORE; ++k) v48[k] = k < 44 ? acc[k] : 0.f;
+    tr_step<48, 16>(v48, v24, lane);
     tr_step<24, 8>(v24, v12, lane);
     tr_step<12, 4>(v12, v6, lane);
     tr_step<6, 2>(v6, v3, lane);
@@ -647,8 +728,11 @@ __global__ void __launch_bounds__(32 * NWMAX, NWMAX <= 8 ? 4 : 2)
       const bool skip = (fl & LM_MARG) && !(fl & LM_TO_MARG);
       const bool sel = !skip && (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0);
       if (sel) {
-        float hdd = hdd_s[ls];
-        const float bd = bd_s[ls];
+        float hdd = 0.f, bd = 0.f;
+        for (int wi = 0; wi < nwarps; ++wi) {
+          hdd += hdd_w[ls * nwarps + wi];
+          bd += bd_w[ls * nwarps + wi];
+        }
         w.b_d[gl] = bd;
         if (hdd > 1e-15f) {
           if (for_marg && w.fixed[f]) hdd += 1e8f;  // kScaleNullspaceRegularizer
@@ -1729,17 +1813,34 @@ __global__ void __launch_bounds__(64) k_pair_setup(const FrameParams* __restrict
   }
 }
 
-// {I,dx,dy} float3 -> float4 texels
-__global__ void k_pack_image(const float* __restrict__ src, float4* __restrict__ dst, int n) {
+// residual vectors of a freshly pushed frame: rows (phys -> p) and (p -> phys) of status / cand / jac_valid / energy := 0
+// (ResidualPoint ctor, local_frame.hpp:212-219).  grid = (ceil(mp / 256), max_frames, 2)
+__global__ void k_clear_frame_rows(uint8_t* __restrict__ status, uint8_t* __restrict__ cand,
+                                   uint8_t* __restrict__ jac_valid, float* __restrict__ energy, int phys, int mp) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= mp) return;
+  const int p = blockIdx.y;
+  const size_t row = blockIdx.z ? (size_t)(p * PBA_MAXF + phys) : (size_t)(phys * PBA_MAXF + p);
+  const size_t i = row * mp + l;
+  status[i] = 0;
+  cand[i] = 0;
+  jac_valid[i] = 0;
+  energy[i] = 0.f;
+}
+
+// Device image layout: per pixel x a 32-byte record {texel(x), texel(x + 1)}, texel = {I, dx, dy, 0} (the right
+// neighbour is clamped at the last column, which the 4-pixel ROI border keeps from ever being sampled).
+// {I,dx,dy} float3 -> records
+__global__ void k_pack_image(const float* __restrict__ src, float4* __restrict__ dst, int n, int W) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+  if (i >= n) return;
+  const int j = ((i % W) == W - 1) ? i : i + 1;
+  dst[2 * (size_t)i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+  dst[2 * (size_t)i + 1] = make_float4(src[3 * j], src[3 * j + 1], src[3 * j + 2], 0.f);
 }
 
 // gradient packing from the intensity plane, features/src/calculate_pixelinfo.cpp:340-374
-__global__ void k_pixelinfo(const float* __restrict__ I, float4* __restrict__ dst, int W, int H) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= W || y >= H) return;
+__device__ __forceinline__ float4 pixelinfo_at(const float* __restrict__ I, int x, int y, int W, int H) {
   const float c = I[y * W + x];
   float dx, dy;
   if (x == 0) dx = 1.0f * (I[y * W + 1] - c);
@@ -1747,7 +1848,14 @@ __global__ void k_pixelinfo(const float* __restrict__ I, float4* __restrict__ ds
   else dx = 0.5f * (I[y * W + x + 1] - I[y * W + x - 1]);
   const int yu = y == 0 ? y : y - 1, yb = y == H - 1 ? y : y + 1;
   dy = ((y == 0 || y == H - 1) ? 1.0f : 0.5f) * (I[yb * W + x] - I[yu * W + x]);
-  dst[y * W + x] = make_float4(c, dx, dy, 0.f);
+  return make_float4(c, dx, dy, 0.f);
+}
+__global__ void k_pixelinfo(const float* __restrict__ I, float4* __restrict__ dst, int W, int H) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  dst[2 * ((size_t)y * W + x)] = pixelinfo_at(I, x, y, W, H);
+  dst[2 * ((size_t)y * W + x) + 1] = pixelinfo_at(I, min(x + 1, W - 1), y, W, H);
 }
 
 
@@ -1931,17 +2039,13 @@ __device__ __forceinline__ double rcp64(double d) {
   return d == 0.0 ? 0.0 : 1.0 / d;
 }
 
-__device__ long long g_lmclk[16];
-#define LMCLK(i) do { if (threadIdx.x == 0) g_lmclk[i] = clock64(); } while (0)
 template <int DP>
 __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
                                                  const int* fixed, int N, const double* __restrict__ Hp,
                                                  const double* __restrict__ bp, const double* __restrict__ Hs,
                                                  const double* __restrict__ bs, const double* __restrict__ Hmarg,
                                                  const double* __restrict__ bmarg, double* __restrict__ step_dev) {
-  LMCLK(0);
   if (ctl->done) return;
-  LMCLK(1);
   constexpr int LD = DP + 1;   // row stride of S (odd: conflict-free column walks)
   constexpr int LPS = 9;       // row stride of Lp
   extern __shared__ double sh[];
@@ -1966,7 +2070,6 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
     }
   }
   // unscaled system:  H_pose(+priors, +lambda on the diagonal) + H_marg - H_schur / (1 + lambda)
-  LMCLK(2);
   if (tid < D) {
     const size_t idx = (size_t)tid * D + tid;
     const int f = tid / 8, k = tid % 8;
@@ -1979,7 +2082,6 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
     pre[tid] = 1.0 / sqrt(v + 10.0);      // jacobiPreconditioner, +10 floor
   }
   __syncthreads();
-  LMCLK(3);
   // fill the lower triangle: 8 independent (Hp, Hs[, Hmarg]) loads in flight per thread per trip, so the fill costs
   // a few L2 round trips instead of one per element
   for (int base = 0; base < D * D; base += 256 * 8) {
@@ -2007,12 +2109,9 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
     if (Hmarg) b += bmarg[tid] + hm[tid];
     S[D * LD + tid] = b * pre[tid];
   }
-
-  LMCLK(4);
   const int ty = tid >> 4, tx = tid & 15;
   for (int kb = 0; kb < D; kb += 8) {
     __syncthreads();
-    if (kb == 8) LMCLK(5);
     const int i = kb + tid;  // this thread's row (row D is the right-hand side)
     const bool act = i <= D;
     // the 8x8 diagonal block, packed lower triangle g[r (r + 1) / 2 + c], factored redundantly by every thread
@@ -2072,7 +2171,6 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
     }
   }
   __syncthreads();
-  LMCLK(6);
   if (tid < D) st[tid] = S[D * LD + tid] * dinv[tid];  // z = D^-1 L^-1 b
   // blocked back substitution L^T x = z, l_ki = x_ki / d_i: every thread solves the 8x8 triangle of the block
   // redundantly in registers, then row i < kb subtracts the block's contribution -- one barrier per 8 unknowns
@@ -2099,7 +2197,6 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
     }
   }
   __syncthreads();
-  LMCLK(7);
   if (tid < D) {
     const double x = hm[tid] * pre[tid];
     step_dev[tid] = x;
@@ -2154,7 +2251,6 @@ void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int 
                                 reinterpret_cast<const double2*>(n_part), n_n);
 }
 
-void read_lm_clocks(long long* out) { cudaMemcpyFromSymbol(out, g_lmclk, sizeof(long long) * 16); }
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
                     const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s) {
   const int D = 8 * N;
@@ -2177,9 +2273,15 @@ void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs
   k_pair_setup<<<n_frames, 64, 0, s>>>(frames, n_frames, pairs, pasm);
 }
 
-void launch_pack_image(const float* src3, float4* dst, int n_px, cudaStream_t s) {
+void launch_clear_frame_rows(uint8_t* status, uint8_t* cand, uint8_t* jac_valid, float* energy, int phys, int mp,
+                             int max_frames, cudaStream_t s) {
   ++g_launches;
-  k_pack_image<<<(n_px + 255) / 256, 256, 0, s>>>(src3, dst, n_px);
+  k_clear_frame_rows<<<dim3((mp + 255) / 256, max_frames, 2), 256, 0, s>>>(status, cand, jac_valid, energy, phys, mp);
+}
+
+void launch_pack_image(const float* src3, float4* dst, int n_px, int W, cudaStream_t s) {
+  ++g_launches;
+  k_pack_image<<<(n_px + 255) / 256, 256, 0, s>>>(src3, dst, n_px, W);
 }
 
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s) {
@@ -2192,10 +2294,17 @@ int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, d
                           const LmCtl* ctl, int ctl_mode) {
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return 0;
-  dim3 g((m + 31) / 32, w.n_frames * (w.n_frames - 1));
+  const int N = w.n_frames;
+  // landmarks per CTA: fill the machine once (threads of N - 1 warps, up to 2048 resident per SM)
+  const int threads = 32 * (N - 1);
+  const int resident = sm_count() * std::max(1, 2048 / threads);
+  int lpb = 8;
+  while (lpb < 256 && (long)((m + lpb - 1) / lpb) * N > resident) lpb += 4;
+  dim3 g((m + lpb - 1) / lpb, N);
+  const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + (size_t)lpb * sizeof(LandmarkRec) + (size_t)(N - 1) * 8;
   ++g_launches;
-  if (fej) k_residual_sweep<true><<<g, 256, 0, s>>>(w, sigma, huber, reinterpret_cast<double2*>(part), ctl, ctl_mode);
-  else k_residual_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber, reinterpret_cast<double2*>(part), ctl, ctl_mode);
+  if (fej) k_residual_sweep<true><<<g, threads, smem, s>>>(w, sigma, huber, lpb, reinterpret_cast<double2*>(part), ctl, ctl_mode);
+  else k_residual_sweep<false><<<g, threads, smem, s>>>(w, sigma, huber, lpb, reinterpret_cast<double2*>(part), ctl, ctl_mode);
   return (int)(g.x * g.y);  // partial slots written
 }
 
@@ -2209,24 +2318,29 @@ void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, in
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s) {
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return;
-  dim3 g((m + 31) / 32, w.n_frames * (w.n_frames - 1));
+  // groups of 32 landmarks per CTA: 1 for small windows (more CTAs than one wave needs), up to 8 for large ones
+  const int subs = std::max(1, std::min(8, m / 2048));
+  dim3 g((m + 32 * subs - 1) / (32 * subs), w.n_frames * (w.n_frames - 1));
   ++g_launches;
-  if (fej) k_materialise_sweep<true><<<g, 256, 0, s>>>(w, sigma, huber);
-  else k_materialise_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber);
+  if (fej) k_materialise_sweep<true><<<g, 256, 0, s>>>(w, sigma, huber, subs);
+  else k_materialise_sweep<false><<<g, 256, 0, s>>>(w, sigma, huber, subs);
 }
 
-template <int NWMAX>
+int g_fused_minb = 3;  // resident CTAs per SM the fused linearise is compiled for (N <= 9): 4 -> 64 registers, 3 -> 80
+void set_fused_min_blocks(int b) { g_fused_minb = b <= 3 ? 3 : 4; }
+
+template <int NWMAX, int MINB>
 static void launch_fused_t(const WindowDev& w, float sigma, int huber, int fej, int for_marg, int lpb, dim3 g,
                            int threads, size_t smem, float* core, float* schur, cudaStream_t s, const LmCtl* ctl) {
   static bool attr[2] = {false, false};
   if (smem > 48 * 1024 && !attr[fej ? 1 : 0]) {
-    if (fej) cudaFuncSetAttribute(k_linearize_fused<true, NWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    else cudaFuncSetAttribute(k_linearize_fused<false, NWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (fej) cudaFuncSetAttribute(k_linearize_fused<true, NWMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    else cudaFuncSetAttribute(k_linearize_fused<false, NWMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr[fej ? 1 : 0] = true;
   }
   ++g_launches;
-  if (fej) k_linearize_fused<true, NWMAX><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl);
-  else k_linearize_fused<false, NWMAX><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl);
+  if (fej) k_linearize_fused<true, NWMAX, MINB><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl);
+  else k_linearize_fused<false, NWMAX, MINB><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl);
 }
 
 FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
@@ -2237,7 +2351,8 @@ FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, in
   const int N = w.n_frames, D = 8 * N;
   // landmarks per CTA: the candidate whose wave count times per-CTA work (lpb/4 loop trips + the fixed prologue /
   // epilogue, worth ~1.5 trips) is smallest -- small windows want many small CTAs, large ones amortise the epilogue
-  const int resident = sm_count() * (N <= 9 ? 4 : 2);
+  const int minb = N <= 9 ? g_fused_minb : 2;
+  const int resident = sm_count() * minb;
   int lpb = 16;
   double best = 1e30;
   for (int cand = 8; cand <= 64; cand += 4) {
@@ -2249,11 +2364,12 @@ FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, in
       lpb = cand;
     }
   }
-  const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + (size_t)lpb * (D + 2) * sizeof(float);
+  const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + (size_t)lpb * (D + 2 + 2 * (N - 1)) * sizeof(float);
   dim3 g((m + lpb - 1) / lpb, N);
   const int threads = 32 * (N - 1);
-  if (N <= 9) launch_fused_t<8>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
-  else launch_fused_t<15>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
+  if (N <= 9 && minb == 4) launch_fused_t<8, 4>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
+  else if (N <= 9) launch_fused_t<8, 3>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
+  else launch_fused_t<15, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
   shape.lpb = lpb;
   shape.chunks = (int)g.x;
   return shape;

@@ -66,6 +66,16 @@ def kernels(tag):
                 for k in WANT:
                     if k in d:
                         f.write(f"| {k} | {d[k]} | {u.get(k, '')} |\n")
+                # warp stall reasons (cycles stalled per issued instruction), largest first
+                stalls = []
+                for k in hdr:
+                    if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and k in d:
+                        try:
+                            stalls.append((float(d[k].replace(",", "")), k))
+                        except ValueError:
+                            pass
+                for v, k in sorted(stalls, reverse=True)[:8]:
+                    f.write(f"| {k} | {v:.2f} | warps per issue |\n")
                 f.write("\n")
             src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
             tmp = f"/tmp/src_{name}.csv"
