@@ -361,16 +361,13 @@ def run_ours(args):
             del win4
 
     def teardown():
-        # the library's NCCL communicator is destroyed by every rank at the same point, while all are alive
+        # every rank reaches this point with its work finished; after a last barrier the processes leave through
+        # os._exit (main()), so that no NCCL / CUDA destructor of any library can block a rank at exit
         sys.stdout.flush()
         if world > 1:
             torch.cuda.synchronize()
             dist.barrier()
-            h.close()
-            dist.barrier()
-            dist.destroy_process_group()
-        else:
-            h.close()
+            torch.cuda.synchronize()
 
     if rank != 0:
         teardown()

@@ -610,6 +610,12 @@ int dpba_destroy(dpba_handle* h) {
   if (!h) return DPBA_E_INVALID;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
+  // the LM graph holds captured NCCL kernels: it must go before the communicator it references
+  if (h->lm_graph_exec) {
+    cudaGraphExecDestroy(h->lm_graph_exec);
+    h->lm_graph_exec = nullptr;
+  }
   if (h->comm) nccl_api().CommDestroy(h->comm);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->fork_ev) cudaEventDestroy(e);

@@ -67,11 +67,11 @@ def main():
     dist.broadcast(flag, 0)
     torch.cuda.synchronize()
     dist.barrier()
-    h.close()  # ncclCommDestroy while every rank is still alive
-    say("closed")
-    dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() else 1)
+    torch.cuda.synchronize()
+    code = 0 if flag.item() else 1
+    say("done, exit code", code)
+    sys.stdout.flush()
+    os._exit(code)  # no NCCL / CUDA destructor can block a rank at exit
 
 
 if __name__ == "__main__":
