@@ -280,6 +280,54 @@ def make_window(
     return SynthWindow(frames=frames, width=W, height=H, statuses=statuses, seed=seed)
 
 
+def scene_plane():
+    """The textured plane every synthetic frame looks at: unit normal n and offset d (n . X = d)."""
+    n = np.array([0.1, -0.05, 1.0])
+    n /= np.linalg.norm(n)
+    return n, float(n @ np.array([0.0, 0.0, 5.0]))
+
+
+def plane_depth(T_w_c, intr, W, H):
+    """Per-pixel depth (along the camera z axis) of the scene plane seen from pose T_w_c, (H, W) float64."""
+    n, d = scene_plane()
+    fx, fy, cx, cy = intr
+    u, v = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    dirs_c = np.stack([(u - cx) / fx, (v - cy) / fy, np.ones_like(u)], axis=-1)
+    R, t = T_w_c[:3, :3], T_w_c[:3, 3]
+    return (d - n @ t) / ((dirs_c @ R.T) @ n)
+
+
+@dataclass
+class AlignmentCase:
+    """Input of the coarse tracker's direct image alignment: the last keyframe with a
+    reference depth map (reference frame, fixed) and a new frame with a perturbed pose guess (target frame)."""
+    reference: SynthFrame
+    target: SynthFrame
+    T_w_target_guess: np.ndarray   # 4x4, what the tracker's motion model proposes
+    T_t_r_true: np.ndarray         # 4x4 ground truth target <- reference
+    idepth_sum: np.ndarray         # (H, W) depth-map accumulators as create_depth_maps.cpp leaves them
+    weight: np.ndarray             # (H, W)
+    width: int
+    height: int
+
+
+def make_alignment_case(seed=0, width=640, height=480, density=0.05, pose_noise=5e-3, idepth_noise=2e-3,
+                        ab_scale=0.0) -> AlignmentCase:
+    """density = fraction of pixels that carry depth (1.0 = BASELINE.json configs[2]'s synthetic full-frame bound; the
+    reference's own depth map is sparse: splatted landmarks + one dilation, tracker/src/create_depth_maps.cpp:19-122)."""
+    win = make_window(n_frames=2, points_per_frame=1, width=width, height=height, seed=seed, pose_noise=0.0, eps_scale=0.0,
+                      ab_scale=ab_scale)
+    ref, tgt = win.frames
+    rng = np.random.default_rng(seed + 77)
+    depth = plane_depth(ref.T_w_true, ref.intr, width, height)
+    weight = (rng.random((height, width)) < density).astype(np.float64) * rng.integers(1, 4, (height, width))
+    idepth = 1.0 / depth + rng.uniform(-1, 1, (height, width)) * idepth_noise
+    guess = tgt.T_w_true @ se3_exp(rng.uniform(-1, 1, 6) * pose_noise)
+    return AlignmentCase(reference=ref, target=tgt, T_w_target_guess=guess,
+                         T_t_r_true=np.linalg.inv(tgt.T_w_true) @ ref.T_w_true, idepth_sum=idepth * weight, weight=weight,
+                         width=width, height=height)
+
+
 CONFIGS = {
     # BASELINE.json configs[0]: correctness anchor (replaces the absent track30seconds)
     "anchor": dict(n_frames=3, points_per_frame=200),
