@@ -11,14 +11,16 @@ from dsopp_b200 import capi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
-    src = open(os.path.join(ROOT, "include", "dsopp_cuda_pba.h")).read()
+def header_symbols(header="dsopp_cuda_pba.h", prefix="dpba_"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(dpba_[a-z_0-9]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z_0-9]+)\s*\(", src)))
 
 
 def test_header_and_binding_agree():
+    from dsopp_b200 import pose_alignment
     assert header_symbols() == sorted(capi.SIGNATURES)
+    assert header_symbols("dsopp_cuda_pose_alignment.h", "dpa_") == sorted(pose_alignment.SIGNATURES)
 
 
 def test_library_exports_every_declared_symbol():
@@ -26,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         from dsopp_b200 import build
         build.build_cuda()
     lib = ctypes.CDLL(capi.CUDA_LIB_PATH)
-    for name in header_symbols():
+    for name in header_symbols() + header_symbols("dsopp_cuda_pose_alignment.h", "dpa_"):
         assert hasattr(lib, name), name
     assert b"sm_100a" in ctypes.cast(lib.dpba_version, ctypes.CFUNCTYPE(ctypes.c_char_p))()
 
