@@ -7,6 +7,7 @@
 #include <string>
 
 #include "cuda_photometric_bundle_adjustment.hpp"
+#include "cuda_pose_alignment.hpp"
 
 using namespace dsopp_b200;
 
@@ -233,3 +234,62 @@ __attribute__((visibility("default"))) void dpbah_sym_pinv(int n, const double* 
 }
 
 }  // extern "C"
+
+// ---- CudaPoseAlignment (coarse tracker), the call sequence of monocular_tracker.cpp:199-214 ------------------------
+extern "C" {
+__attribute__((visibility("default"))) void* dpah_create(int max_width, int max_height, int max_iterations, double sigma,
+                                                         double reg_a, double reg_b) {
+  try {
+    dsopp_b200::PoseAlignmentOptions o;
+    o.max_iterations = (size_t)max_iterations;
+    o.sigma_huber_loss = sigma;
+    o.affine_brightness_regularizer[0] = reg_a;
+    o.affine_brightness_regularizer[1] = reg_b;
+    return new dsopp_b200::CudaPoseAlignment(o, max_width, max_height);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+__attribute__((visibility("default"))) void dpah_destroy(void* s) { delete (dsopp_b200::CudaPoseAlignment*)s; }
+// one level: reset(); pushFrame(reference, depth map); pushFrame(target); solve().  Returns rmse (< 0: error / kZeroCost)
+__attribute__((visibility("default"))) double dpah_align_level(
+    void* s, int width, int height, const double* intr, const float* ref_image, const float* idepth_sum, const float* weight,
+    const double* ref_T, double ref_exposure, const double* ref_ab, const float* tgt_image, const uint8_t* tgt_mask,
+    const double* tgt_T_guess, double tgt_exposure, const double* tgt_ab, const double* prior_rotation, double* T_out,
+    double* ab_out, double* cov_out, int* n_landmarks) {
+  try {
+    auto& a = *(dsopp_b200::CudaPoseAlignment*)s;
+    a.reset();
+    if (prior_rotation) a.setRotationPrior(prior_rotation);
+    dsopp_b200::AlignmentFrameView r, t;
+    r.timestamp = 1;
+    t.timestamp = 2;
+    std::memcpy(r.t_world_agent, ref_T, sizeof(r.t_world_agent));
+    std::memcpy(t.t_world_agent, tgt_T_guess, sizeof(t.t_world_agent));
+    r.exposure_time = ref_exposure;
+    t.exposure_time = tgt_exposure;
+    for (int k = 0; k < 2; ++k) r.affine_brightness[k] = ref_ab[k], t.affine_brightness[k] = tgt_ab[k];
+    for (int k = 0; k < 4; ++k) r.intrinsics[k] = t.intrinsics[k] = intr[k];
+    r.width = t.width = width;
+    r.height = t.height = height;
+    r.image_I_dx_dy = ref_image;
+    r.depth_idepth_sum = idepth_sum;
+    r.depth_weight = weight;
+    t.image_I_dx_dy = tgt_image;
+    t.mask = tgt_mask;
+    const int n = a.pushReferenceFrame(r);
+    if (n_landmarks) *n_landmarks = n;
+    a.pushTargetFrame(t);
+    const double rmse = a.solve(1);
+    std::memcpy(T_out, a.targetPose(), 12 * sizeof(double));
+    ab_out[0] = a.targetAffineBrightness()[0];
+    ab_out[1] = a.targetAffineBrightness()[1];
+    if (cov_out) std::memcpy(cov_out, a.tTargetReferenceCovariance(), 36 * sizeof(double));
+    return rmse;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -2.0;
+  }
+}
+}

@@ -178,3 +178,39 @@ class CudaPhotometricBundleAdjustment:
         if self.lib.dpbah_covariance(self.s, ref_id, tgt_id, _ptr(out)) != 0:
             return None
         return out.reshape(6, 6)
+
+
+class PoseAligner:
+    """C++ CudaPoseAlignment (csrc/host/cuda_pose_alignment.hpp) through libdsopp_pba_host.so."""
+
+    def __init__(self, max_width, max_height, max_iterations=50, sigma=20.0, ab_reg=(1e12, 1e8)):
+        self.lib = load_library()
+        self.lib.dpah_create.restype = _P
+        self.lib.dpah_create.argtypes = [_I, _I, _I, _D, _D, _D]
+        self.lib.dpah_destroy.argtypes = [_P]
+        self.lib.dpah_align_level.restype = _D
+        self.lib.dpah_align_level.argtypes = [_P, _I, _I, _P, _P, _P, _P, _P, _D, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P, _P]
+        self.s = self.lib.dpah_create(max_width, max_height, max_iterations, sigma, ab_reg[0], ab_reg[1])
+        if not self.s:
+            raise DpbaError(f"dpah_create failed: {self.lib.dpah_last_error().decode() if hasattr(self.lib, 'dpah_last_error') else self.lib.dpbah_last_error().decode()}")
+
+    def close(self):
+        if self.s:
+            self.lib.dpah_destroy(self.s)
+            self.s = None
+
+    def align_level(self, intr, ref_image, idepth_sum, weight, ref_T, ref_exposure, ref_ab, tgt_image, tgt_mask, tgt_T_guess,
+                    tgt_exposure, tgt_ab, prior_rotation=None):
+        """reset(); pushFrame(reference + depth map); pushFrame(target); solve() -> dict(rmse, T_w_target, ab, cov, n)."""
+        ref_image, tgt_image = _f32(ref_image), _f32(tgt_image)
+        ids, w, mask = _f32(idepth_sum), _f32(weight), _u8(tgt_mask)
+        H, W = w.shape
+        it, rT, tT = _f64(intr), pose34(ref_T), pose34(tgt_T_guess)
+        rab, tab, pr = _f64(ref_ab), _f64(tgt_ab), _f64(prior_rotation)
+        T, ab, cov, n = np.zeros(12), np.zeros(2), np.zeros(36), _I()
+        rmse = self.lib.dpah_align_level(self.s, W, H, _ptr(it), _ptr(ref_image), _ptr(ids), _ptr(w), _ptr(rT), ref_exposure,
+                                         _ptr(rab), _ptr(tgt_image), _ptr(mask), _ptr(tT), tgt_exposure, _ptr(tab), _ptr(pr),
+                                         _ptr(T), _ptr(ab), _ptr(cov), C.byref(n))
+        if rmse == -2.0:
+            raise DpbaError(self.lib.dpbah_last_error().decode())
+        return dict(rmse=rmse, T_w_target=np.vstack([T.reshape(3, 4), [0, 0, 0, 1.0]]), ab=ab, cov=cov.reshape(6, 6), n=n.value)

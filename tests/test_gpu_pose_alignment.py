@@ -104,3 +104,42 @@ def test_empty_reference_and_error_codes():
     with pytest.raises(capi.DpbaError):
         al.set_reference_landmarks(np.zeros((101, 2)), np.zeros(101), np.zeros(101), r.T_w_true, r.exposure, r.ab0, r.intr, 160, 120)
     al.close()
+
+
+def test_coarse_to_fine_through_the_cpp_host_class():
+    """The tracker's loop (monocular_tracker.cpp:199-214) over 4 pyramid levels, coarse to fine, through the C++
+    CudaPoseAlignment mirror of EigenPoseAlignment: reset / pushFrame x2 / solve per level, each level starting from
+    the previous level's pose.  Level images are 2x2 box pyramids (downscale_image.hpp:16-33), per-level intrinsics
+    are f / 2^l without a half-pixel shift (camera_calibration.cpp:66-70), depth-map accumulators are summed 2x2
+    (create_depth_maps.cpp)."""
+    from dsopp_b200 import host
+    from oracle import pba_oracle as O
+    case = synth.make_alignment_case(seed=9, width=640, height=480, density=0.05, pose_noise=1.5e-2)
+    r, t = case.reference, case.target
+    levels = 4
+    ref_I, tgt_I = [r.image[..., 0]], [t.image[..., 0]]
+    ids, w = [case.idepth_sum.astype(np.float32)], [case.weight.astype(np.float32)]
+    for _ in range(1, levels):
+        ref_I.append(synth.downscale(ref_I[-1]))
+        tgt_I.append(synth.downscale(tgt_I[-1]))
+        a, b = ids[-1], w[-1]
+        ids.append(a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2])
+        w.append(b[0::2, 0::2] + b[1::2, 0::2] + b[0::2, 1::2] + b[1::2, 1::2])
+    al = host.PoseAligner(640, 480)
+    T = case.T_w_target_guess
+    err0 = np.linalg.norm((O.se3_inv(case.T_t_r_true) @ (O.se3_inv(T) @ r.T_w_true))[:3, 3])
+    last = None
+    for lvl in range(levels - 1, -1, -1):
+        intr = r.intr / (2 ** lvl)
+        Hh, Ww = ref_I[lvl].shape
+        out = al.align_level(intr, synth.pixelinfo(ref_I[lvl]), ids[lvl], w[lvl], r.T_w_true, r.exposure, r.ab0,
+                             synth.pixelinfo(tgt_I[lvl]), np.full((Hh, Ww), 255, np.uint8), T, t.exposure, t.ab0)
+        assert out["n"] > 0 and out["rmse"] > 0
+        T = out["T_w_target"]
+        last = out
+        err = np.linalg.norm((O.se3_inv(case.T_t_r_true) @ (O.se3_inv(T) @ r.T_w_true))[:3, 3])
+        print(f"[coarse-to-fine] level {lvl}: {Ww}x{Hh}, {out['n']} landmarks, rmse {out['rmse']:.3f}, |dt| {err:.2e}")
+    al.close()
+    assert err < 0.05 * err0 and err < 5e-4
+    cov = last["cov"]
+    assert np.allclose(cov, cov.T, atol=1e-12 * np.abs(cov).max()) and (np.diag(cov) > 0).all()
