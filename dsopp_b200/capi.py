@@ -83,6 +83,8 @@ SIGNATURES = {
     "dpba_stream": (_P, [_P]),
     "dpba_push_frame": (C.c_int, [_P, _I, _P, _P, _P, _D, _P, _P, _I]),
     "dpba_push_frame_intensity": (C.c_int, [_P, _I, _P, _P, _P, _D, _P, _P, _I]),
+    "dpba_push_frame_raw": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _D, _P, _P, _I]),
+    "dpba_build_pyramid": (C.c_int, [_P, _P, _P, _P, _I, _P]),
     "dpba_remove_frame": (C.c_int, [_P, _I]),
     "dpba_num_frames": (C.c_int, [_P]),
     "dpba_set_frame_linearization": (C.c_int, [_P, _I, _P, _P]),
@@ -204,6 +206,21 @@ class Handle:
                                                      _ptr(ab), _ptr(it), int(fixed)))
         return self._ck(self.lib.dpba_push_frame_intensity(self.h, frame_id, _ptr(image), _ptr(mask), _ptr(T),
                                                            exposure, _ptr(ab), _ptr(it), int(fixed)))
+
+    def push_frame_raw(self, frame_id, gray, lut, vignetting, mask, T_w_lin, exposure, ab0, intr, fixed):
+        gray, vignetting, mask, lut = _u8(gray), _u8(vignetting), _u8(mask), _f32(lut)
+        T, ab, it = pose34(T_w_lin), _f64(ab0), _f64(intr)
+        return self._ck(self.lib.dpba_push_frame_raw(self.h, frame_id, _ptr(gray), _ptr(lut), _ptr(vignetting), _ptr(mask),
+                                                     _ptr(T), exposure, _ptr(ab), _ptr(it), int(fixed)))
+
+    def build_pyramid(self, gray, lut=None, vignetting=None, levels=4):
+        gray, vignetting, lut = _u8(gray), _u8(vignetting), _f32(lut)
+        H, W = gray.shape
+        levels = min(levels, 5)
+        outs = [np.zeros((H >> l, W >> l, 3), np.float32) for l in range(levels)]
+        ptrs = (C.c_void_p * levels)(*[o.ctypes.data for o in outs])
+        self._ck(self.lib.dpba_build_pyramid(self.h, _ptr(gray), _ptr(lut), _ptr(vignetting), levels, C.cast(ptrs, C.c_void_p)))
+        return outs
 
     def remove_frame(self, slot):
         self._ck(self.lib.dpba_remove_frame(self.h, slot))

@@ -117,6 +117,9 @@ struct dpba_handle {
   size_t red_n = 0;
   double* step_dev = nullptr;
   float* pair_dist = nullptr;
+  float* pyr_planes = nullptr;   // lazily: intensity planes of the device-side pyramid build (2 * W * H floats)
+  uint8_t* raw_u8 = nullptr;     // lazily: raw gray image + vignetting (2 * W * H bytes)
+  float* lut_dev = nullptr;      // lazily: photometric calibration table (256 floats)
   float* stage = nullptr;  // image upload staging (device)
   float* stage_h = nullptr;  // pinned staging for images
   float *m_r = nullptr, *m_jref = nullptr, *m_jtgt = nullptr, *m_did = nullptr, *m_w = nullptr;
@@ -429,16 +432,18 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
   const size_t npx = (size_t)W * H;
   // page-locked caller buffers are DMA'd directly; pageable ones go through the handle's pinned staging buffer
   cudaPointerAttributes attr;
-  const bool pinned = cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  const bool pinned = channels < 0 || (cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost);
   cudaGetLastError();
   const float* src = image;
-  if (!pinned) {
-    memcpy(h->stage_h, image, npx * channels * sizeof(float));
-    src = h->stage_h;
+  if (channels > 0) {
+    if (!pinned) {
+      memcpy(h->stage_h, image, npx * channels * sizeof(float));
+      src = h->stage_h;
+    }
+    CK(cudaMemcpyAsync(h->stage, src, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   }
-  CK(cudaMemcpyAsync(h->stage, src, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   if (channels == 3) pba::launch_pack_image(h->stage, h->img[phys], (int)npx, W, h->stream);
-  else pba::launch_pixelinfo(h->stage, h->img[phys], W, H, h->stream);
+  else pba::launch_pixelinfo(channels > 0 ? h->stage : image, h->img[phys], W, H, h->stream);  // -1: device plane
   CK(cudaGetLastError());
   if (mask) CK(cudaMemcpyAsync(h->mask[phys], mask, npx, cudaMemcpyHostToDevice, h->stream));
   else CK(cudaMemsetAsync(h->mask[phys], 255, npx, h->stream));
@@ -599,7 +604,8 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   CKC(cudaMalloc(&h->stage, npx * 3 * sizeof(float)));
   CKC(cudaMallocHost(&h->stage_h, npx * 3 * sizeof(float)));
   // one window's worth of landmark records (52 B each, 256 B aligned per array) and status rows, twice
-  h->arena_cap = 2 * ((size_t)cfg->max_frames * (mp * 64 + 1024) + (size_t)cfg->max_frames * cfg->max_frames * (mp + 256));
+  h->arena_cap = 2 * ((size_t)cfg->max_frames * (mp * 64 + 1024) + (size_t)cfg->max_frames * cfg->max_frames * (mp + 256)) +
+                 4 * npx + 4096;  // + raw 8-bit frames and vignetting of the device-side image preparation
   CKC(cudaMallocHost(&h->arena_h, h->arena_cap));
 #undef CKC
   *out = h;
@@ -629,7 +635,7 @@ int dpba_destroy(dpba_handle* h) {
                  h->pairs,   h->pasm,   h->fparams,      h->red,        h->step_dev, h->pair_dist, h->stage,
                  h->m_r,     h->m_jref, h->m_jtgt,       h->m_did,      h->m_w,    h->red2,    h->ctl,
                  h->lmopt,   h->fixed_dev, h->marg_dev, h->core_part, h->fschur_part, h->core, h->schur_part, h->bs_part, h->e_part,
-                 h->n_part};
+                 h->n_part, h->pyr_planes, h->raw_u8, h->lut_dev};
   for (void* p : dev) cudaFree(p);
   cudaFreeHost(h->fparams_h);
   cudaFreeHost(h->red_h);
@@ -654,6 +660,82 @@ int dpba_push_frame_intensity(dpba_handle* h, int32_t frame_id, const float* ima
                               const double T[12], double exposure, const double ab0[2], const double intr[4],
                               int32_t fixed) {
   return push_frame_common(h, frame_id, image_I, 1, mask, T, exposure, ab0, intr, fixed);
+}
+
+// device-side image preparation: uploads the raw gray frame (+ table, vignetting) and leaves the
+// photometrically corrected level-0 intensity plane in h->pyr_planes
+static int raw_to_plane(dpba_handle* h, const uint8_t* gray, const float* lut, const uint8_t* vignetting) {
+  const size_t npx = (size_t)h->cfg.width * h->cfg.height;
+  if (!h->pyr_planes) {
+    CK(cudaMalloc(&h->pyr_planes, 2 * npx * sizeof(float)));
+    CK(cudaMalloc(&h->raw_u8, 2 * npx));
+    CK(cudaMalloc(&h->lut_dev, 256 * sizeof(float)));
+  }
+  uint8_t* g = (uint8_t*)arena_alloc(h, npx);
+  if (!g) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+  memcpy(g, gray, npx);
+  CK(cudaMemcpyAsync(h->raw_u8, g, npx, cudaMemcpyHostToDevice, h->stream));
+  if (lut) {
+    float* l = (float*)arena_alloc(h, 256 * sizeof(float));
+    if (!l) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+    memcpy(l, lut, 256 * sizeof(float));
+    CK(cudaMemcpyAsync(h->lut_dev, l, 256 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  float max_v = 0.f;
+  if (vignetting) {
+    uint8_t* v = (uint8_t*)arena_alloc(h, npx);
+    if (!v) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+    memcpy(v, vignetting, npx);
+    uint8_t m = 0;  // cv::minMaxLoc(vignetting, nullptr, &max), photometrically_corrected_image.cpp:11-14
+    for (size_t i = 0; i < npx; ++i) m = vignetting[i] > m ? vignetting[i] : m;
+    max_v = (float)m;
+    CK(cudaMemcpyAsync(h->raw_u8 + npx, v, npx, cudaMemcpyHostToDevice, h->stream));
+  }
+  pba::launch_photometric(h->raw_u8, lut ? h->lut_dev : nullptr, vignetting ? h->raw_u8 + npx : nullptr, max_v, h->pyr_planes,
+                          (int)npx, h->stream);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int dpba_push_frame_raw(dpba_handle* h, int32_t frame_id, const uint8_t* gray, const float* photometric_calibration,
+                        const uint8_t* vignetting, const uint8_t* mask, const double T[12], double exposure,
+                        const double ab0[2], const double intr[4], int32_t fixed) {
+  REQUIRE(h, "null handle");
+  REQUIRE(gray, "null image");
+  int rc = raw_to_plane(h, gray, photometric_calibration, vignetting);
+  if (rc) return rc;
+  // the plane is already on the device: push_frame_common takes it from there
+  return push_frame_common(h, frame_id, h->pyr_planes, -1, mask, T, exposure, ab0, intr, fixed);
+}
+
+int dpba_build_pyramid(dpba_handle* h, const uint8_t* gray, const float* photometric_calibration,
+                       const uint8_t* vignetting, int32_t levels, float* const* out_I_dx_dy) {
+  REQUIRE(h, "null handle");
+  REQUIRE(gray && out_I_dx_dy && levels >= 1, "bad argument");
+  if (levels > 5) levels = 5;  // kMaxPyramidDepth, features/include/features/camera/pixel_data_frame.hpp:26
+  int rc = raw_to_plane(h, gray, photometric_calibration, vignetting);
+  if (rc) return rc;
+  int W = h->cfg.width, H = h->cfg.height;
+  const size_t npx = (size_t)W * H;
+  float* cur = h->pyr_planes;
+  float* nxt = h->pyr_planes + npx;
+  for (int l = 0; l < levels; ++l) {
+    if (out_I_dx_dy[l]) {
+      pba::launch_pixelinfo3(cur, h->stage, W, H, h->stream);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(out_I_dx_dy[l], h->stage, (size_t)W * H * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));  // h->stage is reused by the next level
+    }
+    if (l + 1 < levels) {
+      pba::launch_downscale(cur, nxt, W, H, h->stream);
+      CK(cudaGetLastError());
+      std::swap(cur, nxt);  // the coarser plane is at most a quarter of the finer: both halves of pyr_planes suffice
+      W /= 2;
+      H /= 2;
+    }
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return levels;
 }
 
 int dpba_remove_frame(dpba_handle* h, int32_t slot) {

@@ -133,6 +133,10 @@ void launch_clear_frame_rows(uint8_t* status, uint8_t* cand, uint8_t* jac_valid,
                              int max_frames, cudaStream_t s);
 void launch_pack_image(const float* src3, float4* dst, int n_px, int W, cudaStream_t s);
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s);
+void launch_photometric(const uint8_t* gray, const float* lut, const uint8_t* vignetting, float max_v, float* out, int n,
+                        cudaStream_t s);
+void launch_downscale(const float* src, float* dst, int W, int H, cudaStream_t s);
+void launch_pixelinfo3(const float* I, float* dst, int W, int H, cudaStream_t s);
 int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* e_part, cudaStream_t s,
                           const LmCtl* ctl = nullptr, int ctl_mode = 0);
 void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, int n_e, const double* n_part, int n_n,

@@ -1850,6 +1850,41 @@ __device__ __forceinline__ float4 pixelinfo_at(const float* __restrict__ I, int 
   dy = ((y == 0 || y == H - 1) ? 1.0f : 0.5f) * (I[yb * W + x] - I[yu * W + x]);
   return make_float4(c, dx, dy, 0.f);
 }
+// photometricallyCorrectedImage, features/src/photometrically_corrected_image.cpp:9-29:
+// I = lut[gray] * (max_vignetting / (vignetting + 1)); lut == null: identity, vignetting == null: no second factor
+__global__ void k_photometric(const uint8_t* __restrict__ gray, const float* __restrict__ lut,
+                              const uint8_t* __restrict__ vignetting, float max_v, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t g = gray[i];
+  float v = lut ? lut[g] : (float)g;
+  if (vignetting) v = __fmul_rn(v, __fdiv_rn(max_v, __fadd_rn((float)vignetting[i], 1.f)));
+  out[i] = v;
+}
+
+// downscaleImage, features/internal/features/camera/downscale_image.hpp:16-33: 0.25 * (((A + B) + C) + D) with
+// A = (even, even), B = (odd, odd), C = (even, odd), D = (odd, even) -- the reference's summation order
+__global__ void k_downscale(const float* __restrict__ src, float* __restrict__ dst, int W, int H) {
+  const int W2 = W / 2, H2 = H / 2;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W2 || y >= H2) return;
+  const float a = src[(2 * y) * W + 2 * x], b = src[(2 * y + 1) * W + 2 * x + 1];
+  const float c = src[(2 * y) * W + 2 * x + 1], d = src[(2 * y + 1) * W + 2 * x];
+  dst[y * W2 + x] = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d));
+}
+
+// {I,dx,dy} interleaved float3 (the PixelMap<1> storage) from the intensity plane, for host consumers
+__global__ void k_pixelinfo3(const float* __restrict__ I, float* __restrict__ dst, int W, int H) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const float4 t = pixelinfo_at(I, x, y, W, H);
+  float* o = dst + 3 * ((size_t)y * W + x);
+  o[0] = t.x;
+  o[1] = t.y;
+  o[2] = t.z;
+}
+
 __global__ void k_pixelinfo(const float* __restrict__ I, float4* __restrict__ dst, int W, int H) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -2282,6 +2317,22 @@ void launch_clear_frame_rows(uint8_t* status, uint8_t* cand, uint8_t* jac_valid,
 void launch_pack_image(const float* src3, float4* dst, int n_px, int W, cudaStream_t s) {
   ++g_launches;
   k_pack_image<<<(n_px + 255) / 256, 256, 0, s>>>(src3, dst, n_px, W);
+}
+
+void launch_photometric(const uint8_t* gray, const float* lut, const uint8_t* vignetting, float max_v, float* out, int n,
+                        cudaStream_t s) {
+  ++g_launches;
+  k_photometric<<<(n + 255) / 256, 256, 0, s>>>(gray, lut, vignetting, max_v, out, n);
+}
+void launch_downscale(const float* src, float* dst, int W, int H, cudaStream_t s) {
+  dim3 b(32, 8), g((W / 2 + 31) / 32, (H / 2 + 7) / 8);
+  ++g_launches;
+  k_downscale<<<g, b, 0, s>>>(src, dst, W, H);
+}
+void launch_pixelinfo3(const float* I, float* dst, int W, int H, cudaStream_t s) {
+  dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+  ++g_launches;
+  k_pixelinfo3<<<g, b, 0, s>>>(I, dst, W, H);
 }
 
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s) {

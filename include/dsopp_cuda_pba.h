@@ -110,6 +110,19 @@ int dpba_push_frame(dpba_handle* h, int32_t frame_id, const float* image_I_dx_dy
 int dpba_push_frame_intensity(dpba_handle* h, int32_t frame_id, const float* image_I, const uint8_t* mask,
                               const double T_w_agent_lin[12], double exposure_time,
                               const double affine_brightness0[2], const double intr[4], int32_t fixed);
+/* As dpba_push_frame but from the RAW 8-bit gray frame: photometric correction (table of 256 floats or NULL = identity,
+ * vignetting image or NULL; features/src/photometrically_corrected_image.cpp:9-29) and the {I,dx,dy} packing run on
+ * the device -- 0.3 MB cross PCIe per VGA keyframe instead of 3.7 MB. */
+int dpba_push_frame_raw(dpba_handle* h, int32_t frame_id, const uint8_t* gray, const float* photometric_calibration,
+                        const uint8_t* vignetting, const uint8_t* mask, const double T_w_agent_lin[12],
+                        double exposure_time, const double affine_brightness0[2], const double intr[4],
+                        int32_t fixed);
+/* PixelDataFrame (features/src/pixel_data_frame.cpp:12-31) on the device: corrected level 0, 2x2 box pyramid
+ * (features/internal/features/camera/downscale_image.hpp:16-33, same summation order), gradients per level; level l is
+ * written to out_I_dx_dy[l] as (H >> l) x (W >> l) x 3 floats (NULL entries are skipped).  levels is capped at 5
+ * (kMaxPyramidDepth).  Bit-identical to the reference's float build.  Returns the number of levels. */
+int dpba_build_pyramid(dpba_handle* h, const uint8_t* gray, const float* photometric_calibration,
+                       const uint8_t* vignetting, int32_t levels, float* const* out_I_dx_dy);
 /* frames.erase(...) of a marginalised frame (PBA/eigen_photometric_bundle_adjustment_problem.hpp:201-202);
  * later slots shift down by one. */
 int dpba_remove_frame(dpba_handle* h, int32_t slot);
