@@ -325,6 +325,39 @@ def run_ours(args):
         ms, _ = timed(e2e_step)
         if i >= args.warmup:
             e2e_ms.append(ms)
+
+    # the same step fed with RAW 8-bit frames (dpba_push_frame_raw: photometric table + gradients on the device,
+    # SURVEY 8f-4) -- informational; `e2e` above stays the {I,dx,dy} upload the reference's pushFrame receives
+    raw_frames = [pin(np.clip(np.rint(f.image[..., 0]), 0, 255).astype(np.uint8)) for f in win.frames]
+    keep += [x[1] for x in raw_frames]
+    lut = np.arange(256, dtype=np.float32)
+
+    def e2e_raw_step():
+        for _ in range(h.n_frames):
+            h.remove_frame(0)
+        for (f, img, msk, uv, idp, pat, flg), (g, _) in zip(host_frames, raw_frames):
+            h.push_frame_raw(f.frame_id, g, lut, None, msk, f.T_w_lin, f.exposure, f.ab0, f.intr, f.fixed)
+        for i, (f, img, msk, uv, idp, pat, flg) in enumerate(host_frames):
+            h.set_landmarks(i, uv, idp, pat, flg)
+            h.set_frame_statuses(i, host_status[i])
+        h.set_state(eps0, np.zeros_like(eps0))
+        solve()
+        h.get_state()
+        for i in range(n):
+            h.get_landmarks(i)
+            h.get_frame_statuses(i)
+
+    e2e_raw_ms = []
+    for i in range(3 + min(args.steps, 10)):
+        ms, _ = timed(e2e_raw_step)
+        if i >= 3:
+            e2e_raw_ms.append(ms)
+    t_raw = torch.tensor([sum(e2e_raw_ms) / len(e2e_raw_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_raw, op=dist.ReduceOp.MAX)
+    e2e_raw_value = units_global * GN_ITERS / (float(t_raw.item()) * 1e-3)
+    # leave the handle with the float window for the sweeps timed below
+    e2e_step()
     t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -443,6 +476,9 @@ def run_ours(args):
                 "ms_per_step": sum(e2e_ms) / len(e2e_ms),
                 "path": "dpba_remove_frame/push_frame/set_landmarks/set_frame_statuses/set_state from pinned host buffers, "
                         "dpba_first_estimate + dpba_solve_lm, dpba_get_* readback"},
+        "e2e_raw_frames": {"value": e2e_raw_value, "unit": UNIT, "ms_per_step": float(t_raw.item()),
+                           "h2d_bytes_per_step": int(h2d - sum(x[1].nbytes for x in host_frames) + sum(x[0].nbytes for x in raw_frames)),
+                           "path": "as e2e, but dpba_push_frame_raw: 8-bit frames in, photometric table + {I,dx,dy} on the device"},
         "gpu_launches": int(launches),
         "roofline": roofline, "roofline_sweep": roofline_sweep, "roofline_sweep_big": roofline_sweep_big,
         "kernel_ms": kernel_ms,

@@ -113,6 +113,7 @@ SIGNATURES = {
     "dpba_change_residual_statuses": (C.c_int, [_P, _I]),
     "dpba_landmarks_energy": (C.c_int, [_P, _I, C.POINTER(_D), C.POINTER(_I)]),
     "dpba_update_point_statuses": (C.c_int, [_P, _I, _D, C.POINTER(_D)]),
+    "dpba_refine_immature_landmarks": (C.c_int, [_P, _I, _I, _P, _P, _P, _I, _D, _P, _P, _P]),
     "dpba_solve_lm": (C.c_int, [_P, C.POINTER(LmOptions), _P, _P, _D, C.POINTER(LmResult)]),
     "dpba_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "dpba_launch_count": (C.c_int64, []),
@@ -354,6 +355,15 @@ class Handle:
         t = _D()
         self._ck(self.lib.dpba_update_point_statuses(self.h, min_valid, sigma, C.byref(t)))
         return t.value
+
+    def refine_immature_landmarks(self, ref_slot, proj_xy, idepth, patch, minimum_inliers, sigma=20.0):
+        """optimizeImmatureLandmark for every candidate -> (idepth, activate, n_valid)."""
+        xy, idp, pt = _f32(proj_xy), _f32(idepth), _f32(patch)
+        n = len(idp)
+        out, act, nv = np.zeros(n, np.float32), np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        self._ck(self.lib.dpba_refine_immature_landmarks(self.h, ref_slot, n, _ptr(xy), _ptr(idp), _ptr(pt), minimum_inliers,
+                                                         sigma, _ptr(out), _ptr(act), _ptr(nv)))
+        return out, act.astype(bool), nv
 
     def solve_lm(self, sigma=20.0, ab_reg=(1e12, 1e8), fixed_reg=1e16, max_it=7, min_it=3, ftol=1e-8, ptol=1e-8,
                  force_accept=True, lambda0=1e-5, decrease=1.0, increase=1.0, fej=True, H_marg=None, b_marg=None,

@@ -738,6 +738,43 @@ int dpba_build_pyramid(dpba_handle* h, const uint8_t* gray, const float* photome
   return levels;
 }
 
+int dpba_refine_immature_landmarks(dpba_handle* h, int32_t ref_slot, int32_t n, const float* proj_xy,
+                                   const float* idepth, const float* patch, int32_t minimum_inliers,
+                                   double sigma_huber, float* idepth_out, uint8_t* activate,
+                                   int32_t* number_of_valid_residuals) {
+  REQUIRE(h, "null handle");
+  REQUIRE(ref_slot >= 0 && ref_slot < h->n_frames && h->n_frames >= 2, "bad reference slot");
+  REQUIRE(n >= 0 && (n == 0 || (proj_xy && idepth && patch)), "null argument");
+  if (n == 0) return DPBA_SUCCESS;
+  // the candidates travel through a scratch allocation sized for this call (activation happens once per keyframe)
+  float* dev = nullptr;
+  const size_t words = (size_t)n * (2 + 1 + 8 + 1 + 1) + (n + 3) / 4;
+  CK(cudaMallocAsync((void**)&dev, words * sizeof(float), h->stream));
+  float* d_proj = dev;
+  float* d_id = d_proj + 2 * (size_t)n;
+  float* d_patch = d_id + n;
+  float* d_out = d_patch + 8 * (size_t)n;
+  int* d_nv = reinterpret_cast<int*>(d_out + n);
+  uint8_t* d_act = reinterpret_cast<uint8_t*>(d_nv + n);
+  CK(cudaMemcpyAsync(d_proj, proj_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_id, idepth, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_patch, patch, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, h->stream));
+  int rc = sync_pairs(h);  // t_t_r = T_w_t^-1 T_w_r and the brightness scale at the current frame state (:159-163)
+  if (rc) return rc;
+  WindowDev w = make_window(h);
+  // std::min(minimum_inliers, active frames - 1), :331
+  const int min_inl = std::min<int>(minimum_inliers, h->n_frames - 1);
+  pba::launch_refine_immature(w, ref_slot, n, d_proj, d_id, d_patch, min_inl, (float)sigma_huber, d_out, d_act, d_nv, h->stream);
+  CK(cudaGetLastError());
+  if (idepth_out) CK(cudaMemcpyAsync(idepth_out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (activate) CK(cudaMemcpyAsync(activate, d_act, n, cudaMemcpyDeviceToHost, h->stream));
+  if (number_of_valid_residuals)
+    CK(cudaMemcpyAsync(number_of_valid_residuals, d_nv, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaFreeAsync(dev, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
 int dpba_remove_frame(dpba_handle* h, int32_t slot) {
   REQUIRE(h, "null handle");
   REQUIRE(slot >= 0 && slot < h->n_frames, "slot out of range");

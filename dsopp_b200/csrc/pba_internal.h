@@ -159,7 +159,10 @@ void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s,
                    int with_statuses = 0);
 void launch_change_statuses(const WindowDev& w, int accept, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cudaStream_t s);
-void launch_first_estimate(const WindowDev& w, cudaStream_t s);  // K6: idepth snapshot + reprojection_jacobians_valid
+void launch_first_estimate(const WindowDev& w, cudaStream_t s);
+void launch_refine_immature(const WindowDev& w, int r, int n, const float* proj, const float* idepth_in, const float* patch8,
+                            int min_inliers, float sigma, float* idepth_out, uint8_t* activate, int* n_valid_out,
+                            cudaStream_t s);  // K6: idepth snapshot + reprojection_jacobians_valid
 void launch_apply_point_statuses(const WindowDev& w, float threshold, int min_valid, const float* pair_dist,
                                  cudaStream_t s);
 int sm_count();

@@ -1638,6 +1638,147 @@ __global__ void k_apply_point_statuses(const __grid_constant__ WindowDev w, floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// Immature-landmark activation refine: LandmarkActivationProblem + optimizeImmatureLandmark,
+// tracker/landmarks_activator/src/landmarks_activator.cpp:122-316 -- per candidate a 1-D Levenberg-Marquardt on the
+// inverse depth over all other frames of the window (8-pixel pattern, Huber weight, inlier energy cap 8 * 12^2,
+// lambda0 = 0.1, <= 3 iterations, /2 on accept, x5 on reject, ptol 1e-8, ftol 0).  Thousands of independent tiny
+// problems: one WARP per candidate, 8 lanes per target frame (4 targets per pass), the whole LM in registers.
+// One evaluation yields the energy AND (H, b) at the same inverse depth: linearize() after an accepted step is at the
+// trial point the energy was just evaluated at, so the reference's two passes are one here.
+// ------------------------------------------------------------------------------------------------
+struct ActEval {
+  float energy, H, b;
+  int n;
+};
+__device__ __forceinline__ ActEval act_eval(const WindowDev& w, const PairConst* __restrict__ pcs, int r, float u0, float v0,
+                                            float patch, float rho, float sigma, int lane) {
+  const int N = w.n_frames;
+  const int px = lane & 7, grp = lane >> 3;
+  const float xmax = (float)(w.W - 5), ymax = (float)(w.H - 5);
+  const float ur = u0 + pat_x(px), vr = v0 + pat_y(px);
+  ActEval out{0.f, 0.f, 0.f, 0};
+  for (int base = 0; base < N - 1; base += 4) {  // uniform trip count: the shuffles below need the whole warp
+    const int ti = base + grp;
+    const bool have = ti < N - 1;
+    const int t = have ? ti + (ti >= r) : (r == 0 ? 1 : 0);
+    const PairConst& pc = pcs[r * PBA_MAXF + t];
+    bool ok = have && valid_idepth(rho) && in_roi(ur, vr, xmax, ymax);
+    const float X = row_apply4(ldf4(pc.A + 0), ur, vr, rho);
+    const float Y = row_apply4(ldf4(pc.A + 4), ur, vr, rho);
+    const float Z = row_apply4(ldf4(pc.A + 8), ur, vr, rho);
+    ok = ok && Z > 0.f;
+    const float rz = __frcp_rn(Z);
+    const float tu = __fmul_rn(X, rz), tv = __fmul_rn(Y, rz);
+    ok = ok && in_roi(tu, tv, xmax, ymax);
+    ok = group_all(ok, lane);
+    {  // target_mask.valid(target_pattern), bounds are implied by the ROI test; branch-free (groups differ in t)
+      const bool need = !w.mask_all[t];
+      const int midx = (ok && need) ? (int)roundf(tv) * w.W + (int)roundf(tu) : 0;
+      const bool mv = need ? w.mask[t][midx] != 0 : true;
+      ok = group_all(ok && mv, lane);
+    }
+    const float su = ok ? tu : 8.f, sv = ok ? tv : 8.f;
+    const int ix = (int)su, iy = (int)sv;
+    const float dx = su - (float)ix, dy = sv - (float)iy, dxdy = dx * dy;
+    const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1.f - dx - dy + dxdy;
+    const float4* p = w.img[t] + ((size_t)iy * w.W + ix) * 2;
+    float4 t00, t01, t10, t11;
+    ldg256_nc(p, t00, t01);
+    ldg256_nc(p + 2 * (size_t)w.W, t10, t11);
+    const float I = w11 * t11.x + w10 * t10.x + w01 * t01.x + w00 * t00.x;
+    const float dIu = w11 * t11.y + w10 * t10.y + w01 * t01.y + w00 * t00.y;
+    const float dIv = w11 * t11.z + w10 * t10.z + w01 * t01.z + w00 * t00.z;
+    const float res = ok ? (I - pc.b_t) - pc.s * (patch - pc.b_r) : 0.f;
+    const float n2 = group_sum(res * res);
+    const float wgt = n2 > sigma * sigma ? sigma * rsqrt_approx(n2) : 1.f;  // :176
+    // d r / d idepth (camera_reproject.hpp:339-344)
+    const float qx = row_apply4(ldf4(pc.M + 0), ur, vr, rho);
+    const float qy = row_apply4(ldf4(pc.M + 4), ur, vr, rho);
+    const float qz = row_apply4(ldf4(pc.M + 8), ur, vr, rho);
+    const float sI = rcp_approx(ok ? qz : 1.f);
+    const float b0 = qx * sI, b1 = qy * sI;
+    const float du = pc.fx_t * (pc.tr[0] * sI - pc.tr[2] * sI * b0), dv = pc.fy_t * (pc.tr[1] * sI - pc.tr[2] * sI * b1);
+    const float d = ok ? dIu * du + dIv * dv : 0.f;
+    const float hd = group_sum(d * d), bd = group_sum(d * res);
+    if (px == 0 && ok) {  // one lane per target adds the target's terms
+      if (n2 < 8.f * 144.f) {  // kMaxEnergyForInliers, :124,178-183
+        out.energy += wgt * n2;
+        out.n += 1;
+      } else {
+        out.energy += 8.f * 144.f;
+      }
+      out.H += wgt * hd;  // linearize() has no inlier cap, :243-244
+      out.b += wgt * bd;
+    }
+  }
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {  // across the 4 groups (only lane px == 0 of each holds data)
+    out.energy += __shfl_xor_sync(FULL, out.energy, o);
+    out.H += __shfl_xor_sync(FULL, out.H, o);
+    out.b += __shfl_xor_sync(FULL, out.b, o);
+    out.n += __shfl_xor_sync(FULL, out.n, o);
+  }
+  // broadcast lane 0's totals
+  out.energy = __shfl_sync(FULL, out.energy, 0);
+  out.H = __shfl_sync(FULL, out.H, 0);
+  out.b = __shfl_sync(FULL, out.b, 0);
+  out.n = __shfl_sync(FULL, out.n, 0);
+  return out;
+}
+
+__global__ void __launch_bounds__(256) k_refine_immature(const __grid_constant__ WindowDev w, int r, int n,
+                                                         const float2* __restrict__ proj, const float* __restrict__ idepth_in,
+                                                         const float* __restrict__ patch8, int min_inliers, float sigma,
+                                                         float* __restrict__ idepth_out, uint8_t* __restrict__ activate,
+                                                         int* __restrict__ n_valid_out) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= n) return;  // whole warps leave together
+  const float2 uv = proj[c];
+  const float patch = patch8[(size_t)c * 8 + (lane & 7)];
+  float rho = idepth_in[c];
+  // levenberg_marquardt_algorithm::solve (lm.hpp:77-128) with the options of :294-300
+  ActEval cur = act_eval(w, w.pairs, r, uv.x, uv.y, patch, rho, sigma, lane);
+  float energy = cur.energy, H = cur.H, b = cur.b, lambda = 0.1f;
+  int nvalid = cur.n;
+  bool stop = nvalid == 0, converged = false;  // calculateEnergy(): no valid residual -> idepth = -1, stop (:192-195)
+  for (int it = 0; it < 3 && !converged && nvalid > 0; ++it) {
+    if (H == 0.f) stop = true;  // linearize(): hessian_ == 0 (:249)
+    const float step = b / (H + H * lambda);  // calculateStep (:252-256)
+    const float old = rho;
+    rho -= step;
+    if (stop) {  // the trial calculateEnergy() returns {0, 0}: rejectStep(); break (lm.hpp:95-98)
+      rho = old;
+      break;
+    }
+    const ActEval tr = act_eval(w, w.pairs, r, uv.x, uv.y, patch, rho, sigma, lane);
+    if (tr.n == 0) {
+      stop = true;
+      rho = old;
+      break;
+    }
+    if (tr.energy < energy) {  // acceptStep(): (idepth^2, step^2) (:258); function_tolerance = 0 never fires
+      if (step * step < 1e-8f * (rho * rho + 1e-8f)) converged = true;
+      energy = tr.energy;
+      nvalid = tr.n;
+      H = tr.H;
+      b = tr.b;
+      lambda *= 0.5f;
+    } else {
+      rho = old;  // rejectStep(): the previous (H, b) stay valid
+      lambda *= 5.f;
+    }
+  }
+  if (stop) rho = -1.f;  // the trailing calculateEnergy() with stop_ set (:150-153)
+  if (lane == 0) {
+    const bool act = !(nvalid < min_inliers || rho < 0.f);  // :308-314
+    idepth_out[c] = rho;
+    activate[c] = act ? 1 : 0;
+    n_valid_out[c] = nvalid;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-pair constants in fp64 (evaluate_jacobians.hpp:36-66, camera_reproject.hpp:235-260,
 // first_estimate_jacobians.hpp:28-37).  Sophus exp / Adj restated from the closed forms.
 // ------------------------------------------------------------------------------------------------
@@ -2534,6 +2675,15 @@ void launch_landmarks_energy(const WindowDev& w, int for_marg, double* scal, cud
   dim3 g((m + 255) / 256, w.n_frames * (w.n_frames - 1));
   ++g_launches;
   k_landmarks_energy<<<g, 256, 0, s>>>(w, for_marg, scal);
+}
+
+void launch_refine_immature(const WindowDev& w, int r, int n, const float* proj, const float* idepth_in, const float* patch8,
+                            int min_inliers, float sigma, float* idepth_out, uint8_t* activate, int* n_valid_out,
+                            cudaStream_t s) {
+  if (n <= 0) return;
+  ++g_launches;
+  k_refine_immature<<<(n + 7) / 8, 256, 0, s>>>(w, r, n, reinterpret_cast<const float2*>(proj), idepth_in, patch8, min_inliers,
+                                              sigma, idepth_out, activate, n_valid_out);
 }
 
 void launch_first_estimate(const WindowDev& w, cudaStream_t s) {

@@ -217,6 +217,18 @@ int dpba_landmarks_energy(dpba_handle* h, int32_t for_marginalized, double* ener
 int dpba_update_point_statuses(dpba_handle* h, int32_t minimum_valid_reprojections, double sigma_huber,
                                double* energy_threshold);
 
+/* ---- immature-landmark activation refine ------------------------------------------------- */
+/* optimizeImmatureLandmark for n candidates hosted by frame `ref_slot`
+ * (tracker/landmarks_activator/src/landmarks_activator.cpp:122-316): per candidate a 1-D Levenberg-Marquardt on the
+ * inverse depth over all other frames of the window at their CURRENT state (tWorldAgent, affine brightness), lambda0 =
+ * 0.1, <= 3 iterations.  proj_xy [n][2], idepth [n], patch [n][8].  Outputs (any may be NULL): refined idepth (-1 when
+ * the problem stopped), activate = 1 (kActivate) / 0 (kDelete: fewer valid residuals than min(minimum_inliers, N - 1)
+ * or negative idepth), valid residuals of the accepted state.  The frames must have been pushed (dpba_push_frame*). */
+int dpba_refine_immature_landmarks(dpba_handle* h, int32_t ref_slot, int32_t n, const float* proj_xy,
+                                   const float* idepth, const float* patch, int32_t minimum_inliers,
+                                   double sigma_huber, float* idepth_out, uint8_t* activate,
+                                   int32_t* number_of_valid_residuals);
+
 /* ---- device-resident solve --------------------------------------------------------------- */
 /* energy::levenberg_marquardt_algorithm::Options
  * (energy/problems/include/energy/levenberg_marquardt_algorithm/levenberg_marquardt_algorithm.hpp:38-57) plus the
