@@ -121,7 +121,7 @@ def config_dict(world, extra=None):
         "gn_iters_per_step": GN_ITERS,
         "lm": "levenberg_marquardt_algorithm::solve, force_accept, min_it=max_it=7, tolerances 0 (fixed work per step)",
         "parallelism": f"landmarks sharded over {world} GPU(s), frames replicated",
-        "l2": "256 MiB buffer written between timed steps (L2 flush); within a step the 39 MB image set is L2-resident",
+        "l2": "256 MiB buffer written between timed steps (L2 flush); within a step the 79 MB image set (32-byte texel-pair records) is L2-resident",
     }
     if extra:
         c.update(extra)
@@ -377,6 +377,22 @@ def run_ours(args):
         hh.profile_enable(False)
         return ms / max(cnt, 1)
 
+    # pure-write HBM bandwidth of this device for context: the materialising sweep is ~80 % stores, and a store stream
+    # does not reach the copy figure MEASURED_PEAKS.json holds (read + write bytes of a copy)
+    write_gbs = None
+    if rank == 0:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        big = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            big.fill_(1)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(5):
+            big.fill_(2)
+        ev1.record()
+        torch.cuda.synchronize()
+        write_gbs = 5 * big.numel() / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        del big
     sweep = sweep4 = None
     units4 = 0
     if rank == 0:
@@ -436,7 +452,11 @@ def run_ours(args):
                               "traffic": None, "algorithmic_bytes_per_launch": b4, "avg_launch_ms": sweep4,
                               "timing": "alone, L2 flushed before each launch, 10 launches",
                               "workload": f"configs[3] per-GPU shape at G=1: 8 KF x 20000 points, {units4} patch-residuals",
-                              "patch_residuals_per_s": units4 / (sweep4 * 1e-3)}
+                              "patch_residuals_per_s": units4 / (sweep4 * 1e-3),
+                              "hbm_write_only_gbs_measured": write_gbs,
+                              "note": "traffic = 750 MB per launch (ncu, profiles/): 600 MB of stores + 150 MB of loads; a pure "
+                                      "store stream (torch fill of 1 GiB) reaches hbm_write_only_gbs_measured on this device, "
+                                      "so launch time ~ stores / write rate + loads / read rate"}
     kernel_ms = {k: {"ms_total": v[0], "launches": v[1]} for k, v in prof.items() if v[1]}
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------------------

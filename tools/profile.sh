@@ -17,3 +17,6 @@ ncu --set full --clock-control none --import-source on -k regex:k_materialise_sw
 ncu --set full --clock-control none --import-source on -k regex:k_materialise_sweep -s 4 -c 2 -f -o gpurun_out/prof_k_materialise_sweep \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-big-sweep > gpurun_out/ncu_k_materialise_sweep.log 2>&1
 ls -la gpurun_out/
+# the coarse-tracker alignment kernel (one cluster launch = one LM solve)
+ncu --set full --clock-control none --import-source on -k regex:k_pose_align -s 14 -c 2 -f -o gpurun_out/prof_k_pose_align \
+    python tools/bench_pose_alignment.py > gpurun_out/ncu_k_pose_align.log 2>&1
