@@ -107,6 +107,7 @@ struct dpba_handle {
   int* fixed_dev = nullptr;
   int* fixed_h = nullptr;            // pinned
   bool use_graph = true;
+  bool speculative = true;           // dpba_solve_lm: trial evaluation == next linearisation under force_accept
   cudaGraphExec_t lm_graph_exec = nullptr;
   std::vector<long long> lm_graph_key;
   size_t lm_graph_events = 0;
@@ -1362,6 +1363,88 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
     return m;
   }();
   const int n_norm_parts = ((m_max + 31) / 32) * N;  // CTAs of k_back_substitute
+  // ---- speculative mode (single GPU, force_accept: the production options, fabric.cpp:99) -----------------------------
+  // Under force_accept a rejected step ends the loop, so the linear system of the PREVIOUS state is never needed again
+  // and the trial-state evaluation can be the next iteration's linearisation: the fused linearise carries the pair
+  // energies in the spare slots of its core records, so ONE sweep per iteration yields both E(x + step) and the system
+  // at x + step (the residual-only sweep of every iteration disappears).  The solve result (state, idepths, statuses,
+  // energy) is what the reference computes; only the auxiliary per-landmark fields (hpd, b_d, inv_hdd) are one accepted
+  // step FRESHER than the reference's at the end -- EigenPBA::solve recomputes them in its uncertainty pass anyway
+  // (eigen_photometric_bundle_adjustment.cpp:91-98).  After a rejected step they are recomputed at the restored state.
+  if (h->speculative && od.force_accept && !multi) {
+    const int n_pairs = N * (N - 1);
+    auto spec_linearize = [&](int ctl_mode) {
+      FusedShape shape;
+      {
+        ProfScope ps(h, 0);
+        shape = pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, ctl_mode);
+      }
+      return shape;
+    };
+    // Linearisation k (k = 0: the initial state, k >= 1: the trial state of step k) is followed by
+    //   main branch : core_reduce_k -> lm_energy_k (k = 0: result.energy; k >= 1: accept / reject of step k) -> lm_step_{k+1}
+    //                 -> back_substitute_{k+1} -> fused_{k+1}
+    //   side branch : finish_fused_k, assemble_k (needed by lm_step_{k+1}); accept_landmarks_k (needed by
+    //                 back_substitute_{k+1}); pair_setup_{k+1} (needed by fused_{k+1})
+    // so the critical path of an iteration is fused -> core_reduce -> energy -> step -> back-substitution.
+    FusedShape shape;
+    for (int k = 0; k <= od.max_it; ++k) {
+      const bool more = k < od.max_it;
+      shape = spec_linearize(1);
+      if (more) {
+        if ((rc = stream_edge(h, s, s2))) return rc;
+        ProfScope ps(h, 10, s2);
+        pba::launch_finish_fused(w, rb, shape, s2, h->ctl);
+      }
+      {
+        ProfScope ps(h, 8);
+        pba::launch_core_reduce(w, rb, shape, s, h->ctl);
+      }
+      if (more) {
+        if ((rc = stream_edge(h, s, s2))) return rc;
+        ProfScope ps(h, 9, s2);
+        pba::launch_assemble_blocks(w, fej, rb, shape, s2, h->ctl);
+      }
+      {
+        ProfScope ps(h, 11);
+        pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, rb.scal, Hm, bm,
+                              k == 0 ? pba::LM_ENERGY_INITIAL : pba::LM_ENERGY_TRIAL, s, rb.core, n_pairs,
+                              k ? rb.n_part : nullptr, k ? n_norm_parts : 0, 1);
+      }
+      if (more && (rc = stream_edge(h, s2, s))) return rc;  // finish_fused_k, assemble_k before lm_step_{k+1}
+      if (k > 0) {  // acceptStep() / rejectStep() of the landmarks incl. changeResidualStatuses
+        if ((rc = stream_edge(h, s, s2))) return rc;
+        ProfScope ps(h, 11, s2);
+        pba::launch_accept(w, 0, nullptr, s2, h->ctl, 1);
+      }
+      if (!more) {
+        if (k > 0 && (rc = stream_edge(h, s2, s))) return rc;
+        break;
+      }
+      {
+        ProfScope ps(h, 7);
+        pba::launch_lm_step(h->ctl, h->lmopt, h->fparams, h->fixed_dev, N, ro, Hm, bm, h->step_dev, s);
+      }
+      if (k > 0 && (rc = stream_edge(h, s2, s))) return rc;  // accept_k before back_substitute_{k+1}
+      if ((rc = stream_edge(h, s, s2))) return rc;
+      {
+        ProfScope ps(h, 6, s2);
+        pba::launch_pair_setup(h->fparams, N, h->pairs, h->pasm, s2);
+      }
+      {
+        ProfScope ps(h, 5);
+        pba::launch_back_substitute(w, h->step_dev, 0.0, s, h->ctl, rb.n_part);
+      }
+      if ((rc = stream_edge(h, s2, s))) return rc;
+    }
+    pairs();
+    spec_linearize(3);  // only after a rejected step: landmark fields back to the (restored) final state
+    if ((rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
+    return 0;
+  }
   // result.energy = problem.calculateEnergy()
   if ((rc = energy_eval(0, 0, pba::LM_ENERGY_INITIAL))) return rc;
   for (int it = 0; it < od.max_it; ++it) {
@@ -1459,6 +1542,7 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   // The launch sequence only depends on the window shape and a few options: capture it once into a CUDA graph and
   // replay it (one cudaGraphLaunch instead of ~110 launches per solve); all inputs travel through pinned buffers.
   std::vector<long long> key = {N, od.max_it, od.fej, H_marg != nullptr, h->world, (long long)h->profiling,
+                                (long long)(h->speculative && od.force_accept),
                                 (long long)llround(od.sigma * 1e6)};
   for (int f = 0; f < N; ++f) {
     key.push_back(h->fr[f].n_lm);
@@ -1528,6 +1612,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
   REQUIRE(h && name, "null argument");
   if (!strcmp(name, "cuda_graph")) {
     h->use_graph = value != 0;
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "speculative_linearize")) {
+    h->speculative = value != 0;
+    h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
   if (!strcmp(name, "schur_tensor_cores")) {  // process-wide

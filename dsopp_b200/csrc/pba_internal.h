@@ -116,6 +116,7 @@ struct LmCtl {
   int n_valid, next_n;
   int converged, done, system_valid, accept, iteration, iterations_executed;
   int apply;  // the last trial-energy kernel ran: k_accept_landmarks must apply ctl->accept
+  int relin;  // speculative mode: a trial step was rejected after its linearisation overwrote the landmark fields
 };
 
 namespace pba {
@@ -125,7 +126,7 @@ void launch_lm_init(LmCtl* ctl, const LmOptionsDev* opt, cudaStream_t s);
 void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s);
 void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, double* scal,
                       const double* Hmarg, const double* bmarg, int kind, cudaStream_t s, const double* e_part = nullptr,
-                      int n_e = 0, const double* n_part = nullptr, int n_n = 0);
+                      int n_e = 0, const double* n_part = nullptr, int n_n = 0, int from_core = 0);
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
                     const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s);
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
@@ -143,7 +144,7 @@ void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, in
                         double* scal, cudaStream_t s);
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s);
 FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
-                                  cudaStream_t s, const LmCtl* ctl = nullptr);
+                                  cudaStream_t s, const LmCtl* ctl = nullptr, int ctl_mode = 2);
 void launch_linearize_from_materialized(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
 int launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,

@@ -100,6 +100,7 @@ __device__ __forceinline__ size_t res_index(const WindowDev& w, int r, int t, in
 // linearisation kernels also when the previous linear system is still valid (mode 2)
 __device__ __forceinline__ bool lm_skip(const LmCtl* ctl, int mode) {
   if (!ctl || mode == 0) return false;
+  if (mode == 3) return !ctl->relin;  // re-linearisation at the restored state after a rejected speculative step
   if (ctl->done) return true;
   return mode == 2 && ctl->system_valid;
 }
@@ -592,8 +593,9 @@ __global__ void __launch_bounds__(256, 6) k_materialise_sweep(const __grid_const
 template <bool FEJ, int NWMAX, int MINB>
 __global__ void __launch_bounds__(32 * NWMAX, MINB)
     k_linearize_fused(const __grid_constant__ WindowDev w, float sigma, int huber, int for_marg, int lpb,
-                      float* __restrict__ core_part, float* __restrict__ schur_part, const LmCtl* __restrict__ ctl) {
-  if (lm_skip(ctl, 2)) return;
+                      float* __restrict__ core_part, float* __restrict__ schur_part, const LmCtl* __restrict__ ctl,
+                      int ctl_mode) {
+  if (lm_skip(ctl, ctl_mode)) return;
   extern __shared__ __align__(16) float smem[];
   const int N = w.n_frames;
   const int D = 8 * N;
@@ -625,6 +627,9 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
   float acc[44];  // 36 (upper triangle of the core) + 8 (core^T r); padded to PBA_CORE only for the final reduction
 #pragma unroll
   for (int k = 0; k < 44; ++k) acc[k] = 0.f;
+  // calculateLandmarksEnergy of this pair's residuals (problem.hpp:124-133) rides in the two spare slots of the core
+  // record, so that a linearisation at a trial state also IS the energy evaluation there (device LM, speculative mode)
+  float e_acc = 0.f, n_acc = 0.f;
 
   for (int it = 0; it < lpb; it += 4) {
     const int ls = it + grp;  // slot in the chunk
@@ -643,6 +648,10 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
       if (!o.ok) w.cand[res] = K_OOB;
       else if (o.ev) w.cand[res] = K_OK;
       w.energy[res] = o.e;
+      if (!(lm.flags & LM_MARG)) {
+        e_acc += o.e;
+        n_acc += o.e > 0.f ? 1.f : 0.f;
+      }
     }
     // landmark selection of K3/K4 (hessian_block_evaluation.hpp:68-72,190-194)
     const bool sel = !skip && (for_marg ? (lm.flags & LM_TO_MARG) != 0 : (lm.flags & LM_MARG) == 0);
@@ -685,7 +694,7 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
   {
     float v48[PBA_CORE], v24[24], v12[12], v6[6], v3[3], v2[2];
 #pragma unroll
-    for (int k = 0; k < PBA_CORE; ++k) v48[k] = k < 44 ? acc[k] : 0.f;
+    for (int k = 0; k < PBA_CORE; ++k) v48[k] = k < 44 ? acc[k] : (k == 44 ? e_acc : (k == 45 ? n_acc : 0.f));
     tr_step<48, 16>(v48, v24, lane);
     tr_step<24, 8>(v24, v12, lane);
     tr_step<12, 4>(v12, v6, lane);
@@ -2059,6 +2068,7 @@ __global__ void k_lm_init(LmCtl* ctl, const LmOptionsDev* opt) {
   ctl->system_valid = 0;
   ctl->accept = 0;
   ctl->apply = 0;
+  ctl->relin = 0;
   ctl->iteration = 0;
   ctl->iterations_executed = 0;
 }
@@ -2088,7 +2098,9 @@ __device__ __forceinline__ double block_sum_256(double v, double* red /*[8]*/) {
 __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
                                                    int N, double* scal, const double* Hmarg,
                                                    const double* bmarg, int kind, const double2* __restrict__ e_part,
-                                                   int n_e, const double2* __restrict__ n_part, int n_n) {
+                                                   int n_e, const double2* __restrict__ n_part, int n_n, int from_core) {
+  // from_core: e_part is the per-pair core array (k_core_reduce): entry (r, t) holds (energy, n_valid) of the pair in
+  // slots 44 / 45 of its 48-double record; n_e = N (N - 1) ordered pairs
   if (kind == pba::LM_ENERGY_TRIAL && ctl->done) {
     if (threadIdx.x == 0) ctl->apply = 0;
     return;
@@ -2100,7 +2112,14 @@ __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDe
   if (e_part) {  // single-GPU: the second stage of the (energy, n) / norm reductions happens here, no extra launch
     double a = 0, b = 0, c = 0, d = 0;
     for (int k = i; k < n_e; k += 256) {
-      const double2 v = e_part[k];
+      size_t idx = k;
+      if (from_core) {
+        const int r = k / (N - 1);
+        int t = k % (N - 1);
+        t += (t >= r);
+        idx = ((size_t)(r * PBA_MAXF + t) * PBA_CORE + 44) / 2;
+      }
+      const double2 v = e_part[idx];
       a += v.x;
       b += v.y;
     }
@@ -2160,6 +2179,7 @@ __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDe
         if (fabs(ctl->energy - E) / ctl->energy < opt->ftol) ctl->converged = 1;  // before the accept test (Q7)
         ctl->accept = (E < ctl->energy || (opt->force_accept && ctl->iteration < opt->min_it)) ? 1 : 0;
       }
+      if (ctl->accept <= 0) ctl->relin = 1;  // speculative mode: the landmark fields now belong to a rejected state
       ctl->apply = 1;
       s_accept = ctl->accept;
     }
@@ -2427,10 +2447,10 @@ void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s
 
 void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, double* scal,
                       const double* Hmarg, const double* bmarg, int kind, cudaStream_t s, const double* e_part, int n_e,
-                      const double* n_part, int n_n) {
+                      const double* n_part, int n_n, int from_core) {
   ++g_launches;
   k_lm_energy<<<1, 256, 0, s>>>(ctl, opt, fr, N, scal, Hmarg, bmarg, kind, reinterpret_cast<const double2*>(e_part), n_e,
-                                reinterpret_cast<const double2*>(n_part), n_n);
+                                reinterpret_cast<const double2*>(n_part), n_n, from_core);
 }
 
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
@@ -2544,7 +2564,8 @@ void set_fused_min_blocks(int b) { g_fused_minb = b <= 3 ? 3 : 4; }
 
 template <int NWMAX, int MINB>
 static void launch_fused_t(const WindowDev& w, float sigma, int huber, int fej, int for_marg, int lpb, dim3 g,
-                           int threads, size_t smem, float* core, float* schur, cudaStream_t s, const LmCtl* ctl) {
+                           int threads, size_t smem, float* core, float* schur, cudaStream_t s, const LmCtl* ctl,
+                           int ctl_mode) {
   static bool attr[2] = {false, false};
   if (smem > 48 * 1024 && !attr[fej ? 1 : 0]) {
     if (fej) cudaFuncSetAttribute(k_linearize_fused<true, NWMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -2552,12 +2573,12 @@ static void launch_fused_t(const WindowDev& w, float sigma, int huber, int fej, 
     attr[fej ? 1 : 0] = true;
   }
   ++g_launches;
-  if (fej) k_linearize_fused<true, NWMAX, MINB><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl);
-  else k_linearize_fused<false, NWMAX, MINB><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl);
+  if (fej) k_linearize_fused<true, NWMAX, MINB><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl, ctl_mode);
+  else k_linearize_fused<false, NWMAX, MINB><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl, ctl_mode);
 }
 
 FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
-                                  cudaStream_t s, const LmCtl* ctl) {
+                                  cudaStream_t s, const LmCtl* ctl, int ctl_mode) {
   FusedShape shape{0, 0};
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return shape;
@@ -2580,9 +2601,9 @@ FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, in
   const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + (size_t)lpb * (D + 2 + 2 * (N - 1)) * sizeof(float);
   dim3 g((m + lpb - 1) / lpb, N);
   const int threads = 32 * (N - 1);
-  if (N <= 9 && minb == 4) launch_fused_t<8, 4>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
-  else if (N <= 9) launch_fused_t<8, 3>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
-  else launch_fused_t<15, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl);
+  if (N <= 9 && minb == 4) launch_fused_t<8, 4>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode);
+  else if (N <= 9) launch_fused_t<8, 3>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode);
+  else launch_fused_t<15, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode);
   shape.lpb = lpb;
   shape.chunks = (int)g.x;
   return shape;
