@@ -1624,6 +1624,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "fused_prefetch")) {  // process-wide A/B switch
+    pba::set_fused_prefetch(value != 0);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
   if (!strcmp(name, "fused_min_blocks")) {  // process-wide: 4 (64 registers per thread) or 3 (96)
     pba::set_fused_min_blocks((int)value);
     h->lm_graph_key.clear();

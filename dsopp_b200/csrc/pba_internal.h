@@ -171,4 +171,5 @@ long long launch_count();
 void add_launches(long long n);
 void set_schur_mma(bool on);
 void set_fused_min_blocks(int b);
+void set_fused_prefetch(bool on);
 }  // namespace pba

@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(256, 6) k_materialise_sweep(const __grid_const
 // time keeping its pair's 44 running sums in registers, so the per-landmark quantities that couple the targets
 // (H_pd, H_dd, b_d) meet in shared memory.
 // ------------------------------------------------------------------------------------------------
-template <bool FEJ, int NWMAX, int MINB>
+template <bool FEJ, int NWMAX, int MINB, bool PREFETCH>
 __global__ void __launch_bounds__(32 * NWMAX, MINB)
     k_linearize_fused(const __grid_constant__ WindowDev w, float sigma, int huber, int for_marg, int lpb,
                       float* __restrict__ core_part, float* __restrict__ schur_part, const LmCtl* __restrict__ ctl,
@@ -610,18 +610,33 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
   float* bd_s = hdd_s + lpb;                                         // [lpb] weight * b_d
   float* hdd_w = bd_s + lpb;                                         // [lpb][nwarps] per-target H_dd terms
   float* bd_w = hdd_w + lpb * nwarps;                                // [lpb][nwarps] per-target b_d terms
+  // the chunk's landmark records, staged once and shared by the N - 1 target warps (16-byte aligned: every term above
+  // is a multiple of 4 floats when lpb is)
+  LandmarkRec* recs = reinterpret_cast<LandmarkRec*>(bd_w + lpb * nwarps + ((4 - ((lpb * (D + 2 + 2 * nwarps)) & 3)) & 3));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int px = lane & 7, grp = lane >> 3;
   const int t = warp + (warp >= f);
+  const int lm_base = lm_index(w, f, 0);
 
   for (int i = threadIdx.x; i < lpb * (D + 2 + 2 * nwarps); i += blockDim.x) hpd_s[i] = 0.f;
   reinterpret_cast<float4*>(&pcs[warp])[lane] = reinterpret_cast<const float4*>(&w.pairs[f * PBA_MAXF + t])[lane];
+  for (int i = threadIdx.x; i < lpb; i += blockDim.x) {
+    const int gl = lm_base + min(l0 + i, M - 1);
+    LandmarkRec r;
+    r.k = w.lmk[gl];
+    const float4 p0 = ldf4(w.patch + (size_t)gl * 8), p1 = ldf4(w.patch + (size_t)gl * 8 + 4);
+    r.patch[0] = p0.x, r.patch[1] = p0.y, r.patch[2] = p0.z, r.patch[3] = p0.w;
+    r.patch[4] = p1.x, r.patch[5] = p1.y, r.patch[6] = p1.z, r.patch[7] = p1.w;
+    r.step = w.idepth_step[gl];
+    r.flags = w.flags[gl];
+    r.pad0 = r.pad1 = 0.f;
+    recs[i] = r;
+  }
   __syncthreads();
   const PairConst& pc = pcs[warp];
   const float4* img = w.img[t];
   const uint8_t* mask = w.mask_all[t] ? nullptr : w.mask[t];
   const float pox = pat_x(px), poy = pat_y(px);
-  const int lm_base = lm_index(w, f, 0);
   const size_t res_base = res_index(w, f, t, 0);
 
   float acc[44];  // 36 (upper triangle of the core) + 8 (core^T r); padded to PBA_CORE only for the final reduction
@@ -636,7 +651,29 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
     const int l = l0 + ls;
     const bool inb = l < M;
     const int li = inb ? l : 0;
-    LandmarkIn lm = load_landmark(w, lm_base + li, px);
+    if (PREFETCH && it + 4 < lpb) {
+      // The warp stalls longest on the L2 gathers of the bilinear taps (r01f capture: the first consumer of the taps
+      // holds ~20 % of the stall samples).  The NEXT group's records are already in shared memory, so its tap
+      // addresses cost a few FMAs: prefetch those two 32-byte records into L1 while this group's arithmetic runs.
+      const LandmarkRec& nx = recs[min(ls + 4, lpb - 1)];
+      const float un = nx.k.x + pox, vn = nx.k.y + poy, rn = nx.k.z + nx.step;
+      const float Xn = pc.A[0] * un + pc.A[1] * vn + (pc.A[2] + pc.A[3] * rn);
+      const float Yn = pc.A[4] * un + pc.A[5] * vn + (pc.A[6] + pc.A[7] * rn);
+      const float Zn = pc.A[8] * un + pc.A[9] * vn + (pc.A[10] + pc.A[11] * rn);
+      const float rzn = rcp_approx(Zn);
+      const int ixn = min(max((int)(Xn * rzn), 0), w.W - 2), iyn = min(max((int)(Yn * rzn), 0), w.H - 2);
+      const float4* pn = img + ((size_t)iyn * w.W + ixn) * 2;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pn));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + 2 * (size_t)w.W));
+    }
+    const LandmarkRec& rec = recs[inb ? ls : 0];
+    LandmarkIn lm;
+    lm.u = rec.k.x;
+    lm.v = rec.k.y;
+    lm.rho = rec.k.z + rec.step;
+    lm.rho0 = rec.k.w;
+    lm.patch = rec.patch[px];
+    lm.flags = rec.flags;
     const bool skip = !inb || ((lm.flags & LM_MARG) && !(lm.flags & LM_TO_MARG));
     const size_t res = res_base + li;
     const int status = skip ? K_OUTLIER : w.status[res];
@@ -2562,19 +2599,30 @@ void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fe
 int g_fused_minb = 3;  // resident CTAs per SM the fused linearise is compiled for (N <= 9): 4 -> 64 registers, 3 -> 80
 void set_fused_min_blocks(int b) { g_fused_minb = b <= 3 ? 3 : 4; }
 
-template <int NWMAX, int MINB>
-static void launch_fused_t(const WindowDev& w, float sigma, int huber, int fej, int for_marg, int lpb, dim3 g,
+bool g_fused_prefetch = false;  // L1 prefetch of the next group's image taps: measured 42.6 us against 39.1 us without (issue-bound kernel), kept as an A/B switch (option "fused_prefetch")
+void set_fused_prefetch(bool on) { g_fused_prefetch = on; }
+
+template <int NWMAX, int MINB, bool PF>
+static void launch_fused_tp(const WindowDev& w, float sigma, int huber, int fej, int for_marg, int lpb, dim3 g,
                            int threads, size_t smem, float* core, float* schur, cudaStream_t s, const LmCtl* ctl,
                            int ctl_mode) {
   static bool attr[2] = {false, false};
   if (smem > 48 * 1024 && !attr[fej ? 1 : 0]) {
-    if (fej) cudaFuncSetAttribute(k_linearize_fused<true, NWMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    else cudaFuncSetAttribute(k_linearize_fused<false, NWMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (fej) cudaFuncSetAttribute(k_linearize_fused<true, NWMAX, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    else cudaFuncSetAttribute(k_linearize_fused<false, NWMAX, MINB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr[fej ? 1 : 0] = true;
   }
   ++g_launches;
-  if (fej) k_linearize_fused<true, NWMAX, MINB><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl, ctl_mode);
-  else k_linearize_fused<false, NWMAX, MINB><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl, ctl_mode);
+  if (fej) k_linearize_fused<true, NWMAX, MINB, PF><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl, ctl_mode);
+  else k_linearize_fused<false, NWMAX, MINB, PF><<<g, threads, smem, s>>>(w, sigma, huber, for_marg, lpb, core, schur, ctl, ctl_mode);
+}
+
+template <int NWMAX, int MINB>
+static void launch_fused_t(const WindowDev& w, float sigma, int huber, int fej, int for_marg, int lpb, dim3 g,
+                           int threads, size_t smem, float* core, float* schur, cudaStream_t s, const LmCtl* ctl,
+                           int ctl_mode) {
+  if (g_fused_prefetch) launch_fused_tp<NWMAX, MINB, true>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, core, schur, s, ctl, ctl_mode);
+  else launch_fused_tp<NWMAX, MINB, false>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, core, schur, s, ctl, ctl_mode);
 }
 
 FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
@@ -2598,7 +2646,8 @@ FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, in
       lpb = cand;
     }
   }
-  const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + (size_t)lpb * (D + 2 + 2 * (N - 1)) * sizeof(float);
+  const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + ((size_t)lpb * (D + 2 + 2 * (N - 1)) + 3) * sizeof(float) +
+                      (size_t)lpb * sizeof(LandmarkRec);
   dim3 g((m + lpb - 1) / lpb, N);
   const int threads = 32 * (N - 1);
   if (N <= 9 && minb == 4) launch_fused_t<8, 4>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode);
