@@ -78,6 +78,14 @@ struct dpba_handle {
   float4* lmk = nullptr;  // {u, v, idepth, idepth at the FEJ linearisation point}
   float *idepth_step = nullptr, *patch = nullptr;
   float* lm_slab = nullptr;  // owns idepth_step, inv_hdd, b_d, rel_baseline, n_inliers ([5][max_frames * max_pts])
+  // Host mirror of everything updateFrame reads (photometric_bundle_adjustment.cpp:182-264), filled by ONE bulk readback
+  // on the first dpba_get_* after the device state changed; later getters are plain memcpy's.  The reference always
+  // follows solve() by updateFrame for every active frame (monocular_tracker.cpp:251-256).
+  bool rb_valid = false;
+  float* rb_slab = nullptr;     // pinned [5][max_frames * max_pts]
+  float4* rb_lmk = nullptr;     // pinned
+  uint8_t* rb_flags = nullptr;  // pinned
+  uint8_t *rb_status = nullptr, *rb_cand = nullptr;  // pinned, first max_frames * 16 rows
   // pinned staging arena for the small host arrays (landmarks, statuses): the caller's buffer is copied here and
   // DMA'd asynchronously, so set_* calls return without a stream synchronisation and the caller may reuse its buffer
   char* arena_h = nullptr;
@@ -282,6 +290,7 @@ ReduceBuf redbuf_out(dpba_handle* h) {
 }
 
 WindowDev make_window(dpba_handle* h) {
+  h->rb_valid = false;  // every kernel-launching path builds its WindowDev here: the device state is about to change
   WindowDev w;
   memset(&w, 0, sizeof(w));
   w.n_frames = h->n_frames;
@@ -415,11 +424,28 @@ void host_se3_exp_translation(const double* T_lin, const double* eps, double* t_
     t_out[i] = T_lin[i * 4 + 3] + T_lin[i * 4 + 0] * tv[0] + T_lin[i * 4 + 1] * tv[1] + T_lin[i * 4 + 2] * tv[2];
 }
 
+// one bulk device -> pinned host readback of the landmark arrays and residual statuses
+int ensure_readback(dpba_handle* h) {
+  if (h->rb_valid) return 0;
+  const size_t mp = h->cfg.max_points_per_frame, nlm = (size_t)h->cfg.max_frames * mp;
+  const size_t nst = (size_t)h->cfg.max_frames * PBA_MAXF * mp;
+  CK(cudaMemcpyAsync(h->rb_slab, h->lm_slab, 5 * nlm * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->rb_lmk, h->lmk, nlm * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->rb_flags, h->flags, nlm, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->rb_status, h->status, nst, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->rb_cand, h->cand, nst, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->arena_used = 0;  // the stream is idle
+  h->rb_valid = true;
+  return 0;
+}
+
 int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int channels, const uint8_t* mask,
                       const double* T, double exposure, const double* ab0, const double* intr, int32_t fixed) {
   REQUIRE(h, "null handle");
   REQUIRE(image && T && ab0 && intr, "null argument");
   if (h->n_frames >= h->cfg.max_frames) return fail(h, DPBA_E_CAPACITY, "window is full");
+  h->rb_valid = false;
   REQUIRE(!fixed || h->n_frames == 0, "only the first frame can be fixed (hessian_block_evaluation.hpp:143)");
   REQUIRE(exposure > 0, "exposure_time must be positive");
   int phys = -1;
@@ -476,6 +502,7 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
 int upload_landmarks(dpba_handle* h, int slot, int first, int n, const float* uv, const float* idepth,
                      const float* patch, const uint8_t* flags) {
   const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame + first;
+  h->rb_valid = false;
   if (n == 0) return 0;
   float4* lk = (float4*)arena_alloc(h, sizeof(float4) * n);
   float* pt = (float*)arena_alloc(h, sizeof(float) * 8 * n);
@@ -608,6 +635,11 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   h->arena_cap = 2 * ((size_t)cfg->max_frames * (mp * 64 + 1024) + (size_t)cfg->max_frames * cfg->max_frames * (mp + 256)) +
                  4 * npx + 4096;  // + raw 8-bit frames and vignetting of the device-side image preparation
   CKC(cudaMallocHost(&h->arena_h, h->arena_cap));
+  CKC(cudaMallocHost(&h->rb_slab, 5 * nlm * sizeof(float)));
+  CKC(cudaMallocHost(&h->rb_lmk, nlm * sizeof(float4)));
+  CKC(cudaMallocHost(&h->rb_flags, nlm));
+  CKC(cudaMallocHost(&h->rb_status, (size_t)cfg->max_frames * PBA_MAXF * mp));
+  CKC(cudaMallocHost(&h->rb_cand, (size_t)cfg->max_frames * PBA_MAXF * mp));
 #undef CKC
   *out = h;
   return DPBA_SUCCESS;
@@ -642,6 +674,11 @@ int dpba_destroy(dpba_handle* h) {
   cudaFreeHost(h->red_h);
   cudaFreeHost(h->stage_h);
   cudaFreeHost(h->arena_h);
+  cudaFreeHost(h->rb_slab);
+  cudaFreeHost(h->rb_lmk);
+  cudaFreeHost(h->rb_flags);
+  cudaFreeHost(h->rb_status);
+  cudaFreeHost(h->rb_cand);
   cudaFreeHost(h->ctl_h);
   cudaFreeHost(h->lmopt_h);
   cudaFreeHost(h->marg_h);
@@ -779,6 +816,7 @@ int dpba_refine_immature_landmarks(dpba_handle* h, int32_t ref_slot, int32_t n, 
 int dpba_remove_frame(dpba_handle* h, int32_t slot) {
   REQUIRE(h, "null handle");
   REQUIRE(slot >= 0 && slot < h->n_frames, "slot out of range");
+  h->rb_valid = false;
   h->phys_used[h->fr[slot].phys] = false;
   for (int f = slot; f + 1 < h->n_frames; ++f) h->fr[f] = h->fr[f + 1];
   --h->n_frames;
@@ -837,6 +875,7 @@ int dpba_set_landmark_flags(dpba_handle* h, int32_t slot, int32_t n, const uint8
   REQUIRE(h, "null handle");
   REQUIRE(slot >= 0 && slot < h->n_frames && flags, "bad argument");
   REQUIRE(n == h->fr[slot].n_lm, "flag count must equal the landmark count");
+  h->rb_valid = false;
   const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame;
   if (n) {
     uint8_t* st = (uint8_t*)arena_alloc(h, n);
@@ -859,38 +898,18 @@ int dpba_get_landmarks(dpba_handle* h, int32_t slot, int32_t n, float* idepth, f
   REQUIRE(n >= 0 && n <= h->fr[slot].n_lm, "n exceeds the landmark count");
   const size_t base = (size_t)h->fr[slot].phys * h->cfg.max_points_per_frame;
   if (n == 0) return DPBA_SUCCESS;
-  // device -> pinned arena (asynchronous, one synchronisation) -> caller; a direct copy into pageable memory would
-  // synchronise once per array.  The arena is emptied first so that it cannot wrap in the middle of this call.
-  CK(cudaStreamSynchronize(h->stream));
-  h->arena_used = 0;
+  int rc = ensure_readback(h);
+  if (rc) return rc;
   const size_t nlm = (size_t)h->cfg.max_frames * h->cfg.max_points_per_frame;
-  float* slab = nullptr;  // [5][n]: idepth_step, inv_hdd, b_d, rel_baseline, n_inliers
-  float* idp = nullptr;
-  uint8_t* flg = nullptr;
-  if (idepth_step || inv_hdd || b_d || n_inl || rel_baseline) {
-    if (!(slab = (float*)arena_alloc(h, 5 * sizeof(float) * n))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
-    CK(cudaMemcpy2DAsync(slab, sizeof(float) * n, h->lm_slab + base, nlm * sizeof(float), sizeof(float) * n, 5,
-                         cudaMemcpyDeviceToHost, h->stream));
-  }
-  if (idepth) {
-    if (!(idp = (float*)arena_alloc(h, sizeof(float) * n))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
-    CK(cudaMemcpy2DAsync(idp, sizeof(float), reinterpret_cast<const float*>(h->lmk + base) + 2, sizeof(float4),
-                         sizeof(float), n, cudaMemcpyDeviceToHost, h->stream));
-  }
-  if (flags) {
-    if (!(flg = (uint8_t*)arena_alloc(h, n))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
-    CK(cudaMemcpyAsync(flg, h->flags + base, n, cudaMemcpyDeviceToHost, h->stream));
-  }
-  CK(cudaStreamSynchronize(h->stream));
   const size_t nb = sizeof(float) * n;
-  if (idepth) memcpy(idepth, idp, nb);
-  if (idepth_step) memcpy(idepth_step, slab, nb);
-  if (inv_hdd) memcpy(inv_hdd, slab + n, nb);
-  if (b_d) memcpy(b_d, slab + 2 * (size_t)n, nb);
-  if (rel_baseline) memcpy(rel_baseline, slab + 3 * (size_t)n, nb);
-  if (n_inl) memcpy(n_inl, slab + 4 * (size_t)n, nb);
-  if (flags) memcpy(flags, flg, n);
-  h->arena_used = 0;  // the stream is idle: nothing references the arena any more
+  if (idepth)
+    for (int l = 0; l < n; ++l) idepth[l] = h->rb_lmk[base + l].z;
+  if (idepth_step) memcpy(idepth_step, h->rb_slab + base, nb);
+  if (inv_hdd) memcpy(inv_hdd, h->rb_slab + nlm + base, nb);
+  if (b_d) memcpy(b_d, h->rb_slab + 2 * nlm + base, nb);
+  if (rel_baseline) memcpy(rel_baseline, h->rb_slab + 3 * nlm + base, nb);
+  if (n_inl) memcpy(n_inl, h->rb_slab + 4 * nlm + base, nb);
+  if (flags) memcpy(flags, h->rb_flags + base, n);
   return DPBA_SUCCESS;
 }
 
@@ -907,6 +926,7 @@ int dpba_get_pose_idepth_blocks(dpba_handle* h, int32_t slot, int32_t n, float* 
 }
 
 static int set_statuses_row(dpba_handle* h, int r, int t, int n, const uint8_t* st) {
+  h->rb_valid = false;
   const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
   if (!n) return 0;
   uint8_t* stg = (uint8_t*)arena_alloc(h, n);
@@ -928,6 +948,7 @@ int dpba_set_frame_statuses(dpba_handle* h, int32_t r, int32_t n, const uint8_t*
   REQUIRE(h, "null handle");
   REQUIRE(r >= 0 && r < h->n_frames && per_target, "bad argument");
   REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
+  h->rb_valid = false;
   if (n == 0) return DPBA_SUCCESS;
   // The residual vectors (r -> t) of one reference frame are rows [phys_t] of one contiguous [16][max_pts] block.
   // When every other frame is given, the rows are packed in the arena in device layout and sent with ONE copy per
@@ -971,33 +992,15 @@ int dpba_get_frame_statuses(dpba_handle* h, int32_t r, int32_t n, uint8_t* const
   REQUIRE(r >= 0 && r < h->n_frames, "bad argument");
   REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
   if (n == 0) return DPBA_SUCCESS;
-  CK(cudaStreamSynchronize(h->stream));  // empty the arena first: it must not wrap in the middle of this call
-  h->arena_used = 0;
-  // one copy per array for the whole [phys lo .. phys hi] row range of reference r, then scattered on the host
-  int lo = PBA_MAXF, hi = -1;
-  for (int t = 0; t < h->n_frames; ++t) {
-    lo = std::min(lo, h->fr[t].phys);
-    hi = std::max(hi, h->fr[t].phys);
-  }
-  const size_t mp = h->cfg.max_points_per_frame, rows = (size_t)(hi - lo + 1);
-  const size_t base = ((size_t)h->fr[r].phys * PBA_MAXF + lo) * mp;
-  uint8_t *ss = nullptr, *sc = nullptr;
-  if (statuses) {
-    if (!(ss = (uint8_t*)arena_alloc(h, rows * mp))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
-    CK(cudaMemcpyAsync(ss, h->status + base, rows * mp, cudaMemcpyDeviceToHost, h->stream));
-  }
-  if (candidates) {
-    if (!(sc = (uint8_t*)arena_alloc(h, rows * mp))) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
-    CK(cudaMemcpyAsync(sc, h->cand + base, rows * mp, cudaMemcpyDeviceToHost, h->stream));
-  }
-  CK(cudaStreamSynchronize(h->stream));
+  int rc = ensure_readback(h);
+  if (rc) return rc;
+  const size_t mp = h->cfg.max_points_per_frame;
   for (int t = 0; t < h->n_frames; ++t) {
     if (t == r) continue;
-    const size_t off = (size_t)(h->fr[t].phys - lo) * mp;
-    if (ss && statuses[t]) memcpy(statuses[t], ss + off, n);
-    if (sc && candidates[t]) memcpy(candidates[t], sc + off, n);
+    const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * mp;
+    if (statuses && statuses[t]) memcpy(statuses[t], h->rb_status + base, n);
+    if (candidates && candidates[t]) memcpy(candidates[t], h->rb_cand + base, n);
   }
-  h->arena_used = 0;
   return DPBA_SUCCESS;
 }
 
@@ -1006,9 +1009,10 @@ int dpba_get_statuses(dpba_handle* h, int32_t r, int32_t t, int32_t n, uint8_t* 
   REQUIRE(r >= 0 && r < h->n_frames && t >= 0 && t < h->n_frames && r != t, "bad pair");
   REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
   const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
-  if (n && st) CK(cudaMemcpyAsync(st, h->status + base, n, cudaMemcpyDeviceToHost, h->stream));
-  if (n && cand) CK(cudaMemcpyAsync(cand, h->cand + base, n, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  int rc = ensure_readback(h);
+  if (rc) return rc;
+  if (n && st) memcpy(st, h->rb_status + base, n);
+  if (n && cand) memcpy(cand, h->rb_cand + base, n);
   return DPBA_SUCCESS;
 }
 
@@ -1513,6 +1517,7 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   REQUIRE(h->n_frames >= 2, "need at least two frames");
   REQUIRE((H_marg == nullptr) == (b_marg == nullptr), "H_marg and b_marg must be given together");
   REQUIRE(o->max_num_iterations >= 0 && o->max_num_iterations <= 64, "max_num_iterations out of range");
+  h->rb_valid = false;  // a graph replay does not pass through make_window()
   const int N = h->n_frames, D = 8 * N;
   LmOptionsDev& od = *h->lmopt_h;
   od.max_it = o->max_num_iterations;
