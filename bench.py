@@ -437,7 +437,11 @@ def run_ours(args):
     achieved = fused_bytes / (fused_avg * 1e-3) / 1e9 if fused_avg > 0 else 0.0
     roofline = {"kernel": "k_linearize_fused (K1+K3+K4a, nothing materialised)", "bound": "hbm",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": None, "peak_source": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+                # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture of this
+                # configuration (profiles/r01h_k_linearize_fused.md; cold L2: the 79 MB image set is read in part)
+                "traffic": (60.58e6 + 2.60e6) if (world == 1 and N_FRAMES == 8 and PTS_PER_GPU == 2000) else None,
+                "traffic_source": "profiles/r01h_k_linearize_fused.md",
+                "peak_source": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_launch": fused_bytes, "avg_launch_ms": fused_avg, "launches_timed": fused_n,
                 "note": "fused linearise is bound by fp32 issue + L2 gathers, not HBM (SURVEY 8d: ~90 FLOP/B); "
                         "see roofline_sweep for the HBM-bound materialising sweep the 60% target is stated on"}
@@ -445,7 +449,9 @@ def run_ours(args):
     sweep_ach = sweep_bytes / (sweep * 1e-3) / 1e9 if sweep else 0.0
     roofline_sweep = {"kernel": "k_materialise_sweep (K1, reference-surface mode, 595 B/unit)", "bound": "hbm",
                       "achieved": sweep_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                      "frac": sweep_ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": sweep_bytes,
+                      "frac": sweep_ach / peaks["hbm_gbs"],
+                      "traffic": (60.51e6 + 22.97e6) if (N_FRAMES == 8 and PTS_PER_GPU == 2000) else None,  # profiles/r01h_k_materialise_sweep.md (65 MB of the stores are still in L2 when the kernel ends)
+                      "algorithmic_bytes_per_launch": sweep_bytes,
                       "avg_launch_ms": sweep, "timing": "alone, L2 flushed before each launch, 10 launches",
                       "workload": f"configs[1], {units_local} patch-residuals"}
     roofline_sweep_big = None
@@ -454,7 +460,8 @@ def run_ours(args):
         a4 = b4 / (sweep4 * 1e-3) / 1e9
         roofline_sweep_big = {"kernel": "k_materialise_sweep (K1, reference-surface mode, 595 B/unit)", "bound": "hbm",
                               "achieved": a4, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a4 / peaks["hbm_gbs"],
-                              "traffic": None, "algorithmic_bytes_per_launch": b4, "avg_launch_ms": sweep4,
+                              "traffic": 155.45e6 + 600.48e6,  # profiles/r01h_k_materialise_sweep_big.md
+                              "algorithmic_bytes_per_launch": b4, "avg_launch_ms": sweep4,
                               "timing": "alone, L2 flushed before each launch, 10 launches",
                               "workload": f"configs[3] per-GPU shape at G=1: 8 KF x 20000 points, {units4} patch-residuals",
                               "patch_residuals_per_s": units4 / (sweep4 * 1e-3),
