@@ -123,7 +123,6 @@ namespace pba {
 // kinds for launch_lm_energy
 enum { LM_ENERGY_INITIAL = 0, LM_ENERGY_TRIAL = 1, LM_ENERGY_FINAL = 2 };
 void launch_lm_init(LmCtl* ctl, const LmOptionsDev* opt, cudaStream_t s);
-void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s);
 void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, double* scal,
                       const double* Hmarg, const double* bmarg, int kind, cudaStream_t s, const double* e_part = nullptr,
                       int n_e = 0, const double* n_part = nullptr, int n_n = 0, int from_core = 0);

@@ -2110,12 +2110,6 @@ __global__ void k_lm_init(LmCtl* ctl, const LmOptionsDev* opt) {
   ctl->iterations_executed = 0;
 }
 
-__global__ void k_lm_zero(const LmCtl* ctl, double* p, int n, int mode) {
-  if (lm_skip(ctl, mode)) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 0.0;
-}
-
 // calculateEnergy() tail (problem.hpp:293-316), the accept decision (levenberg_marquardt_algorithm.hpp:95-104) and,
 // for a trial energy, acceptStep / rejectStep of the frame state plus the loop bookkeeping (problem.hpp:366-402,
 // lm.hpp:104-122) -- one single-CTA kernel per energy evaluation.  k_accept_landmarks runs right after it and applies
@@ -2475,11 +2469,6 @@ int sm_count() {
 void launch_lm_init(LmCtl* ctl, const LmOptionsDev* opt, cudaStream_t s) {
   ++g_launches;
   k_lm_init<<<1, 32, 0, s>>>(ctl, opt);
-}
-
-void launch_lm_zero(const LmCtl* ctl, double* p, int n, int mode, cudaStream_t s) {
-  ++g_launches;
-  k_lm_zero<<<(n + 255) / 256, 256, 0, s>>>(ctl, p, n, mode);
 }
 
 void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, double* scal,
