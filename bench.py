@@ -196,6 +196,8 @@ def run_ours(args):
     h = capi.upload_window(win, device=local, rank=rank, world_size=world)
     if args.fused_min_blocks:
         h.set_option("fused_min_blocks", args.fused_min_blocks)
+    if args.speculative_multi_gpu >= 0:
+        h.set_option("speculative_multi_gpu", args.speculative_multi_gpu)
     if args.fused_prefetch >= 0:
         h.set_option("fused_prefetch", args.fused_prefetch)
     if world > 1:
@@ -530,6 +532,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-big-sweep", action="store_true", help="skip the 20000-points/KF materialising-sweep roofline")
     ap.add_argument("--fused-min-blocks", type=int, default=0, help="tuning A/B: 3 or 4 resident CTAs/SM for the fused linearise")
+    ap.add_argument("--speculative-multi-gpu", type=int, default=-1, help="A/B: one-allreduce speculative device LM for N > 1")
     ap.add_argument("--fused-prefetch", type=int, default=-1, help="tuning A/B: 0/1 L1 prefetch of the next taps in the fused linearise")
     ap.add_argument("--host-lm", action="store_true", help="drive the LM loop from the C++ host adapter instead of dpba_solve_lm")
     args = ap.parse_args()

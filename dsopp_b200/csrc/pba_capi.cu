@@ -116,6 +116,7 @@ struct dpba_handle {
   int* fixed_h = nullptr;            // pinned
   bool use_graph = true;
   bool speculative = true;           // dpba_solve_lm: trial evaluation == next linearisation under force_accept
+  bool speculative_multi = true;     // ... also with world_size > 1 (one allreduce per iteration); 2-GPU check: same state and energy as the two-sweep sequence
   cudaGraphExec_t lm_graph_exec = nullptr;
   std::vector<long long> lm_graph_key;
   size_t lm_graph_events = 0;
@@ -378,7 +379,7 @@ int ensure_materialized(dpba_handle* h) {
 }
 
 // sum the [core | Hs | bs | scal] block over ranks (one fused in-place NCCL allreduce on the compute stream)
-enum { EX_SYSTEM = 0, EX_SCAL = 1 };
+enum { EX_SYSTEM = 0, EX_SCAL = 1, EX_ALL = 2 };
 int exchange_raw(dpba_handle* h, size_t off, size_t n) {
   if (h->world <= 1 || !h->comm) return 0;
   NcclApi& nc = nccl_api();
@@ -390,6 +391,7 @@ int exchange_raw(dpba_handle* h, size_t off, size_t n) {
 // one fused in-place-shaped allreduce of either the linear system [Hp | bp | Hs | bs] or the 8 scalars
 int exchange(dpba_handle* h, int what) {
   const RedLayout L = red_layout(h->n_frames);
+  if (what == EX_ALL) return exchange_raw(h, L.hp, L.n - L.hp);  // system and scalars in ONE allreduce
   return what == EX_SYSTEM ? exchange_raw(h, L.hp, L.scal - L.hp) : exchange_raw(h, L.scal, 8);
 }
 
@@ -1449,6 +1451,78 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
     CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
     return 0;
   }
+  // ---- speculative mode on several GPUs (option "speculative_multi_gpu") ----------------------------------------------
+  // Same idea as above, with ONE NCCL allreduce per iteration: the pair energies and landmark norms of this rank are
+  // reduced into the scalar slots, which sit right behind [H_pp | b_p | H_s | b_s] in the exchange buffer, so the system
+  // of linearisation k and the energy of the state it was taken at cross NVLink together; every rank then takes the
+  // same decision from the same sums.
+  if (h->speculative && h->speculative_multi && od.force_accept && multi) {
+    FusedShape shape;
+    for (int k = 0; k <= od.max_it; ++k) {
+      const bool more = k < od.max_it;
+      {
+        ProfScope ps(h, 0);
+        shape = pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 1);
+      }
+      if (more) {
+        if ((rc = stream_edge(h, s, s2))) return rc;
+        ProfScope ps(h, 10, s2);
+        pba::launch_finish_fused(w, rb, shape, s2, h->ctl);
+      }
+      {
+        ProfScope ps(h, 8);
+        pba::launch_core_reduce(w, rb, shape, s, h->ctl);
+      }
+      pba::launch_reduce_scal(h->ctl, 1, rb.core, N * (N - 1), k ? rb.n_part : nullptr, k ? n_norm_parts : 0, rb.scal, s, N);
+      if (more) {
+        {
+          ProfScope ps(h, 9);
+          pba::launch_assemble_blocks(w, fej, rb, shape, s, h->ctl);
+        }
+        if ((rc = stream_edge(h, s2, s))) return rc;
+      }
+      if ((rc = exchange(h, more ? EX_ALL : EX_SCAL))) return rc;
+      {
+        ProfScope ps(h, 11);
+        pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, ro.scal, Hm, bm,
+                              k == 0 ? pba::LM_ENERGY_INITIAL : pba::LM_ENERGY_TRIAL, s);
+      }
+      if (k > 0) {
+        if ((rc = stream_edge(h, s, s2))) return rc;
+        ProfScope ps(h, 11, s2);
+        pba::launch_accept(w, 0, nullptr, s2, h->ctl, 1);
+      }
+      if (!more) {
+        if (k > 0 && (rc = stream_edge(h, s2, s))) return rc;
+        break;
+      }
+      {
+        ProfScope ps(h, 7);
+        pba::launch_lm_step(h->ctl, h->lmopt, h->fparams, h->fixed_dev, N, ro, Hm, bm, h->step_dev, s);
+      }
+      if (k > 0 && (rc = stream_edge(h, s2, s))) return rc;
+      if ((rc = stream_edge(h, s, s2))) return rc;
+      {
+        ProfScope ps(h, 6, s2);
+        pba::launch_pair_setup(h->fparams, N, h->pairs, h->pasm, s2);
+      }
+      {
+        ProfScope ps(h, 5);
+        pba::launch_back_substitute(w, h->step_dev, 0.0, s, h->ctl, rb.n_part);
+      }
+      if ((rc = stream_edge(h, s2, s))) return rc;
+    }
+    pairs();
+    {
+      ProfScope ps(h, 0);
+      pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 3);
+    }
+    if ((rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
+    return 0;
+  }
   // result.energy = problem.calculateEnergy()
   if ((rc = energy_eval(0, 0, pba::LM_ENERGY_INITIAL))) return rc;
   for (int it = 0; it < od.max_it; ++it) {
@@ -1547,7 +1621,7 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   // The launch sequence only depends on the window shape and a few options: capture it once into a CUDA graph and
   // replay it (one cudaGraphLaunch instead of ~110 launches per solve); all inputs travel through pinned buffers.
   std::vector<long long> key = {N, od.max_it, od.fej, H_marg != nullptr, h->world, (long long)h->profiling,
-                                (long long)(h->speculative && od.force_accept),
+                                (long long)(h->speculative && od.force_accept), (long long)h->speculative_multi,
                                 (long long)llround(od.sigma * 1e6)};
   for (int f = 0; f < N; ++f) {
     key.push_back(h->fr[f].n_lm);
@@ -1617,6 +1691,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
   REQUIRE(h && name, "null argument");
   if (!strcmp(name, "cuda_graph")) {
     h->use_graph = value != 0;
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "speculative_multi_gpu")) {
+    h->speculative_multi = value != 0;
+    h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
   if (!strcmp(name, "speculative_linearize")) {

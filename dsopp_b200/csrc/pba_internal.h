@@ -140,7 +140,7 @@ void launch_pixelinfo3(const float* I, float* dst, int W, int H, cudaStream_t s)
 int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* e_part, cudaStream_t s,
                           const LmCtl* ctl = nullptr, int ctl_mode = 0);
 void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, int n_e, const double* n_part, int n_n,
-                        double* scal, cudaStream_t s);
+                        double* scal, cudaStream_t s, int core_frames = 0);
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s);
 FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
                                   cudaStream_t s, const LmCtl* ctl = nullptr, int ctl_mode = 2);

@@ -437,12 +437,19 @@ __global__ void __launch_bounds__(480) k_residual_sweep(const __grid_constant__ 
 __global__ void __launch_bounds__(1024) k_reduce_scal(const LmCtl* __restrict__ ctl, int ctl_mode,
                                                       const double2* __restrict__ e_part, int n_e,
                                                       const double2* __restrict__ n_part, int n_n,
-                                                      double* __restrict__ scal) {
+                                                      double* __restrict__ scal, int core_frames) {
   if (lm_skip(ctl, ctl_mode)) return;
   __shared__ double s[4][32];
   double a = 0, b = 0, c = 0, d = 0;
   for (int i = threadIdx.x; i < n_e; i += blockDim.x) {
-    const double2 v = e_part[i];
+    size_t idx = i;
+    if (core_frames) {  // e_part is the per-pair core array: (energy, n_valid) in slots 44 / 45 of pair (r, t)
+      const int r = i / (core_frames - 1);
+      int t = i % (core_frames - 1);
+      t += (t >= r);
+      idx = ((size_t)(r * PBA_MAXF + t) * PBA_CORE + 44) / 2;
+    }
+    const double2 v = e_part[idx];
     a += v.x;
     b += v.y;
   }
@@ -2553,10 +2560,10 @@ int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, d
 }
 
 void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, int n_e, const double* n_part, int n_n,
-                        double* scal, cudaStream_t s) {
+                        double* scal, cudaStream_t s, int core_frames) {
   ++g_launches;
   k_reduce_scal<<<1, 1024, 0, s>>>(ctl, ctl_mode, reinterpret_cast<const double2*>(e_part), n_e,
-                                   reinterpret_cast<const double2*>(n_part), n_n, scal);
+                                   reinterpret_cast<const double2*>(n_part), n_n, scal, core_frames);
 }
 
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s) {

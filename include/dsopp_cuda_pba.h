@@ -270,7 +270,9 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* options, const double* 
  * sequence as one CUDA graph.  "speculative_linearize" (default 1): under force_accept (single GPU) dpba_solve_lm
  * evaluates the trial energy with the fused linearise, which then serves as the next iteration's linearize(); state,
  * idepths, statuses and energy are unchanged, the per-landmark hpd / b_d / inv_hdd left behind are those of the final
- * state (the reference's are one accepted step older; its uncertainty pass recomputes them).  "fused_min_blocks"
+ * state (the reference's are one accepted step older; its uncertainty pass recomputes them).  "speculative_multi_gpu"
+ * (default 1): the same with world_size > 1, the pair energies travelling in the scalar slots behind the system so that
+ * ONE allreduce per iteration carries both.  "fused_prefetch" (default 0): L1 prefetch A/B switch.  "fused_min_blocks"
  * (3 or 4, process-wide): resident CTAs per SM the fused linearise is built for.  "schur_tensor_cores" (default 1, process-wide): the Schur-complement SYRK runs as
  * 3xTF32 mma.sync; 0 selects the fp32 FFMA kernel. */
 int dpba_set_option(dpba_handle* h, const char* name, int64_t value);

@@ -30,6 +30,8 @@ def main():
     dist.broadcast(uid, 0)
     say("unique id broadcast")
     h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    if os.environ.get("DPBA_SPEC_MULTI"):
+        h.set_option("speculative_multi_gpu", int(os.environ["DPBA_SPEC_MULTI"]))
     say("dpba_comm_init done")
     h.first_estimate()
     Hp, bp, Hs, bs = h.linearize(20.0, True, True, False)
@@ -39,6 +41,22 @@ def main():
     h.first_estimate()
     E, it, conv, nv = h.solve_lm(20.0)
     say("solve_lm done")
+    if os.environ.get("DPBA_SPEC_MULTI"):
+        # the same solve through the other launch sequence (two sweeps + two allreduces per iteration) on the SAME
+        # handle and communicator (an NCCL unique id serves one communicator): must agree
+        eps_a, _ = h.get_state()
+        shard = [sharding.shard_indices(len(f.idepth), rank, world) for f in win.frames]
+        for i, f in enumerate(win.frames):
+            h.set_landmarks(i, f.uv[shard[i]], f.idepth[shard[i]], f.patch[shard[i]], f.flags[shard[i]])
+        for (r_, t_), st in win.statuses.items():
+            h.set_statuses(r_, t_, st[shard[r_]])
+        h.set_state(np.concatenate([f.state_eps for f in win.frames]), np.zeros(8 * win.n_frames))
+        h.set_option("speculative_multi_gpu", 0)
+        h.first_estimate()
+        E2, it2, _, nv2 = h.solve_lm(20.0)
+        eps2, _ = h.get_state()
+        say(f"speculative multi-GPU E={E!r} it={it} nv={nv} | two-sweep multi-GPU E={E2!r} it={it2} nv={nv2} | max|d eps| {np.abs(eps_a - eps2).max():.2e}")
+        assert abs(E - E2) <= 1e-6 * abs(E2) and it == it2 and nv == nv2 and np.abs(eps_a - eps2).max() < 1e-6
     eps, _ = h.get_state()
     idepth = [h.get_landmarks(i)["idepth"] for i in range(win.n_frames)]
     ok = True
