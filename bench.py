@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -258,7 +258,6 @@ def run_ours(args):
         if i >= args.warmup:
             step_ms.append(ms)
             launches += nl
-    clocks = sampler.stop()
     assert all(it == GN_ITERS for it in iters_seen), iters_seen
     t_local = sum(step_ms)
     t = torch.tensor([t_local], dtype=torch.float64, device=dev)
@@ -365,6 +364,9 @@ def run_ours(args):
     e2e_raw_value = units_global * GN_ITERS / (float(t_raw.item()) * 1e-3)
     # leave the handle with the float window for the sweeps timed below
     e2e_step()
+    # clocks / throttle reasons were sampled from the first timed `value` step to the last timed e2e step (the timed
+    # `value` region alone lasts ~20 ms, less than one nvidia-smi sampling period)
+    clocks = sampler.stop()
     t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
