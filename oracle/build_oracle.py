@@ -28,6 +28,21 @@ def _build(target, flags):
     return target
 
 
+PA_SRC = os.path.join(HERE, "cpu_ref", "pose_alignment_cpu_ref.cpp")
+PA_LIB = os.path.join(OUT, "libpose_alignment_cpu_ref.so")
+
+
+def build_pose_alignment():
+    """oracle/_build/libpose_alignment_cpu_ref.so: serial C++ restatement of the coarse-tracker aligner (-O3 -march=native)."""
+    os.makedirs(OUT, exist_ok=True)
+    if os.path.exists(PA_LIB) and os.path.getmtime(PA_LIB) >= os.path.getmtime(PA_SRC):
+        return PA_LIB
+    cmd = ["g++", "-std=c++17", "-O3", "-fPIC", "-shared", "-Wall", "-march=native", "-o", PA_LIB, PA_SRC]
+    print("+", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return PA_LIB
+
+
 def build_portable():
     return _build(PORTABLE, ["-march=x86-64-v3", "-ffp-contract=off"])
 

@@ -166,3 +166,36 @@ def solve(ref: PAFrame, tgt: PAFrame, uv, idepth, patch, sigma_huber=20.0, ab_re
     rmse = float(np.sqrt(energy / n / 1)) if n > 0 else float("inf")  # :328, PatternSize = 1
     return dict(rmse=rmse, energy=energy, n_valid=n, converged=conv, T_t_r=p.T, ab_eps=p.ab_eps, H=p.H,
                 T_w_target=ref.T_lin @ O.se3_inv(p.T), iterations=len(trace) if trace is not None else None)
+
+
+def solve_cpp(ref: PAFrame, tgt: PAFrame, uv, idepth, patch, sigma_huber=20.0, ab_reg=(1e12, 1e8), opt=None):
+    """The same solve through the serial C++ restatement (oracle/cpu_ref/pose_alignment_cpu_ref.cpp): a second checker
+    and the timed CPU baseline of the aligner.  Returns the dict of solve() plus `seconds`."""
+    import ctypes as C
+    import time
+
+    from . import build_oracle
+    lib = C.CDLL(build_oracle.build_pose_alignment())
+    lib.paref_solve.restype = C.c_double
+    opt = opt or default_options()
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rT, tT = f64(ref.T_lin[:3, :4]).reshape(12), f64(tgt.T_lin[:3, :4]).reshape(12)
+    rab, tab, ri, ti = f64(ref.ab0), f64(tgt.ab0), f64(ref.intr), f64(tgt.intr)
+    img = np.ascontiguousarray(tgt.image, dtype=np.float32)
+    mask = np.ascontiguousarray(tgt.mask, dtype=np.uint8)
+    xy, idp, pt, reg = f64(uv).reshape(-1, 2), f64(idepth), f64(patch), f64(ab_reg)
+    T, ab, H = np.zeros(12), np.zeros(2), np.zeros(64)
+    nv, it, cv = C.c_int(), C.c_int(), C.c_int()
+    t0 = time.perf_counter()
+    e = lib.paref_solve(ptr(rT), C.c_double(ref.exposure), ptr(rab), ptr(ri), C.c_int(ref.W), C.c_int(ref.H), ptr(tT),
+                        C.c_double(tgt.exposure), ptr(tab), ptr(ti), C.c_int(tgt.W), C.c_int(tgt.H), ptr(img),
+                        ptr(mask) if mask.min() == 0 else None, C.c_int(len(idp)), ptr(xy), ptr(idp), ptr(pt),
+                        C.c_double(sigma_huber), ptr(reg), C.c_int(opt.max_num_iterations), C.c_double(opt.initial_lambda),
+                        C.c_double(opt.function_tolerance), C.c_double(opt.parameter_tolerance),
+                        C.c_double(opt.decrease_on_accept), C.c_double(opt.increase_on_reject), ptr(T), ptr(ab), ptr(H),
+                        C.byref(nv), C.byref(it), C.byref(cv))
+    dt = time.perf_counter() - t0
+    T44 = np.vstack([T.reshape(3, 4), [0, 0, 0, 1.0]])
+    return dict(energy=e, n_valid=nv.value, iterations=it.value, converged=bool(cv.value), T_t_r=T44, ab_eps=ab,
+                H=H.reshape(8, 8), rmse=float(np.sqrt(e / nv.value)) if nv.value else float("inf"), seconds=dt)

@@ -90,3 +90,20 @@ def test_alignment_recovers_the_ground_truth_relative_pose():
         assert err1 < 0.1 * err0 and err1 < 3e-4 and ang1 < 1e-4, (seed, err0, err1, ang1)
         e = [t["energy"] for t in trace if t["accepted"]]
         assert all(b < a for a, b in zip(e, e[1:]))  # accepted energies decrease
+
+
+def test_cpp_restatement_matches_the_numpy_oracle():
+    """Two independent restatements of eigen_pose_alignment.cpp (NumPy, vectorised; C++, the reference's serial
+    two-pass dataflow) must agree to rounding."""
+    for seed, density, W, H, ab_scale, reg in ((3, 0.02, 640, 480, 0.0, (1e12, 1e8)), (6, 0.3, 320, 240, 1.0, (10.0, 1e-2))):
+        case = synth.make_alignment_case(seed=seed, width=W, height=H, density=density, pose_noise=4e-3, ab_scale=ab_scale)
+        ref, tgt = case_frames(case)
+        uv, idepth, patch = PA.landmarks_from_depth_map(case.idepth_sum, case.weight, case.reference.image)
+        trace = []
+        a = PA.solve(ref, tgt, uv, idepth, patch, ab_reg=reg, trace=trace)
+        b = PA.solve_cpp(ref, tgt, uv, idepth, patch, ab_reg=reg)
+        assert b["n_valid"] == a["n_valid"] and b["iterations"] == len(trace) and b["converged"] == a["converged"]
+        assert abs(b["energy"] - a["energy"]) <= 1e-9 * a["energy"]
+        assert np.abs(b["T_t_r"] - a["T_t_r"]).max() <= 1e-9
+        assert np.abs(b["ab_eps"] - a["ab_eps"]).max() <= 1e-8 * max(1.0, np.abs(a["ab_eps"]).max())
+        assert np.abs(b["H"] - a["H"]).max() <= 1e-9 * np.abs(a["H"]).max()

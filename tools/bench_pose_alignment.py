@@ -34,8 +34,10 @@ for name, W, H, density in (("sparse 640x480 (2% of pixels)", 640, 480, 0.02), (
     tr = []
     PA.solve(ref, tgt, uv, idepth, patch, trace=tr)
     cpu_ms = (time.perf_counter() - t0) * 1e3
+    cpp = min((PA.solve_cpp(ref, tgt, uv, idepth, patch) for _ in range(3)), key=lambda o: o["seconds"])
     med = float(np.median(ms))
     out.append(dict(case=name, landmarks=n, lm_iterations=res["iterations"], gpu_ms_per_solve=med,
-                    gpu_point_residuals_per_s=n * sweeps / (med * 1e-3), numpy_oracle_ms_per_solve=cpu_ms, rmse=res["rmse"]))
+                    gpu_point_residuals_per_s=n * sweeps / (med * 1e-3), numpy_oracle_ms_per_solve=cpu_ms,
+                    cpp_serial_ms_per_solve=cpp["seconds"] * 1e3, cpp_lm_iterations=cpp["iterations"], rmse=res["rmse"]))
     al.close()
 print(json.dumps(out))
