@@ -33,11 +33,12 @@ PA_LIB = os.path.join(OUT, "libpose_alignment_cpu_ref.so")
 
 
 def build_pose_alignment():
-    """oracle/_build/libpose_alignment_cpu_ref.so: serial C++ restatement of the coarse-tracker aligner (-O3 -march=native)."""
+    """oracle/_build/libpose_alignment_cpu_ref.so: serial C++ restatement of the coarse-tracker aligner.  Portable flags
+    (x86-64-v3): the library may be built in one container and loaded on another host."""
     os.makedirs(OUT, exist_ok=True)
     if os.path.exists(PA_LIB) and os.path.getmtime(PA_LIB) >= os.path.getmtime(PA_SRC):
         return PA_LIB
-    cmd = ["g++", "-std=c++17", "-O3", "-fPIC", "-shared", "-Wall", "-march=native", "-o", PA_LIB, PA_SRC]
+    cmd = ["g++", "-std=c++17", "-O3", "-fPIC", "-shared", "-Wall", "-march=x86-64-v3", "-o", PA_LIB, PA_SRC]
     print("+", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return PA_LIB
