@@ -208,6 +208,10 @@ def run_ours(args):
         h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
         h.first_estimate()
         h.evaluate(SIGMA, True, True)  # first collective outside any graph capture: NCCL sets its channels up here
+        if args.peer_exchange:
+            capi.attach_peers(h, rank, world, dev)
+            h.set_option("peer_exchange", 1)
+            h.evaluate(SIGMA, True, True)
 
     ab0 = np.stack([f.ab0 for f in win.frames])
     fixed = [int(f.fixed) for f in win.frames]
@@ -506,7 +510,9 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+        "dtype": "f32", "data": "synthetic",
+        "config": config_dict(world, {"exchange": "NVLink mailbox all-reduce (peer_exchange.cu)" if args.peer_exchange and world > 1
+                                      else ("ncclAllReduce of the packed system, one per GN iteration" if world > 1 else "none")}),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_box[0]),
                 "ms_per_step": sum(e2e_ms) / len(e2e_ms),
@@ -535,6 +541,8 @@ def main():
     ap.add_argument("--no-big-sweep", action="store_true", help="skip the 20000-points/KF materialising-sweep roofline")
     ap.add_argument("--fused-min-blocks", type=int, default=0, help="tuning A/B: 3 or 4 resident CTAs/SM for the fused linearise")
     ap.add_argument("--speculative-multi-gpu", type=int, default=-1, help="A/B: one-allreduce speculative device LM for N > 1")
+    ap.add_argument("--peer-exchange", action="store_true",
+                    help="N > 1: sum the exchange block with the library's NVLink mailbox kernel instead of ncclAllReduce")
     ap.add_argument("--fused-prefetch", type=int, default=-1, help="tuning A/B: 0/1 L1 prefetch of the next taps in the fused linearise")
     ap.add_argument("--host-lm", action="store_true", help="drive the LM loop from the C++ host adapter instead of dpba_solve_lm")
     args = ap.parse_args()

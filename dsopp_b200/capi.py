@@ -121,6 +121,8 @@ SIGNATURES = {
     "dpba_profile_read": (C.c_int, [_P, _P, _P]),
     "dpba_comm_unique_id": (C.c_int, [_P]),
     "dpba_comm_init": (C.c_int, [_P, _P, _I, _I]),
+    "dpba_peer_export": (C.c_int, [_P, _P]),
+    "dpba_peer_attach": (C.c_int, [_P, _P, _I, _I]),
 }
 
 _lib = None
@@ -393,6 +395,29 @@ class Handle:
     def comm_init(self, uid: bytes, rank, world):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._ck(self.lib.dpba_comm_init(self.h, C.cast(buf, C.c_void_p), rank, world))
+
+    def peer_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's exchange mailbox (all-gather them, then peer_attach)."""
+        buf = (C.c_uint8 * 64)()
+        self._ck(self.lib.dpba_peer_export(self.h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def peer_attach(self, handles: bytes, rank, world):
+        assert len(handles) == 64 * world
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._ck(self.lib.dpba_peer_attach(self.h, C.cast(buf, C.c_void_p), rank, world))
+
+
+def attach_peers(h: "Handle", rank, world, device):
+    """Exchange the mailbox handles over torch.distributed and attach them (callers barrier afterwards)."""
+    import torch
+    import torch.distributed as dist
+
+    mine = torch.frombuffer(bytearray(h.peer_export()), dtype=torch.uint8).to(device)
+    every = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(every, mine)
+    h.peer_attach(b"".join(bytes(t.cpu().numpy().tobytes()) for t in every), rank, world)
+    dist.barrier()
 
 
 def launch_count() -> int:

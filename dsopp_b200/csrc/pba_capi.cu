@@ -137,6 +137,14 @@ struct dpba_handle {
   int lin_frames = 0;
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
+  // peer-memory exchange (peer_exchange.cu): this rank's mailbox, the peers' mailboxes opened over CUDA IPC
+  void* peer_box = nullptr;
+  void* peer_open[pba::PEER_MAXW] = {};
+  unsigned* peer_ctr = nullptr;  // device: {seq, done}
+  int* peer_err_h = nullptr;     // mapped pinned: set by the kernel after a time-out
+  pba::PeerDev peer{};
+  bool peer_attached = false;
+  bool peer_on = false;          // option "peer_exchange"
   // per-kernel CUDA-event profiling (dpba_profile_*)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;           // pairs: [2i] start, [2i+1] stop
@@ -167,6 +175,12 @@ inline RedLayout red_layout(int n_frames) {
 }
 constexpr size_t N_RED = 2 * (MAXD * MAXD + MAXD) + 8;
 constexpr size_t N_EXCHANGE = N_RED;
+static_assert(N_EXCHANGE % 2 == 0, "the peer exchange moves double2");
+constexpr size_t PEER_BOX_DATA = 2 * (size_t)pba::PEER_MAXW * N_EXCHANGE;  // doubles
+constexpr size_t PEER_BOX_BYTES = PEER_BOX_DATA * sizeof(double) + (size_t)pba::PEER_MAXW * pba::PEER_MAXC * sizeof(unsigned);
+
+// several ranks AND a way to sum over them (NCCL communicator or attached peer mailboxes)
+inline bool multi_gpu(const dpba_handle* h) { return h->world > 1 && (h->comm || h->peer_on); }
 
 int fail(dpba_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -279,7 +293,7 @@ ReduceBuf redbuf(dpba_handle* h) {
 // (out-of-place allreduce, so a skipped linearisation re-reduces the same partials instead of summing sums)
 ReduceBuf redbuf_out(dpba_handle* h) {
   ReduceBuf rb = redbuf(h);
-  if (h->world > 1 && h->comm) {
+  if (multi_gpu(h)) {
     const RedLayout L = red_layout(h->n_frames);
     rb.Hp = h->red2 + L.hp;
     rb.bp = h->red2 + L.bp;
@@ -378,13 +392,25 @@ int ensure_materialized(dpba_handle* h) {
   return 0;
 }
 
-// sum the [core | Hs | bs | scal] block over ranks (one fused in-place NCCL allreduce on the compute stream)
+// sum the [core | Hs | bs | scal] block over ranks on the compute stream: our own one-shot kernel over NVLink peer
+// memory when the mailboxes are attached and the option is on, else one NCCL allreduce (out of place: red -> red2)
 enum { EX_SYSTEM = 0, EX_SCAL = 1, EX_ALL = 2 };
 int exchange_raw(dpba_handle* h, size_t off, size_t n) {
-  if (h->world <= 1 || !h->comm) return 0;
+  if (!multi_gpu(h)) return 0;
+  if (h->peer_on) {
+    pba::launch_peer_allreduce(h->peer, h->red, h->red2, off, n, h->stream);
+    return 0;
+  }
   NcclApi& nc = nccl_api();
   ncclResult_t r = nc.AllReduce(h->red + off, h->red2 + off, n, ncclDouble, ncclSum, h->comm, h->stream);
   if (r != ncclSuccess) return fail(h, DPBA_E_COMM, std::string("ncclAllReduce: ") + nc.GetErrorString(r));
+  return 0;
+}
+
+// after a stream synchronisation: did a peer exchange kernel give up waiting?
+int peer_check(dpba_handle* h) {
+  if (h->peer_err_h && *h->peer_err_h)
+    return fail(h, DPBA_E_COMM, "peer exchange timed out waiting for another rank (results are invalid)");
   return 0;
 }
 
@@ -658,6 +684,12 @@ int dpba_destroy(dpba_handle* h) {
     h->lm_graph_exec = nullptr;
   }
   if (h->comm) nccl_api().CommDestroy(h->comm);
+  // peers' mailboxes are closed, ours is freed: the caller puts a barrier between the last solve and dpba_destroy
+  for (void* p : h->peer_open)
+    if (p) cudaIpcCloseMemHandle(p);
+  cudaFree(h->peer_box);
+  cudaFree(h->peer_ctr);
+  if (h->peer_err_h) cudaFreeHost(h->peer_err_h);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->fork_ev) cudaEventDestroy(e);
   if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -1069,6 +1101,7 @@ int dpba_evaluate(dpba_handle* h, double sigma, int32_t huber, int32_t fej, doub
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->red_h, redbuf_out(h).scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (peer_check(h)) return DPBA_E_COMM;
   if (energy) *energy = h->red_h[0];
   if (n_valid) *n_valid = (int32_t)llround(h->red_h[1]);
   return DPBA_SUCCESS;
@@ -1142,7 +1175,7 @@ static int linearize_impl(dpba_handle* h, double sigma, int32_t huber, int32_t f
       pba::launch_finish_fused(w, rb, shape, h->stream);
     }
   } else {
-    if (h->world > 1 && h->comm) return fail(h, DPBA_E_STATE, "dpba_linearize_materialized is single-GPU only");
+    if (multi_gpu(h)) return fail(h, DPBA_E_STATE, "dpba_linearize_materialized is single-GPU only");
     {
       ProfScope ps(h, 3);
       pba::launch_materialise_sweep(w, (float)sigma, huber, fej, h->stream);
@@ -1161,6 +1194,7 @@ static int linearize_impl(dpba_handle* h, double sigma, int32_t huber, int32_t f
   // [Hp | bp | Hs | bs] is contiguous: one device-to-host copy
   CK(cudaMemcpyAsync(h->red_h, redbuf_out(h).Hp, (L.scal - L.hp) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (peer_check(h)) return DPBA_E_COMM;
   if (H_pose) memcpy(H_pose, h->red_h + L.hp, (size_t)D * D * sizeof(double));
   if (b_pose) memcpy(b_pose, h->red_h + L.bp, D * sizeof(double));
   if (H_schur) memcpy(H_schur, h->red_h + L.hs, (size_t)D * D * sizeof(double));
@@ -1207,6 +1241,7 @@ int dpba_accept(dpba_handle* h, double* state_sq, double* step_sq) {
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->red_h, redbuf_out(h).scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (peer_check(h)) return DPBA_E_COMM;
   double st = h->red_h[2], sp = h->red_h[3];
   for (int f = 0; f < h->n_frames; ++f) {  // problem.hpp:369-376
     FrameHost& F = h->fr[f];
@@ -1255,6 +1290,7 @@ int dpba_landmarks_energy(dpba_handle* h, int32_t for_marg, double* energy, int3
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->red_h, redbuf_out(h).scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (peer_check(h)) return DPBA_E_COMM;
   if (energy) *energy = h->red_h[0];
   if (n_valid) *n_valid = (int32_t)llround(h->red_h[1]);
   return DPBA_SUCCESS;
@@ -1341,7 +1377,7 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
   pairs();
   // residual-only sweep + calculateEnergy tail.  Single GPU: k_lm_energy sums the per-CTA partials itself; with
   // several ranks the partials are summed first so that the 8 scalars can cross NVLink before the decision.
-  const bool multi = h->world > 1 && h->comm;
+  const bool multi = multi_gpu(h);
   auto energy_eval = [&](int ctl_mode, int n_norm_parts, int kind) -> int {
     int n_e;
     {
@@ -1622,7 +1658,7 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   // replay it (one cudaGraphLaunch instead of ~110 launches per solve); all inputs travel through pinned buffers.
   std::vector<long long> key = {N, od.max_it, od.fej, H_marg != nullptr, h->world, (long long)h->profiling,
                                 (long long)(h->speculative && od.force_accept), (long long)h->speculative_multi,
-                                (long long)llround(od.sigma * 1e6)};
+                                (long long)llround(od.sigma * 1e6), (long long)h->peer_on};
   for (int f = 0; f < N; ++f) {
     key.push_back(h->fr[f].n_lm);
     key.push_back(h->fr[f].phys);
@@ -1672,6 +1708,7 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
     if ((rc = lm_enqueue(h, H_marg != nullptr))) return rc;
   }
   CK(cudaStreamSynchronize(h->stream));
+  if (peer_check(h)) return DPBA_E_COMM;
   if (h->profiling) profile_collect(h);
   for (int f = 0; f < N; ++f)
     for (int k = 0; k < 8; ++k) {
@@ -1695,6 +1732,12 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
   }
   if (!strcmp(name, "speculative_multi_gpu")) {
     h->speculative_multi = value != 0;
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "peer_exchange")) {  // our NVLink mailbox all-reduce instead of ncclAllReduce
+    if (value && !h->peer_attached) return fail(h, DPBA_E_STATE, "peer_exchange needs dpba_peer_attach first");
+    h->peer_on = value != 0;
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
@@ -1765,6 +1808,61 @@ int dpba_comm_init(dpba_handle* h, const uint8_t id[128], int32_t rank, int32_t 
   if (r != ncclSuccess) return fail(h, DPBA_E_COMM, std::string("ncclCommInitRank: ") + nc.GetErrorString(r));
   h->world = world;
   h->rank = rank;
+  return DPBA_SUCCESS;
+}
+
+int dpba_peer_export(dpba_handle* h, uint8_t handle[64]) {
+  REQUIRE(h && handle, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  CK(cudaSetDevice(h->cfg.device));
+  if (!h->peer_box) {
+    CK(cudaMalloc(&h->peer_box, PEER_BOX_BYTES));
+    CK(cudaMalloc(&h->peer_ctr, 2 * sizeof(unsigned)));
+    CK(cudaHostAlloc(&h->peer_err_h, sizeof(int), cudaHostAllocMapped));
+    *h->peer_err_h = 0;
+  }
+  CK(cudaMemset(h->peer_box, 0, PEER_BOX_BYTES));
+  CK(cudaMemset(h->peer_ctr, 0, 2 * sizeof(unsigned)));
+  CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t ipc;
+  CK(cudaIpcGetMemHandle(&ipc, h->peer_box));
+  memcpy(handle, &ipc, 64);
+  return DPBA_SUCCESS;
+}
+
+int dpba_peer_attach(dpba_handle* h, const uint8_t* handles, int32_t rank, int32_t world) {
+  REQUIRE(h && handles, "null argument");
+  REQUIRE(world >= 2 && world <= pba::PEER_MAXW && rank >= 0 && rank < world, "peer exchange: 2..8 ranks of one node");
+  REQUIRE(h->peer_box, "dpba_peer_export first");
+  REQUIRE(!h->peer_attached, "peers already attached");
+  REQUIRE(!h->comm || (h->world == world && h->rank == rank), "rank / world differ from dpba_comm_init");
+  CK(cudaSetDevice(h->cfg.device));
+  pba::PeerDev pd{};
+  for (int r = 0; r < world; ++r) {
+    void* base = h->peer_box;
+    if (r != rank) {
+      cudaIpcMemHandle_t ipc;
+      memcpy(&ipc, handles + (size_t)r * 64, 64);
+      cudaError_t e = cudaIpcOpenMemHandle(&base, ipc, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fail(h, DPBA_E_COMM, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+      h->peer_open[r] = base;
+    }
+    pd.data[r] = static_cast<double*>(base);
+    pd.flag[r] = reinterpret_cast<unsigned*>(static_cast<double*>(base) + PEER_BOX_DATA);
+  }
+  pd.seq = h->peer_ctr;
+  pd.done = h->peer_ctr + 1;
+  int* err_dev = nullptr;
+  CK(cudaHostGetDevicePointer(&err_dev, h->peer_err_h, 0));
+  pd.error = err_dev;
+  pd.rank = rank;
+  pd.world = world;
+  pd.slot = N_EXCHANGE;
+  h->peer = pd;
+  h->world = world;
+  h->rank = rank;
+  h->peer_attached = true;
   return DPBA_SUCCESS;
 }
 

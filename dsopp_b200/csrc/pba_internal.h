@@ -171,4 +171,18 @@ void add_launches(long long n);
 void set_schur_mma(bool on);
 void set_fused_min_blocks(int b);
 void set_fused_prefetch(bool on);
+
+// ---- peer-memory exchange (peer_exchange.cu): one-shot all-reduce over NVLink mailboxes -------------------------------
+constexpr int PEER_MAXW = 8;   // ranks of one NVSwitch domain
+constexpr int PEER_MAXC = 32;  // CTAs of one exchange kernel (each with its own arrival flag per source rank)
+struct PeerDev {
+  double* data[PEER_MAXW];    // mailbox data of rank r: [2 parities][PEER_MAXW sources][slot] doubles
+  unsigned* flag[PEER_MAXW];  // mailbox flags of rank r: [PEER_MAXW sources][PEER_MAXC] epochs
+  unsigned* seq;              // local: number of completed exchanges (the epoch of the last one)
+  unsigned* done;             // local: CTAs of the running exchange that have finished
+  int* error;                 // local (mapped pinned host memory): 1 after a time-out
+  int rank, world;
+  size_t slot;                // doubles per [parity][source] slot
+};
+void launch_peer_allreduce(const PeerDev& pd, const double* in, double* out, size_t off, size_t n, cudaStream_t s);
 }  // namespace pba

@@ -274,7 +274,8 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* options, const double* 
  * (default 1): the same with world_size > 1, the pair energies travelling in the scalar slots behind the system so that
  * ONE allreduce per iteration carries both.  "fused_prefetch" (default 0): L1 prefetch A/B switch.  "fused_min_blocks"
  * (3 or 4, process-wide): resident CTAs per SM the fused linearise is built for.  "schur_tensor_cores" (default 1, process-wide): the Schur-complement SYRK runs as
- * 3xTF32 mma.sync; 0 selects the fp32 FFMA kernel. */
+ * 3xTF32 mma.sync; 0 selects the fp32 FFMA kernel.  "peer_exchange" (default 0, needs dpba_peer_attach): the sum over
+ * ranks runs as the library's own NVLink mailbox kernel instead of ncclAllReduce. */
 int dpba_set_option(dpba_handle* h, const char* name, int64_t value);
 
 /* ---- measurement hooks (no reference counterpart) --------------------------------------- */
@@ -295,6 +296,14 @@ int dpba_profile_read(dpba_handle* h, double ms[DPBA_PROFILE_KINDS], int32_t lau
 /* 128-byte NCCL unique id created on rank 0, broadcast by the caller (torch.distributed / MPI / files). */
 int dpba_comm_unique_id(uint8_t id[128]);
 int dpba_comm_init(dpba_handle* h, const uint8_t id[128], int32_t rank, int32_t world_size);
+/* Optional: sum the exchange block with the library's own one-shot kernel over NVLink peer memory instead of
+ * ncclAllReduce (66.6 KB per GN iteration: latency, not bandwidth).  Every rank exports its mailbox (a 64-byte
+ * cudaIpcMemHandle_t), the caller all-gathers the handles (rank-major, world_size * 64 bytes), every rank attaches,
+ * the caller BARRIERS, then dpba_set_option(h, "peer_exchange", 1).  All ranks must make the same sequence of solver
+ * calls (they do: frames are replicated); a rank that never arrives makes the others fail with DPBA_E_COMM after ~2 s
+ * instead of hanging.  Barrier again before dpba_destroy.  One node (one NVSwitch domain), 2..8 ranks. */
+int dpba_peer_export(dpba_handle* h, uint8_t ipc_handle[64]);
+int dpba_peer_attach(dpba_handle* h, const uint8_t* ipc_handles, int32_t rank, int32_t world_size);
 
 #ifdef __cplusplus
 }

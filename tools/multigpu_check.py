@@ -2,6 +2,10 @@
 reduced system inside dpba_linearize / dpba_solve_lm) must reproduce the single-GPU solve of the same window.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multigpu_check.py
+
+DPBA_SPEC_MULTI=1   also compares the one-allreduce speculative sequence with the two-sweep sequence
+DPBA_PEER_EXCHANGE=1 also repeats everything with the NVLink mailbox all-reduce (peer_exchange.cu) instead of NCCL
+(run under `timeout`: the kernel gives up after ~2 s per exchange if a peer never arrives, it does not hang)
 """
 import os
 import sys
@@ -57,6 +61,37 @@ def main():
         eps2, _ = h.get_state()
         say(f"speculative multi-GPU E={E!r} it={it} nv={nv} | two-sweep multi-GPU E={E2!r} it={it2} nv={nv2} | max|d eps| {np.abs(eps_a - eps2).max():.2e}")
         assert abs(E - E2) <= 1e-6 * abs(E2) and it == it2 and nv == nv2 and np.abs(eps_a - eps2).max() < 1e-6
+    if os.environ.get("DPBA_PEER_EXCHANGE"):
+        # the same solve with the library's own NVLink mailbox all-reduce instead of ncclAllReduce, on the SAME handle:
+        # every rank sums the same values in rank order, so state and energy must agree to rounding with the NCCL run
+        eps_a, _ = h.get_state()
+        capi.attach_peers(h, rank, world, dev)
+        h.set_option("peer_exchange", 1)
+        say("peers attached")
+        shard = [sharding.shard_indices(len(f.idepth), rank, world) for f in win.frames]
+        for i, f in enumerate(win.frames):
+            h.set_landmarks(i, f.uv[shard[i]], f.idepth[shard[i]], f.patch[shard[i]], f.flags[shard[i]])
+        for (r_, t_), st in win.statuses.items():
+            h.set_statuses(r_, t_, st[shard[r_]])
+        h.set_state(np.concatenate([f.state_eps for f in win.frames]), np.zeros(8 * win.n_frames))
+        h.first_estimate()
+        Hp3, bp3, Hs3, bs3 = h.linearize(20.0, True, True, False)
+        for a_, b_, nm in ((Hp3, Hp, "Hp"), (bp3, bp, "bp"), (Hs3, Hs, "Hs"), (bs3, bs, "bs")):
+            err = np.abs(a_ - b_).max() / max(np.abs(b_).max(), 1e-30)
+            say(f"peer exchange {nm}: max|d|/max|nccl| = {err:.2e}")
+            assert err < 1e-12
+        e3, n3 = h.evaluate(20.0, True, True)
+        assert abs(e3 - e) <= 1e-12 * abs(e) and n3 == n
+        h.first_estimate()
+        E3, it3, _, nv3 = h.solve_lm(20.0)
+        eps3, _ = h.get_state()
+        say(f"NCCL E={E!r} it={it} nv={nv} | peer exchange E={E3!r} it={it3} nv={nv3} | max|d eps| {np.abs(eps_a - eps3).max():.2e}")
+        assert abs(E - E3) <= 1e-6 * abs(E) and it == it3 and nv == nv3 and np.abs(eps_a - eps3).max() < 1e-6
+        # replicas must hold bitwise identical states (same sums in the same order on every rank)
+        mine = torch.from_numpy(eps3.copy()).to(dev)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        assert all(torch.equal(every[0], t) for t in every), "replicated LM state differs between ranks"
     eps, _ = h.get_state()
     idepth = [h.get_landmarks(i)["idepth"] for i in range(win.n_frames)]
     ok = True
