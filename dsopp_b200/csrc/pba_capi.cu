@@ -145,6 +145,10 @@ struct dpba_handle {
   pba::PeerDev peer{};
   bool peer_attached = false;
   bool peer_on = false;          // option "peer_exchange"
+  // device-side quantile of updatePointStatuses (energy_quantile.cu)
+  bool device_quantile = false;  // option "device_quantile"
+  pba::SelectState* sel_dev = nullptr;
+  pba::SelectState* sel_h = nullptr;  // pinned
   // per-kernel CUDA-event profiling (dpba_profile_*)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;           // pairs: [2i] start, [2i+1] stop
@@ -689,6 +693,8 @@ int dpba_destroy(dpba_handle* h) {
     if (p) cudaIpcCloseMemHandle(p);
   cudaFree(h->peer_box);
   cudaFree(h->peer_ctr);
+  cudaFree(h->sel_dev);
+  if (h->sel_h) cudaFreeHost(h->sel_h);
   if (h->peer_err_h) cudaFreeHost(h->peer_err_h);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->fork_ev) cudaEventDestroy(e);
@@ -1304,7 +1310,7 @@ int dpba_update_point_statuses(dpba_handle* h, int32_t min_valid, double sigma, 
   std::vector<float> energies;
   std::vector<float> e(mp);
   std::vector<uint8_t> st(mp), fl(mp);
-  for (int r = 0; r < N; ++r) {
+  for (int r = 0; r < N && !h->device_quantile; ++r) {
     const int n = h->fr[r].n_lm;
     if (!n) continue;
     CK(cudaMemcpyAsync(fl.data(), h->flags + (size_t)h->fr[r].phys * mp, n, cudaMemcpyDeviceToHost, h->stream));
@@ -1320,7 +1326,20 @@ int dpba_update_point_statuses(dpba_handle* h, int32_t min_valid, double sigma, 
   }
   if (h->world > 1) return fail(h, DPBA_E_STATE, "update_point_statuses: gather the energies on the caller for world_size > 1");
   float thr = 0.f;
-  if (!energies.empty()) {
+  if (h->device_quantile) {
+    // exact radix select on the device: no status / energy row crosses PCIe, one small readback
+    if (!h->sel_dev) {
+      CK(cudaMalloc(&h->sel_dev, sizeof(pba::SelectState)));
+      CK(cudaMallocHost(&h->sel_h, sizeof(pba::SelectState)));
+    }
+    int nmax = 0;
+    for (int r = 0; r < N; ++r) nmax = std::max(nmax, h->fr[r].n_lm);
+    pba::launch_energy_quantile(make_window(h), nmax, 0.75, h->sel_dev, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->sel_h, h->sel_dev, sizeof(pba::SelectState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->sel_h->count) thr = h->sel_h->value + (float)(sigma * sigma / 2);
+  } else if (!energies.empty()) {
     const size_t k = (size_t)((double)energies.size() * 0.75);
     std::nth_element(energies.begin(), energies.begin() + (long)k, energies.end());
     thr = energies[k] + (float)(sigma * sigma / 2);
@@ -1733,6 +1752,10 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
   if (!strcmp(name, "speculative_multi_gpu")) {
     h->speculative_multi = value != 0;
     h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "device_quantile")) {  // updatePointStatuses: radix select on the device instead of host nth_element
+    h->device_quantile = value != 0;
     return DPBA_SUCCESS;
   }
   if (!strcmp(name, "peer_exchange")) {  // our NVLink mailbox all-reduce instead of ncclAllReduce

@@ -185,4 +185,14 @@ struct PeerDev {
   size_t slot;                // doubles per [parity][source] slot
 };
 void launch_peer_allreduce(const PeerDev& pd, const double* in, double* out, size_t off, size_t n, cudaStream_t s);
+
+// ---- device-side quantile of updatePointStatuses (energy_quantile.cu) -------------------------------------------------
+struct SelectState {
+  unsigned hist[256];
+  unsigned prefix, mask;     // bytes of the k-th key fixed so far
+  unsigned long long k;      // rank of the wanted element among the keys that match the prefix
+  unsigned count;            // residuals that took part
+  float value;               // result: the k-th smallest energy
+};
+void launch_energy_quantile(const WindowDev& w, int nmax, double frac, SelectState* st, cudaStream_t s);
 }  // namespace pba

@@ -275,7 +275,9 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* options, const double* 
  * ONE allreduce per iteration carries both.  "fused_prefetch" (default 0): L1 prefetch A/B switch.  "fused_min_blocks"
  * (3 or 4, process-wide): resident CTAs per SM the fused linearise is built for.  "schur_tensor_cores" (default 1, process-wide): the Schur-complement SYRK runs as
  * 3xTF32 mma.sync; 0 selects the fp32 FFMA kernel.  "peer_exchange" (default 0, needs dpba_peer_attach): the sum over
- * ranks runs as the library's own NVLink mailbox kernel instead of ncclAllReduce. */
+ * ranks runs as the library's own NVLink mailbox kernel instead of ncclAllReduce.  "device_quantile" (default 0):
+ * dpba_update_point_statuses finds the 75 % energy quantile with an exact radix select on the device instead of
+ * reading the rows back for std::nth_element. */
 int dpba_set_option(dpba_handle* h, const char* name, int64_t value);
 
 /* ---- measurement hooks (no reference counterpart) --------------------------------------- */

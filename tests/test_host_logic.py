@@ -51,3 +51,35 @@ def test_pseudo_inverse(n_null):
     P = host.sym_pinv(H, n_null)
     ref = O.pseudo_inverse(H, n_null)
     assert np.allclose(P, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+
+
+def test_radix_select_is_nth_element():
+    """The selection rule of csrc/energy_quantile.cu restated in NumPy (order-preserving integer image of the floats,
+    four most-significant-byte-first passes narrowing (prefix, k)) returns the element std::nth_element returns at
+    k = size_t(n * 0.75)  (photometric_bundle_adjustment.cpp:358-361)."""
+    rng = np.random.default_rng(0)
+
+    def select(x, frac=0.75):
+        u = x.astype(np.float32).view(np.uint32)
+        key = np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.uint32)
+        n = len(key)
+        k = int(float(n) * frac)
+        prefix, mask = np.uint32(0), np.uint32(0)
+        for shift in (24, 16, 8, 0):
+            sel = key[(key & mask) == prefix]
+            hist = np.bincount((sel >> np.uint32(shift)) & np.uint32(255), minlength=256)
+            below, b = 0, 0
+            while b < 255 and below + hist[b] <= k:
+                below += hist[b]
+                b += 1
+            k -= below
+            prefix |= np.uint32(b << shift)
+            mask |= np.uint32(255 << shift)
+        back = np.uint32(prefix & 0x7FFFFFFF) if prefix & 0x80000000 else np.uint32(~prefix)
+        return np.array([back], dtype=np.uint32).view(np.float32)[0]
+
+    for n in (1, 2, 3, 7, 1000, 4097):
+        for x in (rng.exponential(50.0, n), rng.normal(0.0, 3.0, n), np.full(n, 2.5), np.round(rng.uniform(0, 4, n))):
+            x = x.astype(np.float32)
+            k = int(float(n) * 0.75)
+            assert select(x) == np.partition(x, k)[k]
