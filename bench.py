@@ -166,6 +166,50 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def _time_cpu_window(cwin, use_float, threads, budget_s, max_iters):
+    """Median per-phase seconds of GN iterations of oracle/cpu_ref on `cwin` (bounded by time and count)."""
+    from oracle import cpu_ref
+    cw = cpu_ref.CpuWindow(cwin, use_float=use_float, threads=threads, native=True)
+    cw.first_estimate()
+    ts, t_begin = [], time.perf_counter()
+    for i in range(2 + max_iters):
+        _, tm, _ = cw.gn_iteration(SIGMA, True, 1e-5, AB_REG, FIXED_REG)
+        if i >= 2:
+            ts.append(tm.copy())
+        if time.perf_counter() - t_begin > budget_s and len(ts) >= 3:
+            break
+    cw.close()
+    return np.median(np.array(ts), axis=0), len(ts)
+
+
+def cpu_baseline_leg():
+    """SURVEY 8(d) 'CPU reference timing': the reference's three-pass dataflow (oracle/cpu_ref) on this box's host
+    cores -- double on min(nproc, 8) - 1 threads (the reference's TBB cap, dsopp_main.cpp:114-117) is the headline;
+    the float build and the 1-thread figure ride along on shorter samples.  Reported, never required."""
+    try:
+        from dsopp_b200 import synth
+        cwin = synth.make_window(n_frames=N_FRAMES, points_per_frame=PTS_PER_GPU, seed=0, ab_scale=0.0)
+        threads = max(1, min(os.cpu_count() or 1, 8) - 1)
+        med, n = _time_cpu_window(cwin, False, threads, 20.0, 40)
+        cpu = {"value": cwin.units / med[5], "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n} GN iterations of the same {cwin.units}-unit window, double precision, "
+                         f"reference three-pass dataflow (oracle/cpu_ref, -O3 -march=native), median",
+               "phase_ms": {"sweep_K1": 1e3 * med[0], "posepose_K3": 1e3 * med[1], "schur_K4": 1e3 * med[2],
+                            "solve_K5": 1e3 * med[3], "energy_K2": 1e3 * med[4], "iteration": 1e3 * med[5]},
+               "host_cores_total": os.cpu_count()}
+        variants = {}
+        for name, use_float, th in (("float_%dthreads" % threads, True, threads), ("double_1thread", False, 1)):
+            try:
+                m, k = _time_cpu_window(cwin, use_float, th, 6.0, 12)
+                variants[name] = {"value": cwin.units / m[5], "cores": th, "iterations": k, "iteration_ms": 1e3 * m[5]}
+            except Exception as ex:
+                variants[name] = {"value": None, "error": str(ex)}
+        cpu["variants"] = variants
+        return cpu
+    except Exception as ex:  # the baseline is reported, never required
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+
 # --------------------------------------------------------------------------------------------------
 def pin(a):
     import torch
@@ -480,32 +524,7 @@ def run_ours(args):
     kernel_ms = {k: {"ms_total": v[0], "launches": v[1]} for k, v in prof.items() if v[1]}
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------------------
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        try:
-            from oracle import cpu_ref
-            from dsopp_b200 import synth
-            cwin = synth.make_window(n_frames=N_FRAMES, points_per_frame=PTS_PER_GPU, seed=0, ab_scale=0.0)
-            threads = max(1, min(os.cpu_count() or 1, 8) - 1)  # TBB cap of the reference, dsopp_main.cpp:114-117
-            cw = cpu_ref.CpuWindow(cwin, use_float=False, threads=threads, native=True)
-            cw.first_estimate()
-            ts, t_begin = [], time.perf_counter()
-            for i in range(2 + 40):
-                e, tm, _ = cw.gn_iteration(SIGMA, True, 1e-5, AB_REG, FIXED_REG)
-                if i >= 2:
-                    ts.append(tm.copy())
-                if time.perf_counter() - t_begin > 20 and len(ts) >= 5:
-                    break
-            ts = np.array(ts)
-            med = np.median(ts, axis=0)
-            cpu = {"value": cwin.units / med[5], "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{len(ts)} GN iterations of the same {cwin.units}-unit window, double precision, "
-                             f"reference three-pass dataflow (oracle/cpu_ref, -O3 -march=native), median",
-                   "phase_ms": {"sweep_K1": 1e3 * med[0], "posepose_K3": 1e3 * med[1], "schur_K4": 1e3 * med[2],
-                                "solve_K5": 1e3 * med[3], "energy_K2": 1e3 * med[4], "iteration": 1e3 * med[5]},
-                   "host_cores_total": os.cpu_count()}
-        except Exception as ex:  # the baseline is reported, never required
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu else None
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -1,8 +1,9 @@
 """Builds oracle/cpu_ref (the C++ restatement used as checker and as the timed CPU baseline).
 
   oracle/_build/libpba_cpu_ref.so         -O3 -march=x86-64-v3 -ffp-contract=off  (portable, bit-stable predicates)
-  oracle/_build/libpba_cpu_ref_native.so  -O3 -march=native                       (timing; the reference's own flags,
-                                          CMakeLists.txt:28) -- built on the machine that runs the benchmark
+  oracle/_build/libpba_cpu_ref_native_<cpu>.so  -O3 -march=native                 (timing; the reference's own flags,
+                                          CMakeLists.txt:28) -- built on the machine that runs the benchmark, the name
+                                          carries a digest of that machine's CPU flags
 
 The reference itself (oracle/_ref) cannot be built: its path needs Eigen, Sophus, TBB and glog, none of which
 is installed, so there is no recipe for it.
@@ -15,7 +16,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "cpu_ref", "pba_cpu_ref.cpp")
 OUT = os.path.join(HERE, "_build")
 PORTABLE = os.path.join(OUT, "libpba_cpu_ref.so")
-NATIVE = os.path.join(OUT, "libpba_cpu_ref_native.so")
 
 
 def _build(target, flags):
@@ -48,8 +48,24 @@ def build_portable():
     return _build(PORTABLE, ["-march=x86-64-v3", "-ffp-contract=off"])
 
 
+def _host_tag():
+    """-march=native code only runs on the CPU it was built for: the file name carries a digest of this host's CPU
+    flags, so a library that travelled here from another machine is never loaded."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
 def build_native():
-    return _build(NATIVE, ["-march=native"])
+    return _build(os.path.join(OUT, f"libpba_cpu_ref_native_{_host_tag()}.so"), ["-march=native"])
 
 
 if __name__ == "__main__":
