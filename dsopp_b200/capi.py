@@ -121,6 +121,7 @@ SIGNATURES = {
     "dpba_profile_read": (C.c_int, [_P, _P, _P]),
     "dpba_comm_unique_id": (C.c_int, [_P]),
     "dpba_comm_init": (C.c_int, [_P, _P, _I, _I]),
+    "dpba_create_reference_depth_maps": (C.c_int, [_P, _I, C.c_double, _P, _P]),
     "dpba_peer_export": (C.c_int, [_P, _P]),
     "dpba_peer_attach": (C.c_int, [_P, _P, _I, _I]),
 }
@@ -366,6 +367,15 @@ class Handle:
         self._ck(self.lib.dpba_refine_immature_landmarks(self.h, ref_slot, n, _ptr(xy), _ptr(idp), _ptr(pt), minimum_inliers,
                                                          sigma, _ptr(out), _ptr(act), _ptr(nv)))
         return out, act.astype(bool), nv
+
+    def create_reference_depth_maps(self, n_levels=4, idepth_variance=-1.0):
+        """createReferenceDepthMaps from the resident window -> list over levels of (idepth_sum, weight), (H_l, W_l) each."""
+        W, H = self.cfg.width, self.cfg.height
+        out = [(np.empty((H >> l, W >> l), np.float32), np.empty((H >> l, W >> l), np.float32)) for l in range(n_levels)]
+        pi = (C.c_void_p * n_levels)(*[a.ctypes.data for a, _ in out])
+        pw = (C.c_void_p * n_levels)(*[b.ctypes.data for _, b in out])
+        self._ck(self.lib.dpba_create_reference_depth_maps(self.h, n_levels, float(idepth_variance), pi, pw))
+        return out
 
     def solve_lm(self, sigma=20.0, ab_reg=(1e12, 1e8), fixed_reg=1e16, max_it=7, min_it=3, ftol=1e-8, ptol=1e-8,
                  force_accept=True, lambda0=1e-5, decrease=1.0, increase=1.0, fej=True, H_marg=None, b_marg=None,

@@ -149,6 +149,8 @@ struct dpba_handle {
   bool device_quantile = false;  // option "device_quantile"
   pba::SelectState* sel_dev = nullptr;
   pba::SelectState* sel_h = nullptr;  // pinned
+  float* dm_buf = nullptr;       // reference depth maps (depth_maps.cu), lazily: 4 * sum_l (W>>l)(H>>l) floats
+  int dm_levels = 0;
   // per-kernel CUDA-event profiling (dpba_profile_*)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;           // pairs: [2i] start, [2i+1] stop
@@ -694,6 +696,7 @@ int dpba_destroy(dpba_handle* h) {
   cudaFree(h->peer_box);
   cudaFree(h->peer_ctr);
   cudaFree(h->sel_dev);
+  cudaFree(h->dm_buf);
   if (h->sel_h) cudaFreeHost(h->sel_h);
   if (h->peer_err_h) cudaFreeHost(h->peer_err_h);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -1740,6 +1743,41 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
     result->converged = h->ctl_h->converged;
     result->iterations = h->ctl_h->iterations_executed;
   }
+  return DPBA_SUCCESS;
+}
+
+int dpba_create_reference_depth_maps(dpba_handle* h, int32_t n_levels, double idepth_variance, float* const* idepth_sum,
+                                     float* const* weight) {
+  REQUIRE(h, "null handle");
+  REQUIRE(h->n_frames >= 1, "no frame");
+  REQUIRE(n_levels >= 1 && n_levels <= 8, "1..8 pyramid levels");
+  REQUIRE((h->cfg.width >> (n_levels - 1)) >= 1 && (h->cfg.height >> (n_levels - 1)) >= 1, "too many levels for this image");
+  const int W = h->cfg.width, H = h->cfg.height;
+  if (!h->dm_buf || h->dm_levels < n_levels) {
+    if (h->dm_buf) {
+      CK(cudaStreamSynchronize(h->stream));
+      cudaFree(h->dm_buf);
+      h->dm_buf = nullptr;
+    }
+    CK(cudaMalloc(&h->dm_buf, pba::dm_level_offset(W, H, n_levels) * sizeof(float)));
+    h->dm_levels = n_levels;
+  }
+  int rc = sync_pairs(h);  // T_target_reference of every older keyframe at the accepted state (tWorldAgent, :29)
+  if (rc) return rc;
+  const bool was_valid = h->rb_valid;
+  const WindowDev w = make_window(h);
+  h->rb_valid = was_valid;  // read-only on the window: the host mirror stays valid
+  pba::launch_reference_depth_maps(w, n_levels, (float)idepth_variance, h->dm_buf, h->stream);
+  CK(cudaGetLastError());
+  for (int l = 0; l < n_levels; ++l) {
+    const size_t nl = (size_t)(W >> l) * (size_t)(H >> l);
+    const float* base = h->dm_buf + pba::dm_level_offset(W, H, l);
+    if (idepth_sum && idepth_sum[l])
+      CK(cudaMemcpyAsync(idepth_sum[l], base + 2 * nl, nl * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (weight && weight[l])
+      CK(cudaMemcpyAsync(weight[l], base + 3 * nl, nl * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
   return DPBA_SUCCESS;
 }
 

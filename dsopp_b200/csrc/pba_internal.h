@@ -195,4 +195,8 @@ struct SelectState {
   float value;               // result: the k-th smallest energy
 };
 void launch_energy_quantile(const WindowDev& w, int nmax, double frac, SelectState* st, cudaStream_t s);
+
+// ---- reference depth maps of the coarse tracker (depth_maps.cu) --------------------------------------------------------
+size_t dm_level_offset(int W, int H, int level);
+void launch_reference_depth_maps(const WindowDev& w, int n_levels, float const_var, float* buf, cudaStream_t s);
 }  // namespace pba

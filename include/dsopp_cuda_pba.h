@@ -266,6 +266,18 @@ typedef struct dpba_lm_result {
 int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* options, const double* H_marg, const double* b_marg,
                   double energy_marg, dpba_lm_result* result);
 
+/* createReferenceDepthMaps (src/tracker/tracker/src/create_depth_maps.cpp:122-146; the tracker calls it right after
+ * every BA solve, monocular_tracker.cpp:465,509) from the window resident in the handle: every landmark of the older
+ * keyframes with status kOk towards the NEWEST keyframe, neither outlier nor marginalised, is reprojected into the
+ * newest keyframe and {idepth / depth_scale * w, w}, w = sqrt(1e-3 / (variance + 1e-12)), is accumulated at the rounded
+ * pixel (:19-58); coarser levels are 2x2 sums (:70-88); empty interior pixels are dilated from their non-empty
+ * neighbours (:90-120).  idepth_variance < 0 takes each landmark's inv_hessian_idepth_idepth (the reference with
+ * estimate_uncertainty, photometric_bundle_adjustment.cpp:252), otherwise the given constant (1e-5 in the reference).
+ * idepth_sum[l] / weight[l] (either array or any entry may be NULL): host buffers of (height >> l) * (width >> l)
+ * floats, row-major [y][x] (= the reference's map(x, y)) -- the two planes dpa_set_reference_depth_map takes. */
+int dpba_create_reference_depth_maps(dpba_handle* h, int32_t n_levels, double idepth_variance, float* const* idepth_sum,
+                                     float* const* weight);
+
 /* Tuning knobs without a reference counterpart.  "cuda_graph" (default 1): dpba_solve_lm replays its launch
  * sequence as one CUDA graph.  "speculative_linearize" (default 1): under force_accept (single GPU) dpba_solve_lm
  * evaluates the trial energy with the fused linearise, which then serves as the next iteration's linearize(); state,

@@ -58,3 +58,43 @@ def test_device_quantile_with_no_eligible_residual():
     h.change_residual_statuses(True)
     assert h.update_point_statuses(1, SIGMA) == 0.0
     h.close()
+
+
+def _compare_maps(got, ref, rtol):
+    for lvl, ((gi, gw), (ri, rw)) in enumerate(zip(got, ref)):
+        assert gi.shape == ri.shape
+        g_on, r_on = gw > 0, rw > 0
+        # fp32 reprojection on the device vs float64 in the oracle: a landmark whose reprojection lies within ~1e-4 px of
+        # a rounding boundary may land on the neighbouring pixel (and drag its dilated neighbours along)
+        assert (g_on != r_on).sum() <= 12 * (1 + (lvl == 0)), (lvl, (g_on != r_on).sum())
+        both = g_on & r_on
+        bad_w = np.abs(gw[both] - rw[both]) > rtol * np.abs(rw[both])
+        bad_i = np.abs(gi[both] - ri[both]) > rtol * np.abs(ri[both])
+        assert bad_w.sum() <= 12 and bad_i.sum() <= 12, (lvl, bad_w.sum(), bad_i.sum())
+
+
+def test_reference_depth_maps_equal_the_oracle():
+    """createReferenceDepthMaps (create_depth_maps.cpp:122-146) on the device vs oracle/depth_map_oracle.py."""
+    from dsopp_b200 import capi
+    from oracle import depth_map_oracle as D
+    from oracle import pba_oracle as O
+
+    win = synth.make_window(n_frames=5, points_per_frame=400, seed=8, ab_scale=0.0)
+    win.frames[1].flags[::7] |= synth.FLAG_OUTLIER
+    win.statuses[(2, 4)][::5] = 1  # kOutlier towards the newest keyframe
+    frames = O.frames_from_window(win)
+    h = capi.upload_window(win)
+    h.first_estimate()
+    # constant variance (the reference without estimate_uncertainty)
+    got = h.create_reference_depth_maps(4, 1e-5)
+    ref = D.create_reference_depth_maps(frames, 4)
+    _compare_maps(got, ref, 1e-4)
+    # per-landmark variance = inv_hessian_idepth_idepth of the last linearisation
+    O.first_estimate_jacobians(frames)
+    prob = O.Problem(frames, SIGMA)
+    prob.linearize()
+    h.linearize(SIGMA, True, True, False)
+    got = h.create_reference_depth_maps(4, -1.0)
+    ref = D.create_reference_depth_maps(frames, 4, [f.inv_hdd for f in frames])
+    _compare_maps(got, ref, 5e-3)
+    h.close()
