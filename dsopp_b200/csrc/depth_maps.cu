@@ -11,7 +11,8 @@
 //                                (levels >= 2) neighbours
 // Everything the function reads is already on the device after a solve (landmarks, statuses towards the newest
 // keyframe, per-pair reprojection constants, inv_hessian_idepth_idepth), so nothing is uploaded; the maps are the input
-// of dpa_set_reference_depth_map (csrc/pose_alignment.cu).  fp32 with float atomics for the rare collisions of two
+// of dpa_set_reference_depth_map (csrc/pose_alignment.cu).  The per-thread bodies live in depth_maps_body.h so that
+// tests/emu can run them on the CPU.  fp32 with float atomics for the rare collisions of two
 // landmarks on one pixel (order of two or three additions: last-bit differences, stated in the test).
 //
 // STATUS: written in round 1 after the GPU budget was spent -- compiled for sm_100a, NOT yet run on hardware; new entry
@@ -20,102 +21,36 @@
 
 #include <cstdint>
 
+#include "depth_maps_body.h"
 #include "pba_internal.h"
 
 namespace pba {
 
 namespace {
 
-constexpr int DM_K_OK = 0;
-constexpr int DM_LM_MARG = 1, DM_LM_OUTLIER = 4;
-
-__device__ __forceinline__ float dm_row(const float* a, float u, float v, float rho) {
-  // same rounding as the sweeps' reprojection (explicitly rounded, never contracted): the ROI predicate below decides
-  // which pixel a landmark lands on
-  return __fadd_rn(__fadd_rn(__fmul_rn(a[0], u), __fmul_rn(a[1], v)), __fadd_rn(a[2], __fmul_rn(a[3], rho)));
-}
-
 __global__ void __launch_bounds__(256) k_depth_splat(const __grid_constant__ WindowDev w, float const_var,
                                                      float* __restrict__ idw, float* __restrict__ wgt) {
-  const int t = w.n_frames - 1;
-  const int r = blockIdx.y;
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= w.n_lm[r]) return;
-  const size_t gl = (size_t)w.phys[r] * w.max_pts + l;
-  if (w.flags[gl] & (DM_LM_MARG | DM_LM_OUTLIER)) return;                                   // :40
-  const size_t res = ((size_t)(w.phys[r] * PBA_MAXF + w.phys[t])) * w.max_pts + l;
-  if (w.status[res] != DM_K_OK) return;                                                     // :38
-  const float4 lm = w.lmk[gl];
-  const float u = lm.x, v = lm.y, rho = lm.z;
-  const float xmax = (float)(w.W - 5), ymax = (float)(w.H - 5);
-  if (!(rho > -1e-4f && rho < 1010.f)) return;                                              // validIdepth
-  if (!(u >= 4.f && v >= 4.f && u <= xmax && v <= ymax)) return;                            // insideCameraROI(reference)
-  const PairConst& pc = w.pairs[r * PBA_MAXF + t];
-  const float X = dm_row(pc.A + 0, u, v, rho), Y = dm_row(pc.A + 4, u, v, rho), Z = dm_row(pc.A + 8, u, v, rho);
-  if (!(Z > 0.f)) return;
-  const float rz = __frcp_rn(Z);
-  const float tu = __fmul_rn(X, rz), tv = __fmul_rn(Y, rz);
-  if (!(tu >= 4.f && tv >= 4.f && tu <= xmax && tv <= ymax)) return;                        // insideCameraROI(target)
-  const int ix = (int)floorf(tu + 0.5f), iy = (int)floorf(tv + 0.5f);                       // round(), positive operands
-  const float qz = dm_row(pc.M + 8, u, v, rho);                                             // getDepthScale
-  const float var = const_var >= 0.f ? const_var : w.inv_hdd[gl];
-  const float wt = sqrtf(1e-3f / (var + 1e-12f));                                           // :52
-  atomicAdd(&idw[(size_t)iy * w.W + ix], rho / qz * wt);
-  atomicAdd(&wgt[(size_t)iy * w.W + ix], wt);
+  dm_splat_thread(w, const_var, idw, wgt, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void __launch_bounds__(256) k_depth_coarse(const float* __restrict__ idw_up, const float* __restrict__ wgt_up,
                                                       int W_up, float* __restrict__ idw, float* __restrict__ wgt, int W,
                                                       int H) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W || y >= H) return;
-  const size_t a = (size_t)(2 * y) * W_up + 2 * x, b = a + W_up;
-  // order of the reference's sum: (2x,2y) + (2x+1,2y) + (2x,2y+1) + (2x+1,2y+1)
-  idw[(size_t)y * W + x] = ((idw_up[a] + idw_up[a + 1]) + idw_up[b]) + idw_up[b + 1];
-  wgt[(size_t)y * W + x] = ((wgt_up[a] + wgt_up[a + 1]) + wgt_up[b]) + wgt_up[b + 1];
+  dm_coarse_pixel(idw_up, wgt_up, W_up, idw, wgt, W, H, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y);
 }
 
 __global__ void __launch_bounds__(256) k_depth_dilate(const float* __restrict__ idw_in, const float* __restrict__ wgt_in,
                                                       float* __restrict__ idw_out, float* __restrict__ wgt_out, int W,
                                                       int H, int axis_neighbours) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W || y >= H) return;
-  const size_t i = (size_t)y * W + x;
-  float id = idw_in[i], wt = wgt_in[i];
-  if (wt <= 0.f && x >= 1 && y >= 1 && x < W - 1 && y < H - 1) {
-    // offsets in the reference's order (:103-107): axis (1,0) (-1,0) (0,1) (0,-1); diagonal (1,1) (-1,-1) (1,-1) (-1,1)
-    const int dxa[4] = {1, -1, 0, 0}, dya[4] = {0, 0, 1, -1};
-    const int dxd[4] = {1, -1, 1, -1}, dyd[4] = {1, -1, -1, 1};
-    float sum = 0.f, num = 0.f, numn = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int dx = axis_neighbours ? dxa[k] : dxd[k], dy = axis_neighbours ? dya[k] : dyd[k];
-      const size_t j = (size_t)(y + dy) * W + (x + dx);
-      const float nw = wgt_in[j];
-      if (nw > 0.f) {
-        sum += idw_in[j];
-        num += nw;
-        numn += 1.f;
-      }
-    }
-    if (numn > 0.f) {
-      id = sum / numn;
-      wt = num / numn;
-    }
-  }
-  idw_out[i] = id;
-  wgt_out[i] = wt;
+  dm_dilate_pixel(idw_in, wgt_in, idw_out, wgt_out, W, H, axis_neighbours, blockIdx.x * blockDim.x + threadIdx.x,
+                  blockIdx.y);
 }
 
 }  // namespace
 
 // buf: 4 * sum_l (W>>l)(H>>l) floats: per level [idw_raw | wgt_raw | idw | wgt]; the dilated maps of level l start at
 // dm_level_offset(...) + 2 * n_l.  The caller has the per-pair constants at the accepted state (k_pair_setup).
-size_t dm_level_offset(int W, int H, int level) {
-  size_t off = 0;
-  for (int l = 0; l < level; ++l) off += 4 * (size_t)(W >> l) * (size_t)(H >> l);
-  return off;
-}
+size_t dm_level_offset(int W, int H, int level) { return dm_level_offset_of(W, H, level); }
 
 void launch_reference_depth_maps(const WindowDev& w, int n_levels, float const_var, float* buf, cudaStream_t s) {
   const int W = w.W, H = w.H;

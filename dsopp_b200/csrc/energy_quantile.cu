@@ -11,41 +11,19 @@
 // (prefix, k).  Four passes give the k-th smallest bit pattern, i.e. the very float nth_element returns.
 //
 // STATUS: written in round 1 after the GPU budget was spent -- compiled for sm_100a, NOT yet run on hardware, so the
-// C ABI keeps the host path unless the option is set (tests/test_gpu_parity.py has the comparison, enabled with
-// DPBA_TEST_EXPERIMENTAL=1).
+// C ABI keeps the host path unless the option is set (tests/test_zz_gpu_experimental.py has the comparison, enabled with
+// DPBA_TEST_EXPERIMENTAL=1).  The enumeration and selection code lives in energy_quantile_body.h and also runs on the
+// CPU in tests/test_kernel_emulation.py.
 #include <cuda_runtime.h>
 
 #include <cstdint>
 
+#include "energy_quantile_body.h"
 #include "pba_internal.h"
 
 namespace pba {
 
 namespace {
-
-constexpr int SEL_K_OK = 0;     // ResidualStatus kOk
-constexpr int SEL_LM_MARG = 1;  // landmark is_marginalized
-
-__device__ __forceinline__ unsigned ordered_key(float x) {
-  const unsigned u = __float_as_uint(x);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_to_float(unsigned k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
-// key of flattened residual `idx` (pair-major, `nmax` landmark slots per ordered pair); false when it does not take part
-__device__ __forceinline__ bool residual_key(const WindowDev& w, long long idx, int nmax, unsigned& key) {
-  const int N = w.n_frames;
-  const int p = (int)(idx / nmax), l = (int)(idx - (long long)p * nmax);
-  const int r = p / N, t = p - r * N;
-  if (p >= N * N || r == t || w.frame_marg[t] || l >= w.n_lm[r]) return false;
-  if (w.flags[(size_t)w.phys[r] * w.max_pts + l] & SEL_LM_MARG) return false;
-  const size_t res = ((size_t)(w.phys[r] * PBA_MAXF + w.phys[t])) * w.max_pts + l;
-  if (w.status[res] != SEL_K_OK) return false;
-  key = ordered_key(w.energy[res]);
-  return true;
-}
 
 // one radix pass: histogram of byte (key >> shift) over the residuals whose higher bytes equal st->prefix
 __global__ void __launch_bounds__(256) k_select_hist(const __grid_constant__ WindowDev w, SelectState* __restrict__ st,
@@ -77,48 +55,18 @@ __global__ void __launch_bounds__(256) k_select_pick(SelectState* __restrict__ s
   h[threadIdx.x] = st->hist[threadIdx.x];
   st->hist[threadIdx.x] = 0;
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  unsigned long long k = st->k;
-  if (shift == 24) {  // first pass: the histogram covers everything -> n and k = size_t(n * 0.75)  (:358)
-    unsigned long long n = 0;
-    for (int b = 0; b < 256; ++b) n += h[b];
-    st->count = (unsigned)n;
-    k = (unsigned long long)((double)n * frac);
-    if (n == 0) {
-      st->value = 0.f;
-      return;
-    }
-  } else if (st->count == 0) {
-    return;
-  }
-  unsigned long long below = 0;
-  int b = 0;
-  for (; b < 255; ++b) {
-    if (below + h[b] > k) break;
-    below += h[b];
-  }
-  st->k = k - below;
-  st->prefix |= (unsigned)b << shift;
-  st->mask |= 255u << shift;
-  if (shift == 0) st->value = key_to_float(st->prefix);
+  if (threadIdx.x == 0) select_pick(st, h, shift, frac);
 }
 
 __global__ void k_select_init(SelectState* st) {
-  st->hist[threadIdx.x] = 0;
-  if (threadIdx.x == 0) {
-    st->prefix = 0;
-    st->mask = 0;
-    st->k = 0;
-    st->count = 0;
-    st->value = 0.f;
-  }
+  if (threadIdx.x == 0) select_init(st);
 }
 
 }  // namespace
 
 // leaves {count, value = k-th smallest energy (k = size_t(count * frac))} in *st; `nmax` = max landmarks of a frame
 void launch_energy_quantile(const WindowDev& w, int nmax, double frac, SelectState* st, cudaStream_t s) {
-  k_select_init<<<1, 256, 0, s>>>(st);
+  k_select_init<<<1, 32, 0, s>>>(st);
   if (nmax > 0) {
     const long long total = (long long)w.n_frames * w.n_frames * nmax;
     long long ctas = (total + 255) / 256;
