@@ -44,8 +44,10 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   return v;
 }
 
-// ~2 s at 1.9 GHz: a peer that has not arrived by then never will (it failed); give up loudly instead of hanging the GPU
-constexpr long long PEER_TIMEOUT_CYCLES = 4000000000LL;
+// ~15 s at 1.9 GHz.  Ranks legitimately reach an exchange seconds apart (first-call graph instantiation, a rank that
+// does extra host work), so the bound is generous; a peer that has not arrived by then has failed -- give up loudly
+// (DPBA_E_COMM on the host) instead of hanging the GPU until an outer limit kills the process
+constexpr long long PEER_TIMEOUT_CYCLES = 30000000000LL;
 
 __global__ void __launch_bounds__(256) k_peer_allreduce(PeerDev pd, const double* __restrict__ in,
                                                         double* __restrict__ out, size_t off, size_t n2) {
@@ -85,7 +87,8 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerDev pd, const double
     // ---- wait for the same slice of rank threadIdx.x ---------------------------------------------------------------
     const unsigned* f = my_flags + threadIdx.x * PEER_MAXC + c;
     const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+    // after one time-out the run is lost anyway: later exchanges do not wait again (the host reports DPBA_E_COMM)
+    while (*reinterpret_cast<volatile int*>(pd.error) == 0 && (int)(ld_acquire_sys(f) - epoch) < 0) {
       __nanosleep(32);
       if (clock64() - t0 > PEER_TIMEOUT_CYCLES) {
         *pd.error = 1;

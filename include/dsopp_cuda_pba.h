@@ -314,7 +314,7 @@ int dpba_comm_init(dpba_handle* h, const uint8_t id[128], int32_t rank, int32_t 
  * ncclAllReduce (66.6 KB per GN iteration: latency, not bandwidth).  Every rank exports its mailbox (a 64-byte
  * cudaIpcMemHandle_t), the caller all-gathers the handles (rank-major, world_size * 64 bytes), every rank attaches,
  * the caller BARRIERS, then dpba_set_option(h, "peer_exchange", 1).  All ranks must make the same sequence of solver
- * calls (they do: frames are replicated); a rank that never arrives makes the others fail with DPBA_E_COMM after ~2 s
+ * calls (they do: frames are replicated); a rank that never arrives makes the others fail with DPBA_E_COMM after ~15 s
  * instead of hanging.  Barrier again before dpba_destroy.  One node (one NVSwitch domain), 2..8 ranks. */
 int dpba_peer_export(dpba_handle* h, uint8_t ipc_handle[64]);
 int dpba_peer_attach(dpba_handle* h, const uint8_t* ipc_handles, int32_t rank, int32_t world_size);

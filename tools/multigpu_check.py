@@ -5,7 +5,7 @@ reduced system inside dpba_linearize / dpba_solve_lm) must reproduce the single-
 
 DPBA_SPEC_MULTI=1   also compares the one-allreduce speculative sequence with the two-sweep sequence
 DPBA_PEER_EXCHANGE=1 also repeats everything with the NVLink mailbox all-reduce (peer_exchange.cu) instead of NCCL
-(run under `timeout`: the kernel gives up after ~2 s per exchange if a peer never arrives, it does not hang)
+(run under `timeout`: the kernel gives up after ~15 s per exchange if a peer never arrives, it does not hang)
 """
 import os
 import sys
