@@ -140,7 +140,7 @@ struct dpba_handle {
   // peer-memory exchange (peer_exchange.cu): this rank's mailbox, the peers' mailboxes opened over CUDA IPC
   void* peer_box = nullptr;
   void* peer_open[pba::PEER_MAXW] = {};
-  unsigned* peer_ctr = nullptr;  // device: {seq, done}
+  unsigned* peer_ctr = nullptr;  // device: {seq, done, error, pad}
   int* peer_err_h = nullptr;     // mapped pinned: set by the kernel after a time-out
   pba::PeerDev peer{};
   bool peer_attached = false;
@@ -1878,12 +1878,12 @@ int dpba_peer_export(dpba_handle* h, uint8_t handle[64]) {
   CK(cudaSetDevice(h->cfg.device));
   if (!h->peer_box) {
     CK(cudaMalloc(&h->peer_box, PEER_BOX_BYTES));
-    CK(cudaMalloc(&h->peer_ctr, 2 * sizeof(unsigned)));
+    CK(cudaMalloc(&h->peer_ctr, 4 * sizeof(unsigned)));  // seq, done, error, pad
     CK(cudaHostAlloc(&h->peer_err_h, sizeof(int), cudaHostAllocMapped));
     *h->peer_err_h = 0;
   }
   CK(cudaMemset(h->peer_box, 0, PEER_BOX_BYTES));
-  CK(cudaMemset(h->peer_ctr, 0, 2 * sizeof(unsigned)));
+  CK(cudaMemset(h->peer_ctr, 0, 4 * sizeof(unsigned)));
   CK(cudaDeviceSynchronize());
   cudaIpcMemHandle_t ipc;
   CK(cudaIpcGetMemHandle(&ipc, h->peer_box));
@@ -1916,7 +1916,8 @@ int dpba_peer_attach(dpba_handle* h, const uint8_t* handles, int32_t rank, int32
   pd.done = h->peer_ctr + 1;
   int* err_dev = nullptr;
   CK(cudaHostGetDevicePointer(&err_dev, h->peer_err_h, 0));
-  pd.error = err_dev;
+  pd.error = reinterpret_cast<int*>(h->peer_ctr + 2);
+  pd.error_host = err_dev;
   pd.rank = rank;
   pd.world = world;
   pd.slot = N_EXCHANGE;

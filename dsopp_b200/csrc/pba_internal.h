@@ -180,7 +180,8 @@ struct PeerDev {
   unsigned* flag[PEER_MAXW];  // mailbox flags of rank r: [PEER_MAXW sources][PEER_MAXC] epochs
   unsigned* seq;              // local: number of completed exchanges (the epoch of the last one)
   unsigned* done;             // local: CTAs of the running exchange that have finished
-  int* error;                 // local (mapped pinned host memory): 1 after a time-out
+  int* error;                 // local device word: 1 after a time-out (later exchanges do not wait again)
+  int* error_host;            // the same flag in mapped pinned host memory, for the host to read after a synchronisation
   int rank, world;
   size_t slot;                // doubles per [parity][source] slot
 };

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerDev pd, const double
     while (*reinterpret_cast<volatile int*>(pd.error) == 0 && (int)(ld_acquire_sys(f) - epoch) < 0) {
       __nanosleep(32);
       if (clock64() - t0 > PEER_TIMEOUT_CYCLES) {
-        *pd.error = 1;
+        *reinterpret_cast<volatile int*>(pd.error) = 1;
+        *reinterpret_cast<volatile int*>(pd.error_host) = 1;
         break;
       }
     }
