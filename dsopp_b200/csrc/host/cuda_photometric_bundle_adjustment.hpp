@@ -14,7 +14,7 @@
 #include <vector>
 
 #include "cuda_pba_problem.hpp"
-#include "levenberg_marquardt_algorithm.hpp"
+#include "lm_driver.hpp"
 
 namespace dsopp_b200 {
 

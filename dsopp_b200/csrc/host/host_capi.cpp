@@ -208,6 +208,64 @@ __attribute__((visibility("default"))) int dpbah_lm_solve(dpba_handle* h, int n_
   return 0;
 }
 
+// The LM driver on a SCRIPTED problem (energies, valid counts and step norms come from arrays; every call is recorded):
+// lets the tests compare its control flow call by call with the reference's own driver (tests/test_reference_parts.py).
+// calls_out codes: 0 calculateEnergy, 1 linearize, 2 calculateStep, 3 acceptStep, 4 rejectStep.  Returns the call count.
+__attribute__((visibility("default"))) int dpbah_lm_scripted(int max_it, double lambda0, double ftol, double ptol,
+                                                            int force_accept, int min_it, double decrease,
+                                                            double increase, const double* energies, const int* valid,
+                                                            int n_energy, const double* norms, int n_norms,
+                                                            int* calls_out, int cap_calls, double* lambdas_out,
+                                                            int cap_lambdas, double* energy_out, int* valid_out,
+                                                            int* converged_out) {
+  namespace lm = levenberg_marquardt_algorithm;
+  struct Scripted {
+    const double* e;
+    const int* v;
+    int ne;
+    const double* nr;
+    int nn;
+    int ie = 0, ia = 0;
+    std::vector<int> calls;
+    std::vector<double> lambdas;
+    std::pair<lm::Precision, int> calculateEnergy() {
+      calls.push_back(0);
+      const int i = ie < ne ? ie : ne - 1;
+      ++ie;
+      return {e[i], v[i]};
+    }
+    void linearize() { calls.push_back(1); }
+    void calculateStep(const lm::Precision lambda) {
+      calls.push_back(2);
+      lambdas.push_back(lambda);
+    }
+    std::pair<lm::Precision, lm::Precision> acceptStep() {
+      calls.push_back(3);
+      const int i = ia < nn ? ia : nn - 1;
+      ++ia;
+      return {nr[2 * i], nr[2 * i + 1]};
+    }
+    void rejectStep() { calls.push_back(4); }
+    bool stop() { return false; }
+  } p{energies, valid, n_energy, norms, n_norms, 0, 0, {}, {}};
+  lm::Options o;
+  o.max_num_iterations = (size_t)max_it;
+  o.min_num_iterations = (size_t)min_it;
+  o.function_tolerance = ftol;
+  o.parameter_tolerance = ptol;
+  o.force_accept = force_accept != 0;
+  o.initial_levenberg_marquardt_regularizer = lambda0;
+  o.levenberg_marquardt_regularizer_decrease_on_accept = decrease;
+  o.levenberg_marquardt_regularizer_increase_on_reject = increase;
+  const lm::Result r = lm::solve(p, o);
+  for (int i = 0; i < (int)p.calls.size() && i < cap_calls; ++i) calls_out[i] = p.calls[i];
+  for (int i = 0; i < (int)p.lambdas.size() && i < cap_lambdas; ++i) lambdas_out[i] = p.lambdas[i];
+  *energy_out = r.energy;
+  *valid_out = r.number_of_valid_residuals;
+  *converged_out = r.converged ? 1 : 0;
+  return (int)p.calls.size();
+}
+
 __attribute__((visibility("default"))) void dpbah_normal_solve(int n, const double* H, const double* b, double* x) {
   NormalLinearSystem s(n);
   std::memcpy(s.H.a.data(), H, (size_t)n * n * sizeof(double));

@@ -39,6 +39,8 @@ def load_library():
     lib.dpbah_lm_solve.argtypes = [_P, _I, _P, _P, _D, _D, _D, _D, _I, _I, _D, _D, _I, _D, _D, _D, C.POINTER(_D),
                                    C.POINTER(_I)]
     lib.dpbah_normal_solve.argtypes = [_I, _P, _P, _P]
+    lib.dpbah_lm_scripted.restype = _I
+    lib.dpbah_lm_scripted.argtypes = [_I, _D, _D, _D, _I, _I, _D, _D, _P, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P]
     lib.dpbah_reduce_system.argtypes = [_I, _P, _P, _I, _P]
     lib.dpbah_sym_pinv.argtypes = [_I, _P, _I, _P]
     _lib = lib
@@ -57,6 +59,27 @@ def normal_solve(H, b):
     x = np.zeros_like(b)
     lib.dpbah_normal_solve(len(b), _ptr(H), _ptr(b), _ptr(x))
     return x
+
+
+LM_CALL_NAMES = ["energy", "linearize", "step", "accept", "reject"]
+
+
+def lm_scripted(energies, valid, norms, max_it=50, lambda0=1e-5, ftol=1e-8, ptol=1e-8, force_accept=False, min_it=0,
+                dec=2.0, inc=10.0):
+    """The C++ host LM driver on a scripted problem -> (calls, lambdas, energy, n_valid, converged); no GPU involved."""
+    lib = load_library()
+    e = _f64(energies)
+    v = np.ascontiguousarray(valid, dtype=np.int32)
+    nr = _f64(np.asarray(norms, dtype=np.float64).reshape(-1, 2))
+    calls = np.zeros(8 * (max_it + 2), np.int32)
+    lams = np.zeros(max_it + 2)
+    out_e, out_v, out_c = np.zeros(1), np.zeros(1, np.int32), np.zeros(1, np.int32)
+    n = lib.dpbah_lm_scripted(int(max_it), lambda0, ftol, ptol, int(force_accept), int(min_it), dec, inc, _ptr(e), _ptr(v),
+                              len(e), _ptr(nr), len(nr), _ptr(calls), len(calls), _ptr(lams), len(lams), _ptr(out_e),
+                              _ptr(out_v), _ptr(out_c))
+    calls = calls[:n]
+    return ([LM_CALL_NAMES[c] for c in calls], lams[:int((calls == 2).sum())].copy(), float(out_e[0]), int(out_v[0]),
+            bool(out_c[0]))
 
 
 def reduce_system(H, b, elim):

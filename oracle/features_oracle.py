@@ -6,6 +6,9 @@ Restates, paths relative to /root/reference/src/features/:
   PixelDataFrame (pyramid)        src/pixel_data_frame.cpp:12-31
   {I,dx,dy} packing               src/calculate_pixelinfo.cpp:340-374 (scalar definition; the AVX2 path is tested equal to
                                   it by test/test/features/test_dxdy_accelerated.cpp:43-80)
+pixel_info is PINNED by the reference itself: calculate_pixelinfo.cpp compiles here from its own source
+(oracle/build_ref.py) and pixel_info equals it bit for bit in double (AVX2 and plain-C paths) and float
+(tests/test_reference_parts.py, tests/golden/ref_parts.npz).  The other three are parity unpinned (OpenCV / Eigen absent).
 All arithmetic is exact in the given dtype (float32 = the reference's USE_FLOAT build), so the device result must be
 bit-identical: the only operations are a table look-up, one multiply by max / (v + 1), sums of four and halves.
 """

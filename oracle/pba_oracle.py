@@ -12,6 +12,9 @@ reference's own *property* tests (tests/test_oracle_properties.py):
   test_reprojects.cpp (left-perturbation reprojection Jacobians),
   test_analytical_diff.cpp (analytic vs numeric residual Jacobians),
   test_dxdy_accelerated.cpp (gradient definition).
+EXCEPT lm_solve below: the reference's LM driver is one of the two pieces that do compile here from their own source
+(oracle/build_ref.py), and lm_solve reproduces its call sequence, lambda schedule and result exactly on scripted
+problems (tests/test_reference_parts.py, tests/golden/ref_parts.npz).
 
 Third-party arithmetic restated from its published closed forms (sources not under
 /root/reference): Sophus @593db475 (SE3::exp, Adj, inverse; tangent = [upsilon; omega]) and

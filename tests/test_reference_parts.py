@@ -1,0 +1,162 @@
+"""Pins against the REFERENCE ITSELF, for the two pieces of it that compile here from their own sources
+(oracle/build_ref.py -> oracle/_ref/libdsopp_ref_parts.so; everything else on the path needs Eigen / Sophus / TBB):
+
+  * dsopp::features::calculate_pixelinfo<1>  (src/features/src/calculate_pixelinfo.cpp):
+    the {I, dx, dy} gradient definition the bilinear sampler reads -- both its AVX2 and its plain-C path;
+  * levenberg_marquardt_algorithm::solve     (levenberg_marquardt_algorithm.hpp:77-128, row a17): the LM control flow,
+    driven by scripted problems and compared call by call.
+
+Each check runs twice: against the committed golden vectors made from the reference (tests/golden/ref_parts.npz,
+tools/make_ref_golden.py) -- always -- and against the library itself when it can be built or was shipped.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from dsopp_b200 import synth
+from oracle import features_oracle as F
+from oracle import pba_oracle as O
+from oracle import ref_parts as R
+
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_parts.npz"))
+needs_ref = pytest.mark.skipif(not R.available(), reason="neither /root/reference nor oracle/_ref is present")
+CALLS = R.CALL_NAMES
+
+
+class Scripted:
+    """The problem the shim scripts (oracle/ref_shims/ref_parts.cpp), for oracle.pba_oracle.lm_solve."""
+
+    def __init__(self, energies, valid, norms):
+        self.e, self.v, self.norms = energies, valid, np.asarray(norms).reshape(-1, 2)
+        self.ie = self.ia = 0
+        self.calls, self.lams = [], []
+
+    def calculate_energy(self):
+        self.calls.append("energy")
+        i = min(self.ie, len(self.e) - 1)
+        self.ie += 1
+        return float(self.e[i]), int(self.v[i])
+
+    def linearize(self):
+        self.calls.append("linearize")
+
+    def calculate_step(self, lam):
+        self.calls.append("step")
+        self.lams.append(lam)
+        return np.zeros(1)
+
+    def accept_step(self):
+        self.calls.append("accept")
+        i = min(self.ia, len(self.norms) - 1)
+        self.ia += 1
+        return float(self.norms[i, 0]), float(self.norms[i, 1])
+
+    def reject_step(self):
+        self.calls.append("reject")
+
+    def stop(self):
+        return False
+
+
+def oracle_lm(e, v, norms, max_it, lambda0, ftol, ptol, force_accept, min_it, dec, inc):
+    p = Scripted(e, v, norms)
+    opt = O.LMOptions(int(max_it), lambda0, ftol, ptol, bool(force_accept), int(min_it), dec, inc)
+    energy, nvalid, conv = O.lm_solve(p, opt)
+    return p.calls, np.array(p.lams), energy, nvalid, conv
+
+
+def golden_lm_cases():
+    for i in range(int(GOLDEN["lm_n"])):
+        o = GOLDEN[f"lm_{i}_opts"]
+        yield (i, GOLDEN[f"lm_{i}_e"], GOLDEN[f"lm_{i}_v"], GOLDEN[f"lm_{i}_norms"],
+               dict(max_it=int(o[0]), lambda0=o[1], ftol=o[2], ptol=o[3], force_accept=bool(o[4]), min_it=int(o[5]),
+                    dec=o[6], inc=o[7]))
+
+
+# ---- LM control flow ---------------------------------------------------------------------------------------------
+def test_lm_restatement_reproduces_the_reference_traces_golden():
+    seen = set()
+    for i, e, v, nr, o in golden_lm_cases():
+        calls, lams, E, nv, conv = oracle_lm(e, v, nr, **o)
+        ref_calls = [CALLS[c] for c in GOLDEN[f"lm_{i}_calls"]]
+        assert calls == ref_calls, (i, o)
+        assert np.array_equal(lams, GOLDEN[f"lm_{i}_lams"]), i
+        rE, rn, rc = GOLDEN[f"lm_{i}_result"]
+        assert (E, nv, bool(conv)) == (rE, int(rn), bool(rc)), i
+        seen.add((o["force_accept"], "reject" in calls, bool(conv), nv == 0 or 0 in v))
+    # the fixture exercises every branch: forced and free runs, rejected steps, convergence, zero valid residuals
+    assert len(seen) >= 10
+
+
+def test_product_host_lm_driver_reproduces_the_reference_traces_golden():
+    """dsopp_b200/csrc/host/lm_driver.hpp (the C++ driver the drop-in solver class runs) on the same scripts."""
+    from dsopp_b200 import host
+    for i, e, v, nr, o in golden_lm_cases():
+        calls, lams, E, nv, conv = host.lm_scripted(e, v, nr, **o)
+        assert calls == [CALLS[c] for c in GOLDEN[f"lm_{i}_calls"]], (i, o)
+        assert np.array_equal(lams, GOLDEN[f"lm_{i}_lams"]), i
+        rE, rn, rc = GOLDEN[f"lm_{i}_result"]
+        assert (E, nv, conv) == (rE, int(rn), bool(rc)), i
+
+
+@needs_ref
+def test_lm_restatement_reproduces_the_reference_live():
+    from dsopp_b200 import host
+    rng = np.random.default_rng(123)
+    for _ in range(300):
+        max_it = int(rng.choice([1, 2, 7, 20]))
+        m = max_it + 3
+        e = np.cumprod(np.concatenate([[rng.uniform(1e2, 1e5)], rng.choice([0.5, 0.99, 1.0, 1.0 - 1e-9, 1.3], m - 1)]))
+        v = rng.integers(0, 4, m).astype(np.int32) * rng.integers(0, 2, m).astype(np.int32) + (rng.random(m) < 0.9)
+        nr = np.stack([rng.uniform(1e-2, 1e3, m), 10.0 ** rng.uniform(-13, 0, m)], axis=1)
+        force = bool(rng.integers(0, 2))
+        o = dict(max_it=max_it, lambda0=1e-5, ftol=float(rng.choice([1e-8, 0.0])), ptol=float(rng.choice([1e-8, 0.0])),
+                 force_accept=force, min_it=3 if force else 0, dec=float(rng.choice([1.0, 2.0])),
+                 inc=float(rng.choice([1.0, 10.0])))
+        ref = R.lm_solve(e, v.astype(np.int32), nr, **o)
+        got = oracle_lm(e, v.astype(np.int32), nr, **o)
+        assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and got[2:] == ref[2:], o
+        cpp = host.lm_scripted(e, v.astype(np.int32), nr, **o)
+        assert cpp[0] == ref[0] and np.array_equal(cpp[1], ref[1]) and cpp[2:] == ref[2:], o
+
+
+def test_production_options_follow_the_reference():
+    """fabric.cpp:99 options (force_accept, min 3, max 7, decrease = increase = 1): three forced accepts, then the first
+    rejected step ends the solve after one more energy evaluation."""
+    e = [100.0, 120.0, 90.0, 95.0, 80.0, 85.0, 70.0]
+    calls, lams, E, nv, conv = oracle_lm(e, [9] * 7, [[1.0, 1.0]], 7, 1e-5, 1e-8, 1e-8, True, 3, 1.0, 1.0)
+    assert calls == ["energy"] + ["linearize", "step", "energy", "accept"] * 4 + ["linearize", "step", "energy", "reject",
+                                                                                  "energy"]
+    assert E == 80.0 and np.all(lams == 1e-5)
+    if R.available():
+        assert R.lm_solve(e, [9] * 7, [[1.0, 1.0]], 7, 1e-5, 1e-8, 1e-8, True, 3, 1.0, 1.0)[0] == calls
+
+
+# ---- gradient definition -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["a", "b", "c", "d", "e"])
+def test_pixelinfo_restatements_equal_the_reference_golden(name):
+    I = GOLDEN[f"px_{name}_in"]
+    ref64, ref32 = GOLDEN[f"px_{name}_f64"], GOLDEN[f"px_{name}_f32"]
+    # bit for bit, in both precisions, for both restatements (oracle/features_oracle.py feeds the GPU image-preparation
+    # tests, dsopp_b200/synth.py builds every synthetic window)
+    assert np.array_equal(F.pixel_info(I), ref64)
+    assert np.array_equal(synth.pixelinfo(I), ref64)
+    assert np.array_equal(F.pixel_info(I.astype(np.float32)), ref32)
+    assert np.array_equal(synth.pixelinfo(I.astype(np.float32)), ref32)
+
+
+@needs_ref
+@pytest.mark.parametrize("shape,aligned", [((480, 640), True), ((480, 640), False), ((60, 80), True), ((31, 45), False),
+                                           ((2, 3), False)])
+def test_pixelinfo_restatements_equal_the_reference_live(shape, aligned):
+    I = np.random.default_rng(shape[0]).uniform(0.0, 255.0, shape)
+    assert np.array_equal(F.pixel_info(I), R.pixelinfo(I, aligned))           # AVX2 path when aligned, else plain C
+    I32 = I.astype(np.float32)
+    assert np.array_equal(F.pixel_info(I32), R.pixelinfo(I32, aligned))
+
+
+@needs_ref
+def test_reference_avx2_dispatch_quirk_is_guarded():
+    with pytest.raises(ValueError):
+        R.pixelinfo(np.zeros((8, 12)), aligned=True)
