@@ -206,3 +206,58 @@ def test_energy_quantile_without_any_eligible_residual(emu):
     count = emu.emu_energy_quantile(3, 32, _p(n_lm), _p(np.arange(3, dtype=np.int32)), _p(np.zeros(3, np.int32)),
                                     _p(flags), _p(status), _p(energy), 0.75, _p(value))
     assert count == 0 and value[0] == 0.0
+
+
+# ---- NVLink mailbox all-reduce with real threads ---------------------------------------------------------------------
+PEER_SRC = os.path.join(ROOT, "tests", "emu", "peer_emu.cpp")
+PEER_LIB = os.path.join(OUT, "libpeer_emu.so")
+EMU_FLAGS = ["-std=c++17", "-O1", "-g", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include",
+             "-I", os.path.join(ROOT, "dsopp_b200", "csrc"), "-I", os.path.join(ROOT, "include")]
+
+
+def lm_exchange_calls(n_frames=8):
+    """(offset, count) of the exchanges dpba_solve_lm / dpba_linearize / dpba_evaluate issue: the whole block (system +
+    scalars), the system alone, the 8 scalars alone -- different grid sizes over overlapping parts of the mailbox."""
+    D = 8 * n_frames
+    sysn = 2 * (D * D + D)
+    calls = [(0, sysn + 8)] * 3 + [(sysn, 8), (0, sysn), (sysn, 8), (sysn, 8)] + [(0, sysn + 8)] * 4 + [(sysn, 8)]
+    return np.array([c[0] for c in calls], np.int64), np.array([c[1] for c in calls], np.int64), sysn + 8
+
+
+@pytest.fixture(scope="module")
+def peer_emu():
+    os.makedirs(OUT, exist_ok=True)
+    deps = [PEER_SRC, os.path.join(ROOT, "dsopp_b200", "csrc", "peer_exchange_body.h"),
+            os.path.join(ROOT, "dsopp_b200", "csrc", "pba_internal.h")]
+    if not os.path.exists(PEER_LIB) or any(os.path.getmtime(d) > os.path.getmtime(PEER_LIB) for d in deps):
+        subprocess.check_call(["g++"] + EMU_FLAGS + ["-fPIC", "-shared", "-o", PEER_LIB, PEER_SRC])
+    lib = C.CDLL(PEER_LIB)
+    lib.emu_peer_run.restype = C.c_longlong
+    lib.emu_peer_run.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint, C.c_int]
+    return lib
+
+
+@pytest.mark.parametrize("world,n_frames", [(2, 8), (3, 5), (8, 8), (4, 16)])
+def test_peer_exchange_code_with_real_threads(peer_emu, world, n_frames):
+    """peer_exchange_body.h (the kernel's own steps) with one host thread per CTA and rank: every rank gets the
+    rank-ordered sum of every exchange, bit for bit, whatever the interleaving and however far one rank runs ahead."""
+    offs, ns, slot = lm_exchange_calls(n_frames)
+    for seed in range(4):
+        bad = peer_emu.emu_peer_run(world, len(offs), _p(offs), _p(ns), slot, seed, 150 if seed else 0)
+        assert bad == 0, (world, seed, bad)
+
+
+def test_peer_exchange_code_is_race_free_under_thread_sanitizer():
+    exe = os.path.join(OUT, "peer_tsan")
+    main = os.path.join(ROOT, "tests", "emu", "peer_tsan_main.cpp")
+    os.makedirs(OUT, exist_ok=True)
+    build = subprocess.run(["g++"] + EMU_FLAGS + ["-fsanitize=thread", "-Wno-tsan", "-o", exe, main, PEER_SRC],
+                           capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime here: " + build.stderr[-200:])
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
+    if "FATAL: ThreadSanitizer" in run.stderr:  # e.g. unsupported address-space layout inside a sandbox
+        pytest.skip(run.stderr.strip().splitlines()[0])
+    assert "WARNING: ThreadSanitizer" not in run.stderr, run.stderr[-2000:]
+    assert run.returncode == 0 and "wrong elements: 0" in run.stdout, (run.returncode, run.stdout, run.stderr[-500:])
