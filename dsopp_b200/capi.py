@@ -146,7 +146,10 @@ def load_library(path: str = CUDA_LIB_PATH):
 
 
 def _ptr(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    """Address of a NumPy array for a c_void_p parameter (None -> NULL).  The plain integer is about twice as cheap as
+    ndarray.ctypes.data_as(), and an upload / readback makes ~130 of these.  The caller keeps `a` referenced until the C
+    call has returned (every wrapper below binds its converted arrays to local names first)."""
+    return None if a is None else a.ctypes.data
 
 
 def _f32(a):
@@ -282,15 +285,16 @@ class Handle:
         arrs = {t: _u8(a) for t, a in items if a is not None and t != r}
         n = len(next(iter(arrs.values()))) if arrs else 0
         ptrs = (C.c_void_p * n_fr)(*[arrs[t].ctypes.data if t in arrs else None for t in range(n_fr)])
-        self._ck(self.lib.dpba_set_frame_statuses(self.h, r, n, C.cast(ptrs, C.c_void_p)))
+        self._ck(self.lib.dpba_set_frame_statuses(self.h, r, n, ptrs))
 
     def get_frame_statuses(self, r):
         """-> (statuses, candidates), each uint8 [n_frames][n]; row r is unused (zeros)."""
         n_fr, n = self.n_frames, self.num_landmarks(r)
         st, cd = np.zeros((n_fr, n), np.uint8), np.zeros((n_fr, n), np.uint8)
-        ps = (C.c_void_p * n_fr)(*[st[t].ctypes.data if t != r and n else None for t in range(n_fr)])
-        pc = (C.c_void_p * n_fr)(*[cd[t].ctypes.data if t != r and n else None for t in range(n_fr)])
-        self._ck(self.lib.dpba_get_frame_statuses(self.h, r, n, C.cast(ps, C.c_void_p), C.cast(pc, C.c_void_p)))
+        b_st, b_cd = st.ctypes.data, cd.ctypes.data  # C-contiguous: row t starts n bytes after row t - 1
+        ps = (C.c_void_p * n_fr)(*[b_st + t * n if t != r and n else None for t in range(n_fr)])
+        pc = (C.c_void_p * n_fr)(*[b_cd + t * n if t != r and n else None for t in range(n_fr)])
+        self._ck(self.lib.dpba_get_frame_statuses(self.h, r, n, ps, pc))
         return st, cd
 
     def set_state(self, eps=None, step=None):
