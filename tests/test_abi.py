@@ -49,3 +49,20 @@ def test_product_package_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
                 assert not re.search(r'#include\s+[<"][^>"]*oracle', text), f
+
+
+def test_every_bound_call_declares_its_argument_types():
+    """The bindings pass array addresses as plain integers (capi._ptr): a call without declared argtypes would let ctypes
+    truncate them to a C int.  Every dpba_* / dpa_* call must be in its module's SIGNATURES table, every dpbah_* / dpah_*
+    call in host.py must have an explicit argtypes line."""
+    from dsopp_b200 import pose_alignment
+    pkg = os.path.join(ROOT, "dsopp_b200")
+    for mod, fname in ((capi, "capi.py"), (pose_alignment, "pose_alignment.py")):
+        src = open(os.path.join(pkg, fname)).read()
+        called = set(re.findall(r"lib\.((?:dpa|dpba)_[a-z_0-9]+)\(", src))
+        assert called <= set(mod.SIGNATURES), sorted(called - set(mod.SIGNATURES))
+        assert all(args is not None for _, args in mod.SIGNATURES.values())
+    src = open(os.path.join(pkg, "host.py")).read()
+    called = set(re.findall(r"lib\.((?:dpbah|dpah)_[a-z_0-9]+)\(", src))
+    typed = set(re.findall(r"lib\.((?:dpbah|dpah)_[a-z_0-9]+)\.argtypes", src))
+    assert called - typed <= {"dpbah_last_error", "dpah_last_error"}, sorted(called - typed)
