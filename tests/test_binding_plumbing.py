@@ -90,9 +90,49 @@ SCRIPT = textwrap.dedent('''
     h.set_state(eps * 2, None)             # NULL keeps the other half
     e3, s3 = h.get_state()
     assert np.array_equal(e3, eps * 2) and np.array_equal(s3, step)
-    for _ in range(4):
+    # every other wrapper: the argument conversion must go through (a pointer handed to the wrong kind of parameter raises
+    # ctypes.ArgumentError here instead of on the GPU box)
+    f0 = win.frames[0]
+    n0 = h.num_landmarks(0)
+    h.set_frame_linearization(0, f0.T_w_lin, f0.ab0)
+    h.set_frame_flags(0, True, False)
+    h.set_landmarks(0, f0.uv, f0.idepth, f0.patch, None)
+    h.set_landmarks(0, f0.uv[:3], f0.idepth[:3], f0.patch[:3], f0.flags[:3], append=True)
+    h.set_landmarks(0, f0.uv, f0.idepth, f0.patch, f0.flags)
+    h.set_landmark_flags(0, f0.flags)
+    assert h.get_pose_idepth_blocks(0).shape == (n0, 8 * 4)
+    h.set_statuses(0, 1, win.statuses[(0, 1)])
+    st, cd = h.get_statuses(0, 1)
+    assert st.shape == (n0,) and cd.shape == (n0,)
+    h.first_estimate()
+    assert h.evaluate(20.0) == (0.0, 0)
+    h.evaluate_jacobians(20.0)
+    blk = h.download_residual_block(0, 1)
+    assert blk["J_ref"].shape == (n0, 8, 8)
+    for mat in (False, True):
+        Hp, bp, Hs, bs = h.linearize(20.0, True, True, False, materialized=mat)
+        assert Hp.shape == (32, 32) and bs.shape == (32,)
+    h.back_substitute(np.zeros(32), 1e-5)
+    h.accept(), h.reject(), h.change_residual_statuses(True), h.landmarks_energy(), h.update_point_statuses(1, 20.0)
+    out, act, nv = h.refine_immature_landmarks(0, f0.uv[:5], f0.idepth[:5], f0.patch[:5, 0], 2)
+    assert out.shape == (5,) and act.dtype == bool and nv.shape == (5,)
+    maps = h.create_reference_depth_maps(3, 1e-5)
+    assert [m[0].shape for m in maps] == [(48, 64), (24, 32), (12, 16)]
+    h.solve_lm(20.0)
+    h.solve_lm(20.0, H_marg=np.eye(32), b_marg=np.zeros(32), energy_marg=1.0)
+    h.set_option("cuda_graph", 1)
+    h.profile_enable(True)
+    assert set(h.profile_read()) == set(h.PROFILE_KINDS)
+    h.comm_init(bytes(128), 0, 1)
+    assert len(h.peer_export()) == 64
+    h.peer_attach(bytes(128), 0, 2)
+    gray = np.zeros((48, 64), np.uint8)
+    h.push_frame_raw(9, gray, np.arange(256, dtype=np.float32), None, f0.mask, f0.T_w_lin, 1.0, f0.ab0, f0.intr, False)
+    assert [o.shape for o in h.build_pyramid(gray, np.arange(256, dtype=np.float32), gray, 3)] == [(48, 64, 3), (24, 32, 3), (12, 16, 3)]
+    h.push_frame(10, np.zeros((48, 64), np.float32), f0.mask, f0.T_w_lin, 1.0, f0.ab0, f0.intr, False)   # intensity-only form
+    while h.n_frames:
         h.remove_frame(0)
-    assert h.n_frames == 0
+    assert len(capi.comm_unique_id()) == 128 and capi.launch_count() == 0
     print("PLUMBING OK")
 ''')
 
