@@ -716,3 +716,76 @@ int dpa_solve(dpa_handle* h, const dpa_options* o, const double* prior_rotation,
 
 }  // extern "C"
 #pragma GCC visibility pop
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Mean-square optical flow of the reference landmarks under a relative pose (keyframe decision of the tracker):
+// calculateMeanSquareOpticalFlow, src/tracker/tracker/src/monocular_tracker.cpp:104-133, evaluated by the tracker on
+// level 0 of the reference depth map with the pose the aligner just returned, and once more with the rotation removed
+// (:474-480).  The landmark list compacted by dpa_set_reference_depth_map is exactly the pixel set the reference loops
+// over (4-px border, weight > 0, idepth >= 1e-6), so this is one grid-stride reduction over data that is already
+// resident: fp32 per landmark (optical_flow_body.h), fp64 sums, one (sum, count) pair per CTA added up on the host in
+// CTA order (deterministic).  STATUS: written after the round-1 GPU minutes were spent; the per-landmark body runs on the
+// CPU against the oracle (tests/test_kernel_emulation.py), the kernel itself has not run on hardware yet.
+// ------------------------------------------------------------------------------------------------------------------------
+#include "optical_flow_body.h"
+
+namespace {
+constexpr int OF_THREADS = 256;
+
+__global__ void __launch_bounds__(OF_THREADS) k_optical_flow(const float4* __restrict__ lm, int n, pba::FlowConst c,
+                                                             double2* __restrict__ partial) {
+  double sum = 0.0, cnt = 0.0;
+  for (int i = blockIdx.x * OF_THREADS + threadIdx.x; i < n; i += gridDim.x * OF_THREADS) {
+    float sq;
+    if (pba::flow_term(c, lm[i], sq)) {
+      sum += (double)sq;
+      cnt += 1.0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  __shared__ double2 red[OF_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_double2(sum, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double2 t = red[0];
+    for (int k = 1; k < OF_THREADS / 32; ++k) {
+      t.x += red[k].x;
+      t.y += red[k].y;
+    }
+    partial[blockIdx.x] = t;
+  }
+}
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" int dpa_mean_square_optical_flow(dpa_handle* h, const double T_target_reference[12], double* flow,
+                                            int32_t* n_used) {
+  PREQ(h, "null handle");
+  PREQ(T_target_reference && flow, "null argument");
+  PREQ(h->have_ref, "dpa_set_reference_* first");
+  const pba::FlowConst c = pba::make_flow_const(T_target_reference, h->ref.intr, h->ref.W, h->ref.H);
+  double sum = 0.0, cnt = 0.0;
+  if (h->n > 0) {
+    const int ctas = std::min(2 * pba::sm_count(), (h->n + OF_THREADS - 1) / OF_THREADS);
+    double2* partial = reinterpret_cast<double2*>(h->stage2);  // depth-map accumulators are consumed by now
+    PREQ((size_t)ctas * sizeof(double2) <= (size_t)2 * h->cfg.max_width * h->cfg.max_height * sizeof(float), "staging too small");
+    pba::add_launches(1);
+    k_optical_flow<<<ctas, OF_THREADS, 0, h->stream>>>(h->lm, h->n, c, partial);
+    PCK(cudaGetLastError());
+    std::vector<double2> host(ctas);
+    PCK(cudaMemcpyAsync(host.data(), partial, sizeof(double2) * ctas, cudaMemcpyDeviceToHost, h->stream));
+    PCK(cudaStreamSynchronize(h->stream));
+    for (const double2& p : host) {
+      sum += p.x;
+      cnt += p.y;
+    }
+  }
+  *flow = sqrt(sum / cnt);  // 0 / 0 = NaN when nothing reprojects, as in the reference (:132)
+  if (n_used) *n_used = (int32_t)cnt;
+  return DPBA_SUCCESS;
+}
+#pragma GCC visibility pop

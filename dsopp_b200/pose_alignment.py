@@ -39,6 +39,7 @@ SIGNATURES = {
     "dpa_set_target": (C.c_int, [_P, _P, _P, _P, _D, _P, _P, _I, _I]),
     "dpa_solve": (C.c_int, [_P, C.POINTER(Options), _P, C.POINTER(Result)]),
     "dpa_get_trace": (C.c_int, [_P, _I, _P, _P, _P]),
+    "dpa_mean_square_optical_flow": (C.c_int, [_P, _P, C.POINTER(_D), C.POINTER(C.c_int32)]),
 }
 
 _bound = False
@@ -118,6 +119,13 @@ class Aligner:
         H, W = image.shape[:2]
         self._ck(self.lib.dpa_set_target(self.h, capi._ptr(image), capi._ptr(mask), capi._ptr(T), exposure, capi._ptr(ab),
                                          capi._ptr(it), W, H))
+
+    def mean_square_optical_flow(self, T_target_reference):
+        """calculateMeanSquareOpticalFlow over the resident reference landmarks -> (flow, landmarks used)."""
+        T = capi.pose34(T_target_reference)
+        flow, n = _D(), C.c_int32()
+        self._ck(self.lib.dpa_mean_square_optical_flow(self.h, capi._ptr(T), C.byref(flow), C.byref(n)))
+        return flow.value, n.value
 
     def trace(self):
         e, lam, acc = np.zeros(64), np.zeros(64), np.zeros(64, np.int32)

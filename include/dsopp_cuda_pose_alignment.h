@@ -91,6 +91,12 @@ int dpa_set_target(dpa_handle* h, const float* image_I_dx_dy, const uint8_t* mas
  * (setRotationPrior, :254-258). */
 int dpa_solve(dpa_handle* h, const dpa_options* options, const double* prior_rotation_t_r, dpa_result* result);
 
+/* calculateMeanSquareOpticalFlow (src/tracker/tracker/src/monocular_tracker.cpp:104-133; the tracker's keyframe
+ * decision evaluates it on level 0 with the aligned pose and once more with the rotation set to identity, :474-480)
+ * over the reference landmarks of the last dpa_set_reference_* call: sqrt(mean |unproject(x) - unproject(reproject(x))|^2)
+ * over the landmarks that reproject successfully under T_target_reference (3x4 row-major).  *flow is NaN when none does
+ * (0 / 0 in the reference); *n_used (may be NULL) is their number. */
+int dpa_mean_square_optical_flow(dpa_handle* h, const double T_target_reference[12], double* flow, int32_t* n_used);
 /* Trace of the last dpa_solve: trial energy, regulariser and accept decision of every executed loop body (at most 64).
  * Returns the number of entries written.  Any pointer may be NULL. */
 int dpa_get_trace(dpa_handle* h, int32_t capacity, double* energies, double* lambdas, int32_t* accepted);

@@ -51,6 +51,32 @@ def landmarks_from_depth_map(idepth_sum, weight, image):
     return uv, idepth, patch
 
 
+def mean_square_optical_flow(idepth_sum, weight, T_t_r, intr):
+    """calculateMeanSquareOpticalFlow, src/tracker/tracker/src/monocular_tracker.cpp:104-133 (the keyframe decision's
+    input, evaluated on level 0 of the reference depth map with the pose the aligner returned, :474-480): over the same
+    pixels the depth-map LocalFrame takes (4-px border, weight > 0, idepth >= 1e-6) that reproject successfully,
+    sqrt(mean |unproject(x) - unproject(reprojection)|^2).  Empty set -> NaN (0 / 0), as in the reference."""
+    uv, idepth, _ = landmarks_from_depth_map(idepth_sum, weight, np.zeros(weight.shape + (1,)))
+    Hh, Ww = weight.shape
+    fx, fy, cx, cy = intr
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    Kinv = np.eye(4)
+    Kinv[0, 0], Kinv[1, 1], Kinv[0, 2], Kinv[1, 2] = 1 / fx, 1 / fy, -cx / fx, -cy / fy
+    A = K @ np.asarray(T_t_r, dtype=np.float64)[:3, :4] @ Kinv   # ArrayReprojector::reproject_, camera_reproject.hpp:256
+    p = uv @ A[:, :2].T + A[:, 2] + idepth[:, None] * A[:, 3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = p[:, :2] / p[:, 2:3]
+
+    def roi(q):
+        return (q[:, 0] >= 4) & (q[:, 1] >= 4) & (q[:, 0] <= Ww - 5) & (q[:, 1] <= Hh - 5)
+
+    with np.errstate(invalid="ignore"):
+        ok = (idepth > -1e-4) & (idepth < 1010.0) & roi(uv) & (p[:, 2] > 0) & roi(np.where(np.isfinite(t), t, -1.0))
+    d = (uv[ok] - t[ok]) / np.array([fx, fy])    # rays have z = 1 (pinhole_camera.hpp:137-139): the z difference is 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return float(np.sqrt(np.float64((d * d).sum()) / np.float64(ok.sum()))), int(ok.sum())
+
+
 def mask_valid_checked(mask, pts):
     """CameraMask::valid<true> (bounds checked), sensors/.../mask/camera_mask.hpp:48-66."""
     xi = np.floor(np.abs(pts[..., 0]) + 0.5).astype(np.int64) * np.sign(pts[..., 0]).astype(np.int64)

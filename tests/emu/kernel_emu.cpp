@@ -4,12 +4,14 @@
 // show: anything that depends on real concurrency (atomics order, warp intrinsics) -- that stays with the -m gpu tests.
 //
 // Built by tests/test_kernel_emulation.py:  g++ -O1 -ffp-contract=off -I/usr/local/cuda/include -I dsopp_b200/csrc
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
 
 #include "depth_maps_body.h"
 #include "energy_quantile_body.h"
+#include "optical_flow_body.h"
 
 using namespace pba;
 
@@ -116,6 +118,22 @@ unsigned emu_energy_quantile(int n_frames, int max_pts, const int* n_lm, const i
   }
   *value = st.value;
   return st.count;
+}
+
+// k_optical_flow (pose_alignment.cu): the per-landmark term over all landmarks, fp64 sums; returns the count
+int emu_optical_flow(int n, const float* lm4, const double* T_target_reference, const double* intr, int W, int H,
+                     double* flow) {
+  const FlowConst c = make_flow_const(T_target_reference, intr, W, H);
+  double sum = 0.0, cnt = 0.0;
+  for (int i = 0; i < n; ++i) {
+    float sq;
+    if (flow_term(c, reinterpret_cast<const float4*>(lm4)[i], sq)) {
+      sum += (double)sq;
+      cnt += 1.0;
+    }
+  }
+  *flow = std::sqrt(sum / cnt);
+  return (int)cnt;
 }
 
 }  // extern "C"

@@ -30,7 +30,8 @@ MAXF = 16  # PBA_MAXF
 def emu():
     os.makedirs(OUT, exist_ok=True)
     csrc = os.path.join(ROOT, "dsopp_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in ("depth_maps_body.h", "energy_quantile_body.h", "pba_internal.h")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("depth_maps_body.h", "energy_quantile_body.h", "optical_flow_body.h",
+                                                    "pba_internal.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-Wall",
                                "-I/usr/local/cuda/include", "-I", csrc, "-I", os.path.join(ROOT, "include"),
@@ -42,6 +43,8 @@ def emu():
     lib.emu_reference_depth_maps.argtypes = [C.c_int] * 4 + [C.c_void_p] * 8 + [C.c_int, C.c_float, C.c_void_p]
     lib.emu_energy_quantile.restype = C.c_uint
     lib.emu_energy_quantile.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_double, C.c_void_p]
+    lib.emu_optical_flow.restype = C.c_int
+    lib.emu_optical_flow.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return lib
 
 
@@ -206,6 +209,35 @@ def test_energy_quantile_without_any_eligible_residual(emu):
     count = emu.emu_energy_quantile(3, 32, _p(n_lm), _p(np.arange(3, dtype=np.int32)), _p(np.zeros(3, np.int32)),
                                     _p(flags), _p(status), _p(energy), 0.75, _p(value))
     assert count == 0 and value[0] == 0.0
+
+
+@pytest.mark.parametrize("motion", ["small", "no_rotation", "leaves_the_image", "behind_the_camera"])
+def test_mean_square_optical_flow_on_the_cpu(emu, motion):
+    """calculateMeanSquareOpticalFlow (monocular_tracker.cpp:104-133): the per-landmark body of k_optical_flow and the
+    fp32 reprojection constants over the landmark list the aligner compacts from a depth map, against the oracle."""
+    from oracle import pose_alignment_oracle as PA
+    win = synth.make_window(n_frames=5, points_per_frame=500, seed=11, pose_noise=0.0, idepth_noise=0.0, eps_scale=0.0,
+                            ab_scale=0.0)
+    frames = O.frames_from_window(win)
+    idw, wgt = D.create_reference_depth_maps(frames, 1)[0]
+    uv, idepth, _ = PA.landmarks_from_depth_map(idw, wgt, np.zeros(wgt.shape + (1,)))
+    lm = np.zeros((len(idepth), 4), np.float32)
+    lm[:, :2], lm[:, 2] = uv, idepth
+    xi = {"small": [0.03, -0.02, 0.05, 0.01, -0.015, 0.008], "no_rotation": [0.03, -0.02, 0.05, 0, 0, 0],
+          "leaves_the_image": [1.5, 0.4, 0.0, 0.0, 0.3, 0.0], "behind_the_camera": [0, 0, -30.0, 0, 0, 0]}[motion]
+    T = O.se3_exp(np.array(xi))
+    intr = np.asarray(win.frames[-1].intr, np.float64)
+    ref_flow, ref_n = PA.mean_square_optical_flow(idw, wgt, T, intr)
+    T34 = np.ascontiguousarray(T[:3, :4]).reshape(12)
+    flow = np.zeros(1)
+    n = emu.emu_optical_flow(len(lm), _p(lm), _p(T34), _p(intr), win.width, win.height, _p(flow))
+    assert len(lm) > 5000
+    if motion == "behind_the_camera":
+        assert ref_n == 0 and n == 0 and np.isnan(ref_flow) and np.isnan(flow[0])
+        return
+    assert abs(n - ref_n) <= 3               # landmarks within fp32 rounding of the ROI border
+    assert ref_n > (100 if motion == "leaves_the_image" else 5000)
+    assert abs(flow[0] - ref_flow) <= 2e-4 * ref_flow
 
 
 # ---- NVLink mailbox all-reduce with real threads ---------------------------------------------------------------------

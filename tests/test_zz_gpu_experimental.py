@@ -98,3 +98,29 @@ def test_reference_depth_maps_equal_the_oracle():
     ref = D.create_reference_depth_maps(frames, 4, [f.inv_hdd for f in frames])
     _compare_maps(got, ref, 5e-3)
     h.close()
+
+
+def test_mean_square_optical_flow_equals_the_oracle():
+    """calculateMeanSquareOpticalFlow (monocular_tracker.cpp:104-133) over the aligner's resident landmark list."""
+    from dsopp_b200 import pose_alignment
+    from oracle import depth_map_oracle as D
+    from oracle import pba_oracle as O
+    from oracle import pose_alignment_oracle as PA
+
+    win = synth.make_window(n_frames=5, points_per_frame=500, seed=11, pose_noise=0.0, idepth_noise=0.0, eps_scale=0.0,
+                            ab_scale=0.0)
+    frames = O.frames_from_window(win)
+    idw, wgt = D.create_reference_depth_maps(frames, 1)[0]
+    sf = win.frames[-1]
+    al = pose_alignment.Aligner(idw.size, win.width, win.height)
+    n = al.set_reference_depth_map(sf.image, idw.astype(np.float32), wgt.astype(np.float32), sf.T_w_lin, sf.exposure, sf.ab0,
+                                   sf.intr)
+    assert n > 5000
+    for xi in ([0.03, -0.02, 0.05, 0.01, -0.015, 0.008], [0.03, -0.02, 0.05, 0, 0, 0], [1.5, 0.4, 0.0, 0.0, 0.3, 0.0]):
+        T = O.se3_exp(np.array(xi))
+        ref_flow, ref_n = PA.mean_square_optical_flow(idw, wgt, T, np.asarray(sf.intr, np.float64))
+        flow, used = al.mean_square_optical_flow(T)
+        assert abs(used - ref_n) <= 3 and abs(flow - ref_flow) <= 2e-4 * ref_flow
+    flow, used = al.mean_square_optical_flow(O.se3_exp(np.array([0, 0, -30.0, 0, 0, 0])))
+    assert used == 0 and np.isnan(flow)
+    al.close()
