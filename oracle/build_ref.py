@@ -8,6 +8,7 @@ supplies that one name):
 
   src/features/src/calculate_pixelinfo.cpp                    -> ref_pixelinfo_f64 / ref_pixelinfo_f32
   .../levenberg_marquardt_algorithm/levenberg_marquardt_algorithm.hpp (header-only template) -> ref_lm_solve
+  src/common/pattern/include/common/pattern/pattern.hpp (constants; needs only the NAME Eigen::Matrix)  -> ref_pattern
 
 They are compiled WHERE THEY LIE under /root/reference (never copied), together with oracle/ref_shims/ref_parts.cpp, into
 oracle/_ref/libdsopp_ref_parts.so (git-ignored, travels to the GPU box with the snapshot).  /root/reference does not
@@ -25,7 +26,8 @@ SHIM = os.path.join(HERE, "ref_shims", "ref_parts.cpp")
 REF_SOURCES = [os.path.join(REF, "src/features/src/calculate_pixelinfo.cpp")]
 REF_HEADERS = [os.path.join(REF, "src/energy/problems/include/energy/levenberg_marquardt_algorithm/levenberg_marquardt_algorithm.hpp"),
                os.path.join(REF, "src/common/include/common/settings.hpp"),
-               os.path.join(REF, "src/features/internal/features/camera/calculate_pixelinfo.hpp")]
+               os.path.join(REF, "src/features/internal/features/camera/calculate_pixelinfo.hpp"),
+               os.path.join(REF, "src/common/pattern/include/common/pattern/pattern.hpp")]
 
 
 def available():
@@ -37,7 +39,8 @@ def build():
     have_ref = all(os.path.exists(p) for p in REF_SOURCES + REF_HEADERS)
     if not have_ref:
         return LIB if os.path.exists(LIB) else None
-    deps = REF_SOURCES + REF_HEADERS + [SHIM, os.path.join(HERE, "ref_stubs", "Eigen", "Core")]
+    deps = REF_SOURCES + REF_HEADERS + [SHIM, os.path.join(HERE, "ref_stubs", "Eigen", "Core"),
+                                        os.path.join(HERE, "ref_stubs", "Eigen", "Dense")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(OUT, exist_ok=True)
@@ -46,6 +49,7 @@ def build():
     cmd = ["g++", "-std=c++20", "-O3", "-march=x86-64-v3", "-fPIC", "-shared",
            "-I", os.path.join(HERE, "ref_stubs"),
            "-I", os.path.join(REF, "src/common/include"),
+           "-I", os.path.join(REF, "src/common/pattern/include"),
            "-I", os.path.join(REF, "src/features/internal"),
            "-I", os.path.join(REF, "src/energy/problems/include"),
            "-o", LIB, SHIM] + REF_SOURCES

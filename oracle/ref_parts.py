@@ -31,6 +31,17 @@ def load():
     return _lib
 
 
+def pattern():
+    """dsopp::Pattern -> ((8, 2) offsets (x_i, y_i), centre index)."""
+    lib = load()
+    xy = np.zeros(16)
+    c = C.c_int()
+    lib.ref_pattern.restype = C.c_int
+    lib.ref_pattern.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    n = lib.ref_pattern(xy.ctypes.data, C.byref(c))
+    return xy.reshape(n, 2), c.value
+
+
 def _aligned(shape, dtype, align=32, offset=0):
     """Array whose data pointer is `offset` bytes past a multiple of `align` (the reference picks its AVX2 path by
     alignment, calculate_pixelinfo.cpp:386-392)."""

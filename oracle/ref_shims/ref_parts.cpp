@@ -5,6 +5,7 @@
 //                                                                 gradient definition, AVX2 and plain-C paths)
 //   src/energy/problems/include/energy/levenberg_marquardt_algorithm/levenberg_marquardt_algorithm.hpp
 //                                                                 levenberg_marquardt_algorithm::solve (row a17)
+//   src/common/pattern/include/common/pattern/pattern.hpp         the 8-pixel residual pattern (constants only)
 //
 // The reference sources are NOT copied: oracle/build_ref.py compiles them where they lie under /root/reference and this
 // file only declares / instantiates what it calls.  The LM driver is a template over a problem type; here it is
@@ -14,6 +15,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "common/pattern/pattern.hpp"
 #include "energy/levenberg_marquardt_algorithm/levenberg_marquardt_algorithm.hpp"
 #include "features/camera/calculate_pixelinfo.hpp"
 
@@ -57,6 +59,13 @@ struct ScriptedProblem {
 }  // namespace
 
 extern "C" {
+
+// dsopp::Pattern (src/common/pattern/include/common/pattern/pattern.hpp:17-34): size, centre index, (x_i, y_i) offsets
+int ref_pattern(double* xy16, int* center) {
+  for (int i = 0; i < 2 * dsopp::Pattern::kSize; ++i) xy16[i] = static_cast<double>(dsopp::Pattern::pattern_data[i]);
+  *center = dsopp::Pattern::kCenter;
+  return dsopp::Pattern::kSize;
+}
 
 void ref_pixelinfo_f64(const double* in, double* out, int width, int height) {
   dsopp::features::calculate_pixelinfo<1>(in, out, width, height);

@@ -133,6 +133,26 @@ def test_production_options_follow_the_reference():
         assert R.lm_solve(e, [9] * 7, [[1.0, 1.0]], 7, 1e-5, 1e-8, 1e-8, True, 3, 1.0, 1.0)[0] == calls
 
 
+# ---- residual pattern ---------------------------------------------------------------------------------------------
+def test_pattern_tables_equal_the_reference():
+    """dsopp::Pattern (common/pattern/pattern.hpp:17-34): the oracle's table, the generator's table and the two
+    nibble-packed constants the CUDA kernels decode (pat_x / pat_y in pba_kernels.cu) are the reference's 8 offsets in
+    the reference's order (the order is what quirk Q1 and the FEJ rows depend on)."""
+    import re
+    ref = GOLDEN["pattern_xy"]
+    assert ref.shape == (8, 2) and int(GOLDEN["pattern_center"]) == 4 and np.all(ref[4] == 0)
+    if R.available():
+        live, center = R.pattern()
+        assert np.array_equal(live, ref) and center == 4
+    assert np.array_equal(O.PATTERN, ref) and np.array_equal(synth.PATTERN, ref)
+    src = open(os.path.join(os.path.dirname(__file__), "..", "dsopp_b200", "csrc", "pba_kernels.cu")).read()
+    for name, col in (("pat_x", 0), ("pat_y", 1)):
+        m = re.search(name + r"\(int i\) \{ return \(float\)\(\((0x[0-9a-fA-F]+)u >> \(4 \* i\)\) & 15u\) - 2\.f; \}", src)
+        assert m, name
+        packed = int(m.group(1), 16)
+        assert [((packed >> (4 * i)) & 15) - 2 for i in range(8)] == list(ref[:, col].astype(int)), name
+
+
 # ---- gradient definition -----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["a", "b", "c", "d", "e"])
 def test_pixelinfo_restatements_equal_the_reference_golden(name):

@@ -57,6 +57,8 @@ def main():
         out[f"px_{name}_f32"] = R.pixelinfo(I.astype(np.float32), aligned=False)
         if W % 8 == 0:                                                          # AVX2 path (double, aligned, width % 8 == 0)
             assert np.array_equal(out[f"px_{name}_f64"], R.pixelinfo(I, aligned=True))
+    pat, center = R.pattern()
+    out["pattern_xy"], out["pattern_center"] = pat, np.array(center)
     cases = lm_cases()
     out["lm_n"] = np.array(len(cases))
     for i, (e, v, nr, o) in enumerate(cases):
