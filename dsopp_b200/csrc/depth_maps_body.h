@@ -42,7 +42,12 @@ __host__ __device__ inline void dm_splat_thread(const WindowDev& w, float const_
   const size_t res = ((size_t)(w.phys[r] * PBA_MAXF + w.phys[t])) * w.max_pts + l;
   if (w.status[res] != DM_K_OK) return;                                                     // :38
   const float4 lm = w.lmk[gl];
-  const float u = lm.x, v = lm.y, rho = lm.z;
+  const float u = lm.x, v = lm.y;
+  float rho = lm.z;
+  // the reference splats the TRACK's landmarks, i.e. the solver's after updateFrame's post-processing
+  // (photometric_bundle_adjustment.cpp:232-238): |idepth| < 1e-8 becomes 0, any other negative idepth marks an outlier
+  if (fabsf(rho) < 1e-8f) rho = 0.f;
+  else if (rho < 0.f) return;
   const float xmax = (float)(w.W - 5), ymax = (float)(w.H - 5);
   if (!(rho > -1e-4f && rho < 1010.f)) return;                                              // validIdepth
   if (!(u >= 4.f && v >= 4.f && u <= xmax && v <= ymax)) return;                            // insideCameraROI(reference)

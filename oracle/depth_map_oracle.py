@@ -51,6 +51,12 @@ def fill_fine_depth_map(frames, idepth_variance=None):
             if ref.lm_outlier[l] or ref.lm_marginalized[l]:
                 continue
             rho = ref.idepth[l]
+            # the reference reads the TRACK's landmarks: the solver's after updateFrame's post-processing
+            # (photometric_bundle_adjustment.cpp:232-238) -- |idepth| < 1e-8 -> 0, other negative idepths -> outlier
+            if abs(rho) < 1e-8:
+                rho = 0.0
+            elif rho < 0:
+                continue
             uv = ref.uv[l]
             # scalar reproject, camera_reproject.hpp:270-293 (one point: ROI of that point only)
             ok = bool(O.valid_idepth(rho)) and _in_roi(uv, ref.W, ref.H)

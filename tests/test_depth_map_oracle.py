@@ -79,6 +79,23 @@ def test_splatted_inverse_depth_is_the_scene_seen_from_the_newest_keyframe():
     assert xs.min() >= 4 and ys.min() >= 4 and xs.max() <= win.width - 5 and ys.max() <= win.height - 5
 
 
+def test_track_post_processing_of_inverse_depths():
+    """updateFrame (photometric_bundle_adjustment.cpp:232-238) stands between the solver and the track the depth maps read:
+    negative inverse depths are outliers there, tiny ones are zero."""
+    win, frames = exact_window(n_frames=3, pts=60, seed=7)
+    base = D.fill_fine_depth_map(frames)[1].sum()
+    frames[0].lm_outlier[:10] = True
+    without = D.fill_fine_depth_map(frames)[1].sum()       # the map without the first ten landmarks of frame 0
+    frames[0].lm_outlier[:10] = False
+    assert without < base
+    frames[0].idepth[:10] = -0.02
+    assert np.isclose(D.fill_fine_depth_map(frames)[1].sum(), without)   # negative: outliers in the track, not splatted
+    frames[0].idepth[:10] = 5e-9
+    idw, wgt = D.fill_fine_depth_map(frames)
+    assert wgt.sum() > without                  # tiny: they count again (where the reprojection stays in the image) ...
+    assert np.all(idw >= 0)                     # ... with inverse depth exactly 0
+
+
 def test_uncertainty_weights():
     win, frames = exact_window(n_frames=3, pts=100, seed=4)
     var = [np.full(len(f.idepth), 1e-5) for f in frames]

@@ -126,6 +126,8 @@ def test_depth_map_kernels_on_the_cpu(emu, phys):
     win.frames[1].flags[::7] |= synth.FLAG_OUTLIER
     win.frames[0].flags[::9] |= synth.FLAG_MARGINALIZED
     win.statuses[(2, 4)][::5] = 1  # kOutlier towards the newest keyframe
+    win.frames[3].idepth[::11] = -0.01     # negative inverse depth: an outlier in the track (updateFrame), not splatted
+    win.frames[3].idepth[1::11] = 3e-9     # below kIdepthEps: splatted as idepth 0
     frames = O.frames_from_window(win)
     O.first_estimate_jacobians(frames)
     O.Problem(frames, 20.0).linearize()  # inv_hdd per landmark
