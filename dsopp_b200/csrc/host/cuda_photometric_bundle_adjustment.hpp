@@ -243,6 +243,30 @@ class CudaPhotometricBundleAdjustment {
     if (n) dpba_check(h_, dpba_get_frame_statuses(h_, slot, n, rows, nullptr));  // one synchronisation per frame
   }
 
+  // createReferenceDepthMaps (src/tracker/tracker/src/create_depth_maps.cpp:122-146), which the tracker calls right after
+  // solve / updateSolver (monocular_tracker.cpp:465,509): built on the device from the window this solver holds.
+  // Level l: (height >> l) x (width >> l), row-major [y][x] = the reference's map(x, y); `idepth` is the weighted SUM.
+  struct DepthMapLevel {
+    int width = 0, height = 0;
+    std::vector<float> idepth, weight;
+  };
+  std::vector<DepthMapLevel> createReferenceDepthMaps(int width, int height, int levels) {
+    std::vector<DepthMapLevel> maps(levels);
+    std::vector<float*> pi(levels), pw(levels);
+    for (int l = 0; l < levels; ++l) {
+      maps[l].width = width >> l;
+      maps[l].height = height >> l;
+      maps[l].idepth.assign((size_t)maps[l].width * maps[l].height, 0.f);
+      maps[l].weight.assign((size_t)maps[l].width * maps[l].height, 0.f);
+      pi[l] = maps[l].idepth.data();
+      pw[l] = maps[l].weight.data();
+    }
+    // idepthVariance of the track: inv_hessian_idepth_idepth with uncertainty estimation, else the constant 1e-5
+    // (photometric_bundle_adjustment.cpp:252-254)
+    dpba_check(h_, dpba_create_reference_depth_maps(h_, levels, estimate_uncertainty_ ? -1.0 : 1e-5, pi.data(), pw.data()));
+    return maps;
+  }
+
  private:
   int slotOf(long long timestamp) const {
     for (size_t i = 0; i < frames_.size(); ++i)

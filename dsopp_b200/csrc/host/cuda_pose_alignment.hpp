@@ -131,6 +131,15 @@ class CudaPoseAlignment {
   const double* tTargetReferenceCovariance() const { return covariance_; }  // 6x6 row-major
   const dpa_result& lastResult() const { return last_; }
 
+  // calculateMeanSquareOpticalFlow (src/tracker/tracker/src/monocular_tracker.cpp:104-133) over the reference landmarks
+  // of the last pushed reference frame; the tracker evaluates it with the aligned t_t_r and once more with the rotation
+  // set to identity (:474-480).  NaN when no landmark reprojects (0 / 0 in the reference).
+  double meanSquareOpticalFlow(const double t_target_reference[12]) const {
+    double flow = 0;
+    check(dpa_mean_square_optical_flow(h_, t_target_reference, &flow, nullptr));
+    return flow;
+  }
+
  private:
   void check(int rc) const {
     if (rc < 0) throw std::runtime_error(std::string("pose alignment: ") + dpa_last_error(h_));
