@@ -253,14 +253,13 @@ class Handle:
 
     def get_landmarks(self, slot):
         n = self.num_landmarks(slot)
-        out = dict(
-            idepth=np.zeros(n, np.float32), idepth_step=np.zeros(n, np.float32), inv_hdd=np.zeros(n, np.float32),
-            b_d=np.zeros(n, np.float32), flags=np.zeros(n, np.uint8), n_inliers=np.zeros(n, np.uint32),
-            rel_baseline=np.zeros(n, np.float32))
-        self._ck(self.lib.dpba_get_landmarks(self.h, slot, n, _ptr(out["idepth"]), _ptr(out["idepth_step"]),
-                                             _ptr(out["inv_hdd"]), _ptr(out["b_d"]), _ptr(out["flags"]),
-                                             _ptr(out["n_inliers"]), _ptr(out["rel_baseline"])))
-        return out
+        f32 = np.zeros((5, n), np.float32)  # one block, five contiguous rows: one address lookup instead of five
+        flags, n_inl = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+        b, row = f32.ctypes.data, 4 * n
+        self._ck(self.lib.dpba_get_landmarks(self.h, slot, n, b, b + row, b + 2 * row, b + 3 * row, _ptr(flags),
+                                             _ptr(n_inl), b + 4 * row))
+        return dict(idepth=f32[0], idepth_step=f32[1], inv_hdd=f32[2], b_d=f32[3], flags=flags, n_inliers=n_inl,
+                    rel_baseline=f32[4])
 
     def get_pose_idepth_blocks(self, slot):
         n = self.num_landmarks(slot)
