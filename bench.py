@@ -135,10 +135,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cpu_ref
-    win = build_window(1)
     cores = os.cpu_count() or 1
     threads = cores
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the restatement asks for its thread count per parallel region
+    # (num_threads clause), which overrides that, but the OpenMP runtime must not have been capped at load time either
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    from oracle import cpu_ref
+    win = build_window(1)
     cw = cpu_ref.CpuWindow(win, use_float=False, threads=threads, native=True)
     cw.first_estimate()
     units = win.units
