@@ -176,14 +176,17 @@ def _time_cpu_window(cwin, use_float, threads, budget_s, max_iters):
     cw = cpu_ref.CpuWindow(cwin, use_float=use_float, threads=threads, native=True)
     cw.first_estimate()
     ts, t_begin = [], time.perf_counter()
-    for i in range(2 + max_iters):
-        _, tm, _ = cw.gn_iteration(SIGMA, True, 1e-5, AB_REG, FIXED_REG)
+    first_step = None
+    for i in range(max(2, GN_ITERS) + max_iters):
+        e, tm, _ = cw.gn_iteration(SIGMA, True, 1e-5, AB_REG, FIXED_REG)
+        if i == GN_ITERS - 1:  # the first GN_ITERS iterations from the fresh window ARE one bench step: keep its result
+            first_step = {"energy": float(e), "eps": cw.get_state()[0].copy()}
         if i >= 2:
             ts.append(tm.copy())
-        if time.perf_counter() - t_begin > budget_s and len(ts) >= 3:
+        if time.perf_counter() - t_begin > budget_s and len(ts) >= 3 and first_step is not None:
             break
     cw.close()
-    return np.median(np.array(ts), axis=0), len(ts)
+    return np.median(np.array(ts), axis=0), len(ts), first_step
 
 
 def cpu_baseline_leg():
@@ -194,17 +197,17 @@ def cpu_baseline_leg():
         from dsopp_b200 import synth
         cwin = synth.make_window(n_frames=N_FRAMES, points_per_frame=PTS_PER_GPU, seed=0, ab_scale=0.0)
         threads = max(1, min(os.cpu_count() or 1, 8) - 1)
-        med, n = _time_cpu_window(cwin, False, threads, 20.0, 40)
+        med, n, first_step = _time_cpu_window(cwin, False, threads, 20.0, 40)
         cpu = {"value": cwin.units / med[5], "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{n} GN iterations of the same {cwin.units}-unit window, double precision, "
                          f"reference three-pass dataflow (oracle/cpu_ref, -O3 -march=native), median",
                "phase_ms": {"sweep_K1": 1e3 * med[0], "posepose_K3": 1e3 * med[1], "schur_K4": 1e3 * med[2],
                             "solve_K5": 1e3 * med[3], "energy_K2": 1e3 * med[4], "iteration": 1e3 * med[5]},
-               "host_cores_total": os.cpu_count()}
+               "host_cores_total": os.cpu_count(), "_first_step": first_step}
         variants = {}
         for name, use_float, th in (("float_%dthreads" % threads, True, threads), ("double_1thread", False, 1)):
             try:
-                m, k = _time_cpu_window(cwin, use_float, th, 6.0, 12)
+                m, k, _ = _time_cpu_window(cwin, use_float, th, 6.0, 12)
                 variants[name] = {"value": cwin.units / m[5], "cores": th, "iterations": k, "iteration_ms": 1e3 * m[5]}
             except Exception as ex:
                 variants[name] = {"value": None, "error": str(ex)}
@@ -301,16 +304,18 @@ def run_ours(args):
 
     # ---- value: resident window (per-kernel event profiling OFF: the graph holds kernels only) ------------------
     sampler = ClockSampler(local)
-    step_ms, launches, iters_seen = [], 0, []
+    step_ms, launches, solved = [], 0, []
     for i in range(args.warmup + args.steps):
         reset_resident()
         if i == args.warmup:
             sampler.start()
-        ms, nl = timed(lambda: iters_seen.append(solve()[1]))
+        ms, nl = timed(lambda: solved.append(solve()))
         if i >= args.warmup:
             step_ms.append(ms)
             launches += nl
+    iters_seen = [r_[1] for r_ in solved]
     assert all(it == GN_ITERS for it in iters_seen), iters_seen
+    energy_dev, eps_dev = float(solved[-1][0]), h.get_state()[0].copy()
     t_local = sum(step_ms)
     t = torch.tensor([t_local], dtype=torch.float64, device=dev)
     if world > 1:
@@ -328,101 +333,61 @@ def run_ours(args):
     prof = h.profile_read()
     h.profile_enable(False)
 
-    # ---- e2e: host buffers in, results out, every step ------------------------------------------------
+    # ---- e2e: host buffers in, results out, every step, through ONE C++ call (dpbah_solve_window) ------------------
     keep = []
+
+    def pinned(a):
+        x, t_ = pin(a)
+        keep.append(t_)
+        return x
+
+    def pinned_alloc(shape, dtype):
+        return pinned(np.zeros(shape, dtype))
+
     host_frames = []
     for i, f in enumerate(win.frames):
-        img, t1 = pin(f.image.astype(np.float32))
-        msk, t2 = pin(f.mask)
-        s = shard[i]
-        uv, t3 = pin(f.uv[s].astype(np.float32))
-        idp, t4 = pin(f.idepth[s].astype(np.float32))
-        pat, t5 = pin(f.patch[s].astype(np.float32))
-        flg, t6 = pin(f.flags[s])
-        keep += [t1, t2, t3, t4, t5, t6]
-        host_frames.append((f, img, msk, uv, idp, pat, flg))
-    host_status = []
-    for r in range(n):
-        rows = {}
-        for tt in range(n):
-            if tt != r:
-                a, tk = pin(win.statuses[(r, tt)][shard[r]])
-                keep.append(tk)
-                rows[tt] = a
-        host_status.append(rows)
-    h2d = sum(x[1].nbytes + x[2].nbytes + x[3].nbytes + x[4].nbytes + x[5].nbytes + x[6].nbytes for x in host_frames)
-    h2d += sum(v.nbytes for rows in host_status for v in rows.values()) + eps0.nbytes * 2
-    d2h_box = [0]
+        s_ = shard[i]
+        host_frames.append(dict(frame_id=f.frame_id, image=pinned(f.image.astype(np.float32)), mask=pinned(f.mask),
+                                T_w_lin=f.T_w_lin, exposure=f.exposure, ab0=f.ab0, intr=f.intr, fixed=f.fixed,
+                                uv=pinned(f.uv[s_].astype(np.float32)), idepth=pinned(f.idepth[s_].astype(np.float32)),
+                                patch=pinned(f.patch[s_].astype(np.float32)), flags=pinned(f.flags[s_])))
+    host_status = {(r, tt): pinned(win.statuses[(r, tt)][shard[r]]) for r in range(n) for tt in range(n) if tt != r}
+    lm_kw = dict(sigma=SIGMA, ab_reg=AB_REG, fixed_reg=FIXED_REG, max_it=GN_ITERS, min_it=GN_ITERS, ftol=0.0, ptol=0.0,
+                 force_accept=True, lambda0=1e-5)
+    step_io = host.WindowStep(h, host_frames, host_status, eps0, alloc=pinned_alloc, **lm_kw)
+    raw_frames = [pinned(np.clip(np.rint(f.image[..., 0]), 0, 255).astype(np.uint8)) for f in win.frames]
+    step_raw = host.WindowStep(h, host_frames, host_status, eps0, alloc=pinned_alloc, raw_gray=raw_frames,
+                               photometric_lut=np.arange(256, dtype=np.float32), **lm_kw)
 
-    def e2e_step():
-        # the whole window goes host -> device every step (the tracker uploads ONE new keyframe per solve)
-        for _ in range(h.n_frames):
-            h.remove_frame(0)
-        for (f, img, msk, uv, idp, pat, flg) in host_frames:
-            h.push_frame(f.frame_id, img, msk, f.T_w_lin, f.exposure, f.ab0, f.intr, f.fixed)
-        for i, (f, img, msk, uv, idp, pat, flg) in enumerate(host_frames):
-            h.set_landmarks(i, uv, idp, pat, flg)
-            h.set_frame_statuses(i, host_status[i])
-        h.set_state(eps0, np.zeros_like(eps0))
-        solve()
-        nbytes = 0
-        eps, step = h.get_state()
-        nbytes += eps.nbytes + step.nbytes
-        for i in range(n):
-            lm = h.get_landmarks(i)
-            nbytes += sum(v.nbytes for v in lm.values())
-            st, cd = h.get_frame_statuses(i)
-            nbytes += (st.nbytes + cd.nbytes) * (n - 1) // n
-        # what actually crosses PCIe: the first getter after the solve mirrors ALL landmark arrays and status rows of
-        # the handle in one bulk readback (5 floats + float4 + flag per landmark slot, 2 x 16 status rows per frame slot)
-        mpp, nfr = max(len(s_) for s_ in shard), n
-        d2h_box[0] = max(nbytes, nfr * mpp * (5 * 4 + 16 + 1) + 2 * nfr * 16 * mpp + 2 * eps.nbytes)
+    def time_e2e(io, steps, warm):
+        out_ms = []
+        for i in range(warm + steps):
+            ms, _ = timed(io.run)
+            if i >= warm:
+                out_ms.append(ms)
+        t_ = torch.tensor([sum(out_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item()) / steps
 
-    e2e_ms = []
-    for i in range(args.warmup + args.steps):
-        ms, _ = timed(e2e_step)
-        if i >= args.warmup:
-            e2e_ms.append(ms)
-
+    e2e_ms_per_step = time_e2e(step_io, args.steps, args.warmup)
+    e2e_value = units_global * GN_ITERS / (e2e_ms_per_step * 1e-3)
+    e2e_energy, e2e_iters = step_io.io.energy, step_io.io.iterations
+    h2d = int(step_io.io.h2d_bytes)
+    # what actually crosses PCIe on the way back: the first getter after the solve mirrors ALL landmark arrays and status
+    # rows of the handle in one bulk readback (5 floats + float4 + flag per landmark slot, 2 x 16 status rows per frame
+    # slot); the arrays handed to the caller are a subset of it
+    mpp = max(len(s_) for s_ in shard)
+    d2h = max(int(step_io.io.d2h_bytes), n * mpp * (5 * 4 + 16 + 1) + 2 * n * 16 * mpp + 2 * 8 * n * 8)
     # the same step fed with RAW 8-bit frames (dpba_push_frame_raw: photometric table + gradients on the device,
-    # SURVEY 8f-4) -- informational; `e2e` above stays the {I,dx,dy} upload the reference's pushFrame receives
-    raw_frames = [pin(np.clip(np.rint(f.image[..., 0]), 0, 255).astype(np.uint8)) for f in win.frames]
-    keep += [x[1] for x in raw_frames]
-    lut = np.arange(256, dtype=np.float32)
-
-    def e2e_raw_step():
-        for _ in range(h.n_frames):
-            h.remove_frame(0)
-        for (f, img, msk, uv, idp, pat, flg), (g, _) in zip(host_frames, raw_frames):
-            h.push_frame_raw(f.frame_id, g, lut, None, msk, f.T_w_lin, f.exposure, f.ab0, f.intr, f.fixed)
-        for i, (f, img, msk, uv, idp, pat, flg) in enumerate(host_frames):
-            h.set_landmarks(i, uv, idp, pat, flg)
-            h.set_frame_statuses(i, host_status[i])
-        h.set_state(eps0, np.zeros_like(eps0))
-        solve()
-        h.get_state()
-        for i in range(n):
-            h.get_landmarks(i)
-            h.get_frame_statuses(i)
-
-    e2e_raw_ms = []
-    for i in range(3 + min(args.steps, 10)):
-        ms, _ = timed(e2e_raw_step)
-        if i >= 3:
-            e2e_raw_ms.append(ms)
-    t_raw = torch.tensor([sum(e2e_raw_ms) / len(e2e_raw_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_raw, op=dist.ReduceOp.MAX)
-    e2e_raw_value = units_global * GN_ITERS / (float(t_raw.item()) * 1e-3)
-    # leave the handle with the float window for the sweeps timed below
-    e2e_step()
+    # SURVEY 8f-4) -- informational; `e2e` stays the {I,dx,dy} upload the reference's pushFrame receives
+    e2e_raw_ms = time_e2e(step_raw, min(args.steps, 10), 3)
+    e2e_raw_value = units_global * GN_ITERS / (e2e_raw_ms * 1e-3)
+    h2d_raw = int(step_raw.io.h2d_bytes)
+    step_io.run()  # leave the handle with the float window for the sweeps timed below
     # clocks / throttle reasons were sampled from the first timed `value` step to the last timed e2e step (the timed
     # `value` region alone lasts ~20 ms, less than one nvidia-smi sampling period)
     clocks = sampler.stop()
-    t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = units_global * GN_ITERS * args.steps / (float(t.item()) * 1e-3)
 
     # ---- materialising sweep (K1, reference-surface mode) timed alone with an L2 flush before each launch --------
     def time_sweep(hh):
@@ -471,13 +436,18 @@ def run_ours(args):
             del win4
 
     def teardown():
-        # every rank reaches this point with its work finished; after a last barrier the processes leave through
-        # os._exit (main()), so that no NCCL / CUDA destructor of any library can block a rank at exit
+        # ordered shutdown, then a normal interpreter exit: the handle first (dpba_destroy destroys the captured LM graph
+        # BEFORE its NCCL communicator -- a graph that still references the communicator's kernels is what used to block
+        # the exit), then torch's process group.  All ranks have finished their work when they get here.
         sys.stdout.flush()
+        torch.cuda.synchronize()
         if world > 1:
-            torch.cuda.synchronize()
             dist.barrier()
-            torch.cuda.synchronize()
+        h.close()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
 
     if rank != 0:
         teardown()
@@ -529,6 +499,22 @@ def run_ours(args):
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------------------
     cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu else None
+    # the timed step against the CPU restatement (double) of the same step: 7 forced GN iterations from the same window.
+    # Tolerances as in tests/test_gpu_baseline_sizes.py (fp32 device arithmetic vs float64): energy 2e-5 relative, pose
+    # increments / affine gain 2e-5 absolute, affine offset 1e-4 (intensities 0..255 in fp32)
+    parity_check = None
+    if cpu and cpu.get("_first_step"):
+        fs = cpu.pop("_first_step")
+        d = np.abs(eps_dev - fs["eps"]).reshape(n, 8)
+        rel_e = abs(energy_dev - fs["energy"]) / abs(fs["energy"])
+        rel_e2e = abs(e2e_energy - fs["energy"]) / abs(fs["energy"])
+        parity_check = {"against": "oracle/cpu_ref double, same window, same 7 forced GN iterations",
+                        "energy_device": energy_dev, "energy_e2e_call": e2e_energy, "energy_cpu_ref": fs["energy"],
+                        "energy_rel_diff": rel_e, "energy_rel_diff_e2e": rel_e2e,
+                        "state_max_abs_diff_pose_and_a": float(d[:, :7].max()), "state_max_abs_diff_b": float(d[:, 7].max()),
+                        "ok": bool(rel_e <= 2e-5 and rel_e2e <= 2e-5 and d[:, :7].max() <= 2e-5 and d[:, 7].max() <= 1e-4)}
+    elif cpu:
+        cpu.pop("_first_step", None)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -537,17 +523,18 @@ def run_ours(args):
         "config": config_dict(world, {"exchange": "NVLink mailbox all-reduce (peer_exchange.cu)" if args.peer_exchange and world > 1
                                       else ("ncclAllReduce of the packed system, one per GN iteration" if world > 1 else "none")}),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_box[0]),
-                "ms_per_step": sum(e2e_ms) / len(e2e_ms),
-                "path": "dpba_remove_frame/push_frame/set_landmarks/set_frame_statuses/set_state from pinned host buffers, "
-                        "dpba_first_estimate + dpba_solve_lm, dpba_get_* readback"},
-        "e2e_raw_frames": {"value": e2e_raw_value, "unit": UNIT, "ms_per_step": float(t_raw.item()),
-                           "h2d_bytes_per_step": int(h2d - sum(x[1].nbytes for x in host_frames) + sum(x[0].nbytes for x in raw_frames)),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms_per_step,
+                "path": "dpbah_solve_window (C++ host library, one call per step): dpba_remove_frame / push_frame / "
+                        "set_landmarks / set_frame_statuses / set_state from pinned host buffers, dpba_first_estimate + "
+                        "dpba_solve_lm, dpba_get_state / get_landmarks / get_frame_statuses into host arrays"},
+        "e2e_raw_frames": {"value": e2e_raw_value, "unit": UNIT, "ms_per_step": e2e_raw_ms, "h2d_bytes_per_step": h2d_raw,
                            "path": "as e2e, but dpba_push_frame_raw: 8-bit frames in, photometric table + {I,dx,dy} on the device"},
         "gpu_launches": int(launches),
         "roofline": roofline, "roofline_sweep": roofline_sweep, "roofline_sweep_big": roofline_sweep_big,
         "kernel_ms": kernel_ms,
         "cpu_baseline": cpu,
+        "parity_check": parity_check,
         "us_per_gn_iter": 1e3 * total_ms / args.steps / GN_ITERS,
     }
     print(json.dumps(out), flush=True)
@@ -576,7 +563,6 @@ def main():
         run_ours(args)
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)  # skip interpreter finalisation (CUDA / NCCL destructors of other libraries may block at exit)
 
 
 if __name__ == "__main__":

@@ -89,6 +89,7 @@ SIGNATURES = {
     "dpba_num_frames": (C.c_int, [_P]),
     "dpba_set_frame_linearization": (C.c_int, [_P, _I, _P, _P]),
     "dpba_set_frame_flags": (C.c_int, [_P, _I, _I, _I]),
+    "dpba_set_frame_marginalized": (C.c_int, [_P, _I, _I]),
     "dpba_set_landmarks": (C.c_int, [_P, _I, _I, _P, _P, _P, _P]),
     "dpba_append_landmarks": (C.c_int, [_P, _I, _I, _P, _P, _P, _P]),
     "dpba_set_landmark_flags": (C.c_int, [_P, _I, _I, _P]),
@@ -97,6 +98,8 @@ SIGNATURES = {
     "dpba_get_pose_idepth_blocks": (C.c_int, [_P, _I, _I, _P]),
     "dpba_set_statuses": (C.c_int, [_P, _I, _I, _I, _P]),
     "dpba_get_statuses": (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    "dpba_append_statuses": (C.c_int, [_P, _I, _I, _I, _I, _P]),
+    "dpba_get_residual_scalars": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dpba_set_frame_statuses": (C.c_int, [_P, _I, _I, _P]),
     "dpba_get_frame_statuses": (C.c_int, [_P, _I, _I, _P, _P]),
     "dpba_set_state": (C.c_int, [_P, _P, _P]),
@@ -271,11 +274,25 @@ class Handle:
         st = _u8(statuses)
         self._ck(self.lib.dpba_set_statuses(self.h, r, t, len(st), _ptr(st)))
 
+    def append_statuses(self, r, t, first, statuses):
+        st = _u8(statuses)
+        self._ck(self.lib.dpba_append_statuses(self.h, r, t, int(first), len(st), _ptr(st)))
+
+    def set_frame_marginalized(self, slot, is_marginalized):
+        self._ck(self.lib.dpba_set_frame_marginalized(self.h, slot, int(is_marginalized)))
+
     def get_statuses(self, r, t):
         n = self.num_landmarks(r)
         st, cand = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
         self._ck(self.lib.dpba_get_statuses(self.h, r, t, n, _ptr(st), _ptr(cand)))
         return st, cand
+
+    def get_residual_scalars(self, r, t):
+        """-> (energy float32[n], reprojection_jacobians_valid uint8[n]) of the residual vector r -> t."""
+        n = self.num_landmarks(r)
+        e, jv = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        self._ck(self.lib.dpba_get_residual_scalars(self.h, r, t, n, _ptr(e), _ptr(jv)))
+        return e, jv
 
     def set_frame_statuses(self, r, per_target):
         """per_target: dict {target slot: uint8[n]} or list indexed by slot (None entries skipped)."""

@@ -16,7 +16,7 @@
 // landmarks on one pixel (order of two or three additions: last-bit differences, stated in the test).
 //
 // STATUS: written in round 1 after the GPU budget was spent -- compiled for sm_100a, NOT yet run on hardware; new entry
-// point, nothing else calls it.  Oracle: oracle/depth_map_oracle.py; GPU comparison: tests/test_zz_gpu_experimental.py.
+// point, nothing else calls it.  Oracle: oracle/depth_map_oracle.py; GPU comparison: tests/test_gpu_device_paths.py.
 #include <cuda_runtime.h>
 
 #include <cstdint>

@@ -1,19 +1,20 @@
-// Device-side 75 % energy quantile of updatePointStatuses (option "device_quantile", default OFF).
+// Device-side 75 % energy quantile of updatePointStatuses (option "device_quantile", default ON since round 2).
 //
 // Reference: PhotometricBundleAdjustment::updatePointStatuses, first half
 // (src/energy/problems/src/photometric_bundle_adjustment/photometric_bundle_adjustment.cpp:325-361): the energies of all
 // kOk residuals of non-marginalised landmarks towards non-marginalised targets are collected into one vector and
 // std::nth_element picks element k = size_t(n * 0.75); the outlier threshold is that energy + sigma^2 / 2.
-// The host version (dpba_update_point_statuses) reads N(N-1) status / energy rows back and calls nth_element; this one
+// The host version (option device_quantile = 0) reads N(N-1) status / energy rows back and calls nth_element; this one
 // never moves the rows: an EXACT radix select on the order-preserving integer image of the floats, most significant
 // byte first -- per pass one histogram kernel over all residuals (per-CTA shared-memory histograms with
 // warp-aggregated atomics, then at most 256 global atomics per CTA) and one tiny kernel that picks the byte and narrows
-// (prefix, k).  Four passes give the k-th smallest bit pattern, i.e. the very float nth_element returns.
+// (prefix, k).  Four passes give the k-th smallest bit pattern, i.e. the very float nth_element returns.  With landmarks
+// sharded over several GPUs the 256-bin histogram of every pass is summed over the ranks before the pick, so every rank
+// selects the same element of the union.
 //
-// STATUS: written in round 1 after the GPU budget was spent -- compiled for sm_100a, NOT yet run on hardware, so the
-// C ABI keeps the host path unless the option is set (tests/test_zz_gpu_experimental.py has the comparison, enabled with
-// DPBA_TEST_EXPERIMENTAL=1).  The enumeration and selection code lives in energy_quantile_body.h and also runs on the
-// CPU in tests/test_kernel_emulation.py.
+// Validated on B200 against the host path (tests/test_gpu_device_paths.py, tests/test_gpu_baseline_sizes.py: identical
+// threshold bits, statuses, flags and inlier counts).  The enumeration and selection code lives in
+// energy_quantile_body.h and also runs on the CPU in tests/test_kernel_emulation.py.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -65,7 +66,8 @@ __global__ void k_select_init(SelectState* st) {
 }  // namespace
 
 // leaves {count, value = k-th smallest energy (k = size_t(count * frac))} in *st; `nmax` = max landmarks of a frame
-void launch_energy_quantile(const WindowDev& w, int nmax, double frac, SelectState* st, cudaStream_t s) {
+void launch_energy_quantile(const WindowDev& w, int nmax, double frac, SelectState* st, cudaStream_t s,
+                            int (*after_hist)(void*), void* after_hist_arg) {
   k_select_init<<<1, 32, 0, s>>>(st);
   if (nmax > 0) {
     const long long total = (long long)w.n_frames * w.n_frames * nmax;
@@ -74,6 +76,7 @@ void launch_energy_quantile(const WindowDev& w, int nmax, double frac, SelectSta
     if (ctas > cap) ctas = cap;
     for (int shift = 24; shift >= 0; shift -= 8) {
       k_select_hist<<<(unsigned)ctas, 256, 0, s>>>(w, st, shift, nmax);
+      if (after_hist && after_hist(after_hist_arg)) return;
       k_select_pick<<<1, 256, 0, s>>>(st, shift, frac);
     }
     add_launches(8);

@@ -107,6 +107,7 @@ class CudaPhotometricBundleAdjustment {
     m.affine_brightness0[1] = frame.affine_brightness[1];
     m.exposure_time = frame.exposure_time;
     frames_.push_back(m);
+    dpba_check(h_, dpba_set_frame_marginalized(h_, slot, m.is_marginalized));
     dpba_check(h_, dpba_set_landmarks(h_, slot, frame.n_landmarks, frame.projections, frame.idepths, frame.patches,
                                       frame.landmark_flags));
     uploadStatuses(slot, frame);
@@ -140,11 +141,12 @@ class CudaPhotometricBundleAdjustment {
                                            frame.patches + 8 * old_n,
                                            frame.landmark_flags ? frame.landmark_flags + old_n : nullptr));
     }
-    uploadStatuses(slot, frame, old_n);
+    appendStatuses(slot, frame, old_n);
     FrameMeta& m = frames_[slot];
     m.to_marginalize = frame.is_marginalized && !m.is_marginalized;
     m.is_marginalized = frame.is_marginalized;
     dpba_check(h_, dpba_set_frame_flags(h_, slot, m.fixed, m.to_marginalize));
+    dpba_check(h_, dpba_set_frame_marginalized(h_, slot, m.is_marginalized));
   }
 
   // EigenPhotometricBundleAdjustment::solve (eigen_photometric_bundle_adjustment.cpp:59-101)
@@ -284,14 +286,28 @@ class CudaPhotometricBundleAdjustment {
     return eps;
   }
 
-  void uploadStatuses(int slot, const KeyframeView& frame, int /*first*/ = 0) {
+  // pushFrame (photometric_bundle_adjustment.cpp:104-123): the residual vectors between the new frame and every local,
+  // not marginalised frame are created in full, in both directions.
+  void uploadStatuses(int slot, const KeyframeView& frame) {
     for (const auto& [other_id, st] : frame.statuses_as_reference) {
       const int o = slotOfId(other_id);
-      if (o >= 0 && o != slot && !st.empty()) dpba_check(h_, dpba_set_statuses(h_, slot, o, (int)st.size(), st.data()));
+      if (o >= 0 && o != slot && !frames_[o].is_marginalized && !st.empty())
+        dpba_check(h_, dpba_set_statuses(h_, slot, o, (int)st.size(), st.data()));
     }
     for (const auto& [other_id, st] : frame.statuses_as_target) {
       const int o = slotOfId(other_id);
-      if (o >= 0 && o != slot && !st.empty()) dpba_check(h_, dpba_set_statuses(h_, o, slot, (int)st.size(), st.data()));
+      if (o >= 0 && o != slot && !frames_[o].is_marginalized && !st.empty())
+        dpba_check(h_, dpba_set_statuses(h_, o, slot, (int)st.size(), st.data()));
+    }
+  }
+  // LocalFrame::update (local_frame.hpp:505-518): only the residual vectors this frame is the REFERENCE of grow, and only
+  // by the statuses of the freshly matured landmarks [first, size); what the solver decided for the existing residuals
+  // (kOutlier from updatePointStatuses, kOOB from changeResidualStatuses) stays.
+  void appendStatuses(int slot, const KeyframeView& frame, int first) {
+    for (const auto& [other_id, st] : frame.statuses_as_reference) {
+      const int o = slotOfId(other_id);
+      if (o < 0 || o == slot || (int)st.size() <= first) continue;
+      dpba_check(h_, dpba_append_statuses(h_, slot, o, first, (int)st.size() - first, st.data() + first));
     }
   }
 

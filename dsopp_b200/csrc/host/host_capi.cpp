@@ -171,6 +171,95 @@ __attribute__((visibility("default"))) int dpbah_covariance(void* s, int ref_id,
   return 0;
 }
 
+// One whole solver step from HOST buffers in ONE call: drop the resident window, push every keyframe (images are DMA'd
+// straight from the caller's buffers when those are page-locked), landmarks, connection statuses and state, run
+// firstEstimateJacobians + the device-resident levenberg_marquardt_algorithm::solve, and write the results updateFrame
+// reads (photometric_bundle_adjustment.cpp:182-264) back into the caller's arrays.  Exactly the C-ABI call sequence a
+// host program makes for pushFrame x N / solve / updateFrame x N, without an interpreter between the calls; bench.py
+// times it as `e2e`.  Every pointer is a host pointer; rows of `statuses` / `statuses_out` are indexed [r * n + t].
+struct dpbah_window_io {
+  int32_t n_frames;
+  const int32_t* frame_ids;
+  const float* const* images;       // [n] H*W*3 {I,dx,dy}
+  const uint8_t* const* masks;      // [n] H*W (entries may be null)
+  const double* T_w_lin;            // [n][12]
+  const double* exposure;           // [n]
+  const double* ab0;                // [n][2]
+  const double* intr;               // [n][4]
+  const int32_t* fixed;             // [n]
+  const int32_t* n_landmarks;       // [n]
+  const float* const* uv;           // [n] -> [m][2]
+  const float* const* idepth;       // [n] -> [m]
+  const float* const* patch;        // [n] -> [m][8]
+  const uint8_t* const* flags;      // [n] -> [m]
+  const uint8_t* const* statuses;   // [n*n] -> [m_r] (null on the diagonal)
+  const double* eps0;               // [8n]
+  dpba_lm_options lm;
+  // results
+  double* eps_out;                  // [8n]
+  float* const* idepth_out;         // [n] -> [m]
+  float* const* inv_hdd_out;
+  float* const* rel_baseline_out;
+  uint8_t* const* flags_out;
+  uint32_t* const* n_inliers_out;
+  uint8_t* const* statuses_out;     // [n*n] -> [m_r]
+  double energy;
+  int32_t iterations, n_valid, converged;
+  int64_t h2d_bytes, d2h_bytes;     // counted from the arrays handed over / written back
+  // optional: RAW 8-bit frames instead of `images` (dpba_push_frame_raw: photometric table, gradients on the device)
+  const uint8_t* const* raw_gray;   // [n] H*W, or null
+  const float* photometric_lut;     // [256]
+};
+
+__attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dpbah_window_io* io, int width, int height) {
+  GUARD({
+    const int n = io->n_frames;
+    int64_t h2d = 0, d2h = 0;
+    while (dpba_num_frames(h) > 0) dpba_check(h, dpba_remove_frame(h, 0));
+    const size_t npx = (size_t)width * height;
+    for (int f = 0; f < n; ++f) {
+      if (io->raw_gray) {
+        dpba_check(h, dpba_push_frame_raw(h, io->frame_ids[f], io->raw_gray[f], io->photometric_lut, nullptr, io->masks[f],
+                                          io->T_w_lin + 12 * f, io->exposure[f], io->ab0 + 2 * f, io->intr + 4 * f,
+                                          io->fixed[f]));
+        h2d += (int64_t)npx + 1024 + (io->masks[f] ? (int64_t)npx : 0);
+      } else {
+        dpba_check(h, dpba_push_frame(h, io->frame_ids[f], io->images[f], io->masks[f], io->T_w_lin + 12 * f,
+                                      io->exposure[f], io->ab0 + 2 * f, io->intr + 4 * f, io->fixed[f]));
+        h2d += (int64_t)npx * 12 + (io->masks[f] ? (int64_t)npx : 0);
+      }
+    }
+    std::vector<double> zero(8 * (size_t)n, 0.0);
+    for (int f = 0; f < n; ++f) {
+      const int m = io->n_landmarks[f];
+      dpba_check(h, dpba_set_landmarks(h, f, m, io->uv[f], io->idepth[f], io->patch[f], io->flags[f]));
+      dpba_check(h, dpba_set_frame_statuses(h, f, m, io->statuses + (size_t)f * n));
+      h2d += (int64_t)m * (8 + 4 + 32 + 1) + (int64_t)m * (n - 1);
+    }
+    dpba_check(h, dpba_set_state(h, io->eps0, zero.data()));
+    h2d += 2 * 8 * (int64_t)n * 8;
+    dpba_check(h, dpba_first_estimate(h));
+    dpba_lm_result r;
+    dpba_check(h, dpba_solve_lm(h, &io->lm, nullptr, nullptr, 0.0, &r));
+    io->energy = r.energy;
+    io->iterations = r.iterations;
+    io->n_valid = r.number_of_valid_residuals;
+    io->converged = r.converged;
+    dpba_check(h, dpba_get_state(h, io->eps_out, zero.data()));
+    d2h += 2 * 8 * (int64_t)n * 8;
+    for (int f = 0; f < n; ++f) {
+      const int m = io->n_landmarks[f];
+      dpba_check(h, dpba_get_landmarks(h, f, m, io->idepth_out[f], nullptr, io->inv_hdd_out[f], nullptr, io->flags_out[f],
+                                       io->n_inliers_out[f], io->rel_baseline_out[f]));
+      dpba_check(h, dpba_get_frame_statuses(h, f, m, io->statuses_out + (size_t)f * n, nullptr));
+      d2h += (int64_t)m * (4 * 4 + 1) + (int64_t)m * (n - 1);
+    }
+    io->h2d_bytes = h2d;
+    io->d2h_bytes = d2h;
+  });
+  return 0;
+}
+
 // levenberg_marquardt_algorithm::solve over a window that was uploaded through the C ABI directly.
 // trace (optional): per loop body [accepted, energy, n_valid, step(8N)...], row stride 3 + 8N.
 __attribute__((visibility("default"))) int dpbah_lm_solve(dpba_handle* h, int n_frames, const double* ab0,

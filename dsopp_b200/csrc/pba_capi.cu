@@ -146,7 +146,7 @@ struct dpba_handle {
   bool peer_attached = false;
   bool peer_on = false;          // option "peer_exchange"
   // device-side quantile of updatePointStatuses (energy_quantile.cu)
-  bool device_quantile = false;  // option "device_quantile"
+  bool device_quantile = true;   // option "device_quantile" (0: host nth_element over rows read back)
   pba::SelectState* sel_dev = nullptr;
   pba::SelectState* sel_h = nullptr;  // pinned
   float* dm_buf = nullptr;       // reference depth maps (depth_maps.cu), lazily: 4 * sum_l (W>>l)(H>>l) floats
@@ -889,6 +889,13 @@ int dpba_set_frame_flags(dpba_handle* h, int32_t slot, int32_t fixed, int32_t to
   return DPBA_SUCCESS;
 }
 
+int dpba_set_frame_marginalized(dpba_handle* h, int32_t slot, int32_t is_marginalized) {
+  REQUIRE(h, "null handle");
+  REQUIRE(slot >= 0 && slot < h->n_frames, "slot out of range");
+  h->fr[slot].is_marg = is_marginalized ? 1 : 0;
+  return DPBA_SUCCESS;
+}
+
 int dpba_set_landmarks(dpba_handle* h, int32_t slot, int32_t n, const float* uv, const float* idepth,
                        const float* patch, const uint8_t* flags) {
   REQUIRE(h, "null handle");
@@ -968,9 +975,9 @@ int dpba_get_pose_idepth_blocks(dpba_handle* h, int32_t slot, int32_t n, float* 
   return DPBA_SUCCESS;
 }
 
-static int set_statuses_row(dpba_handle* h, int r, int t, int n, const uint8_t* st) {
+static int set_statuses_row(dpba_handle* h, int r, int t, int n, const uint8_t* st, int first = 0) {
   h->rb_valid = false;
-  const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
+  const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame + (size_t)first;
   if (!n) return 0;
   uint8_t* stg = (uint8_t*)arena_alloc(h, n);
   if (!stg) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
@@ -985,6 +992,14 @@ int dpba_set_statuses(dpba_handle* h, int32_t r, int32_t t, int32_t n, const uin
   REQUIRE(r >= 0 && r < h->n_frames && t >= 0 && t < h->n_frames && r != t && st, "bad pair");
   REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
   return set_statuses_row(h, r, t, n, st);
+}
+
+int dpba_append_statuses(dpba_handle* h, int32_t r, int32_t t, int32_t first, int32_t n, const uint8_t* st) {
+  REQUIRE(h, "null handle");
+  REQUIRE(r >= 0 && r < h->n_frames && t >= 0 && t < h->n_frames && r != t, "bad pair");
+  REQUIRE(first >= 0 && n >= 0 && first + n <= h->cfg.max_points_per_frame, "range out of bounds");
+  REQUIRE(n == 0 || st, "null statuses");
+  return set_statuses_row(h, r, t, n, st, first);
 }
 
 int dpba_set_frame_statuses(dpba_handle* h, int32_t r, int32_t n, const uint8_t* const* per_target) {
@@ -1009,6 +1024,7 @@ int dpba_set_frame_statuses(dpba_handle* h, int32_t r, int32_t n, const uint8_t*
     uint8_t* stg = (uint8_t*)arena_alloc(h, rows * mp);
     if (!stg) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
     bool covered[PBA_MAXF] = {};
+    memset(stg, 0, rows * mp);  // slots [n, max_pts) of every row and the unused r -> r row: kOk, never stale bytes
     for (int t = 0; t < h->n_frames; ++t) {
       covered[h->fr[t].phys - lo] = true;
       if (t != r) memcpy(stg + (size_t)(h->fr[t].phys - lo) * mp, per_target[t], n);
@@ -1056,6 +1072,18 @@ int dpba_get_statuses(dpba_handle* h, int32_t r, int32_t t, int32_t n, uint8_t* 
   if (rc) return rc;
   if (n && st) memcpy(st, h->rb_status + base, n);
   if (n && cand) memcpy(cand, h->rb_cand + base, n);
+  return DPBA_SUCCESS;
+}
+
+int dpba_get_residual_scalars(dpba_handle* h, int32_t r, int32_t t, int32_t n, float* energy, uint8_t* valid) {
+  REQUIRE(h, "null handle");
+  REQUIRE(r >= 0 && r < h->n_frames && t >= 0 && t < h->n_frames && r != t, "bad pair");
+  REQUIRE(n >= 0 && n <= h->cfg.max_points_per_frame, "n out of range");
+  if (!n) return DPBA_SUCCESS;
+  const size_t base = ((size_t)(h->fr[r].phys * PBA_MAXF + h->fr[t].phys)) * h->cfg.max_points_per_frame;
+  if (energy) CK(cudaMemcpyAsync(energy, h->energy + base, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (valid) CK(cudaMemcpyAsync(valid, h->jac_valid + base, n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return DPBA_SUCCESS;
 }
 
@@ -1313,7 +1341,10 @@ int dpba_update_point_statuses(dpba_handle* h, int32_t min_valid, double sigma, 
   std::vector<float> energies;
   std::vector<float> e(mp);
   std::vector<uint8_t> st(mp), fl(mp);
-  for (int r = 0; r < N && !h->device_quantile; ++r) {
+  const bool dev_q = h->device_quantile || h->world > 1;  // sharded landmarks: only the device select sees every rank
+  if (h->world > 1 && !(h->comm && nccl_api().ok))
+    return fail(h, DPBA_E_STATE, "update_point_statuses with world_size > 1 needs the NCCL communicator (dpba_comm_init)");
+  for (int r = 0; r < N && !dev_q; ++r) {
     const int n = h->fr[r].n_lm;
     if (!n) continue;
     CK(cudaMemcpyAsync(fl.data(), h->flags + (size_t)h->fr[r].phys * mp, n, cudaMemcpyDeviceToHost, h->stream));
@@ -1327,9 +1358,8 @@ int dpba_update_point_statuses(dpba_handle* h, int32_t min_valid, double sigma, 
         if (!(fl[l] & DPBA_LM_MARGINALIZED) && st[l] == DPBA_OK_STATUS) energies.push_back(e[l]);
     }
   }
-  if (h->world > 1) return fail(h, DPBA_E_STATE, "update_point_statuses: gather the energies on the caller for world_size > 1");
   float thr = 0.f;
-  if (h->device_quantile) {
+  if (dev_q) {
     // exact radix select on the device: no status / energy row crosses PCIe, one small readback
     if (!h->sel_dev) {
       CK(cudaMalloc(&h->sel_dev, sizeof(pba::SelectState)));
@@ -1337,7 +1367,28 @@ int dpba_update_point_statuses(dpba_handle* h, int32_t min_valid, double sigma, 
     }
     int nmax = 0;
     for (int r = 0; r < N; ++r) nmax = std::max(nmax, h->fr[r].n_lm);
-    pba::launch_energy_quantile(make_window(h), nmax, 0.75, h->sel_dev, h->stream);
+    if (h->world > 1) {  // every rank must run the same number of passes: the largest shard decides
+      // (shards differ by at most one landmark per frame; nmax only bounds the enumeration, so the local maximum + 1 is
+      // a safe common value without another exchange)
+      nmax += 1;
+    }
+    struct HistExchange {
+      dpba_handle* h;
+      static int run(void* p) {
+        dpba_handle* hh = ((HistExchange*)p)->h;
+        const ncclResult_t r = nccl_api().AllReduce(hh->sel_dev->hist, hh->sel_dev->hist, 256, ncclUint32, ncclSum, hh->comm,
+                                                    hh->stream);
+        if (r != ncclSuccess) {
+          hh->err = std::string("ncclAllReduce(histogram): ") + nccl_api().GetErrorString(r);
+          return 1;
+        }
+        return 0;
+      }
+    } hx{h};
+    h->err.clear();
+    pba::launch_energy_quantile(make_window(h), nmax, 0.75, h->sel_dev, h->stream, h->world > 1 ? &HistExchange::run : nullptr,
+                                &hx);
+    if (h->world > 1 && !h->err.empty()) return DPBA_E_COMM;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->sel_h, h->sel_dev, sizeof(pba::SelectState), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1681,9 +1732,10 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   std::vector<long long> key = {N, od.max_it, od.fej, H_marg != nullptr, h->world, (long long)h->profiling,
                                 (long long)(h->speculative && od.force_accept), (long long)h->speculative_multi,
                                 (long long)llround(od.sigma * 1e6), (long long)h->peer_on};
-  for (int f = 0; f < N; ++f) {
+  for (int f = 0; f < N; ++f) {  // every per-frame field of WindowDev (the captured kernels hold it BY VALUE)
     key.push_back(h->fr[f].n_lm);
     key.push_back(h->fr[f].phys);
+    key.push_back(h->fr[f].mask_all | (h->fr[f].fixed << 1) | (h->fr[f].is_marg << 2));
   }
   int rc = 0;
   if (h->use_graph) {

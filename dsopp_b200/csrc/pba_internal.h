@@ -195,7 +195,10 @@ struct SelectState {
   unsigned count;            // residuals that took part
   float value;               // result: the k-th smallest energy
 };
-void launch_energy_quantile(const WindowDev& w, int nmax, double frac, SelectState* st, cudaStream_t s);
+// `after_hist` (may be null) runs after every histogram pass, before the byte is picked: with several ranks it sums
+// st->hist over the ranks (256 unsigned), which makes the select exact over the union of the shards
+void launch_energy_quantile(const WindowDev& w, int nmax, double frac, SelectState* st, cudaStream_t s,
+                            int (*after_hist)(void*) = nullptr, void* after_hist_arg = nullptr);
 
 // ---- reference depth maps of the coarse tracker (depth_maps.cu) --------------------------------------------------------
 size_t dm_level_offset(int W, int H, int level);

@@ -219,23 +219,27 @@ __device__ __forceinline__ void eval_pixel(const PairConst& pc, const LandmarkIn
   const float su = ev ? tu : 8.f, sv = ev ? tv : 8.f;
   const int ix = (int)su, iy = (int)sv;
   const float dx = su - (float)ix, dy = sv - (float)iy;
-  const float dxdy = dx * dy;
-  const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = 1.f - dx - dy + dxdy;
+  // The intensity, the residual and the patch energy feed the 75 % energy quantile of updatePointStatuses, i.e. connection
+  // statuses: their operation sequence is pinned (explicit roundings / fused multiply-adds) and restated by the float
+  // build of oracle/cpu_ref (`device_ops`), so that the bookkeeping can be compared bit for bit.
+  const float dxdy = __fmul_rn(dx, dy);
+  const float w11 = dxdy, w10 = __fsub_rn(dy, dxdy), w01 = __fsub_rn(dx, dxdy),
+              w00 = __fadd_rn(__fsub_rn(__fsub_rn(1.f, dx), dy), dxdy);
   // the image is stored as 32-byte records {texel(x), texel(x + 1)}: the two horizontal taps of a row are ONE
   // 256-bit load (half the gather instructions and L1 wavefronts of four 128-bit loads)
   const float4* p = img + ((size_t)iy * W + ix) * 2;
   float4 t00, t01, t10, t11;
   ldg256_nc(p, t00, t01);
   ldg256_nc(p + 2 * (size_t)W, t10, t11);
-  const float I = w11 * t11.x + w10 * t10.x + w01 * t01.x + w00 * t00.x;
+  const float I = __fmaf_rn(w00, t00.x, __fmaf_rn(w01, t01.x, __fmaf_rn(w10, t10.x, __fmul_rn(w11, t11.x))));
   // r = (I_t - b_t) - s (patch - b_r), evaluate_jacobians.hpp:124-135
-  const float r = ev ? (I - pc.b_t) - pc.s * (lm.patch - pc.b_r) : 0.f;
-  const float n2 = group_sum(r * r);
+  const float r = ev ? __fmaf_rn(-pc.s, __fsub_rn(lm.patch, pc.b_r), __fsub_rn(I, pc.b_t)) : 0.f;
+  const float n2 = group_sum(__fmul_rn(r, r));
+  const float sig2 = __fmul_rn(sigma, sigma);
   float e = 0.5f * n2, wgt = 1.f;
-  if (huber && n2 > sigma * sigma) {  // evaluate_jacobians.hpp:139-146; MUFU.RSQ (2 ulp) instead of IEEE sqrt + divide
-    const float rn = rsqrt_approx(n2);
-    wgt = sigma * rn;
-    e = sigma * (n2 * rn) - sigma * sigma * 0.5f;
+  if (huber && n2 > sig2) {  // evaluate_jacobians.hpp:139-146
+    wgt = sigma * rsqrt_approx(n2);  // weight: MUFU.RSQ (2 ulp), no status depends on it
+    e = __fmaf_rn(sigma, __fsqrt_rn(n2), -(0.5f * sig2));  // energy: correctly rounded (it is compared with the quantile)
   }
   o.r = r;
   o.e = ev ? e : 0.f;

@@ -110,6 +110,91 @@ def lm_solve(handle: capi.Handle, ab0, fixed, sigma=20.0, ab_reg=(1e12, 1e8), fi
     return e.value, it.value
 
 
+class _WindowIOStruct(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("frame_ids", _P), ("images", _P), ("masks", _P), ("T_w_lin", _P), ("exposure", _P),
+                ("ab0", _P), ("intr", _P), ("fixed", _P), ("n_landmarks", _P), ("uv", _P), ("idepth", _P), ("patch", _P),
+                ("flags", _P), ("statuses", _P), ("eps0", _P), ("lm", capi.LmOptions), ("eps_out", _P), ("idepth_out", _P),
+                ("inv_hdd_out", _P), ("rel_baseline_out", _P), ("flags_out", _P), ("n_inliers_out", _P),
+                ("statuses_out", _P), ("energy", C.c_double), ("iterations", C.c_int32), ("n_valid", C.c_int32),
+                ("converged", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("raw_gray", _P),
+                ("photometric_lut", _P)]
+
+
+class WindowStep:
+    """dpbah_solve_window: one whole solver step from host buffers in ONE C++ call (push every keyframe, landmarks,
+    statuses, state -> firstEstimateJacobians + device LM -> results back).  `frames`: list of dicts with the host arrays
+    (frame_id, image HxWx3 f32, mask HxW u8 or None, T_w_lin, exposure, ab0, intr, fixed, uv, idepth, patch, flags);
+    `statuses[(r, t)]`: uint8 per landmark of r.  Arrays are used in place -- pass page-locked ones to have them DMA'd
+    without a staging copy.  Results land in `self.out` (eps, and per frame idepth / inv_hdd / rel_baseline / flags /
+    n_inliers / statuses[t])."""
+
+    def __init__(self, handle: capi.Handle, frames, statuses, eps0, sigma=20.0, ab_reg=(1e12, 1e8), fixed_reg=1e16, max_it=7,
+                 min_it=3, ftol=1e-8, ptol=1e-8, force_accept=True, lambda0=1e-5, decrease=1.0, increase=1.0, fej=True,
+                 alloc=None, raw_gray=None, photometric_lut=None):
+        self.lib = load_library()
+        self.lib.dpbah_solve_window.argtypes = [_P, C.POINTER(_WindowIOStruct), _I, _I]
+        self.h = handle
+        n = len(frames)
+        alloc = alloc or (lambda shape, dtype: np.zeros(shape, dtype))
+        k = self._keep = {}
+        k["ids"] = np.ascontiguousarray([f["frame_id"] for f in frames], dtype=np.int32)
+        k["T"] = np.ascontiguousarray(np.stack([pose34(f["T_w_lin"]) for f in frames]))
+        k["exp"] = np.ascontiguousarray([f["exposure"] for f in frames], dtype=np.float64)
+        k["ab0"] = np.ascontiguousarray(np.stack([_f64(f["ab0"]) for f in frames]))
+        k["intr"] = np.ascontiguousarray(np.stack([_f64(f["intr"]) for f in frames]))
+        k["fixed"] = np.ascontiguousarray([int(f["fixed"]) for f in frames], dtype=np.int32)
+        k["n_lm"] = np.ascontiguousarray([len(f["idepth"]) for f in frames], dtype=np.int32)
+        k["eps0"] = _f64(eps0)
+        k["frames"] = frames
+        k["statuses"] = statuses
+
+        def ptr_array(items):
+            return (C.c_void_p * len(items))(*[None if a is None else a.ctypes.data for a in items])
+
+        for name, dt in (("image", np.float32), ("uv", np.float32), ("idepth", np.float32), ("patch", np.float32),
+                         ("flags", np.uint8)):
+            for f in frames:
+                a = f[name]
+                assert a.dtype == dt and a.flags["C_CONTIGUOUS"], name
+        k["p_images"] = ptr_array([f["image"] for f in frames])
+        k["p_masks"] = ptr_array([f.get("mask") for f in frames])
+        k["p_uv"] = ptr_array([f["uv"] for f in frames])
+        k["p_idepth"] = ptr_array([f["idepth"] for f in frames])
+        k["p_patch"] = ptr_array([f["patch"] for f in frames])
+        k["p_flags"] = ptr_array([f["flags"] for f in frames])
+        k["p_status"] = ptr_array([None if r == t else statuses[(r, t)] for r in range(n) for t in range(n)])
+        self.out = dict(eps=np.zeros(8 * n))
+        for name, dt in (("idepth", np.float32), ("inv_hdd", np.float32), ("rel_baseline", np.float32), ("flags", np.uint8),
+                         ("n_inliers", np.uint32)):
+            self.out[name] = [alloc(int(m), dt) for m in k["n_lm"]]
+            k["p_out_" + name] = ptr_array(self.out[name])
+        self.out["statuses"] = [[None if r == t else alloc(int(k["n_lm"][r]), np.uint8) for t in range(n)] for r in range(n)]
+        k["p_out_status"] = ptr_array([self.out["statuses"][r][t] for r in range(n) for t in range(n)])
+        io = self.io = _WindowIOStruct()
+        io.n_frames = n
+        io.frame_ids, io.T_w_lin, io.exposure = k["ids"].ctypes.data, k["T"].ctypes.data, k["exp"].ctypes.data
+        io.ab0, io.intr, io.fixed, io.n_landmarks = (k["ab0"].ctypes.data, k["intr"].ctypes.data, k["fixed"].ctypes.data,
+                                                     k["n_lm"].ctypes.data)
+        cast = lambda a: C.cast(a, C.c_void_p)
+        io.images, io.masks, io.uv, io.idepth = cast(k["p_images"]), cast(k["p_masks"]), cast(k["p_uv"]), cast(k["p_idepth"])
+        io.patch, io.flags, io.statuses, io.eps0 = cast(k["p_patch"]), cast(k["p_flags"]), cast(k["p_status"]), k["eps0"].ctypes.data
+        io.lm = capi.LmOptions(max_it, min_it, int(force_accept), int(fej), lambda0, ftol, ptol, decrease, increase, sigma,
+                               (C.c_double * 2)(*ab_reg), fixed_reg)
+        io.eps_out = self.out["eps"].ctypes.data
+        io.idepth_out, io.inv_hdd_out = cast(k["p_out_idepth"]), cast(k["p_out_inv_hdd"])
+        io.rel_baseline_out, io.flags_out = cast(k["p_out_rel_baseline"]), cast(k["p_out_flags"])
+        io.n_inliers_out, io.statuses_out = cast(k["p_out_n_inliers"]), cast(k["p_out_status"])
+        if raw_gray is not None:  # 8-bit frames: dpba_push_frame_raw (photometric table + {I,dx,dy} on the device)
+            k["raw"], k["lut"] = [_u8(g) for g in raw_gray], _f32(photometric_lut)
+            k["p_raw"] = ptr_array(k["raw"])
+            io.raw_gray, io.photometric_lut = cast(k["p_raw"]), k["lut"].ctypes.data
+
+    def run(self):
+        """-> (energy, iterations); results in self.out, byte counters in self.io.h2d_bytes / d2h_bytes."""
+        _ck(self.lib.dpbah_solve_window(self.h.h, C.byref(self.io), self.h.cfg.width, self.h.cfg.height))
+        return self.io.energy, self.io.iterations
+
+
 class CudaPhotometricBundleAdjustment:
     """Python proxy of the C++ class of the same name (csrc/host/cuda_photometric_bundle_adjustment.hpp)."""
 

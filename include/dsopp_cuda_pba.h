@@ -131,6 +131,9 @@ int dpba_num_frames(const dpba_handle* h);
 int dpba_set_frame_linearization(dpba_handle* h, int32_t slot, const double T_w_agent_lin[12],
                                  const double affine_brightness0[2]);
 int dpba_set_frame_flags(dpba_handle* h, int32_t slot, int32_t fixed, int32_t to_marginalize);
+/* LocalFrame::is_marginalized (PBA/local_frame.hpp:571; set from ActiveKeyframe::isMarginalized, :320): a marginalised
+ * frame is skipped as a target by updatePointStatuses (photometric_bundle_adjustment.cpp:339,377) */
+int dpba_set_frame_marginalized(dpba_handle* h, int32_t slot, int32_t is_marginalized);
 
 /* Landmarks hosted by `slot` (LocalFrame::active_landmarks, PBA/local_frame.hpp:327-333): replaces all n
  * landmarks.  proj_xy [n][2], idepth [n], patch [n][8], flags [n] (DPBA_LM_*).  idepth_step := 0. */
@@ -153,6 +156,17 @@ int dpba_get_pose_idepth_blocks(dpba_handle* h, int32_t slot, int32_t n, float* 
 int dpba_set_statuses(dpba_handle* h, int32_t ref_slot, int32_t tgt_slot, int32_t n, const uint8_t* statuses);
 int dpba_get_statuses(dpba_handle* h, int32_t ref_slot, int32_t tgt_slot, int32_t n, uint8_t* statuses,
                       uint8_t* candidates);
+/* LocalFrame::update (PBA/local_frame.hpp:505-518): statuses of freshly matured landmarks are APPENDED to the residual
+ * vector (ref_slot -> tgt_slot) from index `first` on; residuals [0, first) -- which the solver owns by then (kOutlier /
+ * kOOB set by updatePointStatuses / changeResidualStatuses) -- are not touched */
+int dpba_append_statuses(dpba_handle* h, int32_t ref_slot, int32_t tgt_slot, int32_t first, int32_t n,
+                         const uint8_t* statuses);
+/* Per-residual scalars the sweeps keep resident, for the residual vector (ref_slot -> tgt_slot): ResidualPoint::energy of
+ * the last evaluation (PBA/local_frame.hpp:203, PBA/evaluate_jacobians.hpp:136-146,184-194) and
+ * ResidualPoint::reprojection_jacobians_valid of the last firstEstimateJacobians pass (PBA/local_frame.hpp:197,
+ * PBA/first_estimate_jacobians.hpp:52-54).  Either output may be NULL.  Plain device reads, no mode required. */
+int dpba_get_residual_scalars(dpba_handle* h, int32_t ref_slot, int32_t tgt_slot, int32_t n, float* energy,
+                              uint8_t* reprojection_jacobians_valid);
 
 /* All residual vectors of one reference frame in one call -- what the LocalFrame ctor / LocalFrame::update do with
  * frame.connections() (PBA/local_frame.hpp:336-347,506-520).  per_target[t] -> [n] statuses towards slot t;

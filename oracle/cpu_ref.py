@@ -44,6 +44,12 @@ def _load(native=False):
     lib.cpuref_gn_iteration.restype = C.c_double
     lib.cpuref_gn_iteration.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_double,
                                         C.c_void_p, C.c_void_p]
+    lib.cpuref_set_device_ops.argtypes = [C.c_void_p, C.c_int]
+    lib.cpuref_update_point_statuses.restype = C.c_double
+    lib.cpuref_update_point_statuses.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    lib.cpuref_get_jac_valid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.cpuref_set_idepths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.cpuref_get_landmark_flags.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     _libs[key] = lib
     return lib
 
@@ -81,10 +87,39 @@ class CpuWindow:
         eps = np.ascontiguousarray(np.concatenate([f.state_eps for f in win.frames]), dtype=np.float64)
         self.lib.cpuref_set_state(self.h, _p(eps), _p(np.zeros_like(eps)))
 
+        self.frames_meta = [(np.array(f.ab0, dtype=np.float64), bool(f.fixed)) for f in win.frames]
+
     def close(self):
         if self.h:
             self.lib.cpuref_destroy(self.h)
             self.h = None
+
+    def set_device_ops(self, on=True):
+        """float build: residual / energy arithmetic in the CUDA kernels' operation order (bit-exact bookkeeping checks)."""
+        self.lib.cpuref_set_device_ops(self.h, int(on))
+
+    def update_point_statuses(self, min_valid, sigma):
+        return self.lib.cpuref_update_point_statuses(self.h, int(min_valid), float(sigma))
+
+    def jac_valid(self, r, t):
+        out = np.zeros(self.counts[r], np.uint8)
+        self.lib.cpuref_get_jac_valid(self.h, r, t, _p(out))
+        return out
+
+    def set_statuses(self, r, t, st):
+        st = np.ascontiguousarray(st, dtype=np.uint8)
+        self.lib.cpuref_set_statuses(self.h, r, t, len(st), _p(st))
+
+    def set_idepths(self, slot, idepth=None, idepth_step=None):
+        a = None if idepth is None else np.ascontiguousarray(idepth, dtype=np.float64)
+        b = None if idepth_step is None else np.ascontiguousarray(idepth_step, dtype=np.float64)
+        self.lib.cpuref_set_idepths(self.h, slot, self.counts[slot], _p(a), _p(b))
+
+    def landmark_flags(self, slot):
+        n = self.counts[slot]
+        out = dict(outlier=np.zeros(n, np.uint8), n_inliers=np.zeros(n, np.uint32), rel_baseline=np.zeros(n))
+        self.lib.cpuref_get_landmark_flags(self.h, slot, _p(out["outlier"]), _p(out["n_inliers"]), _p(out["rel_baseline"]))
+        return out
 
     def __del__(self):
         self.close()
@@ -161,6 +196,68 @@ class CpuWindow:
         reg = np.ascontiguousarray(ab_reg, dtype=np.float64)
         e = self.lib.cpuref_gn_iteration(self.h, sigma, int(fej), lam, _p(reg), fixed_reg, _p(times), _p(step))
         return e, times, step
+
+
+class CpuRefProblem:
+    """LevenbergMarquardtProblem over a CpuWindow (PBA/eigen_photometric_bundle_adjustment_problem.hpp:255-429): the same
+    six methods as oracle.pba_oracle.Problem, so oracle.pba_oracle.lm_solve drives it -- the C++ restatement at sizes the
+    NumPy oracle would need minutes for.  Priors and the reduced solve are done here in float64 NumPy."""
+
+    def __init__(self, cw: CpuWindow, sigma, ab_reg=(1e12, 1e8), fixed_reg=1e16, fej=True, H_marg=None, b_marg=None,
+                 energy_marg=0.0):
+        self.cw, self.sigma, self.fej = cw, float(sigma), fej
+        self.ab_reg, self.fixed_reg = np.asarray(ab_reg, dtype=np.float64), float(fixed_reg)
+        d = 8 * cw.n
+        self.H_marg = np.zeros((d, d)) if H_marg is None else np.array(H_marg, dtype=np.float64)
+        self.b_marg = np.zeros(d) if b_marg is None else np.array(b_marg, dtype=np.float64)
+        self.energy_marg = float(energy_marg)
+
+    def calculate_energy(self):
+        self.cw.evaluate(self.sigma, self.fej, False, True)
+        eps, step = self.cw.get_state()
+        s = eps + step
+        energy = self.energy_marg + self.b_marg @ s + 0.5 * (s @ (self.H_marg @ s))
+        for i, (ab0, _) in enumerate(self.cw.frames_meta):
+            ab = ab0 + s[8 * i + 6:8 * i + 8]
+            energy += 0.5 * float((ab * self.ab_reg) @ ab)
+        le, nv = self.cw.landmarks_energy()
+        return energy + le, nv
+
+    def linearize(self):
+        self.cw.evaluate(self.sigma, self.fej, True, True)
+        self.H_pose, self.b_pose = self.cw.pose_pose()
+        eps, _ = self.cw.get_state()
+        for i, (ab0, fixed) in enumerate(self.cw.frames_meta):
+            o = 8 * i
+            if fixed:
+                self.H_pose[o:o + 8, o:o + 8] += np.eye(8) * self.fixed_reg
+                self.b_pose[o:o + 8] += self.fixed_reg * eps[o:o + 8]
+            else:
+                self.H_pose[o + 6:o + 8, o + 6:o + 8] += np.diag(self.ab_reg)
+                self.b_pose[o + 6:o + 8] += self.ab_reg * (ab0 + eps[o + 6:o + 8])
+        self.H_schur, self.b_schur = self.cw.schur()
+
+    def calculate_step(self, lam):
+        eps, _ = self.cw.get_state()
+        H = self.H_pose + self.H_marg
+        b = self.b_pose + self.b_marg
+        H[np.diag_indices_from(H)] += np.diag(self.H_pose) * lam
+        k = -1.0 / (1.0 + lam)
+        H = H + self.H_schur * k
+        b = b + self.b_schur * k + self.H_marg @ eps
+        step = normal_solve(H, b)
+        self.cw.set_state(None, -step)
+        self.cw.calculate_idepths(step, lam)
+        return step
+
+    def accept_step(self):
+        return self.cw.accept()
+
+    def reject_step(self):
+        self.cw.reject()
+
+    def stop(self):
+        return False
 
 
 def normal_solve(H, b, native=False):

@@ -275,10 +275,28 @@ inline void sample(const Frame<S>& f, S x, S y, S out[3]) {  // features/.../pix
   for (int c = 0; c < 3; ++c) out[c] = w11 * q[3 + c] + w10 * q[c] + w01 * p[3 + c] + w00 * p[c];
 }
 
+// Intensity sample with the CUDA kernels' exact operation sequence (eval_pixel in dsopp_b200/csrc/pba_kernels.cu: products
+// of the weights rounded separately, the four taps folded by a chain of fused multiply-adds).  Only the `device_ops`
+// flavour of the float build uses it, so that residual energies -- and with them the 75 % quantile threshold of
+// updatePointStatuses -- can be compared with the device bit for bit.
+inline float sample_intensity_device_ops(const Frame<float>& f, float x, float y) {
+  const int ix = (int)x, iy = (int)y;
+  const float dx = x - (float)ix, dy = y - (float)iy, dxdy = dx * dy;
+  const float w11 = dxdy, w10 = dy - dxdy, w01 = dx - dxdy, w00 = ((1.f - dx) - dy) + dxdy;
+  const float* p = f.image.data() + ((size_t)iy * f.W + ix) * 3;
+  const float* q = p + (size_t)f.W * 3;
+  return fmaf(w00, p[0], fmaf(w01, p[3], fmaf(w10, q[0], w11 * q[3])));
+}
+inline double sample_intensity_device_ops(const Frame<double>& f, double x, double y) {
+  (void)f, (void)x, (void)y;
+  return 0;  // the flavour exists for the float build only
+}
+
 template <typename S>
 struct Window {
   std::vector<std::unique_ptr<Frame<S>>> frames;
   int threads = 1;
+  bool device_ops = false;  // float build: residual / energy arithmetic in the CUDA kernels' operation order
   std::vector<double> Hpose, bpose, Hschur, bschur;  // last linearisation
 
   int N() const { return (int)frames.size(); }
@@ -359,20 +377,34 @@ struct Window {
         if (ok && res.status == K_OK) {
           res.cand = K_OK;
           S dIu[P], dIv[P], n2 = 0;
+          const bool dev = device_ops && sizeof(S) == 4;
           for (int i = 0; i < P; ++i) {
             S smp[3];
             sample(T, tp[i][0], tp[i][1], smp);
             dIu[i] = smp[1];
             dIv[i] = smp[2];
-            res.residuals[i] = (smp[0] - pc.b_t) - pc.s * (lm.patch[i] - pc.b_r);
+            if (dev) {  // r = fma(-s, patch - b_r, I - b_t) with I from the kernels' tap chain
+              const S I = (S)sample_intensity_device_ops(T, tp[i][0], tp[i][1]);
+              res.residuals[i] = (S)fmaf(-(float)pc.s, (float)(lm.patch[i] - pc.b_r), (float)(I - pc.b_t));
+            } else {
+              res.residuals[i] = (smp[0] - pc.b_t) - pc.s * (lm.patch[i] - pc.b_r);
+            }
             n2 += res.residuals[i] * res.residuals[i];
+          }
+          S sig2_cmp = sig2;
+          if (dev) {  // the kernels' 8-lane butterfly: (i, i^4), then (i, i^2), then (i, i^1); sigma^2 in float
+            S q[P];
+            for (int i = 0; i < P; ++i) q[i] = res.residuals[i] * res.residuals[i];
+            const S a0 = q[0] + q[4], a1 = q[1] + q[5], a2 = q[2] + q[6], a3 = q[3] + q[7];
+            n2 = (a0 + a2) + (a1 + a3);
+            sig2_cmp = sigma * sigma;
           }
           res.energy = n2 * S(0.5);
           res.huber_weight = 1;
-          if (huber && n2 > sig2) {
+          if (huber && n2 > sig2_cmp) {
             const S nrm = std::sqrt(n2);
             res.huber_weight = sigma / nrm;
-            res.energy = sigma * nrm - sig2 * S(0.5);
+            res.energy = dev ? (S)fmaf((float)sigma, (float)nrm, -(float)(sig2_cmp * S(0.5))) : sigma * nrm - sig2 * S(0.5);
           }
           if (eval_jac) {
             for (int i = 0; i < P; ++i) {
@@ -621,6 +653,58 @@ struct Window {
     *step_sq = b;
   }
 
+  // updatePointStatuses, energy/problems/src/photometric_bundle_adjustment.cpp:322-406: 75 % quantile of the energies of
+  // kOk residuals of active landmarks (+ sigma^2 / 2) -> residuals above it are reset to {kOutlier} (quirk Q6), inlier
+  // counts, relative baseline, outlier flag.  Arithmetic in Scalar like the reference (Precision).
+  double update_point_statuses(int min_valid, double sigma_d) {
+    const int n = N();
+    std::vector<S> energies;
+    for (int r = 0; r < n; ++r) {
+      const Frame<S>& R = *frames[r];
+      for (int t = 0; t < n; ++t) {
+        if (t == r || frames[t]->is_marg) continue;
+        for (size_t l = 0; l < R.lms.size(); ++l)
+          if (!R.lms[l].is_marg && R.res[t][l].status == K_OK) energies.push_back(R.res[t][l].energy);
+      }
+    }
+    S thr = 0;
+    if (!energies.empty()) {
+      const size_t k = (size_t)((double)energies.size() * 0.75);
+      std::nth_element(energies.begin(), energies.begin() + (long)k, energies.end());
+      thr = energies[k] + (S)(sigma_d * sigma_d / 2);
+    }
+    std::vector<double> tw((size_t)n * 3);
+    for (int f = 0; f < n; ++f) {  // translation of tWorldAgent() = T_lin exp(eps[0:6])  (local_frame.hpp:525-527)
+      const SE3 T = mul(frames[f]->T_lin, expm(frames[f]->eps, 1.0));
+      for (int k = 0; k < 3; ++k) tw[3 * f + k] = T.t[k];
+    }
+    for (int r = 0; r < n; ++r) {
+      Frame<S>& R = *frames[r];
+      for (size_t l = 0; l < R.lms.size(); ++l) {
+        Landmark<S>& lm = R.lms[l];
+        if (lm.is_marg) continue;
+        uint32_t valid = 0;
+        for (int t = 0; t < n; ++t) {
+          if (t == r || frames[t]->is_marg) continue;
+          ResidualPoint<S>& rp = R.res[t][l];
+          if (rp.energy > thr) {
+            rp = ResidualPoint<S>();
+            rp.status = rp.cand = K_OUTLIER;
+          }
+          if (rp.status == K_OK) {
+            const double dx = tw[3 * r] - tw[3 * t], dy = tw[3 * r + 1] - tw[3 * t + 1], dz = tw[3 * r + 2] - tw[3 * t + 2];
+            const S dist = (S)sqrt(dx * dx + dy * dy + dz * dz);
+            lm.rel_baseline = std::max(lm.rel_baseline, lm.idepth * dist);
+            ++valid;
+          }
+        }
+        lm.n_inliers = valid;
+        if ((int)valid < min_valid) lm.is_outlier = true;
+      }
+    }
+    return (double)thr;
+  }
+
   void reject() {
     for (auto& f : frames) {
       for (int k = 0; k < 8; ++k) f->step[k] = 0;
@@ -833,6 +917,44 @@ void cpuref_change_statuses(void* h, int accept) {
   DISPATCH(w.change_statuses(accept), w.change_statuses(accept));
 }
 void cpuref_normal_solve(int n, const double* H, const double* b, double* x) { normal_solve(n, H, b, x); }
+void cpuref_set_device_ops(void* h, int on) {
+  AnyWindow* a = (AnyWindow*)h;
+  a->wf.device_ops = a->wd.device_ops = on != 0;
+}
+double cpuref_update_point_statuses(void* h, int min_valid, double sigma) {
+  AnyWindow* a = (AnyWindow*)h;
+  DISPATCH(return w.update_point_statuses(min_valid, sigma), return w.update_point_statuses(min_valid, sigma));
+}
+void cpuref_get_jac_valid(void* h, int r, int t, uint8_t* out) {
+  AnyWindow* a = (AnyWindow*)h;
+  DISPATCH(for (size_t l = 0; l < w.frames[r]->res[t].size(); ++l) out[l] = w.frames[r]->res[t][l].jac_valid,
+           for (size_t l = 0; l < w.frames[r]->res[t].size(); ++l) out[l] = w.frames[r]->res[t][l].jac_valid);
+}
+// plant a landmark state (e.g. the device's, float bits carried exactly by the doubles)
+void cpuref_set_idepths(void* h, int slot, int n, const double* idepth, const double* idepth_step) {
+  AnyWindow* a = (AnyWindow*)h;
+#define BODY                                                   \
+  auto& v = w.frames[slot]->lms;                               \
+  using SS = decltype(v[0].idepth);                            \
+  for (int l = 0; l < n && l < (int)v.size(); ++l) {           \
+    if (idepth) v[l].idepth = (SS)idepth[l];                   \
+    if (idepth_step) v[l].idepth_step = (SS)idepth_step[l];    \
+  }
+  DISPATCH(BODY, BODY);
+#undef BODY
+}
+void cpuref_get_landmark_flags(void* h, int slot, uint8_t* outlier, uint32_t* n_inliers, double* rel_baseline) {
+  AnyWindow* a = (AnyWindow*)h;
+#define BODY                                                   \
+  const auto& v = w.frames[slot]->lms;                         \
+  for (size_t l = 0; l < v.size(); ++l) {                      \
+    if (outlier) outlier[l] = v[l].is_outlier;                 \
+    if (n_inliers) n_inliers[l] = v[l].n_inliers;              \
+    if (rel_baseline) rel_baseline[l] = v[l].rel_baseline;     \
+  }
+  DISPATCH(BODY, BODY);
+#undef BODY
+}
 
 // residual block download in the same layout as dpba_download_residual_block (doubles)
 void cpuref_get_residuals(void* h, int r, int t, double* res, double* jref, double* jtgt, double* did, double* wgt,

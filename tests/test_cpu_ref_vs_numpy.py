@@ -99,3 +99,61 @@ def test_gn_iteration_matches_numpy_lm_body():
         assert np.linalg.norm(st - step) <= 1e-6 * np.linalg.norm(step) + 1e-12
         assert times[5] > 0
     cw.close()
+
+
+def test_update_point_statuses_port_matches_numpy_oracle():
+    """updatePointStatuses of the C++ restatement (double) against the NumPy oracle: threshold, reset residuals, inlier
+    counts, relative baselines, outlier flags (photometric_bundle_adjustment.cpp:322-406)."""
+    win = synth.make_window(n_frames=5, points_per_frame=200, seed=14)
+    flagged(win)
+    frames = O.frames_from_window(win)
+    cw = cpu_ref.CpuWindow(win, use_float=False, threads=2)
+    O.first_estimate_jacobians(frames)
+    cw.first_estimate()
+    O.evaluate_jacobians(frames, SIGMA, fej=True, evaluate_jacobians=False, new_point=True, huber=True)
+    O.change_residual_statuses(frames)
+    cw.evaluate(SIGMA, True, False)
+    cw.change_statuses(True)
+    thr_ref = O.update_point_statuses(frames, 1, SIGMA)
+    thr = cw.update_point_statuses(1, SIGMA)
+    assert abs(thr - thr_ref) <= 1e-9 * thr_ref
+    for i, f in enumerate(frames):
+        lf = cw.landmark_flags(i)
+        act = ~f.lm_marginalized
+        assert (lf["n_inliers"][act] == f.n_inliers[act]).all()
+        assert (lf["outlier"].astype(bool)[act] == f.lm_outlier[act]).all()
+        assert np.allclose(lf["rel_baseline"][act], f.rel_baseline[act], rtol=1e-9, atol=1e-12)
+        for j, g in enumerate(frames):
+            if i != j:
+                got = cw.residuals(i, j)
+                assert (got["status"] == f.residuals[g.id].status).all()
+    cw.close()
+
+
+def test_device_op_flavour_of_the_float_port_only_moves_last_bits():
+    """`device_ops` (the kernels' operation order: tap chain of fused multiply-adds, 8-lane butterfly, correctly rounded
+    Huber energy) must be the same arithmetic as the plain float build up to rounding, and leave the double build alone."""
+    win = synth.make_window(n_frames=4, points_per_frame=300, seed=15)
+    a = cpu_ref.CpuWindow(win, use_float=True)
+    b = cpu_ref.CpuWindow(win, use_float=True)
+    b.set_device_ops(True)
+    d0 = cpu_ref.CpuWindow(win, use_float=False)
+    d1 = cpu_ref.CpuWindow(win, use_float=False)
+    d1.set_device_ops(True)
+    for c in (a, b, d0, d1):
+        c.first_estimate()
+        c.evaluate(SIGMA, True, True)
+    n_huber = 0
+    for r in range(4):
+        for t in range(4):
+            if r != t:
+                x, y = a.residuals(r, t), b.residuals(r, t)
+                assert (x["cand"] == y["cand"]).all() and (a.jac_valid(r, t) == b.jac_valid(r, t)).all()
+                assert np.allclose(x["r"], y["r"], rtol=0, atol=2e-4)      # intensities 0..255: a few ulp of 256
+                assert np.allclose(x["e"], y["e"], rtol=2e-5, atol=1e-3)
+                n_huber += int((y["w"] < 1).sum())
+                for k in ("r", "e", "cand"):
+                    assert np.array_equal(d0.residuals(r, t)[k], d1.residuals(r, t)[k])
+    assert n_huber > 0  # the Huber branch was exercised
+    for c in (a, b, d0, d1):
+        c.close()

@@ -125,5 +125,9 @@ def test_cuda_path_matches_the_golden_outputs(gold):
     assert it == 7
     assert abs(e - float(gold["out_lm_energy"])) <= 2e-4 * abs(float(gold["out_lm_energy"]))
     s, _ = h2.get_state()
-    assert np.abs(s - gold["out_lm_state"]).max() <= 2e-5 * max(1.0, np.abs(gold["out_lm_state"]).max())
+    d = np.abs(s - gold["out_lm_state"]).reshape(n, 8)
+    # pose increments and the affine gain a: 2e-5 absolute (|eps| ~ 1e-3 .. 2e-2).  The affine offset b is subtracted from
+    # intensities of 0..255 whose fp32 spacing is 1.5e-5: it cannot be resolved below a few of those (1e-4 = 6 ulp).
+    assert d[:, :7].max() <= 2e-5, d[:, :7].max()
+    assert d[:, 7].max() <= 1e-4, d[:, 7].max()
     h.close(), h2.close()

@@ -1,18 +1,14 @@
-"""GPU checks of code paths that were written after the round-1 GPU budget was spent and have NOT run on hardware yet.
-
-They are opt-in (DPBA_TEST_EXPERIMENTAL=1) and the options they exercise are off by default, so the default `-m gpu` run
-only covers validated code; the file sorts last so that nothing here can disturb the parity suite.  Once a path has
-passed on a B200 its option becomes the default and its test moves into tests/test_gpu_parity.py.
+"""GPU checks of the device-side paths next to the solve: the exact radix-select quantile of updatePointStatuses against the
+host nth_element path, the reference depth maps of the coarse tracker and the mean-square optical flow of the keyframe
+decision against their oracles.  (Round 1 wrote them after its GPU minutes were spent; they first ran -- and passed -- on a
+B200 in round 2, which is when the device quantile became the default.)
 """
-import os
-
 import numpy as np
 import pytest
 
 from dsopp_b200 import synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("DPBA_TEST_EXPERIMENTAL"), reason="unvalidated paths are opt-in")]
+pytestmark = pytest.mark.gpu
 
 SIGMA = 20.0
 
