@@ -4,3 +4,7 @@ d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print("value %.1f M/s  us/iter %.1f  e2e %.1f M/s (%.2f ms/step)" % (d["value"] / 1e6, d["us_per_gn_iter"], d["e2e"]["value"] / 1e6, d["e2e"]["ms_per_step"]))
 print(" ".join("%s=%.1f" % (k, 1e3 * v["ms_total"] / v["launches"]) for k, v in d["kernel_ms"].items()))
 print("roofline frac fused %.3f sweep %.3f big %s" % (d["roofline"]["frac"], d["roofline_sweep"]["frac"], d["roofline_sweep_big"] and round(d["roofline_sweep_big"]["frac"], 3)))
+if d.get("parity_check"):
+    print("parity_check", d["parity_check"])
+if d.get("e2e_raw_frames"):
+    print("e2e raw frames %.1f M/s (%.2f ms/step)" % (d["e2e_raw_frames"]["value"] / 1e6, d["e2e_raw_frames"]["ms_per_step"]))
