@@ -25,7 +25,12 @@ AB_REG = (1e12, 1e8)
 FIXED_REG = 1e16
 RTOL_SYS = 5e-6   # H blocks: |d| <= RTOL_SYS * max|H|  (fp64 accumulation of fp32 terms)
 RTOL_B = 2e-4     # b blocks: |d| <= RTOL_B * max|b|    (cancelling sum, fp32 residual floor)
-RTOL_E = 2e-6     # energy of a sweep: relative
+# Energy of one sweep away from the optimum.  The device holds the per-pair constants (K_t T K_r^-1, brightness scale) in
+# fp32: they differ from the oracle's doubles by ~6e-8 relative, i.e. the sweep sees relative poses perturbed by ~1e-7, and
+# at the (deliberately perturbed) initial state the energy has a gradient of |b| ~ 1e6 per unit of pose -- a first-order
+# difference of |b| * 1e-7 * (a few), measured 9e-6 of E.  At the optimum the gradient vanishes and the LM energies below
+# agree to 1e-6 (tolerance 2e-5).
+RTOL_E = 5e-5
 CONFIGS = {
     "configs1_8x2000": dict(n_frames=8, points_per_frame=2000, seed=0, ab_scale=0.0),
     "configs3_8x20000": dict(n_frames=8, points_per_frame=20000, seed=1, ab_scale=0.0),

@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_check.sh [tag]'
 tag=${1:-check}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/${tag}_gpu_tests.log 2>&1
+timeout 900 python -m pytest tests -q -m gpu > gpurun_out/${tag}_gpu_tests.log 2>&1
 echo "gpu tests exit $?" >> gpurun_out/${tag}_gpu_tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/${tag}_smoke.log
