@@ -42,6 +42,12 @@ def main():
     say("linearize done")
     e, n = h.evaluate(20.0, True, True)
     say("evaluate done")
+    # updatePointStatuses over the union of the shards: the device radix select sums its 256-bin histograms over the ranks
+    # (identical inputs -> identical per-residual energies -> the very same threshold float as the unsharded window)
+    h.change_residual_statuses(True)
+    thr = h.update_point_statuses(1, 20.0)
+    inl = [h.get_landmarks(i)["n_inliers"].copy() for i in range(win.n_frames)]
+    say(f"update_point_statuses done, threshold {thr!r}")
     h.first_estimate()
     E, it, conv, nv = h.solve_lm(20.0)
     say("solve_lm done")
@@ -100,6 +106,13 @@ def main():
         ref.first_estimate()
         Hp1, bp1, Hs1, bs1 = ref.linearize(20.0, True, True, False)
         e1, n1 = ref.evaluate(20.0, True, True)
+        ref.change_residual_statuses(True)
+        thr1 = ref.update_point_statuses(1, 20.0)
+        print(f"outlier threshold sharded {thr!r} vs unsharded {thr1!r}")
+        ok &= np.float32(thr) == np.float32(thr1)
+        for i in range(win.n_frames):
+            full = ref.get_landmarks(i)["n_inliers"]
+            ok &= np.array_equal(full[sharding.shard_indices(len(full), 0, world)], inl[i])
         ref.first_estimate()
         E1, it1, _, nv1 = ref.solve_lm(20.0)
         eps1, _ = ref.get_state()
@@ -122,9 +135,14 @@ def main():
     dist.barrier()
     torch.cuda.synchronize()
     code = 0 if flag.item() else 1
+    # ordered shutdown and a normal exit: the handle first (its captured graph, then its communicator), then torch's group
+    h.close()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
     say("done, exit code", code)
     sys.stdout.flush()
-    os._exit(code)  # no NCCL / CUDA destructor can block a rank at exit
+    sys.exit(code)
 
 
 if __name__ == "__main__":
