@@ -87,6 +87,7 @@ SIGNATURES = {
     "dpba_build_pyramid": (C.c_int, [_P, _P, _P, _P, _I, _P]),
     "dpba_remove_frame": (C.c_int, [_P, _I]),
     "dpba_num_frames": (C.c_int, [_P]),
+    "dpba_synchronize": (C.c_int, [_P]),
     "dpba_set_frame_linearization": (C.c_int, [_P, _I, _P, _P]),
     "dpba_set_frame_flags": (C.c_int, [_P, _I, _I, _I]),
     "dpba_set_frame_marginalized": (C.c_int, [_P, _I, _I]),
@@ -231,6 +232,9 @@ class Handle:
         ptrs = (C.c_void_p * levels)(*[o.ctypes.data for o in outs])
         self._ck(self.lib.dpba_build_pyramid(self.h, _ptr(gray), _ptr(lut), _ptr(vignetting), levels, C.cast(ptrs, C.c_void_p)))
         return outs
+
+    def synchronize(self):
+        self._ck(self.lib.dpba_synchronize(self.h))
 
     def remove_frame(self, slot):
         self._ck(self.lib.dpba_remove_frame(self.h, slot))

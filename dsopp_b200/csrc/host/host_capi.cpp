@@ -1,6 +1,7 @@
 // Flat C shim over the C++ host side (CudaPhotometricBundleAdjustment, the LM driver and NormalLinearSystem) so
 // that pytest / bench.py can drive exactly the code a C++ caller would link.  Not part of the drop-in boundary:
 // that is include/dsopp_cuda_pba.h.
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -209,13 +210,28 @@ struct dpbah_window_io {
   // optional: RAW 8-bit frames instead of `images` (dpba_push_frame_raw: photometric table, gradients on the device)
   const uint8_t* const* raw_gray;   // [n] H*W, or null
   const float* photometric_lut;     // [256]
+  // host wall-clock per phase [ms]: 0 remove, 1 push frames, 2 landmarks + statuses + state, 3 firstEstimate + solve
+  // (includes waiting for the queued uploads), 4 readback.  sync_phases != 0 drains the stream after every phase so
+  // that the device time of the asynchronous uploads is attributed to its own phase (diagnostics only).
+  double phase_ms[5];
+  int32_t sync_phases;
 };
 
 __attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dpbah_window_io* io, int width, int height) {
   GUARD({
     const int n = io->n_frames;
     int64_t h2d = 0, d2h = 0;
+    using clk = std::chrono::steady_clock;
+    auto t_prev = clk::now();
+    int phase = 0;
+    auto mark = [&]() {
+      if (io->sync_phases) dpba_check(h, dpba_synchronize(h));
+      const auto t = clk::now();
+      io->phase_ms[phase++] = std::chrono::duration<double, std::milli>(t - t_prev).count();
+      t_prev = t;
+    };
     while (dpba_num_frames(h) > 0) dpba_check(h, dpba_remove_frame(h, 0));
+    mark();
     const size_t npx = (size_t)width * height;
     for (int f = 0; f < n; ++f) {
       if (io->raw_gray) {
@@ -229,6 +245,7 @@ __attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dp
         h2d += (int64_t)npx * 12 + (io->masks[f] ? (int64_t)npx : 0);
       }
     }
+    mark();
     std::vector<double> zero(8 * (size_t)n, 0.0);
     for (int f = 0; f < n; ++f) {
       const int m = io->n_landmarks[f];
@@ -238,6 +255,7 @@ __attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dp
     }
     dpba_check(h, dpba_set_state(h, io->eps0, zero.data()));
     h2d += 2 * 8 * (int64_t)n * 8;
+    mark();
     dpba_check(h, dpba_first_estimate(h));
     dpba_lm_result r;
     dpba_check(h, dpba_solve_lm(h, &io->lm, nullptr, nullptr, 0.0, &r));
@@ -245,6 +263,7 @@ __attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dp
     io->iterations = r.iterations;
     io->n_valid = r.number_of_valid_residuals;
     io->converged = r.converged;
+    mark();
     dpba_check(h, dpba_get_state(h, io->eps_out, zero.data()));
     d2h += 2 * 8 * (int64_t)n * 8;
     for (int f = 0; f < n; ++f) {
@@ -254,6 +273,7 @@ __attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dp
       dpba_check(h, dpba_get_frame_statuses(h, f, m, io->statuses_out + (size_t)f * n, nullptr));
       d2h += (int64_t)m * (4 * 4 + 1) + (int64_t)m * (n - 1);
     }
+    mark();
     io->h2d_bytes = h2d;
     io->d2h_bytes = d2h;
   });

@@ -869,6 +869,12 @@ int dpba_remove_frame(dpba_handle* h, int32_t slot) {
 
 int dpba_num_frames(const dpba_handle* h) { return h ? h->n_frames : DPBA_E_INVALID; }
 
+int dpba_synchronize(dpba_handle* h) {
+  REQUIRE(h, "null handle");
+  CK(cudaStreamSynchronize(h->stream));
+  return DPBA_SUCCESS;
+}
+
 int dpba_set_frame_linearization(dpba_handle* h, int32_t slot, const double T[12], const double ab0[2]) {
   REQUIRE(h, "null handle");
   REQUIRE(slot >= 0 && slot < h->n_frames && T && ab0, "bad argument");

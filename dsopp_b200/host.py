@@ -117,7 +117,7 @@ class _WindowIOStruct(C.Structure):
                 ("inv_hdd_out", _P), ("rel_baseline_out", _P), ("flags_out", _P), ("n_inliers_out", _P),
                 ("statuses_out", _P), ("energy", C.c_double), ("iterations", C.c_int32), ("n_valid", C.c_int32),
                 ("converged", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("raw_gray", _P),
-                ("photometric_lut", _P)]
+                ("photometric_lut", _P), ("phase_ms", C.c_double * 5), ("sync_phases", C.c_int32)]
 
 
 class WindowStep:

@@ -127,6 +127,9 @@ int dpba_build_pyramid(dpba_handle* h, const uint8_t* gray, const float* photome
  * later slots shift down by one. */
 int dpba_remove_frame(dpba_handle* h, int32_t slot);
 int dpba_num_frames(const dpba_handle* h);
+/* Drains the handle's stream: every upload queued by the set_* / push_* calls has landed and borrowed page-locked
+ * buffers may be reused (the reference has no counterpart: its pushFrame copies synchronously) */
+int dpba_synchronize(dpba_handle* h);
 /* relinearizeSystem (photometric_bundle_adjustment.cpp:311-316): new linearisation point / affine0, eps := 0 */
 int dpba_set_frame_linearization(dpba_handle* h, int32_t slot, const double T_w_agent_lin[12],
                                  const double affine_brightness0[2]);

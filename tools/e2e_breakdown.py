@@ -1,61 +1,54 @@
-"""Where the end-to-end step of bench.py spends its time (run under gpurun): wall-clock per phase with a device
-synchronisation after each phase, plus the raw pinned H2D bandwidth of this box for scale."""
-import os, sys, time
+"""Where the end-to-end step (dpbah_solve_window, bench.py's `e2e`) spends its time: host wall-clock per phase, once with
+the asynchronous uploads left in flight (what bench.py times) and once with the stream drained after every phase.
+   python tools/e2e_breakdown.py [--raw]"""
+import os
+import sys
+
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from dsopp_b200 import capi, synth
-import bench
 
-win = bench.build_window(1)
-n = win.n_frames
-h = capi.upload_window(win)
-eps0 = np.concatenate([f.state_eps for f in win.frames])
-keep, host_frames, host_status = [], [], []
-for i, f in enumerate(win.frames):
-    arrs = [bench.pin(a) for a in (f.image.astype(np.float32), f.mask, f.uv.astype(np.float32), f.idepth.astype(np.float32), f.patch.astype(np.float32), f.flags)]
-    keep += [a[1] for a in arrs]
-    host_frames.append((f,) + tuple(a[0] for a in arrs))
-    rows = {}
-    for t in range(n):
-        if t != i:
-            a, tk = bench.pin(win.statuses[(i, t)]); keep.append(tk); rows[t] = a
-    host_status.append(rows)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dsopp_b200 import capi, host, synth  # noqa: E402
 
-def sync():
-    torch.cuda.synchronize()
+PHASES = ["remove", "push_frames", "landmarks+statuses+state", "first_estimate+solve", "readback"]
 
-def step(tm):
-    t0 = time.perf_counter()
-    for _ in range(h.n_frames):
-        h.remove_frame(0)
-    for (f, img, msk, uv, idp, pat, flg) in host_frames:
-        h.push_frame(f.frame_id, img, msk, f.T_w_lin, f.exposure, f.ab0, f.intr, f.fixed)
-    t1 = time.perf_counter(); sync(); t2 = time.perf_counter()
-    for i, (f, img, msk, uv, idp, pat, flg) in enumerate(host_frames):
-        h.set_landmarks(i, uv, idp, pat, flg)
-        h.set_frame_statuses(i, host_status[i])
-    h.set_state(eps0, np.zeros_like(eps0))
-    t3 = time.perf_counter(); sync(); t4 = time.perf_counter()
-    h.first_estimate()
-    h.solve_lm(20.0, max_it=7, min_it=7, ftol=0.0, ptol=0.0)
-    t5 = time.perf_counter()
-    h.get_state()
-    for i in range(n):
-        h.get_landmarks(i)
-        h.get_frame_statuses(i)
-    t6 = time.perf_counter()
-    tm.append([t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5, t6 - t0])
 
-tm = []
-for i in range(13):
-    step(tm)
-tm = np.array(tm[3:]) * 1e3
-print("ms: push_frame calls %.3f | drain %.3f | landmarks+statuses calls %.3f | drain %.3f | first_estimate+solve %.3f | readback %.3f | total %.3f" % tuple(np.median(tm, axis=0)))
-# raw H2D for scale
-src = torch.empty(32 << 20, dtype=torch.uint8).pin_memory(); dst = torch.empty(32 << 20, dtype=torch.uint8, device="cuda")
-for _ in range(3): dst.copy_(src, non_blocking=True)
-sync(); t0 = time.perf_counter()
-for _ in range(10): dst.copy_(src, non_blocking=True)
-sync(); dt = (time.perf_counter() - t0) / 10
-print("raw pinned H2D 32 MiB: %.3f ms = %.1f GB/s" % (dt * 1e3, (32 << 20) / dt / 1e9))
+def main():
+    raw = "--raw" in sys.argv
+    win = synth.make_window(n_frames=8, points_per_frame=2000, seed=0, ab_scale=0.0)
+    h = capi.upload_window(win)
+    keep = []
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+
+    n = win.n_frames
+    frames = [dict(frame_id=f.frame_id, image=pinned(f.image.astype(np.float32)), mask=pinned(f.mask), T_w_lin=f.T_w_lin,
+                   exposure=f.exposure, ab0=f.ab0, intr=f.intr, fixed=f.fixed, uv=pinned(f.uv.astype(np.float32)),
+                   idepth=pinned(f.idepth.astype(np.float32)), patch=pinned(f.patch.astype(np.float32)), flags=pinned(f.flags))
+              for f in win.frames]
+    st = {k: pinned(v) for k, v in win.statuses.items()}
+    eps0 = np.concatenate([f.state_eps for f in win.frames])
+    kw = dict(max_it=7, min_it=7, ftol=0.0, ptol=0.0, alloc=lambda s, d: pinned(np.zeros(s, d)))
+    if raw:
+        kw.update(raw_gray=[pinned(np.clip(np.rint(f.image[..., 0]), 0, 255).astype(np.uint8)) for f in win.frames],
+                  photometric_lut=np.arange(256, dtype=np.float32))
+    io = host.WindowStep(h, frames, st, eps0, **kw)
+    for sync in (0, 1):
+        io.io.sync_phases = sync
+        acc = np.zeros(5)
+        for i in range(3 + 20):
+            io.run()
+            if i >= 3:
+                acc += np.array(list(io.io.phase_ms))
+        acc /= 20
+        print(f"{'raw 8-bit frames' if raw else '{I,dx,dy} frames'}, sync after every phase = {sync}: total {acc.sum():.3f} ms; " +
+              ", ".join(f"{p} {v:.3f}" for p, v in zip(PHASES, acc)))
+    print("h2d bytes", io.io.h2d_bytes, "d2h bytes", io.io.d2h_bytes)
+    h.close()
+
+
+if __name__ == "__main__":
+    main()

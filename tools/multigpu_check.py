@@ -42,12 +42,6 @@ def main():
     say("linearize done")
     e, n = h.evaluate(20.0, True, True)
     say("evaluate done")
-    # updatePointStatuses over the union of the shards: the device radix select sums its 256-bin histograms over the ranks
-    # (identical inputs -> identical per-residual energies -> the very same threshold float as the unsharded window)
-    h.change_residual_statuses(True)
-    thr = h.update_point_statuses(1, 20.0)
-    inl = [h.get_landmarks(i)["n_inliers"].copy() for i in range(win.n_frames)]
-    say(f"update_point_statuses done, threshold {thr!r}")
     h.first_estimate()
     E, it, conv, nv = h.solve_lm(20.0)
     say("solve_lm done")
@@ -101,18 +95,30 @@ def main():
     eps, _ = h.get_state()
     idepth = [h.get_landmarks(i)["idepth"] for i in range(win.n_frames)]
     ok = True
+
+    def reset(hh, rk, ws):
+        sh = [sharding.shard_indices(len(f.idepth), rk, ws) for f in win.frames]
+        for i, f in enumerate(win.frames):
+            hh.set_landmarks(i, f.uv[sh[i]], f.idepth[sh[i]], f.patch[sh[i]], f.flags[sh[i]])
+        for (r_, t_), st in win.statuses.items():
+            hh.set_statuses(r_, t_, st[sh[r_]])
+        hh.set_state(np.concatenate([f.state_eps for f in win.frames]), np.zeros(8 * win.n_frames))
+        hh.first_estimate()
+        hh.evaluate(20.0, True, True)
+        hh.change_residual_statuses(True)
+
+    # updatePointStatuses over the union of the shards, from the initial window again: the device radix select sums its
+    # 256-bin histograms over the ranks (identical inputs -> identical per-residual energies -> the very same threshold
+    # float and inlier counts as the unsharded window)
+    reset(h, rank, world)
+    thr = h.update_point_statuses(1, 20.0)
+    inl = [h.get_landmarks(i)["n_inliers"].copy() for i in range(win.n_frames)]
+    say(f"update_point_statuses done, threshold {thr!r}")
     if rank == 0:
         ref = capi.upload_window(win, device=local)
         ref.first_estimate()
         Hp1, bp1, Hs1, bs1 = ref.linearize(20.0, True, True, False)
         e1, n1 = ref.evaluate(20.0, True, True)
-        ref.change_residual_statuses(True)
-        thr1 = ref.update_point_statuses(1, 20.0)
-        print(f"outlier threshold sharded {thr!r} vs unsharded {thr1!r}")
-        ok &= np.float32(thr) == np.float32(thr1)
-        for i in range(win.n_frames):
-            full = ref.get_landmarks(i)["n_inliers"]
-            ok &= np.array_equal(full[sharding.shard_indices(len(full), 0, world)], inl[i])
         ref.first_estimate()
         E1, it1, _, nv1 = ref.solve_lm(20.0)
         eps1, _ = ref.get_state()
@@ -127,6 +133,13 @@ def main():
             full = ref.get_landmarks(i)["idepth"]
             mine = full[sharding.shard_indices(len(full), 0, world)]
             ok &= np.abs(mine - idepth[i]).max() < 5e-5
+        reset(ref, 0, 1)
+        thr1 = ref.update_point_statuses(1, 20.0)
+        print(f"outlier threshold sharded {thr!r} vs unsharded {thr1!r}")
+        ok &= bool(np.float32(thr) == np.float32(thr1))
+        for i in range(win.n_frames):
+            full = ref.get_landmarks(i)["n_inliers"]
+            ok &= bool(np.array_equal(full[sharding.shard_indices(len(full), 0, world)], inl[i]))
         print("MULTIGPU_CHECK", "PASS" if ok else "FAIL", f"world={world}")
         ref.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
