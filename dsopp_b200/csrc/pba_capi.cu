@@ -131,6 +131,12 @@ struct dpba_handle {
   uint8_t* raw_u8 = nullptr;     // lazily: raw gray image + vignetting (2 * W * H bytes)
   float* lut_dev = nullptr;      // lazily: photometric calibration table (256 floats)
   float* stage = nullptr;  // image upload staging (device)
+  // {I,dx,dy} uploads are pipelined: the DMA of keyframe k + 1 (copy stream, staging buffer k + 1 mod 2) runs while the
+  // pack kernel of keyframe k reads its staging buffer on the main stream
+  float* stage_alt = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+  int stage_idx = 0;
   float* stage_h = nullptr;  // pinned staging for images
   float *m_r = nullptr, *m_jref = nullptr, *m_jtgt = nullptr, *m_did = nullptr, *m_w = nullptr;
   bool linearized = false;
@@ -496,17 +502,36 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
   const bool pinned = channels < 0 || (cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost);
   cudaGetLastError();
   const float* src = image;
-  if (channels > 0) {
+  const bool mask_all = !mask || memchr(mask, 0, npx) == nullptr;
+  if (channels == 3) {
     if (!pinned) {
+      CK(cudaStreamSynchronize(h->copy_stream));  // the previous pageable push may still be reading stage_h
       memcpy(h->stage_h, image, npx * channels * sizeof(float));
       src = h->stage_h;
     }
-    CK(cudaMemcpyAsync(h->stage, src, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    const int sb = h->stage_idx;
+    h->stage_idx ^= 1;
+    float* dst = sb ? h->stage_alt : h->stage;
+    CK(cudaStreamWaitEvent(h->copy_stream, h->stage_free[sb], 0));  // its last reader (a pack kernel) has finished
+    CK(cudaMemcpyAsync(dst, src, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->stage_ready[sb], h->copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->stage_ready[sb], 0));
+    pba::launch_pack_image(dst, h->img[phys], (int)npx, W, h->stream);
+    CK(cudaEventRecord(h->stage_free[sb], h->stream));
+  } else {
+    if (channels > 0) {
+      if (!pinned) {
+        memcpy(h->stage_h, image, npx * channels * sizeof(float));
+        src = h->stage_h;
+      }
+      CK(cudaMemcpyAsync(h->stage, src, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    }
+    pba::launch_pixelinfo(channels > 0 ? h->stage : image, h->img[phys], W, H, h->stream);  // -1: device plane
+    if (channels > 0) CK(cudaEventRecord(h->stage_free[0], h->stream));  // h->stage is staging buffer 0 of the pipeline
   }
-  if (channels == 3) pba::launch_pack_image(h->stage, h->img[phys], (int)npx, W, h->stream);
-  else pba::launch_pixelinfo(channels > 0 ? h->stage : image, h->img[phys], W, H, h->stream);  // -1: device plane
   CK(cudaGetLastError());
-  if (mask) CK(cudaMemcpyAsync(h->mask[phys], mask, npx, cudaMemcpyHostToDevice, h->stream));
+  // a mask without a zero is never looked at by the sweeps (WindowDev::mask_all): no need to send it over PCIe
+  if (!mask_all) CK(cudaMemcpyAsync(h->mask[phys], mask, npx, cudaMemcpyHostToDevice, h->stream));
   else CK(cudaMemsetAsync(h->mask[phys], 255, npx, h->stream));
   // new residual vectors of this frame start as kOk until dpba_set_statuses says otherwise: the rows (phys -> p) are
   // contiguous, the rows (p -> phys) are one strided 2-D memset per array
@@ -515,7 +540,7 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
   CK(cudaGetLastError());
   // pageable images went through stage_h, which the next push reuses; page-locked images are BORROWED until the next
   // synchronising call (solve / get_*), exactly as LocalFrame borrows its PixelMap pointers (local_frame.hpp:44,325)
-  if (!pinned) CK(cudaStreamSynchronize(h->stream));
+  if (!pinned && channels != 3) CK(cudaStreamSynchronize(h->stream));
   FrameHost& F = h->fr[h->n_frames];
   F = FrameHost();
   F.id = frame_id;
@@ -526,8 +551,7 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
   F.ab0[1] = ab0[1];
   memcpy(F.intr, intr, sizeof(F.intr));
   F.fixed = fixed ? 1 : 0;
-  F.mask_all = 1;
-  if (mask) F.mask_all = memchr(mask, 0, npx) == nullptr;
+  F.mask_all = mask_all ? 1 : 0;
   h->phys_used[phys] = true;
   h->linearized = false;
   return h->n_frames++;
@@ -664,6 +688,12 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   CKC(cudaMalloc(&h->step_dev, MAXD * sizeof(double)));
   CKC(cudaMalloc(&h->pair_dist, PBA_MAXF * PBA_MAXF * sizeof(float)));
   CKC(cudaMalloc(&h->stage, npx * 3 * sizeof(float)));
+  CKC(cudaMalloc(&h->stage_alt, npx * 3 * sizeof(float)));
+  CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) {
+    CKC(cudaEventCreateWithFlags(&h->stage_ready[k], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->stage_free[k], cudaEventDisableTiming));
+  }
   CKC(cudaMallocHost(&h->stage_h, npx * 3 * sizeof(float)));
   // one window's worth of landmark records (52 B each, 256 B aligned per array) and status rows, twice
   h->arena_cap = 2 * ((size_t)cfg->max_frames * (mp * 64 + 1024) + (size_t)cfg->max_frames * cfg->max_frames * (mp + 256)) +
@@ -702,6 +732,15 @@ int dpba_destroy(dpba_handle* h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->fork_ev) cudaEventDestroy(e);
   if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->copy_stream) {
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamDestroy(h->copy_stream);
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (h->stage_ready[k]) cudaEventDestroy(h->stage_ready[k]);
+    if (h->stage_free[k]) cudaEventDestroy(h->stage_free[k]);
+  }
+  cudaFree(h->stage_alt);
   for (int p = 0; p < PBA_MAXF; ++p) {
     cudaFree(h->img[p]);
     cudaFree(h->mask[p]);
@@ -806,6 +845,7 @@ int dpba_build_pyramid(dpba_handle* h, const uint8_t* gray, const float* photome
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(out_I_dx_dy[l], h->stage, (size_t)W * H * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));  // h->stage is reused by the next level
+      CK(cudaEventRecord(h->stage_free[0], h->stream));
     }
     if (l + 1 < levels) {
       pba::launch_downscale(cur, nxt, W, H, h->stream);
