@@ -247,6 +247,12 @@ def run_ours(args):
     h = capi.upload_window(win, device=local, rank=rank, world_size=world)
     if args.fused_min_blocks:
         h.set_option("fused_min_blocks", args.fused_min_blocks)
+    if args.fused_version:
+        h.set_option("fused_version", args.fused_version)
+    if args.merged_tail >= 0:
+        h.set_option("merged_tail", args.merged_tail)
+    if args.pdl >= 0:
+        h.set_option("pdl", args.pdl)
     if args.speculative_multi_gpu >= 0:
         h.set_option("speculative_multi_gpu", args.speculative_multi_gpu)
     if args.fused_prefetch >= 0:
@@ -550,6 +556,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-big-sweep", action="store_true", help="skip the 20000-points/KF materialising-sweep roofline")
     ap.add_argument("--fused-min-blocks", type=int, default=0, help="tuning A/B: 3 or 4 resident CTAs/SM for the fused linearise")
+    ap.add_argument("--fused-version", type=int, default=0, help="A/B: 1 = first-generation fused linearise (8 lanes per patch), 2 = one thread per patch-residual")
+    ap.add_argument("--pdl", type=int, default=-1, help="A/B: programmatic dependent launch between the device-LM kernels (default 1)")
+    ap.add_argument("--merged-tail", type=int, default=-1, help="A/B: 1 = three launches per LM iteration (default), 0 = the eight-kernel sequence")
     ap.add_argument("--speculative-multi-gpu", type=int, default=-1, help="A/B: one-allreduce speculative device LM for N > 1")
     ap.add_argument("--peer-exchange", action="store_true",
                     help="N > 1: sum the exchange block with the library's NVLink mailbox kernel instead of ncclAllReduce")

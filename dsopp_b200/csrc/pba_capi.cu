@@ -116,6 +116,11 @@ struct dpba_handle {
   int* fixed_h = nullptr;            // pinned
   bool use_graph = true;
   bool speculative = true;           // dpba_solve_lm: trial evaluation == next linearisation under force_accept
+  // round 2 experiment, option "merged_tail": three launches per iteration (sweep with the accept / back-substitution fold,
+  // k_reduce_system, k_lm_solve) instead of eight kernels on two graph branches.  Measured SLOWER on B200 (94 against 89 us
+  // per iteration, profiles/r02_ab.md): the single-CTA k_lm_solve serialises what the two-branch graph overlaps, so the
+  // eight-kernel sequence stays the default.
+  bool merged_tail = false;
   bool speculative_multi = true;     // ... also with world_size > 1 (one allreduce per iteration); 2-GPU check: same state and energy as the two-sweep sequence
   cudaGraphExec_t lm_graph_exec = nullptr;
   std::vector<long long> lm_graph_key;
@@ -1532,6 +1537,47 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
   // energy) is what the reference computes; only the auxiliary per-landmark fields (hpd, b_d, inv_hdd) are one accepted
   // step FRESHER than the reference's at the end -- EigenPBA::solve recomputes them in its uncertainty pass anyway
   // (eigen_photometric_bundle_adjustment.cpp:91-98).  After a rejected step they are recomputed at the restored state.
+  // ---- round 2: the same speculative sequence in THREE launches per iteration ------------------------------------------
+  //   sweep_k        k_linearize_fused2 with the fold: closes trial k - 1 for its landmarks / residuals (accept or reject),
+  //                  back-substitutes step k, evaluates + linearises the trial state of step k
+  //   reduce_k       k_reduce_system: core reduction, H_pp block assembly, Schur partial reduction
+  //   solve_k        k_lm_solve: energy decision of trial k (k = 0: initial energy), calculateStep k + 1, pair constants
+  // instead of eight kernels on two graph branches; nothing but the three is on the critical path.
+  if (h->speculative && od.force_accept && !multi && h->merged_tail && pba::fused_version() == 2) {
+    const int n_pairs = N * (N - 1);
+    FusedShape shape{0, 0};
+    for (int k = 0; k <= od.max_it; ++k) {
+      const bool more = k < od.max_it;
+      {
+        ProfScope ps(h, 0);
+        shape = pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 1, k ? h->step_dev : nullptr);
+      }
+      {
+        ProfScope ps(h, 8);
+        pba::launch_reduce_system(w, fej, rb, shape, more ? 1 : 0, s, h->ctl);
+      }
+      {
+        ProfScope ps(h, 7);
+        pba::launch_lm_solve(h->ctl, h->lmopt, h->fparams, h->fixed_dev, N, rb.scal, ro, Hm, bm, h->step_dev,
+                             k == 0 ? pba::LM_ENERGY_INITIAL : pba::LM_ENERGY_TRIAL, rb.core, n_pairs,
+                             k ? rb.n_part : nullptr, k ? shape.chunks * N : 0, 1, more ? 1 : 0, h->pairs, h->pasm, s);
+      }
+    }
+    {  // the last trial's acceptStep() / rejectStep() has no following sweep to ride on
+      ProfScope ps(h, 11);
+      pba::launch_accept(w, 0, nullptr, s, h->ctl, 1);
+    }
+    pairs();
+    {
+      ProfScope ps(h, 0);
+      pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 3);  // only after a rejected step (see below)
+    }
+    if ((rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
+    return 0;
+  }
   if (h->speculative && od.force_accept && !multi) {
     const int n_pairs = N * (N - 1);
     auto spec_linearize = [&](int ctl_mode) {
@@ -1777,7 +1823,8 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   // replay it (one cudaGraphLaunch instead of ~110 launches per solve); all inputs travel through pinned buffers.
   std::vector<long long> key = {N, od.max_it, od.fej, H_marg != nullptr, h->world, (long long)h->profiling,
                                 (long long)(h->speculative && od.force_accept), (long long)h->speculative_multi,
-                                (long long)llround(od.sigma * 1e6), (long long)h->peer_on};
+                                (long long)llround(od.sigma * 1e6), (long long)h->peer_on, (long long)h->merged_tail,
+                                (long long)pba::fused_version()};
   for (int f = 0; f < N; ++f) {  // every per-frame field of WindowDev (the captured kernels hold it BY VALUE)
     key.push_back(h->fr[f].n_lm);
     key.push_back(h->fr[f].phys);
@@ -1915,6 +1962,21 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "pdl")) {  // process-wide: programmatic dependent launch between the kernels of the device LM
+    pba::set_pdl(value != 0);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "merged_tail")) {
+    h->merged_tail = value != 0;
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "fused_version")) {  // process-wide: 2 = one thread per patch-residual (default), 1 = 8 lanes per patch
+    pba::set_fused_version((int)value);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
   if (!strcmp(name, "fused_min_blocks")) {  // process-wide: 4 (64 registers per thread) or 3 (96)
     pba::set_fused_min_blocks((int)value);
     h->lm_graph_key.clear();
@@ -1924,6 +1986,15 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
 }
 
 int64_t dpba_launch_count(void) { return (int64_t)pba::launch_count(); }
+
+int dpba_debug_stamps(int32_t enable, int64_t out[64]) {
+  long long tmp[64];
+  cudaDeviceSynchronize();
+  pba::debug_stamps(enable, tmp);
+  if (out)
+    for (int i = 0; i < 64; ++i) out[i] = tmp[i];
+  return DPBA_SUCCESS;
+}
 
 int dpba_profile_enable(dpba_handle* h, int32_t on) {
   REQUIRE(h, "null handle");

@@ -129,6 +129,14 @@ void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int 
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
                     const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s);
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
+// round 2: energy decision + calculateStep + per-pair constants of the trial state in one single-CTA launch
+void launch_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, double* scal,
+                     ReduceBuf rb, const double* Hmarg, const double* bmarg, double* step_dev, int kind,
+                     const double* e_part, int n_e, const double* n_part, int n_n, int from_core, int with_step,
+                     PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
+// round 2: core reduction + block assembly + Schur partial reduction in one launch
+void launch_reduce_system(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, int with_system, cudaStream_t s,
+                          const LmCtl* ctl = nullptr);
 void launch_clear_frame_rows(uint8_t* status, uint8_t* cand, uint8_t* jac_valid, float* energy, int phys, int mp,
                              int max_frames, cudaStream_t s);
 void launch_pack_image(const float* src3, float4* dst, int n_px, int W, cudaStream_t s);
@@ -142,8 +150,14 @@ int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, d
 void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, int n_e, const double* n_part, int n_n,
                         double* scal, cudaStream_t s, int core_frames = 0);
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s);
+// fold_step (second-generation kernel, device LM only): the pose step whose back-substitution -- together with the
+// acceptStep / rejectStep of the previous trial -- this sweep performs for its own landmarks before evaluating; the
+// per-CTA norm partials go to rb.n_part [n_frames * shape.chunks] (double2)
 FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
-                                  cudaStream_t s, const LmCtl* ctl = nullptr, int ctl_mode = 2);
+                                  cudaStream_t s, const LmCtl* ctl = nullptr, int ctl_mode = 2,
+                                  const double* fold_step = nullptr);
+int fused_version();
+void debug_stamps(int enable, long long out[64]);
 void launch_linearize_from_materialized(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
 int launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,
@@ -170,6 +184,8 @@ long long launch_count();
 void add_launches(long long n);
 void set_schur_mma(bool on);
 void set_fused_min_blocks(int b);
+void set_fused_version(int v);
+void set_pdl(bool on);
 void set_fused_prefetch(bool on);
 
 // ---- peer-memory exchange (peer_exchange.cu): one-shot all-reduce over NVLink mailboxes -------------------------------

@@ -105,6 +105,13 @@ __device__ __forceinline__ bool lm_skip(const LmCtl* ctl, int mode) {
   return mode == 2 && ctl->system_valid;
 }
 
+// clock64() stamps of the single-CTA LM kernels (diagnostics: dpba_debug_stamps); written by thread 0 only
+__device__ long long g_stamps[64];
+__device__ int g_stamps_on = 0;
+__device__ __forceinline__ void stamp(int i) {
+  if (g_stamps_on && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_stamps[i] = clock64();
+}
+
 // MUFU.RSQ / MUFU.RCP (<= 2 ulp) without the denormal fix-up code of rsqrtf() / 1.f / x; used only where no connection
 // status depends on the result (Huber weight, Jacobians)
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -867,6 +874,451 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused linearise, second generation (round 2): ONE THREAD PER PATCH-RESIDUAL.
+//
+// The first generation spreads a patch over 8 lanes (lane = pattern pixel): every per-residual quantity is computed 8
+// times, every 8-pixel sum costs shuffles, and the kernel executes ~670 warp instructions per 4 residuals.  Here a lane owns
+// a landmark and walks the 8 pattern pixels itself: the patch sums, the Huber weight and the per-landmark H_pd / H_dd / b_d
+// terms are plain register arithmetic, the per-residual work is done once, and the pixels of one residual give the
+// thread 8 independent gathers to keep in flight (instruction-level parallelism instead of occupancy).
+//
+//   grid  = (chunks of `lpb` landmarks -- a multiple of 32 --, host frames), block = 32 (N - 1): one warp per target
+//   pass 1 (per pixel)  reproject with the current state (pinned operation order: the status predicates),
+//                       gather the four taps (two LDG.E.256), intensity / gradient, raw residual
+//   between             all-pixel validity, mask, committed status -> evaluated?, patch norm, Huber weight, energy
+//   pass 2 (per pixel)  reprojection Jacobians at the (FEJ) linearisation point, u = [g(6), c, 1], running sums of the
+//                       pair's 8x8 core / core^T r in 44 registers, per-landmark p_t = sum w d u, H_dd, b_d in registers
+// Everything after the sweep (reference block of H_pd, 1x1 Schur inverse, H_pd rows to HBM, the chunk's rank-k update)
+// is the first generation's epilogue on the same shared-memory layout, so the second-stage kernels are unchanged.
+// The arithmetic that decides statuses and energies is the same sequence of rounded operations as in eval_pixel.
+// ------------------------------------------------------------------------------------------------
+template <bool FEJ, int NWMAX, int MINB>
+__global__ void __launch_bounds__(32 * NWMAX, MINB)
+    k_linearize_fused2(const __grid_constant__ WindowDev w, float sigma, int huber, int for_marg, int lpb,
+                       float* __restrict__ core_part, float* __restrict__ schur_part, const LmCtl* __restrict__ ctl,
+                       int ctl_mode, int fold, const double* __restrict__ step_pose, double2* __restrict__ norms) {
+  // fold (device LM, speculative sequence): this sweep evaluates the trial state of step k + 1, so it first closes
+  // step k for ITS landmarks and residuals -- acceptStep() / rejectStep() incl. changeResidualStatuses (problem.hpp:20-35,
+  // 377-384,395-399; k_accept_landmarks) -- and then back-substitutes the new pose step into their inverse depths
+  // (calculateIdepths, hessian_block_evaluation.hpp:238-263; k_back_substitute).  Two launches and their boundaries
+  // leave the critical path of an iteration; every landmark / residual is touched by exactly one CTA / thread.
+  const int N = w.n_frames;
+  const int D = 8 * N;
+  const int f = blockIdx.y;
+  const int M = w.n_lm[f];
+  const int l0 = blockIdx.x * lpb;
+  const int nwarps = N - 1;
+  const int lm_base0 = lm_index(w, f, 0);
+  cudaGridDependencySynchronize();  // programmatic dependent launch: everything above ran beside the predecessor's tail
+  if (fold && ctl->apply) {
+    const int accept = ctl->accept;
+    const int tw = threadIdx.x >> 5;
+    const int tt = tw + (tw >= f);
+    const size_t rb0 = res_index(w, f, tt, 0);
+    for (int ls = threadIdx.x & 31; ls < lpb; ls += 32) {
+      const int l = l0 + ls;
+      if (l >= M) break;
+      if (accept > 0) w.status[rb0 + l] = w.cand[rb0 + l];
+      else w.cand[rb0 + l] = w.status[rb0 + l];
+    }
+    for (int ls = threadIdx.x; ls < lpb; ls += blockDim.x) {
+      const int l = l0 + ls;
+      if (l >= M) break;
+      const int gl = lm_base0 + l;
+      if (accept > 0) w.lmk[gl].z += w.idepth_step[gl];
+      w.idepth_step[gl] = 0.f;
+    }
+  }
+  if (lm_skip(ctl, ctl_mode)) return;
+  extern __shared__ __align__(16) float smem[];
+  if (fold) {
+    float* sp = smem;  // the pose step, staged in the (not yet used) dynamic shared memory
+    __syncthreads();   // the commits above
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sp[i] = (float)step_pose[i];
+    __syncthreads();
+    const float inv_lambda = (float)(1.0 / (1.0 + ctl->lambda));
+    double n_state = 0, n_step = 0;
+    const int px = threadIdx.x & 7;
+    for (int lsb = 0; lsb < lpb; lsb += blockDim.x >> 3) {  // 8 lanes per landmark, as k_back_substitute
+      const int ls = lsb + (threadIdx.x >> 3);
+      const int l = l0 + ls;
+      const bool inb = ls < lpb && l < M;
+      const int gl = lm_base0 + (inb ? l : 0);
+      float dot = 0.f;
+      if (inb) {
+        const float* hrow = w.hpd + (size_t)gl * w.hpd_stride;
+        for (int c = px; c < D; c += 8) dot += hrow[c] * sp[c];
+      }
+      dot = group_sum(dot);
+      if (inb && px == 0) {
+        const int fl = w.flags[gl];
+        float stp = w.idepth_step[gl];
+        if (!(fl & LM_MARG) && !(fl & LM_ILL)) {
+          stp = -((w.b_d[gl] - dot) * inv_lambda * w.inv_hdd[gl]);
+          w.idepth_step[gl] = stp;
+        }
+        const float id = w.lmk[gl].z;  // landmark part of acceptStep's norms (problem.hpp:377-382)
+        n_state += (double)id * id;
+        n_step += (double)stp * stp;
+      }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      n_state += __shfl_xor_sync(FULL, n_state, sft);
+      n_step += __shfl_xor_sync(FULL, n_step, sft);
+    }
+    __syncthreads();  // sp is dead; the same words now collect the warps' norm partials
+    double* nw = reinterpret_cast<double*>(smem);
+    if ((threadIdx.x & 31) == 0) {
+      nw[2 * (threadIdx.x >> 5)] = n_state;
+      nw[2 * (threadIdx.x >> 5) + 1] = n_step;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, b = 0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+        a += nw[2 * i];
+        b += nw[2 * i + 1];
+      }
+      norms[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = make_double2(a, b);
+    }
+    __syncthreads();  // idepth_step of this chunk is final; smem is free for the sweep
+  }
+  if (l0 >= M) return;
+  PairConst* pcs = reinterpret_cast<PairConst*>(smem);               // [nwarps]
+  float* hpd_s = smem + (size_t)nwarps * (sizeof(PairConst) / 4);    // [lpb][D]
+  float* hdd_s = hpd_s + lpb * D;                                    // [lpb] Schur weight 1/H_dd after the finalise
+  float* bd_s = hdd_s + lpb;                                         // [lpb] weight * b_d
+  float* hdd_w = bd_s + lpb;                                         // [lpb][nwarps] per-target H_dd terms
+  float* bd_w = hdd_w + lpb * nwarps;                                // [lpb][nwarps] per-target b_d terms
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = warp + (warp >= f);
+  const int lm_base = lm_index(w, f, 0);
+
+  for (int i = threadIdx.x; i < lpb * (D + 2 + 2 * nwarps); i += blockDim.x) hpd_s[i] = 0.f;
+  reinterpret_cast<float4*>(&pcs[warp])[lane] = reinterpret_cast<const float4*>(&w.pairs[f * PBA_MAXF + t])[lane];
+  __syncthreads();
+  const PairConst& pc = pcs[warp];
+  const float4* __restrict__ img = w.img[t];
+  const uint8_t* __restrict__ mask = w.mask_all[t] ? nullptr : w.mask[t];
+  const size_t res_base = res_index(w, f, t, 0);
+  const int W = w.W;
+  const float xmax = (float)(w.W - 5), ymax = (float)(w.H - 5);
+  const float sig2 = __fmul_rn(sigma, sigma);
+  // where this lane's two slots of the warp-reduced 48-vector live (see the transpose-reduce below)
+  const int off = ((lane & 16) ? 24 : 0) + ((lane & 8) ? 12 : 0) + ((lane & 4) ? 6 : 0) + ((lane & 2) ? 3 : 0) +
+                  ((lane & 1) ? 2 : 0);
+  // running totals of the pair's core record: only TWO registers per lane live across the landmark groups (the 44 sums
+  // of a group are reduced over the warp right after its pass 2, so they do not occupy registers during the gathers)
+  float tot0 = 0.f, tot1 = 0.f;
+
+  for (int g0 = 0; g0 < lpb; g0 += 32) {
+    const int ls = g0 + lane;  // slot in the chunk
+    const int l = l0 + ls;
+    const bool inb = l < M;
+    const int gl = lm_base + (inb ? l : 0);
+    const float4 k4 = w.lmk[gl];
+    const int flags = w.flags[gl];
+    const bool skip = !inb || ((flags & LM_MARG) && !(flags & LM_TO_MARG));  // evaluate_jacobians.hpp:83
+    const size_t res = res_base + (inb ? l : 0);
+    const int status = skip ? K_OUTLIER : w.status[res];
+    const bool jv = FEJ ? (w.jac_valid[res] != 0) : true;
+    const float u = k4.x, v = k4.y, rho0 = k4.w;
+    const float rho = skip ? -1.f : k4.z + w.idepth_step[gl];  // -1 forces !ok
+    const float* __restrict__ patch = w.patch + (size_t)gl * 8;
+
+    // ---- pass 1: reprojection at the current state, taps, raw residuals -------------------------------------------------
+    // row . [u, v, 1, rho] = (a0 u + a1 v) + (a2 + a3 rho): the second bracket is the same for the 8 pixels
+    const float* PA = (FEJ) ? pc.A : pc.M;  // non-FEJ: the Jacobian variant projects through M and K_t (see eval_pixel)
+    const float c0 = __fadd_rn(PA[2], __fmul_rn(PA[3], rho));
+    const float c1 = __fadd_rn(PA[6], __fmul_rn(PA[7], rho));
+    const float c2 = __fadd_rn(PA[10], __fmul_rn(PA[11], rho));
+    bool ok = valid_idepth(rho);
+    float rr[8], gu[8], gv[8];
+    // two batches of four pixels: addresses first, then the eight 256-bit gathers back to back, then the arithmetic --
+    // the thread keeps 8 independent L2 round trips in flight instead of one
+#pragma unroll
+    for (int h4 = 0; h4 < 8; h4 += 4) {
+      float fdx[4], fdy[4];
+      const float4* tp[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int p = h4 + q4;
+        const float ox = (float)((int)((0x21420312u >> (4 * p)) & 15u) - 2), oy = (float)((int)((0x01222334u >> (4 * p)) & 15u) - 2);
+        const float ur = u + ox, vr = v + oy;
+        bool okp = in_roi(ur, vr, xmax, ymax);
+        const float X = __fadd_rn(__fadd_rn(__fmul_rn(PA[0], ur), __fmul_rn(PA[1], vr)), c0);
+        const float Y = __fadd_rn(__fadd_rn(__fmul_rn(PA[4], ur), __fmul_rn(PA[5], vr)), c1);
+        const float Z = __fadd_rn(__fadd_rn(__fmul_rn(PA[8], ur), __fmul_rn(PA[9], vr)), c2);
+        okp = okp && (Z > 0.f);
+        const float rz = __frcp_rn(Z);
+        float tu, tv;
+        if (FEJ) {
+          tu = __fmul_rn(X, rz);
+          tv = __fmul_rn(Y, rz);
+        } else {
+          tu = __fmul_rn(__fadd_rn(__fmul_rn(pc.fx_t, X), __fmul_rn(pc.cx_t, Z)), rz);
+          tv = __fmul_rn(__fadd_rn(__fmul_rn(pc.fy_t, Y), __fmul_rn(pc.cy_t, Z)), rz);
+        }
+        okp = okp && in_roi(tu, tv, xmax, ymax);
+        if (mask) {  // CameraMask::valid<false>: round() + lookup, only meaningful after the ROI test (quirk Q5)
+          const int midx = okp ? (int)roundf(tv) * W + (int)roundf(tu) : 0;
+          okp = okp && (mask[midx] != 0);
+        }
+        ok = ok && okp;
+        // gather speculatively (a pixel that failed goes to texel (8, 8)); whether the residual is evaluated at all is
+        // only known after the 8th pixel, and an unevaluated one contributes through weights that are exactly zero
+        const float su = okp ? tu : 8.f, sv = okp ? tv : 8.f;
+        const int ix = (int)su, iy = (int)sv;
+        fdx[q4] = su - (float)ix;
+        fdy[q4] = sv - (float)iy;
+        tp[q4] = img + ((size_t)iy * W + ix) * 2;
+      }
+      float4 t00[4], t01[4], t10[4], t11[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        ldg256_nc(tp[q4], t00[q4], t01[q4]);
+        ldg256_nc(tp[q4] + 2 * (size_t)W, t10[q4], t11[q4]);
+      }
+      const float4 pq = ldf4(patch + h4);
+      const float pv4[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int p = h4 + q4;
+        const float dx = fdx[q4], dy = fdy[q4];
+        const float dxdy = __fmul_rn(dx, dy);
+        const float w11 = dxdy, w10 = __fsub_rn(dy, dxdy), w01 = __fsub_rn(dx, dxdy),
+                    w00 = __fadd_rn(__fsub_rn(__fsub_rn(1.f, dx), dy), dxdy);
+        const float I = __fmaf_rn(w00, t00[q4].x, __fmaf_rn(w01, t01[q4].x, __fmaf_rn(w10, t10[q4].x, __fmul_rn(w11, t11[q4].x))));
+        rr[p] = __fmaf_rn(-pc.s, __fsub_rn(pv4[q4], pc.b_r), __fsub_rn(I, pc.b_t));  // evaluate_jacobians.hpp:124-135
+        gu[p] = (w11 * t11[q4].y + w10 * t10[q4].y + w01 * t01[q4].y + w00 * t00[q4].y) * pc.fx_t;
+        gv[p] = (w11 * t11[q4].z + w10 * t10[q4].z + w01 * t01[q4].z + w00 * t00[q4].z) * pc.fy_t;
+      }
+    }
+    if (FEJ) ok = ok && jv;  // evaluate_jacobians.hpp:94
+    const bool ev = ok && (status == K_OK);
+    // patch norm in the 8-lane butterfly order of the first generation (and of oracle/cpu_ref `device_ops`)
+    float q[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      rr[p] = ev ? rr[p] : 0.f;
+      gu[p] = ev ? gu[p] : 0.f;
+      gv[p] = ev ? gv[p] : 0.f;
+      q[p] = __fmul_rn(rr[p], rr[p]);
+    }
+    const float n2 = __fadd_rn(__fadd_rn(__fadd_rn(q[0], q[4]), __fadd_rn(q[2], q[6])),
+                               __fadd_rn(__fadd_rn(q[1], q[5]), __fadd_rn(q[3], q[7])));
+    float e = 0.5f * n2, wgt = 1.f;
+    if (huber && n2 > sig2) {  // evaluate_jacobians.hpp:139-146
+      wgt = sigma * rsqrt_approx(n2);
+      e = __fmaf_rn(sigma, __fsqrt_rn(n2), -(0.5f * sig2));
+    }
+    e = ev ? e : 0.f;
+    float e_add = 0.f, n_add = 0.f;
+    if (!skip) {
+      if (!ok) w.cand[res] = K_OOB;       // evaluate_jacobians.hpp:111-113
+      else if (ev) w.cand[res] = K_OK;    // :115
+      w.energy[res] = e;
+      if (!(flags & LM_MARG)) {           // calculateLandmarksEnergy, problem.hpp:124-133
+        e_add = e;
+        n_add = e > 0.f ? 1.f : 0.f;
+      }
+    }
+    // landmark selection of K3/K4 (hessian_block_evaluation.hpp:68-72,190-194)
+    const bool sel = !skip && (for_marg ? (flags & LM_TO_MARG) != 0 : (flags & LM_MARG) == 0);
+    const float wq = (sel && ev) ? wgt : 0.f;
+
+    // ---- pass 2: Jacobians at the linearisation point, the group's sums ---------------------------------------------------
+    const float* PM = FEJ ? pc.M0 : pc.M;
+    const float rho_j = FEJ ? rho0 : rho;
+    const float* tt = FEJ ? pc.t0 : pc.tr;
+    const float m0 = PM[2] + PM[3] * rho_j, m1 = PM[6] + PM[7] * rho_j, m2 = PM[10] + PM[11] * rho_j;
+    const float cs = ev ? (FEJ ? pc.s0_last : pc.s) : 0.f, cb = FEJ ? pc.b_r0 : pc.b_r;
+    float acc[44];
+#pragma unroll
+    for (int k = 0; k < 44; ++k) acc[k] = 0.f;
+    float pt[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pt[k] = 0.f;
+    float hdd = 0.f, bd = 0.f;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const float ox = (float)((int)((0x21420312u >> (4 * p)) & 15u) - 2), oy = (float)((int)((0x01222334u >> (4 * p)) & 15u) - 2);
+      const float ur = u + ox, vr = v + oy;
+      const float qx = PM[0] * ur + PM[1] * vr + m0;
+      const float qy = PM[4] * ur + PM[5] * vr + m1;
+      const float qz = PM[8] * ur + PM[9] * vr + m2;
+      const float sI = rcp_approx(ev ? qz : 1.f);  // Jacobians only (no status depends on it): MUFU.RCP
+      const float b0 = (ev ? qx : 0.f) * sI, b1 = (ev ? qy : 0.f) * sI;
+      const float nid = rho_j * sI;
+      const float gup = gu[p], gvp = gv[p];
+      const float du_id = tt[0] * sI - tt[2] * sI * b0;
+      const float dv_id = tt[1] * sI - tt[2] * sI * b1;
+      const float b0b1 = b0 * b1;
+      float uu[8];
+      uu[0] = gup * nid;
+      uu[1] = gvp * nid;
+      uu[2] = -gup * (nid * b0) - gvp * (nid * b1);
+      uu[3] = -gup * b0b1 - gvp * (b1 * b1 + 1.f);
+      uu[4] = gup * (b0 * b0 + 1.f) + gvp * b0b1;
+      uu[5] = -gup * b1 + gvp * b0;
+      uu[6] = cs * (patch[p] - cb);
+      uu[7] = 1.f;
+      const float d = gup * du_id + gvp * dv_id;  // evaluate_jacobians.hpp:165-174
+      float wu[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wu[k] = wq * uu[k];
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = a; b < 8; ++b) acc[idx++] += wu[a] * uu[b];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) acc[36 + a] += wu[a] * rr[p];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pt[k] += wu[k] * d;
+      const float wd = wq * d;
+      hdd += wd * d;
+      bd += wd * rr[p];
+    }
+    if (sel) {  // this thread is the only writer of target block t of its landmark
+      float4* hp = reinterpret_cast<float4*>(hpd_s + ls * D + 8 * t);
+      hp[0] = make_float4(-pt[0], -pt[1], -pt[2], -pt[3]);
+      hp[1] = make_float4(-pt[4], -pt[5], -pt[6], -pt[7]);
+      hdd_w[ls * nwarps + warp] = hdd;
+      bd_w[ls * nwarps + warp] = bd;
+    }
+    // warp-wide transpose-reduce of the group's 44 sums + (energy, n): 24+12+6+3+2 = 47 shuffles; every lane ends up with
+    // (at most) two entries of the 48-vector and adds them to its running totals
+    {
+      float v48[PBA_CORE], v24[24], v12[12], v6[6], v3[3], v2[2];
+#pragma unroll
+      for (int k = 0; k < PBA_CORE; ++k) v48[k] = k < 44 ? acc[k] : (k == 44 ? e_add : (k == 45 ? n_add : 0.f));
+      tr_step<48, 16>(v48, v24, lane);
+      tr_step<24, 8>(v24, v12, lane);
+      tr_step<12, 4>(v12, v6, lane);
+      tr_step<6, 2>(v6, v3, lane);
+      tr_step<3, 1>(v3, v2, lane);
+      tot0 += v2[0];
+      tot1 += v2[1];
+    }
+  }
+
+  {
+    // this warp's 48 partial sums go to its own slot [host frame][chunk][target warp][48]: plain coalesced stores, summed
+    // over the chunks in fp64 by k_core_reduce (no atomics, deterministic)
+    float* dst = core_part + (((size_t)f * gridDim.x + blockIdx.x) * nwarps + warp) * PBA_CORE;
+    dst[off] = tot0;
+    if (!(lane & 1)) dst[off + 1] = tot1;
+  }
+  __syncthreads();
+
+  // reference block of H_pd:  sum_t B_t^T p_t  with p_t = -(target block t)   (J_ref = U B)
+  for (int i = threadIdx.x; i < lpb * 8; i += blockDim.x) {
+    const int ls = i >> 3, j = i & 7;
+    float refv = 0.f;
+    for (int wi = 0; wi < nwarps; ++wi) {
+      const int tt2 = wi + (wi >= f);
+      const float* ptv = hpd_s + ls * D + 8 * tt2;
+      const PairConst& pw = pcs[wi];
+      if (j < 6) {
+        const float* adj = FEJ ? pw.adj0 : pw.adj;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) refv -= adj[k * 6 + j] * ptv[k];
+      } else if (j == 6) {
+        refv -= ptv[6];
+      } else {
+        refv -= (FEJ ? pw.s0 : pw.s) * ptv[7];
+      }
+    }
+    hpd_s[ls * D + 8 * f + j] = refv;
+  }
+  __syncthreads();
+
+  // finalise the chunk's landmarks (hessian_block_evaluation.hpp:213-227)
+  for (int ls = threadIdx.x; ls < lpb; ls += blockDim.x) {
+    const int l = l0 + ls;
+    float sc = 0.f, sb = 0.f;
+    if (l < M) {
+      const int gl = lm_base + l;
+      const int fl = w.flags[gl];
+      const bool skip = (fl & LM_MARG) && !(fl & LM_TO_MARG);
+      const bool sel = !skip && (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0);
+      if (sel) {
+        float hdd = 0.f, bd = 0.f;
+        for (int wi = 0; wi < nwarps; ++wi) {
+          hdd += hdd_w[ls * nwarps + wi];
+          bd += bd_w[ls * nwarps + wi];
+        }
+        w.b_d[gl] = bd;
+        if (hdd > 1e-15f) {
+          if (for_marg && w.fixed[f]) hdd += 1e8f;  // kScaleNullspaceRegularizer
+          sc = 1.f / hdd;
+          sb = sc * bd;
+          w.inv_hdd[gl] = sc;
+          w.flags[gl] = (uint8_t)(fl & ~LM_ILL);
+        } else {
+          w.flags[gl] = (uint8_t)(fl | LM_ILL);
+        }
+      }
+    }
+    hdd_s[ls] = sc;
+    bd_s[ls] = sb;
+  }
+  __syncthreads();
+  const int D4 = D / 4;
+  for (int i = threadIdx.x; i < lpb * D4; i += blockDim.x) {
+    const int ls = i / D4;
+    const int l = l0 + ls;
+    if (l >= M) break;
+    const int gl = lm_base + l;
+    const int fl = w.flags[gl];
+    const bool skip = (fl & LM_MARG) && !(fl & LM_TO_MARG);
+    const bool sel = !skip && (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0);
+    if (sel)
+      reinterpret_cast<float4*>(w.hpd + (size_t)gl * w.hpd_stride)[i - ls * D4] =
+          reinterpret_cast<const float4*>(hpd_s + ls * D)[i - ls * D4];
+  }
+  // K4 second half for this chunk: S = sum_l s_l H_pd_l H_pd_l^T (upper triangle as 4x4 tiles), b = sum_l s_l b_d_l H_pd_l
+  {
+    const int T4 = D / 4, ntri = T4 * (T4 + 1) / 2, nout = ntri * 16 + D;
+    float* part = schur_part + ((size_t)f * gridDim.x + blockIdx.x) * nout;
+    for (int tile = threadIdx.x; tile < ntri; tile += blockDim.x) {
+      int ty = 0, rem = tile;
+      while (rem >= T4 - ty) {
+        rem -= T4 - ty;
+        ++ty;
+      }
+      const int tx = ty + rem;
+      float a[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a[k] = 0.f;
+      for (int ls = 0; ls < lpb; ++ls) {
+        const float sc = hdd_s[ls];
+        const float4 qv = ldf4(hpd_s + ls * D + 4 * ty);
+        const float4 pv = ldf4(hpd_s + ls * D + 4 * tx);
+        const float qa[4] = {sc * qv.x, sc * qv.y, sc * qv.z, sc * qv.w};
+        const float pa2[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[i * 4 + j] += qa[i] * pa2[j];
+      }
+      float4* dst = reinterpret_cast<float4*>(part + tile * 16);
+      dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+      dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+      dst[2] = make_float4(a[8], a[9], a[10], a[11]);
+      dst[3] = make_float4(a[12], a[13], a[14], a[15]);
+    }
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float b = 0.f;
+      for (int ls = 0; ls < lpb; ++ls) b += bd_s[ls] * hpd_s[ls * D + c];
+      part[ntri * 16 + c] = b;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Reference three-pass dataflow on the device (cross-check + materialising-sweep measurement):
 // K3 from the materialised arrays: per ordered pair H_rr, H_rt, H_tt, b_r, b_t written straight into H / b.
 // grid = (chunks, pairs), 208 threads = one per output element.
@@ -1475,6 +1927,218 @@ __global__ void __launch_bounds__(1024) k_finish_fused(const __grid_constant__ W
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_reduce_system (round 2): the whole second stage of a linearisation in ONE launch -- what k_core_reduce, k_assemble and
+// k_finish_fused do in three.  Blocks [0, N (N + 1) / 2) assemble one upper-triangular 8x8 block pair of H_pp each and
+// reduce the per-chunk core records they need on the fly (a pair's 48 sums over <= a few dozen chunk CTAs: cheaper than a
+// launch boundary); the diagonal blocks also publish the reduced cores (slots 44 / 45 carry the pair energies the LM
+// decision reads).  The remaining blocks sum the per-chunk Schur partials.  with_system = 0 (the last evaluation of a
+// solve): only the cores are reduced.
+// ------------------------------------------------------------------------------------------------
+constexpr int RSYS_W = ASM_W + 96;  // per assemble warp: the k_assemble staging + the two reduced cores (48 doubles each)
+__global__ void __launch_bounds__(1024) k_reduce_system(const __grid_constant__ WindowDev w, int fej,
+                                                        const float* __restrict__ core_part, int lpb, int chunks,
+                                                        double* __restrict__ core, double* __restrict__ Hp,
+                                                        double* __restrict__ bp, const float* __restrict__ fpart,
+                                                        double* __restrict__ Hs, double* __restrict__ bs,
+                                                        const LmCtl* __restrict__ ctl, int with_system) {
+  cudaGridDependencySynchronize();
+  if (lm_skip(ctl, 1)) return;
+  extern __shared__ double rs_sm[];
+  const int N = w.n_frames, D = 8 * N;
+  const int NB = N * (N + 1) / 2;
+  const bool st0 = g_stamps_on && threadIdx.x == 0 && blockIdx.x == 0;
+  const bool st1 = g_stamps_on && threadIdx.x == 0 && (int)blockIdx.x == NB;
+  if (st0) g_stamps[30] = clock64();
+  if (st1) g_stamps[40] = clock64();
+  if ((int)blockIdx.x < NB) {
+    // ---- assemble block (bi <= bj), cf. k_assemble ---------------------------------------------------------------------
+    int bi = 0, rem = blockIdx.x;
+    while (rem >= N - bi) {
+      rem -= N - bi;
+      ++bi;
+    }
+    const int bj = bi + rem;
+    const bool diag = bi == bj;
+    if (!with_system && !diag) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = lane >> 2, j0 = (lane & 3) * 2;
+    const int nterms = diag ? N - 1 : 2;
+    double* Cw = rs_sm + (size_t)min(warp, max(2, N - 1) - 1) * RSYS_W;
+    double* Bw = Cw + 64;
+    double* Tw = Bw + 64;
+    double* Ow = Tw + 64;
+    double* bw = Ow + 64;
+    double* c_rt = Cw + ASM_W;   // reduced core of the pair r -> t
+    double* c_tr = c_rt + 48;    // ... of the pair t -> r
+    if (warp < nterms) {
+      const int r = diag ? bi : (warp ? bj : bi);
+      const int t = diag ? warp + (warp >= bi) : (warp ? bi : bj);
+      // sum the chunk CTAs' records: [host frame][chunk][target warp][48] floats, fixed order, fp64
+      for (int side = 0; side < 2; ++side) {
+        const int hf = side ? t : r, tf = side ? r : t;     // host frame and target frame of this record
+        const int tw = tf - (tf > hf);                       // the target's warp index in the sweep CTA of hf
+        const int nchunk = (w.n_lm[hf] + lpb - 1) / lpb;
+        const float* p = core_part + ((size_t)hf * chunks * (N - 1) + tw) * PBA_CORE;
+        double a0 = 0, a1 = 0;
+        const size_t cs = (size_t)(N - 1) * PBA_CORE;
+        const bool hi = lane < PBA_CORE - 32;
+        int ch = 0;
+        for (; ch + 8 <= nchunk; ch += 8) {  // 16 independent loads in flight per lane, then the fixed-order fp64 sums
+          float x[8], y[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float* q = p + (size_t)(ch + u) * cs;
+            x[u] = q[lane];
+            y[u] = hi ? q[32 + lane] : 0.f;
+          }
+          // fp32 -> fp64 conversions run on B200's thin fp64 pipe (they were the top stall of this kernel): eight chunk
+          // records are summed pairwise in fp32 first (relative rounding 2e-7 on records that are themselves fp32 sums
+          // of ~500 products), one conversion per eight
+          a0 += (double)(((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7])));
+          a1 += (double)(((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7])));
+        }
+        for (; ch < nchunk; ++ch) {
+          const float* q = p + (size_t)ch * cs;
+          a0 += (double)q[lane];
+          if (hi) a1 += (double)q[32 + lane];
+        }
+        double* dst = side ? c_tr : c_rt;
+        dst[lane] = a0;
+        if (lane < PBA_CORE - 32) dst[32 + lane] = a1;
+        if (diag && side == 0) {  // publish: every ordered pair (r, t) belongs to exactly one diagonal block's warp
+          double* g = core + (size_t)(r * PBA_MAXF + t) * PBA_CORE;
+          g[lane] = a0;
+          if (lane < PBA_CORE - 32) g[32 + lane] = a1;
+        }
+      }
+      __syncwarp();
+      if (st0) g_stamps[31] = clock64();
+      if (with_system) {
+        const PairAssemble& pa = w.pairs_asm[r * PBA_MAXF + t];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          Cw[i * 8 + j0 + q] = core_at(c_rt, i, j0 + q);
+          Bw[i * 8 + j0 + q] = bm_at(pa, fej, i, j0 + q);
+        }
+        const double ctr0 = diag ? core_at(c_tr, i, j0) : 0.0, ctr1 = diag ? core_at(c_tr, i, j0 + 1) : 0.0;
+        const double q_rt = (diag && lane < 8) ? c_rt[36 + lane] : 0.0, q_tr = (diag && lane < 8) ? c_tr[36 + lane] : 0.0;
+        if (diag && lane < 8) bw[lane] = q_rt;
+        __syncwarp();
+        double s0 = 0, s1 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // (B^T C)[i][j]
+          s0 += Bw[k * 8 + i] * Cw[k * 8 + j0];
+          s1 += Bw[k * 8 + i] * Cw[k * 8 + j0 + 1];
+        }
+        if (!diag) {
+          Ow[i * 8 + j0] = -s0;
+          Ow[i * 8 + j0 + 1] = -s1;
+        } else {
+          Tw[i * 8 + j0] = s0;
+          Tw[i * 8 + j0 + 1] = s1;
+          double br = 0;
+          if (lane < 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) br += Bw[k * 8 + lane] * bw[k];  // B^T q_rt
+          }
+          __syncwarp();
+          double h0 = ctr0, h1 = ctr1;  // + H_tt of the pair t -> r
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // B^T C B
+            h0 += Tw[i * 8 + k] * Bw[k * 8 + j0];
+            h1 += Tw[i * 8 + k] * Bw[k * 8 + j0 + 1];
+          }
+          Ow[i * 8 + j0] = h0;
+          Ow[i * 8 + j0 + 1] = h1;
+          if (lane < 8) bw[lane] = br - q_tr;  // b_t of the pair t -> r is -q_tr
+        }
+      }
+    }
+    if (st0) g_stamps[32] = clock64();
+    __syncthreads();
+    if (st0) g_stamps[33] = clock64();
+    if (!with_system) return;
+    for (int o = threadIdx.x; o < 64; o += blockDim.x) {
+      const int oi = o >> 3, oj = o & 7;
+      if (!diag) {
+        const double acc = rs_sm[oi * 8 + oj + 192] + rs_sm[RSYS_W + oj * 8 + oi + 192];
+        Hp[(size_t)(8 * bi + oi) * D + 8 * bj + oj] = acc;
+        Hp[(size_t)(8 * bj + oj) * D + 8 * bi + oi] = acc;
+      } else {
+        const int ii = max(oi, oj), jj = min(oi, oj);  // selfadjointView<Lower>
+        double acc = 0;
+        for (int wi = 0; wi < nterms; ++wi) acc += rs_sm[wi * RSYS_W + 192 + ii * 8 + jj];
+        Hp[(size_t)(8 * bi + oi) * D + 8 * bi + oj] = acc;
+        if (oj == 0) {
+          double bacc = 0;
+          for (int wi = 0; wi < nterms; ++wi) bacc += rs_sm[wi * RSYS_W + 256 + oi];
+          bp[8 * bi + oi] = bacc;
+        }
+      }
+    }
+    if (st0) g_stamps[34] = clock64();
+    return;
+  }
+  if (!with_system) return;
+  // ---- Schur partial reduction, cf. k_finish_fused ------------------------------------------------------------------------
+  __shared__ double red[32][33];
+  __shared__ int s_nch[PBA_MAXF];
+  const int T4 = D / 4, ntri = T4 * (T4 + 1) / 2, nout = ntri * 16 + D;
+  const int g = threadIdx.x >> 5, oo = threadIdx.x & 31;
+  const int o = ((int)blockIdx.x - NB) * 32 + oo;
+  if (threadIdx.x < PBA_MAXF) s_nch[threadIdx.x] = threadIdx.x < N ? (w.n_lm[threadIdx.x] + lpb - 1) / lpb : 0;
+  __syncthreads();
+  double acc = 0;
+  if (o < nout) {
+    const int rows = N * chunks;
+    const float* p = fpart + o;
+    auto P = [&](int q) -> float {
+      const int f = q / chunks;
+      return (q - f * chunks) < s_nch[f] ? p[(size_t)q * nout] : 0.f;
+    };
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int q = g;
+    for (; q + 96 < rows; q += 128) {
+      a0 += P(q);
+      a1 += P(q + 32);
+      a2 += P(q + 64);
+      a3 += P(q + 96);
+      if (((q - g) & 511) == 384) {  // bound the fp32 partial sums: flush to fp64 every 16 rows
+        acc += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+        a0 = a1 = a2 = a3 = 0.f;
+      }
+    }
+    for (; q < rows; q += 32) a0 += P(q);
+    acc += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+  }
+  if (st1) g_stamps[41] = clock64();
+  red[g][oo] = acc;
+  __syncthreads();
+  if (st1) g_stamps[42] = clock64();
+  if (g == 0 && o < nout) {
+    double sum = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) sum += red[k][oo];
+    if (o >= ntri * 16) {
+      bs[o - ntri * 16] = sum;
+    } else {
+      const int tile = o >> 4, e = o & 15;
+      int ty = 0, rem2 = tile;
+      while (rem2 >= T4 - ty) {
+        rem2 -= T4 - ty;
+        ++ty;
+      }
+      const int r = 4 * ty + (e >> 2), cc = 4 * (ty + rem2) + (e & 3);
+      if (r <= cc) {
+        Hs[(size_t)r * D + cc] = sum;
+        Hs[(size_t)cc * D + r] = sum;
+      }
+    }
+  }
+  if (st1) g_stamps[43] = clock64();
 }
 
 // second stage of the Schur reduction + symmetrisation of both systems (hessian_block_evaluation.hpp:147-163):
@@ -2137,7 +2801,7 @@ __device__ __forceinline__ double block_sum_256(double v, double* red /*[8]*/) {
   return s;
 }
 
-__global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
+__device__ __forceinline__ void lm_energy_body(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
                                                    int N, double* scal, const double* Hmarg,
                                                    const double* bmarg, int kind, const double2* __restrict__ e_part,
                                                    int n_e, const double2* __restrict__ n_part, int n_n, int from_core) {
@@ -2151,6 +2815,7 @@ __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDe
   __shared__ double red[8];
   __shared__ int s_accept;
   const int D = 8 * N, i = threadIdx.x;
+  stamp(50);
   if (e_part) {  // single-GPU: the second stage of the (energy, n) / norm reductions happens here, no extra launch
     double a = 0, b = 0, c = 0, d = 0;
     for (int k = i; k < n_e; k += 256) {
@@ -2185,6 +2850,7 @@ __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDe
       }
     }
   }
+  stamp(51);
   if (i < D) s[i] = fr[i / 8].eps[i % 8] + fr[i / 8].step[i % 8];
   __syncthreads();
   double acc = 0;
@@ -2226,6 +2892,7 @@ __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDe
       s_accept = ctl->accept;
     }
   }
+  stamp(52);
   if (kind != pba::LM_ENERGY_TRIAL) return;
   __syncthreads();
   // acceptStep / rejectStep for the frame state (problem.hpp:366-376,392-402); one thread per state entry
@@ -2266,6 +2933,13 @@ __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDe
   if (ctl->iteration >= opt->max_it || ctl->converged || ctl->n_valid <= 0) ctl->done = 1;
 }
 
+__global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
+                                                   int N, double* scal, const double* Hmarg,
+                                                   const double* bmarg, int kind, const double2* __restrict__ e_part,
+                                                   int n_e, const double2* __restrict__ n_part, int n_n, int from_core) {
+  lm_energy_body(ctl, opt, fr, N, scal, Hmarg, bmarg, kind, e_part, n_e, n_part, n_n, from_core);
+}
+
 // calculateStep (problem.hpp:342-357): priors (problem.hpp:37-77), full system, Jacobi preconditioner + LDL^T
 // (normal_linear_system.cpp:10-59), all fp64 in one CTA.
 //
@@ -2284,11 +2958,11 @@ __device__ __forceinline__ double rcp64(double d) {
 }
 
 template <int DP>
-__global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
-                                                 const int* fixed, int N, const double* __restrict__ Hp,
-                                                 const double* __restrict__ bp, const double* __restrict__ Hs,
-                                                 const double* __restrict__ bs, const double* __restrict__ Hmarg,
-                                                 const double* __restrict__ bmarg, double* __restrict__ step_dev) {
+__device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
+                                             const int* fixed, int N, const double* __restrict__ Hp,
+                                             const double* __restrict__ bp, const double* __restrict__ Hs,
+                                             const double* __restrict__ bs, const double* __restrict__ Hmarg,
+                                             const double* __restrict__ bmarg, double* __restrict__ step_dev) {
   if (ctl->done) return;
   constexpr int LD = DP + 1;   // row stride of S (odd: conflict-free column walks)
   constexpr int LPS = 9;       // row stride of Lp
@@ -2354,22 +3028,27 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
     S[D * LD + tid] = b * pre[tid];
   }
   const int ty = tid >> 4, tx = tid & 15;
+  __shared__ double s_ld[36], s_inv[8];  // l_cj (j < c) and 1 / d_j of the current diagonal block
+  stamp(2);
   for (int kb = 0; kb < D; kb += 8) {
     __syncthreads();
+    if (kb < 64) stamp(3 + kb / 8);
     const int i = kb + tid;  // this thread's row (row D is the right-hand side)
     const bool act = i <= D;
-    // the 8x8 diagonal block, packed lower triangle g[r (r + 1) / 2 + c], factored redundantly by every thread
-    double g[36], inv[8], a[8];
+    double a[8];
     if (act) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = (i >= kb + c) ? S[i * LD + kb + c] : 0.0;
+    }
+    // The 8x8 diagonal block, packed lower triangle g[r (r + 1) / 2 + c]: factored by warp 0 alone and published through
+    // shared memory.  (Round 1 let every thread factor it redundantly to save this publication; the 140 dependent-ish
+    // fp64 FMAs times 256 threads then cost more pipe time than the whole trailing update -- fp64 is 59 FMA/clk/SM here.)
+    if (tid < 32) {
+      double g[36], inv[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) g[r * (r + 1) / 2 + c] = S[(kb + r) * LD + kb + c];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = (i >= kb + c) ? S[i * LD + kb + c] : 0.0;
-    }
-    __syncthreads();  // rows kb..kb+7 are overwritten below by their owners
-    if (act) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         inv[j] = rcp64(g[j * (j + 1) / 2 + j]);
@@ -2380,25 +3059,37 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
           for (int c = j + 1; c <= r; ++c) g[r * (r + 1) / 2 + c] -= l * g[c * (c + 1) / 2 + j];
         }
       }
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s_inv[j] = inv[j];
+          dinv[kb + j] = inv[j];
+#pragma unroll
+          for (int c = j + 1; c < 8; ++c) s_ld[c * (c + 1) / 2 + j] = g[c * (c + 1) / 2 + j] * inv[j];
+        }
+      }
+    }
+    if (kb == 0) stamp(11);
+    __syncthreads();  // s_ld / s_inv published; rows kb..kb+7 are overwritten below by their owners
+    if (kb == 0) stamp(12);
+    if (act) {
       // own row: same recurrence (for a row of the diagonal block the entries right of the diagonal are unused)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
 #pragma unroll
-        for (int c = j + 1; c < 8; ++c) a[c] -= a[j] * (g[c * (c + 1) / 2 + j] * inv[j]);
+        for (int c = j + 1; c < 8; ++c) a[c] -= a[j] * s_ld[c * (c + 1) / 2 + j];
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (i >= kb + j) {
-          S[i * LD + kb + j] = a[j];        // raw column entry x_ij = l_ij d_j
-          Lp[i * LPS + j] = a[j] * inv[j];  // l_ij
+          S[i * LD + kb + j] = a[j];          // raw column entry x_ij = l_ij d_j
+          Lp[i * LPS + j] = a[j] * s_inv[j];  // l_ij
         }
       }
-      if (tid == 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dinv[kb + j] = inv[j];
-      }
     }
+    if (kb == 0) stamp(13);
     __syncthreads();
+    if (kb == 0) stamp(14);
     // trailing update of the lower triangle (and the rhs row): S[r][c] -= sum_j x_rj l_cj
     const int m0 = kb + 8;
     for (int r = m0 + ty; r <= D; r += 16) {
@@ -2415,6 +3106,7 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
     }
   }
   __syncthreads();
+  stamp(18);
   if (tid < D) st[tid] = S[D * LD + tid] * dinv[tid];  // z = D^-1 L^-1 b
   // blocked back substitution L^T x = z, l_ki = x_ki / d_i: every thread solves the 8x8 triangle of the block
   // redundantly in registers, then row i < kb subtracts the block's contribution -- one barrier per 8 unknowns
@@ -2448,6 +3140,136 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
   }
 }
 
+template <int DP>
+__global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
+                                                 const int* fixed, int N, const double* __restrict__ Hp,
+                                                 const double* __restrict__ bp, const double* __restrict__ Hs,
+                                                 const double* __restrict__ bs, const double* __restrict__ Hmarg,
+                                                 const double* __restrict__ bmarg, double* __restrict__ step_dev) {
+  lm_step_body<DP>(ctl, opt, fr, fixed, N, Hp, bp, Hs, bs, Hmarg, bmarg, step_dev);
+}
+
+// Per-pair constants by ONE CTA: thread per frame for the exponentials, then thread per ORDERED PAIR (same arithmetic,
+// same results as k_pair_setup, which uses a CTA per reference frame) -- the tail of k_lm_solve.
+__device__ __forceinline__ void pair_setup_body(const FrameParams* __restrict__ fr, int N, PairConst* __restrict__ pairs,
+                                                PairAssemble* __restrict__ pasm) {
+  __shared__ SE3d s_et[PBA_MAXF], s_ti[PBA_MAXF], s_ep[PBA_MAXF], s_tl[PBA_MAXF];
+  __shared__ double s_a[PBA_MAXF], s_b[PBA_MAXF];
+  const int tid = threadIdx.x;
+  if (tid < N) {
+    const FrameParams& F = fr[tid];
+    double e[6];
+    for (int k = 0; k < 6; ++k) e[k] = F.eps[k] + F.step[k];
+    se3_exp(e, -1.0, s_et[tid]);
+    se3_exp(e, 1.0, s_ep[tid]);
+    SE3d T;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) T.R[i * 3 + j] = F.T_lin[i * 4 + j];
+      T.t[i] = F.T_lin[i * 4 + 3];
+    }
+    se3_inv(T, s_ti[tid]);
+    s_tl[tid] = T;
+    s_a[tid] = F.ab0[0] + F.eps[6] + F.step[6];
+    s_b[tid] = F.ab0[1] + F.eps[7] + F.step[7];
+  }
+  __syncthreads();
+  for (int p = tid; p < N * (N - 1); p += blockDim.x) {
+    const int r = p / (N - 1);
+    int t = p % (N - 1);
+    t += (t >= r);
+    const FrameParams& R = fr[r];
+    const FrameParams& T = fr[t];
+    SE3d T0, tmp, Tc;
+    se3_mul(s_ti[t], s_tl[r], T0);  // t_t_r0 (evaluate_jacobians.hpp:47-48)
+    se3_mul(T0, s_ep[r], tmp);
+    se3_mul(s_et[t], tmp, Tc);      // t_t_r = exp(-eps_t) T0 exp(eps_r)  (:49)
+    PairConst pc;
+    PairAssemble& pa = pasm[r * PBA_MAXF + t];
+    make_proj(Tc, R.intr, T.intr, pc.M, pc.A);
+    make_proj(T0, R.intr, T.intr, pc.M0, nullptr);
+    for (int i = 0; i < 3; ++i) {
+      pc.tr[i] = (float)Tc.t[i];
+      pc.t0[i] = (float)T0.t[i];
+    }
+    pc.tr[3] = pc.t0[3] = 0.f;
+    double adj_cur[36], adj_fej[36];
+    se3_adj(Tc, adj_cur);
+    se3_adj(T0, adj_fej);
+    for (int i = 0; i < 36; ++i) {
+      pc.adj[i] = (float)adj_cur[i];
+      pc.adj0[i] = (float)adj_fej[i];
+      pa.adj_cur[i] = adj_cur[i];
+      pa.adj_fej[i] = adj_fej[i];
+    }
+    const double ratio = T.exposure / R.exposure;
+    pa.s = ratio * exp(s_a[t] - s_a[r]);
+    pa.s0 = ratio * exp(T.ab0[0] - R.ab0[0]);
+    const int last = (r == N - 1) ? N - 2 : N - 1;  // last target in deque order (quirk Q1)
+    const double s0_last = (fr[last].exposure / R.exposure) * exp(fr[last].ab0[0] - R.ab0[0]);
+    pc.s = (float)pa.s;
+    pc.s0 = (float)pa.s0;
+    pc.s0_last = (float)s0_last;
+    pc.b_t = (float)s_b[t];
+    pc.b_r = (float)s_b[r];
+    pc.b_r0 = (float)R.ab0[1];
+    pc.fx_t = (float)T.intr[0];
+    pc.fy_t = (float)T.intr[1];
+    pc.cx_t = (float)T.intr[2];
+    pc.cy_t = (float)T.intr[3];
+    pc.pad0 = pc.pad1 = 0.f;
+    const float4* src = reinterpret_cast<const float4*>(&pc);
+    float4* dst = reinterpret_cast<float4*>(&pairs[r * PBA_MAXF + t]);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(PairConst) / 16); ++i) dst[i] = src[i];
+  }
+}
+
+// One launch for the serial middle of a device-LM iteration: the energy decision (k_lm_energy), calculateStep
+// (k_lm_step) and the per-pair constants of the new trial state (k_pair_setup) -- three single-CTA kernels and their
+// launch boundaries become one.  with_step = 0: decision only (the last evaluation of a solve).
+template <int DP>
+__global__ void __launch_bounds__(256) k_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed,
+                                                  int N, double* scal, const double* __restrict__ Hp,
+                                                  const double* __restrict__ bp, const double* __restrict__ Hs,
+                                                  const double* __restrict__ bs, const double* __restrict__ Hmarg,
+                                                  const double* __restrict__ bmarg, double* __restrict__ step_dev, int kind,
+                                                  const double2* __restrict__ e_part, int n_e,
+                                                  const double2* __restrict__ n_part, int n_n, int from_core, int with_step,
+                                                  PairConst* __restrict__ pairs, PairAssemble* __restrict__ pasm) {
+  cudaGridDependencySynchronize();
+  stamp(0);
+  lm_energy_body(ctl, opt, fr, N, scal, Hmarg, bmarg, kind, e_part, n_e, n_part, n_n, from_core);
+  stamp(1);
+  if (!with_step) return;
+  __syncthreads();  // ctl / frame state written by thread 0 and the state threads above
+  if (ctl->done) return;
+  lm_step_body<DP>(ctl, opt, fr, fixed, N, Hp, bp, Hs, bs, Hmarg, bmarg, step_dev);
+  __syncthreads();  // fr[].step
+  stamp(20);
+  pair_setup_body(fr, N, pairs, pasm);
+  stamp(21);
+}
+
+
+// Programmatic dependent launch: the kernel may be SCHEDULED while its predecessor in the stream drains (its CTAs are
+// resident and their prologue runs); it calls cudaGridDependencySynchronize() before touching anything the predecessor
+// wrote.  Removes most of the launch gap between the small kernels of a device-LM iteration; captured into the graph as a
+// programmatic edge.
+bool g_pdl = false;  // measured: no effect on the captured LM graph (profiles/r02_ab.md); option "pdl"
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 int max_landmarks(const WindowDev& w) {
   int m = 0;
@@ -2505,6 +3327,47 @@ void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, 
     }
     k_lm_step<128><<<1, 256, smem_of(128), s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
   }
+}
+
+void launch_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, double* scal,
+                     ReduceBuf rb, const double* Hmarg, const double* bmarg, double* step_dev, int kind,
+                     const double* e_part, int n_e, const double* n_part, int n_n, int from_core, int with_step,
+                     PairConst* pairs, PairAssemble* pasm, cudaStream_t s) {
+  const int D = 8 * N;
+  ++g_launches;
+  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP) * sizeof(double); };
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_lm_solve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(64));
+    cudaFuncSetAttribute(k_lm_solve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128));
+    attr_set = true;
+  }
+  if (D <= 64)
+    launch_pdl(k_lm_solve<64>, dim3(1), dim3(256), smem_of(64), s, ctl, opt, fr, fixed, N, scal, (const double*)rb.Hp,
+               (const double*)rb.bp, (const double*)rb.Hs, (const double*)rb.bs, Hmarg, bmarg, step_dev, kind,
+               (const double2*)e_part, n_e, (const double2*)n_part, n_n, from_core, with_step, pairs, pasm);
+  else
+    launch_pdl(k_lm_solve<128>, dim3(1), dim3(256), smem_of(128), s, ctl, opt, fr, fixed, N, scal, (const double*)rb.Hp,
+               (const double*)rb.bp, (const double*)rb.Hs, (const double*)rb.bs, Hmarg, bmarg, step_dev, kind,
+               (const double2*)e_part, n_e, (const double2*)n_part, n_n, from_core, with_step, pairs, pasm);
+}
+
+void launch_reduce_system(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, int with_system, cudaStream_t s,
+                          const LmCtl* ctl) {
+  const int N = w.n_frames, D = 8 * N;
+  if (N < 2 || shape.lpb == 0) return;
+  const int NB = N * (N + 1) / 2;
+  const int T4 = D / 4, nout = T4 * (T4 + 1) / 2 * 16 + D;
+  const int NF = with_system ? (nout + 31) / 32 : 0;
+  const size_t smem = (size_t)std::max(2, N - 1) * RSYS_W * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_reduce_system, cudaFuncAttributeMaxDynamicSharedMemorySize, 15 * RSYS_W * (int)sizeof(double));
+    attr_set = true;
+  }
+  ++g_launches;
+  launch_pdl(k_reduce_system, dim3(NB + NF), dim3(1024), smem, s, w, fej, (const float*)rb.core_part, shape.lpb, shape.chunks,
+             rb.core, rb.Hp, rb.bp, (const float*)rb.fschur_part, rb.Hs, rb.bs, ctl, with_system);
 }
 
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s) {
@@ -2596,6 +3459,9 @@ void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fe
   else k_materialise_sweep<false><<<g, 256, 0, s>>>(w, order, sigma, huber, subs);
 }
 
+int g_fused_version = 2;  // 2: one thread per patch-residual (k_linearize_fused2); 1: 8 lanes per patch-residual
+void set_fused_version(int v) { g_fused_version = v == 1 ? 1 : 2; }
+void set_pdl(bool on) { g_pdl = on; }
 int g_fused_minb = 3;  // resident CTAs per SM the fused linearise is compiled for (N <= 9): 4 -> 64 registers, 3 -> 80
 void set_fused_min_blocks(int b) { g_fused_minb = b <= 3 ? 3 : 4; }
 
@@ -2625,8 +3491,62 @@ static void launch_fused_t(const WindowDev& w, float sigma, int huber, int fej, 
   else launch_fused_tp<NWMAX, MINB, false>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, core, schur, s, ctl, ctl_mode);
 }
 
+template <int NWMAX, int MINB>
+static void launch_fused2_t(const WindowDev& w, float sigma, int huber, int fej, int for_marg, int lpb, dim3 g, int threads,
+                            size_t smem, float* core_part, float* schur_part, cudaStream_t s, const LmCtl* ctl, int ctl_mode,
+                            int fold, const double* step_pose, double2* norms) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_linearize_fused2<true, NWMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_linearize_fused2<false, NWMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr = true;
+  }
+  ++g_launches;
+  if (fej) launch_pdl(k_linearize_fused2<true, NWMAX, MINB>, g, dim3(threads), smem, s, w, sigma, huber, for_marg, lpb, core_part, schur_part, ctl, ctl_mode, fold, step_pose, norms);
+  else launch_pdl(k_linearize_fused2<false, NWMAX, MINB>, g, dim3(threads), smem, s, w, sigma, huber, for_marg, lpb, core_part, schur_part, ctl, ctl_mode, fold, step_pose, norms);
+}
+
+// second generation: `lpb` is a multiple of 32 (a lane owns a landmark); 2 CTAs per SM are resident (<= 144 registers)
+static FusedShape launch_linearize_fused2(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
+                                          cudaStream_t s, const LmCtl* ctl, int ctl_mode, const double* fold_step) {
+  FusedShape shape{0, 0};
+  const int m = max_landmarks(w);
+  if (m == 0 || w.n_frames < 2) return shape;
+  const int N = w.n_frames, D = 8 * N;
+  const long resident = (long)sm_count() * 2;
+  int lpb = 32;
+  double best = 1e300;
+  for (int cand = 32; cand <= 256; cand += 32) {
+    const long blocks = (long)((m + cand - 1) / cand) * N;
+    const double waves = (double)((blocks + resident - 1) / resident);
+    const double cost = waves * (cand / 32 + 0.5);  // per CTA: cand / 32 landmark groups + prologue / epilogue
+    if (cost < best - 1e-9) {
+      best = cost;
+      lpb = cand;
+    }
+  }
+  const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + ((size_t)lpb * (D + 2 + 2 * (N - 1)) + 3) * sizeof(float);
+  dim3 g((m + lpb - 1) / lpb, N);
+  const int threads = 32 * (N - 1);
+  const int fold = fold_step != nullptr && ctl != nullptr;
+  double2* norms = reinterpret_cast<double2*>(rb.n_part);
+  if (N <= 8) launch_fused2_t<7, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms);
+  else if (N <= 9) launch_fused2_t<8, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms);
+  else launch_fused2_t<15, 1>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms);
+  shape.lpb = lpb;
+  shape.chunks = (int)g.x;
+  return shape;
+}
+
+int fused_version() { return g_fused_version; }
+void debug_stamps(int enable, long long out[64]) {
+  cudaMemcpyToSymbol(g_stamps_on, &enable, sizeof(int));
+  if (out) cudaMemcpyFromSymbol(out, g_stamps, 64 * sizeof(long long));
+}
+
 FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, int fej, int for_marg, ReduceBuf rb,
-                                  cudaStream_t s, const LmCtl* ctl, int ctl_mode) {
+                                  cudaStream_t s, const LmCtl* ctl, int ctl_mode, const double* fold_step) {
+  if (g_fused_version == 2) return launch_linearize_fused2(w, sigma, huber, fej, for_marg, rb, s, ctl, ctl_mode, fold_step);
   FusedShape shape{0, 0};
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return shape;

@@ -312,6 +312,10 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value);
 /* ---- measurement hooks (no reference counterpart) --------------------------------------- */
 /* kernels launched by this process so far (every launch wrapper counts itself) */
 int64_t dpba_launch_count(void);
+/* Diagnostics: clock64() stamps taken by thread 0 at the phase boundaries of the single-CTA LM kernel (energy decision,
+ * system fill, the block steps of the LDL^T, back substitution, pair constants) during the LAST launch; enable = 1 arms
+ * the stamping (process-wide), out (may be NULL) receives the 64 stamps of the last launch. */
+int dpba_debug_stamps(int32_t enable, int64_t out[64]);
 /* Per-kernel device timing with CUDA events recorded on the handle's stream around each launch.
  * kinds: 0 fused linearise sweep, 1 Schur SYRK (three-pass path), 2 residual-only sweep, 3 materialising sweep,
  *        4 assemble+symmetrise (three-pass path), 5 back-substitution, 6 per-pair constants,

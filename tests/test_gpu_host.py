@@ -52,7 +52,12 @@ def test_solver_class_solve_and_update_frame():
         assert np.abs(out["T_w_agent"] - f.t_world_agent()[:3, :4]).max() <= 2e-5
         assert np.abs(out["ab"] - f.affine_brightness()).max() <= 2e-5
         act = ~f.lm_marginalized
-        assert np.abs(out["idepth"][act] - f.idepth[act]).max() <= 3e-5
+        # delta_rho = -(b_d - H_pd^T step) / ((1 + lambda) H_dd): the fp32 floor of b_d is amplified by 1 / H_dd, so the
+        # bound scales with the landmark's own inverse-depth standard deviation sqrt(inv_hdd) -- the bound of
+        # test_gpu_parity.py::test_lm_solve_through_the_c_abi_tracks_the_oracle
+        d_id = np.abs(out["idepth"][act] - f.idepth[act])
+        assert (d_id <= 5e-5 + 2e-2 * np.sqrt(np.maximum(f.inv_hdd[act], 0.0))).all(), d_id.max()
+        assert np.mean(d_id <= 5e-5) >= 0.99
         assert (out["outlier"].astype(bool) != f.lm_outlier).sum() <= 1
         assert (out["inliers"] != f.n_inliers).sum() <= 2
         good = ~f.ill & (f.inv_hdd > 0)

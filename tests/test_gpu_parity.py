@@ -242,9 +242,12 @@ def test_lm_solve_through_the_c_abi_tracks_the_oracle(capi, name, ab_scale, ab_r
         sn = np.linalg.norm(b["step"])
         print(f"[lm {name}] it={a['it']} energy rel err {abs(a['energy'] - b['energy']) / abs(b['energy']):.2e} "
               f"step rel err {np.linalg.norm(a['step'] - b['step']) / sn:.2e} |step|={sn:.2e}")
-        # once the iteration converges the step is the difference of two nearby fixed points: absolute floor
-        atol = 2e-5 * max(1.0, max(np.abs(f.ab0).max() for f in win.frames))
-        assert np.linalg.norm(a["step"] - b["step"]) <= RTOL_STEP * sn + atol, (a["it"], np.linalg.norm(a["step"] - b["step"]), sn)
+        # once the iteration converges the step is the difference of two nearby fixed points: absolute floors.  Pose and
+        # affine-gain components: 2e-5.  The affine OFFSET b is subtracted from intensities of 0..255 whose fp32 spacing is
+        # 1.5e-5, so a step in b cannot be resolved below a few of those: 1e-4 (cf. tests/test_golden.py)
+        dstep = np.abs(a["step"] - b["step"]).reshape(-1, 8)
+        assert np.linalg.norm(dstep[:, :7]) <= RTOL_STEP * sn + 2e-5, (a["it"], np.linalg.norm(dstep[:, :7]), sn)
+        assert dstep[:, 7].max() <= RTOL_STEP * sn + 1e-4, (a["it"], dstep[:, 7].max(), sn)
     assert abs(len(tr) - len(tr_ref)) <= 1
     assert abs(e - e_ref) <= 2e-4 * abs(e_ref)
     eps, _ = h.get_state()
