@@ -268,6 +268,8 @@ def run_ours(args):
         if args.peer_exchange:
             capi.attach_peers(h, rank, world, dev)
             h.set_option("peer_exchange", 1)
+            if args.peer_fused >= 0:
+                h.set_option("peer_fused", args.peer_fused)
             h.evaluate(SIGMA, True, True)
 
     ab0 = np.stack([f.ab0 for f in win.frames])
@@ -562,6 +564,7 @@ def main():
     ap.add_argument("--speculative-multi-gpu", type=int, default=-1, help="A/B: one-allreduce speculative device LM for N > 1")
     ap.add_argument("--peer-exchange", action="store_true",
                     help="N > 1: sum the exchange block with the library's NVLink mailbox kernel instead of ncclAllReduce")
+    ap.add_argument("--peer-fused", type=int, default=-1, help="N > 1 with --peer-exchange: 1 = exchange fused into the producers / consumers (default), 0 = stand-alone mailbox kernel")
     ap.add_argument("--fused-prefetch", type=int, default=-1, help="tuning A/B: 0/1 L1 prefetch of the next taps in the fused linearise")
     ap.add_argument("--host-lm", action="store_true", help="drive the LM loop from the C++ host adapter instead of dpba_solve_lm")
     args = ap.parse_args()

@@ -156,6 +156,8 @@ struct dpba_handle {
   pba::PeerDev peer{};
   bool peer_attached = false;
   bool peer_on = false;          // option "peer_exchange"
+  bool peer_fused = true;        // option "peer_fused": inside dpba_solve_lm the exchange rides in the producers' epilogues
+                                 // and the consumers' prologues (no exchange kernel); 0 = the stand-alone mailbox kernel
   // device-side quantile of updatePointStatuses (energy_quantile.cu)
   bool device_quantile = true;   // option "device_quantile" (0: host nth_element over rows read back)
   pba::SelectState* sel_dev = nullptr;
@@ -194,7 +196,9 @@ constexpr size_t N_RED = 2 * (MAXD * MAXD + MAXD) + 8;
 constexpr size_t N_EXCHANGE = N_RED;
 static_assert(N_EXCHANGE % 2 == 0, "the peer exchange moves double2");
 constexpr size_t PEER_BOX_DATA = 2 * (size_t)pba::PEER_MAXW * N_EXCHANGE;  // doubles
-constexpr size_t PEER_BOX_BYTES = PEER_BOX_DATA * sizeof(double) + (size_t)pba::PEER_MAXW * pba::PEER_MAXC * sizeof(unsigned);
+constexpr size_t PEER_BOX_FLAGS = (size_t)pba::PEER_MAXW * pba::PEER_MAXC;  // words
+constexpr size_t PEER_BOX_COUNTERS = 2 * 2 * (size_t)pba::PEER_MAXW;         // words: [parity][kind][source]
+constexpr size_t PEER_BOX_BYTES = PEER_BOX_DATA * sizeof(double) + (PEER_BOX_FLAGS + PEER_BOX_COUNTERS) * sizeof(unsigned);
 
 // several ranks AND a way to sum over them (NCCL communicator or attached peer mailboxes)
 inline bool multi_gpu(const dpba_handle* h) { return h->world > 1 && (h->comm || h->peer_on); }
@@ -1658,6 +1662,10 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
   // of linearisation k and the energy of the state it was taken at cross NVLink together; every rank then takes the
   // same decision from the same sums.
   if (h->speculative && h->speculative_multi && od.force_accept && multi) {
+    // fused exchange (peer mailboxes attached, option peer_exchange + peer_fused): no collective call and no exchange
+    // kernel -- the producers push into every rank's mailbox, k_lm_energy / k_lm_step wait, sum in rank order and close
+    const int fx = (h->peer_on && h->peer_attached && h->peer_fused) ? 1 : 0;
+    const int sys_ctas = pba::system_producer_ctas(N);
     FusedShape shape;
     for (int k = 0; k <= od.max_it; ++k) {
       const bool more = k < od.max_it;
@@ -1668,25 +1676,26 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
       if (more) {
         if ((rc = stream_edge(h, s, s2))) return rc;
         ProfScope ps(h, 10, s2);
-        pba::launch_finish_fused(w, rb, shape, s2, h->ctl);
+        pba::launch_finish_fused(w, rb, shape, s2, h->ctl, fx);
       }
       {
         ProfScope ps(h, 8);
         pba::launch_core_reduce(w, rb, shape, s, h->ctl);
       }
-      pba::launch_reduce_scal(h->ctl, 1, rb.core, N * (N - 1), k ? rb.n_part : nullptr, k ? n_norm_parts : 0, rb.scal, s, N);
+      pba::launch_reduce_scal(h->ctl, 1, rb.core, N * (N - 1), k ? rb.n_part : nullptr, k ? n_norm_parts : 0, rb.scal, s, N, fx);
       if (more) {
         {
           ProfScope ps(h, 9);
-          pba::launch_assemble_blocks(w, fej, rb, shape, s, h->ctl);
+          pba::launch_assemble_blocks(w, fej, rb, shape, s, h->ctl, fx);
         }
         if ((rc = stream_edge(h, s2, s))) return rc;
       }
-      if ((rc = exchange(h, more ? EX_ALL : EX_SCAL))) return rc;
+      if (!fx && (rc = exchange(h, more ? EX_ALL : EX_SCAL))) return rc;
       {
         ProfScope ps(h, 11);
         pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, ro.scal, Hm, bm,
-                              k == 0 ? pba::LM_ENERGY_INITIAL : pba::LM_ENERGY_TRIAL, s);
+                              k == 0 ? pba::LM_ENERGY_INITIAL : pba::LM_ENERGY_TRIAL, s, nullptr, 0, nullptr, 0, 0,
+                              fx ? (more ? 1 : 2) : 0);
       }
       if (k > 0) {
         if ((rc = stream_edge(h, s, s2))) return rc;
@@ -1699,7 +1708,7 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
       }
       {
         ProfScope ps(h, 7);
-        pba::launch_lm_step(h->ctl, h->lmopt, h->fparams, h->fixed_dev, N, ro, Hm, bm, h->step_dev, s);
+        pba::launch_lm_step(h->ctl, h->lmopt, h->fparams, h->fixed_dev, N, ro, Hm, bm, h->step_dev, s, fx ? sys_ctas : 0);
       }
       if (k > 0 && (rc = stream_edge(h, s2, s))) return rc;
       if ((rc = stream_edge(h, s, s2))) return rc;
@@ -1823,7 +1832,8 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   // replay it (one cudaGraphLaunch instead of ~110 launches per solve); all inputs travel through pinned buffers.
   std::vector<long long> key = {N, od.max_it, od.fej, H_marg != nullptr, h->world, (long long)h->profiling,
                                 (long long)(h->speculative && od.force_accept), (long long)h->speculative_multi,
-                                (long long)llround(od.sigma * 1e6), (long long)h->peer_on, (long long)h->merged_tail,
+                                (long long)llround(od.sigma * 1e6), (long long)h->peer_on + 2 * (long long)h->peer_fused,
+                                (long long)h->merged_tail,
                                 (long long)pba::fused_version()};
   for (int f = 0; f < N; ++f) {  // every per-frame field of WindowDev (the captured kernels hold it BY VALUE)
     key.push_back(h->fr[f].n_lm);
@@ -1962,6 +1972,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "peer_fused")) {
+    h->peer_fused = value != 0;
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
   if (!strcmp(name, "pdl")) {  // process-wide: programmatic dependent launch between the kernels of the device LM
     pba::set_pdl(value != 0);
     h->lm_graph_key.clear();
@@ -2080,7 +2095,9 @@ int dpba_peer_attach(dpba_handle* h, const uint8_t* handles, int32_t rank, int32
     }
     pd.data[r] = static_cast<double*>(base);
     pd.flag[r] = reinterpret_cast<unsigned*>(static_cast<double*>(base) + PEER_BOX_DATA);
+    pd.cnt[r] = pd.flag[r] + PEER_BOX_FLAGS;
   }
+  pd.red_base = h->red;
   pd.seq = h->peer_ctr;
   pd.done = h->peer_ctr + 1;
   int* err_dev = nullptr;
@@ -2091,6 +2108,8 @@ int dpba_peer_attach(dpba_handle* h, const uint8_t* handles, int32_t rank, int32
   pd.world = world;
   pd.slot = N_EXCHANGE;
   h->peer = pd;
+  pba::set_peer_context(pd);  // process-wide __device__ copy for the fused exchange (one sharded handle per process)
+  CK(cudaGetLastError());
   h->world = world;
   h->rank = rank;
   h->peer_attached = true;

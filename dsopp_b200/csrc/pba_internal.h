@@ -123,11 +123,15 @@ namespace pba {
 // kinds for launch_lm_energy
 enum { LM_ENERGY_INITIAL = 0, LM_ENERGY_TRIAL = 1, LM_ENERGY_FINAL = 2 };
 void launch_lm_init(LmCtl* ctl, const LmOptionsDev* opt, cudaStream_t s);
+// peer_collect (fused exchange): 1 = wait for every rank's scalars and sum them in rank order into `scal` first;
+// 2 = the same and close the exchange (no calculateStep follows)
 void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, double* scal,
                       const double* Hmarg, const double* bmarg, int kind, cudaStream_t s, const double* e_part = nullptr,
-                      int n_e = 0, const double* n_part = nullptr, int n_n = 0, int from_core = 0);
+                      int n_e = 0, const double* n_part = nullptr, int n_n = 0, int from_core = 0, int peer_collect = 0);
+// peer_expected > 0 (fused exchange): wait for that many system arrivals per rank, sum the ranks' blocks in rank order
+// into rb (contiguous [H_pp | b_p | H_s | b_s]) and close the exchange
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
-                    const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s);
+                    const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s, int peer_expected = 0);
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
 // round 2: energy decision + calculateStep + per-pair constants of the trial state in one single-CTA launch
 void launch_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, double* scal,
@@ -147,8 +151,9 @@ void launch_downscale(const float* src, float* dst, int W, int H, cudaStream_t s
 void launch_pixelinfo3(const float* I, float* dst, int W, int H, cudaStream_t s);
 int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, double* e_part, cudaStream_t s,
                           const LmCtl* ctl = nullptr, int ctl_mode = 0);
+// peer_push != 0 (fused exchange): the kernel also stores its results into every rank's mailbox and counts its arrival
 void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, int n_e, const double* n_part, int n_n,
-                        double* scal, cudaStream_t s, int core_frames = 0);
+                        double* scal, cudaStream_t s, int core_frames = 0, int peer_push = 0);
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s);
 // fold_step (second-generation kernel, device LM only): the pose step whose back-substitution -- together with the
 // acceptStep / rejectStep of the previous trial -- this sweep performs for its own landmarks before evaluating; the
@@ -164,9 +169,12 @@ void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape
                      const LmCtl* ctl = nullptr);
 void launch_core_reduce(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_assemble_blocks(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,
-                            const LmCtl* ctl = nullptr);
+                            const LmCtl* ctl = nullptr, int peer_push = 0);
+// number of CTAs of launch_assemble_blocks + launch_finish_fused for a window of N frames (arrivals per rank, kind 1)
+int system_producer_ctas(int n_frames);
 void launch_finish_system(int D, ReduceBuf rb, int nsb, cudaStream_t s, const LmCtl* ctl = nullptr);
-void launch_finish_fused(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl = nullptr);
+void launch_finish_fused(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl = nullptr,
+                         int peer_push = 0);
 void launch_back_substitute(const WindowDev& w, const double* step_pose_dev, double lambda, cudaStream_t s,
                             const LmCtl* ctl = nullptr, double* norms = nullptr);
 void launch_accept(const WindowDev& w, int accept, double* scal, cudaStream_t s, const LmCtl* ctl = nullptr,
@@ -200,7 +208,14 @@ struct PeerDev {
   int* error_host;            // the same flag in mapped pinned host memory, for the host to read after a synchronisation
   int rank, world;
   size_t slot;                // doubles per [parity][source] slot
+  // fused exchange (round 2): arrival COUNTERS of rank r's mailbox, [2 parities][2 kinds][PEER_MAXW sources]; every
+  // producer CTA of source s adds one to its counter in every mailbox after its pushes (kind 0: the 8 scalars, kind 1:
+  // the system [H_pp | b_p | H_s | b_s])
+  unsigned* cnt[PEER_MAXW];
+  const double* red_base;     // local exchange block the producers write: element index = pointer - red_base
 };
+// context of the fused exchange, copied to a __device__ symbol when the peers are attached (process-wide)
+void set_peer_context(const PeerDev& pd);
 void launch_peer_allreduce(const PeerDev& pd, const double* in, double* out, size_t off, size_t n, cudaStream_t s);
 
 // ---- device-side quantile of updatePointStatuses (energy_quantile.cu) -------------------------------------------------

@@ -112,6 +112,93 @@ __device__ __forceinline__ void stamp(int i) {
   if (g_stamps_on && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_stamps[i] = clock64();
 }
 
+// ---- fused exchange over NVLink peer memory (round 2) -------------------------------------------------------------------
+// The sharded solve sums ONE block per iteration over the ranks ([H_pp | b_p | H_s | b_s | 8 scalars], 66.6 KB at 8
+// keyframes).  As a separate collective (ncclAllReduce, or the stand-alone mailbox kernel of peer_exchange.cu) it costs
+// 22-52 us per iteration on 2-8 B200s -- launch boundaries and a latency-bound kernel between the producers and the LM
+// step.  Here the exchange has no kernel of its own: the PRODUCERS (k_assemble, k_finish_fused, k_reduce_scal) store every
+// result into slot [parity][rank] of every rank's mailbox while they write it locally (posted NVLink stores), fence, and
+// add one to their arrival counter in every mailbox (red.release.sys); the CONSUMERS (k_lm_energy, k_lm_step) wait for the
+// counters of all ranks (ld.acquire.sys, with a time-out), sum the W slots IN RANK ORDER from local L2 -- every rank adds
+// the same values in the same order, so the replicated LM step stays bitwise identical -- and bump the epoch.  Parity and
+// epoch are those of peer_exchange.cu (one counter for both kinds of exchange), so the two can interleave.
+__device__ pba::PeerDev g_peer;
+__device__ __forceinline__ unsigned peer_epoch() { return *reinterpret_cast<volatile unsigned*>(g_peer.seq) + 1u; }
+__device__ __forceinline__ void red_store(double* p, double v, int peer_push, unsigned epoch) {
+  *p = v;
+  if (peer_push) {
+    const size_t idx = (size_t)(p - g_peer.red_base);
+    const size_t off = ((size_t)(epoch & 1u) * pba::PEER_MAXW + (size_t)g_peer.rank) * g_peer.slot + idx;
+#pragma unroll
+    for (int r = 0; r < pba::PEER_MAXW; ++r)
+      if (r < g_peer.world) g_peer.data[r][off] = v;
+  }
+}
+// all threads of a producer CTA, after their red_store()s
+__device__ __forceinline__ void peer_arrive(int kind, unsigned epoch) {
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < g_peer.world) {
+    unsigned* c = nullptr;
+#pragma unroll
+    for (int r = 0; r < pba::PEER_MAXW; ++r)
+      if (r == (int)threadIdx.x) c = g_peer.cnt[r];
+    c += ((epoch & 1u) * 2 + kind) * pba::PEER_MAXW + g_peer.rank;
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+  }
+}
+// all threads of the (single) consumer CTA: returns once `expected` arrivals of kind `kind` from every rank are visible
+__device__ __forceinline__ void peer_wait_arrivals(int kind, unsigned epoch, unsigned expected) {
+  if ((int)threadIdx.x < g_peer.world) {
+    const unsigned* c = nullptr;
+#pragma unroll
+    for (int r = 0; r < pba::PEER_MAXW; ++r)
+      if (r == g_peer.rank) c = g_peer.cnt[r];
+    c += ((epoch & 1u) * 2 + kind) * pba::PEER_MAXW + threadIdx.x;
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+      if (v >= expected || *reinterpret_cast<volatile int*>(g_peer.error)) break;
+      if (clock64() - t0 > 30000000000LL) {  // ~15 s: a peer that has not arrived by then has failed (DPBA_E_COMM)
+        *reinterpret_cast<volatile int*>(g_peer.error) = 1;
+        *reinterpret_cast<volatile int*>(g_peer.error_host) = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+// all threads: out[i] = sum over ranks (in rank order) of slot [parity][r][off + i], i < n
+__device__ __forceinline__ void peer_collect(double* out, size_t off, int n, unsigned epoch) {
+  const double* box = nullptr;
+#pragma unroll
+  for (int r = 0; r < pba::PEER_MAXW; ++r)
+    if (r == g_peer.rank) box = g_peer.data[r];
+  box += (size_t)(epoch & 1u) * pba::PEER_MAXW * g_peer.slot + off;
+  const int W = g_peer.world;
+  for (int i = 2 * threadIdx.x; i < n; i += 2 * blockDim.x) {  // off and n are even
+    double2 acc = __ldcg(reinterpret_cast<const double2*>(box + i));
+    for (int r = 1; r < W; ++r) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(box + (size_t)r * g_peer.slot + i));
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+    *reinterpret_cast<double2*>(out + i) = acc;
+  }
+}
+// thread 0 of the consumer, after a barrier: counters of this parity back to zero, epoch published
+__device__ __forceinline__ void peer_close(unsigned epoch) {
+  unsigned* c = nullptr;
+#pragma unroll
+  for (int r = 0; r < pba::PEER_MAXW; ++r)
+    if (r == g_peer.rank) c = g_peer.cnt[r];
+  c += (epoch & 1u) * 2 * pba::PEER_MAXW;
+  for (int i = 0; i < 2 * pba::PEER_MAXW; ++i) *reinterpret_cast<volatile unsigned*>(c + i) = 0u;
+  __threadfence();
+  *reinterpret_cast<volatile unsigned*>(g_peer.seq) = epoch;
+}
+
 // MUFU.RSQ / MUFU.RCP (<= 2 ulp) without the denormal fix-up code of rsqrtf() / 1.f / x; used only where no connection
 // status depends on the result (Huber weight, Jacobians)
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -448,8 +535,9 @@ __global__ void __launch_bounds__(480) k_residual_sweep(const __grid_constant__ 
 __global__ void __launch_bounds__(1024) k_reduce_scal(const LmCtl* __restrict__ ctl, int ctl_mode,
                                                       const double2* __restrict__ e_part, int n_e,
                                                       const double2* __restrict__ n_part, int n_n,
-                                                      double* __restrict__ scal, int core_frames) {
+                                                      double* __restrict__ scal, int core_frames, int peer_push) {
   if (lm_skip(ctl, ctl_mode)) return;
+  const unsigned epoch = peer_push ? peer_epoch() : 0u;
   __shared__ double s[4][32];
   double a = 0, b = 0, c = 0, d = 0;
   for (int i = threadIdx.x; i < n_e; i += blockDim.x) {
@@ -499,15 +587,17 @@ __global__ void __launch_bounds__(1024) k_reduce_scal(const LmCtl* __restrict__ 
     }
     if (lane == 0) {
       if (e_part) {
-        scal[0] = a;
-        scal[1] = b;
+        red_store(&scal[0], a, peer_push, epoch);
+        red_store(&scal[1], b, peer_push, epoch);
       }
-      if (n_part) {
-        scal[2] = c;
-        scal[3] = d;
+      // the fused exchange always carries all four scalars (a consumer sums whatever is in the slot)
+      if (n_part || peer_push) {
+        red_store(&scal[2], c, peer_push, epoch);
+        red_store(&scal[3], d, peer_push, epoch);
       }
     }
   }
+  if (peer_push) peer_arrive(0, epoch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1779,8 +1869,9 @@ __device__ __forceinline__ double bm_at(const PairAssemble& pa, int fej, int i, 
 constexpr int ASM_W = 264;  // doubles of shared memory per warp: C, B, T1, out (64 each) + b (8)
 __global__ void __launch_bounds__(512) k_assemble(const __grid_constant__ WindowDev w, int fej,
                                                   const double* __restrict__ core, double* __restrict__ Hp,
-                                                  double* __restrict__ bp, const LmCtl* __restrict__ ctl) {
+                                                  double* __restrict__ bp, const LmCtl* __restrict__ ctl, int peer_push) {
   if (lm_skip(ctl, 2)) return;
+  const unsigned epoch = peer_push ? peer_epoch() : 0u;
   extern __shared__ double asm_sm[];
   const int N = w.n_frames, D = 8 * N;
   // blockIdx.x enumerates the upper-triangular block pairs (bi <= bj)
@@ -1850,28 +1941,30 @@ __global__ void __launch_bounds__(512) k_assemble(const __grid_constant__ Window
     const int oi = o >> 3, oj = o & 7;
     if (!diag) {
       const double acc = asm_sm[oi * 8 + oj + 192] + asm_sm[ASM_W + oj * 8 + oi + 192];
-      Hp[(size_t)(8 * bi + oi) * D + 8 * bj + oj] = acc;
-      Hp[(size_t)(8 * bj + oj) * D + 8 * bi + oi] = acc;
+      red_store(&Hp[(size_t)(8 * bi + oi) * D + 8 * bj + oj], acc, peer_push, epoch);
+      red_store(&Hp[(size_t)(8 * bj + oj) * D + 8 * bi + oi], acc, peer_push, epoch);
     } else {
       const int ii = max(oi, oj), jj = min(oi, oj);  // selfadjointView<Lower>
       double acc = 0;
       for (int wi = 0; wi < nterms; ++wi) acc += asm_sm[wi * ASM_W + 192 + ii * 8 + jj];
-      Hp[(size_t)(8 * bi + oi) * D + 8 * bi + oj] = acc;
+      red_store(&Hp[(size_t)(8 * bi + oi) * D + 8 * bi + oj], acc, peer_push, epoch);
       if (oj == 0) {
         double bacc = 0;
         for (int wi = 0; wi < nterms; ++wi) bacc += asm_sm[wi * ASM_W + 256 + oi];
-        bp[8 * bi + oi] = bacc;
+        red_store(&bp[8 * bi + oi], bacc, peer_push, epoch);
       }
     }
   }
+  if (peer_push) peer_arrive(1, epoch);
 }
 
 // second stage of the fused path's Schur reduction: out[o] = sum over the chunk CTAs of part[cta][o], o over the
 // 4x4 upper-triangle tiles and b.  16 groups of 64 outputs per CTA; each group strides over the chunk CTAs.
 __global__ void __launch_bounds__(1024) k_finish_fused(const __grid_constant__ WindowDev w, int lpb, int chunks,
                                                        const float* __restrict__ part, double* __restrict__ Hs,
-                                                       double* __restrict__ bs, const LmCtl* __restrict__ ctl) {
+                                                       double* __restrict__ bs, const LmCtl* __restrict__ ctl, int peer_push) {
   if (lm_skip(ctl, 2)) return;
+  const unsigned epoch = peer_push ? peer_epoch() : 0u;
   __shared__ double red[32][33];
   const int N = w.n_frames, D = 8 * N;
   const int T4 = D / 4, ntri = T4 * (T4 + 1) / 2, nout = ntri * 16 + D;
@@ -1912,7 +2005,7 @@ __global__ void __launch_bounds__(1024) k_finish_fused(const __grid_constant__ W
 #pragma unroll
     for (int k = 0; k < 32; ++k) s += red[k][oo];
     if (o >= ntri * 16) {
-      bs[o - ntri * 16] = s;
+      red_store(&bs[o - ntri * 16], s, peer_push, epoch);
     } else {
       const int tile = o >> 4, e = o & 15;
       int ty = 0, rem = tile;
@@ -1922,11 +2015,12 @@ __global__ void __launch_bounds__(1024) k_finish_fused(const __grid_constant__ W
       }
       const int r = 4 * ty + (e >> 2), cc = 4 * (ty + rem) + (e & 3);
       if (r <= cc) {  // diagonal tiles also carry r > cc: dropped, the mirror keeps H_s exactly symmetric
-        Hs[(size_t)r * D + cc] = s;
-        Hs[(size_t)cc * D + r] = s;
+        red_store(&Hs[(size_t)r * D + cc], s, peer_push, epoch);
+        if (r != cc) red_store(&Hs[(size_t)cc * D + r], s, peer_push, epoch);
       }
     }
   }
+  if (peer_push) peer_arrive(1, epoch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2936,7 +3030,17 @@ __device__ __forceinline__ void lm_energy_body(LmCtl* ctl, const LmOptionsDev* o
 __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
                                                    int N, double* scal, const double* Hmarg,
                                                    const double* bmarg, int kind, const double2* __restrict__ e_part,
-                                                   int n_e, const double2* __restrict__ n_part, int n_n, int from_core) {
+                                                   int n_e, const double2* __restrict__ n_part, int n_n, int from_core,
+                                                   int peer_collect_mode, int peer_scal_off) {
+  if (peer_collect_mode && !(kind == pba::LM_ENERGY_TRIAL && ctl->done)) {
+    // fused exchange: the scalars of every rank (one arrival each), summed in rank order
+    const unsigned epoch = peer_epoch();
+    peer_wait_arrivals(0, epoch, 1u);
+    peer_collect(scal, (size_t)peer_scal_off, 8, epoch);
+    __syncthreads();
+    if (peer_collect_mode == 2 && threadIdx.x == 0) peer_close(epoch);
+    __syncthreads();
+  }
   lm_energy_body(ctl, opt, fr, N, scal, Hmarg, bmarg, kind, e_part, n_e, n_part, n_n, from_core);
 }
 
@@ -3145,7 +3249,17 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
                                                  const int* fixed, int N, const double* __restrict__ Hp,
                                                  const double* __restrict__ bp, const double* __restrict__ Hs,
                                                  const double* __restrict__ bs, const double* __restrict__ Hmarg,
-                                                 const double* __restrict__ bmarg, double* __restrict__ step_dev) {
+                                                 const double* __restrict__ bmarg, double* __restrict__ step_dev,
+                                                 int peer_expected, double* sys_out, int n_sys) {
+  if (peer_expected && !ctl->done) {
+    // fused exchange: [H_pp | b_p | H_s | b_s] of every rank, summed in rank order into the block lm_step_body reads
+    const unsigned epoch = peer_epoch();
+    peer_wait_arrivals(1, epoch, (unsigned)peer_expected);
+    peer_collect(sys_out, 0, n_sys, epoch);
+    __syncthreads();
+    if (threadIdx.x == 0) peer_close(epoch);
+    __syncthreads();
+  }
   lm_step_body<DP>(ctl, opt, fr, fixed, N, Hp, bp, Hs, bs, Hmarg, bmarg, step_dev);
 }
 
@@ -3306,26 +3420,30 @@ void launch_lm_init(LmCtl* ctl, const LmOptionsDev* opt, cudaStream_t s) {
 
 void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int N, double* scal,
                       const double* Hmarg, const double* bmarg, int kind, cudaStream_t s, const double* e_part, int n_e,
-                      const double* n_part, int n_n, int from_core) {
+                      const double* n_part, int n_n, int from_core, int peer_collect) {
   ++g_launches;
+  const int D = 8 * N;
   k_lm_energy<<<1, 256, 0, s>>>(ctl, opt, fr, N, scal, Hmarg, bmarg, kind, reinterpret_cast<const double2*>(e_part), n_e,
-                                reinterpret_cast<const double2*>(n_part), n_n, from_core);
+                                reinterpret_cast<const double2*>(n_part), n_n, from_core, peer_collect, 2 * (D * D + D));
 }
 
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
-                    const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s) {
+                    const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s, int peer_expected) {
   const int D = 8 * N;
+  const int n_sys = 2 * (D * D + D);
   ++g_launches;
   auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP) * sizeof(double); };
   if (D <= 64) {
-    k_lm_step<64><<<1, 256, smem_of(64), s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
+    k_lm_step<64><<<1, 256, smem_of(64), s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev,
+                                              peer_expected, rb.Hp, n_sys);
   } else {
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(k_lm_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128));
       attr_set = true;
     }
-    k_lm_step<128><<<1, 256, smem_of(128), s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev);
+    k_lm_step<128><<<1, 256, smem_of(128), s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev,
+                                                peer_expected, rb.Hp, n_sys);
   }
 }
 
@@ -3427,10 +3545,17 @@ int launch_residual_sweep(const WindowDev& w, float sigma, int huber, int fej, d
 }
 
 void launch_reduce_scal(const LmCtl* ctl, int ctl_mode, const double* e_part, int n_e, const double* n_part, int n_n,
-                        double* scal, cudaStream_t s, int core_frames) {
+                        double* scal, cudaStream_t s, int core_frames, int peer_push) {
   ++g_launches;
   k_reduce_scal<<<1, 1024, 0, s>>>(ctl, ctl_mode, reinterpret_cast<const double2*>(e_part), n_e,
-                                   reinterpret_cast<const double2*>(n_part), n_n, scal, core_frames);
+                                   reinterpret_cast<const double2*>(n_part), n_n, scal, core_frames, peer_push);
+}
+
+void set_peer_context(const PeerDev& pd) { cudaMemcpyToSymbol(g_peer, &pd, sizeof(PeerDev)); }
+
+int system_producer_ctas(int n_frames) {
+  const int D = 8 * n_frames, T4 = D / 4, nout = T4 * (T4 + 1) / 2 * 16 + D;
+  return n_frames * (n_frames + 1) / 2 + (nout + 31) / 32;
 }
 
 void launch_materialise_sweep(const WindowDev& w, float sigma, int huber, int fej, cudaStream_t s) {
@@ -3626,12 +3751,13 @@ void launch_core_reduce(const WindowDev& w, ReduceBuf rb, FusedShape shape, cuda
 }
 
 void launch_assemble_blocks(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,
-                            const LmCtl* ctl) {
+                            const LmCtl* ctl, int peer_push) {
   const int N = w.n_frames;
   if (N < 2 || shape.lpb == 0) return;
   ++g_launches;
   const int threads = 32 * std::max(2, N - 1);
-  k_assemble<<<N * (N + 1) / 2, threads, (size_t)(threads / 32) * ASM_W * sizeof(double), s>>>(w, fej, rb.core, rb.Hp, rb.bp, ctl);
+  k_assemble<<<N * (N + 1) / 2, threads, (size_t)(threads / 32) * ASM_W * sizeof(double), s>>>(w, fej, rb.core, rb.Hp, rb.bp, ctl,
+                                                                                                peer_push);
 }
 
 void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl) {
@@ -3641,12 +3767,12 @@ void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape
 
 // fused path: sums the per-chunk Schur partials written by k_linearize_fused and mirrors H_s (k_assemble already
 // wrote a symmetric Hp)
-void launch_finish_fused(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl) {
+void launch_finish_fused(const WindowDev& w, ReduceBuf rb, FusedShape shape, cudaStream_t s, const LmCtl* ctl, int peer_push) {
   const int N = w.n_frames, D = 8 * N;
   if (N < 2 || shape.lpb == 0) return;
   const int T4 = D / 4, nout = T4 * (T4 + 1) / 2 * 16 + D;
   ++g_launches;
-  k_finish_fused<<<(nout + 31) / 32, 1024, 0, s>>>(w, shape.lpb, shape.chunks, rb.fschur_part, rb.Hs, rb.bs, ctl);
+  k_finish_fused<<<(nout + 31) / 32, 1024, 0, s>>>(w, shape.lpb, shape.chunks, rb.fschur_part, rb.Hs, rb.bs, ctl, peer_push);
 }
 
 // sums the Schur partials of `nsb` CTAs into Hs / bs (skipped when nsb == 0 and Hs == nullptr) and symmetrises Hp

@@ -13,4 +13,6 @@ timeout 300 $RUN --master-port 29514 bench.py --gpus $N --no-cpu --no-big-sweep 
 echo "exit $?" >> gpurun_out/${tag}_bench_peer.err
 grep -h "MULTIGPU_CHECK\|exit\|peer exchange\|threshold\|Error\|error" gpurun_out/${tag}_check_nccl.log gpurun_out/${tag}_check_peer.log | tail -30
 tail -n 3 gpurun_out/${tag}_bench_nccl.err gpurun_out/${tag}_bench_peer.err
-for f in gpurun_out/${tag}_bench_nccl.json gpurun_out/${tag}_bench_peer.json; do python tools/bench_summary.py $f; done
+timeout 300 $RUN --master-port 29515 bench.py --gpus $N --no-cpu --no-big-sweep --peer-exchange --peer-fused 0 > gpurun_out/${tag}_bench_peer_kernel.json 2> gpurun_out/${tag}_bench_peer_kernel.err
+echo "exit $?" >> gpurun_out/${tag}_bench_peer_kernel.err
+for f in gpurun_out/${tag}_bench_nccl.json gpurun_out/${tag}_bench_peer.json gpurun_out/${tag}_bench_peer_kernel.json; do echo $f; python tools/bench_summary.py $f; done
