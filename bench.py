@@ -443,6 +443,80 @@ def run_ours(args):
             h4.close()
             del win4
 
+    # ---- configs[3]: the large window north_star shards -- 8 keyframes x 20000 points (1.12 M patch-residuals), STRONG
+    # scaling: the same window on every N, landmarks dealt over the ranks, one exchange of the reduced system per GN
+    # iteration.  Every --gpus N line carries it, so the N = 1, 2, 4, 8 lines give the strong curve.  With N > 1 rank 0 also
+    # linearises the UNSHARDED window on its own GPU and compares: the exchanged system must equal it.
+    config3 = None
+    if not args.no_config3:
+        from dsopp_b200 import synth
+        win3 = synth.make_window(n_frames=N_FRAMES, points_per_frame=20000, seed=1, ab_scale=0.0)
+        h3 = capi.upload_window(win3, device=local, rank=rank, world_size=world)
+        shard3 = [np.arange(rank, len(f.idepth), world) for f in win3.frames]
+        eps3 = np.concatenate([f.state_eps for f in win3.frames])
+        if world > 1:
+            uid3 = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid3.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid3, 0)
+            h3.comm_init(bytes(uid3.cpu().numpy().tobytes()), rank, world)
+        h3.first_estimate()
+        sys3 = h3.linearize(SIGMA, True, True, False)  # also the first collective of this communicator (outside capture)
+        check3 = None
+        if world > 1 and rank == 0:
+            href = capi.upload_window(win3, device=local)
+            href.first_estimate()
+            ref3 = href.linearize(SIGMA, True, True, False)
+            href.close()
+            errs = {nm: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+                    for nm, a, b in zip(("H_pose", "b_pose", "H_schur", "b_schur"), sys3, ref3)}
+            check3 = {"sharded_vs_unsharded_rel_max": errs, "ok": bool(max(errs.values()) <= 1e-9),
+                      "what": "rank 0: dpba_linearize of the window sharded over N ranks (exchanged sum) against the same "
+                              "window unsharded on one GPU; fp64 sums in a different order"}
+        stream3 = torch.cuda.ExternalStream(h3.stream, device=dev)
+
+        def reset3():
+            for i, f in enumerate(win3.frames):
+                h3.set_landmarks(i, f.uv[shard3[i]], f.idepth[shard3[i]], f.patch[shard3[i]], f.flags[shard3[i]])
+            for (r_, t_), st_ in win3.statuses.items():
+                h3.set_statuses(r_, t_, st_[shard3[r_]])
+            h3.set_state(eps3, np.zeros_like(eps3))
+
+        def solve3():
+            h3.first_estimate()
+            return h3.solve_lm(SIGMA, AB_REG, FIXED_REG, max_it=GN_ITERS, min_it=GN_ITERS, ftol=0.0, ptol=0.0, force_accept=True,
+                               lambda0=1e-5)
+
+        ms3, res3 = [], None
+        for i in range(3 + 10):
+            reset3()
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream3)
+            res3 = solve3()
+            a1.record(stream3)
+            torch.cuda.synchronize()
+            if i >= 3:
+                ms3.append(a0.elapsed_time(a1))
+        t3 = torch.tensor([sum(ms3)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        ms_step3 = float(t3.item()) / len(ms3)
+        config3 = {"workload": f"configs[3]: {N_FRAMES} keyframes x 20000 points/KF ({win3.units} patch-residuals), landmarks "
+                               f"sharded over {world} GPU(s) (strong scaling), one exchange of the reduced 8N x 8N system per GN iteration",
+                   "value": win3.units * GN_ITERS / (ms_step3 * 1e-3), "unit": UNIT, "ms_per_step": ms_step3,
+                   "us_per_gn_iter": 1e3 * ms_step3 / GN_ITERS, "steps": len(ms3), "energy": float(res3[0]),
+                   "iterations": int(res3[1]), "n_gpus": world, "scaling": "strong", "multi_gpu_check": check3}
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        h3.close()
+        del win3
+
     def teardown():
         # ordered shutdown, then a normal interpreter exit: the handle first (dpba_destroy destroys the captured LM graph
         # BEFORE its NCCL communicator -- a graph that still references the communicator's kernels is what used to block
@@ -543,6 +617,7 @@ def run_ours(args):
         "kernel_ms": kernel_ms,
         "cpu_baseline": cpu,
         "parity_check": parity_check,
+        "config3_strong": config3,
         "us_per_gn_iter": 1e3 * total_ms / args.steps / GN_ITERS,
     }
     print(json.dumps(out), flush=True)
@@ -556,6 +631,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config3", action="store_true", help="skip the configs[3] strong-scaling leg (8 KF x 20000 points)")
     ap.add_argument("--no-big-sweep", action="store_true", help="skip the 20000-points/KF materialising-sweep roofline")
     ap.add_argument("--fused-min-blocks", type=int, default=0, help="tuning A/B: 3 or 4 resident CTAs/SM for the fused linearise")
     ap.add_argument("--fused-version", type=int, default=0, help="A/B: 1 = first-generation fused linearise (8 lanes per patch), 2 = one thread per patch-residual")

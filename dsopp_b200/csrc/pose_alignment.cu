@@ -189,9 +189,17 @@ struct PaShared {
   int n_valid, converged, iteration, go;
 };
 
-// one sweep over the landmarks at the state in sh.T / sh.ab_eps; leaves the cluster-wide sums in sh.tot
-__device__ void pa_sweep(const PaProblem& p, PaShared& sh, cg::cluster_group& cluster, int parity) {
+// one sweep over the landmarks at the state in sh.T / sh.ab_eps; leaves the sums over ALL CTAs in sh.tot.
+// GRID = false: the CTAs are the 8 of one thread-block cluster, their partial sums meet through distributed shared
+// memory after a cluster barrier.  GRID = true (round 2, dense depth maps): the CTAs are a cooperative grid with one CTA
+// per SM, the partial sums meet in global memory after a grid barrier -- the whole chip sweeps, where the cluster
+// version leaves 140 of 148 SMs idle (0.46 ms for 298 k points).  Either way every CTA adds the
+// same partials in the same order and takes the identical LM decision.
+template <bool GRID>
+__device__ void pa_sweep(const PaProblem& p, PaShared& sh, int parity, double* __restrict__ gpart) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int blk = GRID ? (int)blockIdx.x : (int)cg::this_cluster().block_rank();
+  const int nblk = GRID ? (int)gridDim.x : PA_CLUSTER;
   if (tid == 0) make_consts(sh.T, p, sh.ab_eps[0], sh.ab_eps[1], sh.c);
   __syncthreads();
   const PaConst& c = sh.c;
@@ -202,8 +210,8 @@ __device__ void pa_sweep(const PaProblem& p, PaShared& sh, cg::cluster_group& cl
   float acc[PA_SUMS];
 #pragma unroll
   for (int k = 0; k < PA_SUMS; ++k) acc[k] = 0.f;
-  const int stride = PA_CLUSTER * PA_THREADS;
-  for (int i = (int)cluster.block_rank() * PA_THREADS + tid; i < p.n; i += stride) {
+  const int stride = nblk * PA_THREADS;
+  for (int i = blk * PA_THREADS + tid; i < p.n; i += stride) {
     const float4 lm = p.lm[i];
     const float x = lm.x, y = lm.y, rho = lm.z, patch = lm.w;
     // reprojectPattern, values (camera_reproject.hpp:270-293): success = validIdepth, ROI(reference), z > 0, ROI(target)
@@ -276,24 +284,47 @@ __device__ void pa_sweep(const PaProblem& p, PaShared& sh, cg::cluster_group& cl
     for (int wv = 0; wv < PA_THREADS / 32; ++wv) s += (double)sh.warp_part[wv][tid];
     sh.part[parity][tid] = s;
   }
-  cluster.sync();  // every CTA's part[parity] is complete and visible
-  if (tid < PA_SUMS) {
-    double s = 0;
-    for (unsigned rk = 0; rk < PA_CLUSTER; ++rk) {
-      const PaShared* peer = cluster.map_shared_rank(&sh, rk);
-      s += peer->part[parity][tid];
+  if (GRID) {
+    double* mine = gpart + ((size_t)parity * nblk + blk) * PA_SUMS;
+    if (tid < PA_SUMS) mine[tid] = sh.part[parity][tid];
+    __threadfence();
+    cg::this_grid().sync();  // every CTA's partial is in global memory
+    // 8 thread groups stride over the CTAs, then the groups are added in a fixed order: the same sum on every CTA
+    const int k = tid & 63, g = tid >> 6;
+    if (k < PA_SUMS) {
+      const double* src = gpart + (size_t)parity * nblk * PA_SUMS + k;
+      double a = 0;
+      for (int b = g; b < nblk; b += PA_THREADS / 64) a += __ldcg(src + (size_t)b * PA_SUMS);
+      reinterpret_cast<double*>(sh.warp_part)[g * PA_SUMS + k] = a;  // warp_part is free again (16 x 46 floats >= 8 x 46 doubles)
     }
-    sh.tot[tid] = s;
+    __syncthreads();
+    if (tid < PA_SUMS) {
+      double t = 0;
+      for (int g2 = 0; g2 < PA_THREADS / 64; ++g2) t += reinterpret_cast<double*>(sh.warp_part)[g2 * PA_SUMS + tid];
+      sh.tot[tid] = t;
+    }
+    __syncthreads();
+  } else {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();  // every CTA's part[parity] is complete and visible
+    if (tid < PA_SUMS) {
+      double s = 0;
+      for (unsigned rk = 0; rk < PA_CLUSTER; ++rk) {
+        const PaShared* peer = cluster.map_shared_rank(&sh, rk);
+        s += peer->part[parity][tid];
+      }
+      sh.tot[tid] = s;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // part[parity] is rewritten two sweeps from now; the cluster barrier of the next sweep lies in between
+  // part[parity] is rewritten two sweeps from now; the barrier of the next sweep lies in between
 }
 
-__global__ void __cluster_dims__(PA_CLUSTER, 1, 1) __launch_bounds__(PA_THREADS)
-    k_pose_align(const PaProblem p, PaOut* __restrict__ out) {
-  cg::cluster_group cluster = cg::this_cluster();
+template <bool GRID>
+__device__ __forceinline__ void pose_align_body(const PaProblem& p, PaOut* __restrict__ out, double* __restrict__ gpart) {
   __shared__ PaShared sh;
   const int tid = threadIdx.x;
+  const bool first_cta = GRID ? blockIdx.x == 0 : cg::this_cluster().block_rank() == 0;
   if (tid == 0) {
     for (int i = 0; i < 12; ++i) sh.T[i] = p.T0[i];
     sh.ab_eps[0] = sh.ab_eps[1] = 0.0;
@@ -318,7 +349,7 @@ __global__ void __cluster_dims__(PA_CLUSTER, 1, 1) __launch_bounds__(PA_THREADS)
     for (int a = 0; a < 8; ++a) sh.bc[a] = sh.tot[36 + a];
   };
   // result.energy = problem.calculateEnergy(); the first linearize() sees the same samples
-  pa_sweep(p, sh, cluster, parity);
+  pa_sweep<GRID>(p, sh, parity, gpart);
   parity ^= 1;
   if (tid == 0) {
     sh.energy = total_energy();
@@ -348,13 +379,13 @@ __global__ void __cluster_dims__(PA_CLUSTER, 1, 1) __launch_bounds__(PA_THREADS)
       for (int i = 0; i < 8; ++i) sh.step[i] = step[i];
     }
     __syncthreads();
-    pa_sweep(p, sh, cluster, parity);  // calculateEnergy() at the trial state (+ the system, should it be accepted)
+    pa_sweep<GRID>(p, sh, parity, gpart);  // calculateEnergy() at the trial state (+ the system, should it be accepted)
     parity ^= 1;
     if (tid == 0) {
       const double next_energy = total_energy();
       const int next_n = (int)llrint(sh.tot[45]);
       bool stop_now = false;
-      if (cluster.block_rank() == 0 && sh.iteration < PA_TRACE) {
+      if (first_cta && sh.iteration < PA_TRACE) {
         out->trace_energy[sh.iteration] = next_energy;
         out->trace_lambda[sh.iteration] = sh.lambda;
         out->trace_accept[sh.iteration] = next_n != 0 && next_energy < sh.energy;
@@ -388,7 +419,7 @@ __global__ void __cluster_dims__(PA_CLUSTER, 1, 1) __launch_bounds__(PA_THREADS)
     }
     __syncthreads();
   }
-  if (cluster.block_rank() == 0 && tid == 0) {
+  if (first_cta && tid == 0) {
     out->energy = sh.energy;
     out->n_valid = sh.n_valid;
     out->converged = sh.converged;
@@ -400,7 +431,18 @@ __global__ void __cluster_dims__(PA_CLUSTER, 1, 1) __launch_bounds__(PA_THREADS)
     out->H[6 * 8 + 6] += p.ab_reg[0];  // problem.hessian() = system_.H incl. the affine prior (:178-185)
     out->H[7 * 8 + 7] += p.ab_reg[1];
   }
-  cluster.sync();  // no CTA may exit while a peer could still read its shared memory
+  if (!GRID) cg::this_cluster().sync();  // no CTA may exit while a peer could still read its shared memory
+}
+
+__global__ void __cluster_dims__(PA_CLUSTER, 1, 1) __launch_bounds__(PA_THREADS)
+    k_pose_align(const PaProblem p, PaOut* __restrict__ out) {
+  pose_align_body<false>(p, out, nullptr);
+}
+
+// whole-chip variant: cooperative launch, one CTA per SM, partial sums through global memory (gpart: [2][grid][PA_SUMS])
+__global__ void __launch_bounds__(PA_THREADS) k_pose_align_grid(const PaProblem p, PaOut* __restrict__ out,
+                                                                double* __restrict__ gpart) {
+  pose_align_body<true>(p, out, gpart);
 }
 
 // ---- depth map -> landmarks on the device (local_frame.hpp:367-392), order preserved -------------------------------
@@ -472,6 +514,9 @@ struct dpa_handle {
   PaOut* out_dev = nullptr;
   PaOut* out_h = nullptr;       // pinned
   int* total_h = nullptr;       // pinned
+  double* gpart = nullptr;      // whole-chip variant: [2][SMs][PA_SUMS] partial sums (lazily)
+  int sm_count = 0;
+  int grid_min_points = 32768;  // from this many landmarks on the cooperative whole-chip kernel is used (dpa_set_grid_threshold)
 };
 
 namespace {
@@ -565,6 +610,7 @@ int dpa_destroy(dpa_handle* h) {
   cudaFreeHost(h->out_h);
   cudaFreeHost(h->total_h);
   if (h->stream) cudaStreamDestroy(h->stream);
+  cudaFree(h->gpart);
   delete h;
   return DPBA_SUCCESS;
 }
@@ -654,6 +700,12 @@ int dpa_set_target(dpa_handle* h, const float* image, const uint8_t* mask, const
   return DPBA_SUCCESS;
 }
 
+int dpa_set_grid_threshold(dpa_handle* h, int32_t min_points) {
+  PREQ(h, "null handle");
+  h->grid_min_points = min_points < 0 ? 0x7fffffff : min_points;
+  return DPBA_SUCCESS;
+}
+
 int dpa_get_trace(dpa_handle* h, int32_t capacity, double* energies, double* lambdas, int32_t* accepted) {
   PREQ(h, "null handle");
   const int n = std::min(std::min(h->out_h->iterations, (int)PA_TRACE), (int)capacity);
@@ -694,7 +746,22 @@ int dpa_solve(dpa_handle* h, const dpa_options* o, const double* prior_rotation,
   p.dec = o->regularizer_decrease_on_accept;
   p.inc = o->regularizer_increase_on_reject;
   pba::add_launches(1);
-  k_pose_align<<<PA_CLUSTER, PA_THREADS, 0, h->stream>>>(p, h->out_dev);
+  if (h->n >= h->grid_min_points) {
+    // dense depth map: one CTA per SM (cooperative launch), grid barrier between the sweeps
+    if (!h->sm_count) {
+      int dev = 0, coop = 0;
+      PCK(cudaGetDevice(&dev));
+      PCK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
+      PCK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+      PREQ(coop, "cooperative launch not supported");
+      PCK(cudaMalloc(&h->gpart, 2 * (size_t)h->sm_count * PA_SUMS * sizeof(double)));
+    }
+    int grid = std::min(h->sm_count, (h->n + PA_THREADS - 1) / PA_THREADS);
+    void* args[] = {(void*)&p, (void*)&h->out_dev, (void*)&h->gpart};
+    PCK(cudaLaunchCooperativeKernel((const void*)k_pose_align_grid, dim3(grid), dim3(PA_THREADS), args, 0, h->stream));
+  } else {
+    k_pose_align<<<PA_CLUSTER, PA_THREADS, 0, h->stream>>>(p, h->out_dev);
+  }
   PCK(cudaGetLastError());
   PCK(cudaMemcpyAsync(h->out_h, h->out_dev, sizeof(PaOut), cudaMemcpyDeviceToHost, h->stream));
   PCK(cudaStreamSynchronize(h->stream));

@@ -40,6 +40,7 @@ SIGNATURES = {
     "dpa_solve": (C.c_int, [_P, C.POINTER(Options), _P, C.POINTER(Result)]),
     "dpa_get_trace": (C.c_int, [_P, _I, _P, _P, _P]),
     "dpa_mean_square_optical_flow": (C.c_int, [_P, _P, C.POINTER(_D), C.POINTER(C.c_int32)]),
+    "dpa_set_grid_threshold": (C.c_int, [_P, _I]),
 }
 
 _bound = False
@@ -119,6 +120,9 @@ class Aligner:
         H, W = image.shape[:2]
         self._ck(self.lib.dpa_set_target(self.h, capi._ptr(image), capi._ptr(mask), capi._ptr(T), exposure, capi._ptr(ab),
                                          capi._ptr(it), W, H))
+
+    def set_grid_threshold(self, min_points):
+        self._ck(self.lib.dpa_set_grid_threshold(self.h, int(min_points)))
 
     def mean_square_optical_flow(self, T_target_reference):
         """calculateMeanSquareOpticalFlow over the resident reference landmarks -> (flow, landmarks used)."""

@@ -100,6 +100,13 @@ int dpa_mean_square_optical_flow(dpa_handle* h, const double T_target_reference[
 /* Trace of the last dpa_solve: trial energy, regulariser and accept decision of every executed loop body (at most 64).
  * Returns the number of entries written.  Any pointer may be NULL. */
 int dpa_get_trace(dpa_handle* h, int32_t capacity, double* energies, double* lambdas, int32_t* accepted);
+/* Tuning knob without a reference counterpart: from `min_points` reference landmarks on, dpa_solve runs the sweeps on a
+ * cooperative grid with one CTA per SM (partial sums through global memory, grid barrier per sweep) instead of one
+ * 8-CTA cluster (distributed shared memory).  Default 32768: the sparse depth maps of the reference (~6 k points) stay
+ * on the cluster kernel, the dense raster of BASELINE configs[2] (298 k points) uses the whole chip.  min_points < 0:
+ * never.  Same arithmetic, same summation order inside a CTA; the order ACROSS CTAs differs, so results agree to fp64
+ * rounding of the partial sums, not bit for bit. */
+int dpa_set_grid_threshold(dpa_handle* h, int32_t min_points);
 
 #ifdef __cplusplus
 }

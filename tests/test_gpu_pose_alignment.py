@@ -12,7 +12,8 @@ from dsopp_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def run_case(seed, W, H, density, ab_scale=0.0, device_depth_map=False, mask_hole=False, ab_reg=(1e12, 1e8)):
+def run_case(seed, W, H, density, ab_scale=0.0, device_depth_map=False, mask_hole=False, ab_reg=(1e12, 1e8),
+             grid_threshold=None):
     from dsopp_b200 import pose_alignment as G
     from oracle import pba_oracle as O
     from oracle import pose_alignment_oracle as PA
@@ -37,6 +38,8 @@ def run_case(seed, W, H, density, ab_scale=0.0, device_depth_map=False, mask_hol
     else:
         al.set_reference_landmarks(uv, idepth, patch, r.T_w_true, r.exposure, r.ab0, r.intr, W, H)
     al.set_target(t.image, mask, case.T_w_target_guess, t.exposure, t.ab0, t.intr)
+    if grid_threshold is not None:
+        al.set_grid_threshold(grid_threshold)
     got = al.solve(G.default_options(ab_reg=ab_reg))
     gtr = al.trace()
     al.close()
@@ -79,6 +82,23 @@ def test_sparse_depth_map_full_resolution():
 
 def test_dense_raster_quarter_resolution_with_device_side_landmarks():
     run_case(seed=4, W=320, H=240, density=1.0, device_depth_map=True)
+
+
+def test_dense_raster_full_resolution_on_the_whole_chip():
+    """BASELINE configs[2] as stated: 640x480, every pixel carries depth (298 k one-pixel residuals), 6 + 2 parameters.
+    298 k landmarks select the cooperative whole-chip kernel (one CTA per SM, grid barrier per sweep)."""
+    run_case(seed=5, W=640, H=480, density=1.0, device_depth_map=True)
+
+
+def test_whole_chip_and_cluster_kernels_agree():
+    """Same arithmetic per point, same order inside a CTA; only the order in which the CTAs' fp64 partial sums are added
+    differs (148 CTAs through global memory against 8 through distributed shared memory)."""
+    a = run_case(seed=4, W=320, H=240, density=1.0, device_depth_map=True, grid_threshold=0)    # whole chip
+    b = run_case(seed=4, W=320, H=240, density=1.0, device_depth_map=True, grid_threshold=-1)   # one cluster
+    assert a["iterations"] == b["iterations"] and a["n_valid"] == b["n_valid"]
+    assert abs(a["energy"] - b["energy"]) <= 1e-9 * abs(b["energy"])
+    assert np.abs(a["T_t_r"] - b["T_t_r"]).max() <= 1e-9
+    assert np.abs(a["H"] - b["H"]).max() <= 1e-9 * np.abs(b["H"]).max()
 
 
 def test_affine_brightness_is_estimated_when_the_prior_is_weak():

@@ -8,3 +8,6 @@ if d.get("parity_check"):
     print("parity_check", d["parity_check"])
 if d.get("e2e_raw_frames"):
     print("e2e raw frames %.1f M/s (%.2f ms/step)" % (d["e2e_raw_frames"]["value"] / 1e6, d["e2e_raw_frames"]["ms_per_step"]))
+if d.get("config3_strong"):
+    c = d["config3_strong"]
+    print("config3 strong: %.1f M/s, %.1f us/iter at N=%d, check %s" % (c["value"] / 1e6, c["us_per_gn_iter"], c["n_gpus"], c["multi_gpu_check"]))
