@@ -218,6 +218,127 @@ def cpu_baseline_leg():
 
 
 # --------------------------------------------------------------------------------------------------
+def pose_alignment_leg(torch):
+    from dsopp_b200 import pose_alignment as G, synth
+    from oracle import pose_alignment_oracle as PA
+    out = {"workload": "configs[2]: direct image alignment of a new frame to the last keyframe, 640x480, SE3 + affine "
+                       "(6 + 2 DoF), 1-pixel residuals, LM lambda0 = 1e-2 x/÷ 2, <= 50 iterations, 4 pyramid levels coarse to fine",
+           "cases": []}
+    for name, density in (("dense (every pixel carries depth: BASELINE's full-frame bound)", 1.0),
+                          ("sparse (2 % of the pixels: the reference's splatted depth map)", 0.02)):
+        case = synth.make_alignment_case(seed=3, width=640, height=480, density=density, pose_noise=4e-3)
+        r, t = case.reference, case.target
+        ref_I, tgt_I = [r.image[..., 0]], [t.image[..., 0]]
+        ids, w = [case.idepth_sum.astype(np.float32)], [case.weight.astype(np.float32)]
+        for _ in range(1, 4):
+            ref_I.append(synth.downscale(ref_I[-1]))
+            tgt_I.append(synth.downscale(tgt_I[-1]))
+            a, b = ids[-1], w[-1]
+            ids.append(a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2])
+            w.append(b[0::2, 0::2] + b[1::2, 0::2] + b[0::2, 1::2] + b[1::2, 1::2])
+        al = G.Aligner(640 * 480, 640, 480)
+        stream = torch.cuda.ExternalStream(al.stream)
+        T = case.T_w_target_guess
+        levels, gpu_total, cpu_total, units = [], 0.0, 0.0, 0
+        for lvl in range(3, -1, -1):
+            intr = r.intr / (2 ** lvl)
+            Hh, Ww = ref_I[lvl].shape
+            ref_img, tgt_img = synth.pixelinfo(ref_I[lvl]), synth.pixelinfo(tgt_I[lvl])
+            mask = np.full((Hh, Ww), 255, np.uint8)
+            n = al.set_reference_depth_map(ref_img, ids[lvl], w[lvl], r.T_w_true, r.exposure, r.ab0, intr)
+            al.set_target(tgt_img, mask, T, t.exposure, t.ab0, intr)
+            ms, res = [], None
+            for i in range(3 + 10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                res = al.solve()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ms.append(e0.elapsed_time(e1))
+            uv, idepth, patch = PA.landmarks_from_depth_map(ids[lvl].astype(np.float64), w[lvl].astype(np.float64), ref_img)
+            ref = PA.PAFrame(r.T_w_true, r.exposure, r.ab0, intr, ref_img, np.full((Hh, Ww), 255, np.uint8))
+            tgt = PA.PAFrame(T, t.exposure, t.ab0, intr, tgt_img, mask)
+            cpp = min((PA.solve_cpp(ref, tgt, uv, idepth, patch) for _ in range(2)), key=lambda o: o["seconds"])
+            med = float(np.median(ms))
+            sweeps = res["iterations"] + 1
+            levels.append({"level": lvl, "size": [Ww, Hh], "landmarks": int(n), "lm_iterations": int(res["iterations"]),
+                           "gpu_ms": med, "cpu_serial_cpp_ms": cpp["seconds"] * 1e3, "cpu_lm_iterations": int(cpp["iterations"]),
+                           "rmse": float(res["rmse"]), "rmse_cpu": float(cpp.get("rmse", float("nan")))})
+            gpu_total += med
+            cpu_total += cpp["seconds"] * 1e3
+            units += int(n) * sweeps
+            T = res["T_w_target"]
+        al.close()
+        out["cases"].append({"case": name, "levels": levels, "gpu_ms_coarse_to_fine": gpu_total,
+                             "cpu_serial_cpp_ms_coarse_to_fine": cpu_total, "speedup": cpu_total / gpu_total,
+                             "gpu_point_residuals_per_s": units / (gpu_total * 1e-3),
+                             "timing": "CUDA events around dpa_solve (one kernel launch + result readback per level), median of 10"})
+    return out
+
+
+def marginalisation_leg():
+    """configs[4]: Schur-eliminate the oldest keyframe (2000 landmarks) of the 8-keyframe window into the dense prior.
+    GPU: CudaPhotometricBundleAdjustment::marginalizeNow (firstEstimateJacobians + fused linearise over the flagged landmarks
+    + landmark energy on the device, the 64x64 algebra and reduce_system in fp64 on the host), wall clock incl. every
+    synchronisation.  CPU: the same update with oracle/cpu_ref (double, reference dataflow) + NumPy for the 64x64 part."""
+    from dsopp_b200 import host, synth
+    from oracle import cpu_ref, pba_oracle as O
+    win = synth.make_window(n_frames=N_FRAMES, points_per_frame=PTS_PER_GPU, seed=0, ab_scale=0.0)
+    gpu_ms = []
+    for rep in range(4):
+        pba = host.CudaPhotometricBundleAdjustment(win.width, win.height, max_frames=9, max_points=2048, estimate_uncertainty=False)
+        ids = []
+        for f in win.frames:
+            pba.push_frame(f.frame_id, f.timestamp, f.T_w_lin, f.exposure, f.ab0, f.intr, f.image, f.mask, f.uv, f.idepth,
+                           f.patch, f.flags, fixed=f.fixed, other_ids=ids)
+            ids.append(f.frame_id)
+        f = win.frames[0]
+        pba.update_local_frame(f.frame_id, f.timestamp, f.T_w_lin, f.exposure, f.ab0, f.intr, f.uv, f.idepth, f.patch,
+                               np.full(len(f.idepth), synth.FLAG_MARGINALIZED, np.uint8), is_marginalized=True)
+        t0 = time.perf_counter()
+        pba.marginalize_now()
+        dt = time.perf_counter() - t0
+        if rep:
+            gpu_ms.append(dt * 1e3)
+        Hm, bm, em = pba.marginalized_system()
+        pba.close()
+    # CPU: same flags, same update
+    win.frames[0].flags[:] = synth.FLAG_MARGINALIZED | synth.FLAG_TO_MARGINALIZE
+    threads = max(1, min(os.cpu_count() or 1, 8) - 1)
+    cpu_ms = []
+    for rep in range(3):
+        cw = cpu_ref.CpuWindow(win, use_float=False, threads=threads, native=True)
+        t0 = time.perf_counter()
+        cw.first_estimate()
+        cw.evaluate(SIGMA, True, True)
+        cw.change_statuses(True)
+        Hp, bp = cw.pose_pose(True)
+        Hs, bs = cw.schur(True)
+        e_l, _ = cw.landmarks_energy(True)
+        eps, _ = cw.get_state()
+        H, b = Hp - Hs, bp - bs
+        e_marg = e_l + eps @ (H @ eps) - eps @ b
+        b = b - H @ eps
+        prior_H, prior_b = np.zeros_like(H), np.zeros_like(b)
+        prior_H[:8, :8] += np.eye(8) * FIXED_REG  # the dropped frame is the fixed one
+        prior_b[:8] += FIXED_REG * eps[:8]
+        prior_b -= prior_H @ eps
+        Hr, br = O.reduce_system(H + prior_H, b + prior_b, list(range(8)))
+        cpu_ms.append((time.perf_counter() - t0) * 1e3)
+        cw.close()
+    n = 8 * (N_FRAMES - 1)
+    err_h = float(np.abs(Hm[:n, :n] - Hr).max() / np.abs(Hr).max())
+    return {"workload": f"configs[4]: marginalisation of the oldest keyframe ({PTS_PER_GPU} landmarks) of the {N_FRAMES}-keyframe "
+                        f"window into the dense {n}x{n} prior (updateMarginalizedLinearSystem + reduce_system)",
+            "gpu_ms": float(np.median(gpu_ms)), "cpu_port_ms": float(np.median(cpu_ms)), "cpu_threads": threads,
+            "speedup": float(np.median(cpu_ms) / np.median(gpu_ms)),
+            "landmarks_marginalised": int(len(win.frames[0].idepth)),
+            "patch_residuals_per_s": float(len(win.frames[0].idepth) * (N_FRAMES - 1) / (np.median(gpu_ms) * 1e-3)),
+            "prior_rel_diff_gpu_vs_cpu_port": err_h,
+            "timing": "wall clock around CudaPhotometricBundleAdjustment::marginalizeNow (synchronous), median of 3"}
+
+
 def pin(a):
     import torch
     t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -517,6 +638,25 @@ def run_ours(args):
         h3.close()
         del win3
 
+    # ---- configs[2]: coarse-tracker direct image alignment, 640x480, SE3 + affine (6 + 2), full-frame residual, 4 pyramid
+    # levels coarse to fine (kNumberOfPyramidLevels = 4; monocular_tracker.cpp:199-214).  GPU: one kernel launch per level
+    # runs the whole LM solve (whole-chip cooperative kernel for the dense levels); CPU: the serial C++ restatement of
+    # EigenPoseAlignment (the reference runs it on one core), timed on this box.  Also the reference-realistic SPARSE depth
+    # map (2 % of the pixels carry depth).  Rank 0 only.
+    config2 = None
+    if rank == 0 and not args.no_config2:
+        try:
+            config2 = pose_alignment_leg(torch)
+        except Exception as ex:  # reported, never required for the headline metric
+            config2 = {"error": repr(ex)}
+
+    config4 = None
+    if rank == 0 and world == 1 and not args.no_config4:
+        try:
+            config4 = marginalisation_leg()
+        except Exception as ex:
+            config4 = {"error": repr(ex)}
+
     def teardown():
         # ordered shutdown, then a normal interpreter exit: the handle first (dpba_destroy destroys the captured LM graph
         # BEFORE its NCCL communicator -- a graph that still references the communicator's kernels is what used to block
@@ -618,6 +758,8 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "parity_check": parity_check,
         "config3_strong": config3,
+        "config2_pose_alignment": config2,
+        "config4_marginalisation": config4,
         "us_per_gn_iter": 1e3 * total_ms / args.steps / GN_ITERS,
     }
     print(json.dumps(out), flush=True)
@@ -631,6 +773,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config4", action="store_true", help="skip the configs[4] marginalisation leg")
+    ap.add_argument("--no-config2", action="store_true", help="skip the configs[2] pose-alignment leg")
     ap.add_argument("--no-config3", action="store_true", help="skip the configs[3] strong-scaling leg (8 KF x 20000 points)")
     ap.add_argument("--no-big-sweep", action="store_true", help="skip the 20000-points/KF materialising-sweep roofline")
     ap.add_argument("--fused-min-blocks", type=int, default=0, help="tuning A/B: 3 or 4 resident CTAs/SM for the fused linearise")

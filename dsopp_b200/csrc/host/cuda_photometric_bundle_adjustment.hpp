@@ -245,6 +245,13 @@ class CudaPhotometricBundleAdjustment {
     if (n) dpba_check(h_, dpba_get_frame_statuses(h_, slot, n, rows, nullptr));  // one synchronisation per frame
   }
 
+  // The frames_.size() > 1 half of pushFrame on its own (eigen_photometric_bundle_adjustment.cpp:121-130): what the next
+  // pushFrame would do before it appends its frame.  Lets a caller (bench.py configs[4], the tests) run and time the
+  // marginalisation update without uploading a new keyframe.
+  void marginalizeNow() {
+    if (frames_.size() > 1) marginalize();
+  }
+
   // createReferenceDepthMaps (src/tracker/tracker/src/create_depth_maps.cpp:122-146), which the tracker calls right after
   // solve / updateSolver (monocular_tracker.cpp:465,509): built on the device from the window this solver holds.
   // Level l: (height >> l) x (width >> l), row-major [y][x] = the reference's map(x, y); `idepth` is the weighted SUM.

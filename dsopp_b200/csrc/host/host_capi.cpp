@@ -128,6 +128,11 @@ __attribute__((visibility("default"))) int dpbah_solve(void* s, double* energy, 
   return 0;
 }
 
+__attribute__((visibility("default"))) int dpbah_marginalize_now(void* s) {
+  GUARD(((Solver*)s)->pba->marginalizeNow());
+  return 0;
+}
+
 __attribute__((visibility("default"))) int dpbah_num_frames(void* s) { return (int)((Solver*)s)->pba->frames().size(); }
 
 __attribute__((visibility("default"))) int dpbah_frame_ids(void* s, int* ids) {

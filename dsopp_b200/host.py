@@ -259,6 +259,11 @@ class CudaPhotometricBundleAdjustment:
         _ck(self.lib.dpbah_solve(self.s, C.byref(e), C.byref(it)))
         return e.value, it.value
 
+    def marginalize_now(self):
+        """updateMarginalizedLinearSystem of the flagged landmarks / frames (what the next pushFrame does first)."""
+        self.lib.dpbah_marginalize_now.argtypes = [_P]
+        _ck(self.lib.dpbah_marginalize_now(self.s))
+
     @property
     def frame_ids(self):
         ids = np.zeros(capi.MAX_FRAMES, np.int32)

@@ -241,3 +241,49 @@ def test_production_lm_solve_matches_cpu_ref_double_at_configs1(capi):
         assert abs(its - len(trace)) <= 1
     h.close()
     cw.close()
+
+
+def _flag_first_frame_for_marginalisation(pba, win):
+    f = win.frames[0]
+    flags = np.full(len(f.idepth), synth.FLAG_MARGINALIZED, np.uint8)
+    pba.update_local_frame(f.frame_id, f.timestamp, f.T_w_lin, f.exposure, f.ab0, f.intr, f.uv, f.idepth, f.patch, flags,
+                           is_marginalized=True)
+
+
+def test_marginalisation_of_the_oldest_keyframe_at_configs4():
+    """BASELINE configs[4]: Schur-eliminate the oldest keyframe (all its 2000 landmarks) of the 8 x 2000 window into the
+    dense prior -- updateMarginalizedLinearSystem (problem.hpp:146-203) + reduce_system (normal_linear_system.cpp:18-50)
+    through the C++ solver class, against the NumPy oracle's restatement of the same at the same size.
+    Tolerances: the reference's own bar for this path is 5e-3 |x| + 1e1 (test_linear_system.cpp:294-299,351-356); here
+    2e-4 of max|H| and 2e-4 of max|b| (fp32 sweep, fp64 sums, fp64 host algebra)."""
+    from dsopp_b200 import host
+    from oracle import pba_oracle as O
+    win = synth.make_window(n_frames=8, points_per_frame=2000, seed=0, ab_scale=0.0)
+    frames = O.frames_from_window(win)
+    ref = O.EigenPBA(estimate_uncertainty=False)
+    ref.set_frames(frames)
+    f0 = frames[0]
+    f0.lm_to_marginalize[:] = True
+    f0.lm_marginalized[:] = True
+    f0.to_marginalize, f0.is_marginalized = True, True
+    ref.marginalize()
+    assert len(ref.frames) == 7
+    pba = host.CudaPhotometricBundleAdjustment(win.width, win.height, max_frames=9, max_points=2048, estimate_uncertainty=False)
+    ids = []
+    for f in win.frames:
+        pba.push_frame(f.frame_id, f.timestamp, f.T_w_lin, f.exposure, f.ab0, f.intr, f.image, f.mask, f.uv, f.idepth, f.patch,
+                       f.flags, fixed=f.fixed, other_ids=ids)
+        ids.append(f.frame_id)
+    _flag_first_frame_for_marginalisation(pba, win)
+    pba.marginalize_now()
+    assert pba.frame_ids == [f.frame_id for f in win.frames[1:]]
+    Hm, bm, em = pba.marginalized_system()
+    n = 8 * 7
+    scale_h, scale_b = np.abs(ref.H_marg).max(), np.abs(ref.b_marg).max()
+    err_h = np.abs(Hm[:n, :n] - ref.H_marg[:n, :n]).max() / scale_h
+    err_b = np.abs(bm[:n] - ref.b_marg[:n]).max() / scale_b
+    print(f"[configs4] H_marg rel err {err_h:.2e}, b_marg rel err {err_b:.2e}, energy {em:.4f} vs {ref.energy_marg:.4f}")
+    assert err_h <= 2e-4 and err_b <= 2e-4
+    assert abs(em - ref.energy_marg) <= 2e-4 * abs(ref.energy_marg) + 1e-6 * scale_h
+    assert np.allclose(Hm[:n, :n], Hm[:n, :n].T, atol=1e-9 * scale_h)
+    pba.close()

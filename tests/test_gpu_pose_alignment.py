@@ -91,14 +91,14 @@ def test_dense_raster_full_resolution_on_the_whole_chip():
 
 
 def test_whole_chip_and_cluster_kernels_agree():
-    """Same arithmetic per point, same order inside a CTA; only the order in which the CTAs' fp64 partial sums are added
-    differs (148 CTAs through global memory against 8 through distributed shared memory)."""
+    """Same arithmetic per point; what differs is which points share a thread's fp32 running sums (the stride is the
+    number of CTAs x 512) and the order of the CTAs' fp64 partials: agreement to fp32 summation noise (1e-6 relative)."""
     a = run_case(seed=4, W=320, H=240, density=1.0, device_depth_map=True, grid_threshold=0)    # whole chip
     b = run_case(seed=4, W=320, H=240, density=1.0, device_depth_map=True, grid_threshold=-1)   # one cluster
     assert a["iterations"] == b["iterations"] and a["n_valid"] == b["n_valid"]
-    assert abs(a["energy"] - b["energy"]) <= 1e-9 * abs(b["energy"])
-    assert np.abs(a["T_t_r"] - b["T_t_r"]).max() <= 1e-9
-    assert np.abs(a["H"] - b["H"]).max() <= 1e-9 * np.abs(b["H"]).max()
+    assert abs(a["energy"] - b["energy"]) <= 2e-6 * abs(b["energy"])
+    assert np.abs(a["T_t_r"] - b["T_t_r"]).max() <= 1e-6
+    assert np.abs(a["H"] - b["H"]).max() <= 2e-6 * np.abs(b["H"]).max()
 
 
 def test_affine_brightness_is_estimated_when_the_prior_is_weak():

@@ -11,3 +11,10 @@ if d.get("e2e_raw_frames"):
 if d.get("config3_strong"):
     c = d["config3_strong"]
     print("config3 strong: %.1f M/s, %.1f us/iter at N=%d, check %s" % (c["value"] / 1e6, c["us_per_gn_iter"], c["n_gpus"], c["multi_gpu_check"]))
+if d.get("config2_pose_alignment"):
+    for c in d["config2_pose_alignment"].get("cases", []):
+        print("config2 %s: gpu %.3f ms, cpu serial %.1f ms (x%.0f)" % (c["case"][:6], c["gpu_ms_coarse_to_fine"], c["cpu_serial_cpp_ms_coarse_to_fine"], c["speedup"]))
+    if "error" in d["config2_pose_alignment"]:
+        print("config2 error", d["config2_pose_alignment"]["error"])
+if d.get("config4_marginalisation"):
+    print("config4", {k: v for k, v in d["config4_marginalisation"].items() if k in ("gpu_ms", "cpu_port_ms", "speedup", "prior_rel_diff_gpu_vs_cpu_port", "error")})

@@ -6,6 +6,6 @@ RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-add
 i=0
 for opts in "$@"; do
   i=$((i+1))
-  timeout 300 $RUN --master-port $((29520+i)) bench.py --gpus $N --no-cpu --no-big-sweep --no-config3 $opts > gpurun_out/${tag}_mab$i.json 2> gpurun_out/${tag}_mab$i.err
+  timeout 300 $RUN --master-port $((29520+i)) bench.py --gpus $N --no-cpu --no-big-sweep --no-config3 --no-config2 --no-config4 $opts > gpurun_out/${tag}_mab$i.json 2> gpurun_out/${tag}_mab$i.err
   echo "== N=$N $opts (exit $?)"; python tools/bench_summary.py gpurun_out/${tag}_mab$i.json | head -2
 done
