@@ -284,7 +284,8 @@ def marginalisation_leg():
     synchronisation.  CPU: the same update with oracle/cpu_ref (double, reference dataflow) + NumPy for the 64x64 part."""
     from dsopp_b200 import host, synth
     from oracle import cpu_ref, pba_oracle as O
-    win = synth.make_window(n_frames=N_FRAMES, points_per_frame=PTS_PER_GPU, seed=0, ab_scale=0.0)
+    # eps_scale = 0: keyframes enter the solver class at their linearisation point
+    win = synth.make_window(n_frames=N_FRAMES, points_per_frame=PTS_PER_GPU, seed=0, ab_scale=0.0, eps_scale=0.0)
     gpu_ms = []
     for rep in range(4):
         pba = host.CudaPhotometricBundleAdjustment(win.width, win.height, max_frames=9, max_points=2048, estimate_uncertainty=False)

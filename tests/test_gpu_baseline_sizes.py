@@ -258,7 +258,8 @@ def test_marginalisation_of_the_oldest_keyframe_at_configs4():
     2e-4 of max|H| and 2e-4 of max|b| (fp32 sweep, fp64 sums, fp64 host algebra)."""
     from dsopp_b200 import host
     from oracle import pba_oracle as O
-    win = synth.make_window(n_frames=8, points_per_frame=2000, seed=0, ab_scale=0.0)
+    # eps_scale = 0: a keyframe enters the solver class at its linearisation point (KeyframeView carries a pose, no eps)
+    win = synth.make_window(n_frames=8, points_per_frame=2000, seed=0, ab_scale=0.0, eps_scale=0.0)
     frames = O.frames_from_window(win)
     ref = O.EigenPBA(estimate_uncertainty=False)
     ref.set_frames(frames)
