@@ -285,6 +285,75 @@ __attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dp
   return 0;
 }
 
+// The tracker's steady state in ONE call: the oldest keyframe leaves the window, ONE new keyframe is pushed from host
+// buffers (image, landmarks, its connection statuses in both directions), then firstEstimateJacobians + the device LM and the
+// results of EVERY frame come back -- marginalisation policy aside, this is monocular_tracker.cpp:491-507 per keyframe.
+// The benchmark recycles the frame that left as the one that arrives, so the window always holds the same n keyframes (in
+// rotating order) and every step does the same work.  `order` (n ints, owned by the caller, initialised 0..n-1) maps slot
+// -> index into the io arrays and is rotated by the call.
+__attribute__((visibility("default"))) int dpbah_solve_sliding(dpba_handle* h, dpbah_window_io* io, int32_t* order, int width,
+                                                              int height) {
+  GUARD({
+    const int n = io->n_frames;
+    if (dpba_num_frames(h) != n) throw DpbaFailure(DPBA_E_STATE, "dpbah_solve_sliding: load the window with dpbah_solve_window first");
+    int64_t h2d = 0, d2h = 0;
+    const size_t npx = (size_t)width * height;
+    const int f = order[0];  // leaves as the oldest, arrives as the newest
+    dpba_check(h, dpba_remove_frame(h, 0));
+    for (int k = 0; k + 1 < n; ++k) order[k] = order[k + 1];
+    order[n - 1] = f;
+    dpba_check(h, dpba_set_frame_flags(h, 0, 1, 0));  // the new oldest keyframe holds the gauge (frame 0 is the fixed one)
+    dpba_check(h, dpba_push_frame(h, io->frame_ids[f], io->images[f], io->masks[f], io->T_w_lin + 12 * f, io->exposure[f],
+                                  io->ab0 + 2 * f, io->intr + 4 * f, 0));
+    h2d += (int64_t)npx * 12 + (io->masks[f] ? (int64_t)npx : 0);
+    const int slot = n - 1, m = io->n_landmarks[f];
+    dpba_check(h, dpba_set_landmarks(h, slot, m, io->uv[f], io->idepth[f], io->patch[f], io->flags[f]));
+    h2d += (int64_t)m * (8 + 4 + 32 + 1);
+    for (int t = 0; t + 1 < n; ++t) {  // the new frame's residual vectors, both directions
+      const int g = order[t];
+      dpba_check(h, dpba_set_statuses(h, slot, t, m, io->statuses[(size_t)f * n + g]));
+      dpba_check(h, dpba_set_statuses(h, t, slot, io->n_landmarks[g], io->statuses[(size_t)g * n + f]));
+      h2d += m + io->n_landmarks[g];
+    }
+    // same starting state every step (the benchmark's steps must do the same work): landmarks of the frames that stayed
+    // and the pose increments go back to the initial estimate
+    std::vector<double> eps(8 * (size_t)n), zero(8 * (size_t)n, 0.0);
+    for (int t = 0; t < n; ++t) {
+      for (int k = 0; k < 8; ++k) eps[8 * t + k] = io->eps0[8 * order[t] + k];
+      if (t + 1 < n) {
+        const int g = order[t];
+        dpba_check(h, dpba_set_landmarks(h, t, io->n_landmarks[g], io->uv[g], io->idepth[g], io->patch[g], io->flags[g]));
+        const uint8_t* rows[DPBA_MAX_FRAMES] = {};
+        for (int u = 0; u < n; ++u) rows[u] = u == t ? nullptr : io->statuses[(size_t)g * n + order[u]];
+        dpba_check(h, dpba_set_frame_statuses(h, t, io->n_landmarks[g], rows));
+      }
+    }
+    dpba_check(h, dpba_set_state(h, eps.data(), zero.data()));
+    h2d += 2 * 8 * (int64_t)n * 8;
+    dpba_check(h, dpba_first_estimate(h));
+    dpba_lm_result r;
+    dpba_check(h, dpba_solve_lm(h, &io->lm, nullptr, nullptr, 0.0, &r));
+    io->energy = r.energy;
+    io->iterations = r.iterations;
+    io->n_valid = r.number_of_valid_residuals;
+    io->converged = r.converged;
+    dpba_check(h, dpba_get_state(h, io->eps_out, zero.data()));
+    d2h += 2 * 8 * (int64_t)n * 8;
+    for (int t = 0; t < n; ++t) {
+      const int g = order[t], mg = io->n_landmarks[g];
+      dpba_check(h, dpba_get_landmarks(h, t, mg, io->idepth_out[g], nullptr, io->inv_hdd_out[g], nullptr, io->flags_out[g],
+                                       io->n_inliers_out[g], io->rel_baseline_out[g]));
+      uint8_t* rows[DPBA_MAX_FRAMES] = {};
+      for (int u = 0; u < n; ++u) rows[u] = u == t ? nullptr : io->statuses_out[(size_t)g * n + order[u]];
+      dpba_check(h, dpba_get_frame_statuses(h, t, mg, rows, nullptr));
+      d2h += (int64_t)mg * (4 * 4 + 1) + (int64_t)mg * (n - 1);
+    }
+    io->h2d_bytes = h2d;
+    io->d2h_bytes = d2h;
+  });
+  return 0;
+}
+
 // levenberg_marquardt_algorithm::solve over a window that was uploaded through the C ABI directly.
 // trace (optional): per loop body [accepted, energy, n_valid, step(8N)...], row stride 3 + 8N.
 __attribute__((visibility("default"))) int dpbah_lm_solve(dpba_handle* h, int n_frames, const double* ab0,

@@ -122,10 +122,17 @@ struct dpba_handle {
   // eight-kernel sequence stays the default.
   bool merged_tail = false;
   bool speculative_multi = true;     // ... also with world_size > 1 (one allreduce per iteration); 2-GPU check: same state and energy as the two-sweep sequence
-  cudaGraphExec_t lm_graph_exec = nullptr;
-  std::vector<long long> lm_graph_key;
-  size_t lm_graph_events = 0;
-  long long lm_graph_kernels = 0;
+  // captured LM launch sequences, keyed by everything the captured kernels hold by value (window shape, physical slots,
+  // options).  A sliding window cycles through a handful of (logical -> physical slot) maps: a small cache keeps one
+  // graph per map instead of re-capturing on every keyframe.
+  struct LmGraph {
+    std::vector<long long> key;
+    cudaGraphExec_t exec = nullptr;
+    size_t events = 0;
+    long long kernels = 0;
+  };
+  std::vector<LmGraph> lm_graphs;
+  std::vector<long long> lm_graph_key;  // cleared by dpba_set_option: drops every cached graph at the next solve
   bool lm_graph_fresh = false;
   double* marg_dev = nullptr;        // [MAXD*MAXD + MAXD]
   double* marg_h = nullptr;          // pinned staging
@@ -724,10 +731,9 @@ int dpba_destroy(dpba_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stream2) cudaStreamSynchronize(h->stream2);
   // the LM graph holds captured NCCL kernels: it must go before the communicator it references
-  if (h->lm_graph_exec) {
-    cudaGraphExecDestroy(h->lm_graph_exec);
-    h->lm_graph_exec = nullptr;
-  }
+  for (auto& g : h->lm_graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->lm_graphs.clear();
   if (h->comm) nccl_api().CommDestroy(h->comm);
   // peers' mailboxes are closed, ours is freed: the caller puts a barrier between the last solve and dpba_destroy
   for (void* p : h->peer_open)
@@ -774,7 +780,6 @@ int dpba_destroy(dpba_handle* h) {
   cudaFreeHost(h->lmopt_h);
   cudaFreeHost(h->marg_h);
   cudaFreeHost(h->fixed_h);
-  if (h->lm_graph_exec) cudaGraphExecDestroy(h->lm_graph_exec);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return DPBA_SUCCESS;
@@ -1842,11 +1847,20 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   }
   int rc = 0;
   if (h->use_graph) {
-    if (!h->lm_graph_exec || key != h->lm_graph_key) {
-      if (h->lm_graph_exec) {
-        cudaGraphExecDestroy(h->lm_graph_exec);
-        h->lm_graph_exec = nullptr;
+    if (h->lm_graph_key.empty()) {  // an option changed (or first solve): every cached graph is stale
+      for (auto& g : h->lm_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+      h->lm_graphs.clear();
+    }
+    dpba_handle::LmGraph* cur = nullptr;
+    for (auto& g : h->lm_graphs)
+      if (g.key == key) cur = &g;
+    if (!cur) {
+      if (h->lm_graphs.size() >= 16) {  // oldest out
+        if (h->lm_graphs.front().exec) cudaGraphExecDestroy(h->lm_graphs.front().exec);
+        h->lm_graphs.erase(h->lm_graphs.begin());
       }
+      dpba_handle::LmGraph fresh;
       profile_collect(h);
       cudaGraph_t graph = nullptr;
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
@@ -1859,28 +1873,31 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
       if (ce != cudaSuccess) return fail(h, DPBA_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
       {  // kernels per replay, for dpba_launch_count
         size_t nn = 0;
-        h->lm_graph_kernels = 0;
+        fresh.kernels = 0;
         if (cudaGraphGetNodes(graph, nullptr, &nn) == cudaSuccess && nn) {
           std::vector<cudaGraphNode_t> nodes(nn);
           cudaGraphGetNodes(graph, nodes.data(), &nn);
           for (auto nd : nodes) {
             cudaGraphNodeType ty;
-            if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) ++h->lm_graph_kernels;
+            if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) ++fresh.kernels;
           }
         }
       }
-      ce = cudaGraphInstantiate(&h->lm_graph_exec, graph, 0);
+      ce = cudaGraphInstantiate(&fresh.exec, graph, 0);
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) return fail(h, DPBA_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+      fresh.key = key;
+      fresh.events = h->ev_used;
       h->lm_graph_key = key;
-      h->lm_graph_events = h->ev_used;
       h->ev_used = 0;
       h->lm_graph_fresh = true;
+      h->lm_graphs.push_back(fresh);
+      cur = &h->lm_graphs.back();
     }
-    CK(cudaGraphLaunch(h->lm_graph_exec, h->stream));
-    if (!h->lm_graph_fresh) pba::add_launches(h->lm_graph_kernels);  // the capture pass already counted once
+    CK(cudaGraphLaunch(cur->exec, h->stream));
+    if (!h->lm_graph_fresh) pba::add_launches(cur->kernels);  // the capture pass already counted once
     h->lm_graph_fresh = false;
-    if (h->profiling) h->ev_used = h->lm_graph_events;
+    if (h->profiling) h->ev_used = cur->events;
   } else {
     if ((rc = lm_enqueue(h, H_marg != nullptr))) return rc;
   }

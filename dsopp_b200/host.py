@@ -194,6 +194,16 @@ class WindowStep:
         _ck(self.lib.dpbah_solve_window(self.h.h, C.byref(self.io), self.h.cfg.width, self.h.cfg.height))
         return self.io.energy, self.io.iterations
 
+    def run_sliding(self):
+        """dpbah_solve_sliding: the oldest keyframe leaves, ONE keyframe arrives from the host buffers (the one that left,
+        so the window keeps its n frames in rotating order), solve, results of every frame back.  Call run() once first."""
+        if not hasattr(self, "_order"):
+            self._order = np.arange(self.io.n_frames, dtype=np.int32)
+            self.lib.dpbah_solve_sliding.argtypes = [_P, C.POINTER(_WindowIOStruct), _P, _I, _I]
+        _ck(self.lib.dpbah_solve_sliding(self.h.h, C.byref(self.io), self._order.ctypes.data, self.h.cfg.width,
+                                         self.h.cfg.height))
+        return self.io.energy, self.io.iterations
+
 
 class CudaPhotometricBundleAdjustment:
     """Python proxy of the C++ class of the same name (csrc/host/cuda_photometric_bundle_adjustment.hpp)."""

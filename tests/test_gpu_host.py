@@ -227,3 +227,47 @@ def test_batched_frame_statuses_equal_the_per_pair_calls():
             assert (s1 == st[t]).all() and (c1 == cd[t]).all()
     assert (h.get_landmarks(1)["idepth"] == idp_want).all()
     h.close()
+
+
+def test_one_call_window_step_and_sliding_step():
+    """dpbah_solve_window (whole window from host buffers, solve, results back in ONE C++ call) equals the same sequence
+    driven call by call; dpbah_solve_sliding (oldest keyframe out, one keyframe in) returns to the same solve after n steps
+    (the frame that leaves is the one that arrives, so the window then holds its frames in the original order again)."""
+    from dsopp_b200 import capi, host
+    win = synth.make_window(n_frames=4, points_per_frame=200, seed=31, ab_scale=0.0)
+    n = win.n_frames
+    eps0 = np.concatenate([f.state_eps for f in win.frames])
+    h = capi.upload_window(win, max_frames=4)
+    h.first_estimate()
+    e_ref, it_ref, _, nv_ref = h.solve_lm(SIGMA)
+    eps_ref, _ = h.get_state()
+    id_ref = [h.get_landmarks(i)["idepth"].copy() for i in range(n)]
+    st_ref = [h.get_frame_statuses(i)[0].copy() for i in range(n)]
+    frames = [dict(frame_id=f.frame_id, image=np.ascontiguousarray(f.image, np.float32), mask=np.ascontiguousarray(f.mask),
+                   T_w_lin=f.T_w_lin, exposure=f.exposure, ab0=f.ab0, intr=f.intr, fixed=f.fixed,
+                   uv=np.ascontiguousarray(f.uv, np.float32), idepth=np.ascontiguousarray(f.idepth, np.float32),
+                   patch=np.ascontiguousarray(f.patch, np.float32), flags=np.ascontiguousarray(f.flags, np.uint8))
+              for f in win.frames]
+    st = {k: np.ascontiguousarray(v, np.uint8) for k, v in win.statuses.items()}
+    step = host.WindowStep(h, frames, st, eps0)
+    e, it = step.run()
+    assert it == it_ref and step.io.n_valid == nv_ref
+    assert abs(e - e_ref) <= 1e-12 * abs(e_ref)
+    assert np.array_equal(step.out["eps"], eps_ref)
+    for i in range(n):
+        assert np.array_equal(step.out["idepth"][i], id_ref[i])
+        for t in range(n):
+            if t != i:
+                assert np.array_equal(step.out["statuses"][i][t], st_ref[i][t])
+    assert step.io.h2d_bytes > 4 * win.width * win.height * 12 and step.io.d2h_bytes > 0
+    energies = []
+    for k in range(n):
+        ek, itk = step.run_sliding()
+        assert np.isfinite(ek) and itk >= 3
+        energies.append(ek)
+    # n steps later every frame has left and re-entered once: original order, frame 0 holds the gauge again
+    assert abs(energies[-1] - e_ref) <= 1e-9 * abs(e_ref), (energies, e_ref)
+    assert np.abs(step.out["eps"] - eps_ref).max() <= 1e-9
+    # in between the same frames are solved with another keyframe fixed: same scene, energies of the same size
+    assert all(abs(x - e_ref) <= 0.05 * abs(e_ref) for x in energies), (energies, e_ref)
+    h.close()
