@@ -121,7 +121,7 @@ def config_dict(world, extra=None):
         "gn_iters_per_step": GN_ITERS,
         "lm": "levenberg_marquardt_algorithm::solve, force_accept, min_it=max_it=7, tolerances 0 (fixed work per step)",
         "parallelism": f"landmarks sharded over {world} GPU(s), frames replicated",
-        "l2": "256 MiB buffer written between timed steps (L2 flush); within a step the 79 MB image set (32-byte texel-pair records) is L2-resident",
+        "l2": "256 MiB buffer written between timed steps (L2 flush); within a step the 79 MB image set (32-byte texel-pair records) stays in the 126 MB L2",
     }
     if extra:
         c.update(extra)
@@ -701,16 +701,29 @@ def run_ours(args):
     fused_avg = fused_ms / max(fused_n, 1)
     fused_bytes = 51 * units_local + img_bytes + 2 * (D * D + D) * 8
     achieved = fused_bytes / (fused_avg * 1e-3) / 1e9 if fused_avg > 0 else 0.0
-    roofline = {"kernel": "k_linearize_fused (K1+K3+K4a, nothing materialised)", "bound": "hbm",
+    # FLOPs of one launch from the committed SASS mix of the same configuration (profiles/r02a_k_linearize_fused2.md: FFMA
+    # 3.53 M, FMUL 1.49 M, FADD 1.06 M warp instructions per launch at 112 000 patch-residuals): 2750 FLOP per patch-residual
+    FLOP_PER_UNIT = (3534320 * 64 + 1492984 * 32 + 1062992 * 32) / 112000.0
+    FP32_PEAK_TFLOPS = 72.6  # measured on this pool's B200 with tools/fp32_probe.cu (profiles/r02a_fp32_probe.txt)
+    fused_tflops = FLOP_PER_UNIT * units_local / (fused_avg * 1e-3) / 1e12 if fused_avg > 0 else 0.0
+    roofline = {"kernel": "k_linearize_fused2 (K1+K3+K4a, one thread per patch-residual, nothing materialised)", "bound": "hbm",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture of this
-                # configuration (profiles/r01h_k_linearize_fused.md; cold L2: the 79 MB image set is read in part)
-                "traffic": (60.58e6 + 2.60e6) if (world == 1 and N_FRAMES == 8 and PTS_PER_GPU == 2000) else None,
-                "traffic_source": "profiles/r01h_k_linearize_fused.md",
+                # configuration (profiles/r02a_k_linearize_fused2.md; cold L2: the 79 MB image set is read in part)
+                "traffic": (60.91e6 + 1.20e6) if (world == 1 and N_FRAMES == 8 and PTS_PER_GPU == 2000) else None,
+                "traffic_source": "profiles/r02a_k_linearize_fused2.md",
                 "peak_source": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_launch": fused_bytes, "avg_launch_ms": fused_avg, "launches_timed": fused_n,
-                "note": "fused linearise is bound by fp32 issue + L2 gathers, not HBM (SURVEY 8d: ~90 FLOP/B); "
-                        "see roofline_sweep for the HBM-bound materialising sweep the 60% target is stated on"}
+                "note": "the fused linearise is bound by fp32 issue + L2 gather latency, not HBM (SURVEY 8d: ~55 FLOP/B): see "
+                        "roofline_fp32 for the other ceiling and roofline_sweep for the HBM-bound materialising sweep the 60% "
+                        "target is stated on (a kernel that is NOT on the production solve path)"}
+    roofline_fp32 = {"kernel": roofline["kernel"], "bound": "fp32 CUDA-core issue", "achieved": fused_tflops,
+                     "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fused_tflops / FP32_PEAK_TFLOPS,
+                     "peak_source": "measured: tools/fp32_probe.cu, 148 SMs x 125 FFMA/clk (profiles/r02a_fp32_probe.txt)",
+                     "flop_per_patch_residual": FLOP_PER_UNIT,
+                     "flop_source": "SASS opcode mix of the committed capture (FFMA x 2 + FMUL + FADD), profiles/r02a_k_linearize_fused2.md",
+                     "issue_slots_note": "11.4 M warp instructions per launch = 9.8 us at one instruction per scheduler per "
+                                         "clock; the kernel runs at 0.37 of that rate while active (long-scoreboard: L2 gathers)"}
     sweep_bytes = 595 * units_local + img_bytes
     sweep_ach = sweep_bytes / (sweep * 1e-3) / 1e9 if sweep else 0.0
     roofline_sweep = {"kernel": "k_materialise_sweep (K1, reference-surface mode, 595 B/unit)", "bound": "hbm",
@@ -772,7 +785,8 @@ def run_ours(args):
                            "path": "as e2e, but dpba_push_frame_raw: 8-bit frames in, photometric table + {I,dx,dy} on the device"},
         "e2e_one_new_keyframe": e2e_sliding,
         "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_sweep": roofline_sweep, "roofline_sweep_big": roofline_sweep_big,
+        "roofline": roofline, "roofline_fp32": roofline_fp32, "roofline_sweep": roofline_sweep,
+        "roofline_sweep_big": roofline_sweep_big,
         "kernel_ms": kernel_ms,
         "cpu_baseline": cpu,
         "parity_check": parity_check,

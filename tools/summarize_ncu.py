@@ -42,8 +42,8 @@ def launches(tag):
             agg[d["Kernel Name"].split("(")[0]].append(float(d["Metric Value"].replace(",", "")))
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(OUT, f"{tag}_launches.md"), "w") as f:
-        f.write(f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu`\n\n"
-                "`ncu --metrics gpu__time_duration.sum --clock-control none -s 225 -c 400` (cold-cache, serialised: "
+        f.write(f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu --no-big-sweep --no-config2 --no-config3 --no-config4`\n\n"
+                "`ncu --metrics gpu__time_duration.sum --clock-control none -s 340 -c 500` (cold-cache, serialised: "
                 "compare shares, not absolutes).\n\n| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"| `{k[:70]}` | {len(v)} | {sum(v) / 1e3:.1f} | {sum(v) / len(v) / 1e3:.2f} | {sum(v) / tot:.1%} |\n")
