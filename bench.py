@@ -387,11 +387,14 @@ def run_ours(args):
         h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
         h.first_estimate()
         h.evaluate(SIGMA, True, True)  # first collective outside any graph capture: NCCL sets its channels up here
-        if args.peer_exchange:
+        # exchange of the reduced system: ncclAllReduce on 2 GPUs, the library's own NVLink mailbox kernel from 4 GPUs on
+        # (measured on B200: 118.9 vs 126.7 us per iteration at N = 2, 151.3 vs 127.7 at N = 8 -- NCCL's latency grows with
+        # the rank count, the one-shot mailbox exchange does not; profiles/r02_ab.md).  --peer-exchange 0/1 overrides.
+        use_peer = args.peer_exchange == 1 or (args.peer_exchange < 0 and world > 2)
+        if use_peer:
             capi.attach_peers(h, rank, world, dev)
             h.set_option("peer_exchange", 1)
-            if args.peer_fused >= 0:
-                h.set_option("peer_fused", args.peer_fused)
+            h.set_option("peer_fused", args.peer_fused if args.peer_fused >= 0 else 0)
             h.evaluate(SIGMA, True, True)
 
     ab0 = np.stack([f.ab0 for f in win.frames])
@@ -518,9 +521,10 @@ def run_ours(args):
     # from pinned host memory with its landmarks and connection statuses, solve, every frame's results back
     step_io.run()
     e2e_sliding_ms = []
-    for i in range(3 + min(args.steps, 16)):
+    n_warm = n + 1  # one full rotation first: every (logical -> physical slot) map of the cycle has its captured graph
+    for i in range(n_warm + min(args.steps, 16)):
         ms, _ = timed(step_io.run_sliding)
-        if i >= 3:
+        if i >= n_warm:
             e2e_sliding_ms.append(ms)
     t_sl = torch.tensor([sum(e2e_sliding_ms) / len(e2e_sliding_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -599,6 +603,10 @@ def run_ours(args):
                 uid3.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
             dist.broadcast(uid3, 0)
             h3.comm_init(bytes(uid3.cpu().numpy().tobytes()), rank, world)
+            if use_peer:
+                capi.attach_peers(h3, rank, world, dev)
+                h3.set_option("peer_exchange", 1)
+                h3.set_option("peer_fused", 0)
         h3.first_estimate()
         sys3 = h3.linearize(SIGMA, True, True, False)  # also the first collective of this communicator (outside capture)
         check3 = None
@@ -609,9 +617,11 @@ def run_ours(args):
             href.close()
             errs = {nm: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
                     for nm, a, b in zip(("H_pose", "b_pose", "H_schur", "b_schur"), sys3, ref3)}
-            check3 = {"sharded_vs_unsharded_rel_max": errs, "ok": bool(max(errs.values()) <= 1e-9),
+            # the per-chunk partial sums are fp32 (other landmarks share a chunk when the window is sharded), their sum
+            # over chunks and ranks is fp64: agreement to fp32 partial-sum noise, 1e-6 of the largest entry
+            check3 = {"sharded_vs_unsharded_rel_max": errs, "ok": bool(max(errs.values()) <= 1e-6), "tolerance": 1e-6,
                       "what": "rank 0: dpba_linearize of the window sharded over N ranks (exchanged sum) against the same "
-                              "window unsharded on one GPU; fp64 sums in a different order"}
+                              "window unsharded on one GPU"}
         stream3 = torch.cuda.ExternalStream(h3.stream, device=dev)
 
         def reset3():
@@ -773,7 +783,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": config_dict(world, {"exchange": "NVLink mailbox all-reduce (peer_exchange.cu)" if args.peer_exchange and world > 1
+        "config": config_dict(world, {"exchange": "NVLink mailbox all-reduce (peer_exchange.cu)" if world > 1 and use_peer
                                       else ("ncclAllReduce of the packed system, one per GN iteration" if world > 1 else "none")}),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -815,8 +825,9 @@ def main():
     ap.add_argument("--pdl", type=int, default=-1, help="A/B: programmatic dependent launch between the device-LM kernels (default 1)")
     ap.add_argument("--merged-tail", type=int, default=-1, help="A/B: 1 = three launches per LM iteration (default), 0 = the eight-kernel sequence")
     ap.add_argument("--speculative-multi-gpu", type=int, default=-1, help="A/B: one-allreduce speculative device LM for N > 1")
-    ap.add_argument("--peer-exchange", action="store_true",
-                    help="N > 1: sum the exchange block with the library's NVLink mailbox kernel instead of ncclAllReduce")
+    ap.add_argument("--peer-exchange", type=int, default=-1, nargs="?", const=1,
+                    help="N > 1: 1 = sum the exchange block with the library's NVLink mailbox kernel, 0 = ncclAllReduce "
+                         "(default: mailbox kernel from 4 GPUs on)")
     ap.add_argument("--peer-fused", type=int, default=-1, help="N > 1 with --peer-exchange: 1 = exchange fused into the producers / consumers (default), 0 = stand-alone mailbox kernel")
     ap.add_argument("--fused-prefetch", type=int, default=-1, help="tuning A/B: 0/1 L1 prefetch of the next taps in the fused linearise")
     ap.add_argument("--host-lm", action="store_true", help="drive the LM loop from the C++ host adapter instead of dpba_solve_lm")

@@ -95,7 +95,8 @@ __host__ __device__ inline void peer_signal(const PeerDev& pd, int c, unsigned e
 #pragma unroll
   for (int r = 0; r < PEER_MAXW; ++r)
     if (r == s) peer_flags = pd.flag[r];
-  peer_fence_system();
+  // no second fence here: every pushing thread fenced at system scope before the CTA barrier that precedes this call, and
+  // the release store orders this thread's own earlier accesses
   peer_store_release(peer_flags + pd.rank * PEER_MAXC + c, epoch);
 }
 
