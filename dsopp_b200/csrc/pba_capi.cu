@@ -147,7 +147,12 @@ struct dpba_handle {
   // pack kernel of keyframe k reads its staging buffer on the main stream
   float* stage_alt = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t pack_stream = nullptr;   // the pack kernels run beside the main stream, which only joins before the first
+                                        // kernel that reads an image (wait_images): landmark / status uploads and the
+                                        // per-pair constants no longer queue behind the image DMA
   cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+  cudaEvent_t img_done = nullptr, main_mark = nullptr;
+  bool img_pending = false;
   int stage_idx = 0;
   float* stage_h = nullptr;  // pinned staging for images
   float *m_r = nullptr, *m_jref = nullptr, *m_jtgt = nullptr, *m_did = nullptr, *m_w = nullptr;
@@ -332,8 +337,16 @@ ReduceBuf redbuf_out(dpba_handle* h) {
   return rb;
 }
 
+// the main stream joins the image uploads (copy + pack streams); called outside stream capture only
+void wait_images(dpba_handle* h) {
+  if (!h->img_pending) return;
+  cudaStreamWaitEvent(h->stream, h->img_done, 0);
+  h->img_pending = false;
+}
+
 WindowDev make_window(dpba_handle* h) {
   h->rb_valid = false;  // every kernel-launching path builds its WindowDev here: the device state is about to change
+  wait_images(h);       // (dpba_solve_lm joins before it starts capturing; by then nothing is pending here)
   WindowDev w;
   memset(&w, 0, sizeof(w));
   w.n_frames = h->n_frames;
@@ -483,6 +496,7 @@ void host_se3_exp_translation(const double* T_lin, const double* eps, double* t_
 // one bulk device -> pinned host readback of the landmark arrays and residual statuses
 int ensure_readback(dpba_handle* h) {
   if (h->rb_valid) return 0;
+  wait_images(h);  // a synchronising call: borrowed page-locked images are released afterwards
   const size_t mp = h->cfg.max_points_per_frame, nlm = (size_t)h->cfg.max_frames * mp;
   const size_t nst = (size_t)h->cfg.max_frames * PBA_MAXF * mp;
   CK(cudaMemcpyAsync(h->rb_slab, h->lm_slab, 5 * nlm * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -531,9 +545,15 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
     CK(cudaStreamWaitEvent(h->copy_stream, h->stage_free[sb], 0));  // its last reader (a pack kernel) has finished
     CK(cudaMemcpyAsync(dst, src, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
     CK(cudaEventRecord(h->stage_ready[sb], h->copy_stream));
-    CK(cudaStreamWaitEvent(h->stream, h->stage_ready[sb], 0));
-    pba::launch_pack_image(dst, h->img[phys], (int)npx, W, h->stream);
-    CK(cudaEventRecord(h->stage_free[sb], h->stream));
+    // the pack kernel overwrites a physical image slot: everything the main stream has queued so far (a solve that still
+    // reads the slot's previous occupant) comes first
+    CK(cudaEventRecord(h->main_mark, h->stream));
+    CK(cudaStreamWaitEvent(h->pack_stream, h->main_mark, 0));
+    CK(cudaStreamWaitEvent(h->pack_stream, h->stage_ready[sb], 0));
+    pba::launch_pack_image(dst, h->img[phys], (int)npx, W, h->pack_stream);
+    CK(cudaEventRecord(h->stage_free[sb], h->pack_stream));
+    CK(cudaEventRecord(h->img_done, h->pack_stream));
+    h->img_pending = true;
   } else {
     if (channels > 0) {
       if (!pinned) {
@@ -706,6 +726,9 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   CKC(cudaMalloc(&h->stage, npx * 3 * sizeof(float)));
   CKC(cudaMalloc(&h->stage_alt, npx * 3 * sizeof(float)));
   CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&h->pack_stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreateWithFlags(&h->img_done, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&h->main_mark, cudaEventDisableTiming));
   for (int k = 0; k < 2; ++k) {
     CKC(cudaEventCreateWithFlags(&h->stage_ready[k], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->stage_free[k], cudaEventDisableTiming));
@@ -751,6 +774,12 @@ int dpba_destroy(dpba_handle* h) {
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamDestroy(h->copy_stream);
   }
+  if (h->pack_stream) {
+    cudaStreamSynchronize(h->pack_stream);
+    cudaStreamDestroy(h->pack_stream);
+  }
+  if (h->img_done) cudaEventDestroy(h->img_done);
+  if (h->main_mark) cudaEventDestroy(h->main_mark);
   for (int k = 0; k < 2; ++k) {
     if (h->stage_ready[k]) cudaEventDestroy(h->stage_ready[k]);
     if (h->stage_free[k]) cudaEventDestroy(h->stage_free[k]);
@@ -925,6 +954,7 @@ int dpba_num_frames(const dpba_handle* h) { return h ? h->n_frames : DPBA_E_INVA
 
 int dpba_synchronize(dpba_handle* h) {
   REQUIRE(h, "null handle");
+  wait_images(h);
   CK(cudaStreamSynchronize(h->stream));
   return DPBA_SUCCESS;
 }
@@ -1832,6 +1862,7 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   fill_frame_params(h);
   h->linearized = true;
   h->lin_frames = N;
+  wait_images(h);  // before any capture starts: an event recorded outside a capture cannot be waited on inside it
 
   // The launch sequence only depends on the window shape and a few options: capture it once into a CUDA graph and
   // replay it (one cudaGraphLaunch instead of ~110 launches per solve); all inputs travel through pinned buffers.
