@@ -375,6 +375,8 @@ def run_ours(args):
         h.set_option("merged_tail", args.merged_tail)
     if args.pdl >= 0:
         h.set_option("pdl", args.pdl)
+    if args.three_branch >= 0:
+        h.set_option("three_branch", args.three_branch)
     if args.speculative_multi_gpu >= 0:
         h.set_option("speculative_multi_gpu", args.speculative_multi_gpu)
     if args.fused_prefetch >= 0:
@@ -822,6 +824,7 @@ def main():
     ap.add_argument("--no-big-sweep", action="store_true", help="skip the 20000-points/KF materialising-sweep roofline")
     ap.add_argument("--fused-min-blocks", type=int, default=0, help="tuning A/B: 3 or 4 resident CTAs/SM for the fused linearise")
     ap.add_argument("--fused-version", type=int, default=0, help="A/B: 1 = first-generation fused linearise (8 lanes per patch), 2 = one thread per patch-residual")
+    ap.add_argument("--three-branch", type=int, default=-1, help="A/B: 1 = three graph branches, energy decision from the sweep's records (default), 0 = the round-1 two-branch sequence")
     ap.add_argument("--pdl", type=int, default=-1, help="A/B: programmatic dependent launch between the device-LM kernels (default 1)")
     ap.add_argument("--merged-tail", type=int, default=-1, help="A/B: 1 = three launches per LM iteration (default), 0 = the eight-kernel sequence")
     ap.add_argument("--speculative-multi-gpu", type=int, default=-1, help="A/B: one-allreduce speculative device LM for N > 1")

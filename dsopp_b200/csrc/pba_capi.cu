@@ -66,6 +66,8 @@ struct dpba_handle {
   dpba_config cfg;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // side branch of the LM launch sequence (fork/join inside the graph)
+  cudaStream_t stream3 = nullptr;            // second side branch (block assembly beside the Schur reduction)
+  bool three_branch = false;                 // option "three_branch": measured slower (94.7 vs 90.5 us per iteration)
   std::vector<cudaEvent_t> fork_ev;          // dependency-only events of the fork/join edges
   size_t fork_used = 0;
   std::string err = "";
@@ -656,6 +658,7 @@ int dpba_create(const dpba_config* cfg, dpba_handle** out) {
   CKC(cudaSetDevice(cfg->device));
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
   const size_t npx = (size_t)cfg->width * cfg->height;
   const size_t mp = cfg->max_points_per_frame;
   const size_t nlm = (size_t)cfg->max_frames * mp;
@@ -770,6 +773,7 @@ int dpba_destroy(dpba_handle* h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->fork_ev) cudaEventDestroy(e);
   if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->stream3) cudaStreamDestroy(h->stream3);
   if (h->copy_stream) {
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamDestroy(h->copy_stream);
@@ -1617,6 +1621,82 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
     CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
     return 0;
   }
+  // ---- round 2 experiment (option "three_branch", off): THREE graph branches, no core reduction on the critical path ----
+  // Measured SLOWER than the two-branch sequence below (94.7 against 90.5 us per iteration, profiles/r02_ab.md): on this
+  // problem size the small kernels of an iteration do not overlap the way the dependency graph suggests.
+  //   main : sweep_k -> energy decision_k (pair energies straight from the sweep's per-chunk records) -> LM step_{k+1}
+  //          -> back-substitution_{k+1} -> sweep_{k+1}
+  //   s2   : Schur partial reduction_k ; landmark accept_k ; pair constants_{k+1}
+  //   s3   : block assembly_k incl. the core reduction it needs (k_reduce_system without its Schur blocks)
+  // Round 1 ran core reduce -> decision on the main branch and Schur reduce -> assembly one after the other on ONE side
+  // branch (23 us, longer than the main branch's 18.6 us): the LM step started ~10 us later than it does now.
+  if (h->speculative && od.force_accept && !multi && h->three_branch && pba::fused_version() == 2) {
+    cudaStream_t s3 = h->stream3;
+    FusedShape shape{0, 0};
+    for (int k = 0; k <= od.max_it; ++k) {
+      const bool more = k < od.max_it;
+      {
+        ProfScope ps(h, 0);
+        shape = pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 1);
+      }
+      if (more) {
+        if ((rc = stream_edge(h, s, s2))) return rc;
+        if ((rc = stream_edge(h, s, s3))) return rc;
+        {
+          ProfScope ps(h, 10, s2);
+          pba::launch_finish_fused(w, rb, shape, s2, h->ctl);
+        }
+        {
+          ProfScope ps(h, 9, s3);
+          pba::launch_reduce_system(w, fej, rb, shape, 1, s3, h->ctl, 0);
+        }
+      }
+      {
+        ProfScope ps(h, 11);
+        pba::launch_lm_energy_from_records(w, h->ctl, h->lmopt, h->fparams, rb.scal, Hm, bm,
+                                           k == 0 ? pba::LM_ENERGY_INITIAL : pba::LM_ENERGY_TRIAL, rb, shape,
+                                           k ? rb.n_part : nullptr, k ? n_norm_parts : 0, s);
+      }
+      if (more) {
+        if ((rc = stream_edge(h, s2, s))) return rc;  // Schur reduction_k and assembly_k before LM step_{k+1}
+        if ((rc = stream_edge(h, s3, s))) return rc;
+      }
+      if (k > 0) {  // acceptStep() / rejectStep() of the landmarks incl. changeResidualStatuses
+        if ((rc = stream_edge(h, s, s2))) return rc;
+        ProfScope ps(h, 11, s2);
+        pba::launch_accept(w, 0, nullptr, s2, h->ctl, 1);
+      }
+      if (!more) {
+        if (k > 0 && (rc = stream_edge(h, s2, s))) return rc;
+        break;
+      }
+      {
+        ProfScope ps(h, 7);
+        pba::launch_lm_step(h->ctl, h->lmopt, h->fparams, h->fixed_dev, N, ro, Hm, bm, h->step_dev, s);
+      }
+      if (k > 0 && (rc = stream_edge(h, s2, s))) return rc;  // accept_k before back_substitute_{k+1}
+      if ((rc = stream_edge(h, s, s2))) return rc;
+      {
+        ProfScope ps(h, 6, s2);
+        pba::launch_pair_setup(h->fparams, N, h->pairs, h->pasm, s2);
+      }
+      {
+        ProfScope ps(h, 5);
+        pba::launch_back_substitute(w, h->step_dev, 0.0, s, h->ctl, rb.n_part);
+      }
+      if ((rc = stream_edge(h, s2, s))) return rc;
+    }
+    pairs();
+    {
+      ProfScope ps(h, 0);
+      pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 3);  // only after a rejected step
+    }
+    if ((rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
+    return 0;
+  }
   if (h->speculative && od.force_accept && !multi) {
     const int n_pairs = N * (N - 1);
     auto spec_linearize = [&](int ctl_mode) {
@@ -1869,7 +1949,7 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   std::vector<long long> key = {N, od.max_it, od.fej, H_marg != nullptr, h->world, (long long)h->profiling,
                                 (long long)(h->speculative && od.force_accept), (long long)h->speculative_multi,
                                 (long long)llround(od.sigma * 1e6), (long long)h->peer_on + 2 * (long long)h->peer_fused,
-                                (long long)h->merged_tail,
+                                (long long)h->merged_tail + 2 * (long long)h->three_branch,
                                 (long long)pba::fused_version()};
   for (int f = 0; f < N; ++f) {  // every per-frame field of WindowDev (the captured kernels hold it BY VALUE)
     key.push_back(h->fr[f].n_lm);
@@ -2017,6 +2097,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
   }
   if (!strcmp(name, "fused_prefetch")) {  // process-wide A/B switch
     pba::set_fused_prefetch(value != 0);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "three_branch")) {
+    h->three_branch = value != 0;
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }

@@ -140,7 +140,11 @@ void launch_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const
                      PairConst* pairs, PairAssemble* pasm, cudaStream_t s);
 // round 2: core reduction + block assembly + Schur partial reduction in one launch
 void launch_reduce_system(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, int with_system, cudaStream_t s,
-                          const LmCtl* ctl = nullptr);
+                          const LmCtl* ctl = nullptr, int with_schur = 1);
+// energy decision reading the pair energies straight from the sweep's per-chunk records (no k_core_reduce in front)
+void launch_lm_energy_from_records(const WindowDev& w, LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, double* scal,
+                                   const double* Hmarg, const double* bmarg, int kind, ReduceBuf rb, FusedShape shape,
+                                   const double* n_part, int n_n, cudaStream_t s);
 void launch_clear_frame_rows(uint8_t* status, uint8_t* cand, uint8_t* jac_valid, float* energy, int phys, int mp,
                              int max_frames, cudaStream_t s);
 void launch_pack_image(const float* src3, float4* dst, int n_px, int W, cudaStream_t s);

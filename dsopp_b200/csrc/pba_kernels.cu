@@ -3046,6 +3046,55 @@ __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDe
   lm_energy_body(ctl, opt, fr, N, scal, Hmarg, bmarg, kind, e_part, n_e, n_part, n_n, from_core);
 }
 
+// The energy decision straight from the sweep's per-chunk records (slots 44 / 45 of every [frame][chunk][target] record
+// carry the pair energies and valid counts): k_core_reduce leaves the critical path of an iteration -- the block
+// assembly reduces the cores it needs itself, on a side branch (k_reduce_system).
+__global__ void __launch_bounds__(256) k_lm_energy_cp(const __grid_constant__ WindowDev w, LmCtl* ctl, const LmOptionsDev* opt,
+                                                      FrameParams* fr, double* scal, const double* Hmarg, const double* bmarg,
+                                                      int kind, const float* __restrict__ core_part, int lpb, int chunks,
+                                                      const double2* __restrict__ n_part, int n_n) {
+  if (!(kind == pba::LM_ENERGY_TRIAL && ctl->done)) {
+    __shared__ double red4[4][8];
+    const int N = w.n_frames;
+    double a = 0, b = 0, c = 0, d = 0;
+    const int recs = N * chunks * (N - 1);  // [frame][chunk][target warp]
+    for (int i = threadIdx.x; i < recs; i += 256) {
+      const int f = i / (chunks * (N - 1)), ch = (i / (N - 1)) % chunks;
+      if (ch * lpb < w.n_lm[f]) {  // chunk CTAs past a frame's last landmark never ran
+        const float2 v = *reinterpret_cast<const float2*>(core_part + (size_t)i * PBA_CORE + 44);
+        a += (double)v.x;
+        b += (double)v.y;
+      }
+    }
+    for (int i = threadIdx.x; i < n_n; i += 256) {
+      const double2 v = n_part[i];
+      c += v.x;
+      d += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(FULL, a, o);
+      b += __shfl_xor_sync(FULL, b, o);
+      c += __shfl_xor_sync(FULL, c, o);
+      d += __shfl_xor_sync(FULL, d, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red4[0][threadIdx.x >> 5] = a;
+      red4[1][threadIdx.x >> 5] = b;
+      red4[2][threadIdx.x >> 5] = c;
+      red4[3][threadIdx.x >> 5] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double t = 0;
+      for (int k = 0; k < 8; ++k) t += red4[threadIdx.x][k];
+      if (threadIdx.x < 2 || n_part) scal[threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+  lm_energy_body(ctl, opt, fr, w.n_frames, scal, Hmarg, bmarg, kind, nullptr, 0, nullptr, 0, 0);
+}
+
 // calculateStep (problem.hpp:342-357): priors (problem.hpp:37-77), full system, Jacobi preconditioner + LDL^T
 // (normal_linear_system.cpp:10-59), all fp64 in one CTA.
 //
@@ -3429,6 +3478,14 @@ void launch_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, int 
                                 reinterpret_cast<const double2*>(n_part), n_n, from_core, peer_collect, 2 * (D * D + D));
 }
 
+void launch_lm_energy_from_records(const WindowDev& w, LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, double* scal,
+                                   const double* Hmarg, const double* bmarg, int kind, ReduceBuf rb, FusedShape shape,
+                                   const double* n_part, int n_n, cudaStream_t s) {
+  ++g_launches;
+  k_lm_energy_cp<<<1, 256, 0, s>>>(w, ctl, opt, fr, scal, Hmarg, bmarg, kind, rb.core_part, shape.lpb, shape.chunks,
+                                   reinterpret_cast<const double2*>(n_part), n_n);
+}
+
 void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed, int N, ReduceBuf rb,
                     const double* Hmarg, const double* bmarg, double* step_dev, cudaStream_t s, int peer_expected) {
   const int D = 8 * N;
@@ -3473,12 +3530,12 @@ void launch_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const
 }
 
 void launch_reduce_system(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, int with_system, cudaStream_t s,
-                          const LmCtl* ctl) {
+                          const LmCtl* ctl, int with_schur) {
   const int N = w.n_frames, D = 8 * N;
   if (N < 2 || shape.lpb == 0) return;
   const int NB = N * (N + 1) / 2;
   const int T4 = D / 4, nout = T4 * (T4 + 1) / 2 * 16 + D;
-  const int NF = with_system ? (nout + 31) / 32 : 0;
+  const int NF = (with_system && with_schur) ? (nout + 31) / 32 : 0;
   const size_t smem = (size_t)std::max(2, N - 1) * RSYS_W * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
