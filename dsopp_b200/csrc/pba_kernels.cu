@@ -3183,27 +3183,24 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
     S[D * LD + tid] = b * pre[tid];
   }
   const int ty = tid >> 4, tx = tid & 15;
-  __shared__ double s_ld[36], s_inv[8];  // l_cj (j < c) and 1 / d_j of the current diagonal block
   stamp(2);
   for (int kb = 0; kb < D; kb += 8) {
     __syncthreads();
     if (kb < 64) stamp(3 + kb / 8);
     const int i = kb + tid;  // this thread's row (row D is the right-hand side)
     const bool act = i <= D;
-    double a[8];
+    // the 8x8 diagonal block, packed lower triangle g[r (r + 1) / 2 + c], factored redundantly by every thread
+    double g[36], inv[8], a[8];
     if (act) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = (i >= kb + c) ? S[i * LD + kb + c] : 0.0;
-    }
-    // The 8x8 diagonal block, packed lower triangle g[r (r + 1) / 2 + c]: factored by warp 0 alone and published through
-    // shared memory.  (Round 1 let every thread factor it redundantly to save this publication; the 140 dependent-ish
-    // fp64 FMAs times 256 threads then cost more pipe time than the whole trailing update -- fp64 is 59 FMA/clk/SM here.)
-    if (tid < 32) {
-      double g[36], inv[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) g[r * (r + 1) / 2 + c] = S[(kb + r) * LD + kb + c];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = (i >= kb + c) ? S[i * LD + kb + c] : 0.0;
+    }
+    __syncthreads();  // rows kb..kb+7 are overwritten below by their owners
+    if (act) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         inv[j] = rcp64(g[j * (j + 1) / 2 + j]);
@@ -3214,32 +3211,22 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
           for (int c = j + 1; c <= r; ++c) g[r * (r + 1) / 2 + c] -= l * g[c * (c + 1) / 2 + j];
         }
       }
-      if (tid == 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s_inv[j] = inv[j];
-          dinv[kb + j] = inv[j];
-#pragma unroll
-          for (int c = j + 1; c < 8; ++c) s_ld[c * (c + 1) / 2 + j] = g[c * (c + 1) / 2 + j] * inv[j];
-        }
-      }
-    }
-    if (kb == 0) stamp(11);
-    __syncthreads();  // s_ld / s_inv published; rows kb..kb+7 are overwritten below by their owners
-    if (kb == 0) stamp(12);
-    if (act) {
       // own row: same recurrence (for a row of the diagonal block the entries right of the diagonal are unused)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
 #pragma unroll
-        for (int c = j + 1; c < 8; ++c) a[c] -= a[j] * s_ld[c * (c + 1) / 2 + j];
+        for (int c = j + 1; c < 8; ++c) a[c] -= a[j] * (g[c * (c + 1) / 2 + j] * inv[j]);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (i >= kb + j) {
-          S[i * LD + kb + j] = a[j];          // raw column entry x_ij = l_ij d_j
-          Lp[i * LPS + j] = a[j] * s_inv[j];  // l_ij
+          S[i * LD + kb + j] = a[j];        // raw column entry x_ij = l_ij d_j
+          Lp[i * LPS + j] = a[j] * inv[j];  // l_ij
         }
+      }
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dinv[kb + j] = inv[j];
       }
     }
     if (kb == 0) stamp(13);

@@ -19,7 +19,7 @@ names.update({18: "factorised", 20: "step written", 21: "pair constants written"
 print("k_lm_solve energy body (last launch): sums", out[51] - out[50], "priors+decision", out[52] - out[51], " kernel start->body", out[50] - out[0])
 print("k_reduce_system assemble block 0: core reduction", out[31] - out[30], "products", out[32] - out[31], "barrier", out[33] - out[32], "write", out[34] - out[33])
 print("k_reduce_system schur block: sums", out[41] - out[40], "barrier", out[42] - out[41], "final", out[43] - out[42])
-print("block step 0: loads + diagonal factorisation (thread 0)", out[11] - out[3], "barrier", out[12] - out[11], "row recurrence + stores", out[13] - out[12], "barrier", out[14] - out[13], "trailing update", out[4] - out[14])
+print("block step 0: loads + barrier + diagonal block + row recurrence + stores", out[13] - out[3], "barrier", out[14] - out[13], "trailing update", out[4] - out[14])
 prev = 0
 for i in sorted(names):
     print(f"{names[i]:28s} {t[i]:8d} cycles  (+{t[i] - prev})")
