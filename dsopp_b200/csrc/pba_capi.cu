@@ -67,6 +67,7 @@ struct dpba_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // side branch of the LM launch sequence (fork/join inside the graph)
   cudaStream_t stream3 = nullptr;            // second side branch (block assembly beside the Schur reduction)
+  bool final_sweep = false;                  // option "final_sweep": run the (redundant) closing residual sweep of a speculative solve
   bool three_branch = false;                 // option "three_branch": measured slower (94.7 vs 90.5 us per iteration)
   std::vector<cudaEvent_t> fork_ev;          // dependency-only events of the fork/join edges
   size_t fork_used = 0;
@@ -1615,7 +1616,11 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
       ProfScope ps(h, 0);
       pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 3);  // only after a rejected step (see below)
     }
-    if ((rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
+    // The closing calculateEnergy() (levenberg_marquardt_algorithm.hpp:119,126) is a no-op here: the last sweep that ran
+    // -- the trial evaluation of the last accepted step, or the re-linearisation at the restored state after a rejected
+    // one -- already left every residual's energy and candidate at the final state (same per-residual code, same state), and
+    // the accept / reject kernel committed the statuses.  Option "final_sweep" brings the redundant sweep back.
+    if (h->final_sweep && (rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
@@ -1691,7 +1696,11 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
       ProfScope ps(h, 0);
       pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 3);  // only after a rejected step
     }
-    if ((rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
+    // The closing calculateEnergy() (levenberg_marquardt_algorithm.hpp:119,126) is a no-op here: the last sweep that ran
+    // -- the trial evaluation of the last accepted step, or the re-linearisation at the restored state after a rejected
+    // one -- already left every residual's energy and candidate at the final state (same per-residual code, same state), and
+    // the accept / reject kernel committed the statuses.  Option "final_sweep" brings the redundant sweep back.
+    if (h->final_sweep && (rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
@@ -1765,7 +1774,11 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
     }
     pairs();
     spec_linearize(3);  // only after a rejected step: landmark fields back to the (restored) final state
-    if ((rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
+    // The closing calculateEnergy() (levenberg_marquardt_algorithm.hpp:119,126) is a no-op here: the last sweep that ran
+    // -- the trial evaluation of the last accepted step, or the re-linearisation at the restored state after a rejected
+    // one -- already left every residual's energy and candidate at the final state (same per-residual code, same state), and
+    // the accept / reject kernel committed the statuses.  Option "final_sweep" brings the redundant sweep back.
+    if (h->final_sweep && (rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
@@ -1842,7 +1855,11 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
       ProfScope ps(h, 0);
       pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 3);
     }
-    if ((rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
+    // The closing calculateEnergy() (levenberg_marquardt_algorithm.hpp:119,126) is a no-op here: the last sweep that ran
+    // -- the trial evaluation of the last accepted step, or the re-linearisation at the restored state after a rejected
+    // one -- already left every residual's energy and candidate at the final state (same per-residual code, same state), and
+    // the accept / reject kernel committed the statuses.  Option "final_sweep" brings the redundant sweep back.
+    if (h->final_sweep && (rc = energy_eval(0, 0, pba::LM_ENERGY_FINAL))) return rc;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->ctl_h, h->ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->fparams_h, h->fparams, sizeof(FrameParams) * N, cudaMemcpyDeviceToHost, s));
@@ -1949,7 +1966,7 @@ int dpba_solve_lm(dpba_handle* h, const dpba_lm_options* o, const double* H_marg
   std::vector<long long> key = {N, od.max_it, od.fej, H_marg != nullptr, h->world, (long long)h->profiling,
                                 (long long)(h->speculative && od.force_accept), (long long)h->speculative_multi,
                                 (long long)llround(od.sigma * 1e6), (long long)h->peer_on + 2 * (long long)h->peer_fused,
-                                (long long)h->merged_tail + 2 * (long long)h->three_branch,
+                                (long long)h->merged_tail + 2 * (long long)h->three_branch + 4 * (long long)h->final_sweep,
                                 (long long)pba::fused_version()};
   for (int f = 0; f < N; ++f) {  // every per-frame field of WindowDev (the captured kernels hold it BY VALUE)
     key.push_back(h->fr[f].n_lm);
@@ -2097,6 +2114,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
   }
   if (!strcmp(name, "fused_prefetch")) {  // process-wide A/B switch
     pba::set_fused_prefetch(value != 0);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "final_sweep")) {
+    h->final_sweep = value != 0;
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
