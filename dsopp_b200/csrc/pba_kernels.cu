@@ -1087,9 +1087,11 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
   const int t = warp + (warp >= f);
   const int lm_base = lm_index(w, f, 0);
 
+  stamp(30);
   for (int i = threadIdx.x; i < lpb * (D + 2 + 2 * nwarps); i += blockDim.x) hpd_s[i] = 0.f;
   reinterpret_cast<float4*>(&pcs[warp])[lane] = reinterpret_cast<const float4*>(&w.pairs[f * PBA_MAXF + t])[lane];
   __syncthreads();
+  stamp(31);
   const PairConst& pc = pcs[warp];
   const float4* __restrict__ img = w.img[t];
   const uint8_t* __restrict__ mask = w.mask_all[t] ? nullptr : w.mask[t];
@@ -1189,6 +1191,7 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
     }
     if (FEJ) ok = ok && jv;  // evaluate_jacobians.hpp:94
     const bool ev = ok && (status == K_OK);
+    if (g0 == 0) stamp(32);
     // patch norm in the 8-lane butterfly order of the first generation (and of oracle/cpu_ref `device_ops`)
     float q[8];
 #pragma unroll
@@ -1273,6 +1276,7 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
       hdd += wd * d;
       bd += wd * rr[p];
     }
+    if (g0 == 0) stamp(33);
     if (sel) {  // this thread is the only writer of target block t of its landmark
       float4* hp = reinterpret_cast<float4*>(hpd_s + ls * D + 8 * t);
       hp[0] = make_float4(-pt[0], -pt[1], -pt[2], -pt[3]);
@@ -1294,7 +1298,9 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
       tot0 += v2[0];
       tot1 += v2[1];
     }
+    if (g0 == 0) stamp(34);
   }
+  stamp(35);
 
   {
     // this warp's 48 partial sums go to its own slot [host frame][chunk][target warp][48]: plain coalesced stores, summed
@@ -1304,6 +1310,7 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
     if (!(lane & 1)) dst[off + 1] = tot1;
   }
   __syncthreads();
+  stamp(36);
 
   // reference block of H_pd:  sum_t B_t^T p_t  with p_t = -(target block t)   (J_ref = U B)
   for (int i = threadIdx.x; i < lpb * 8; i += blockDim.x) {
@@ -1326,6 +1333,7 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
     hpd_s[ls * D + 8 * f + j] = refv;
   }
   __syncthreads();
+  stamp(37);
 
   // finalise the chunk's landmarks (hessian_block_evaluation.hpp:213-227)
   for (int ls = threadIdx.x; ls < lpb; ls += blockDim.x) {
@@ -1358,6 +1366,7 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
     bd_s[ls] = sb;
   }
   __syncthreads();
+  stamp(38);
   const int D4 = D / 4;
   for (int i = threadIdx.x; i < lpb * D4; i += blockDim.x) {
     const int ls = i / D4;
@@ -1371,6 +1380,7 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
       reinterpret_cast<float4*>(w.hpd + (size_t)gl * w.hpd_stride)[i - ls * D4] =
           reinterpret_cast<const float4*>(hpd_s + ls * D)[i - ls * D4];
   }
+  stamp(39);
   // K4 second half for this chunk: S = sum_l s_l H_pd_l H_pd_l^T (upper triangle as 4x4 tiles), b = sum_l s_l b_d_l H_pd_l
   {
     const int T4 = D / 4, ntri = T4 * (T4 + 1) / 2, nout = ntri * 16 + D;
@@ -1402,12 +1412,14 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
       dst[2] = make_float4(a[8], a[9], a[10], a[11]);
       dst[3] = make_float4(a[12], a[13], a[14], a[15]);
     }
+    stamp(40);
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
       float b = 0.f;
       for (int ls = 0; ls < lpb; ++ls) b += bd_s[ls] * hpd_s[ls * D + c];
       part[ntri * 16 + c] = b;
     }
   }
+  stamp(41);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2047,8 +2059,8 @@ __global__ void __launch_bounds__(1024) k_reduce_system(const __grid_constant__ 
   const int NB = N * (N + 1) / 2;
   const bool st0 = g_stamps_on && threadIdx.x == 0 && blockIdx.x == 0;
   const bool st1 = g_stamps_on && threadIdx.x == 0 && (int)blockIdx.x == NB;
-  if (st0) g_stamps[30] = clock64();
-  if (st1) g_stamps[40] = clock64();
+  if (st0) g_stamps[54] = clock64();
+  if (st1) g_stamps[59] = clock64();
   if ((int)blockIdx.x < NB) {
     // ---- assemble block (bi <= bj), cf. k_assemble ---------------------------------------------------------------------
     int bi = 0, rem = blockIdx.x;
@@ -2111,7 +2123,7 @@ __global__ void __launch_bounds__(1024) k_reduce_system(const __grid_constant__ 
         }
       }
       __syncwarp();
-      if (st0) g_stamps[31] = clock64();
+      if (st0) g_stamps[55] = clock64();
       if (with_system) {
         const PairAssemble& pa = w.pairs_asm[r * PBA_MAXF + t];
 #pragma unroll
@@ -2153,9 +2165,9 @@ __global__ void __launch_bounds__(1024) k_reduce_system(const __grid_constant__ 
         }
       }
     }
-    if (st0) g_stamps[32] = clock64();
+    if (st0) g_stamps[56] = clock64();
     __syncthreads();
-    if (st0) g_stamps[33] = clock64();
+    if (st0) g_stamps[57] = clock64();
     if (!with_system) return;
     for (int o = threadIdx.x; o < 64; o += blockDim.x) {
       const int oi = o >> 3, oj = o & 7;
@@ -2175,7 +2187,7 @@ __global__ void __launch_bounds__(1024) k_reduce_system(const __grid_constant__ 
         }
       }
     }
-    if (st0) g_stamps[34] = clock64();
+    if (st0) g_stamps[58] = clock64();
     return;
   }
   if (!with_system) return;
@@ -2210,10 +2222,10 @@ __global__ void __launch_bounds__(1024) k_reduce_system(const __grid_constant__ 
     for (; q < rows; q += 32) a0 += P(q);
     acc += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
   }
-  if (st1) g_stamps[41] = clock64();
+  if (st1) g_stamps[60] = clock64();
   red[g][oo] = acc;
   __syncthreads();
-  if (st1) g_stamps[42] = clock64();
+  if (st1) g_stamps[61] = clock64();
   if (g == 0 && o < nout) {
     double sum = 0;
 #pragma unroll
@@ -2234,7 +2246,7 @@ __global__ void __launch_bounds__(1024) k_reduce_system(const __grid_constant__ 
       }
     }
   }
-  if (st1) g_stamps[43] = clock64();
+  if (st1) g_stamps[62] = clock64();
 }
 
 // second stage of the Schur reduction + symmetrisation of both systems (hessian_block_evaluation.hpp:147-163):

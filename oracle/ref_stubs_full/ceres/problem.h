@@ -1,0 +1,3 @@
+// STAND-IN -- this is NOT Ceres (see jet.h next to this file).
+#pragma once
+#include "jet.h"

@@ -1,0 +1,5 @@
+// STAND-IN for the protobuf-generated header (see frame.pb.h).
+#pragma once
+namespace dsopp::track::proto {
+class Landmark {};
+}  // namespace dsopp::track::proto

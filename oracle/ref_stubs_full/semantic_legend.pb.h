@@ -1,0 +1,5 @@
+// STAND-IN for the protobuf-generated header (see frame.pb.h).
+#pragma once
+namespace dsopp::sensors::calibration::proto {
+class SemanticLegend {};
+}  // namespace dsopp::sensors::calibration::proto
