@@ -381,6 +381,8 @@ def run_ours(args):
         h.set_option("speculative_multi_gpu", args.speculative_multi_gpu)
     if args.fused_prefetch >= 0:
         h.set_option("fused_prefetch", args.fused_prefetch)
+    if args.fused_epilogue >= 0:
+        h.set_option("fused_epilogue", args.fused_epilogue)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -833,6 +835,7 @@ def main():
                          "(default: mailbox kernel from 4 GPUs on)")
     ap.add_argument("--peer-fused", type=int, default=-1, help="N > 1 with --peer-exchange: 1 = exchange fused into the producers / consumers (default), 0 = stand-alone mailbox kernel")
     ap.add_argument("--fused-prefetch", type=int, default=-1, help="tuning A/B: 0/1 L1 prefetch of the next taps in the fused linearise")
+    ap.add_argument("--fused-epilogue", type=int, default=-1, help="A/B: 1 = second-generation epilogue of the fused sweep (default), 0 = the first generation's")
     ap.add_argument("--host-lm", action="store_true", help="drive the LM loop from the C++ host adapter instead of dpba_solve_lm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

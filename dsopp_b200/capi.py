@@ -122,6 +122,8 @@ SIGNATURES = {
     "dpba_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "dpba_launch_count": (C.c_int64, []),
     "dpba_debug_stamps": (C.c_int, [_I, _P]),
+    "dpba_debug_cta_times": (C.c_int, [_P, _I]),
+    "dpba_debug_kernel_times": (C.c_int, [_P]),
     "dpba_profile_enable": (C.c_int, [_P, _I]),
     "dpba_profile_read": (C.c_int, [_P, _P, _P]),
     "dpba_comm_unique_id": (C.c_int, [_P]),

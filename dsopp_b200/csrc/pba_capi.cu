@@ -2112,6 +2112,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "fused_epilogue")) {  // process-wide A/B switch: 1 = second-generation epilogue of the fused sweep
+    pba::set_fused_epilogue((int)value);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
   if (!strcmp(name, "fused_prefetch")) {  // process-wide A/B switch
     pba::set_fused_prefetch(value != 0);
     h->lm_graph_key.clear();
@@ -2156,6 +2161,18 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
 }
 
 int64_t dpba_launch_count(void) { return (int64_t)pba::launch_count(); }
+
+int dpba_debug_kernel_times(int64_t out[32]) {
+  cudaDeviceSynchronize();
+  pba::debug_kernel_times(reinterpret_cast<long long*>(out));
+  return DPBA_SUCCESS;
+}
+
+int dpba_debug_cta_times(int64_t* out, int32_t n) {
+  cudaDeviceSynchronize();
+  pba::debug_cta_times(reinterpret_cast<long long*>(out), n);
+  return DPBA_SUCCESS;
+}
 
 int dpba_debug_stamps(int32_t enable, int64_t out[64]) {
   long long tmp[64];

@@ -167,6 +167,8 @@ FusedShape launch_linearize_fused(const WindowDev& w, float sigma, int huber, in
                                   const double* fold_step = nullptr);
 int fused_version();
 void debug_stamps(int enable, long long out[64]);
+void debug_cta_times(long long* out, int n);
+void debug_kernel_times(long long out[32]);
 void launch_linearize_from_materialized(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
 int launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,
@@ -199,6 +201,7 @@ void set_fused_min_blocks(int b);
 void set_fused_version(int v);
 void set_pdl(bool on);
 void set_fused_prefetch(bool on);
+void set_fused_epilogue(int v);
 
 // ---- peer-memory exchange (peer_exchange.cu): one-shot all-reduce over NVLink mailboxes -------------------------------
 constexpr int PEER_MAXW = 8;   // ranks of one NVSwitch domain

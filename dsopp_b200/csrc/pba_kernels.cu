@@ -108,6 +108,40 @@ __device__ __forceinline__ bool lm_skip(const LmCtl* ctl, int mode) {
 // clock64() stamps of the single-CTA LM kernels (diagnostics: dpba_debug_stamps); written by thread 0 only
 __device__ long long g_stamps[64];
 __device__ int g_stamps_on = 0;
+// per-CTA timeline of the fused sweep (diagnostics: dpba_debug_cta_times): %globaltimer (ns) at entry, end of the sweep
+// proper, end of the CTA, and the SM it ran on -- written by thread 0 of every CTA while the stamps are on
+__device__ long long g_cta_times[1024 * 4];
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// entry (block 0) and exit (latest block) of the LM-loop kernels in %globaltimer ns (diagnostics: dpba_debug_cta_times reads
+// them behind the CTA table): where an iteration's time goes BETWEEN the kernels
+__device__ unsigned long long g_kst[32];
+struct KStamp {
+  int id;
+  __device__ __forceinline__ explicit KStamp(int i) : id(i) {
+    if (g_stamps_on && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_kst[2 * id] = (unsigned long long)global_ns();
+  }
+  __device__ __forceinline__ ~KStamp() {
+    if (g_stamps_on && threadIdx.x == 0) atomicMax(&g_kst[2 * id + 1], (unsigned long long)global_ns());
+  }
+};
+__device__ __forceinline__ void cta_stamp(int slot) {
+  if (g_stamps_on && threadIdx.x == 0) {
+    const int c = blockIdx.y * gridDim.x + blockIdx.x;
+    if (c < 1024) {
+      if (slot == 3) {
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        g_cta_times[c * 4 + 3] = sm;
+      } else {
+        g_cta_times[c * 4 + slot] = global_ns();
+      }
+    }
+  }
+}
 __device__ __forceinline__ void stamp(int i) {
   if (g_stamps_on && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_stamps[i] = clock64();
 }
@@ -988,7 +1022,12 @@ template <bool FEJ, int NWMAX, int MINB>
 __global__ void __launch_bounds__(32 * NWMAX, MINB)
     k_linearize_fused2(const __grid_constant__ WindowDev w, float sigma, int huber, int for_marg, int lpb,
                        float* __restrict__ core_part, float* __restrict__ schur_part, const LmCtl* __restrict__ ctl,
-                       int ctl_mode, int fold, const double* __restrict__ step_pose, double2* __restrict__ norms) {
+                       int ctl_mode, int fold, const double* __restrict__ step_pose, double2* __restrict__ norms, int epi) {
+  KStamp kstamp_(0);
+  // epi = 1 (round 2, default): second-generation epilogue -- the reference block of H_pd is formed per target inside the
+  // sweep (B_t^T p_t from the registers that hold p_t) and only summed over the targets afterwards, the landmark selection is
+  // staged in shared memory once, and the H_pd row store, the chunk's rank-k update and its b vector run side by side in one
+  // phase (two block barriers after the sweep instead of four).  epi = 0: the first generation's epilogue (A/B).
   // fold (device LM, speculative sequence): this sweep evaluates the trial state of step k + 1, so it first closes
   // step k for ITS landmarks and residuals -- acceptStep() / rejectStep() incl. changeResidualStatuses (problem.hpp:20-35,
   // 377-384,395-399; k_accept_landmarks) -- and then back-substitutes the new pose step into their inverse depths
@@ -1083,11 +1122,15 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
   float* bd_s = hdd_s + lpb;                                         // [lpb] weight * b_d
   float* hdd_w = bd_s + lpb;                                         // [lpb][nwarps] per-target H_dd terms
   float* bd_w = hdd_w + lpb * nwarps;                                // [lpb][nwarps] per-target b_d terms
+  float* ref_w = bd_w + lpb * nwarps;                                // epi: [nwarps][lpb][8] per-target B_t^T p_t
+  int* fl_s = reinterpret_cast<int*>(ref_w + (size_t)nwarps * lpb * 8);  // epi: [lpb] landmark flags (-1: past the end)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = warp + (warp >= f);
   const int lm_base = lm_index(w, f, 0);
 
   stamp(30);
+  cta_stamp(0);
+  cta_stamp(3);
   for (int i = threadIdx.x; i < lpb * (D + 2 + 2 * nwarps); i += blockDim.x) hpd_s[i] = 0.f;
   reinterpret_cast<float4*>(&pcs[warp])[lane] = reinterpret_cast<const float4*>(&w.pairs[f * PBA_MAXF + t])[lane];
   __syncthreads();
@@ -1284,6 +1327,26 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
       hdd_w[ls * nwarps + warp] = hdd;
       bd_w[ls * nwarps + warp] = bd;
     }
+    {
+      if (epi) {  // unconditional: an unselected landmark has p_t = 0 (its weight is zero), and the slots are not pre-zeroed
+        if (warp == 0) fl_s[ls] = inb ? flags : -1;  // the finalise phase reads the flags from here, not from HBM
+        // this target's share of the reference block: B_t^T p_t, B = blockdiag(Adj, 1, s')  (J_ref = U B)
+        const float* adj = FEJ ? pc.adj0 : pc.adj;
+        float rc[8];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          float a = 0.f;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) a += adj[k * 6 + j] * pt[k];
+          rc[j] = a;
+        }
+        rc[6] = pt[6];
+        rc[7] = (FEJ ? pc.s0 : pc.s) * pt[7];
+        float4* rp = reinterpret_cast<float4*>(ref_w + ((size_t)warp * lpb + ls) * 8);
+        rp[0] = make_float4(rc[0], rc[1], rc[2], rc[3]);
+        rp[1] = make_float4(rc[4], rc[5], rc[6], rc[7]);
+      }
+    }
     // warp-wide transpose-reduce of the group's 44 sums + (energy, n): 24+12+6+3+2 = 47 shuffles; every lane ends up with
     // (at most) two entries of the 48-vector and adds them to its running totals
     {
@@ -1311,6 +1374,107 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
   }
   __syncthreads();
   stamp(36);
+  cta_stamp(1);
+
+  if (epi) {
+    // ---- phase A: finalise the chunk's landmarks (hessian_block_evaluation.hpp:213-227) and sum the reference block ------
+    // hdd_s[ls] = 1 / H_dd (0: ill conditioned), bd_s[ls] = b_d / H_dd; a NEGATIVE hdd_s marks a landmark that is not
+    // selected at all (its H_pd row is not stored)
+    for (int ls = threadIdx.x; ls < lpb; ls += blockDim.x) {
+      const int l = l0 + ls;
+      float sc = -1.f, sb = 0.f;
+      const int fl = fl_s[ls];
+      if (fl >= 0) {
+        const int gl = lm_base + l;
+        const bool skip = (fl & LM_MARG) && !(fl & LM_TO_MARG);
+        const bool sel = !skip && (for_marg ? (fl & LM_TO_MARG) != 0 : (fl & LM_MARG) == 0);
+        if (sel) {
+          float hdd = 0.f, bd = 0.f;
+          for (int wi = 0; wi < nwarps; ++wi) {
+            hdd += hdd_w[ls * nwarps + wi];
+            bd += bd_w[ls * nwarps + wi];
+          }
+          w.b_d[gl] = bd;
+          sc = 0.f;
+          if (hdd > 1e-15f) {
+            if (for_marg && w.fixed[f]) hdd += 1e8f;  // kScaleNullspaceRegularizer
+            sc = 1.f / hdd;
+            sb = sc * bd;
+            w.inv_hdd[gl] = sc;
+            w.flags[gl] = (uint8_t)(fl & ~LM_ILL);
+          } else {
+            w.flags[gl] = (uint8_t)(fl | LM_ILL);
+          }
+        }
+      }
+      hdd_s[ls] = sc;
+      bd_s[ls] = sb;
+    }
+    for (int i = threadIdx.x; i < lpb * 8; i += blockDim.x) {
+      float refv = 0.f;
+      for (int wi = 0; wi < nwarps; ++wi) refv += ref_w[(size_t)wi * lpb * 8 + i];  // consecutive lanes, consecutive words
+      hpd_s[(i >> 3) * D + 8 * f + (i & 7)] = refv;
+    }
+    __syncthreads();
+    stamp(38);
+    // ---- phase B: H_pd rows to HBM, the chunk's rank-k update, its b vector -- no barrier between them ---------------------
+    const int D4 = D / 4;
+    for (int i = threadIdx.x; i < lpb * D4; i += blockDim.x) {
+      const int ls = i / D4;
+      if (l0 + ls >= M) break;
+      if (hdd_s[ls] >= 0.f)
+        reinterpret_cast<float4*>(w.hpd + (size_t)(lm_base + l0 + ls) * w.hpd_stride)[i - ls * D4] =
+            reinterpret_cast<const float4*>(hpd_s + ls * D)[i - ls * D4];
+    }
+    stamp(39);
+    const int T4 = D / 4, ntri = T4 * (T4 + 1) / 2, nout = ntri * 16 + D;
+    float* part = schur_part + ((size_t)f * gridDim.x + blockIdx.x) * nout;
+    // the tiles are dealt from the LAST thread downwards and the b entries from the first thread upwards, so that with
+    // ntri + D <= blockDim.x (N <= 8: 136 + 64 <= 224) nobody does both
+    for (int tile = (int)blockDim.x - 1 - (int)threadIdx.x; tile < ntri; tile += blockDim.x) {
+      int ty = 0, rem = tile;
+      while (rem >= T4 - ty) {
+        rem -= T4 - ty;
+        ++ty;
+      }
+      const int tx = ty + rem;
+      float a[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a[k] = 0.f;
+      const float* qp = hpd_s + 4 * ty;
+      const float* pp = hpd_s + 4 * tx;
+#pragma unroll 4
+      for (int ls = 0; ls < lpb; ++ls) {
+        const float sc = fmaxf(hdd_s[ls], 0.f);
+        const float4 qv = ldf4(qp + ls * D);
+        const float4 pv = ldf4(pp + ls * D);
+        const float qa[4] = {sc * qv.x, sc * qv.y, sc * qv.z, sc * qv.w};
+        const float pa2[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[i * 4 + j] += qa[i] * pa2[j];
+      }
+      float4* dst = reinterpret_cast<float4*>(part + tile * 16);
+      dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+      dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+      dst[2] = make_float4(a[8], a[9], a[10], a[11]);
+      dst[3] = make_float4(a[12], a[13], a[14], a[15]);
+    }
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;  // four independent chains (lpb is a multiple of 32)
+      for (int ls = 0; ls < lpb; ls += 4) {
+        b0 += bd_s[ls] * hpd_s[ls * D + c];
+        b1 += bd_s[ls + 1] * hpd_s[(ls + 1) * D + c];
+        b2 += bd_s[ls + 2] * hpd_s[(ls + 2) * D + c];
+        b3 += bd_s[ls + 3] * hpd_s[(ls + 3) * D + c];
+      }
+      part[ntri * 16 + c] = (b0 + b1) + (b2 + b3);
+    }
+    stamp(41);
+    cta_stamp(2);
+    return;
+  }
 
   // reference block of H_pd:  sum_t B_t^T p_t  with p_t = -(target block t)   (J_ref = U B)
   for (int i = threadIdx.x; i < lpb * 8; i += blockDim.x) {
@@ -1848,6 +2012,7 @@ __global__ void __launch_bounds__(256) k_schur_mma(const __grid_constant__ Windo
 __global__ void __launch_bounds__(256) k_core_reduce(const __grid_constant__ WindowDev w,
                                                      const float* __restrict__ core_part, int lpb, int chunk_stride,
                                                      double* __restrict__ core, const LmCtl* __restrict__ ctl) {
+  KStamp kstamp_(1);
   if (lm_skip(ctl, 2)) return;
   __shared__ double red[4][PBA_CORE];
   const int N = w.n_frames;
@@ -1884,6 +2049,7 @@ constexpr int ASM_W = 264;  // doubles of shared memory per warp: C, B, T1, out 
 __global__ void __launch_bounds__(512) k_assemble(const __grid_constant__ WindowDev w, int fej,
                                                   const double* __restrict__ core, double* __restrict__ Hp,
                                                   double* __restrict__ bp, const LmCtl* __restrict__ ctl, int peer_push) {
+  KStamp kstamp_(4);
   if (lm_skip(ctl, 2)) return;
   const unsigned epoch = peer_push ? peer_epoch() : 0u;
   extern __shared__ double asm_sm[];
@@ -1977,6 +2143,7 @@ __global__ void __launch_bounds__(512) k_assemble(const __grid_constant__ Window
 __global__ void __launch_bounds__(1024) k_finish_fused(const __grid_constant__ WindowDev w, int lpb, int chunks,
                                                        const float* __restrict__ part, double* __restrict__ Hs,
                                                        double* __restrict__ bs, const LmCtl* __restrict__ ctl, int peer_push) {
+  KStamp kstamp_(3);
   if (lm_skip(ctl, 2)) return;
   const unsigned epoch = peer_push ? peer_epoch() : 0u;
   __shared__ double red[32][33];
@@ -2286,6 +2453,7 @@ __global__ void k_finish_system(int D, double* __restrict__ Hp, double* __restri
 __global__ void __launch_bounds__(256) k_back_substitute(const __grid_constant__ WindowDev w,
                                                          const double* __restrict__ step_pose, float inv_lambda,
                                                          const LmCtl* __restrict__ ctl, double* __restrict__ norms /* per-CTA (state, step) partials or null */) {
+  KStamp kstamp_(6);
   if (lm_skip(ctl, 1)) return;
   if (ctl) inv_lambda = (float)(1.0 / (1.0 + ctl->lambda));
   __shared__ float sp[PBA_MAXF * 8];
@@ -2345,6 +2513,7 @@ __global__ void __launch_bounds__(256) k_back_substitute(const __grid_constant__
 __global__ void __launch_bounds__(256) k_accept_landmarks(const __grid_constant__ WindowDev w, int accept,
                                                           double* __restrict__ scal, const LmCtl* __restrict__ ctl,
                                                           int with_statuses) {
+  KStamp kstamp_(8);
   if (ctl) {  // device LM: k_lm_energy decided (and already closed the iteration's bookkeeping)
     if (!ctl->apply) return;
     accept = ctl->accept;
@@ -2709,6 +2878,7 @@ __device__ void make_proj(const SE3d& T, const double* ir, const double* it, flo
 
 __global__ void __launch_bounds__(64) k_pair_setup(const FrameParams* __restrict__ fr, int N,
                                                     PairConst* __restrict__ pairs, PairAssemble* __restrict__ pasm) {
+  KStamp kstamp_(7);
   // one CTA per reference frame r.  phase 1 (thread per frame): exp(+eps) of r, exp(-eps) and T_lin^-1 of every
   // target; phase 2 (thread per target): the pair's constants, staged in shared memory; phase 3: coalesced write.
   __shared__ SE3d s_et[PBA_MAXF], s_ti[PBA_MAXF];
@@ -3046,6 +3216,7 @@ __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDe
                                                    const double* bmarg, int kind, const double2* __restrict__ e_part,
                                                    int n_e, const double2* __restrict__ n_part, int n_n, int from_core,
                                                    int peer_collect_mode, int peer_scal_off) {
+  KStamp kstamp_(2);
   if (peer_collect_mode && !(kind == pba::LM_ENERGY_TRIAL && ctl->done)) {
     // fused exchange: the scalars of every rank (one arrival each), summed in rank order
     const unsigned epoch = peer_epoch();
@@ -3301,6 +3472,7 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
                                                  const double* __restrict__ bs, const double* __restrict__ Hmarg,
                                                  const double* __restrict__ bmarg, double* __restrict__ step_dev,
                                                  int peer_expected, double* sys_out, int n_sys) {
+  KStamp kstamp_(5);
   if (peer_expected && !ctl->done) {
     // fused exchange: [H_pp | b_p | H_s | b_s] of every rank, summed in rank order into the block lm_step_body reads
     const unsigned epoch = peer_epoch();
@@ -3648,6 +3820,8 @@ void set_pdl(bool on) { g_pdl = on; }
 int g_fused_minb = 3;  // resident CTAs per SM the fused linearise is compiled for (N <= 9): 4 -> 64 registers, 3 -> 80
 void set_fused_min_blocks(int b) { g_fused_minb = b <= 3 ? 3 : 4; }
 
+int g_fused_epilogue = 1;  // second-generation epilogue of k_linearize_fused2 (option "fused_epilogue", 0 = the first generation's)
+void set_fused_epilogue(int v) { g_fused_epilogue = v != 0; }
 bool g_fused_prefetch = false;  // L1 prefetch of the next group's image taps: measured 42.6 us against 39.1 us without (issue-bound kernel), kept as an A/B switch (option "fused_prefetch")
 void set_fused_prefetch(bool on) { g_fused_prefetch = on; }
 
@@ -3677,7 +3851,7 @@ static void launch_fused_t(const WindowDev& w, float sigma, int huber, int fej, 
 template <int NWMAX, int MINB>
 static void launch_fused2_t(const WindowDev& w, float sigma, int huber, int fej, int for_marg, int lpb, dim3 g, int threads,
                             size_t smem, float* core_part, float* schur_part, cudaStream_t s, const LmCtl* ctl, int ctl_mode,
-                            int fold, const double* step_pose, double2* norms) {
+                            int fold, const double* step_pose, double2* norms, int epi) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_linearize_fused2<true, NWMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -3685,8 +3859,8 @@ static void launch_fused2_t(const WindowDev& w, float sigma, int huber, int fej,
     attr = true;
   }
   ++g_launches;
-  if (fej) launch_pdl(k_linearize_fused2<true, NWMAX, MINB>, g, dim3(threads), smem, s, w, sigma, huber, for_marg, lpb, core_part, schur_part, ctl, ctl_mode, fold, step_pose, norms);
-  else launch_pdl(k_linearize_fused2<false, NWMAX, MINB>, g, dim3(threads), smem, s, w, sigma, huber, for_marg, lpb, core_part, schur_part, ctl, ctl_mode, fold, step_pose, norms);
+  if (fej) launch_pdl(k_linearize_fused2<true, NWMAX, MINB>, g, dim3(threads), smem, s, w, sigma, huber, for_marg, lpb, core_part, schur_part, ctl, ctl_mode, fold, step_pose, norms, epi);
+  else launch_pdl(k_linearize_fused2<false, NWMAX, MINB>, g, dim3(threads), smem, s, w, sigma, huber, for_marg, lpb, core_part, schur_part, ctl, ctl_mode, fold, step_pose, norms, epi);
 }
 
 // second generation: `lpb` is a multiple of 32 (a lane owns a landmark); 2 CTAs per SM are resident (<= 144 registers)
@@ -3708,20 +3882,24 @@ static FusedShape launch_linearize_fused2(const WindowDev& w, float sigma, int h
       lpb = cand;
     }
   }
-  const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + ((size_t)lpb * (D + 2 + 2 * (N - 1)) + 3) * sizeof(float);
+  const int epi = g_fused_epilogue;
+  const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + ((size_t)lpb * (D + 2 + 2 * (N - 1)) + 3) * sizeof(float) +
+                      (epi ? (size_t)lpb * (8 * (N - 1) + 1) * sizeof(float) : 0);
   dim3 g((m + lpb - 1) / lpb, N);
   const int threads = 32 * (N - 1);
   const int fold = fold_step != nullptr && ctl != nullptr;
   double2* norms = reinterpret_cast<double2*>(rb.n_part);
-  if (N <= 8) launch_fused2_t<7, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms);
-  else if (N <= 9) launch_fused2_t<8, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms);
-  else launch_fused2_t<15, 1>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms);
+  if (N <= 8) launch_fused2_t<7, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms, epi);
+  else if (N <= 9) launch_fused2_t<8, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms, epi);
+  else launch_fused2_t<15, 1>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms, epi);
   shape.lpb = lpb;
   shape.chunks = (int)g.x;
   return shape;
 }
 
 int fused_version() { return g_fused_version; }
+void debug_cta_times(long long* out, int n) { cudaMemcpyFromSymbol(out, g_cta_times, sizeof(long long) * (size_t)(n < 4096 ? n : 4096)); }
+void debug_kernel_times(long long out[32]) { cudaMemcpyFromSymbol(out, g_kst, sizeof(long long) * 32); }
 void debug_stamps(int enable, long long out[64]) {
   cudaMemcpyToSymbol(g_stamps_on, &enable, sizeof(int));
   if (out) cudaMemcpyFromSymbol(out, g_stamps, 64 * sizeof(long long));

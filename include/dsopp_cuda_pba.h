@@ -301,7 +301,9 @@ int dpba_create_reference_depth_maps(dpba_handle* h, int32_t n_levels, double id
  * idepths, statuses and energy are unchanged, the per-landmark hpd / b_d / inv_hdd left behind are those of the final
  * state (the reference's are one accepted step older; its uncertainty pass recomputes them).  "speculative_multi_gpu"
  * (default 1): the same with world_size > 1, the pair energies travelling in the scalar slots behind the system so that
- * ONE allreduce per iteration carries both.  "fused_prefetch" (default 0): L1 prefetch A/B switch.  "fused_min_blocks"
+ * ONE allreduce per iteration carries both.  "fused_epilogue" (default 1, process-wide): second-generation epilogue of
+ * the fused sweep (reference block of H_pd formed per target inside the sweep, two block barriers instead of four); 0 selects
+ * the first generation's.  "fused_prefetch" (default 0): L1 prefetch A/B switch.  "fused_min_blocks"
  * (3 or 4, process-wide): resident CTAs per SM the fused linearise is built for.  "schur_tensor_cores" (default 1, process-wide): the Schur-complement SYRK runs as
  * 3xTF32 mma.sync; 0 selects the fp32 FFMA kernel.  "peer_exchange" (default 0, needs dpba_peer_attach): the sum over
  * ranks runs as the library's own NVLink mailbox kernel instead of ncclAllReduce.  "device_quantile" (default 0):
@@ -316,6 +318,13 @@ int64_t dpba_launch_count(void);
  * system fill, the block steps of the LDL^T, back substitution, pair constants) during the LAST launch; enable = 1 arms
  * the stamping (process-wide), out (may be NULL) receives the 64 stamps of the last launch. */
 int dpba_debug_stamps(int32_t enable, int64_t out[64]);
+/* Diagnostics: per-CTA timeline of the last fused sweep taken while the stamps were on -- out[4 c + {0,1,2,3}] = entry, end of
+ * the sweep proper, end of the CTA (%globaltimer, ns) and the SM id of CTA c = blockIdx.y * gridDim.x + blockIdx.x; n <= 4096. */
+int dpba_debug_cta_times(int64_t* out, int32_t n);
+/* Diagnostics: out[2 k], out[2 k + 1] = entry of block 0 and exit of the latest block (%globaltimer, ns) of the last launch of
+ * LM-loop kernel k (0 fused sweep, 1 core reduce, 2 energy decision, 3 Schur reduce, 4 block assembly, 5 LM step,
+ * 6 back-substitution, 7 pair constants, 8 landmark accept) taken while the stamps were on. */
+int dpba_debug_kernel_times(int64_t out[32]);
 /* Per-kernel device timing with CUDA events recorded on the handle's stream around each launch.
  * kinds: 0 fused linearise sweep, 1 Schur SYRK (three-pass path), 2 residual-only sweep, 3 materialising sweep,
  *        4 assemble+symmetrise (three-pass path), 5 back-substitution, 6 per-pair constants,

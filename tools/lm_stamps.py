@@ -28,3 +28,32 @@ for i in sorted(names):
     print(f"{names[i]:28s} {t[i]:8d} cycles  (+{t[i] - prev})")
     prev = t[i]
 h.close()
+
+# per-CTA timeline of the last fused sweep (dpba_debug_cta_times): how long the CTAs take and how they share the SMs
+ct = np.zeros(4096, np.int64)
+lib.dpba_debug_cta_times(ct.ctypes.data, 4096)
+ct = ct.reshape(1024, 4)
+ct = ct[ct[:, 0] > 0]
+if len(ct):
+    t0 = ct[:, 0].min()
+    ent, swp, end, sm = (ct[:, 0] - t0) / 1e3, (ct[:, 1] - ct[:, 0]) / 1e3, (ct[:, 2] - ct[:, 0]) / 1e3, ct[:, 3]
+    per_sm = np.bincount(sm.astype(int))
+    print(f"fused sweep, {len(ct)} CTAs: entry spread {ent.max():.1f} us, kernel span {(ct[:, 2].max() - t0) / 1e3:.1f} us; CTA time "
+          f"min/median/max {end.min():.1f}/{np.median(end):.1f}/{end.max():.1f} us, sweep part {swp.min():.1f}/{np.median(swp):.1f}/{swp.max():.1f} us; "
+          f"SMs with 1/2/3+ CTAs: {(per_sm == 1).sum()}/{(per_sm == 2).sum()}/{(per_sm > 2).sum()}")
+    solo = np.isin(sm, np.nonzero(per_sm == 1)[0])
+    if solo.any() and (~solo).any():
+        print(f"   CTAs alone on their SM: median {np.median(end[solo]):.1f} us (sweep {np.median(swp[solo]):.1f}); sharing an SM: median {np.median(end[~solo]):.1f} us (sweep {np.median(swp[~solo]):.1f})")
+    late = np.argsort(ct[:, 2])[-5:]
+    print("   last five CTAs to finish: " + ", ".join(f"entry {ent[i]:.1f} + {end[i]:.1f} us (sweep {swp[i]:.1f}) on SM {int(sm[i])}" for i in late))
+
+# entry / exit of the LM-loop kernels' last launches (dpba_debug_kernel_times): the gaps BETWEEN the kernels of an iteration
+kt = np.zeros(32, np.int64)
+lib.dpba_debug_kernel_times(kt.ctypes.data)
+knames = ["fused sweep", "core reduce", "energy decision", "schur reduce", "block assembly", "lm step", "back-substitution", "pair constants", "landmark accept"]
+rows = sorted((kt[2 * i], kt[2 * i + 1], knames[i]) for i in range(len(knames)) if kt[2 * i] > 0)
+if rows:
+    t0 = rows[0][0]
+    print("last launches of the LM-loop kernels, us from the first entry (entry -> exit):")
+    for a, b, nm in rows:
+        print(f"   {nm:18s} {(a - t0) / 1e3:8.1f} -> {(b - t0) / 1e3:8.1f}   ({(b - a) / 1e3:5.1f} us)")
