@@ -9,8 +9,9 @@
 // TEST INFRASTRUCTURE: this is (a) the second, independent restatement that the NumPy oracle is cross-checked
 // against, (b) the float32 oracle whose ROI / depth / mask predicates use the same operation order as the CUDA
 // kernels (build with -ffp-contract=off), and (c) the CPU baseline that bench.py times ("port": the reference
-// binary cannot be built here -- Eigen/Sophus/TBB are absent).  PARITY UNPINNED for raw values (no golden
-// vectors exist in the reference); pinned by the property tests in tests/test_oracle_properties.py.
+// binary cannot be built here -- Eigen/Sophus/TBB are absent).  PARITY PINNED through the NumPy oracle, which equals the
+// reference's own code compiled against stand-in third-party headers (oracle/build_ref_pba.py, tests/test_reference_pba.py)
+// and which this file equals element-wise at 1e-9 (tests/test_cpu_ref_vs_numpy.py).
 // Nothing under dsopp_b200/ links or includes this file.
 //
 // Scalar = double is the reference default (cmake/options.cmake:7), float is the CI build.  Per-pair constants

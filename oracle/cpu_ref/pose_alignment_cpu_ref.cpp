@@ -1,6 +1,6 @@
 // CPU restatement (plain C++17, double, SERIAL like the reference) of DSOPP's coarse-tracker direct image alignment.
 // TEST INFRASTRUCTURE / TIMED CPU BASELINE ONLY (see oracle/pose_alignment_oracle.py for the NumPy twin and the
-// "parity unpinned" statement).  Follows, paths relative to /root/reference/src/:
+// statement of how it is pinned against the reference's own PoseAlignerProblem).  Follows, paths relative to /root/reference/src/:
 //   PoseAlignerProblem                energy/problems/src/eigen_pose_alignment.cpp:28-241
 //   EigenPoseAlignment::solve         energy/problems/src/eigen_pose_alignment.cpp:275-329
 //   levenberg_marquardt_algorithm     energy/problems/include/energy/levenberg_marquardt_algorithm/levenberg_marquardt_algorithm.hpp:77-128

@@ -3,18 +3,22 @@
 TEST INFRASTRUCTURE ONLY.  Nothing under dsopp_b200/ may import this module; only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use oracle/.
 
-PARITY UNPINNED for raw values: the reference (RoadlyInc/DSOPP @ a4af2aa) ships no golden
-vectors for this path and its fixture (test/test_data/track30seconds) is not in the checkout,
-and the reference itself cannot be compiled here (Eigen/Sophus/TBB/glog absent).  This file is
-therefore a from-scratch restatement of the reference arithmetic, pinned by re-expressing the
-reference's own *property* tests (tests/test_oracle_properties.py):
+PARITY PINNED against the reference itself (RoadlyInc/DSOPP @ a4af2aa): the reference's own bundle adjustment --
+LocalFrame, PixelMap, the pinhole ArrayReprojector, evaluateJacobians, firstEstimateJacobians_, the Hessian block
+evaluation, the Problem class with its priors, updateMarginalizedLinearSystem, the LM driver, NormalLinearSystem --
+is compiled from its sources, where they lie, against minimal stand-ins of the absent third-party libraries
+(oracle/build_ref_pba.py), and every array it leaves behind on ten scenarios equals what this file computes: flags and
+statuses exactly, values to 1e-9 of the array maximum (tests/test_reference_pba.py; golden vectors of the reference's
+outputs in tests/golden/ref_pba.npz).  updatePointStatuses and relinearizeSystem (photometric_bundle_adjustment.cpp:307-406)
+are part of that build and of the comparison (quantile threshold through the statuses it produces, outlier resets, inlier
+counts, relative baselines).  Independent of that pin the
+reference's own *property* tests are re-expressed in tests/test_oracle_properties.py:
   test_linear_system.cpp (J^T J, Schur and marginalisation identities),
   test_reprojects.cpp (left-perturbation reprojection Jacobians),
   test_analytical_diff.cpp (analytic vs numeric residual Jacobians),
   test_dxdy_accelerated.cpp (gradient definition).
-EXCEPT lm_solve below: the reference's LM driver is one of the two pieces that do compile here from their own source
-(oracle/build_ref.py), and lm_solve reproduces its call sequence, lambda schedule and result exactly on scripted
-problems (tests/test_reference_parts.py, tests/golden/ref_parts.npz).
+lm_solve below additionally reproduces the reference's LM driver call by call on scripted problems
+(oracle/build_ref.py, tests/test_reference_parts.py, tests/golden/ref_parts.npz).
 
 Third-party arithmetic restated from its published closed forms (sources not under
 /root/reference): Sophus @593db475 (SE3::exp, Adj, inverse; tangent = [upsilon; omega]) and

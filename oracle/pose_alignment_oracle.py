@@ -1,8 +1,11 @@
 """CPU oracle (NumPy, float64) of DSOPP's coarse-tracker direct image alignment.
 
-TEST INFRASTRUCTURE ONLY (see oracle/pba_oracle.py).  PARITY UNPINNED for raw values, for the same reasons: the
-reference cannot be built here and ships no golden vectors; pinned by property tests (tests/test_pose_alignment_oracle.py:
-finite-difference Jacobians, recovery of a known relative pose as test_ceres_pose_alignment.cpp:100-139 does).
+TEST INFRASTRUCTURE ONLY (see oracle/pba_oracle.py).  PARITY PINNED against the reference itself: its depth-map LocalFrame
+constructor and its class PoseAlignerProblem are compiled from their sources (oracle/build_ref_pba.py,
+oracle/ref_shims/ref_pose_alignment.cpp) and run under the reference's LM driver; landmark list exactly, energy / pose /
+affine increment / Hessian at 1e-9 (tests/test_reference_pba.py, golden vectors in tests/golden/ref_pba.npz).  Also held by
+property tests (tests/test_pose_alignment_oracle.py: finite-difference Jacobians, recovery of a known relative pose as
+test_ceres_pose_alignment.cpp:100-139 does).
 
 Restates, paths relative to /root/reference/src/:
   PoseAlignerProblem                energy/problems/src/eigen_pose_alignment.cpp:28-241

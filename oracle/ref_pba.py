@@ -49,6 +49,10 @@ def load():
             "refpba_solve": [vp, i, i, d, d, d, i, d, vp, d, vp, vp, vp],
             "refpba_get_intensities": [vp, i, i, vp, vp],
             "refpba_marginalize": [vp, i, d, vp, d],
+            "refpba_update_point_statuses": [vp, i, d],
+            "refpba_relinearize_system": [vp],
+            "refpba_get_relative_baseline": [vp, i, vp],
+            "refpba_get_linearization_point": [vp, i, vp, vp],
         }
         for name, args in sig.items():
             getattr(lib, name).argtypes = args
@@ -207,6 +211,24 @@ class RefWindow:
         self.lib.refpba_get_marginalized(self.h, H.ctypes.data, b.ctypes.data, C.byref(e), C.byref(size))
         return H, b, e.value
 
+    def update_point_statuses(self, min_valid=1, sigma_huber=20.0):
+        """PhotometricBundleAdjustment::updatePointStatuses (photometric_bundle_adjustment.cpp:318-406)."""
+        self.lib.refpba_update_point_statuses(self.h, int(min_valid), float(sigma_huber))
+
+    def relinearize_system(self):
+        """PhotometricBundleAdjustment::relinearizeSystem (photometric_bundle_adjustment.cpp:307-316)."""
+        self.lib.refpba_relinearize_system(self.h)
+
+    def relative_baseline(self, f):
+        out = np.zeros(self.n_lm[f])
+        self.lib.refpba_get_relative_baseline(self.h, f, out.ctypes.data)
+        return out
+
+    def linearization_point(self, f):
+        T, ab = np.zeros((3, 4)), np.zeros(2)
+        self.lib.refpba_get_linearization_point(self.h, f, T.ctypes.data, ab.ctypes.data)
+        return T, ab
+
     def get_intensities(self, f, uv):
         uv = _f64(uv)
         n = len(uv)
@@ -233,3 +255,37 @@ def window_from_synth(win, raw_images):
     for (r, t), st in win.statuses.items():
         rw.set_statuses(r, t, st)
     return rw
+
+
+def pose_alignment_solve(ref_T, ref_exposure, ref_ab, ref_intensity, tgt_T, tgt_exposure, tgt_ab, tgt_intensity, intr,
+                         idepth_sum, weight, tgt_mask=None, sigma_huber=20.0, affine_reg=(1e12, 1e8), max_iterations=50,
+                         trust_region_radius=1e2, function_tolerance=1e-5, parameter_tolerance=1e-5, prior_rotation=None):
+    """The reference's coarse-tracker alignment: the depth-map LocalFrame constructor (local_frame.hpp:350-393), class
+    PoseAlignerProblem (eigen_pose_alignment.cpp:24-242) under levenberg_marquardt_algorithm::solve, set up as
+    EigenPoseAlignment::solve does (:275-329).  Images are raw (H, W) intensities; (idepth_sum, weight) is the depth map.
+    -> dict(energy, n_valid, converged, T_t_r (4x4), ab_eps, H (8x8), uv, idepth, patch of the landmarks it made)"""
+    lib = load()
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    lib.refpa_solve.restype = d
+    lib.refpa_solve.argtypes = [vp, d, vp, vp, vp, d, vp, vp, vp, vp, i, i, vp, vp, d, vp, i, d, d, d, vp, vp, vp, vp, vp, vp, vp, i,
+                                vp, vp, vp]
+    ri, ti = _f64(ref_intensity), _f64(tgt_intensity)
+    Hh, Ww = ri.shape
+    rT, tT = _f64(np.asarray(ref_T)[:3, :4]), _f64(np.asarray(tgt_T)[:3, :4])
+    rab, tab, k, reg = _f64(ref_ab), _f64(tgt_ab), _f64(intr), _f64(affine_reg)
+    ds, wt = _f64(idepth_sum), _f64(weight)
+    m = None if tgt_mask is None else np.ascontiguousarray(tgt_mask, dtype=np.uint8)
+    pr = None if prior_rotation is None else _f64(prior_rotation)
+    cap = Hh * Ww
+    T, ab, H = np.zeros((3, 4)), np.zeros(2), np.zeros((8, 8))
+    uv, idp, pt = np.zeros((cap, 2)), np.zeros(cap), np.zeros(cap)
+    nv, cv, nl = C.c_int32(), C.c_int32(), C.c_int32()
+    e = lib.refpa_solve(rT.ctypes.data, float(ref_exposure), rab.ctypes.data, ri.ctypes.data, tT.ctypes.data,
+                        float(tgt_exposure), tab.ctypes.data, ti.ctypes.data, None if m is None else m.ctypes.data,
+                        k.ctypes.data, Ww, Hh, ds.ctypes.data, wt.ctypes.data, float(sigma_huber), reg.ctypes.data,
+                        int(max_iterations), float(trust_region_radius), float(function_tolerance), float(parameter_tolerance),
+                        None if pr is None else pr.ctypes.data, T.ctypes.data, ab.ctypes.data, H.ctypes.data,
+                        C.addressof(nv), C.addressof(cv), C.addressof(nl), cap, uv.ctypes.data, idp.ctypes.data, pt.ctypes.data)
+    n = nl.value
+    return dict(energy=e, n_valid=nv.value, converged=bool(cv.value), T_t_r=np.vstack([T, [0, 0, 0, 1.0]]), ab_eps=ab, H=H,
+                uv=uv[:n].copy(), idepth=idp[:n].copy(), patch=pt[:n].copy())

@@ -13,6 +13,7 @@
 //   PBA/eigen_photometric_bundle_adjustment_problem.hpp   the Problem class, priors, energies, marginalisation  (a14-a16, a20)
 //   energy/levenberg_marquardt_algorithm/levenberg_marquardt_algorithm.hpp   the LM driver            (a17)
 //   energy/normal_linear_system.hpp + .cpp NormalLinearSystem::solve / reduce_system                (a18)
+//   energy/problems/src/photometric_bundle_adjustment.cpp:299-406   updatePointStatuses, relinearizeSystem    (a19)
 //   sensors/camera_calibration/mask/camera_mask.hpp + .cpp   CameraMask::valid
 // What is NOT the reference's: the third-party libraries under it (Eigen, Sophus, oneTBB, glog, OpenCV, Ceres, the
 // protobuf-generated headers) are absent from this image and are replaced by the minimal stand-ins in
@@ -27,6 +28,14 @@
 #include <memory>
 #include <set>
 #include <vector>
+
+// src/energy/problems/src/photometric_bundle_adjustment.cpp, lines 1-413: the member-function TEMPLATES of
+// PhotometricBundleAdjustment (updatePointStatuses :318-406, relinearizeSystem :307-316) without the explicit instantiations
+// that follow them (those would instantiate the members that need the track subsystem).  The build recipe hands these lines
+// over as a temporary file outside the repository (oracle/build_ref_pba.py).
+#include <glog/logging.h>  // the reference file gets LOG transitively from the real third-party headers
+
+#include REF_PBA_PREFIX
 
 #include "energy/camera_model/pinhole/pinhole_camera.hpp"
 #include "energy/levenberg_marquardt_algorithm/levenberg_marquardt_algorithm.hpp"
@@ -95,7 +104,48 @@ void solve_lm(Window* w, const dsopp::energy::levenberg_marquardt_algorithm::Opt
 
 }  // namespace
 
+// The reference's header names this class, at global scope, as a friend of PhotometricBundleAdjustment
+// (photometric_bundle_adjustment.hpp:15,169 -- its own benchmark uses it to reach the protected members).  Here it runs
+// the protected, non-virtual updatePointStatuses / relinearizeSystem on the window's frames.  The solver class is
+// abstract and its virtual members need the track subsystem, so no object of it is ever constructed: the two functions read
+// nothing but `frames_`, and are called on raw storage in which exactly that member has been constructed.
+class LinearSystemBenchmarkData {
+ public:
+  using PBA = prob::PhotometricBundleAdjustment<Precision, Motion, Model, kP, dsopp::features::PixelMap, true, true, true, 1>;
+  static void run(Window* w, int what, size_t min_valid, Precision sigma) {
+    alignas(PBA) static unsigned char storage[sizeof(PBA)];
+    PBA* p = reinterpret_cast<PBA*>(storage);
+    auto* frames = new (&p->frames_) std::deque<std::unique_ptr<Frame>>();
+    std::swap(*frames, w->frames);
+    if (what == 0)
+      p->updatePointStatuses(min_valid, sigma);
+    else
+      p->relinearizeSystem();
+    std::swap(*frames, w->frames);
+    frames->~deque();
+  }
+};
+
 extern "C" {
+
+// PhotometricBundleAdjustment::updatePointStatuses (photometric_bundle_adjustment.cpp:318-406) and ::relinearizeSystem
+// (:307-316), which EigenPhotometricBundleAdjustment::solve runs after the LM loop (eigen_photometric_bundle_adjustment.cpp:88,99)
+void refpba_update_point_statuses(void* h, int min_valid, double sigma) {
+  LinearSystemBenchmarkData::run(W(h), 0, static_cast<size_t>(min_valid), static_cast<Precision>(sigma));
+}
+void refpba_relinearize_system(void* h) { LinearSystemBenchmarkData::run(W(h), 1, 0, 0); }
+void refpba_get_relative_baseline(void* h, int f, double* out) {
+  const auto& lms = W(h)->frames[static_cast<size_t>(f)]->active_landmarks.at(kSensor);
+  for (size_t i = 0; i < lms.size(); ++i) out[i] = static_cast<double>(lms[i].relative_baseline);
+}
+void refpba_get_linearization_point(void* h, int f, double* T_34, double* ab0) {
+  const Frame& fr = *W(h)->frames[static_cast<size_t>(f)];
+  const auto m = fr.T_w_agent_linearization_point.matrix3x4();
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) T_34[4 * i + j] = static_cast<double>(m(i, j));
+  ab0[0] = static_cast<double>(fr.affine_brightness0(0));
+  ab0[1] = static_cast<double>(fr.affine_brightness0(1));
+}
 
 void* refpba_create() {
   auto* w = new Window;

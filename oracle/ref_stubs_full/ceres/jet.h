@@ -2,7 +2,14 @@
 // Eigen-backend bundle adjustment never instantiates (CeresGrid, the Jet overload of PixelMap::Evaluate, Ceres priors).
 #pragma once
 #include <Eigen/Dense>
+#include <cmath>
 namespace ceres {
+using std::abs;
+using std::cos;
+using std::exp;
+using std::pow;
+using std::sin;
+using std::sqrt;
 template <class T, int N>
 struct Jet {
   T a;

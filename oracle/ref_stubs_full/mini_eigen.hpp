@@ -433,6 +433,11 @@ class MatrixBase {
     }
     return derived();
   }
+  template <class T2, int N2>
+  Derived& operator+=(const DiagonalWrapper<T2, N2>& d) {
+    for (Index i = 0; i < d.v.size(); ++i) derived().ref(i, i) += d.v[i];
+    return derived();
+  }
   Derived& operator*=(const Scalar& s) {
     for (Index i = 0; i < rows(); ++i)
       for (Index j = 0; j < cols(); ++j) derived().ref(i, j) *= s;
@@ -1502,6 +1507,13 @@ class Quaternion {
 using Quaterniond = Quaternion<double>;
 using Quaternionf = Quaternion<float>;
 
+template <class T>
+struct NumTraits {
+  static constexpr T epsilon() { return std::numeric_limits<T>::epsilon(); }
+  static constexpr T dummy_precision() { return T(1e-12); }
+  static constexpr T highest() { return std::numeric_limits<T>::max(); }
+  static constexpr T lowest() { return std::numeric_limits<T>::lowest(); }
+};
 template <class M>
 class JacobiSVD;  // named by the reference's pseudoInverse (uncertainty path, not pinned here)
 

@@ -161,6 +161,19 @@ class OracleBackend:
         e, n, c = O.lm_solve(prob, opt)
         return float(e), int(n), bool(c)
 
+    def finish_solve(self, sigma):
+        """What EigenPhotometricBundleAdjustment::solve does after the LM loop without uncertainties
+        (eigen_photometric_bundle_adjustment.cpp:88,99): relinearizeSystem, updatePointStatuses(1, sigma)."""
+        last = self.frames[-1]  # photometric_bundle_adjustment.cpp:311-316
+        last.T_lin = last.t_world_agent()
+        last.ab0 = last.affine_brightness()
+        last.state_eps = np.zeros(O.BLOCK)
+        O.update_point_statuses(self.frames, 1, sigma)
+
+    def extras(self, f):
+        fr = self.frames[f]
+        return dict(rel_baseline=fr.rel_baseline.copy(), n_inliers=fr.n_inliers.copy(), T_lin=fr.T_lin[:3, :4].copy(), ab0=fr.ab0.copy())
+
     def marginalize(self, fej, sigma):
         if fej:
             O.first_estimate_jacobians(self.frames)
@@ -218,6 +231,14 @@ class ReferenceBackend:
     def solve(self, fej, max_iterations, force_accept, sigma):
         return self.rw.solve(fej=fej, max_iterations=max_iterations, force_accept=force_accept, sigma_huber=sigma,
                              affine_reg=AB_REG, fixed_reg=FIXED_REG)
+
+    def finish_solve(self, sigma):
+        self.rw.relinearize_system()
+        self.rw.update_point_statuses(1, sigma)
+
+    def extras(self, f):
+        T, ab = self.rw.linearization_point(f)
+        return dict(rel_baseline=self.rw.relative_baseline(f), n_inliers=self.rw.landmarks(f)["n_inliers"], T_lin=T, ab0=ab)
 
     def marginalize(self, fej, sigma):
         before = self.rw.n_frames
@@ -285,6 +306,13 @@ def seq_solve(b, fej, max_iterations=7, force_accept=True, sigma=SIGMA):
     e, n, c = b.solve(fej, max_iterations, force_accept, sigma)
     out["solve/result"] = np.array([e, n, float(c)])
     _snapshot(b, out, "solve", with_jac=False)
+    # ... and what follows the loop: relinearizeSystem + updatePointStatuses (the 75 % energy quantile, outlier resets,
+    # inlier counts, relative baselines)
+    b.finish_solve(sigma)
+    _snapshot(b, out, "finish", with_jac=False)
+    for f in range(b.n):
+        for k, v in b.extras(f).items():
+            out[f"finish/lm{f}/{k}" if k in ("rel_baseline", "n_inliers") else f"finish/frame{f}/{k}"] = np.asarray(v)
     return out
 
 
@@ -320,7 +348,7 @@ RUNS = {
 }
 
 # integer / boolean keys are compared exactly, the rest relatively to the array's largest magnitude
-EXACT = ("status", "cand", "jac_valid", "ill", "flags", "n_frames")
+EXACT = ("status", "cand", "jac_valid", "ill", "flags", "n_frames", "n_inliers")
 
 
 def compare(ref, got, rtol=1e-9, skip=()):
@@ -345,3 +373,50 @@ def compare(ref, got, rtol=1e-9, skip=()):
         if not err <= rtol:
             bad.append((k, err))
     return bad
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# coarse-tracker image alignment: the reference's PoseAlignerProblem under its LM driver
+# ----------------------------------------------------------------------------------------------------------------------
+PA_CASES = {  # name -> (seed, density, width, height, ab_scale, affine regulariser, masked target?)
+    "pa_sparse": (3, 0.05, 160, 120, 0.0, (1e12, 1e8), False),
+    "pa_masked_affine": (6, 0.3, 160, 120, 1.0, (10.0, 1e-2), True),
+    "pa_dense": (8, 1.0, 96, 64, 0.0, (1e12, 1e8), False),
+}
+
+
+def pa_case(name):
+    seed, density, W, H, ab_scale, reg, masked = PA_CASES[name]
+    case = synth.make_alignment_case(seed=seed, width=W, height=H, density=density, pose_noise=4e-3, ab_scale=ab_scale)
+    r, t = case.reference, case.target
+    rraw, traw = r.image[..., 0].astype(np.float64), t.image[..., 0].astype(np.float64)
+    mask = t.mask.copy()
+    if masked:
+        mask[20:40, 30:90] = 0
+        mask[::9, ::4] = 0
+    w, s = case.weight.copy(), case.idepth_sum.copy()
+    w[10, 10], s[10, 10] = 2.0, 1e-7  # inverse depth below kMinIdepth: no landmark (local_frame.hpp:379-381)
+    w[2, 50] = 1.0  # inside the 4-px border: no landmark (:372-373)
+    return dict(case=case, rraw=rraw, traw=traw, mask=mask, weight=w, idepth_sum=s, reg=reg)
+
+
+def pa_run_oracle(name):
+    from oracle import pose_alignment_oracle as PA
+    c = pa_case(name)
+    r, t = c["case"].reference, c["case"].target
+    ref = PA.PAFrame(r.T_w_true, r.exposure, r.ab0, r.intr, FO.pixel_info(c["rraw"]), r.mask)
+    tgt = PA.PAFrame(c["case"].T_w_target_guess, t.exposure, t.ab0, t.intr, FO.pixel_info(c["traw"]), c["mask"])
+    uv, idepth, patch = PA.landmarks_from_depth_map(c["idepth_sum"], c["weight"], ref.image)
+    a = PA.solve(ref, tgt, uv, idepth, patch, ab_reg=c["reg"])
+    return {"pa/result": np.array([a["energy"], a["n_valid"], float(a["converged"])]), "pa/T_t_r": a["T_t_r"][:3, :4],
+            "pa/ab_eps": a["ab_eps"], "pa/H": a["H"], "pa/uv": uv, "pa/idepth": idepth, "pa/patch": patch}
+
+
+def pa_run_reference(name):
+    from oracle import ref_pba
+    c = pa_case(name)
+    r, t = c["case"].reference, c["case"].target
+    b = ref_pba.pose_alignment_solve(r.T_w_true, r.exposure, r.ab0, c["rraw"], c["case"].T_w_target_guess, t.exposure, t.ab0,
+                                     c["traw"], r.intr, c["idepth_sum"], c["weight"], tgt_mask=c["mask"], affine_reg=c["reg"])
+    return {"pa/result": np.array([b["energy"], b["n_valid"], float(b["converged"])]), "pa/T_t_r": b["T_t_r"][:3, :4],
+            "pa/ab_eps": b["ab_eps"], "pa/H": b["H"], "pa/uv": b["uv"], "pa/idepth": b["idepth"], "pa/patch": b["patch"]}

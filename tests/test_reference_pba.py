@@ -41,7 +41,8 @@ def golden():
 
 
 def test_golden_covers_every_run(golden):
-    assert set(golden) == set(RC.RUNS)
+    assert set(golden) == set(RC.RUNS) | set(RC.PA_CASES)
+    golden = {k: v for k, v in golden.items() if k in RC.RUNS}
     for name, arrays in golden.items():
         leaves = {k.rsplit("/", 1)[-1] for k in arrays}
         assert {"status", "cand", "r", "w", "e", "idepth", "state_eps"} & leaves, name
@@ -132,3 +133,29 @@ def test_landmark_patch_sampling_live():
     assert np.abs(got - want).max() <= 1e-12 * 255
     # the synthetic generator's integer-position patches are exactly these samples
     assert np.abs(got[:20] - win.frames[0].patch[:20]).max() <= 1e-4  # float32 image in the generator
+
+
+def _pa_compare(ref, got, subsample):
+    assert np.array_equal(np.asarray(ref["pa/uv"], np.int64), np.asarray(got["pa/uv"], np.int64))  # same landmarks, same order
+    gi, gp = (got["pa/idepth"][::7], got["pa/patch"][::7]) if subsample else (got["pa/idepth"], got["pa/patch"])
+    assert np.array_equal(ref["pa/idepth"], gi) and np.array_equal(ref["pa/patch"], gp)  # idepth / weight and I(x, y): exact
+    assert ref["pa/result"][1] == got["pa/result"][1] and ref["pa/result"][2] == got["pa/result"][2]
+    assert abs(ref["pa/result"][0] - got["pa/result"][0]) <= RTOL * ref["pa/result"][0]
+    assert np.abs(ref["pa/T_t_r"] - got["pa/T_t_r"]).max() <= RTOL
+    assert np.abs(ref["pa/ab_eps"] - got["pa/ab_eps"]).max() <= RTOL * max(1.0, np.abs(ref["pa/ab_eps"]).max())
+    assert np.abs(ref["pa/H"] - got["pa/H"]).max() <= RTOL * np.abs(ref["pa/H"]).max()
+
+
+@pytest.mark.parametrize("name", list(RC.PA_CASES))
+def test_pose_alignment_oracle_reproduces_the_reference_golden(golden, name):
+    """The coarse tracker's image alignment: the reference's depth-map LocalFrame constructor
+    (local_frame.hpp:350-393) and its class PoseAlignerProblem (eigen_pose_alignment.cpp:24-242) under its LM driver, set up
+    as EigenPoseAlignment::solve does, against oracle/pose_alignment_oracle.py: the landmark list exactly, energy / pose /
+    affine increment / Hessian at 1e-9."""
+    _pa_compare(golden[name], RC.pa_run_oracle(name), subsample=True)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(RC.PA_CASES))
+def test_pose_alignment_oracle_reproduces_the_reference_live(name):
+    _pa_compare(RC.pa_run_reference(name), RC.pa_run_oracle(name), subsample=False)

@@ -27,8 +27,10 @@ def keep(key):
     tag, mid, leaf = (key.split("/") + [""])[:3] if key.count("/") == 2 else (key.split("/")[0], "", key.split("/")[-1])
     if mid == "":  # systems, energies, results
         return True
+    if tag == "finish":
+        return leaf in ("status", "cand", "e", "flags", "n_inliers", "rel_baseline", "T_lin", "ab0", "state_eps", "idepth")
     if tag in ("solve", "marg"):
-        return leaf not in ("corrected", "Hpd", "bcs") or (leaf == "Hpd" and mid == "lm1")
+        return leaf not in ("corrected", "Hpd", "bcs", "r", "jac_valid") or (leaf == "Hpd" and mid == "lm1")
     if tag == "lin" and mid.startswith("res"):
         if leaf in BIG:
             return mid in KEEP_JAC_PAIRS and leaf in ("J_ref", "J_tgt", "d_idepth")
@@ -55,6 +57,14 @@ def main():
         for k, v in kept.items():
             out[f"{name}::{k}"] = v
         print(f"{name}: {len(kept)} of {len(ref)} arrays kept")
+    for name in RC.PA_CASES:
+        ref = RC.pa_run_reference(name)
+        ref["pa/uv"] = ref["pa/uv"].astype(np.int16)  # integer pixel positions
+        ref["pa/idepth"] = ref["pa/idepth"][::7]  # a cross-section; the live test compares every landmark
+        ref["pa/patch"] = ref["pa/patch"][::7]
+        for k, v in ref.items():
+            out[f"{name}::{k}"] = v
+        print(f"{name}: {len(ref['pa/uv'])} landmarks, energy {ref['pa/result'][0]:.6f}")
     path = os.path.join(ROOT, "tests", "golden", "ref_pba.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path) // 1024, "KiB,", len(out), "arrays")
