@@ -38,7 +38,7 @@ def build_cuda(force=False, verbose_ptxas=False):
     os.makedirs(LIB, exist_ok=True)
     srcs = [os.path.join(CSRC, "pba_kernels.cu"), os.path.join(CSRC, "pba_capi.cu"), os.path.join(CSRC, "pose_alignment.cu"),
             os.path.join(CSRC, "peer_exchange.cu"), os.path.join(CSRC, "energy_quantile.cu"),
-            os.path.join(CSRC, "depth_maps.cu")]
+            os.path.join(CSRC, "depth_maps.cu"), os.path.join(CSRC, "image_tma.cu")]
     deps = srcs + [os.path.join(CSRC, "pba_internal.h"), os.path.join(CSRC, "depth_maps_body.h"),
                    os.path.join(CSRC, "energy_quantile_body.h"), os.path.join(CSRC, "peer_exchange_body.h"), os.path.join(ROOT, "include", "dsopp_cuda_pba.h"),
                    os.path.join(ROOT, "include", "dsopp_cuda_pose_alignment.h")]

@@ -124,6 +124,7 @@ SIGNATURES = {
     "dpba_debug_stamps": (C.c_int, [_I, _P]),
     "dpba_debug_cta_times": (C.c_int, [_P, _I]),
     "dpba_debug_kernel_times": (C.c_int, [_P]),
+    "dpba_debug_pixelinfo_ab": (C.c_int, [_I, _I, _I, _P, _P]),
     "dpba_profile_enable": (C.c_int, [_P, _I]),
     "dpba_profile_read": (C.c_int, [_P, _P, _P]),
     "dpba_comm_unique_id": (C.c_int, [_P]),

@@ -2117,6 +2117,10 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "pixelinfo_tma")) {  // process-wide A/B switch: {I,dx,dy} packing with the tile staged by TMA
+    pba::set_pixelinfo_tma(value != 0);
+    return DPBA_SUCCESS;
+  }
   if (!strcmp(name, "fused_prefetch")) {  // process-wide A/B switch
     pba::set_fused_prefetch(value != 0);
     h->lm_graph_key.clear();
@@ -2161,6 +2165,58 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
 }
 
 int64_t dpba_launch_count(void) { return (int64_t)pba::launch_count(); }
+
+int dpba_debug_pixelinfo_ab(int32_t W, int32_t H, int32_t reps, double ms_per_launch[2], int64_t* mismatching_words) {
+  if (W < 8 || H < 8 || reps < 1 || !ms_per_launch || !mismatching_words) return DPBA_E_INVALID;
+  const size_t n = (size_t)W * H;
+  std::vector<float> host(n);
+  uint32_t st = 12345u;
+  for (size_t i = 0; i < n; ++i) {
+    st = st * 1664525u + 1013904223u;
+    host[i] = (float)(st >> 8) * (255.f / 16777216.f);
+  }
+  float* I = nullptr;
+  float4 *a = nullptr, *b = nullptr;
+  cudaStream_t s;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(&I, n * 4) != cudaSuccess || cudaMalloc(&a, n * 32) != cudaSuccess || cudaMalloc(&b, n * 32) != cudaSuccess)
+    return DPBA_E_CUDA;
+  cudaStreamCreate(&s);
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaMemcpy(I, host.data(), n * 4, cudaMemcpyHostToDevice);
+  cudaMemset(a, 0xff, n * 32);
+  cudaMemset(b, 0x7f, n * 32);
+  int rc = DPBA_SUCCESS;
+  for (int variant = 0; variant < 2 && rc == DPBA_SUCCESS; ++variant) {
+    pba::set_pixelinfo_tma(false);
+    for (int r = -3; r < reps; ++r) {  // three warm-up launches
+      if (r == 0) cudaEventRecord(e0, s);
+      if (variant == 0) pba::launch_pixelinfo(I, a, W, H, s);
+      else if (!pba::launch_pixelinfo_tma(I, b, W, H, s)) rc = DPBA_E_STATE;
+    }
+    cudaEventRecord(e1, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) rc = DPBA_E_CUDA;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms_per_launch[variant] = ms / reps;
+  }
+  if (rc == DPBA_SUCCESS) {
+    std::vector<uint32_t> ha(n * 8), hb(n * 8);
+    cudaMemcpy(ha.data(), a, n * 32, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hb.data(), b, n * 32, cudaMemcpyDeviceToHost);
+    int64_t bad = 0;
+    for (size_t i = 0; i < n * 8; ++i) bad += ha[i] != hb[i];
+    *mismatching_words = bad;
+  }
+  cudaFree(I);
+  cudaFree(a);
+  cudaFree(b);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(s);
+  return rc;
+}
 
 int dpba_debug_kernel_times(int64_t out[32]) {
   cudaDeviceSynchronize();

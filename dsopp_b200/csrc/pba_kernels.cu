@@ -3750,7 +3750,15 @@ void launch_pixelinfo3(const float* I, float* dst, int W, int H, cudaStream_t s)
   k_pixelinfo3<<<g, b, 0, s>>>(I, dst, W, H);
 }
 
+// Measured on B200 (dpba_debug_pixelinfo_ab, profiles/r02_ab.md): the TMA-staged variant (image_tma.cu) produces bit-identical
+// records in the same time -- 6.16 against 6.16 us per launch at 640x480, 4.2 against 3.9 us at 160x120, 20.5 against 21.4 us at
+// 1920x1080.  Every input pixel is touched by at most five neighbouring threads of one CTA, which L1 serves, and the kernel
+// is bound by its 32-byte-per-pixel output stream (3.2 TB/s at 1080p) and, below VGA, by the launch itself.  The direct
+// kernel stays the default; option "pixelinfo_tma" selects the TMA variant.
+static bool g_pixelinfo_tma = false;
+void set_pixelinfo_tma(bool on) { g_pixelinfo_tma = on; }
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s) {
+  if (g_pixelinfo_tma && launch_pixelinfo_tma(I, dst, W, H, s)) return;
   dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
   ++g_launches;
   k_pixelinfo<<<g, b, 0, s>>>(I, dst, W, H);

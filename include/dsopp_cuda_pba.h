@@ -303,7 +303,8 @@ int dpba_create_reference_depth_maps(dpba_handle* h, int32_t n_levels, double id
  * (default 1): the same with world_size > 1, the pair energies travelling in the scalar slots behind the system so that
  * ONE allreduce per iteration carries both.  "fused_epilogue" (default 1, process-wide): second-generation epilogue of
  * the fused sweep (reference block of H_pd formed per target inside the sweep, two block barriers instead of four); 0 selects
- * the first generation's.  "fused_prefetch" (default 0): L1 prefetch A/B switch.  "fused_min_blocks"
+ * the first generation's.  "pixelinfo_tma" (default 0, process-wide): the {I,dx,dy} packing of uploaded frames stages its
+ * tile with TMA (dpba_debug_pixelinfo_ab has the A/B).  "fused_prefetch" (default 0): L1 prefetch A/B switch.  "fused_min_blocks"
  * (3 or 4, process-wide): resident CTAs per SM the fused linearise is built for.  "schur_tensor_cores" (default 1, process-wide): the Schur-complement SYRK runs as
  * 3xTF32 mma.sync; 0 selects the fp32 FFMA kernel.  "peer_exchange" (default 0, needs dpba_peer_attach): the sum over
  * ranks runs as the library's own NVLink mailbox kernel instead of ncclAllReduce.  "device_quantile" (default 0):
@@ -325,6 +326,12 @@ int dpba_debug_cta_times(int64_t* out, int32_t n);
  * LM-loop kernel k (0 fused sweep, 1 core reduce, 2 energy decision, 3 Schur reduce, 4 block assembly, 5 LM step,
  * 6 back-substitution, 7 pair constants, 8 landmark accept) taken while the stamps were on. */
 int dpba_debug_kernel_times(int64_t out[32]);
+/* A/B of the {I, dx, dy} gradient packing (calculate_pixelinfo, features/src/calculate_pixelinfo.cpp:340-374) on a W x H
+ * pseudo-random plane: variant 0 reads the stencil straight from global memory (k_pixelinfo, the default), variant 1 stages
+ * the tile in shared memory with TMA (cp.async.bulk.tensor.2d + mbarrier, k_pixelinfo_tma; option "pixelinfo_tma" routes the
+ * product path through it).  ms_per_launch[v] = device time per launch over `reps` launches (CUDA events, after warm-up);
+ * mismatching_words = 32-bit words in which the two outputs differ (0: bit-identical). */
+int dpba_debug_pixelinfo_ab(int32_t W, int32_t H, int32_t reps, double ms_per_launch[2], int64_t* mismatching_words);
 /* Per-kernel device timing with CUDA events recorded on the handle's stream around each launch.
  * kinds: 0 fused linearise sweep, 1 Schur SYRK (three-pass path), 2 residual-only sweep, 3 materialising sweep,
  *        4 assemble+symmetrise (three-pass path), 5 back-substitution, 6 per-pair constants,
