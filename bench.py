@@ -358,6 +358,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    peers_attached = False
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -395,6 +396,7 @@ def run_ours(args):
         # (measured on B200: 118.9 vs 126.7 us per iteration at N = 2, 151.3 vs 127.7 at N = 8 -- NCCL's latency grows with
         # the rank count, the one-shot mailbox exchange does not; profiles/r02_ab.md).  --peer-exchange 0/1 overrides.
         use_peer = args.peer_exchange == 1 or (args.peer_exchange < 0 and world > 2)
+        peers_attached = use_peer
         if use_peer:
             capi.attach_peers(h, rank, world, dev)
             h.set_option("peer_exchange", 1)
@@ -431,6 +433,11 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        if world > 1 and peers_attached and args.device_rendezvous:
+            # the processes leave torch.distributed's barrier tens of microseconds apart; a device-side rendezvous over the
+            # NVLink mailboxes starts the timed region on all ranks at once (dpba_peer_barrier), so that a 0.6 ms step is
+            # not charged with host-side process jitter.  --device-rendezvous 0 switches it off (A/B).
+            h.peer_barrier()
         l0 = capi.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -715,17 +722,17 @@ def run_ours(args):
     fused_avg = fused_ms / max(fused_n, 1)
     fused_bytes = 51 * units_local + img_bytes + 2 * (D * D + D) * 8
     achieved = fused_bytes / (fused_avg * 1e-3) / 1e9 if fused_avg > 0 else 0.0
-    # FLOPs of one launch from the committed SASS mix of the same configuration (profiles/r02a_k_linearize_fused2.md: FFMA
-    # 3.53 M, FMUL 1.49 M, FADD 1.06 M warp instructions per launch at 112 000 patch-residuals): 2750 FLOP per patch-residual
-    FLOP_PER_UNIT = (3534320 * 64 + 1492984 * 32 + 1062992 * 32) / 112000.0
+    # FLOPs of one launch from the committed SASS mix of the same configuration (profiles/r02b_k_linearize_fused2.md: FFMA
+    # 3.46 M, FMUL 1.50 M, FADD 1.15 M warp instructions per launch at 112 000 patch-residuals): 2736 FLOP per patch-residual
+    FLOP_PER_UNIT = (3462640 * 64 + 1500152 * 32 + 1148864 * 32) / 112000.0
     FP32_PEAK_TFLOPS = 72.6  # measured on this pool's B200 with tools/fp32_probe.cu (profiles/r02a_fp32_probe.txt)
     fused_tflops = FLOP_PER_UNIT * units_local / (fused_avg * 1e-3) / 1e12 if fused_avg > 0 else 0.0
     roofline = {"kernel": "k_linearize_fused2 (K1+K3+K4a, one thread per patch-residual, nothing materialised)", "bound": "hbm",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture of this
-                # configuration (profiles/r02a_k_linearize_fused2.md; cold L2: the 79 MB image set is read in part)
-                "traffic": (60.91e6 + 1.20e6) if (world == 1 and N_FRAMES == 8 and PTS_PER_GPU == 2000) else None,
-                "traffic_source": "profiles/r02a_k_linearize_fused2.md",
+                # configuration (profiles/r02b_k_linearize_fused2.md; cold L2: the 79 MB image set is read in part)
+                "traffic": (60.92e6 + 1.85e6) if (world == 1 and N_FRAMES == 8 and PTS_PER_GPU == 2000) else None,
+                "traffic_source": "profiles/r02b_k_linearize_fused2.md",
                 "peak_source": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_launch": fused_bytes, "avg_launch_ms": fused_avg, "launches_timed": fused_n,
                 "note": "the fused linearise is bound by fp32 issue + L2 gather latency, not HBM (SURVEY 8d: ~55 FLOP/B): see "
@@ -735,9 +742,9 @@ def run_ours(args):
                      "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fused_tflops / FP32_PEAK_TFLOPS,
                      "peak_source": "measured: tools/fp32_probe.cu, 148 SMs x 125 FFMA/clk (profiles/r02a_fp32_probe.txt)",
                      "flop_per_patch_residual": FLOP_PER_UNIT,
-                     "flop_source": "SASS opcode mix of the committed capture (FFMA x 2 + FMUL + FADD), profiles/r02a_k_linearize_fused2.md",
-                     "issue_slots_note": "11.4 M warp instructions per launch = 9.8 us at one instruction per scheduler per "
-                                         "clock; the kernel runs at 0.37 of that rate while active (long-scoreboard: L2 gathers)"}
+                     "flop_source": "SASS opcode mix of the committed capture (FFMA x 2 + FMUL + FADD), profiles/r02b_k_linearize_fused2.md",
+                     "issue_slots_note": "10.9 M warp instructions per launch = 9.4 us at one instruction per scheduler per "
+                                         "clock; the kernel runs at 0.36 of that rate while active (long-scoreboard: L2 gathers)"}
     sweep_bytes = 595 * units_local + img_bytes
     sweep_ach = sweep_bytes / (sweep * 1e-3) / 1e9 if sweep else 0.0
     roofline_sweep = {"kernel": "k_materialise_sweep (K1, reference-surface mode, 595 B/unit)", "bound": "hbm",
@@ -836,6 +843,7 @@ def main():
     ap.add_argument("--peer-fused", type=int, default=-1, help="N > 1 with --peer-exchange: 1 = exchange fused into the producers / consumers (default), 0 = stand-alone mailbox kernel")
     ap.add_argument("--fused-prefetch", type=int, default=-1, help="tuning A/B: 0/1 L1 prefetch of the next taps in the fused linearise")
     ap.add_argument("--fused-epilogue", type=int, default=-1, help="A/B: 1 = second-generation epilogue of the fused sweep (default), 0 = the first generation's")
+    ap.add_argument("--device-rendezvous", type=int, default=1, help="N > 1 with the mailbox exchange: start each timed step after a device-side rendezvous of the ranks (default 1)")
     ap.add_argument("--host-lm", action="store_true", help="drive the LM loop from the C++ host adapter instead of dpba_solve_lm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -131,6 +131,7 @@ SIGNATURES = {
     "dpba_comm_init": (C.c_int, [_P, _P, _I, _I]),
     "dpba_create_reference_depth_maps": (C.c_int, [_P, _I, C.c_double, _P, _P]),
     "dpba_peer_export": (C.c_int, [_P, _P]),
+    "dpba_peer_barrier": (C.c_int, [_P]),
     "dpba_peer_attach": (C.c_int, [_P, _P, _I, _I]),
 }
 
@@ -439,6 +440,10 @@ class Handle:
         buf = (C.c_uint8 * 64)()
         self._ck(self.lib.dpba_peer_export(self.h, C.cast(buf, C.c_void_p)))
         return bytes(buf)
+
+    def peer_barrier(self):
+        """Device-side rendezvous of the attached ranks on the handle's stream (dpba_peer_barrier)."""
+        self._ck(self.lib.dpba_peer_barrier(self.h))
 
     def peer_attach(self, handles: bytes, rank, world):
         assert len(handles) == 64 * world

@@ -68,6 +68,7 @@ struct dpba_handle {
   cudaStream_t stream2 = nullptr;            // side branch of the LM launch sequence (fork/join inside the graph)
   cudaStream_t stream3 = nullptr;            // second side branch (block assembly beside the Schur reduction)
   bool final_sweep = false;                  // option "final_sweep": run the (redundant) closing residual sweep of a speculative solve
+  int dbg_freeze = -1;                       // option "debug_freeze_stamps": the diagnostic stamps stop after the energy decision of this iteration
   bool three_branch = false;                 // option "three_branch": measured slower (94.7 vs 90.5 us per iteration)
   std::vector<cudaEvent_t> fork_ev;          // dependency-only events of the fork/join edges
   size_t fork_used = 0;
@@ -1746,6 +1747,10 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
                               k == 0 ? pba::LM_ENERGY_INITIAL : pba::LM_ENERGY_TRIAL, s, rb.core, n_pairs,
                               k ? rb.n_part : nullptr, k ? n_norm_parts : 0, 1);
       }
+      if (k == h->dbg_freeze) {
+        pba::stamps_off_async(s);
+        pba::peer_stamps_off_async(s);
+      }
       if (more && (rc = stream_edge(h, s2, s))) return rc;  // finish_fused_k, assemble_k before lm_step_{k+1}
       if (k > 0) {  // acceptStep() / rejectStep() of the landmarks incl. changeResidualStatuses
         if ((rc = stream_edge(h, s, s2))) return rc;
@@ -1824,6 +1829,10 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
         pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, ro.scal, Hm, bm,
                               k == 0 ? pba::LM_ENERGY_INITIAL : pba::LM_ENERGY_TRIAL, s, nullptr, 0, nullptr, 0, 0,
                               fx ? (more ? 1 : 2) : 0);
+      }
+      if (k == h->dbg_freeze) {
+        pba::stamps_off_async(s);
+        pba::peer_stamps_off_async(s);
       }
       if (k > 0) {
         if ((rc = stream_edge(h, s, s2))) return rc;
@@ -2112,6 +2121,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "fused_lpb_max")) {  // process-wide tuning switch: cap of the fused sweep's landmarks per CTA (32..256)
+    pba::set_fused_lpb_max((int)value);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
   if (!strcmp(name, "fused_epilogue")) {  // process-wide A/B switch: 1 = second-generation epilogue of the fused sweep
     pba::set_fused_epilogue((int)value);
     h->lm_graph_key.clear();
@@ -2123,6 +2137,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
   }
   if (!strcmp(name, "fused_prefetch")) {  // process-wide A/B switch
     pba::set_fused_prefetch(value != 0);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "debug_freeze_stamps")) {  // diagnostics: see dpba_debug_kernel_times
+    h->dbg_freeze = (int)value;
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
@@ -2221,6 +2240,9 @@ int dpba_debug_pixelinfo_ab(int32_t W, int32_t H, int32_t reps, double ms_per_la
 int dpba_debug_kernel_times(int64_t out[32]) {
   cudaDeviceSynchronize();
   pba::debug_kernel_times(reinterpret_cast<long long*>(out));
+  long long pk[4];
+  pba::debug_peer_times(1, pk);  // slots 10, 11: the mailbox exchange kernel (entry / exit, wait for the peers begin / end)
+  out[20] = pk[0], out[21] = pk[1], out[22] = pk[2], out[23] = pk[3];
   return DPBA_SUCCESS;
 }
 
@@ -2233,6 +2255,7 @@ int dpba_debug_cta_times(int64_t* out, int32_t n) {
 int dpba_debug_stamps(int32_t enable, int64_t out[64]) {
   long long tmp[64];
   cudaDeviceSynchronize();
+  pba::debug_peer_times(enable, nullptr);
   pba::debug_stamps(enable, tmp);
   if (out)
     for (int i = 0; i < 64; ++i) out[i] = tmp[i];
@@ -2300,6 +2323,17 @@ int dpba_peer_export(dpba_handle* h, uint8_t handle[64]) {
   cudaIpcMemHandle_t ipc;
   CK(cudaIpcGetMemHandle(&ipc, h->peer_box));
   memcpy(handle, &ipc, 64);
+  return DPBA_SUCCESS;
+}
+
+int dpba_peer_barrier(dpba_handle* h) {
+  REQUIRE(h, "null handle");
+  REQUIRE(h->peer_attached, "dpba_peer_attach first");
+  // a mailbox exchange of the 8 scalar slots into the scratch half of the reduction buffer: it completes on every rank
+  // within a flag's flight time of the last rank's arrival, which is all a rendezvous needs
+  const RedLayout L = red_layout(h->n_frames >= 2 ? h->n_frames : 2);
+  pba::launch_peer_allreduce(h->peer, h->red, h->red2, L.scal, 8, h->stream);
+  CK(cudaGetLastError());
   return DPBA_SUCCESS;
 }
 

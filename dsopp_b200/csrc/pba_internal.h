@@ -172,6 +172,9 @@ int fused_version();
 void debug_stamps(int enable, long long out[64]);
 void debug_cta_times(long long* out, int n);
 void debug_kernel_times(long long out[32]);
+void stamps_off_async(cudaStream_t s);
+void peer_stamps_off_async(cudaStream_t s);
+void debug_peer_times(int enable, long long out[4]);  // peer_exchange.cu: entry, latest exit, wait start, wait end of the last mailbox exchange
 void launch_linearize_from_materialized(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
 int launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);
 void launch_assemble(const WindowDev& w, int fej, ReduceBuf rb, FusedShape shape, cudaStream_t s,
@@ -205,6 +208,7 @@ void set_fused_version(int v);
 void set_pdl(bool on);
 void set_fused_prefetch(bool on);
 void set_fused_epilogue(int v);
+void set_fused_lpb_max(int v);
 
 // ---- peer-memory exchange (peer_exchange.cu): one-shot all-reduce over NVLink mailboxes -------------------------------
 constexpr int PEER_MAXW = 8;   // ranks of one NVSwitch domain

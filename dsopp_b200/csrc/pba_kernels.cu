@@ -572,6 +572,7 @@ __global__ void __launch_bounds__(1024) k_reduce_scal(const LmCtl* __restrict__ 
                                                       const double2* __restrict__ e_part, int n_e,
                                                       const double2* __restrict__ n_part, int n_n,
                                                       double* __restrict__ scal, int core_frames, int peer_push) {
+  KStamp kstamp_(9);
   if (lm_skip(ctl, ctl_mode)) return;
   const unsigned epoch = peer_push ? peer_epoch() : 0u;
   __shared__ double s[4][32];
@@ -3828,6 +3829,8 @@ void set_pdl(bool on) { g_pdl = on; }
 int g_fused_minb = 3;  // resident CTAs per SM the fused linearise is compiled for (N <= 9): 4 -> 64 registers, 3 -> 80
 void set_fused_min_blocks(int b) { g_fused_minb = b <= 3 ? 3 : 4; }
 
+int g_fused_lpb_max = 256;  // largest landmark chunk per CTA the launcher may pick (option "fused_lpb_max")
+void set_fused_lpb_max(int v) { g_fused_lpb_max = v < 32 ? 32 : (v > 256 ? 256 : (v / 32) * 32); }
 int g_fused_epilogue = 1;  // second-generation epilogue of k_linearize_fused2 (option "fused_epilogue", 0 = the first generation's)
 void set_fused_epilogue(int v) { g_fused_epilogue = v != 0; }
 bool g_fused_prefetch = false;  // L1 prefetch of the next group's image taps: measured 42.6 us against 39.1 us without (issue-bound kernel), kept as an A/B switch (option "fused_prefetch")
@@ -3881,7 +3884,13 @@ static FusedShape launch_linearize_fused2(const WindowDev& w, float sigma, int h
   const long resident = (long)sm_count() * 2;
   int lpb = 32;
   double best = 1e300;
-  for (int cand = 32; cand <= 256; cand += 32) {
+  for (int cand = 32; cand <= g_fused_lpb_max; cand += 32) {
+    // two CTAs must stay resident per SM: 2 x (dynamic + 1 KB static + 1 KB reserved) within the 227 KB an SM can carve out,
+    // with room to spare for the carve-out steps (measured: 106 KB per CTA -- lpb 192 with the second-generation epilogue --
+    // ran one CTA per SM and the 1.12 M-unit sweep took 1.6x as long)
+    const size_t need = (size_t)(N - 1) * sizeof(PairConst) + ((size_t)cand * (D + 2 + 2 * (N - 1)) + 3) * sizeof(float) +
+                        (g_fused_epilogue ? (size_t)cand * (8 * (N - 1) + 1) * sizeof(float) : 0);
+    if (cand > 32 && need > 96 * 1024) break;
     const long blocks = (long)((m + cand - 1) / cand) * N;
     const double waves = (double)((blocks + resident - 1) / resident);
     const double cost = waves * (cand / 32 + 0.5);  // per CTA: cand / 32 landmark groups + prologue / epilogue
@@ -3907,6 +3916,11 @@ static FusedShape launch_linearize_fused2(const WindowDev& w, float sigma, int h
 
 int fused_version() { return g_fused_version; }
 void debug_cta_times(long long* out, int n) { cudaMemcpyFromSymbol(out, g_cta_times, sizeof(long long) * (size_t)(n < 4096 ? n : 4096)); }
+void stamps_off_async(cudaStream_t s) {  // a memset node when captured: the stamps keep what they hold from here on
+  void* p = nullptr;
+  cudaGetSymbolAddress(&p, g_stamps_on);
+  cudaMemsetAsync(p, 0, sizeof(int), s);
+}
 void debug_kernel_times(long long out[32]) { cudaMemcpyFromSymbol(out, g_kst, sizeof(long long) * 32); }
 void debug_stamps(int enable, long long out[64]) {
   cudaMemcpyToSymbol(g_stamps_on, &enable, sizeof(int));

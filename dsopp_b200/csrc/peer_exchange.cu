@@ -38,9 +38,19 @@ namespace pba {
 
 namespace {
 
+// diagnostics (dpba_debug_kernel_times slots 10 / 11): entry of CTA 0, start of its wait for the peers, latest exit
+__device__ unsigned long long g_peer_kst[4];
+__device__ int g_peer_stamps_on = 0;
+__device__ __forceinline__ unsigned long long peer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void __launch_bounds__(256) k_peer_allreduce(PeerDev pd, const double* __restrict__ in,
                                                         double* __restrict__ out, size_t off, size_t n2) {
   const int c = blockIdx.x;
+  if (g_peer_stamps_on && c == 0 && threadIdx.x == 0) g_peer_kst[0] = peer_ns();
   const int C = gridDim.x;
   __shared__ unsigned s_epoch;
   if (threadIdx.x == 0) s_epoch = peer_begin(pd);
@@ -53,17 +63,30 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerDev pd, const double
   __threadfence_system();
   __syncthreads();
   // ---- raise our flags, wait for the same slice of every rank ---------------------------------------------------------
+  if (g_peer_stamps_on && c == 0 && threadIdx.x == 0) g_peer_kst[2] = peer_ns();
   if ((int)threadIdx.x < pd.world) {
     peer_signal(pd, c, epoch, (int)threadIdx.x);
     peer_wait(pd, c, epoch, (int)threadIdx.x);
   }
   __syncthreads();
+  if (g_peer_stamps_on && c == 0 && threadIdx.x == 0) g_peer_kst[3] = peer_ns();
   // ---- sum in rank order from the local mailbox ------------------------------------------------------------------------
   for (size_t i = sl.lo + threadIdx.x; i < sl.hi; i += blockDim.x) peer_sum_elem(pd, out, off, epoch, i);
   if (threadIdx.x == 0) peer_finish(pd, C, epoch);
+  if (g_peer_stamps_on && threadIdx.x == 0) atomicMax(&g_peer_kst[1], peer_ns());
 }
 
 }  // namespace
+
+void peer_stamps_off_async(cudaStream_t s) {
+  void* p = nullptr;
+  cudaGetSymbolAddress(&p, g_peer_stamps_on);
+  cudaMemsetAsync(p, 0, sizeof(int), s);
+}
+void debug_peer_times(int enable, long long out[4]) {
+  cudaMemcpyToSymbol(g_peer_stamps_on, &enable, sizeof(int));
+  if (out) cudaMemcpyFromSymbol(out, g_peer_kst, 4 * sizeof(long long));
+}
 
 // n doubles starting at `off` (both even: every block boundary of RedLayout is) of `in`, summed over ranks into `out`
 void launch_peer_allreduce(const PeerDev& pd, const double* in, double* out, size_t off, size_t n, cudaStream_t s) {

@@ -355,6 +355,11 @@ int dpba_comm_init(dpba_handle* h, const uint8_t id[128], int32_t rank, int32_t 
  * instead of hanging.  Barrier again before dpba_destroy.  One node (one NVSwitch domain), 2..8 ranks. */
 int dpba_peer_export(dpba_handle* h, uint8_t ipc_handle[64]);
 int dpba_peer_attach(dpba_handle* h, const uint8_t* ipc_handles, int32_t rank, int32_t world_size);
+/* Device-side rendezvous of the attached ranks on the handle's stream (one mailbox exchange of the scalar slots): work
+ * enqueued after it starts on every rank within a flag's flight time of the last rank's arrival.  bench.py uses it to start
+ * the timed region of a sharded step on all ranks at once instead of after torch.distributed's host-side barrier, whose
+ * exit jitter between processes (tens of microseconds) would otherwise be charged to a 0.6 ms step. */
+int dpba_peer_barrier(dpba_handle* h);
 
 #ifdef __cplusplus
 }

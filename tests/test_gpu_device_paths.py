@@ -120,3 +120,16 @@ def test_mean_square_optical_flow_equals_the_oracle():
     flow, used = al.mean_square_optical_flow(O.se3_exp(np.array([0, 0, -30.0, 0, 0, 0])))
     assert used == 0 and np.isnan(flow)
     al.close()
+
+
+@pytest.mark.parametrize("shape", [(640, 480), (320, 240), (88, 60)])
+def test_tma_staged_pixelinfo_is_bit_identical_to_the_direct_stencil(shape):
+    """k_pixelinfo_tma (cp.async.bulk.tensor.2d + mbarrier, csrc/image_tma.cu) against k_pixelinfo -- the kernel the GPU
+    suite pins against the reference's calculate_pixelinfo -- on a pseudo-random plane, including partial tiles."""
+    import ctypes as C
+    from dsopp_b200 import capi
+    lib = capi.load_library()
+    ms = (C.c_double * 2)()
+    bad = C.c_int64(-1)
+    rc = lib.dpba_debug_pixelinfo_ab(shape[0], shape[1], 3, ms, C.addressof(bad))
+    assert rc == 0 and bad.value == 0, (rc, bad.value)

@@ -27,7 +27,6 @@ prev = 0
 for i in sorted(names):
     print(f"{names[i]:28s} {t[i]:8d} cycles  (+{t[i] - prev})")
     prev = t[i]
-h.close()
 
 # per-CTA timeline of the last fused sweep (dpba_debug_cta_times): how long the CTAs take and how they share the SMs
 ct = np.zeros(4096, np.int64)
@@ -47,7 +46,12 @@ if len(ct):
     late = np.argsort(ct[:, 2])[-5:]
     print("   last five CTAs to finish: " + ", ".join(f"entry {ent[i]:.1f} + {end[i]:.1f} us (sweep {swp[i]:.1f}) on SM {int(sm[i])}" for i in late))
 
-# entry / exit of the LM-loop kernels' last launches (dpba_debug_kernel_times): the gaps BETWEEN the kernels of an iteration
+# entry / exit of the LM-loop kernels' last launches (dpba_debug_kernel_times): the gaps BETWEEN the kernels of an iteration;
+# the stamps are frozen after the energy decision of iteration 6, so the table is one complete iteration (LM step -> energy)
+h.set_option("debug_freeze_stamps", 6)
+lib.dpba_debug_stamps(1, None)
+h.first_estimate()
+h.solve_lm(20.0, max_it=7, min_it=7, ftol=0.0, ptol=0.0)
 kt = np.zeros(32, np.int64)
 lib.dpba_debug_kernel_times(kt.ctypes.data)
 knames = ["fused sweep", "core reduce", "energy decision", "schur reduce", "block assembly", "lm step", "back-substitution", "pair constants", "landmark accept"]
@@ -57,3 +61,4 @@ if rows:
     print("last launches of the LM-loop kernels, us from the first entry (entry -> exit):")
     for a, b, nm in rows:
         print(f"   {nm:18s} {(a - t0) / 1e3:8.1f} -> {(b - t0) / 1e3:8.1f}   ({(b - a) / 1e3:5.1f} us)")
+h.close()
