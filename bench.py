@@ -384,6 +384,9 @@ def run_ours(args):
         h.set_option("fused_prefetch", args.fused_prefetch)
     if args.fused_epilogue >= 0:
         h.set_option("fused_epilogue", args.fused_epilogue)
+    for kv in args.opt:  # any dpba_set_option switch, for A/B runs
+        k_, v_ = kv.split("=")
+        h.set_option(k_, int(v_))
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -844,6 +847,7 @@ def main():
     ap.add_argument("--fused-prefetch", type=int, default=-1, help="tuning A/B: 0/1 L1 prefetch of the next taps in the fused linearise")
     ap.add_argument("--fused-epilogue", type=int, default=-1, help="A/B: 1 = second-generation epilogue of the fused sweep (default), 0 = the first generation's")
     ap.add_argument("--device-rendezvous", type=int, default=1, help="N > 1 with the mailbox exchange: start each timed step after a device-side rendezvous of the ranks (default 1)")
+    ap.add_argument("--opt", action="append", default=[], help="A/B: name=value passed to dpba_set_option (repeatable)")
     ap.add_argument("--host-lm", action="store_true", help="drive the LM loop from the C++ host adapter instead of dpba_solve_lm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

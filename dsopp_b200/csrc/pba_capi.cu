@@ -2121,6 +2121,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "fused2_min_blocks")) {  // process-wide A/B switch: 2 (default) or 3 resident CTAs per SM for the fused sweep
+    pba::set_fused2_min_blocks((int)value);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
   if (!strcmp(name, "fused_lpb_max")) {  // process-wide tuning switch: cap of the fused sweep's landmarks per CTA (32..256)
     pba::set_fused_lpb_max((int)value);
     h->lm_graph_key.clear();

@@ -3829,6 +3829,8 @@ void set_pdl(bool on) { g_pdl = on; }
 int g_fused_minb = 3;  // resident CTAs per SM the fused linearise is compiled for (N <= 9): 4 -> 64 registers, 3 -> 80
 void set_fused_min_blocks(int b) { g_fused_minb = b <= 3 ? 3 : 4; }
 
+int g_fused2_minb = 2;  // A/B (option "fused2_min_blocks"): 3 = the second-generation sweep compiled for three CTAs per SM (<= 96 registers)
+void set_fused2_min_blocks(int b) { g_fused2_minb = b == 3 ? 3 : 2; }
 int g_fused_lpb_max = 256;  // largest landmark chunk per CTA the launcher may pick (option "fused_lpb_max")
 void set_fused_lpb_max(int v) { g_fused_lpb_max = v < 32 ? 32 : (v > 256 ? 256 : (v / 32) * 32); }
 int g_fused_epilogue = 1;  // second-generation epilogue of k_linearize_fused2 (option "fused_epilogue", 0 = the first generation's)
@@ -3881,7 +3883,7 @@ static FusedShape launch_linearize_fused2(const WindowDev& w, float sigma, int h
   const int m = max_landmarks(w);
   if (m == 0 || w.n_frames < 2) return shape;
   const int N = w.n_frames, D = 8 * N;
-  const long resident = (long)sm_count() * 2;
+  const long resident = (long)sm_count() * ((N <= 8 && g_fused2_minb == 3) ? 3 : 2);
   int lpb = 32;
   double best = 1e300;
   for (int cand = 32; cand <= g_fused_lpb_max; cand += 32) {
@@ -3906,7 +3908,8 @@ static FusedShape launch_linearize_fused2(const WindowDev& w, float sigma, int h
   const int threads = 32 * (N - 1);
   const int fold = fold_step != nullptr && ctl != nullptr;
   double2* norms = reinterpret_cast<double2*>(rb.n_part);
-  if (N <= 8) launch_fused2_t<7, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms, epi);
+  if (N <= 8 && g_fused2_minb == 3) launch_fused2_t<7, 3>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms, epi);
+  else if (N <= 8) launch_fused2_t<7, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms, epi);
   else if (N <= 9) launch_fused2_t<8, 2>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms, epi);
   else launch_fused2_t<15, 1>(w, sigma, huber, fej, for_marg, lpb, g, threads, smem, rb.core_part, rb.fschur_part, s, ctl, ctl_mode, fold, fold_step, norms, epi);
   shape.lpb = lpb;
