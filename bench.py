@@ -395,10 +395,11 @@ def run_ours(args):
         h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
         h.first_estimate()
         h.evaluate(SIGMA, True, True)  # first collective outside any graph capture: NCCL sets its channels up here
-        # exchange of the reduced system: ncclAllReduce on 2 GPUs, the library's own NVLink mailbox kernel from 4 GPUs on
-        # (measured on B200: 118.9 vs 126.7 us per iteration at N = 2, 151.3 vs 127.7 at N = 8 -- NCCL's latency grows with
-        # the rank count, the one-shot mailbox exchange does not; profiles/r02_ab.md).  --peer-exchange 0/1 overrides.
-        use_peer = args.peer_exchange == 1 or (args.peer_exchange < 0 and world > 2)
+        # exchange of the reduced system: the library's own NVLink mailbox kernel, scalars and system in two concurrent
+        # exchanges (measured on B200 at N = 2: 102.4 us per iteration against 114.4 with ncclAllReduce in the graph; at
+        # N = 8 NCCL's latency grows with the rank count, the one-shot mailbox exchange does not; profiles/r02_ab.md).
+        # --peer-exchange 0 selects NCCL.
+        use_peer = args.peer_exchange != 0
         peers_attached = use_peer
         if use_peer:
             capi.attach_peers(h, rank, world, dev)

@@ -167,12 +167,14 @@ struct dpba_handle {
   // peer-memory exchange (peer_exchange.cu): this rank's mailbox, the peers' mailboxes opened over CUDA IPC
   void* peer_box = nullptr;
   void* peer_open[pba::PEER_MAXW] = {};
-  unsigned* peer_ctr = nullptr;  // device: {seq, done, error, pad}
+  unsigned* peer_ctr = nullptr;  // device: {seq, done, error, pad} of channel A, {seq, done} of channel B, pad
+  pba::PeerDev peer_b{};         // second, independent mailbox channel (the 8 scalars of a sharded LM iteration; option "split_exchange")
+  bool split_exchange = true;    // sharded speculative LM: scalars and system travel in two concurrent exchanges
   int* peer_err_h = nullptr;     // mapped pinned: set by the kernel after a time-out
   pba::PeerDev peer{};
   bool peer_attached = false;
   bool peer_on = false;          // option "peer_exchange"
-  bool peer_fused = true;        // option "peer_fused": inside dpba_solve_lm the exchange rides in the producers' epilogues
+  bool peer_fused = false;       // option "peer_fused": inside dpba_solve_lm the exchange rides in the producers' epilogues (measured slower than the stand-alone kernel + split exchange: profiles/r02_ab.md)
                                  // and the consumers' prologues (no exchange kernel); 0 = the stand-alone mailbox kernel
   // device-side quantile of updatePointStatuses (energy_quantile.cu)
   bool device_quantile = true;   // option "device_quantile" (0: host nth_element over rows read back)
@@ -214,7 +216,12 @@ static_assert(N_EXCHANGE % 2 == 0, "the peer exchange moves double2");
 constexpr size_t PEER_BOX_DATA = 2 * (size_t)pba::PEER_MAXW * N_EXCHANGE;  // doubles
 constexpr size_t PEER_BOX_FLAGS = (size_t)pba::PEER_MAXW * pba::PEER_MAXC;  // words
 constexpr size_t PEER_BOX_COUNTERS = 2 * 2 * (size_t)pba::PEER_MAXW;         // words: [parity][kind][source]
-constexpr size_t PEER_BOX_BYTES = PEER_BOX_DATA * sizeof(double) + (PEER_BOX_FLAGS + PEER_BOX_COUNTERS) * sizeof(unsigned);
+constexpr size_t PEER_BOX_A_BYTES = PEER_BOX_DATA * sizeof(double) + (PEER_BOX_FLAGS + PEER_BOX_COUNTERS) * sizeof(unsigned);
+// channel B (the 8 scalar slots only): its own data [2 parities][PEER_MAXW sources][8] and flags, behind channel A's region
+constexpr size_t PEER_B_SLOT = 8;
+constexpr size_t PEER_BOX_B_DATA = 2 * (size_t)pba::PEER_MAXW * PEER_B_SLOT;  // doubles
+constexpr size_t PEER_BOX_B_OFFSET = (PEER_BOX_A_BYTES + 255) / 256 * 256;
+constexpr size_t PEER_BOX_BYTES = PEER_BOX_B_OFFSET + PEER_BOX_B_DATA * sizeof(double) + PEER_BOX_FLAGS * sizeof(unsigned);
 
 // several ranks AND a way to sum over them (NCCL communicator or attached peer mailboxes)
 inline bool multi_gpu(const dpba_handle* h) { return h->world > 1 && (h->comm || h->peer_on); }
@@ -449,6 +456,19 @@ int exchange_raw(dpba_handle* h, size_t off, size_t n) {
   NcclApi& nc = nccl_api();
   ncclResult_t r = nc.AllReduce(h->red + off, h->red2 + off, n, ncclDouble, ncclSum, h->comm, h->stream);
   if (r != ncclSuccess) return fail(h, DPBA_E_COMM, std::string("ncclAllReduce: ") + nc.GetErrorString(r));
+  return 0;
+}
+
+// the 8 scalar slots over the second mailbox channel, on stream `s` (runs beside a system exchange on channel A)
+int exchange_scal_b(dpba_handle* h, cudaStream_t s) {
+  const RedLayout L = red_layout(h->n_frames);
+  pba::launch_peer_allreduce(h->peer_b, h->red + L.scal, h->red2 + L.scal, 0, 8, s);
+  return 0;
+}
+// the linear system [Hp | bp | Hs | bs] over channel A on stream `s`
+int exchange_system_on(dpba_handle* h, cudaStream_t s) {
+  const RedLayout L = red_layout(h->n_frames);
+  pba::launch_peer_allreduce(h->peer, h->red, h->red2, L.hp, L.scal - L.hp, s);
   return 0;
 }
 
@@ -1800,7 +1820,72 @@ static int lm_enqueue(dpba_handle* h, bool have_marg) {
     const int fx = (h->peer_on && h->peer_attached && h->peer_fused) ? 1 : 0;
     const int sys_ctas = pba::system_producer_ctas(N);
     FusedShape shape;
-    for (int k = 0; k <= od.max_it; ++k) {
+    // Split exchange (mailbox kernel, option "split_exchange", default on): the energy decision needs the 8 scalars of every
+    // rank, the LM step needs the summed system -- so they travel separately and concurrently.  Main branch: core reduce,
+    // scalar reduce, scalar exchange (channel B), energy decision; side branch: Schur reduce, block assembly, system exchange
+    // (channel A); the LM step joins both.  The decision no longer waits for the assembly of the system and its 66 KB round.
+    const bool split = h->split_exchange && h->peer_on && h->peer_attached && !fx;
+    for (int k = 0; split && k <= od.max_it; ++k) {
+      const bool more = k < od.max_it;
+      {
+        ProfScope ps(h, 0);
+        shape = pba::launch_linearize_fused(w, sigma, 1, fej, 0, rb, s, h->ctl, 1);
+      }
+      if (more) {
+        if ((rc = stream_edge(h, s, s2))) return rc;
+        ProfScope ps(h, 10, s2);
+        pba::launch_finish_fused(w, rb, shape, s2, h->ctl, 0);
+      }
+      {
+        ProfScope ps(h, 8);
+        pba::launch_core_reduce(w, rb, shape, s, h->ctl);
+      }
+      if (more) {
+        if ((rc = stream_edge(h, s, s2))) return rc;  // the block assembly reads the reduced cores
+        {
+          ProfScope ps(h, 9, s2);
+          pba::launch_assemble_blocks(w, fej, rb, shape, s2, h->ctl, 0);
+        }
+        exchange_system_on(h, s2);
+      }
+      pba::launch_reduce_scal(h->ctl, 1, rb.core, N * (N - 1), k ? rb.n_part : nullptr, k ? n_norm_parts : 0, rb.scal, s, N, 0);
+      exchange_scal_b(h, s);
+      {
+        ProfScope ps(h, 11);
+        pba::launch_lm_energy(h->ctl, h->lmopt, h->fparams, N, ro.scal, Hm, bm,
+                              k == 0 ? pba::LM_ENERGY_INITIAL : pba::LM_ENERGY_TRIAL, s, nullptr, 0, nullptr, 0, 0, 0);
+      }
+      if (k == h->dbg_freeze) {
+        pba::stamps_off_async(s);
+        pba::peer_stamps_off_async(s);
+      }
+      if (more && (rc = stream_edge(h, s2, s))) return rc;  // the summed system before the LM step
+      if (k > 0) {
+        if ((rc = stream_edge(h, s, s2))) return rc;
+        ProfScope ps(h, 11, s2);
+        pba::launch_accept(w, 0, nullptr, s2, h->ctl, 1);
+      }
+      if (!more) {
+        if (k > 0 && (rc = stream_edge(h, s2, s))) return rc;
+        break;
+      }
+      {
+        ProfScope ps(h, 7);
+        pba::launch_lm_step(h->ctl, h->lmopt, h->fparams, h->fixed_dev, N, ro, Hm, bm, h->step_dev, s, 0);
+      }
+      if (k > 0 && (rc = stream_edge(h, s2, s))) return rc;
+      if ((rc = stream_edge(h, s, s2))) return rc;
+      {
+        ProfScope ps(h, 6, s2);
+        pba::launch_pair_setup(h->fparams, N, h->pairs, h->pasm, s2);
+      }
+      {
+        ProfScope ps(h, 5);
+        pba::launch_back_substitute(w, h->step_dev, 0.0, s, h->ctl, rb.n_part);
+      }
+      if ((rc = stream_edge(h, s2, s))) return rc;
+    }
+    for (int k = 0; !split && k <= od.max_it; ++k) {
       const bool more = k < od.max_it;
       {
         ProfScope ps(h, 0);
@@ -2121,6 +2206,16 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "peer_fence_all")) {  // A/B: 1 = system-scope fence in every pushing thread of the mailbox exchange (round-1 form)
+    pba::set_peer_fence_all((int)value);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
+  if (!strcmp(name, "split_exchange")) {  // sharded LM with the mailbox kernel: scalars and system in two concurrent exchanges
+    h->split_exchange = value != 0;
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
   if (!strcmp(name, "fused2_min_blocks")) {  // process-wide A/B switch: 2 (default) or 3 resident CTAs per SM for the fused sweep
     pba::set_fused2_min_blocks((int)value);
     h->lm_graph_key.clear();
@@ -2318,12 +2413,12 @@ int dpba_peer_export(dpba_handle* h, uint8_t handle[64]) {
   CK(cudaSetDevice(h->cfg.device));
   if (!h->peer_box) {
     CK(cudaMalloc(&h->peer_box, PEER_BOX_BYTES));
-    CK(cudaMalloc(&h->peer_ctr, 4 * sizeof(unsigned)));  // seq, done, error, pad
+    CK(cudaMalloc(&h->peer_ctr, 8 * sizeof(unsigned)));  // A: seq, done, error, pad; B: seq, done, pad, pad
     CK(cudaHostAlloc(&h->peer_err_h, sizeof(int), cudaHostAllocMapped));
     *h->peer_err_h = 0;
   }
   CK(cudaMemset(h->peer_box, 0, PEER_BOX_BYTES));
-  CK(cudaMemset(h->peer_ctr, 0, 4 * sizeof(unsigned)));
+  CK(cudaMemset(h->peer_ctr, 0, 8 * sizeof(unsigned)));
   CK(cudaDeviceSynchronize());
   cudaIpcMemHandle_t ipc;
   CK(cudaIpcGetMemHandle(&ipc, h->peer_box));
@@ -2375,6 +2470,19 @@ int dpba_peer_attach(dpba_handle* h, const uint8_t* handles, int32_t rank, int32
   pd.world = world;
   pd.slot = N_EXCHANGE;
   h->peer = pd;
+  {  // channel B: same ranks, same error word, its own data / flags / epoch counters
+    pba::PeerDev pb = pd;
+    for (int r = 0; r < world; ++r) {
+      char* base = reinterpret_cast<char*>(pd.data[r]) + PEER_BOX_B_OFFSET;
+      pb.data[r] = reinterpret_cast<double*>(base);
+      pb.flag[r] = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(base) + PEER_BOX_B_DATA);
+      pb.cnt[r] = nullptr;
+    }
+    pb.seq = h->peer_ctr + 4;
+    pb.done = h->peer_ctr + 5;
+    pb.slot = PEER_B_SLOT;
+    h->peer_b = pb;
+  }
   pba::set_peer_context(pd);  // process-wide __device__ copy for the fused exchange (one sharded handle per process)
   CK(cudaGetLastError());
   h->world = world;

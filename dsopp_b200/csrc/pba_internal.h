@@ -174,6 +174,7 @@ void debug_cta_times(long long* out, int n);
 void debug_kernel_times(long long out[32]);
 void stamps_off_async(cudaStream_t s);
 void peer_stamps_off_async(cudaStream_t s);
+void set_peer_fence_all(int v);
 void debug_peer_times(int enable, long long out[4]);  // peer_exchange.cu: entry, latest exit, wait start, wait end of the last mailbox exchange
 void launch_linearize_from_materialized(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s);
 int launch_schur(const WindowDev& w, int for_marg, ReduceBuf rb, cudaStream_t s, const LmCtl* ctl = nullptr);

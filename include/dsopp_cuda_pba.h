@@ -307,7 +307,11 @@ int dpba_create_reference_depth_maps(dpba_handle* h, int32_t n_levels, double id
  * tile with TMA (dpba_debug_pixelinfo_ab has the A/B).  "fused_prefetch" (default 0): L1 prefetch A/B switch.  "fused_min_blocks"
  * (3 or 4, process-wide): resident CTAs per SM the fused linearise is built for.  "schur_tensor_cores" (default 1, process-wide): the Schur-complement SYRK runs as
  * 3xTF32 mma.sync; 0 selects the fp32 FFMA kernel.  "peer_exchange" (default 0, needs dpba_peer_attach): the sum over
- * ranks runs as the library's own NVLink mailbox kernel instead of ncclAllReduce.  "device_quantile" (default 0):
+ * ranks runs as the library's own NVLink mailbox kernel instead of ncclAllReduce; inside dpba_solve_lm the 8 scalars of an
+ * iteration (energies, norms) and its linear system then travel in two concurrent exchanges over two mailbox channels
+ * ("split_exchange", default 1), so that the energy decision does not wait for the assembly of the system.  "peer_fused"
+ * (default 0): the exchange rides in the producers' epilogues and the consumers' prologues instead (measured slower).
+ * "peer_fence_all" (default 0): A/B switch, a system-scope fence in every pushing thread instead of one per signalling thread.  "device_quantile" (default 0):
  * dpba_update_point_statuses finds the 75 % energy quantile with an exact radix select on the device instead of
  * reading the rows back for std::nth_element. */
 int dpba_set_option(dpba_handle* h, const char* name, int64_t value);

@@ -17,7 +17,7 @@ def _gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("peer", [0, 1])
+@pytest.mark.parametrize("peer", [0, 1, 2])
 def test_sharded_solve_equals_unsharded_on_all_visible_gpus(peer):
     n = min(_gpus(), 8)
     if n < 2:
@@ -26,7 +26,8 @@ def test_sharded_solve_equals_unsharded_on_all_visible_gpus(peer):
     n = 8 if n >= 8 else (4 if n >= 4 else 2)
     env = dict(os.environ, DPBA_SPEC_MULTI="1")
     if peer:
-        env["DPBA_PEER_EXCHANGE"] = "1"
+        env["DPBA_PEER_EXCHANGE"] = "1"  # 1: stand-alone mailbox kernel, scalars and system in two concurrent exchanges (the default)
+        env["DPBA_PEER_FUSED"] = "1" if peer == 2 else "0"  # 2: exchange fused into the producers / consumers
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(29540 + peer), os.path.join(ROOT, "tools", "multigpu_check.py")]
     run = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=400)

@@ -67,6 +67,8 @@ def main():
         eps_a, _ = h.get_state()
         capi.attach_peers(h, rank, world, dev)
         h.set_option("peer_exchange", 1)
+        if os.environ.get("DPBA_PEER_FUSED") is not None:  # 0: stand-alone mailbox kernel (and with it the split exchange)
+            h.set_option("peer_fused", int(os.environ["DPBA_PEER_FUSED"]))
         say("peers attached")
         shard = [sharding.shard_indices(len(f.idepth), rank, world) for f in win.frames]
         for i, f in enumerate(win.frames):
