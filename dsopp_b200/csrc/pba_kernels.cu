@@ -3095,8 +3095,18 @@ __device__ __forceinline__ void lm_energy_body(LmCtl* ctl, const LmOptionsDev* o
   __shared__ int s_accept;
   const int D = 8 * N, i = threadIdx.x;
   stamp(50);
+  // Thread 0 takes the decision.  It reads the loop state and the options ONCE, up front and in one batch of independent loads
+  // that overlaps the reductions below, keeps everything in registers, and only stores from then on: the decision used to be a
+  // chain of dependent L2 round trips (ctl->energy, ctl->iteration, scal[] just written by the same thread, ...).
+  LmCtl c;
+  LmOptionsDev o;
+  if (i == 0) {
+    c = *ctl;
+    o = *opt;
+  }
+  double sa = 0, sb = 0, sc = 0, sd = 0;  // (energy, n_valid, landmark state norm, landmark step norm) summed over everything
   if (e_part) {  // single-GPU: the second stage of the (energy, n) / norm reductions happens here, no extra launch
-    double a = 0, b = 0, c = 0, d = 0;
+    double a = 0, b = 0, cc = 0, d = 0;
     for (int k = i; k < n_e; k += 256) {
       size_t idx = k;
       if (from_core) {
@@ -3111,23 +3121,30 @@ __device__ __forceinline__ void lm_energy_body(LmCtl* ctl, const LmOptionsDev* o
     }
     for (int k = i; k < n_n; k += 256) {
       const double2 v = n_part[k];
-      c += v.x;
+      cc += v.x;
       d += v.y;
     }
-    a = block_sum_256(a, red);
-    b = block_sum_256(b, red);
+    sa = block_sum_256(a, red);
+    sb = block_sum_256(b, red);
     if (n_part) {
-      c = block_sum_256(c, red);
-      d = block_sum_256(d, red);
+      sc = block_sum_256(cc, red);
+      sd = block_sum_256(d, red);
     }
     if (i == 0) {
-      scal[0] = a;
-      scal[1] = b;
+      scal[0] = sa;
+      scal[1] = sb;
       if (n_part) {
-        scal[2] = c;
-        scal[3] = d;
+        scal[2] = sc;
+        scal[3] = sd;
       }
     }
+  } else if (i == 0) {  // several GPUs: the exchanged sums
+    sa = scal[0];
+    sb = scal[1];
+  }
+  if (i == 0 && !(e_part && n_part)) {  // norms that an earlier kernel (or the exchange) left in the scalar slots
+    sc = scal[2];
+    sd = scal[3];
   }
   stamp(51);
   if (i < D) s[i] = fr[i / 8].eps[i % 8] + fr[i / 8].step[i % 8];
@@ -3147,28 +3164,36 @@ __device__ __forceinline__ void lm_energy_body(LmCtl* ctl, const LmOptionsDev* o
   }
   const double prior_e = block_sum_256(acc, red);
   if (i == 0) {
-    const double E = opt->energy_marg + prior_e + scal[0];
-    const int n = (int)llrint(scal[1]);
+    const double E = o.energy_marg + prior_e + sa;
+    const int n = (int)llrint(sb);
     if (kind == pba::LM_ENERGY_INITIAL) {
       ctl->energy = E;
       ctl->n_valid = n;
-      if (n <= 0 || opt->max_it <= 0) ctl->done = 1;
+      if (n <= 0 || o.max_it <= 0) ctl->done = 1;
     } else if (kind == pba::LM_ENERGY_TRIAL) {
+      c.next_energy = E;
+      c.next_n = n;
       ctl->next_energy = E;
       ctl->next_n = n;
-      ctl->iterations_executed += 1;
+      ctl->iterations_executed = c.iterations_executed + 1;
       // landmark parts of the norms, accumulated by k_back_substitute (problem.hpp:377-382)
-      ctl->state_sq = scal[2];
-      ctl->step_sq = scal[3];
+      c.state_sq = sc;
+      c.step_sq = sd;
+      ctl->state_sq = sc;
+      ctl->step_sq = sd;
       if (n == 0) {
-        ctl->accept = -1;  // rejectStep(); break
+        c.accept = -1;  // rejectStep(); break
       } else {
-        if (fabs(ctl->energy - E) / ctl->energy < opt->ftol) ctl->converged = 1;  // before the accept test (Q7)
-        ctl->accept = (E < ctl->energy || (opt->force_accept && ctl->iteration < opt->min_it)) ? 1 : 0;
+        if (fabs(c.energy - E) / c.energy < o.ftol) {  // before the accept test (Q7)
+          c.converged = 1;
+          ctl->converged = 1;
+        }
+        c.accept = (E < c.energy || (o.force_accept && c.iteration < o.min_it)) ? 1 : 0;
       }
-      if (ctl->accept <= 0) ctl->relin = 1;  // speculative mode: the landmark fields now belong to a rejected state
+      ctl->accept = c.accept;
+      if (c.accept <= 0) ctl->relin = 1;  // speculative mode: the landmark fields now belong to a rejected state
       ctl->apply = 1;
-      s_accept = ctl->accept;
+      s_accept = c.accept;
     }
   }
   stamp(52);
@@ -3192,24 +3217,29 @@ __device__ __forceinline__ void lm_energy_body(LmCtl* ctl, const LmOptionsDev* o
   sp = block_sum_256(sp, red);
   if (i) return;
   if (accept > 0) {
-    const double stt = ctl->state_sq + st, spp = ctl->step_sq + sp;
+    const double stt = c.state_sq + st, spp = c.step_sq + sp;
     ctl->state_sq = stt;
     ctl->step_sq = spp;
-    if (spp < opt->ptol * (stt + opt->ptol)) ctl->converged = 1;
-    ctl->energy = ctl->next_energy;
-    ctl->n_valid = ctl->next_n;
-    ctl->lambda /= opt->dec;
+    if (spp < o.ptol * (stt + o.ptol)) {
+      c.converged = 1;
+      ctl->converged = 1;
+    }
+    ctl->energy = c.next_energy;
+    ctl->n_valid = c.next_n;
+    c.n_valid = c.next_n;
+    ctl->lambda = c.lambda / o.dec;
     ctl->system_valid = 0;
   } else {
-    if (accept < 0 || opt->force_accept) {
+    if (accept < 0 || o.force_accept) {
       ctl->done = 1;
       return;
     }
-    ctl->lambda *= opt->inc;
+    ctl->lambda = c.lambda * o.inc;
     ctl->system_valid = 1;
   }
-  ctl->iteration += 1;
-  if (ctl->iteration >= opt->max_it || ctl->converged || ctl->n_valid <= 0) ctl->done = 1;
+  c.iteration += 1;
+  ctl->iteration = c.iteration;
+  if (c.iteration >= o.max_it || c.converged || c.n_valid <= 0) ctl->done = 1;
 }
 
 __global__ void __launch_bounds__(256) k_lm_energy(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
