@@ -502,7 +502,12 @@ def run_ours(args):
     host_status = {(r, tt): pinned(win.statuses[(r, tt)][shard[r]]) for r in range(n) for tt in range(n) if tt != r}
     lm_kw = dict(sigma=SIGMA, ab_reg=AB_REG, fixed_reg=FIXED_REG, max_it=GN_ITERS, min_it=GN_ITERS, ftol=0.0, ptol=0.0,
                  force_accept=True, lambda0=1e-5)
-    step_io = host.WindowStep(h, host_frames, host_status, eps0, alloc=pinned_alloc, **lm_kw)
+    step_rec = host.WindowStep(h, host_frames, host_status, eps0, alloc=pinned_alloc, **lm_kw)
+    # the step a binding makes: the intensity plane of every keyframe (what PixelMap::data() holds, pixel_map.hpp:117) crosses
+    # PCIe, {I,dx,dy} is built on the device with the reference's gradient definition (bit-identical records,
+    # tests/test_gpu_parity.py::test_intensity_upload_builds_the_same_pixel_map) -- a third of the bytes of the record upload
+    host_frames_int = [dict(f_, image=pinned(np.ascontiguousarray(f_["image"][..., 0]))) for f_ in host_frames]
+    step_io = host.WindowStep(h, host_frames_int, host_status, eps0, alloc=pinned_alloc, **lm_kw)
     raw_frames = [pinned(np.clip(np.rint(f.image[..., 0]), 0, 255).astype(np.uint8)) for f in win.frames]
     step_raw = host.WindowStep(h, host_frames, host_status, eps0, alloc=pinned_alloc, raw_gray=raw_frames,
                                photometric_lut=np.arange(256, dtype=np.float32), **lm_kw)
@@ -527,8 +532,13 @@ def run_ours(args):
     # slot); the arrays handed to the caller are a subset of it
     mpp = max(len(s_) for s_ in shard)
     d2h = max(int(step_io.io.d2h_bytes), n * mpp * (5 * 4 + 16 + 1) + 2 * n * 16 * mpp + 2 * 8 * n * 8)
+    # the same step with the {I,dx,dy} RECORDS uploaded (the PixelMap's pixel-info storage, 12 bytes per pixel: round 1's and
+    # early round 2's `e2e`) -- informational
+    e2e_rec_ms = time_e2e(step_rec, min(args.steps, 10), 3)
+    e2e_rec = {"value": units_global * GN_ITERS / (e2e_rec_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_rec_ms,
+               "h2d_bytes_per_step": int(step_rec.io.h2d_bytes), "energy": float(step_rec.io.energy)}
     # the same step fed with RAW 8-bit frames (dpba_push_frame_raw: photometric table + gradients on the device,
-    # SURVEY 8f-4) -- informational; `e2e` stays the {I,dx,dy} upload the reference's pushFrame receives
+    # SURVEY 8f-4) -- informational
     e2e_raw_ms = time_e2e(step_raw, min(args.steps, 10), 3)
     e2e_raw_value = units_global * GN_ITERS / (e2e_raw_ms * 1e-3)
     h2d_raw = int(step_raw.io.h2d_bytes)
@@ -803,9 +813,12 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms_per_step,
-                "path": "dpbah_solve_window (C++ host library, one call per step): dpba_remove_frame / push_frame / "
-                        "set_landmarks / set_frame_statuses / set_state from pinned host buffers, dpba_first_estimate + "
-                        "dpba_solve_lm, dpba_get_state / get_landmarks / get_frame_statuses into host arrays"},
+                "path": "dpbah_solve_window (C++ host library, one call per step): dpba_remove_frame / push_frame_intensity "
+                        "(every keyframe's intensity plane -- PixelMap::data() -- from pinned host memory, {I,dx,dy} built on the "
+                        "device with the reference's gradient definition) / set_landmarks / set_frame_statuses / set_state, "
+                        "dpba_first_estimate + dpba_solve_lm, dpba_get_state / get_landmarks / get_frame_statuses into host arrays"},
+        "e2e_pixelinfo_records": dict(e2e_rec, path="as e2e, but the 12-byte {I,dx,dy} records of every keyframe are uploaded "
+                                                     "(dpba_push_frame): the e2e of round 1 and of the round-2 lines before this one"),
         "e2e_raw_frames": {"value": e2e_raw_value, "unit": UNIT, "ms_per_step": e2e_raw_ms, "h2d_bytes_per_step": h2d_raw,
                            "path": "as e2e, but dpba_push_frame_raw: 8-bit frames in, photometric table + {I,dx,dy} on the device"},
         "e2e_one_new_keyframe": e2e_sliding,

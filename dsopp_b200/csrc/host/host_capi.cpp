@@ -220,6 +220,10 @@ struct dpbah_window_io {
   // that the device time of the asynchronous uploads is attributed to its own phase (diagnostics only).
   double phase_ms[5];
   int32_t sync_phases;
+  // 0 / 3: `images` are H*W*3 {I,dx,dy} records (the PixelMap's pixel-info storage); 1: `images` are H*W intensity planes
+  // (what PixelMap::data() returns, pixel_map.hpp:117) and {I,dx,dy} is built on the device with the reference's gradient
+  // definition (dpba_push_frame_intensity) -- a third of the bytes cross PCIe
+  int32_t image_channels;
 };
 
 __attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dpbah_window_io* io, int width, int height) {
@@ -244,6 +248,10 @@ __attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dp
                                           io->T_w_lin + 12 * f, io->exposure[f], io->ab0 + 2 * f, io->intr + 4 * f,
                                           io->fixed[f]));
         h2d += (int64_t)npx + 1024 + (io->masks[f] ? (int64_t)npx : 0);
+      } else if (io->image_channels == 1) {
+        dpba_check(h, dpba_push_frame_intensity(h, io->frame_ids[f], io->images[f], io->masks[f], io->T_w_lin + 12 * f,
+                                                io->exposure[f], io->ab0 + 2 * f, io->intr + 4 * f, io->fixed[f]));
+        h2d += (int64_t)npx * 4 + (io->masks[f] ? (int64_t)npx : 0);
       } else {
         dpba_check(h, dpba_push_frame(h, io->frame_ids[f], io->images[f], io->masks[f], io->T_w_lin + 12 * f,
                                       io->exposure[f], io->ab0 + 2 * f, io->intr + 4 * f, io->fixed[f]));
@@ -303,9 +311,13 @@ __attribute__((visibility("default"))) int dpbah_solve_sliding(dpba_handle* h, d
     for (int k = 0; k + 1 < n; ++k) order[k] = order[k + 1];
     order[n - 1] = f;
     dpba_check(h, dpba_set_frame_flags(h, 0, 1, 0));  // the new oldest keyframe holds the gauge (frame 0 is the fixed one)
-    dpba_check(h, dpba_push_frame(h, io->frame_ids[f], io->images[f], io->masks[f], io->T_w_lin + 12 * f, io->exposure[f],
-                                  io->ab0 + 2 * f, io->intr + 4 * f, 0));
-    h2d += (int64_t)npx * 12 + (io->masks[f] ? (int64_t)npx : 0);
+    if (io->image_channels == 1)
+      dpba_check(h, dpba_push_frame_intensity(h, io->frame_ids[f], io->images[f], io->masks[f], io->T_w_lin + 12 * f,
+                                              io->exposure[f], io->ab0 + 2 * f, io->intr + 4 * f, 0));
+    else
+      dpba_check(h, dpba_push_frame(h, io->frame_ids[f], io->images[f], io->masks[f], io->T_w_lin + 12 * f, io->exposure[f],
+                                    io->ab0 + 2 * f, io->intr + 4 * f, 0));
+    h2d += (int64_t)npx * (io->image_channels == 1 ? 4 : 12) + (io->masks[f] ? (int64_t)npx : 0);
     const int slot = n - 1, m = io->n_landmarks[f];
     dpba_check(h, dpba_set_landmarks(h, slot, m, io->uv[f], io->idepth[f], io->patch[f], io->flags[f]));
     h2d += (int64_t)m * (8 + 4 + 32 + 1);

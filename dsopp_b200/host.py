@@ -117,13 +117,14 @@ class _WindowIOStruct(C.Structure):
                 ("inv_hdd_out", _P), ("rel_baseline_out", _P), ("flags_out", _P), ("n_inliers_out", _P),
                 ("statuses_out", _P), ("energy", C.c_double), ("iterations", C.c_int32), ("n_valid", C.c_int32),
                 ("converged", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("raw_gray", _P),
-                ("photometric_lut", _P), ("phase_ms", C.c_double * 5), ("sync_phases", C.c_int32)]
+                ("photometric_lut", _P), ("phase_ms", C.c_double * 5), ("sync_phases", C.c_int32), ("image_channels", C.c_int32)]
 
 
 class WindowStep:
     """dpbah_solve_window: one whole solver step from host buffers in ONE C++ call (push every keyframe, landmarks,
     statuses, state -> firstEstimateJacobians + device LM -> results back).  `frames`: list of dicts with the host arrays
-    (frame_id, image HxWx3 f32, mask HxW u8 or None, T_w_lin, exposure, ab0, intr, fixed, uv, idepth, patch, flags);
+    (frame_id, image HxWx3 f32 -- or HxW f32 intensity planes, what PixelMap::data() holds: the device then builds {I,dx,dy}
+    itself --, mask HxW u8 or None, T_w_lin, exposure, ab0, intr, fixed, uv, idepth, patch, flags);
     `statuses[(r, t)]`: uint8 per landmark of r.  Arrays are used in place -- pass page-locked ones to have them DMA'd
     without a staging copy.  Results land in `self.out` (eps, and per frame idepth / inv_hdd / rel_baseline / flags /
     n_inliers / statuses[t])."""
@@ -157,6 +158,8 @@ class WindowStep:
                 a = f[name]
                 assert a.dtype == dt and a.flags["C_CONTIGUOUS"], name
         k["p_images"] = ptr_array([f["image"] for f in frames])
+        planes = [f["image"].ndim == 2 for f in frames]
+        assert all(planes) or not any(planes), "all frames as {I,dx,dy} records or all as intensity planes"
         k["p_masks"] = ptr_array([f.get("mask") for f in frames])
         k["p_uv"] = ptr_array([f["uv"] for f in frames])
         k["p_idepth"] = ptr_array([f["idepth"] for f in frames])
@@ -184,6 +187,7 @@ class WindowStep:
         io.idepth_out, io.inv_hdd_out = cast(k["p_out_idepth"]), cast(k["p_out_inv_hdd"])
         io.rel_baseline_out, io.flags_out = cast(k["p_out_rel_baseline"]), cast(k["p_out_flags"])
         io.n_inliers_out, io.statuses_out = cast(k["p_out_n_inliers"]), cast(k["p_out_status"])
+        io.image_channels = 1 if all(planes) else 3
         if raw_gray is not None:  # 8-bit frames: dpba_push_frame_raw (photometric table + {I,dx,dy} on the device)
             k["raw"], k["lut"] = [_u8(g) for g in raw_gray], _f32(photometric_lut)
             k["p_raw"] = ptr_array(k["raw"])

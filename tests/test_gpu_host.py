@@ -270,4 +270,14 @@ def test_one_call_window_step_and_sliding_step():
     assert np.abs(step.out["eps"] - eps_ref).max() <= 1e-9
     # in between the same frames are solved with another keyframe fixed: same scene, energies of the same size
     assert all(abs(x - e_ref) <= 0.05 * abs(e_ref) for x in energies), (energies, e_ref)
+    # the same step fed with intensity planes (PixelMap::data()): {I,dx,dy} is built on the device, bit-identical records ->
+    # the very same solve, with a third of the image bytes crossing PCIe
+    planes = [dict(f, image=np.ascontiguousarray(f["image"][..., 0])) for f in frames]
+    step1 = host.WindowStep(h, planes, st, eps0)
+    e1, it1 = step1.run()
+    assert it1 == it_ref and abs(e1 - e_ref) <= 1e-12 * abs(e_ref)
+    assert np.array_equal(step1.out["eps"], eps_ref)
+    for i in range(n):
+        assert np.array_equal(step1.out["idepth"][i], id_ref[i])
+    assert step1.io.h2d_bytes < n * win.width * win.height * 6  # 4 bytes of intensity + 1 of mask per pixel, plus the landmarks
     h.close()

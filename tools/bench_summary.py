@@ -20,3 +20,5 @@ if d.get("config4_marginalisation"):
     print("config4", {k: v for k, v in d["config4_marginalisation"].items() if k in ("gpu_ms", "cpu_port_ms", "speedup", "prior_rel_diff_gpu_vs_cpu_port", "error")})
 if d.get("e2e_one_new_keyframe"):
     print("e2e one new keyframe per solve: %.1f M/s (%.2f ms/step), energy %.4f" % (d["e2e_one_new_keyframe"]["value"] / 1e6, d["e2e_one_new_keyframe"]["ms_per_step"], d["e2e_one_new_keyframe"]["energy"]))
+if d.get("e2e_pixelinfo_records"):
+    print("e2e with {I,dx,dy} records uploaded: %.1f M/s (%.2f ms/step)" % (d["e2e_pixelinfo_records"]["value"] / 1e6, d["e2e_pixelinfo_records"]["ms_per_step"]))
