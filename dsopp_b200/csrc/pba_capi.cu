@@ -557,7 +557,7 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
   cudaGetLastError();
   const float* src = image;
   const bool mask_all = !mask || memchr(mask, 0, npx) == nullptr;
-  if (channels == 3) {
+  if (channels == 3 || channels == 1) {  // records or intensity plane from the host: pipelined over the copy stream
     if (!pinned) {
       CK(cudaStreamSynchronize(h->copy_stream));  // the previous pageable push may still be reading stage_h
       memcpy(h->stage_h, image, npx * channels * sizeof(float));
@@ -567,14 +567,15 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
     h->stage_idx ^= 1;
     float* dst = sb ? h->stage_alt : h->stage;
     CK(cudaStreamWaitEvent(h->copy_stream, h->stage_free[sb], 0));  // its last reader (a pack kernel) has finished
-    CK(cudaMemcpyAsync(dst, src, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(dst, src, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
     CK(cudaEventRecord(h->stage_ready[sb], h->copy_stream));
     // the pack kernel overwrites a physical image slot: everything the main stream has queued so far (a solve that still
     // reads the slot's previous occupant) comes first
     CK(cudaEventRecord(h->main_mark, h->stream));
     CK(cudaStreamWaitEvent(h->pack_stream, h->main_mark, 0));
     CK(cudaStreamWaitEvent(h->pack_stream, h->stage_ready[sb], 0));
-    pba::launch_pack_image(dst, h->img[phys], (int)npx, W, h->pack_stream);
+    if (channels == 3) pba::launch_pack_image(dst, h->img[phys], (int)npx, W, h->pack_stream);
+    else pba::launch_pixelinfo(dst, h->img[phys], W, H, h->pack_stream);  // {I,dx,dy} from the intensity plane on the device
     CK(cudaEventRecord(h->stage_free[sb], h->pack_stream));
     CK(cudaEventRecord(h->img_done, h->pack_stream));
     h->img_pending = true;
