@@ -2308,6 +2308,7 @@ int dpba_debug_pixelinfo_ab(int32_t W, int32_t H, int32_t reps, double ms_per_la
   cudaMemset(a, 0xff, n * 32);
   cudaMemset(b, 0x7f, n * 32);
   int rc = DPBA_SUCCESS;
+  const bool tma_option = pba::get_pixelinfo_tma();  // the process-wide option is left as it was found
   for (int variant = 0; variant < 2 && rc == DPBA_SUCCESS; ++variant) {
     pba::set_pixelinfo_tma(false);
     for (int r = -3; r < reps; ++r) {  // three warm-up launches
@@ -2329,6 +2330,7 @@ int dpba_debug_pixelinfo_ab(int32_t W, int32_t H, int32_t reps, double ms_per_la
     for (size_t i = 0; i < n * 8; ++i) bad += ha[i] != hb[i];
     *mismatching_words = bad;
   }
+  pba::set_pixelinfo_tma(tma_option);
   cudaFree(I);
   cudaFree(a);
   cudaFree(b);

@@ -151,7 +151,8 @@ void launch_pack_image(const float* src3, float4* dst, int n_px, int W, cudaStre
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s);
 // image_tma.cu: the same records with the intensity tile staged by TMA; false = no tensor map could be made, nothing launched
 bool launch_pixelinfo_tma(const float* I, float4* dst, int W, int H, cudaStream_t s);
-void set_pixelinfo_tma(bool on);  // option "pixelinfo_tma": launch_pixelinfo routes through the TMA variant
+void set_pixelinfo_tma(bool on);
+bool get_pixelinfo_tma();  // option "pixelinfo_tma": launch_pixelinfo routes through the TMA variant
 void launch_photometric(const uint8_t* gray, const float* lut, const uint8_t* vignetting, float max_v, float* out, int n,
                         cudaStream_t s);
 void launch_downscale(const float* src, float* dst, int W, int H, cudaStream_t s);

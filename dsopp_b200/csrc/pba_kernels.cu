@@ -3788,6 +3788,7 @@ void launch_pixelinfo3(const float* I, float* dst, int W, int H, cudaStream_t s)
 // kernel stays the default; option "pixelinfo_tma" selects the TMA variant.
 static bool g_pixelinfo_tma = false;
 void set_pixelinfo_tma(bool on) { g_pixelinfo_tma = on; }
+bool get_pixelinfo_tma() { return g_pixelinfo_tma; }
 void launch_pixelinfo(const float* I, float4* dst, int W, int H, cudaStream_t s) {
   if (g_pixelinfo_tma && launch_pixelinfo_tma(I, dst, W, H, s)) return;
   dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
