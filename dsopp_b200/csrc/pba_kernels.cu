@@ -3332,7 +3332,7 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
                                              const double* __restrict__ bp, const double* __restrict__ Hs,
                                              const double* __restrict__ bs, const double* __restrict__ Hmarg,
                                              const double* __restrict__ bmarg, double* __restrict__ step_dev) {
-  if (ctl->done) return;
+  const int done = ctl->done;  // consulted after the loads below have been issued: its round trip overlaps theirs
   constexpr int LD = DP + 1;   // row stride of S (odd: conflict-free column walks)
   constexpr int LPS = 9;       // row stride of Lp
   extern __shared__ double sh[];
@@ -3344,7 +3344,39 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
   double* st = pre + DP;                // [DP] state eps, later the solution
   double* hm = st + DP;                 // [DP] H_marg * state
   const double lambda = ctl->lambda, ks = -1.0 / (1.0 + lambda);
-  if (tid < DP) st[tid] = tid < D ? fr[tid / 8].eps[tid % 8] : 0.0;
+  // Every global input of the fill is requested UP FRONT, in one batch of independent loads: the first 16 x 256 entries of
+  // (H_pose, H_schur[, H_marg]) -- the whole 64 x 64 system of an 8-keyframe window --, the diagonal, the right-hand sides,
+  // the state and the options.  The fill used to walk five dependent L2 round trips (state, diagonal, two trips of the
+  // triangle, right-hand side) and took 10.5 k of the kernel's 40 k cycles (tools/lm_stamps.py).
+  constexpr int PRE = 16;
+  double hp0[PRE], hs0[PRE], hg0[PRE];
+#pragma unroll
+  for (int q = 0; q < PRE; ++q) {
+    const int idx = q * 256 + tid;
+    const bool in = idx < D * D;
+    hp0[q] = in ? Hp[idx] : 0.0;
+    hs0[q] = in ? Hs[idx] : 0.0;
+    hg0[q] = (in && Hmarg) ? Hmarg[idx] : 0.0;
+  }
+  const double stv = (tid < D) ? fr[tid / 8].eps[tid % 8] : 0.0;
+  double dg_hp = 0, dg_hs = 0, dg_hm = 0, v_bp = 0, v_bs = 0, v_bm = 0, v_ab0 = 0;
+  int v_fixed = 0;
+  if (tid < D) {
+    const size_t idx = (size_t)tid * D + tid;
+    dg_hp = Hp[idx];
+    dg_hs = Hs[idx];
+    if (Hmarg) {
+      dg_hm = Hmarg[idx];
+      v_bm = bmarg[tid];
+    }
+    v_bp = bp[tid];
+    v_bs = bs[tid];
+    v_fixed = fixed[tid / 8];
+    if (tid % 8 >= 6) v_ab0 = fr[tid / 8].ab0[tid % 8 - 6];
+  }
+  const double fixed_reg = opt->fixed_reg, ab_reg0 = opt->ab_reg[0], ab_reg1 = opt->ab_reg[1];
+  if (done) return;
+  if (tid < DP) st[tid] = stv;
   __syncthreads();
   if (Hmarg) {  // warp per row, lanes along the row: coalesced
     const int warp = tid >> 5, lane = tid & 31;
@@ -3358,20 +3390,25 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
   }
   // unscaled system:  H_pose(+priors, +lambda on the diagonal) + H_marg - H_schur / (1 + lambda)
   if (tid < D) {
-    const size_t idx = (size_t)tid * D + tid;
-    const int f = tid / 8, k = tid % 8;
-    double hp = Hp[idx];
-    if (fixed[f]) hp += opt->fixed_reg;
-    else if (k >= 6) hp += opt->ab_reg[k - 6];
+    const int k = tid % 8;
+    double hp = dg_hp;
+    if (v_fixed) hp += fixed_reg;
+    else if (k >= 6) hp += (k == 6 ? ab_reg0 : ab_reg1);
     hp += hp * lambda;  // H.diagonal() += system_pose.H.diagonal() * lambda (prior included)
-    const double v = hp + (Hmarg ? Hmarg[idx] : 0.0) + ks * Hs[idx];
+    const double v = hp + dg_hm + ks * dg_hs;
     dinv[tid] = v;                        // parked here until the fill below
     pre[tid] = 1.0 / sqrt(v + 10.0);      // jacobiPreconditioner, +10 floor
   }
   __syncthreads();
-  // fill the lower triangle: 8 independent (Hp, Hs[, Hmarg]) loads in flight per thread per trip, so the fill costs
-  // a few L2 round trips instead of one per element
-  for (int base = 0; base < D * D; base += 256 * 8) {
+  // fill the lower triangle from the registers ...
+#pragma unroll
+  for (int q = 0; q < PRE; ++q) {
+    const int idx = q * 256 + tid;
+    const int i = idx / D, j = idx - i * D;
+    if (idx < D * D && j <= i) S[i * LD + j] = (i == j ? dinv[i] : hp0[q] + hg0[q] + ks * hs0[q]) * pre[i] * pre[j];
+  }
+  // ... and, for windows of more than 8 keyframes, the rest of it in trips of 8 independent loads per thread
+  for (int base = PRE * 256; base < D * D; base += 256 * 8) {
     double hp[8], hs[8], hg[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -3389,11 +3426,11 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
     }
   }
   if (tid < D) {
-    const int f = tid / 8, k = tid % 8;
-    double b = bp[tid] + ks * bs[tid];
-    if (fixed[f]) b += opt->fixed_reg * st[tid];
-    else if (k >= 6) b += opt->ab_reg[k - 6] * (fr[f].ab0[k - 6] + st[tid]);
-    if (Hmarg) b += bmarg[tid] + hm[tid];
+    const int k = tid % 8;
+    double b = v_bp + ks * v_bs;
+    if (v_fixed) b += fixed_reg * stv;
+    else if (k >= 6) b += (k == 6 ? ab_reg0 : ab_reg1) * (v_ab0 + stv);
+    if (Hmarg) b += v_bm + hm[tid];
     S[D * LD + tid] = b * pre[tid];
   }
   const int ty = tid >> 4, tx = tid & 15;
@@ -3504,6 +3541,7 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
                                                  const double* __restrict__ bmarg, double* __restrict__ step_dev,
                                                  int peer_expected, double* sys_out, int n_sys) {
   KStamp kstamp_(5);
+  stamp(22);
   if (peer_expected && !ctl->done) {
     // fused exchange: [H_pp | b_p | H_s | b_s] of every rank, summed in rank order into the block lm_step_body reads
     const unsigned epoch = peer_epoch();
@@ -3514,6 +3552,7 @@ __global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptio
     __syncthreads();
   }
   lm_step_body<DP>(ctl, opt, fr, fixed, N, Hp, bp, Hs, bs, Hmarg, bmarg, step_dev);
+  stamp(23);
 }
 
 // Per-pair constants by ONE CTA: thread per frame for the exponentials, then thread per ORDERED PAIR (same arithmetic,

@@ -19,6 +19,7 @@ names.update({18: "factorised", 20: "step written", 21: "pair constants written"
 print("k_lm_solve energy body (last launch): sums", out[51] - out[50], "priors+decision", out[52] - out[51], " kernel start->body", out[50] - out[0])
 print("k_reduce_system assemble block 0: core reduction", out[55] - out[54], "products", out[56] - out[55], "barrier", out[57] - out[56], "write", out[58] - out[57], "(merged_tail only)")
 print("k_reduce_system schur block: sums", out[60] - out[59], "barrier", out[61] - out[60], "final", out[62] - out[61], "(merged_tail only)")
+print("k_lm_step [cycles]: entry -> system filled", out[2] - out[22], "| LDL^T", out[18] - out[2], "| back substitution + step written", out[23] - out[18], "| total", out[23] - out[22])
 print("block step 0: loads + barrier + diagonal block + row recurrence + stores", out[13] - out[3], "barrier", out[14] - out[13], "trailing update", out[4] - out[14])
 f = out[30:42] - out[30]
 print("k_linearize_fused2, CTA (0,0) thread 0 [cycles from kernel entry]: prologue barrier", f[1], "| group 0: pass 1 done", f[2], "pass 2 done", f[3], "warp reduce done", f[4],
