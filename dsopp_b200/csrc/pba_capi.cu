@@ -2222,6 +2222,11 @@ int dpba_set_option(dpba_handle* h, const char* name, int64_t value) {
     h->lm_graph_key.clear();
     return DPBA_SUCCESS;
   }
+  if (!strcmp(name, "fused_reduce_once")) {  // process-wide A/B switch: the sweep's per-group warp reductions folded into one per CTA
+    pba::set_fused_reduce_once((int)value);
+    h->lm_graph_key.clear();
+    return DPBA_SUCCESS;
+  }
   if (!strcmp(name, "fused_lpb_max")) {  // process-wide tuning switch: cap of the fused sweep's landmarks per CTA (32..256)
     pba::set_fused_lpb_max((int)value);
     h->lm_graph_key.clear();

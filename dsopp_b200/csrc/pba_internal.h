@@ -211,6 +211,7 @@ void set_pdl(bool on);
 void set_fused_prefetch(bool on);
 void set_fused_epilogue(int v);
 void set_fused_lpb_max(int v);
+void set_fused_reduce_once(int v);
 void set_fused2_min_blocks(int b);
 
 // ---- peer-memory exchange (peer_exchange.cu): one-shot all-reduce over NVLink mailboxes -------------------------------

@@ -1125,6 +1125,10 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
   float* bd_w = hdd_w + lpb * nwarps;                                // [lpb][nwarps] per-target b_d terms
   float* ref_w = bd_w + lpb * nwarps;                                // epi: [nwarps][lpb][8] per-target B_t^T p_t
   int* fl_s = reinterpret_cast<int*>(ref_w + (size_t)nwarps * lpb * 8);  // epi: [lpb] landmark flags (-1: past the end)
+  // epi & 2: the 44 + 2 per-lane sums of the landmark groups are accumulated in shared memory ([warp][46][32], conflict-free)
+  // and reduced over the lanes ONCE per CTA instead of once per group (47 shuffles and ~200 selects each)
+  float* racc = reinterpret_cast<float*>(fl_s + lpb);
+  const bool ronce = (epi & 2) && lpb > 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = warp + (warp >= f);
   const int lm_base = lm_index(w, f, 0);
@@ -1350,7 +1354,20 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
     }
     // warp-wide transpose-reduce of the group's 44 sums + (energy, n): 24+12+6+3+2 = 47 shuffles; every lane ends up with
     // (at most) two entries of the 48-vector and adds them to its running totals
-    {
+    if (ronce) {
+      float* my = racc + (size_t)warp * (46 * 32) + lane;
+      if (g0 == 0) {
+#pragma unroll
+        for (int k = 0; k < 44; ++k) my[k * 32] = acc[k];
+        my[44 * 32] = e_add;
+        my[45 * 32] = n_add;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 44; ++k) my[k * 32] += acc[k];
+        my[44 * 32] += e_add;
+        my[45 * 32] += n_add;
+      }
+    } else {
       float v48[PBA_CORE], v24[24], v12[12], v6[6], v3[3], v2[2];
 #pragma unroll
       for (int k = 0; k < PBA_CORE; ++k) v48[k] = k < 44 ? acc[k] : (k == 44 ? e_add : (k == 45 ? n_add : 0.f));
@@ -1370,8 +1387,25 @@ __global__ void __launch_bounds__(32 * NWMAX, MINB)
     // this warp's 48 partial sums go to its own slot [host frame][chunk][target warp][48]: plain coalesced stores, summed
     // over the chunks in fp64 by k_core_reduce (no atomics, deterministic)
     float* dst = core_part + (((size_t)f * gridDim.x + blockIdx.x) * nwarps + warp) * PBA_CORE;
-    dst[off] = tot0;
-    if (!(lane & 1)) dst[off + 1] = tot1;
+    if (ronce) {
+      // lane L sums rows L and L + 32 of its warp's [46][32] block over the 32 columns, starting at column L (every lane on its
+      // own bank); rows 46, 47 of the record stay zero
+      __syncwarp();
+      const float* base = racc + (size_t)warp * (46 * 32);
+      const bool two = lane + 32 < 46;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const int c = (j + lane) & 31;
+        s0 += base[lane * 32 + c];
+        if (two) s1 += base[(lane + 32) * 32 + c];
+      }
+      dst[lane] = s0;
+      if (lane + 32 < PBA_CORE) dst[lane + 32] = two ? s1 : 0.f;
+    } else {
+      dst[off] = tot0;
+      if (!(lane & 1)) dst[off + 1] = tot1;
+    }
   }
   __syncthreads();
   stamp(36);
@@ -3903,6 +3937,8 @@ int g_fused2_minb = 2;  // A/B (option "fused2_min_blocks"): 3 = the second-gene
 void set_fused2_min_blocks(int b) { g_fused2_minb = b == 3 ? 3 : 2; }
 int g_fused_lpb_max = 256;  // largest landmark chunk per CTA the launcher may pick (option "fused_lpb_max")
 void set_fused_lpb_max(int v) { g_fused_lpb_max = v < 32 ? 32 : (v > 256 ? 256 : (v / 32) * 32); }
+int g_fused_reduce_once = 0;  // A/B (option "fused_reduce_once"): the per-lane sums of the landmark groups meet in shared memory and are reduced once per CTA -- measured slower (32.6 against 30.6 us; 268 against 213 us at 1.12 M units): 41 KB more shared memory per CTA comes out of L1
+void set_fused_reduce_once(int v) { g_fused_reduce_once = v != 0; }
 int g_fused_epilogue = 1;  // second-generation epilogue of k_linearize_fused2 (option "fused_epilogue", 0 = the first generation's)
 void set_fused_epilogue(int v) { g_fused_epilogue = v != 0; }
 bool g_fused_prefetch = false;  // L1 prefetch of the next group's image taps: measured 42.6 us against 39.1 us without (issue-bound kernel), kept as an A/B switch (option "fused_prefetch")
@@ -3961,7 +3997,8 @@ static FusedShape launch_linearize_fused2(const WindowDev& w, float sigma, int h
     // with room to spare for the carve-out steps (measured: 106 KB per CTA -- lpb 192 with the second-generation epilogue --
     // ran one CTA per SM and the 1.12 M-unit sweep took 1.6x as long)
     const size_t need = (size_t)(N - 1) * sizeof(PairConst) + ((size_t)cand * (D + 2 + 2 * (N - 1)) + 3) * sizeof(float) +
-                        (g_fused_epilogue ? (size_t)cand * (8 * (N - 1) + 1) * sizeof(float) : 0);
+                        (g_fused_epilogue ? (size_t)cand * (8 * (N - 1) + 1) * sizeof(float) : 0) +
+                        ((g_fused_epilogue && g_fused_reduce_once) ? (size_t)(N - 1) * 46 * 32 * sizeof(float) : 0);
     if (cand > 32 && need > 96 * 1024) break;
     const long blocks = (long)((m + cand - 1) / cand) * N;
     const double waves = (double)((blocks + resident - 1) / resident);
@@ -3971,9 +4008,10 @@ static FusedShape launch_linearize_fused2(const WindowDev& w, float sigma, int h
       lpb = cand;
     }
   }
-  const int epi = g_fused_epilogue;
+  const int epi = g_fused_epilogue ? (1 | (g_fused_reduce_once ? 2 : 0)) : 0;
   const size_t smem = (size_t)(N - 1) * sizeof(PairConst) + ((size_t)lpb * (D + 2 + 2 * (N - 1)) + 3) * sizeof(float) +
-                      (epi ? (size_t)lpb * (8 * (N - 1) + 1) * sizeof(float) : 0);
+                      (epi ? (size_t)lpb * (8 * (N - 1) + 1) * sizeof(float) : 0) +
+                      ((epi & 2) ? (size_t)(N - 1) * 46 * 32 * sizeof(float) : 0);
   dim3 g((m + lpb - 1) / lpb, N);
   const int threads = 32 * (N - 1);
   const int fold = fold_step != nullptr && ctl != nullptr;
