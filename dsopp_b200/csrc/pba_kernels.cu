@@ -2911,76 +2911,95 @@ __device__ void make_proj(const SE3d& T, const double* ir, const double* it, flo
   }
 }
 
-__global__ void __launch_bounds__(64) k_pair_setup(const FrameParams* __restrict__ fr, int N,
-                                                    PairConst* __restrict__ pairs, PairAssemble* __restrict__ pasm) {
+__global__ void __launch_bounds__(128) k_pair_setup(const FrameParams* __restrict__ fr, int N,
+                                                     PairConst* __restrict__ pairs, PairAssemble* __restrict__ pasm) {
   KStamp kstamp_(7);
-  // one CTA per reference frame r.  phase 1 (thread per frame): exp(+eps) of r, exp(-eps) and T_lin^-1 of every
-  // target; phase 2 (thread per target): the pair's constants, staged in shared memory; phase 3: coalesced write.
+  // one CTA per reference frame r, FOUR warps = four roles, lane = frame.  The kernel sits on the critical path of an LM
+  // iteration (after the LM step, before the sweep) and is a chain of dependent fp64 operations: 1.1 k instructions per warp
+  // at ~10 cycles each when one thread does everything for its pair (profiles/r02c_k_pair_setup.md).  The work of a pair is
+  // therefore split by OUTPUT over the warps -- each recomputes the cheap products it needs -- so that the roles run on four
+  // schedulers at once; every output is computed by the same sequence of operations as before.
+  //   phase 1  warp 0: exp(-eps) of every frame;  warp 1: T_lin^-1 and the affine state of every frame;
+  //            warp 2: exp(+eps) and T_lin of r
+  //   phase 2  warp 0: t_t_r -> transform_unproject_ / reproject_ / translation_ at the current state;
+  //            warp 1: t_t_r -> Adj at the current state;  warp 2: t_t_r0 -> the same at the linearisation point, scalars;
+  //            warp 3: t_t_r0 -> Adj at the linearisation point
+  //   phase 3  coalesced write of the staged records
   __shared__ SE3d s_et[PBA_MAXF], s_ti[PBA_MAXF];
   __shared__ SE3d s_er, s_tl;
   __shared__ double s_a[PBA_MAXF], s_b[PBA_MAXF];
   __shared__ PairConst s_pc[PBA_MAXF];
   __shared__ PairAssemble s_pa[PBA_MAXF];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, role = tid >> 5, lane = tid & 31;
   const int r = blockIdx.x;
-  if (tid < N) {
-    const FrameParams& F = fr[tid];
-    double e[6];
-    for (int k = 0; k < 6; ++k) e[k] = F.eps[k] + F.step[k];
-    se3_exp(e, -1.0, s_et[tid]);
-    SE3d T;
-    for (int i = 0; i < 3; ++i) {
-      for (int j = 0; j < 3; ++j) T.R[i * 3 + j] = F.T_lin[i * 4 + j];
-      T.t[i] = F.T_lin[i * 4 + 3];
+  if (lane < N) {
+    const FrameParams& F = fr[lane];
+    if (role == 0 || (role == 2 && lane == r)) {
+      double e[6];
+      for (int k = 0; k < 6; ++k) e[k] = F.eps[k] + F.step[k];
+      if (role == 0) se3_exp(e, -1.0, s_et[lane]);
+      else se3_exp(e, 1.0, s_er);
     }
-    se3_inv(T, s_ti[tid]);
-    s_a[tid] = F.ab0[0] + F.eps[6] + F.step[6];
-    s_b[tid] = F.ab0[1] + F.eps[7] + F.step[7];
-    if (tid == r) {
-      se3_exp(e, 1.0, s_er);
-      s_tl = T;
+    if (role == 1 || (role == 2 && lane == r)) {
+      SE3d T;
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) T.R[i * 3 + j] = F.T_lin[i * 4 + j];
+        T.t[i] = F.T_lin[i * 4 + 3];
+      }
+      if (role == 1) {
+        se3_inv(T, s_ti[lane]);
+        s_a[lane] = F.ab0[0] + F.eps[6] + F.step[6];
+        s_b[lane] = F.ab0[1] + F.eps[7] + F.step[7];
+      } else {
+        s_tl = T;
+      }
     }
   }
   __syncthreads();
-  const int t = tid;
+  const int t = lane;
   if (t < N && t != r) {
     const FrameParams& R = fr[r];
     const FrameParams& T = fr[t];
-    SE3d T0, tmp, Tc;
-    se3_mul(s_ti[t], s_tl, T0);  // t_t_r0 (evaluate_jacobians.hpp:47-48)
-    se3_mul(T0, s_er, tmp);
-    se3_mul(s_et[t], tmp, Tc);   // t_t_r = exp(-eps_t) T0 exp(eps_r)  (:49)
     PairConst& pc = s_pc[t];
     PairAssemble& pa = s_pa[t];
-    make_proj(Tc, R.intr, T.intr, pc.M, pc.A);
-    make_proj(T0, R.intr, T.intr, pc.M0, nullptr);
-    for (int i = 0; i < 3; ++i) {
-      pc.tr[i] = (float)Tc.t[i];
-      pc.t0[i] = (float)T0.t[i];
+    SE3d T0;
+    se3_mul(s_ti[t], s_tl, T0);  // t_t_r0 (evaluate_jacobians.hpp:47-48)
+    if (role < 2) {
+      SE3d tmp, Tc;
+      se3_mul(T0, s_er, tmp);
+      se3_mul(s_et[t], tmp, Tc);   // t_t_r = exp(-eps_t) T0 exp(eps_r)  (:49)
+      if (role == 0) {
+        make_proj(Tc, R.intr, T.intr, pc.M, pc.A);
+        for (int i = 0; i < 3; ++i) pc.tr[i] = (float)Tc.t[i];
+        pc.tr[3] = 0.f;
+      } else {
+        se3_adj(Tc, pa.adj_cur);
+        for (int i = 0; i < 36; ++i) pc.adj[i] = (float)pa.adj_cur[i];
+      }
+    } else if (role == 2) {
+      make_proj(T0, R.intr, T.intr, pc.M0, nullptr);
+      for (int i = 0; i < 3; ++i) pc.t0[i] = (float)T0.t[i];
+      pc.t0[3] = 0.f;
+      const double ratio = T.exposure / R.exposure;
+      pa.s = ratio * exp(s_a[t] - s_a[r]);
+      pa.s0 = ratio * exp(T.ab0[0] - R.ab0[0]);
+      const int last = (r == N - 1) ? N - 2 : N - 1;  // last target in deque order (quirk Q1)
+      const double s0_last = (fr[last].exposure / R.exposure) * exp(fr[last].ab0[0] - R.ab0[0]);
+      pc.s = (float)pa.s;
+      pc.s0 = (float)pa.s0;
+      pc.s0_last = (float)s0_last;
+      pc.b_t = (float)s_b[t];
+      pc.b_r = (float)s_b[r];
+      pc.b_r0 = (float)R.ab0[1];
+      pc.fx_t = (float)T.intr[0];
+      pc.fy_t = (float)T.intr[1];
+      pc.cx_t = (float)T.intr[2];
+      pc.cy_t = (float)T.intr[3];
+      pc.pad0 = pc.pad1 = 0.f;
+    } else {
+      se3_adj(T0, pa.adj_fej);
+      for (int i = 0; i < 36; ++i) pc.adj0[i] = (float)pa.adj_fej[i];
     }
-    pc.tr[3] = pc.t0[3] = 0.f;
-    se3_adj(Tc, pa.adj_cur);
-    se3_adj(T0, pa.adj_fej);
-    for (int i = 0; i < 36; ++i) {
-      pc.adj[i] = (float)pa.adj_cur[i];
-      pc.adj0[i] = (float)pa.adj_fej[i];
-    }
-    const double ratio = T.exposure / R.exposure;
-    pa.s = ratio * exp(s_a[t] - s_a[r]);
-    pa.s0 = ratio * exp(T.ab0[0] - R.ab0[0]);
-    const int last = (r == N - 1) ? N - 2 : N - 1;  // last target in deque order (quirk Q1)
-    const double s0_last = (fr[last].exposure / R.exposure) * exp(fr[last].ab0[0] - R.ab0[0]);
-    pc.s = (float)pa.s;
-    pc.s0 = (float)pa.s0;
-    pc.s0_last = (float)s0_last;
-    pc.b_t = (float)s_b[t];
-    pc.b_r = (float)s_b[r];
-    pc.b_r0 = (float)R.ab0[1];
-    pc.fx_t = (float)T.intr[0];
-    pc.fy_t = (float)T.intr[1];
-    pc.cx_t = (float)T.intr[2];
-    pc.cy_t = (float)T.intr[3];
-    pc.pad0 = pc.pad1 = 0.f;
   }
   __syncthreads();
   for (int tt = 0; tt < N; ++tt) {
@@ -3824,7 +3843,7 @@ void launch_reduce_system(const WindowDev& w, int fej, ReduceBuf rb, FusedShape 
 
 void launch_pair_setup(const FrameParams* frames, int n_frames, PairConst* pairs, PairAssemble* pasm, cudaStream_t s) {
   ++g_launches;
-  k_pair_setup<<<n_frames, 64, 0, s>>>(frames, n_frames, pairs, pasm);
+  k_pair_setup<<<n_frames, 128, 0, s>>>(frames, n_frames, pairs, pasm);
 }
 
 void launch_clear_frame_rows(uint8_t* status, uint8_t* cand, uint8_t* jac_valid, float* energy, int phys, int mp,
