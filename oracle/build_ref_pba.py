@@ -35,7 +35,7 @@ OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libdsopp_ref_pba.so")
 STUBS = os.path.join(HERE, "ref_stubs_full")
 SHIMS = [os.path.join(HERE, "ref_shims", "ref_pba.cpp"), os.path.join(HERE, "ref_shims", "ref_link_stubs.cpp"),
-         os.path.join(HERE, "ref_shims", "ref_pose_alignment.cpp")]
+         os.path.join(HERE, "ref_shims", "ref_pose_alignment.cpp"), os.path.join(HERE, "ref_shims", "ref_stub_checks.cpp")]
 # The coarse-tracker aligner's algorithm is a class in an anonymous namespace of this file (lines 24-242); the members of
 # EigenPoseAlignment that follow need the track subsystem.  The compiler is given the file's own lines up to the end of that
 # namespace through a temporary copy OUTSIDE the repository, removed after the build (oracle/ref_shims/ref_pose_alignment.cpp).
