@@ -15,8 +15,9 @@
 // tests/emu can run them on the CPU.  fp32 with float atomics for the rare collisions of two
 // landmarks on one pixel (order of two or three additions: last-bit differences, stated in the test).
 //
-// STATUS: written in round 1 after the GPU budget was spent -- compiled for sm_100a, NOT yet run on hardware; new entry
-// point, nothing else calls it.  Oracle: oracle/depth_map_oracle.py; GPU comparison: tests/test_gpu_device_paths.py.
+// Oracle: oracle/depth_map_oracle.py, pinned against the reference's own create_depth_maps.cpp (tests/
+// test_reference_tracker.py).  GPU comparison: tests/test_gpu_device_paths.py (oracle) and tests/test_reference_tracker.py
+// (the reference's golden maps); the per-thread bodies also run on the CPU in tests/test_kernel_emulation.py.
 #include <cuda_runtime.h>
 
 #include <cstdint>

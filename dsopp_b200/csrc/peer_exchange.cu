@@ -22,9 +22,9 @@
 // enough: all exchange kernels of a rank run in stream order, so rank A can only reach exchange k+2 after rank B
 // pushed k+1, which B does after its kernel of exchange k (the reader of parity k&1) has completed.
 //
-// STATUS: written in round 1 after the GPU budget was spent -- compiled for sm_100a, NOT yet run on hardware.  It is
-// off unless dpba_peer_attach() succeeded AND the option "peer_exchange" is set; tools/multigpu_check.py
-// (DPBA_PEER_EXCHANGE=1) compares it with the NCCL path on the same handle.  The steps live in peer_exchange_body.h and
+// STATUS: runs on B200 since round 2 (2, 4 and 8 GPUs: tests/test_gpu_multi.py, profiles/r02_bench_g*.json); bench.py
+// uses it by default for world > 1.  It is off unless dpba_peer_attach() succeeded AND the option "peer_exchange" is
+// set; tools/multigpu_check.py (DPBA_PEER_EXCHANGE=1) compares it with the NCCL path on the same handle.  The steps live in peer_exchange_body.h and
 // run on the CPU with real threads (one per CTA and rank, C++11 atomics for the PTX accesses) in
 // tests/test_kernel_emulation.py.
 #include <cuda_runtime.h>

@@ -1,7 +1,10 @@
 """CPU oracle (NumPy, float64) of the immature-landmark activation refine.
 
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED for raw values (the reference cannot be built here, no golden vectors);
-pinned by property tests (tests/test_activation_oracle.py).
+TEST INFRASTRUCTURE ONLY.  PARITY PINNED: lines 122-316 of the reference file below compile here from their own source
+(oracle/build_ref_tracker.py: the class, optimizeImmatureLandmark, the reference's LM driver, reprojector, PixelMap,
+CameraMask; only the track containers are stand-in records) and this restatement takes the same activate / delete decision
+on every candidate and the same inverse depth at 1e-9 (tests/test_reference_tracker.py, tests/golden/ref_tracker.npz);
+property tests in tests/test_activation_oracle.py.
 
 Restates src/tracker/landmarks_activator/src/landmarks_activator.cpp (paths relative to /root/reference/):
   LandmarkActivationProblem      :122-283   1-D Levenberg-Marquardt on the inverse depth of ONE immature landmark over all

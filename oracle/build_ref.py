@@ -1,8 +1,8 @@
 """Recipe for oracle/_ref: the parts of the REFERENCE ITSELF that compile here from their own sources.
 
 Almost all of the reference's hot path needs Eigen, Sophus, TBB and glog (absent, no network), so the path as a whole
-cannot be built and the restatements in oracle/ stay "parity unpinned" for it.  Two files are the
-exception -- they use nothing but the standard library and AVX2 intrinsics, apart from including common/settings.hpp,
+cannot be built by its own build system; oracle/build_ref_pba.py and oracle/build_ref_tracker.py compile it against
+stand-ins of those libraries instead.  Two files need no stand-in at all -- they use nothing but the standard library and AVX2 intrinsics, apart from including common/settings.hpp,
 whose only third-party line is a type alias on Eigen::aligned_allocator that neither file uses (oracle/ref_stubs/Eigen/Core
 supplies that one name):
 

@@ -15,6 +15,7 @@ code; the stand-ins only supply matrix products, quaternion algebra and containe
 Reference sources compiled (never copied):
   src/energy/camera_model/src/camera_model_base.cpp
   src/features/src/pixel_map.cpp, src/features/src/calculate_pixelinfo.cpp
+  src/features/src/photometrically_corrected_image.cpp, src/features/src/pixel_data_frame.cpp (+ downscale_image.hpp)
   src/sensors/camera_calibration/src/camera_mask.cpp
   src/energy/problems/src/normal_linear_system.cpp
   src/energy/problems/src/eigen_pose_alignment.cpp, lines 1-242 (class PoseAlignerProblem; see POSE_ALIGNMENT_SRC below)
@@ -35,7 +36,8 @@ OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libdsopp_ref_pba.so")
 STUBS = os.path.join(HERE, "ref_stubs_full")
 SHIMS = [os.path.join(HERE, "ref_shims", "ref_pba.cpp"), os.path.join(HERE, "ref_shims", "ref_link_stubs.cpp"),
-         os.path.join(HERE, "ref_shims", "ref_pose_alignment.cpp"), os.path.join(HERE, "ref_shims", "ref_stub_checks.cpp")]
+         os.path.join(HERE, "ref_shims", "ref_pose_alignment.cpp"), os.path.join(HERE, "ref_shims", "ref_stub_checks.cpp"),
+         os.path.join(HERE, "ref_shims", "ref_pyramid.cpp")]
 # The coarse-tracker aligner's algorithm is a class in an anonymous namespace of this file (lines 24-242); the members of
 # EigenPoseAlignment that follow need the track subsystem.  The compiler is given the file's own lines up to the end of that
 # namespace through a temporary copy OUTSIDE the repository, removed after the build (oracle/ref_shims/ref_pose_alignment.cpp).
@@ -47,6 +49,8 @@ REF_SOURCES = [os.path.join(SRC, p) for p in (
     "energy/camera_model/src/camera_model_base.cpp",
     "features/src/pixel_map.cpp",
     "features/src/calculate_pixelinfo.cpp",
+    "features/src/photometrically_corrected_image.cpp",
+    "features/src/pixel_data_frame.cpp",
     "sensors/camera_calibration/src/camera_mask.cpp",
     "energy/problems/src/normal_linear_system.cpp",
 )]

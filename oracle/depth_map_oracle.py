@@ -13,8 +13,10 @@ Restates, in NumPy float64 (the reference's default Precision):
   scalar pinhole reproject   src/energy/projector/include/energy/projector/camera_reproject.hpp:270-293
   call site                  src/tracker/tracker/src/monocular_tracker.cpp:465,509 (right after the BA solve)
 
-PARITY UNPINNED (like the other oracles here: the reference cannot be built and ships no fixture for this function);
-pinned by the properties in tests/test_depth_map_oracle.py.
+PARITY PINNED: create_depth_maps.cpp compiles here WHOLE and unchanged (oracle/build_ref_tracker.py; only the track
+containers it reads are stand-in records) and this restatement fills the same pixels on every level, dilation included, with
+weights and inverse-depth sums at 1e-12 (tests/test_reference_tracker.py, tests/golden/ref_tracker.npz); properties in
+tests/test_depth_map_oracle.py.
 
 Layout: a map is a pair of (H, W) arrays (idepth_w, weight); the reference's `map(x, y)` is element [y, x].
 `idepth_w` is the WEIGHTED SUM of inverse depths, as in the reference: consumers divide by `weight`

@@ -6,9 +6,14 @@ Restates, paths relative to /root/reference/src/features/:
   PixelDataFrame (pyramid)        src/pixel_data_frame.cpp:12-31
   {I,dx,dy} packing               src/calculate_pixelinfo.cpp:340-374 (scalar definition; the AVX2 path is tested equal to
                                   it by test/test/features/test_dxdy_accelerated.cpp:43-80)
-pixel_info is PINNED by the reference itself: calculate_pixelinfo.cpp compiles here from its own source
-(oracle/build_ref.py) and pixel_info equals it bit for bit in double (AVX2 and plain-C paths) and float
-(tests/test_reference_parts.py, tests/golden/ref_parts.npz).  The other three are parity unpinned (OpenCV / Eigen absent).
+PARITY PINNED, all four: the reference's own sources compile here (oracle/build_ref_pba.py: photometrically_corrected_image
+.cpp, pixel_data_frame.cpp with downscale_image.hpp, pixel_map.cpp, calculate_pixelinfo.cpp, against the stand-in Eigen /
+OpenCV headers of oracle/ref_stubs_full) and these functions, run in float64 like the reference's build, equal what they
+return BIT FOR BIT on whole pyramids (tests/test_reference_pyramid.py, tests/golden/ref_pyramid.npz); pixel_info is held
+in addition to the AVX2 and the plain-C routine in double and float (tests/test_reference_parts.py, tests/golden/
+ref_parts.npz).  Domain: level widths that are multiples of 8 -- on other widths the reference's double build leaves columns
+unwritten (the comma in the dispatch at calculate_pixelinfo.cpp:388; test_reference_avx2_dispatch_quirk) and the scalar
+definition restated here is what its own test names as the truth (test/test/features/test_dxdy_accelerated.cpp:43-80).
 All arithmetic is exact in the given dtype (float32 = the reference's USE_FLOAT build), so the device result must be
 bit-identical: the only operations are a table look-up, one multiply by max / (v + 1), sums of four and halves.
 """

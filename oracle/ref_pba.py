@@ -289,3 +289,51 @@ def pose_alignment_solve(ref_T, ref_exposure, ref_ab, ref_intensity, tgt_T, tgt_
     n = nl.value
     return dict(energy=e, n_valid=nv.value, converged=bool(cv.value), T_t_r=np.vstack([T, [0, 0, 0, 1.0]]), ab_eps=ab, H=H,
                 uv=uv[:n].copy(), idepth=idp[:n].copy(), patch=pt[:n].copy())
+
+
+def _u8(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def photometric_correction(gray_u8, lut, vignetting_u8=None):
+    """The reference's photometricallyCorrectedImage (photometrically_corrected_image.cpp:9-29) -> (H, W) float64."""
+    lib = load()
+    g, v, t = _u8(gray_u8), _u8(vignetting_u8), _f64(lut)
+    H, W = g.shape
+    out = np.zeros((H, W))
+    lib.refpyr_photometric_correction.restype = None
+    lib.refpyr_photometric_correction.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.refpyr_photometric_correction(g.ctypes.data, H, W, t.ctypes.data, None if v is None else v.ctypes.data, out.ctypes.data)
+    return out
+
+
+def downscale(image):
+    """The reference's downscaleImage (downscale_image.hpp:16-33) -> (H / 2, W / 2) float64."""
+    lib = load()
+    im = _f64(image)
+    H, W = im.shape
+    out = np.zeros((H // 2, W // 2))
+    lib.refpyr_downscale.restype = None
+    lib.refpyr_downscale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.refpyr_downscale(im.ctypes.data, H, W, out.ctypes.data)
+    return out
+
+
+def pixel_data_frame(gray_u8, lut, vignetting_u8, levels):
+    """The reference's PixelDataFrame constructor (pixel_data_frame.cpp:12-31): photometric correction, levels - 1 halvings,
+    every level packed by PixelMap<1> -> list of (H >> l, W >> l, 3) float64 arrays {I, dx, dy}."""
+    lib = load()
+    g, v, t = _u8(gray_u8), _u8(vignetting_u8), _f64(lut)
+    H, W = g.shape
+    sizes = [(H >> l, W >> l) for l in range(min(levels, 5))]
+    out = np.zeros(sum(h * w * 3 for h, w in sizes))
+    lib.refpyr_pixel_data_frame.restype = C.c_int
+    lib.refpyr_pixel_data_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    n = lib.refpyr_pixel_data_frame(g.ctypes.data, H, W, t.ctypes.data, None if v is None else v.ctypes.data, int(levels),
+                                    out.ctypes.data)
+    assert n == len(sizes), (n, sizes)
+    res, k = [], 0
+    for h, w in sizes:
+        res.append(out[k:k + h * w * 3].reshape(h, w, 3).copy())
+        k += h * w * 3
+    return res

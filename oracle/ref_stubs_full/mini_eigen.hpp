@@ -13,6 +13,7 @@
 #include <array>
 #include <cassert>
 #include <cmath>
+#include <complex>
 #include <cstddef>
 #include <cstdlib>
 #include <initializer_list>
@@ -198,6 +199,22 @@ class LDLT;
 template <class T>
 class CompleteOrthogonalDecomposition;
 
+// arithmetic index sequences: Eigen::seq(first, last, increment) with Eigen::fix<N> constants (downscaleImage)
+namespace internal {
+template <int N>
+struct FixedInt {
+  constexpr operator Index() const { return N; }
+};
+}  // namespace internal
+template <int N>
+inline constexpr internal::FixedInt<N> fix{};
+struct ArithmeticSequence {
+  Index first, size, incr;
+};
+inline ArithmeticSequence seq(Index first, Index last, Index incr = 1) {
+  return ArithmeticSequence{first, (last - first + incr) / incr, incr};
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 template <class Derived>
 class MatrixBase {
@@ -256,6 +273,8 @@ class MatrixBase {
   // index-list views (NormalLinearSystem::reduce_system): evaluated into a plain matrix
   Matrix<Scalar, Dynamic, Dynamic> operator()(const std::vector<int>& ri, const std::vector<int>& ci) const;
   Matrix<Scalar, Dynamic, 1> operator()(const std::vector<int>& ri) const;
+  Matrix<Scalar, Dynamic, Dynamic, PlainOpt_ & RowMajor> operator()(const ArithmeticSequence& ri,
+                                                                    const ArithmeticSequence& ci) const;
 
   // ---- blocks ------------------------------------------------------------------------------------------------
   template <int BR, int BC>
@@ -383,6 +402,14 @@ class MatrixBase {
 
   // ---- in-place ----------------------------------------------------------------------------------------------
   Derived& setZero() { return setConstant(Scalar(0)); }
+  Derived& setOnes() { return setConstant(Scalar(1)); }
+  // NAME ONLY: the general eigenvalue problem (the simple-radial camera's polynomial solver) is not on any tested path
+  struct EigenvaluesNotImplemented {
+    Index rows() const { std::abort(); }
+    std::complex<Scalar> operator[](Index) const { std::abort(); }
+    EigenvaluesNotImplemented eval() const { return *this; }
+  };
+  EigenvaluesNotImplemented eigenvalues() const { std::abort(); }
   Derived& setConstant(const Scalar& v) {
     for (Index i = 0; i < rows(); ++i)
       for (Index j = 0; j < cols(); ++j) derived().ref(i, j) = v;
@@ -752,6 +779,13 @@ class Matrix : public MatrixBase<Matrix<T, R, C, Opt, MR, MC>> {
   Matrix(const DiagonalWrapper<T, N>& d) {
     *this = d;
   }
+  // an evaluated coefficient-wise expression assigned back to the matrix world (Eigen allows Matrix = Array)
+  template <class U, int R2, int C2, int O2>
+  Matrix(const Array<U, R2, C2, O2>& a) {
+    s_.resize(a.rows(), a.cols());
+    for (Index i = 0; i < a.rows(); ++i)
+      for (Index j = 0; j < a.cols(); ++j) ref(i, j) = static_cast<T>(a(i, j));
+  }
 
   template <class O>
   Matrix& operator=(const MatrixBase<O>& o) {
@@ -1027,6 +1061,14 @@ Matrix<typename MatrixBase<D>::Scalar, Dynamic, Dynamic> MatrixBase<D>::operator
   return r;
 }
 template <class D>
+Matrix<typename MatrixBase<D>::Scalar, Dynamic, Dynamic, MatrixBase<D>::PlainOpt_ & RowMajor> MatrixBase<D>::operator()(
+    const ArithmeticSequence& ri, const ArithmeticSequence& ci) const {
+  Matrix<Scalar, Dynamic, Dynamic, PlainOpt_ & RowMajor> r(ri.size, ci.size);
+  for (Index i = 0; i < ri.size; ++i)
+    for (Index j = 0; j < ci.size; ++j) r.ref(i, j) = coeff(ri.first + i * ri.incr, ci.first + j * ci.incr);
+  return r;
+}
+template <class D>
 Matrix<typename MatrixBase<D>::Scalar, Dynamic, 1> MatrixBase<D>::operator()(const std::vector<int>& ri) const {
   Matrix<Scalar, Dynamic, 1> r(static_cast<Index>(ri.size()), 1);
   for (size_t i = 0; i < ri.size(); ++i) r[static_cast<Index>(i)] = clin(ri[i]);
@@ -1159,6 +1201,14 @@ class Array {
       if (lin(k)) return true;
     return false;
   }
+  template <class F>
+  auto unaryExpr(F f) const {
+    return map(f);
+  }
+  template <class U>
+  auto cast() const {
+    return map([](const T& v) { return static_cast<U>(v); });
+  }
   auto square() const {
     return map([](const T& v) { return v * v; });
   }
@@ -1219,6 +1269,17 @@ auto operator*(const T& s, const Array<T, R, C, O>& a) {
   return a.map([&](const T& v) { return s * v; });
 }
 template <class T, int R, int C, int O>
+auto round(const Array<T, R, C, O>& a) {  // std::round coefficient-wise: halves away from zero
+  return a.map([](const T& v) {
+    using std::round;
+    return round(v);
+  });
+}
+template <class T, int R, int C, int O>
+auto operator/(const T& s, const Array<T, R, C, O>& a) {
+  return a.map([&](const T& v) { return s / v; });
+}
+template <class T, int R, int C, int O>
 auto operator-(const Array<T, R, C, O>& a) {
   return a.map([](const T& v) { return -v; });
 }
@@ -1232,22 +1293,57 @@ MatrixBase<D>::array() const {
   return a;
 }
 
-// Map of an Array (PixelMap's storage of PixelInfo records)
-template <class T, int R, int C, int Opt, int MR, int MC, int MO, class S>
-class Map<Array<T, R, C, Opt, MR, MC>, MO, S> {
+// Map of an Array (PixelMap's storage of PixelInfo records; photometricallyCorrectedImage's views of the rasters)
+template <class T, class TP, int R, int C, int Opt>
+class ArrayMapImpl {
  public:
   static constexpr bool RM = (Opt & RowMajor) != 0;
-  Map(T* p, Index r, Index c) : p_(p), r_(r), c_(c) {}
+  ArrayMapImpl(TP* p, Index r, Index c) : p_(p), r_(r), c_(c) {}
   Index rows() const { return r_; }
   Index cols() const { return c_; }
   Index size() const { return r_ * c_; }
-  T& operator()(Index i, Index j) const { return p_[RM ? i * c_ + j : i + j * r_]; }
-  T& operator()(Index k) const { return p_[k]; }
-  T* data() const { return p_; }
+  TP& operator()(Index i, Index j) const { return p_[RM ? i * c_ + j : i + j * r_]; }
+  TP& operator()(Index k) const { return p_[k]; }
+  TP* data() const { return p_; }
+  template <class F>
+  auto unaryExpr(F f) const {
+    using U = std::decay_t<decltype(f(p_[0]))>;
+    Array<U, R, C, Opt> a(r_, c_);
+    for (Index k = 0; k < size(); ++k) a.lin(k) = f(p_[k]);
+    return a;
+  }
+  template <class U>
+  auto cast() const {
+    return unaryExpr([](const T& v) { return static_cast<U>(v); });
+  }
+  // coefficient-wise assignment from an evaluated array of the same shape and storage order
+  template <class U, int R2, int C2, int O2>
+  const ArrayMapImpl& operator=(const Array<U, R2, C2, O2>& a) const {
+    static_assert(((O2 & RowMajor) != 0) == RM, "storage orders differ");
+    for (Index k = 0; k < size(); ++k) p_[k] = a.lin(k);
+    return *this;
+  }
+  template <class U, int R2, int C2, int O2>
+  const ArrayMapImpl& operator*=(const Array<U, R2, C2, O2>& a) const {
+    static_assert(((O2 & RowMajor) != 0) == RM, "storage orders differ");
+    for (Index k = 0; k < size(); ++k) p_[k] *= a.lin(k);
+    return *this;
+  }
 
  private:
-  T* p_;
+  TP* p_;
   Index r_, c_;
+};
+template <class T, int R, int C, int Opt, int MR, int MC, int MO, class S>
+class Map<Array<T, R, C, Opt, MR, MC>, MO, S> : public ArrayMapImpl<T, T, R, C, Opt> {
+ public:
+  using ArrayMapImpl<T, T, R, C, Opt>::ArrayMapImpl;
+  using ArrayMapImpl<T, T, R, C, Opt>::operator=;
+};
+template <class T, int R, int C, int Opt, int MR, int MC, int MO, class S>
+class Map<const Array<T, R, C, Opt, MR, MC>, MO, S> : public ArrayMapImpl<T, const T, R, C, Opt> {
+ public:
+  using ArrayMapImpl<T, const T, R, C, Opt>::ArrayMapImpl;
 };
 
 // ------------------------------------------------------------------------------------------------------------------

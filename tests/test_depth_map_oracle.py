@@ -1,6 +1,7 @@
-"""Pins oracle/depth_map_oracle.py (createReferenceDepthMaps, src/tracker/tracker/src/create_depth_maps.cpp:19-146) with
-properties: the reference holds no test or fixture for this function (test/test/tracker/reference_frame/
-test_reference_frame_depth_map.cpp only checks the consumer side, LocalFrame's depth-map constructor)."""
+"""Properties of oracle/depth_map_oracle.py (createReferenceDepthMaps, src/tracker/tracker/src/create_depth_maps.cpp:19-146).
+The reference holds no test or fixture for this function (test/test/tracker/reference_frame/
+test_reference_frame_depth_map.cpp only checks the consumer side, LocalFrame's depth-map constructor); the value pin against
+the reference's own compiled file is tests/test_reference_tracker.py."""
 import numpy as np
 import pytest
 

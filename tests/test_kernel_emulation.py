@@ -1,4 +1,4 @@
-"""The per-thread bodies of the kernels that have not run on a GPU yet, executed on the CPU (tests/emu/kernel_emu.cpp
+"""The per-thread bodies of the kernels written in round 1 before they could run on a GPU, executed on the CPU (tests/emu/kernel_emu.cpp
 calls the same __host__ __device__ functions once per CUDA thread, over the launcher's grid) and compared with the
 oracles.  This checks indexing, predicates, rounding and buffer layout of
 
