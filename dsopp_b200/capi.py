@@ -102,6 +102,7 @@ SIGNATURES = {
     "dpba_append_statuses": (C.c_int, [_P, _I, _I, _I, _I, _P]),
     "dpba_get_residual_scalars": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dpba_set_frame_statuses": (C.c_int, [_P, _I, _I, _P]),
+    "dpba_set_window_landmarks": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "dpba_get_frame_statuses": (C.c_int, [_P, _I, _I, _P, _P]),
     "dpba_set_state": (C.c_int, [_P, _P, _P]),
     "dpba_get_state": (C.c_int, [_P, _P, _P]),
@@ -311,6 +312,19 @@ class Handle:
         n = len(next(iter(arrs.values()))) if arrs else 0
         ptrs = (C.c_void_p * n_fr)(*[arrs[t].ctypes.data if t in arrs else None for t in range(n_fr)])
         self._ck(self.lib.dpba_set_frame_statuses(self.h, r, n, ptrs))
+
+    def set_window_landmarks(self, uv, idepth, patch, flags=None, statuses=None):
+        """Every slot's landmarks (lists indexed by slot) and, optionally, every residual vector's statuses
+        (dict {(r, t): uint8[n_r]}) in one call: dpba_set_window_landmarks."""
+        n_fr = self.n_frames
+        uv, idepth, patch = [_f32(a) for a in uv], [_f32(a) for a in idepth], [_f32(a) for a in patch]
+        fl = [None] * n_fr if flags is None else [_u8(a) for a in flags]
+        st = {} if statuses is None else {k: _u8(v) for k, v in statuses.items()}
+        cnt = np.array([len(a) for a in idepth], np.int32)
+        arr = lambda xs: (C.c_void_p * len(xs))(*[None if x is None or x.size == 0 else x.ctypes.data for x in xs])  # noqa: E731
+        ps = None if statuses is None else arr([st.get((r, t)) if r != t else None for r in range(n_fr) for t in range(n_fr)])
+        self._ck(self.lib.dpba_set_window_landmarks(self.h, _ptr(cnt), arr(uv), arr(idepth), arr(patch),
+                                                    None if flags is None else arr(fl), ps))
 
     def get_frame_statuses(self, r):
         """-> (statuses, candidates), each uint8 [n_frames][n]; row r is unused (zeros)."""

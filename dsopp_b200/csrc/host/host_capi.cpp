@@ -260,12 +260,9 @@ __attribute__((visibility("default"))) int dpbah_solve_window(dpba_handle* h, dp
     }
     mark();
     std::vector<double> zero(8 * (size_t)n, 0.0);
-    for (int f = 0; f < n; ++f) {
-      const int m = io->n_landmarks[f];
-      dpba_check(h, dpba_set_landmarks(h, f, m, io->uv[f], io->idepth[f], io->patch[f], io->flags[f]));
-      dpba_check(h, dpba_set_frame_statuses(h, f, m, io->statuses + (size_t)f * n));
-      h2d += (int64_t)m * (8 + 4 + 32 + 1) + (int64_t)m * (n - 1);
-    }
+    // every landmark array and every residual vector's statuses in one call: one DMA per device array
+    dpba_check(h, dpba_set_window_landmarks(h, io->n_landmarks, io->uv, io->idepth, io->patch, io->flags, io->statuses));
+    for (int f = 0; f < n; ++f) h2d += (int64_t)io->n_landmarks[f] * (8 + 4 + 32 + 1) + (int64_t)io->n_landmarks[f] * (n - 1);
     dpba_check(h, dpba_set_state(h, io->eps0, zero.data()));
     h2d += 2 * 8 * (int64_t)n * 8;
     mark();
@@ -318,27 +315,25 @@ __attribute__((visibility("default"))) int dpbah_solve_sliding(dpba_handle* h, d
       dpba_check(h, dpba_push_frame(h, io->frame_ids[f], io->images[f], io->masks[f], io->T_w_lin + 12 * f, io->exposure[f],
                                     io->ab0 + 2 * f, io->intr + 4 * f, 0));
     h2d += (int64_t)npx * (io->image_channels == 1 ? 4 : 12) + (io->masks[f] ? (int64_t)npx : 0);
-    const int slot = n - 1, m = io->n_landmarks[f];
-    dpba_check(h, dpba_set_landmarks(h, slot, m, io->uv[f], io->idepth[f], io->patch[f], io->flags[f]));
-    h2d += (int64_t)m * (8 + 4 + 32 + 1);
-    for (int t = 0; t + 1 < n; ++t) {  // the new frame's residual vectors, both directions
-      const int g = order[t];
-      dpba_check(h, dpba_set_statuses(h, slot, t, m, io->statuses[(size_t)f * n + g]));
-      dpba_check(h, dpba_set_statuses(h, t, slot, io->n_landmarks[g], io->statuses[(size_t)g * n + f]));
-      h2d += m + io->n_landmarks[g];
-    }
-    // same starting state every step (the benchmark's steps must do the same work): landmarks of the frames that stayed
-    // and the pose increments go back to the initial estimate
+    // The new frame's landmarks and its residual vectors in both directions; and -- same starting state every step, the
+    // benchmark's steps must do the same work -- the landmarks and statuses of the frames that stayed and the pose
+    // increments go back to the initial estimate: the whole window in one call, pointers permuted into slot order.
     std::vector<double> eps(8 * (size_t)n), zero(8 * (size_t)n, 0.0);
+    std::vector<int32_t> cnt((size_t)n);
+    std::vector<const float*> uv((size_t)n), idp((size_t)n), pat((size_t)n);
+    std::vector<const uint8_t*> flg((size_t)n), sts((size_t)n * n, nullptr);
     for (int t = 0; t < n; ++t) {
-      for (int k = 0; k < 8; ++k) eps[8 * t + k] = io->eps0[8 * order[t] + k];
-      if (t + 1 < n) {
-        const int g = order[t];
-        dpba_check(h, dpba_set_landmarks(h, t, io->n_landmarks[g], io->uv[g], io->idepth[g], io->patch[g], io->flags[g]));
-        const uint8_t* rows[DPBA_MAX_FRAMES] = {};
-        for (int u = 0; u < n; ++u) rows[u] = u == t ? nullptr : io->statuses[(size_t)g * n + order[u]];
-        dpba_check(h, dpba_set_frame_statuses(h, t, io->n_landmarks[g], rows));
-      }
+      const int g = order[t];
+      for (int k = 0; k < 8; ++k) eps[8 * t + k] = io->eps0[8 * g + k];
+      cnt[t] = io->n_landmarks[g], uv[t] = io->uv[g], idp[t] = io->idepth[g], pat[t] = io->patch[g], flg[t] = io->flags[g];
+      for (int u = 0; u < n; ++u)
+        if (u != t) sts[(size_t)t * n + u] = io->statuses[(size_t)g * n + order[u]];
+    }
+    dpba_check(h, dpba_set_window_landmarks(h, cnt.data(), uv.data(), idp.data(), pat.data(), flg.data(), sts.data()));
+    {
+      const int m = io->n_landmarks[f];
+      h2d += (int64_t)m * (8 + 4 + 32 + 1);
+      for (int t = 0; t + 1 < n; ++t) h2d += m + io->n_landmarks[order[t]];
     }
     dpba_check(h, dpba_set_state(h, eps.data(), zero.data()));
     h2d += 2 * 8 * (int64_t)n * 8;

@@ -157,6 +157,7 @@ struct dpba_handle {
   cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
   cudaEvent_t img_done = nullptr, main_mark = nullptr;
   bool img_pending = false;
+  bool pack_after_main = false;  // the pack stream already waits for everything the main stream held at the last join
   int stage_idx = 0;
   float* stage_h = nullptr;  // pinned staging for images
   float *m_r = nullptr, *m_jref = nullptr, *m_jtgt = nullptr, *m_did = nullptr, *m_w = nullptr;
@@ -350,7 +351,10 @@ ReduceBuf redbuf_out(dpba_handle* h) {
 
 // the main stream joins the image uploads (copy + pack streams); called outside stream capture only
 void wait_images(dpba_handle* h) {
+  // after this join the main stream may be given kernels that read the image slots: the next push marks it again
+  h->pack_after_main = false;
   if (!h->img_pending) return;
+  cudaEventRecord(h->img_done, h->pack_stream);  // once for all the packs queued since the last join
   cudaStreamWaitEvent(h->stream, h->img_done, 0);
   h->img_pending = false;
 }
@@ -571,14 +575,18 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
     CK(cudaEventRecord(h->stage_ready[sb], h->copy_stream));
     // the pack kernel overwrites a physical image slot: everything the main stream has queued so far (a solve that still
     // reads the slot's previous occupant) comes first
-    CK(cudaEventRecord(h->main_mark, h->stream));
-    CK(cudaStreamWaitEvent(h->pack_stream, h->main_mark, 0));
+    // (readers of image slots are only queued after wait_images(); between two joins the main stream receives nothing but
+    // uploads, so one mark per run of pushes is enough)
+    if (!h->pack_after_main) {
+      CK(cudaEventRecord(h->main_mark, h->stream));
+      CK(cudaStreamWaitEvent(h->pack_stream, h->main_mark, 0));
+      h->pack_after_main = true;
+    }
     CK(cudaStreamWaitEvent(h->pack_stream, h->stage_ready[sb], 0));
     if (channels == 3) pba::launch_pack_image(dst, h->img[phys], (int)npx, W, h->pack_stream);
     else pba::launch_pixelinfo(dst, h->img[phys], W, H, h->pack_stream);  // {I,dx,dy} from the intensity plane on the device
     CK(cudaEventRecord(h->stage_free[sb], h->pack_stream));
-    CK(cudaEventRecord(h->img_done, h->pack_stream));
-    h->img_pending = true;
+    h->img_pending = true;  // wait_images() records img_done behind the last pack
   } else {
     if (channels > 0) {
       if (!pinned) {
@@ -588,6 +596,7 @@ int push_frame_common(dpba_handle* h, int32_t frame_id, const float* image, int 
       CK(cudaMemcpyAsync(h->stage, src, npx * channels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     }
     pba::launch_pixelinfo(channels > 0 ? h->stage : image, h->img[phys], W, H, h->stream);  // -1: device plane
+    h->pack_after_main = false;  // the main stream now holds a writer of an image slot
     if (channels > 0) CK(cudaEventRecord(h->stage_free[0], h->stream));  // h->stage is staging buffer 0 of the pipeline
   }
   CK(cudaGetLastError());
@@ -1159,6 +1168,87 @@ int dpba_set_frame_statuses(dpba_handle* h, int32_t r, int32_t n, const uint8_t*
     if (t == r || !per_target[t]) continue;
     const int rc = set_statuses_row(h, r, t, n, per_target[t]);
     if (rc) return rc;
+  }
+  return DPBA_SUCCESS;
+}
+
+int dpba_set_window_landmarks(dpba_handle* h, const int32_t* n, const float* const* uv, const float* const* idepth,
+                              const float* const* patch, const uint8_t* const* flags, const uint8_t* const* statuses) {
+  REQUIRE(h, "null handle");
+  REQUIRE(n && uv && idepth && patch, "null argument");
+  const int nf = h->n_frames;
+  const size_t mp = h->cfg.max_points_per_frame;
+  for (int f = 0; f < nf; ++f) {
+    REQUIRE(n[f] >= 0 && (n[f] == 0 || (uv[f] && idepth[f] && patch[f])), "null landmark arrays");
+    if ((size_t)n[f] > mp) return fail(h, DPBA_E_CAPACITY, "too many landmarks for this handle");
+  }
+  if (nf == 0) return DPBA_SUCCESS;
+  // The frames' physical slots: when they are one dense run [lo, hi] every device array is written by ONE DMA out of
+  // the pinned arena, packed there in device layout; otherwise (holes left by removed frames) frame by frame.
+  int lo = PBA_MAXF, hi = -1;
+  bool covered[PBA_MAXF] = {};
+  for (int f = 0; f < nf; ++f) {
+    lo = std::min(lo, h->fr[f].phys);
+    hi = std::max(hi, h->fr[f].phys);
+    covered[h->fr[f].phys] = true;
+  }
+  bool dense = true;
+  for (int p = lo; p <= hi; ++p) dense = dense && covered[p];
+  const size_t rows = (size_t)(hi - lo + 1), cells = rows * mp;
+  const size_t need = cells * (sizeof(float4) + 8 * sizeof(float) + 1) + (statuses ? rows * cells : 0) + 4 * 256;
+  if (!dense || need > h->arena_cap) {
+    for (int f = 0; f < nf; ++f) {
+      int rc = dpba_set_landmarks(h, f, n[f], uv[f], idepth[f], patch[f], flags ? flags[f] : nullptr);
+      if (rc) return rc;
+      if (statuses) {
+        rc = dpba_set_frame_statuses(h, f, n[f], statuses + (size_t)f * nf);
+        if (rc) return rc;
+      }
+    }
+    return DPBA_SUCCESS;
+  }
+  h->rb_valid = false;
+  if (h->arena_used + need > h->arena_cap) {  // the four blocks below must not wrap around each other
+    CK(cudaStreamSynchronize(h->stream));
+    h->arena_used = 0;
+  }
+  float4* lk = (float4*)arena_alloc(h, sizeof(float4) * cells);
+  float* pt = (float*)arena_alloc(h, sizeof(float) * 8 * cells);
+  uint8_t* fl = (uint8_t*)arena_alloc(h, cells);
+  uint8_t* st = statuses ? (uint8_t*)arena_alloc(h, rows * cells) : nullptr;
+  if (!lk || !pt || !fl || (statuses && !st)) return fail(h, DPBA_E_CAPACITY, "staging arena too small");
+  if (st) memset(st, 0, rows * cells);  // slots [n, max_pts) and the unused r -> r rows: kOk, never stale bytes
+  for (int f = 0; f < nf; ++f) {
+    const size_t o = (size_t)(h->fr[f].phys - lo) * mp;
+    const int m = n[f];
+    const float *u = uv[f], *d = idepth[f];
+    for (int l = 0; l < m; ++l) lk[o + l] = make_float4(u[2 * l], u[2 * l + 1], d[l], d[l]);
+    memcpy(pt + 8 * o, patch[f], sizeof(float) * 8 * m);
+    if (flags && flags[f]) memcpy(fl + o, flags[f], m);
+    else memset(fl + o, 0, m);
+    if ((size_t)m < mp) {  // the tail of the slot: defined bytes (no kernel reads past n_lm)
+      memset((void*)(lk + o + m), 0, sizeof(float4) * (mp - m));
+      memset(pt + 8 * (o + m), 0, sizeof(float) * 8 * (mp - m));
+      memset(fl + o + m, 0, mp - m);
+    }
+    if (st)
+      for (int t = 0; t < nf; ++t) {
+        const uint8_t* row = t == f ? nullptr : statuses[(size_t)f * nf + t];
+        if (row) memcpy(st + o * rows + (size_t)(h->fr[t].phys - lo) * mp, row, m);
+      }
+    h->fr[f].n_lm = m;
+  }
+  const size_t base = (size_t)lo * mp;
+  const size_t nlm = (size_t)h->cfg.max_frames * mp;
+  CK(cudaMemcpyAsync(h->lmk + base, lk, sizeof(float4) * cells, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->patch + base * 8, pt, sizeof(float) * 8 * cells, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->flags + base, fl, cells, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemset2DAsync(h->lm_slab + base, nlm * sizeof(float), 0, sizeof(float) * cells, 5, h->stream));
+  if (st) {
+    // residual vectors (r -> t): rows [phys_t] of the [PBA_MAXF][max_pts] block of phys_r -- one 2-D copy per array
+    const size_t sbase = ((size_t)lo * PBA_MAXF + lo) * mp;
+    CK(cudaMemcpy2DAsync(h->status + sbase, (size_t)PBA_MAXF * mp, st, cells, cells, rows, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(h->cand + sbase, (size_t)PBA_MAXF * mp, st, cells, cells, rows, cudaMemcpyHostToDevice, h->stream));
   }
   return DPBA_SUCCESS;
 }

@@ -179,6 +179,16 @@ int dpba_set_frame_statuses(dpba_handle* h, int32_t ref_slot, int32_t n, const u
 int dpba_get_frame_statuses(dpba_handle* h, int32_t ref_slot, int32_t n, uint8_t* const* statuses,
                             uint8_t* const* candidates);
 
+/* The whole window in one call: dpba_set_landmarks for every slot and (when `statuses` is not NULL) dpba_set_frame_statuses
+ * for every reference slot -- what PhotometricBundleAdjustment::pushFrame's LocalFrame constructors do frame by frame
+ * (PBA/local_frame.hpp:314-347) when a tracker hands a window over.  n[f], uv[f], idepth[f], patch[f], flags[f] as in
+ * dpba_set_landmarks (flags, or single entries of it, may be NULL); statuses[r * num_frames + t] -> [n[r]] statuses of the
+ * residual vector (r -> t), NULL on the diagonal, NULL entries leave kOk.  The arrays are packed in device layout in the
+ * handle's pinned arena and every device array is written by ONE asynchronous copy (5 DMAs instead of ~7 per frame); no
+ * stream synchronisation, the caller's buffers are free on return. */
+int dpba_set_window_landmarks(dpba_handle* h, const int32_t* n, const float* const* uv, const float* const* idepth,
+                              const float* const* patch, const uint8_t* const* flags, const uint8_t* const* statuses);
+
 /* state_eps / state_eps_step of all frames, [8N] each (PBA/local_frame.hpp:561-563) */
 int dpba_set_state(dpba_handle* h, const double* state_eps, const double* state_eps_step);
 int dpba_get_state(dpba_handle* h, double* state_eps, double* state_eps_step);

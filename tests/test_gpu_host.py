@@ -229,6 +229,64 @@ def test_batched_frame_statuses_equal_the_per_pair_calls():
     h.close()
 
 
+def test_whole_window_upload_equals_the_per_frame_calls():
+    """dpba_set_window_landmarks (every landmark array and residual-status vector of the window packed in device layout, one
+    DMA per device array) against dpba_set_landmarks + dpba_set_statuses frame by frame: identical device contents and an
+    identical sweep -- on ragged landmark counts below the handle's capacity, after the caller's buffers were scribbled
+    over, and on a window whose physical slots have a hole (the per-frame fallback)."""
+    from dsopp_b200 import capi
+    win = synth.make_window(n_frames=5, points_per_frame=180, seed=6, ab_scale=0.0)
+    n = win.n_frames
+    rng = np.random.default_rng(4)
+    keep = [180, 93, 180, 1, 150]  # ragged: slots are 180 wide
+    for f, m in zip(win.frames, keep):
+        f.uv, f.idepth, f.patch, f.flags = f.uv[:m], f.idepth[:m], f.patch[:m], f.flags[:m]
+    sts = {(r, t): rng.choice([0, 0, 0, 1, 3, 4], keep[r]).astype(np.uint8) for r in range(n) for t in range(n) if r != t}
+    for k, v in sts.items():
+        win.statuses[k] = v
+    a = capi.upload_window(win, max_points=180)  # per-frame calls
+    b = capi.Handle(n, 180, win.width, win.height)
+    for f in win.frames:
+        b.push_frame(f.frame_id, f.image, f.mask, f.T_w_lin, f.exposure, f.ab0, f.intr, f.fixed)
+    bufs = [[np.array(getattr(f, k), dtype=np.float32) for f in win.frames] for k in ("uv", "idepth", "patch")]
+    flags = [np.array(f.flags, dtype=np.uint8) for f in win.frames]
+    st_in = {k: v.copy() for k, v in sts.items()}
+    b.set_window_landmarks(bufs[0], bufs[1], bufs[2], flags, st_in)
+    for group in bufs + [flags, list(st_in.values())]:
+        for arr in group:
+            arr[...] = 77  # the arrays were staged: scribbling must not reach the device
+    b.set_state(np.concatenate([f.state_eps for f in win.frames]), np.zeros(8 * n))
+
+    def same(x, y):
+        for s_ in range(n):
+            lx, ly = x.get_landmarks(s_), y.get_landmarks(s_)
+            assert x.num_landmarks(s_) == y.num_landmarks(s_) == len(lx["idepth"])
+            assert (lx["idepth"] == ly["idepth"]).all() and (lx["flags"] == ly["flags"]).all()
+            for t in range(n):
+                if t != s_:
+                    assert (x.get_statuses(s_, t)[0] == y.get_statuses(s_, t)[0]).all()
+    same(a, b)
+    for h in (a, b):
+        h.first_estimate()
+    assert a.evaluate(SIGMA, True, True) == b.evaluate(SIGMA, True, True)
+    Ha, Hb = a.linearize(SIGMA, True, True), b.linearize(SIGMA, True, True)
+    assert all(np.array_equal(x, y) for x, y in zip(Ha, Hb))
+    # a hole in the physical slots (slot 1 removed): the call falls back to the per-frame path
+    for h in (a, b):
+        h.remove_frame(1)
+    rest = [0, 2, 3, 4]
+    new_st = {(i, j): rng.choice([0, 1, 4], keep[rest[i]]).astype(np.uint8) for i in range(4) for j in range(4) if i != j}
+    fr = [win.frames[k] for k in rest]
+    for i, f in enumerate(fr):
+        a.set_landmarks(i, f.uv, f.idepth * 1.01, f.patch, f.flags)
+    for (i, j), v in new_st.items():
+        a.set_statuses(i, j, v)
+    b.set_window_landmarks([f.uv for f in fr], [f.idepth * 1.01 for f in fr], [f.patch for f in fr], [f.flags for f in fr], new_st)
+    n = 4
+    same(a, b)
+    a.close(), b.close()
+
+
 def test_one_call_window_step_and_sliding_step():
     """dpbah_solve_window (whole window from host buffers, solve, results back in ONE C++ call) equals the same sequence
     driven call by call; dpbah_solve_sliding (oldest keyframe out, one keyframe in) returns to the same solve after n steps
