@@ -3366,17 +3366,36 @@ __global__ void __launch_bounds__(256) k_lm_energy_cp(const __grid_constant__ Wi
 // (normal_linear_system.cpp:10-59), all fp64 in one CTA.
 //
 // Blocked right-looking LDL^T, block size 8, on the lower triangle held in shared memory.  The right-hand side rides
-// along as row D of the matrix, so z = L^-1 b falls out of the factorisation.  Per block step (3 barriers):
-//   panel : thread i owns row kb+i.  Every thread factors the 8x8 diagonal block redundantly in registers (no
-//           barrier, no broadcast) and runs the same recurrence on its own 8 panel entries
+// along as row D of the matrix, so z = L^-1 b falls out of the factorisation.  Per block step (2 barriers):
+//   panel : thread i owns row kb+i.  It reads the FACTORED 8x8 diagonal block (packed triangle + reciprocals, 44 broadcast
+//           loads from Gf) and runs the block's recurrence on its own 8 panel entries
 //             a[c] -= a[j] * l_cj   (j < c),   l_cj = x_cj / d_j,   x = L D  ("raw" columns)
-//   update: A22 -= X L21^T over the trailing lower triangle, 16x16 thread tiling, K = 8.
+//   update: A22 -= X L21^T over the trailing lower triangle, 16x16 thread tiling with 2x2 register tiles, K = 8.
+//   look-ahead: the eight dependent reciprocals of a diagonal block (~90 cycles each) used to open every block step.
+//           Warp 7 -- idle in the panel phase -- now takes the NEXT step's diagonal block out of the trailing update:
+//           it updates those 36 entries first, factors them and leaves the result in Gf while the other warps are busy
+//           with the rest of the update (same sums in the same order: the factorisation is bit-identical).
 // A column-by-column factorisation needs 8N barrier-separated steps whose critical path (publish column, barrier,
 // reciprocal, update) measured ~1500 cycles each on B200 (profiles/r01d_k_lm_step.md); this form has N of them.
 __device__ __forceinline__ double rcp64(double d) {
   // IEEE division: measured 67 cycles on B200 against 131 for an fp32 seed + two Newton steps (the f32<->f64
   // conversions dominate), tools/fp64_probe.cu
   return d == 0.0 ? 0.0 : 1.0 / d;
+}
+
+// LDL^T of an 8x8 block held as a packed lower triangle g[r (r + 1) / 2 + c] in registers: afterwards the diagonal holds
+// d_j, the entries below it the raw columns x_rj = l_rj d_j, inv[j] = 1 / d_j
+__device__ __forceinline__ void ldlt8_packed(double (&g)[36], double (&inv)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    inv[j] = rcp64(g[j * (j + 1) / 2 + j]);
+#pragma unroll
+    for (int r = j + 1; r < 8; ++r) {
+      const double l = g[r * (r + 1) / 2 + j] * inv[j];
+#pragma unroll
+      for (int c = j + 1; c <= r; ++c) g[r * (r + 1) / 2 + c] -= l * g[c * (c + 1) / 2 + j];
+    }
+  }
 }
 
 template <int DP>
@@ -3396,6 +3415,7 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
   double* pre = dinv + DP;              // [DP] Jacobi preconditioner
   double* st = pre + DP;                // [DP] state eps, later the solution
   double* hm = st + DP;                 // [DP] H_marg * state
+  double* Gf = hm + DP;                 // [48] factored diagonal block of the coming block step: 36 packed + 8 reciprocals
   const double lambda = ctl->lambda, ks = -1.0 / (1.0 + lambda);
   // Every global input of the fill is requested UP FRONT, in one batch of independent loads: the first 16 x 256 entries of
   // (H_pose, H_schur[, H_marg]) -- the whole 64 x 64 system of an 8-keyframe window --, the diagonal, the right-hand sides,
@@ -3487,35 +3507,37 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
     S[D * LD + tid] = b * pre[tid];
   }
   const int ty = tid >> 4, tx = tid & 15;
+  const int warp_id = tid >> 5, lane_id = tid & 31;
+  constexpr int LOOKAHEAD_WARP = 7;
   stamp(2);
+  __syncthreads();
+  if (warp_id == LOOKAHEAD_WARP) {  // the first diagonal block
+    double g[36], inv[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) g[r * (r + 1) / 2 + c] = S[r * LD + c];
+    ldlt8_packed(g, inv);
+    if (lane_id == 0) {
+#pragma unroll
+      for (int e = 0; e < 36; ++e) Gf[e] = g[e];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) Gf[36 + j] = inv[j];
+    }
+  }
   for (int kb = 0; kb < D; kb += 8) {
-    __syncthreads();
+    __syncthreads();  // the trailing matrix is up to date and Gf holds this step's factored diagonal block
     if (kb < 64) stamp(3 + kb / 8);
     const int i = kb + tid;  // this thread's row (row D is the right-hand side)
-    const bool act = i <= D;
-    // the 8x8 diagonal block, packed lower triangle g[r (r + 1) / 2 + c], factored redundantly by every thread
-    double g[36], inv[8], a[8];
-    if (act) {
+    if (i <= D) {
+      double g[36], inv[8], a[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int e = 0; e < 36; ++e) g[e] = Gf[e];
 #pragma unroll
-        for (int c = 0; c <= r; ++c) g[r * (r + 1) / 2 + c] = S[(kb + r) * LD + kb + c];
+      for (int j = 0; j < 8; ++j) inv[j] = Gf[36 + j];
 #pragma unroll
       for (int c = 0; c < 8; ++c) a[c] = (i >= kb + c) ? S[i * LD + kb + c] : 0.0;
-    }
-    __syncthreads();  // rows kb..kb+7 are overwritten below by their owners
-    if (act) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        inv[j] = rcp64(g[j * (j + 1) / 2 + j]);
-#pragma unroll
-        for (int r = j + 1; r < 8; ++r) {
-          const double l = g[r * (r + 1) / 2 + j] * inv[j];
-#pragma unroll
-          for (int c = j + 1; c <= r; ++c) g[r * (r + 1) / 2 + c] -= l * g[c * (c + 1) / 2 + j];
-        }
-      }
-      // own row: same recurrence (for a row of the diagonal block the entries right of the diagonal are unused)
+      // own row: the block's recurrence (for a row of the diagonal block the entries right of the diagonal are unused)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -3536,18 +3558,66 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
     if (kb == 0) stamp(13);
     __syncthreads();
     if (kb == 0) stamp(14);
-    // trailing update of the lower triangle (and the rhs row): S[r][c] -= sum_j x_rj l_cj
     const int m0 = kb + 8;
-    for (int r = m0 + ty; r <= D; r += 16) {
-      double x[8];
+    // look-ahead: the next diagonal block -- rows / columns m0 .. m0 + 7 -- leaves the trailing update
+    if (warp_id == LOOKAHEAD_WARP && m0 < D) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = S[r * LD + kb + j];
-      const int cmax = min(r, D - 1);
-      for (int c = m0 + tx; c <= cmax; c += 16) {
-        double acc = 0;
+      for (int q = 0; q < 2; ++q) {  // the 8 x 8 square over 32 lanes x 2; the upper triangle idles
+        const int r = (lane_id >> 3) + 4 * q, c = lane_id & 7;
+        if (c <= r) {
+          double acc = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc += x[j] * Lp[c * LPS + j];
-        S[r * LD + c] -= acc;
+          for (int j = 0; j < 8; ++j) acc += S[(m0 + r) * LD + kb + j] * Lp[(m0 + c) * LPS + j];
+          const double v = S[(m0 + r) * LD + m0 + c] - acc;
+          S[(m0 + r) * LD + m0 + c] = v;  // what the next step's panel threads read as their own row
+          Gf[r * (r + 1) / 2 + c] = v;
+        }
+      }
+      __syncwarp();
+      double g[36], inv[8];
+#pragma unroll
+      for (int e = 0; e < 36; ++e) g[e] = Gf[e];
+      ldlt8_packed(g, inv);
+      __syncwarp();
+      if (lane_id == 0) {
+#pragma unroll
+        for (int e = 0; e < 36; ++e) Gf[e] = g[e];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Gf[36 + j] = inv[j];
+      }
+    }
+    // trailing update of the lower triangle (and the rhs row): S[r][c] -= sum_j x_rj l_cj, rows below the next diagonal block.
+    // 2 x 2 register tile per thread -- rows {r, r + 14} x columns {c, c + 16}, so that the 16 lanes of a half-warp keep
+    // walking Lp and S with the conflict-free strides -- : a panel entry l_cj fetched from shared memory serves two rows
+    // and a row's x_rj two columns; every element is still the same 8-term sum in the same order.
+    const int own_lo = min(m0 + 8, D);  // rows [m0, own_lo) belong to the look-ahead warp, which takes no other share
+    for (int r = m0 + ty; r <= D && warp_id != LOOKAHEAD_WARP; r += 28) {
+      const int r1 = r + 14;
+      const bool has0 = r >= own_lo, has1 = r1 <= D;  // (r1 >= m0 + 14 is never a look-ahead row)
+      double x0[8], x1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x0[j] = has0 ? S[r * LD + kb + j] : 0.0;
+        x1[j] = has1 ? S[r1 * LD + kb + j] : 0.0;
+      }
+      const int cmax0 = has0 ? min(r, D - 1) : -1, cmax1 = has1 ? min(r1, D - 1) : -1;
+      const int cend = max(cmax0, cmax1);
+      for (int c = m0 + tx; c <= cend; c += 32) {
+        const int c1 = c + 16;
+        const bool hc1 = c1 <= cend;
+        double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const double l0 = Lp[c * LPS + j], l1 = hc1 ? Lp[c1 * LPS + j] : 0.0;
+          a00 += x0[j] * l0;
+          a01 += x0[j] * l1;
+          a10 += x1[j] * l0;
+          a11 += x1[j] * l1;
+        }
+        if (c <= cmax0) S[r * LD + c] -= a00;
+        if (c1 <= cmax0) S[r * LD + c1] -= a01;
+        if (c <= cmax1) S[r1 * LD + c] -= a10;
+        if (c1 <= cmax1) S[r1 * LD + c1] -= a11;
       }
     }
   }
@@ -3587,7 +3657,7 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
 }
 
 template <int DP>
-__global__ void __launch_bounds__(256) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
+__global__ void __launch_bounds__(256, 1) k_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr,
                                                  const int* fixed, int N, const double* __restrict__ Hp,
                                                  const double* __restrict__ bp, const double* __restrict__ Hs,
                                                  const double* __restrict__ bs, const double* __restrict__ Hmarg,
@@ -3687,7 +3757,7 @@ __device__ __forceinline__ void pair_setup_body(const FrameParams* __restrict__ 
 // (k_lm_step) and the per-pair constants of the new trial state (k_pair_setup) -- three single-CTA kernels and their
 // launch boundaries become one.  with_step = 0: decision only (the last evaluation of a solve).
 template <int DP>
-__global__ void __launch_bounds__(256) k_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed,
+__global__ void __launch_bounds__(256, 1) k_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const int* fixed,
                                                   int N, double* scal, const double* __restrict__ Hp,
                                                   const double* __restrict__ bp, const double* __restrict__ Hs,
                                                   const double* __restrict__ bs, const double* __restrict__ Hmarg,
@@ -3785,7 +3855,7 @@ void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, 
   const int D = 8 * N;
   const int n_sys = 2 * (D * D + D);
   ++g_launches;
-  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP) * sizeof(double); };
+  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP + 48) * sizeof(double); };
   if (D <= 64) {
     k_lm_step<64><<<1, 256, smem_of(64), s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev,
                                               peer_expected, rb.Hp, n_sys);
@@ -3806,7 +3876,7 @@ void launch_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const
                      PairConst* pairs, PairAssemble* pasm, cudaStream_t s) {
   const int D = 8 * N;
   ++g_launches;
-  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP) * sizeof(double); };
+  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP + 48) * sizeof(double); };
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_lm_solve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(64));
