@@ -3367,14 +3367,17 @@ __global__ void __launch_bounds__(256) k_lm_energy_cp(const __grid_constant__ Wi
 //
 // Blocked right-looking LDL^T, block size 8, on the lower triangle held in shared memory.  The right-hand side rides
 // along as row D of the matrix, so z = L^-1 b falls out of the factorisation.  Per block step (2 barriers):
-//   panel : thread i owns row kb+i.  It reads the FACTORED 8x8 diagonal block (packed triangle + reciprocals, 44 broadcast
+//   panel : thread i owns row kb+i (rows m0 .. m0 + 7, m0 = kb + 8, are the look-ahead warp's).  It reads the FACTORED 8x8 diagonal block (packed triangle + reciprocals, 44 broadcast
 //           loads from Gf) and runs the block's recurrence on its own 8 panel entries
 //             a[c] -= a[j] * l_cj   (j < c),   l_cj = x_cj / d_j,   x = L D  ("raw" columns)
 //   update: A22 -= X L21^T over the trailing lower triangle, 16x16 thread tiling with 2x2 register tiles, K = 8.
 //   look-ahead: the eight dependent reciprocals of a diagonal block (~90 cycles each) used to open every block step.
-//           Warp 7 -- idle in the panel phase -- now takes the NEXT step's diagonal block out of the trailing update:
-//           it updates those 36 entries first, factors them and leaves the result in Gf while the other warps are busy
-//           with the rest of the update (same sums in the same order: the factorisation is bit-identical).
+//           Warp 7 now runs AHEAD of the step.  After the top barrier it does the panel work of rows m0 .. m0 + 7 (the
+//           next diagonal block's own rows), ARRIVES on the panel barrier without waiting (named barrier 1: the other
+//           seven warps bar.sync on it), then updates the 36 entries of the next diagonal block out of the trailing
+//           update, factors them and leaves the result in the other half of Gf -- all while the other warps do their
+//           panel rows and the rest of the trailing update.  Same sums in the same order: the factorisation is
+//           bit-identical to the plain blocked form.
 // A column-by-column factorisation needs 8N barrier-separated steps whose critical path (publish column, barrier,
 // reciprocal, update) measured ~1500 cycles each on B200 (profiles/r01d_k_lm_step.md); this form has N of them.
 __device__ __forceinline__ double rcp64(double d) {
@@ -3415,7 +3418,7 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
   double* pre = dinv + DP;              // [DP] Jacobi preconditioner
   double* st = pre + DP;                // [DP] state eps, later the solution
   double* hm = st + DP;                 // [DP] H_marg * state
-  double* Gf = hm + DP;                 // [48] factored diagonal block of the coming block step: 36 packed + 8 reciprocals
+  double* Gf = hm + DP;                 // [2][48] factored diagonal blocks (36 packed + 8 reciprocals) of this / the next step
   const double lambda = ctl->lambda, ks = -1.0 / (1.0 + lambda);
   // Every global input of the fill is requested UP FRONT, in one batch of independent loads: the first 16 x 256 entries of
   // (H_pose, H_schur[, H_marg]) -- the whole 64 x 64 system of an 8-keyframe window --, the diagonal, the right-hand sides,
@@ -3526,15 +3529,71 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
     }
   }
   for (int kb = 0; kb < D; kb += 8) {
-    __syncthreads();  // the trailing matrix is up to date and Gf holds this step's factored diagonal block
+    const double* Gc = Gf + 48 * ((kb >> 3) & 1);  // this step's factored diagonal block
+    double* Gn = Gf + 48 * (((kb >> 3) & 1) ^ 1);  // the next step's, written by the look-ahead warp meanwhile
+    __syncthreads();  // the trailing matrix is up to date and Gc is complete
     if (kb < 64) stamp(3 + kb / 8);
-    const int i = kb + tid;  // this thread's row (row D is the right-hand side)
-    if (i <= D) {
-      double g[36], inv[8], a[8];
+    const int m0 = kb + 8;
+    double g[36], inv[8], a[8];
+    if (warp_id == LOOKAHEAD_WARP) {
+      // The look-ahead warp runs AHEAD of the block step: it does the panel work of the next diagonal block's own rows
+      // (m0 .. m0 + 7; lanes 0 .. 7), hands them to the others (arrive on the panel barrier, no wait), then updates and
+      // factors the next diagonal block while the other warps are still in their panel phase and trailing update.
 #pragma unroll
-      for (int e = 0; e < 36; ++e) g[e] = Gf[e];
+      for (int e = 0; e < 36; ++e) g[e] = Gc[e];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) inv[j] = Gf[36 + j];
+      for (int j = 0; j < 8; ++j) inv[j] = Gc[36 + j];
+      const int i = m0 + lane_id;
+      if (lane_id < 8 && i <= D) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[c] = S[i * LD + kb + c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int c = j + 1; c < 8; ++c) a[c] -= a[j] * (g[c * (c + 1) / 2 + j] * inv[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          S[i * LD + kb + j] = a[j];
+          Lp[i * LPS + j] = a[j] * inv[j];
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+      asm volatile("bar.arrive 1, 256;" ::: "memory");
+      if (m0 < D) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {  // the 8 x 8 square over 32 lanes x 2; the upper triangle idles
+          const int r = (lane_id >> 3) + 4 * q, c = lane_id & 7;
+          if (c <= r) {
+            double acc = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += S[(m0 + r) * LD + kb + j] * Lp[(m0 + c) * LPS + j];
+            const double v = S[(m0 + r) * LD + m0 + c] - acc;
+            S[(m0 + r) * LD + m0 + c] = v;  // what the next step's panel threads read as their own row
+            Gn[r * (r + 1) / 2 + c] = v;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 36; ++e) g[e] = Gn[e];
+        ldlt8_packed(g, inv);
+        __syncwarp();
+        if (lane_id == 0) {
+#pragma unroll
+          for (int e = 0; e < 36; ++e) Gn[e] = g[e];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) Gn[36 + j] = inv[j];
+        }
+      }
+      continue;
+    }
+    const int i = kb + tid;  // this thread's row (row D is the right-hand side); rows m0 .. m0 + 7 are the look-ahead warp's
+    if (i <= D && (tid < 8 || tid >= 16)) {
+#pragma unroll
+      for (int e = 0; e < 36; ++e) g[e] = Gc[e];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) inv[j] = Gc[36 + j];
 #pragma unroll
       for (int c = 0; c < 8; ++c) a[c] = (i >= kb + c) ? S[i * LD + kb + c] : 0.0;
       // own row: the block's recurrence (for a row of the diagonal block the entries right of the diagonal are unused)
@@ -3556,42 +3615,14 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
       }
     }
     if (kb == 0) stamp(13);
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the panel is complete (the look-ahead warp only arrives)
     if (kb == 0) stamp(14);
-    const int m0 = kb + 8;
-    // look-ahead: the next diagonal block -- rows / columns m0 .. m0 + 7 -- leaves the trailing update
-    if (warp_id == LOOKAHEAD_WARP && m0 < D) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {  // the 8 x 8 square over 32 lanes x 2; the upper triangle idles
-        const int r = (lane_id >> 3) + 4 * q, c = lane_id & 7;
-        if (c <= r) {
-          double acc = 0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc += S[(m0 + r) * LD + kb + j] * Lp[(m0 + c) * LPS + j];
-          const double v = S[(m0 + r) * LD + m0 + c] - acc;
-          S[(m0 + r) * LD + m0 + c] = v;  // what the next step's panel threads read as their own row
-          Gf[r * (r + 1) / 2 + c] = v;
-        }
-      }
-      __syncwarp();
-      double g[36], inv[8];
-#pragma unroll
-      for (int e = 0; e < 36; ++e) g[e] = Gf[e];
-      ldlt8_packed(g, inv);
-      __syncwarp();
-      if (lane_id == 0) {
-#pragma unroll
-        for (int e = 0; e < 36; ++e) Gf[e] = g[e];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) Gf[36 + j] = inv[j];
-      }
-    }
     // trailing update of the lower triangle (and the rhs row): S[r][c] -= sum_j x_rj l_cj, rows below the next diagonal block.
     // 2 x 2 register tile per thread -- rows {r, r + 14} x columns {c, c + 16}, so that the 16 lanes of a half-warp keep
     // walking Lp and S with the conflict-free strides -- : a panel entry l_cj fetched from shared memory serves two rows
     // and a row's x_rj two columns; every element is still the same 8-term sum in the same order.
     const int own_lo = min(m0 + 8, D);  // rows [m0, own_lo) belong to the look-ahead warp, which takes no other share
-    for (int r = m0 + ty; r <= D && warp_id != LOOKAHEAD_WARP; r += 28) {
+    for (int r = m0 + ty; r <= D; r += 28) {
       const int r1 = r + 14;
       const bool has0 = r >= own_lo, has1 = r1 <= D;  // (r1 >= m0 + 14 is never a look-ahead row)
       double x0[8], x1[8];
@@ -3855,7 +3886,7 @@ void launch_lm_step(const LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, 
   const int D = 8 * N;
   const int n_sys = 2 * (D * D + D);
   ++g_launches;
-  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP + 48) * sizeof(double); };
+  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP + 96) * sizeof(double); };
   if (D <= 64) {
     k_lm_step<64><<<1, 256, smem_of(64), s>>>(ctl, opt, fr, fixed, N, rb.Hp, rb.bp, rb.Hs, rb.bs, Hmarg, bmarg, step_dev,
                                               peer_expected, rb.Hp, n_sys);
@@ -3876,7 +3907,7 @@ void launch_lm_solve(LmCtl* ctl, const LmOptionsDev* opt, FrameParams* fr, const
                      PairConst* pairs, PairAssemble* pasm, cudaStream_t s) {
   const int D = 8 * N;
   ++g_launches;
-  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP + 48) * sizeof(double); };
+  auto smem_of = [](int DP) { return (size_t)((DP + 1) * (DP + 1) + (DP + 1) * 9 + 4 * DP + 96) * sizeof(double); };
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_lm_solve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(64));
