@@ -3539,6 +3539,7 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
       // The look-ahead warp runs AHEAD of the block step: it does the panel work of the next diagonal block's own rows
       // (m0 .. m0 + 7; lanes 0 .. 7), hands them to the others (arrive on the panel barrier, no wait), then updates and
       // factors the next diagonal block while the other warps are still in their panel phase and trailing update.
+      // (keeping the factored block in this warp's registers across the steps instead of re-reading it measured slower)
 #pragma unroll
       for (int e = 0; e < 36; ++e) g[e] = Gc[e];
 #pragma unroll
@@ -3659,6 +3660,9 @@ __device__ __forceinline__ void lm_step_body(const LmCtl* ctl, const LmOptionsDe
   // redundantly in registers, then row i < kb subtracts the block's contribution -- one barrier per 8 unknowns
   for (int kb = D - 8; kb >= 0; kb -= 8) {
     __syncthreads();
+    // warps without a row above the block (and that do not publish the solution) skip the redundant 8 x 8 solve: its 44
+    // broadcast loads per warp were half of a block step's time on the CTA's one load / store unit
+    if ((tid & ~31) >= kb && tid >= 32) continue;
     double x[8];
 #pragma unroll
     for (int j = 7; j >= 0; --j) {
